@@ -1,0 +1,209 @@
+/* spatial_b200.h — C ABI of the B200 device layer behind SpatialSimulator::oneStep().
+ *
+ * This is the drop-in boundary for the hot path ("lower boundary").  The host side
+ * (SBML parsing, geometry / membrane classification, boundary-type setup, AST → reverse-polish
+ * streams) hands flattened arrays through these entry points; everything behind them is
+ * hand-written sm_100a CUDA.  No C++ / torch / libSBML types cross this boundary.
+ *
+ * All grids are COMPACT: nx*ny*nz volume cells, x fastest; compact cell (i,j,k) is the reference's
+ * doubled-grid point (2i,2j,2k) (reference SpatialSBML/spatialsimulator.cpp:354-358).
+ *
+ * Every function returns 0 on success and a negative sb2 error code otherwise;
+ * sb2_last_error() gives the message.  A handle is used from one host thread at a time.
+ * There is no CPU fallback: sb2_create fails if no CUDA device is usable.
+ */
+#ifndef SPATIAL_B200_H_
+#define SPATIAL_B200_H_
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define SB2_API __attribute__((visibility("default")))
+#else
+#define SB2_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB2_OK 0
+#define SB2_ERR_ARG (-1)
+#define SB2_ERR_CUDA (-2)
+#define SB2_ERR_STATE (-3)
+#define SB2_ERR_LIMIT (-4) /* model exceeds a documented device limit (species / depth / tokens) */
+
+#define SB2_MAX_SPECIES 8   /* staged (RK) volume species per simulator */
+#define SB2_MAX_GEOS 4      /* volume geometries that host staged species */
+#define SB2_MAX_FIELDS 16   /* read-only fields (coordinates, spatial parameters) */
+#define SB2_MAX_CONSTS 512
+#define SB2_MAX_TOKENS 1024
+#define SB2_MAX_DEPTH 8     /* expression stack depth after operand fusion */
+
+typedef struct sb2_sim sb2_sim;
+
+/* Grid description.  Replaces the Xdiv/Ydiv/Zdiv/deltaX.. members the reference computes in
+ * initFromModel (spatialsimulator.cpp:281-358) and setParameterInfo (setInfoFunction.cpp:296-342). */
+typedef struct {
+  int32_t nx, ny, nz; /* compact cells per axis (nz = 1 in 2-D) */
+  int32_t dim;        /* 2 or 3 */
+  double dx, dy, dz;  /* deltaX/Y/Z */
+  int32_t device;     /* CUDA device ordinal */
+  /* Slab sharding.  The slab axis is y in 2-D and z in 3-D.  The handle HOLDS
+   * ny (2-D) / nz (3-D) rows of a larger grid: the rows it owns, [own_lo, own_hi) in local
+   * indices, plus halo rows of the neighbouring slabs on either side, which the caller keeps up to
+   * date (sb2_species_view + its own exchange).  Only owned rows are computed.  row0 = index of
+   * local row 0 in the whole grid.  own_lo == own_hi == 0: the handle owns every row it holds. */
+  int32_t own_lo, own_hi, row0;
+} sb2_grid;
+
+/* Per-cell geometry flag byte (replaces GeometryInfo::isDomain + bType, mystruct.h:28-61):
+ * bit0 = isDomain==1, bits1..6 = isBofXp, isBofXm, isBofYp, isBofYm, isBofZp, isBofZm. */
+#define SB2_F_DOMAIN 0x01
+#define SB2_F_XP 0x02
+#define SB2_F_XM 0x04
+#define SB2_F_YP 0x08
+#define SB2_F_YM 0x10
+#define SB2_F_ZP 0x20
+#define SB2_F_ZM 0x40
+
+/* Reverse-polish token (replaces one slot of reversePolishInfo {varList, deltaList, constList,
+ * opfuncList}, mystruct.h:20-26, as filled by parseAST, astFunction.cpp:18-107). */
+typedef struct {
+  uint8_t kind;  /* SB2_TOK_* */
+  uint8_t op;    /* SB2_OP_* when kind == SB2_TOK_OP */
+  uint16_t slot; /* VAR: species id; FIELD: field id; CONST: constants-table slot */
+} sb2_token;
+
+#define SB2_TOK_OP 0
+#define SB2_TOK_VAR 1    /* staged species: u + rk[m]*dt*k_{m-1} (calcPDE.cpp:245-248) */
+#define SB2_TOK_FIELD 2  /* raw field value (calcPDE.cpp:249-251) */
+#define SB2_TOK_CONST 3  /* *constList[i] (calcPDE.cpp:253-255) */
+#define SB2_TOK_NOP 4    /* unresolved name: an all-zero slot, acts as a pop (astFunction.cpp:71-88) */
+
+/* Operator codes: our own enumeration of the cases of the interpreter switch at
+ * calcPDE.cpp:259-426 (never libSBML's ASTNodeType_t values). */
+enum {
+  SB2_OP_PLUS = 1, SB2_OP_MINUS, SB2_OP_TIMES, SB2_OP_DIVIDE, SB2_OP_POWER,
+  SB2_OP_LOG, /* log(x)/log(base) */
+  SB2_OP_AND, SB2_OP_OR, SB2_OP_XOR,
+  SB2_OP_EQ, SB2_OP_GEQ, SB2_OP_GT, SB2_OP_LEQ, SB2_OP_LT, SB2_OP_NEQ,
+  /* unary */
+  SB2_OP_ABS = 32, SB2_OP_ARCCOS, SB2_OP_ARCCOSH, SB2_OP_ARCCSC, SB2_OP_ARCSIN, SB2_OP_ARCTAN,
+  SB2_OP_COS, SB2_OP_COSH, SB2_OP_CSC, SB2_OP_EXP, SB2_OP_LN, SB2_OP_ROOT, SB2_OP_SIN,
+  SB2_OP_SINH, SB2_OP_TAN, SB2_OP_TANH, SB2_OP_NOT,
+  /* listed-but-empty cases: the reference only pops (calcPDE.cpp:297-302 etc.) */
+  SB2_OP_POP_ONLY = 64
+};
+
+/* Species reference of a reaction (replaces reactionInfo::spRefList / srStoichiometry /
+ * isVariable, mystruct.h:83-92).  species < 0: reference to a uniform species (skipped). */
+typedef struct {
+  int32_t species;
+  int32_t is_variable;
+  double stoichiometry;
+} sb2_ref;
+
+#define SB2_SRC_NONE 0
+#define SB2_SRC_CONST 1 /* uniform: constants-table slot */
+#define SB2_SRC_FIELD 2 /* field id */
+
+#define SB2_BC_NONE 0
+#define SB2_BC_NEUMANN 1
+#define SB2_BC_DIRICHLET 2
+
+/* sides, in the reference's boundaryIndex order (mystruct.h:12-14) */
+enum { SB2_XMAX = 0, SB2_XMIN, SB2_YMAX, SB2_YMIN, SB2_ZMAX, SB2_ZMIN };
+
+SB2_API int sb2_create(const sb2_grid* grid, sb2_sim** out);
+SB2_API void sb2_destroy(sb2_sim* sim);
+SB2_API const char* sb2_last_error(const sb2_sim* sim); /* sim may be NULL: last create error */
+
+/* Run all work of this handle on an externally owned CUDA stream (cudaStream_t as void*), e.g.
+ * the caller's current torch stream so that its CUDA events bracket the kernels. */
+SB2_API int sb2_set_stream(sb2_sim* sim, void* cuda_stream);
+
+/* Volume geometry that hosts staged species: nx*ny*nz flag bytes.  Returns geo id >= 0.
+ * Replaces GeometryInfo::isDomain/bType/domainIndex for one compartment
+ * (spatialsimulator.cpp:411-717, boundaryFunction.cpp:13-217). */
+SB2_API int sb2_add_geometry(sb2_sim* sim, const uint8_t* cell_flags);
+
+/* Staged species field (value[] + delta[4N], setInfoFunction.cpp:121-126).  Returns species id. */
+SB2_API int sb2_add_species(sb2_sim* sim, int geo, const double* init);
+/* Read-only field (coordinate x/y/z, spatial parameter, constant spatial species). Returns field id. */
+SB2_API int sb2_add_field(sb2_sim* sim, const double* values);
+
+SB2_API int sb2_set_constants(sb2_sim* sim, const double* table, int n);
+SB2_API int sb2_set_constant(sb2_sim* sim, int slot, double value); /* setParameter path (spatialsimulator.cpp:167-223) */
+
+/* kind: 0 = reaction (reactants n_reactants first, then products; calcPDE.cpp:432-446),
+ *       1 = rate rule (refs[0] += stoich*rate; calcPDE.cpp:447-449).
+ * geo: the domain whose cells the law is evaluated on (spatialsimulator.cpp:1381-1390). */
+SB2_API int sb2_add_reaction(sb2_sim* sim, int geo, int kind, const sb2_token* toks, int ntoks,
+                     const sb2_ref* refs, int nrefs, int n_reactants);
+
+/* Diffusion coefficient of a species along axis 0..2 (variableInfo::diffCInfo; calcPDE.cpp:486-511). */
+SB2_API int sb2_set_diffusion(sb2_sim* sim, int species, int axis, int src_kind, int src);
+/* Advection velocity along axis (variableInfo::adCInfo; calcPDE.cpp:564-869). */
+SB2_API int sb2_set_advection(sb2_sim* sim, int species, int axis, int src_kind, int src);
+/* Boundary condition of a species on one side (variableInfo::boundaryInfo; calcPDE.cpp:871-1034). */
+SB2_API int sb2_set_boundary(sb2_sim* sim, int species, int side, int bc_kind, int src_kind, int src);
+
+/* Membrane transport reaction (calcMemTransport, calcPDE.cpp:1036-1482).  The host passes the
+ * membrane points that take part (isDomain==1, off the frame), their axis (0/1/2 from the
+ * membrane bType), fabs(n_axis), and per species reference the compact index of the adjacent
+ * cells on either side (-1 when not in that species' domain) plus the cell two further out used
+ * for the 1.5/-0.5 extrapolation of volume operands (-1 when unavailable). */
+typedef struct {
+  int32_t axis;      /* 0 x, 1 y, 2 z */
+  double abs_normal; /* fabs(nuVec[index].n{x,y,z}) */
+} sb2_mem_point;
+SB2_API int sb2_add_mem_transport(sb2_sim* sim, const sb2_token* toks, int ntoks, const sb2_ref* refs, int nrefs,
+                          int n_reactants, const sb2_mem_point* pts, int npts,
+                          const int32_t* operand_cells /* [n VAR tokens][npts][2]: near, far compact cell or -1 */,
+                          const double* operand_values /* [n FIELD tokens][npts]: value at the membrane point */,
+                          const int32_t* target_cells /* [nrefs][npts][2]: plus side, minus side compact cell or -1 */);
+
+SB2_API int sb2_finalize(sb2_sim* sim);
+
+/* nsteps × oneStep (performStep + updateValues, spatialsimulator.cpp:1236-1544).  The `time`
+ * constant slot is set to (t_arg + i*t_incr)*dt for step i, reproducing sim_time = t*dt
+ * (spatialsimulator.cpp:1358).  time_slot < 0: model does not use time. */
+SB2_API int sb2_step(sb2_sim* sim, double t_arg, double t_incr, double dt, int nsteps, int time_slot);
+
+SB2_API int sb2_download_species(sb2_sim* sim, int species, double* out);      /* compact nx*ny*nz */
+SB2_API int sb2_upload_species(sb2_sim* sim, int species, const double* in);
+SB2_API int sb2_download_stage(sb2_sim* sim, int species, int m, double* out); /* k_m, for tests */
+SB2_API int sb2_upload_field(sb2_sim* sim, int field, const double* in);
+/* CIP-CSLR face point values of an advected species (the odd doubled-grid points between two cells
+ * along `axis`, calcPDE.cpp:588-603): faces[cell] = value at the face between cell and cell + e_axis. */
+SB2_API int sb2_upload_faces(sb2_sim* sim, int species, int axis, const double* in);
+SB2_API int sb2_download_faces(sb2_sim* sim, int species, int axis, double* out);
+
+/* checkStability.cpp:10-52 / 119-154: largest admissible dt (min-reduction over the domain). */
+SB2_API int sb2_min_dt(sb2_sim* sim, double dt, double* out);
+
+/* Device pointers for callers that exchange slab halos themselves (multi-GPU).
+ * which: 0 = u, 1..4 = k0..k3.  row_pitch / plane_pitch in doubles; first_cell = offset of
+ * compact cell (0,0,0) inside the allocation (one guard row / plane precedes it). */
+typedef struct {
+  void* ptr;
+  int64_t row_pitch, plane_pitch, first_cell, n_alloc;
+} sb2_field_view;
+SB2_API int sb2_species_view(sb2_sim* sim, int species, int which, sb2_field_view* out);
+
+/* Split-phase stepping for slab halo exchange.  phase: 0 = every owned row, 1 = only the owned
+ * rows / planes next to a neighbouring slab (what the neighbours need next), 2 = the other owned rows. */
+SB2_API int sb2_begin_step(sb2_sim* sim, double t_arg, double dt, int time_slot);
+SB2_API int sb2_stage(sb2_sim* sim, int m, int phase);
+SB2_API int sb2_end_step(sb2_sim* sim);
+
+/* Counters: kernels launched by this handle since creation. */
+SB2_API int64_t sb2_launch_count(const sb2_sim* sim);
+/* Human readable listing of the compiled device program (for tests / debugging). */
+SB2_API int sb2_program_text(sb2_sim* sim, char* buf, int buflen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPATIAL_B200_H_ */

@@ -1,0 +1,328 @@
+"""spatial_sbml_b200 — B200-native explicit reaction-diffusion-advection step of spatial-sbml.
+
+The product is the shared library ``libspatialb200.so`` (hand-written sm_100a CUDA kernels behind
+the C ABI of ``include/spatial_b200.h``, plus the host-side ``SpatialSimulator`` class with the
+reference's interface and its flat C binding ``include/spatial_sim_c.h``).  This module is the
+thin ctypes binding used by the tests and by ``bench.py``; it contains no numerics.
+
+There is no CPU fallback: if the library cannot be loaded an ImportError-like RuntimeError is
+raised, and stepping without a CUDA device raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libspatialb200.so")
+_lib = None
+
+# public entry points of include/spatial_b200.h and include/spatial_sim_c.h (checked by the tests
+# against the headers)
+SB2_OK = 0
+SB2_F_DOMAIN, SB2_F_XP, SB2_F_XM, SB2_F_YP, SB2_F_YM, SB2_F_ZP, SB2_F_ZM = 1, 2, 4, 8, 16, 32, 64
+SB2_TOK_OP, SB2_TOK_VAR, SB2_TOK_FIELD, SB2_TOK_CONST, SB2_TOK_NOP = 0, 1, 2, 3, 4
+SB2_SRC_NONE, SB2_SRC_CONST, SB2_SRC_FIELD = 0, 1, 2
+SB2_BC_NONE, SB2_BC_NEUMANN, SB2_BC_DIRICHLET = 0, 1, 2
+OPS = dict(PLUS=1, MINUS=2, TIMES=3, DIVIDE=4, POWER=5, LOG=6, AND=7, OR=8, XOR=9, EQ=10, GEQ=11, GT=12,
+           LEQ=13, LT=14, NEQ=15, ABS=32, ARCCOS=33, ARCCOSH=34, ARCCSC=35, ARCSIN=36, ARCTAN=37, COS=38,
+           COSH=39, CSC=40, EXP=41, LN=42, ROOT=43, SIN=44, SINH=45, TAN=46, TANH=47, NOT=48, POP_ONLY=64)
+
+
+class Grid(C.Structure):
+    _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32), ("dim", C.c_int32),
+                ("dx", C.c_double), ("dy", C.c_double), ("dz", C.c_double), ("device", C.c_int32),
+                ("own_lo", C.c_int32), ("own_hi", C.c_int32), ("row0", C.c_int32)]
+
+
+class Token(C.Structure):
+    _fields_ = [("kind", C.c_uint8), ("op", C.c_uint8), ("slot", C.c_uint16)]
+
+
+class Ref(C.Structure):
+    _fields_ = [("species", C.c_int32), ("is_variable", C.c_int32), ("stoichiometry", C.c_double)]
+
+
+class MemPoint(C.Structure):
+    _fields_ = [("axis", C.c_int32), ("abs_normal", C.c_double)]
+
+
+class FieldView(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("row_pitch", C.c_int64), ("plane_pitch", C.c_int64),
+                ("first_cell", C.c_int64), ("n_alloc", C.c_int64)]
+
+
+def _proto(lib):
+    vp, ci, cd, cs = C.c_void_p, C.c_int, C.c_double, C.c_char_p
+    dp = C.POINTER(C.c_double)
+    P = {
+        # --- include/spatial_b200.h
+        "sb2_create": (ci, [C.POINTER(Grid), C.POINTER(vp)]),
+        "sb2_destroy": (None, [vp]),
+        "sb2_last_error": (cs, [vp]),
+        "sb2_set_stream": (ci, [vp, vp]),
+        "sb2_add_geometry": (ci, [vp, C.POINTER(C.c_uint8)]),
+        "sb2_add_species": (ci, [vp, ci, dp]),
+        "sb2_add_field": (ci, [vp, dp]),
+        "sb2_set_constants": (ci, [vp, dp, ci]),
+        "sb2_set_constant": (ci, [vp, ci, cd]),
+        "sb2_add_reaction": (ci, [vp, ci, ci, C.POINTER(Token), ci, C.POINTER(Ref), ci, ci]),
+        "sb2_set_diffusion": (ci, [vp, ci, ci, ci, ci]),
+        "sb2_set_advection": (ci, [vp, ci, ci, ci, ci]),
+        "sb2_set_boundary": (ci, [vp, ci, ci, ci, ci, ci]),
+        "sb2_add_mem_transport": (ci, [vp, C.POINTER(Token), ci, C.POINTER(Ref), ci, ci, C.POINTER(MemPoint), ci,
+                                       C.POINTER(C.c_int32), dp, C.POINTER(C.c_int32)]),
+        "sb2_finalize": (ci, [vp]),
+        "sb2_step": (ci, [vp, cd, cd, cd, ci, ci]),
+        "sb2_download_species": (ci, [vp, ci, dp]),
+        "sb2_upload_species": (ci, [vp, ci, dp]),
+        "sb2_download_stage": (ci, [vp, ci, ci, dp]),
+        "sb2_upload_field": (ci, [vp, ci, dp]),
+        "sb2_upload_faces": (ci, [vp, ci, ci, dp]),
+        "sb2_download_faces": (ci, [vp, ci, ci, dp]),
+        "sb2_min_dt": (ci, [vp, cd, dp]),
+        "sb2_species_view": (ci, [vp, ci, ci, C.POINTER(FieldView)]),
+        "sb2_begin_step": (ci, [vp, cd, cd, ci]),
+        "sb2_stage": (ci, [vp, ci, ci]),
+        "sb2_end_step": (ci, [vp]),
+        "sb2_launch_count": (C.c_int64, [vp]),
+        "sb2_program_text": (ci, [vp, C.c_char_p, ci]),
+        # --- include/spatial_sim_c.h
+        "ssb_new": (vp, []),
+        "ssb_free": (None, [vp]),
+        "ssb_last_error": (cs, [vp]),
+        "ssb_is_initialized": (ci, [vp]),
+        "ssb_set_device": (None, [vp, ci]),
+        "ssb_set_host_only": (None, [vp, ci]),
+        "ssb_set_slab": (None, [vp, ci, ci]),
+        "ssb_set_cuda_stream": (None, [vp, vp]),
+        "ssb_init_from_file": (ci, [vp, cs, ci, ci, ci]),
+        "ssb_init_from_string": (ci, [vp, cs, ci, ci, ci]),
+        "ssb_one_step": (cd, [vp, cd, cd]),
+        "ssb_run_steps": (ci, [vp, cd, cd, ci]),
+        "ssb_run": (ci, [vp, cd, cd]),
+        "ssb_set_parameter": (None, [vp, cs, cd]),
+        "ssb_set_parameter_uniformly": (None, [vp, cs, cd]),
+        "ssb_get_index_for_position": (ci, [vp, cd, cd]),
+        "ssb_get_variable_length": (ci, [vp]),
+        "ssb_get_geometry_length": (ci, [vp]),
+        "ssb_get_xdim": (ci, [vp]),
+        "ssb_get_ydim": (ci, [vp]),
+        "ssb_get_zdim": (ci, [vp]),
+        "ssb_get_variable_at": (cd, [vp, cs, ci, ci, ci]),
+        "ssb_flip_volume_order": (None, [vp]),
+        "ssb_get_variable": (dp, [vp, cs, C.POINTER(ci)]),
+        "ssb_get_geometry": (C.POINTER(ci), [vp, cs, C.POINTER(ci)]),
+        "ssb_get_boundary_type": (C.POINTER(C.c_uint8), [vp, cs, C.POINTER(ci)]),
+        "ssb_get_boundary": (C.POINTER(ci), [vp, cs, C.POINTER(ci)]),
+        "ssb_get_x": (dp, [vp, C.POINTER(ci)]),
+        "ssb_get_y": (dp, [vp, C.POINTER(ci)]),
+        "ssb_get_z": (dp, [vp, C.POINTER(ci)]),
+        "ssb_get_variable_compact": (ci, [vp, cs, dp, C.c_size_t]),
+        "ssb_set_variable_compact": (ci, [vp, cs, dp, C.c_size_t]),
+        "ssb_get_stable_time_step": (cd, [vp, cd]),
+        "ssb_get_num_domain_cells": (C.c_long, [vp]),
+        "ssb_get_num_staged_species": (ci, [vp]),
+        "ssb_get_device_launch_count": (C.c_long, [vp]),
+        "ssb_get_device_handle": (vp, [vp]),
+        "ssb_get_device_program_text": (ci, [vp, C.c_char_p, ci]),
+        "ssb_get_setup_text": (ci, [vp, cs, C.c_char_p, ci]),
+    }
+    for name, (res, args) in P.items():
+        f = getattr(lib, name)  # AttributeError if the library does not export what the headers declare
+        f.restype = res
+        f.argtypes = args
+    return P
+
+
+def load_library():
+    """Load libspatialb200.so (built in-tree by build.sh / __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("%s is missing: run ./build.sh (there is no Python / CPU fallback)" % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        lib._prototypes = _proto(lib)
+        _lib = lib
+    return _lib
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class SpatialSimulator(object):
+    """Python face of the SpatialSimulator class (same method names as the reference's
+    SpatialSBML/spatialsimulator.h:49-294, snake_case aliases not provided on purpose)."""
+
+    def __init__(self, device=0, host_only=False, stream=None, slab=None):
+        self._lib = load_library()
+        self._h = self._lib.ssb_new()
+        self._lib.ssb_set_device(self._h, int(device))
+        if host_only:
+            self._lib.ssb_set_host_only(self._h, 1)
+        if slab is not None:
+            self._lib.ssb_set_slab(self._h, int(slab[0]), int(slab[1]))
+        self._stream = stream
+
+    def close(self):
+        if self._h:
+            self._lib.ssb_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _err(self):
+        return self._lib.ssb_last_error(self._h).decode()
+
+    def _after_init(self, rc):
+        if rc != 0:
+            raise RuntimeError("SpatialSimulator init failed: " + self._err())
+        if self._stream is not None:
+            self._lib.ssb_set_cuda_stream(self._h, C.c_void_p(self._stream))
+
+    def initFromFile(self, path, xdim, ydim, zdim=1):
+        self._after_init(self._lib.ssb_init_from_file(self._h, os.fsencode(path), xdim, ydim, zdim))
+
+    def initFromString(self, sbml, xdim, ydim, zdim=1):
+        self._after_init(self._lib.ssb_init_from_string(self._h, sbml.encode(), xdim, ydim, zdim))
+
+    def oneStep(self, initial_time, step):
+        r = self._lib.ssb_one_step(self._h, float(initial_time), float(step))
+        if r != r:
+            raise RuntimeError("oneStep failed: " + self._err())
+        return r
+
+    def runSteps(self, first_step_index, step, nsteps):
+        if self._lib.ssb_run_steps(self._h, float(first_step_index), float(step), int(nsteps)) != 0:
+            raise RuntimeError("runSteps failed: " + self._err())
+
+    def run(self, end_time, step):
+        if self._lib.ssb_run(self._h, float(end_time), float(step)) != 0:
+            raise RuntimeError("run failed: " + self._err())
+
+    def setParameter(self, id, value):
+        self._lib.ssb_set_parameter(self._h, id.encode(), float(value))
+
+    def setParameterUniformly(self, id, value):
+        self._lib.ssb_set_parameter_uniformly(self._h, id.encode(), float(value))
+
+    def getIndexForPosition(self, x, y):
+        return self._lib.ssb_get_index_for_position(self._h, float(x), float(y))
+
+    def getVariableLength(self):
+        return self._lib.ssb_get_variable_length(self._h)
+
+    def getGeometryLength(self):
+        return self._lib.ssb_get_geometry_length(self._h)
+
+    def getXDim(self):
+        return self._lib.ssb_get_xdim(self._h)
+
+    def getYDim(self):
+        return self._lib.ssb_get_ydim(self._h)
+
+    def getZDim(self):
+        return self._lib.ssb_get_zdim(self._h)
+
+    def getVariableAt(self, id, x, y, z=0):
+        return self._lib.ssb_get_variable_at(self._h, id.encode(), int(x), int(y), int(z))
+
+    def flipVolumeOrder(self):
+        self._lib.ssb_flip_volume_order(self._h)
+
+    def _borrow(self, fn, key, dtype, width=1):
+        n = C.c_int(0)
+        p = fn(self._h, key.encode(), C.byref(n)) if key is not None else fn(self._h, C.byref(n))
+        if not p:
+            return None, n.value
+        return p, n.value
+
+    def getVariable(self, id):
+        """Live doubled-grid view (numpy array over the library's buffer; length+1 entries are backed)."""
+        p, n = self._borrow(self._lib.ssb_get_variable, id, np.float64)
+        if p is None:
+            return None
+        total = self.getGeometryLength() if n > 0 and n + 1 == self.getGeometryLength() else n
+        return np.ctypeslib.as_array(p, shape=(total,))
+
+    def getGeometry(self, compartment):
+        p, n = self._borrow(self._lib.ssb_get_geometry, compartment, np.int32)
+        return None if p is None else np.ctypeslib.as_array(p, shape=(n,))
+
+    def getBoundary(self, compartment):
+        p, n = self._borrow(self._lib.ssb_get_boundary, compartment, np.int32)
+        return None if p is None else np.ctypeslib.as_array(p, shape=(n,))
+
+    def getBoundaryType(self, compartment):
+        p, n = self._borrow(self._lib.ssb_get_boundary_type, compartment, np.uint8)
+        return None if p is None else np.ctypeslib.as_array(p, shape=(n, 6))
+
+    def getX(self):
+        p, n = self._borrow(self._lib.ssb_get_x, None, np.float64)
+        return None if p is None else np.ctypeslib.as_array(p, shape=(n + 1,))
+
+    def getY(self):
+        p, n = self._borrow(self._lib.ssb_get_y, None, np.float64)
+        return None if p is None else np.ctypeslib.as_array(p, shape=(n + 1,))
+
+    def getZ(self):
+        p, n = self._borrow(self._lib.ssb_get_z, None, np.float64)
+        return None if p is None else np.ctypeslib.as_array(p, shape=(n + 1,))
+
+    # ---- additions ----
+    def localShape(self):
+        """(nz, ny, nx) of the compact arrays held by this simulator (the slab incl. halo when sharded)."""
+        txt = self.getSetupText("summary").split("\n")[0].split()
+        return int(txt[3]), int(txt[2]), int(txt[1])
+
+    def getVariableCompact(self, id, out=None):
+        nz, ny, nx = self.localShape()
+        if out is None:
+            out = np.empty((nz, ny, nx), dtype=np.float64)
+        if self._lib.ssb_get_variable_compact(self._h, id.encode(), _dptr(out), out.size) != 0:
+            raise KeyError("no spatial variable %r" % id)
+        return out
+
+    def setVariableCompact(self, id, values):
+        a = np.ascontiguousarray(values, dtype=np.float64)
+        if self._lib.ssb_set_variable_compact(self._h, id.encode(), _dptr(a), a.size) != 0:
+            raise KeyError("cannot set variable %r" % id)
+
+    def getStableTimeStep(self, dt):
+        r = self._lib.ssb_get_stable_time_step(self._h, float(dt))
+        if r != r:
+            raise RuntimeError("getStableTimeStep failed: " + self._err())
+        return r
+
+    def getNumDomainCells(self):
+        return self._lib.ssb_get_num_domain_cells(self._h)
+
+    def getNumStagedSpecies(self):
+        return self._lib.ssb_get_num_staged_species(self._h)
+
+    def getDeviceLaunchCount(self):
+        return self._lib.ssb_get_device_launch_count(self._h)
+
+    def getDeviceHandle(self):
+        return self._lib.ssb_get_device_handle(self._h)
+
+    def setCudaStream(self, stream):
+        self._stream = stream
+        self._lib.ssb_set_cuda_stream(self._h, C.c_void_p(stream))
+
+    def _text(self, fn, *args):
+        n = fn(self._h, *args, None, 0)
+        buf = C.create_string_buffer(n + 1)
+        fn(self._h, *args, buf, n + 1)
+        return buf.value.decode()
+
+    def getDeviceProgramText(self):
+        return self._text(self._lib.ssb_get_device_program_text)
+
+    def getSetupText(self, what):
+        return self._text(self._lib.ssb_get_setup_text, what.encode())

@@ -1,0 +1,657 @@
+// aux_kernels.cu — kernels around the fused stage kernel (sm_100a): boundary-condition lists,
+// CIP-CSLR advection, membrane transport, min-dt reduction.  This translation unit is compiled
+// with -fmad=false so that plain C expressions keep the reference's operation order and rounding.
+#include "sb2_aux.h"
+#include "sb2_ops.cuh"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+namespace {
+
+template <typename T>
+cudaError_t to_device(T** dptr, const std::vector<T>& h, cudaStream_t stream) {
+  *dptr = NULL;
+  if (h.empty()) return cudaSuccess;
+  cudaError_t e = cudaMalloc((void**)dptr, sizeof(T) * h.size());
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpyAsync(*dptr, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess) return e;
+  return cudaStreamSynchronize(stream);
+}
+
+}  // namespace
+
+// =============================================================================================
+// boundary conditions
+// =============================================================================================
+namespace {
+
+struct BcEntry {
+  int species;
+  int64_t cell, valcell;
+  int side;
+  int seq;
+};
+
+struct BcKernelArgs {
+  int n_groups;
+  const int32_t* group_start;
+  const int32_t* group_species;
+  const int64_t* entry_cell;
+  const int64_t* entry_valcell;
+  const int32_t* entry_side;
+  int kind[SB2_MAX_SPECIES][6];
+  int skind[SB2_MAX_SPECIES][6];
+  int src[SB2_MAX_SPECIES][6];
+  double cval[SB2_MAX_SPECIES][6];
+  double delta[3];
+  double* k[SB2_MAX_SPECIES];
+  double* u[SB2_MAX_SPECIES];
+  const double* fields[SB2_MAX_FIELDS];
+  int do_neumann;
+};
+
+__global__ void __launch_bounds__(128) bc_kernel(const __grid_constant__ BcKernelArgs A) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= A.n_groups) return;
+  const int s = A.group_species[g];
+  for (int e = A.group_start[g]; e < A.group_start[g + 1]; ++e) {
+    const int side = A.entry_side[e];
+    const int kind = A.kind[s][side];
+    const double v = (A.skind[s][side] == SB2_SRC_FIELD) ? A.fields[A.src[s][side]][A.entry_valcell[e]] : A.cval[s][side];
+    const int64_t c = A.entry_cell[e];
+    if (kind == SB2_BC_NEUMANN) {
+      // delta += -2.0 * (-bc) / deltaX   (calcPDE.cpp:994)
+      if (A.do_neumann) A.k[s][c] = A.k[s][c] + (-2.0 * (-v)) / A.delta[side >> 1];
+    } else if (kind == SB2_BC_DIRICHLET) {
+      A.u[s][c] = v;  // calcPDE.cpp:995
+    }
+  }
+}
+
+}  // namespace
+
+int sb2_build_boundary_lists(const sb2_grid& g, int64_t P, int64_t PL, int64_t first,
+                             const std::vector<std::vector<uint8_t> >& h_flags, const std::vector<Sb2BcSpecies>& bcs,
+                             const double* consts, cudaStream_t stream, Sb2BoundaryLists& out, std::string& err) {
+  (void)consts;
+  memset(&out, 0, sizeof(out));
+  out.delta[0] = g.dx; out.delta[1] = g.dy; out.delta[2] = g.dz;
+  std::vector<BcEntry> entries;
+  const int nx = g.nx, ny = g.ny, nz = g.nz;
+  auto pad = [&](int i, int j, int k) { return first + (int64_t)k * PL + (int64_t)j * P + i; };
+  // slab: only owned rows / planes receive entries; the reference's row-0 quirks refer to the whole grid
+  const bool whole = g.own_hi <= g.own_lo;
+  const int n_held = g.dim == 3 ? nz : ny;
+  const int own_lo = whole ? 0 : g.own_lo, own_hi = whole ? n_held : g.own_hi;
+  const int gj0 = g.dim == 2 ? g.row0 : 0, gk0 = g.dim == 3 ? g.row0 : 0;
+  for (size_t s = 0; s < bcs.size(); ++s) {
+    for (int k = 0; k < 6; ++k) { out.kind[s][k] = bcs[s].kind[k]; out.skind[s][k] = bcs[s].skind[k]; out.src[s][k] = bcs[s].src[k]; }
+    if (!bcs[s].has_bc) continue;
+    const std::vector<uint8_t>& fl = h_flags[bcs[s].geo];
+    auto dom = [&](int i, int j, int k) -> bool {
+      if (i < 0 || j < 0 || k < 0 || i >= nx || j >= ny || k >= nz) return false;
+      return fl[((int64_t)k * ny + j) * nx + i] & SB2_F_DOMAIN;
+    };
+    int seq = 0;
+    auto add = [&](int side, int ai, int aj, int ak, int vi, int vj, int vk) {
+      if (bcs[s].kind[side] == SB2_BC_NONE) return;
+      const int slabc = g.dim == 3 ? ak : aj;
+      if (slabc < own_lo || slabc >= own_hi) return;
+      BcEntry e;
+      e.species = (int)s; e.cell = pad(ai, aj, ak); e.valcell = pad(vi, vj, vk); e.side = side; e.seq = seq++;
+      entries.push_back(e);
+    };
+    // The loop of calcPDE.cpp:958-1033 over every even point c, restated on compact coordinates.
+    // Flat-index wrap-around of the reference (X±2, X±4 leaving the row) always lands on an odd
+    // row / plane, which no volume domain contains, so it reads as "not in domain" (SURVEY §8 a8').
+    for (int k = 0; k < nz; ++k)
+      for (int j = 0; j < ny; ++j)
+        for (int i = 0; i < nx; ++i) {
+          // X: p = c+1 gets the Xmax condition when its outer neighbour is outside
+          if (dom(i + 1, j, k) && !dom(i + 2, j, k)) add(SB2_XMAX, i + 1, j, k, i + 1, j, k);
+          // Xm is gated by desc.Y.mOutside (calcPDE.cpp:997): skipped on row Y=0 of plane Z=0
+          if (!(k + gk0 == 0 && j + gj0 == 0) && dom(i - 1, j, k) && !dom(i - 2, j, k)) add(SB2_XMIN, i - 1, j, k, i - 1, j, k);
+          if (g.dim >= 2) {
+            if (dom(i, j + 1, k) && !dom(i, j + 2, k)) add(SB2_YMAX, i, j + 1, k, i, j + 1, k);
+            if (dom(i, j - 1, k) && !dom(i, j - 2, k)) add(SB2_YMIN, i, j - 1, k, i, j - 1, k);
+          }
+          if (g.dim >= 3) {
+            // coordinateDesc::set stores Z.p = xp and Z.m = xm (mystruct.h:186-187): the Z tests look
+            // at the X neighbour of c but at the Z±4 point for "outside"
+            if (dom(i + 1, j, k) && !dom(i, j, k + 2)) add(SB2_ZMAX, i + 1, j, k, i + 1, j, k);
+            if (!(i == 0 && j == 0 && k + gk0 == 0) && dom(i - 1, j, k) && !dom(i, j, k - 2)) {
+              if (bcs[s].kind[SB2_ZMIN] == SB2_BC_DIRICHLET) {
+                // value[Z.mm] = bc (calcPDE.cpp:1028); out of the array when k < 2 → skipped
+                if (k - 2 >= 0) add(SB2_ZMIN, i, j, k - 2, i - 1, j, k);
+              } else {
+                add(SB2_ZMIN, i - 1, j, k, i - 1, j, k);
+              }
+            }
+          }
+        }
+  }
+  std::stable_sort(entries.begin(), entries.end(), [](const BcEntry& a, const BcEntry& b) {
+    if (a.species != b.species) return a.species < b.species;
+    return a.cell < b.cell;
+  });
+  std::vector<int32_t> gstart, gspecies, eside;
+  std::vector<int64_t> ecell, evalcell;
+  for (size_t i = 0; i < entries.size(); ++i) {
+    if (i == 0 || entries[i].species != entries[i - 1].species || entries[i].cell != entries[i - 1].cell) {
+      gstart.push_back((int32_t)i);
+      gspecies.push_back(entries[i].species);
+    }
+    ecell.push_back(entries[i].cell);
+    evalcell.push_back(entries[i].valcell);
+    eside.push_back(entries[i].side);
+    const int kind = bcs[entries[i].species].kind[entries[i].side];
+    if (kind == SB2_BC_NEUMANN) out.n_neumann++;
+    if (kind == SB2_BC_DIRICHLET) out.n_dirichlet++;
+  }
+  gstart.push_back((int32_t)entries.size());
+  out.n_groups = (int)gspecies.size();
+  out.n_entries = (int)entries.size();
+  cudaError_t e;
+  if ((e = to_device(&out.d_group_start, gstart, stream)) != cudaSuccess ||
+      (e = to_device(&out.d_group_species, gspecies, stream)) != cudaSuccess ||
+      (e = to_device(&out.d_entry_cell, ecell, stream)) != cudaSuccess ||
+      (e = to_device(&out.d_entry_valcell, evalcell, stream)) != cudaSuccess ||
+      (e = to_device(&out.d_entry_side, eside, stream)) != cudaSuccess) {
+    err = std::string("boundary lists: ") + cudaGetErrorString(e);
+    return SB2_ERR_CUDA;
+  }
+  return SB2_OK;
+}
+
+void sb2_free_boundary_lists(Sb2BoundaryLists& l) {
+  cudaFree(l.d_group_start); cudaFree(l.d_group_species); cudaFree(l.d_entry_cell);
+  cudaFree(l.d_entry_valcell); cudaFree(l.d_entry_side);
+  memset(&l, 0, sizeof(l));
+}
+
+bool sb2_neumann_active(const Sb2BoundaryLists& l, int nspecies, const double* consts) {
+  if (l.n_neumann == 0) return false;
+  for (int s = 0; s < nspecies; ++s)
+    for (int k = 0; k < 6; ++k) {
+      if (l.kind[s][k] != SB2_BC_NEUMANN) continue;
+      if (l.skind[s][k] == SB2_SRC_FIELD) return true;
+      if (l.skind[s][k] == SB2_SRC_CONST && consts[l.src[s][k]] != 0.0) return true;
+    }
+  return false;
+}
+
+cudaError_t sb2_apply_boundary(const Sb2BoundaryLists& l, double* const* k, double* const* u, const double* consts,
+                               double* const* fields, bool do_neumann, cudaStream_t stream, int* launches) {
+  if (l.n_groups == 0) return cudaSuccess;
+  if (!do_neumann && l.n_dirichlet == 0) return cudaSuccess;
+  BcKernelArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_groups = l.n_groups;
+  a.group_start = l.d_group_start; a.group_species = l.d_group_species;
+  a.entry_cell = l.d_entry_cell; a.entry_valcell = l.d_entry_valcell; a.entry_side = l.d_entry_side;
+  for (int s = 0; s < SB2_MAX_SPECIES; ++s) {
+    for (int j = 0; j < 6; ++j) {
+      a.kind[s][j] = l.kind[s][j]; a.skind[s][j] = l.skind[s][j]; a.src[s][j] = l.src[s][j];
+      a.cval[s][j] = (l.skind[s][j] == SB2_SRC_CONST) ? consts[l.src[s][j]] : 0.0;
+    }
+  }
+  for (int d = 0; d < 3; ++d) a.delta[d] = l.delta[d];
+  // only species that own groups are dereferenced
+  for (int s = 0; s < SB2_MAX_SPECIES; ++s) { a.k[s] = NULL; a.u[s] = NULL; }
+  // callers pass arrays sized to the species count; copy what the kinds table says exists
+  for (int s = 0; s < SB2_MAX_SPECIES; ++s) {
+    bool used = false;
+    for (int j = 0; j < 6; ++j) if (l.kind[s][j] != SB2_BC_NONE) used = true;
+    if (used) { a.k[s] = k[s]; a.u[s] = u[s]; }
+  }
+  for (int f = 0; f < SB2_MAX_FIELDS; ++f) a.fields[f] = NULL;
+  for (int s = 0; s < SB2_MAX_SPECIES; ++s)
+    for (int j = 0; j < 6; ++j)
+      if (l.kind[s][j] != SB2_BC_NONE && l.skind[s][j] == SB2_SRC_FIELD) a.fields[l.src[s][j]] = fields[l.src[s][j]];
+  a.do_neumann = do_neumann ? 1 : 0;
+  if (launches) ++*launches;
+  bc_kernel<<<(l.n_groups + 127) / 128, 128, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+// =============================================================================================
+// CIP-CSLR advection
+// =============================================================================================
+namespace {
+
+__device__ __forceinline__ bool cip_dom(const Sb2CipArgs& A, int64_t idx, int c, int n, int off, int64_t st) {
+  const int cc = c + off;
+  if (cc < 0 || cc >= n) return false;
+  return A.flags[idx + off * st] & SB2_F_DOMAIN;
+}
+
+// flux loop of one direction pass (calcPDE.cpp:581-651 for X; Y and Z passes are identical up to the axis)
+__global__ void __launch_bounds__(256) cip_flux_kernel(const __grid_constant__ Sb2CipArgs A, int axis) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y, k = blockIdx.z;
+  if (i >= A.nx) return;
+  const int64_t idx = A.first + (int64_t)k * A.PL + (int64_t)j * A.P + i;
+  const uint32_t f = A.flags[idx];
+  if (!(f & SB2_F_DOMAIN)) return;
+  const int c = axis == 0 ? i : axis == 1 ? j : k;
+  const int n = axis == 0 ? A.nx : axis == 1 ? A.ny : A.nz;
+  const int64_t st = axis == 0 ? 1 : axis == 1 ? A.P : A.PL;
+  const double* val = A.u;
+  const double* face = A.faces[axis];
+  const double delta = A.delta[axis];
+  const double dt = A.dt;
+
+  const bool d_p1 = cip_dom(A, idx, c, n, 1, st), d_p2 = cip_dom(A, idx, c, n, 2, st);
+  const bool d_m1 = cip_dom(A, idx, c, n, -1, st), d_m2 = cip_dom(A, idx, c, n, -2, st);
+  const double v0 = val[idx];
+  // index collapsing of calcPDE.cpp:596-611
+  const double vp3 = d_p2 ? face[idx + st] : (d_p1 ? val[idx + st] : v0);
+  const double vm3 = d_m2 ? face[idx - 2 * st] : (d_m1 ? val[idx - st] : v0);
+  const double vp1 = d_p1 ? face[idx] : v0;
+  const double vp2 = d_p1 ? val[idx + st] : v0;
+  const double vm1 = d_m1 ? face[idx - st] : v0;
+  const double vm2 = d_m1 ? val[idx - st] : v0;
+
+  const double ux = A.aconst[axis];
+  const double Dx = -copysign(1.0, ux) * delta;
+  const double xi = ux * dt;
+  const bool bofp = f & (SB2_F_XP << (2 * axis));
+  const bool bofm = f & (SB2_F_XM << (2 * axis));
+  double g_in = 0.0, g_out = 0.0;
+  if (!bofp) {
+    double a_i, b_i, beta_i;
+    if (ux >= 0) {
+      a_i = vp1;
+      beta_i = ((fabs(vp1 - v0) + DBL_EPSILON) / (fabs(v0 - vm1) + DBL_EPSILON) - 1.0) / Dx;
+      b_i = ((1.0 + beta_i * Dx) * v0 - vp1) / Dx;
+    } else {
+      a_i = vp1;
+      beta_i = ((fabs(vp1 - vp2) + DBL_EPSILON) / (fabs(vp2 - vp3) + DBL_EPSILON) - 1.0) / Dx;
+      b_i = ((1.0 + beta_i * Dx) * vp2 - vp1) / Dx;
+    }
+    const double mxi = -xi;
+    const double den = 1.0 + beta_i * mxi;
+    const double newface = (a_i + 2 * b_i * mxi + beta_i * b_i * (mxi * mxi)) / (den * den) - vp1;
+    if (d_p1) A.tmp_face[idx] = newface;
+    const double G = (-a_i * xi + b_i * (xi * xi)) / (-1.0 + beta_i * xi);
+    if (ux >= 0) g_out = G; else g_in = -G;
+  }
+  if (!bofm) {
+    double a_i2, b_i2, beta_i2;
+    if (ux >= 0) {
+      a_i2 = vm1;
+      beta_i2 = ((fabs(vm1 - vm2) + DBL_EPSILON) / (fabs(vm2 - vm3) + DBL_EPSILON) - 1.0) / Dx;
+      b_i2 = ((1.0 + beta_i2 * Dx) * vm2 - vm1) / Dx;
+      g_in = (-a_i2 * xi + b_i2 * (xi * xi)) / (-1.0 + beta_i2 * xi);
+    } else {
+      a_i2 = vm1;
+      beta_i2 = ((fabs(vm1 - v0) + DBL_EPSILON) / (fabs(v0 - vp1) + DBL_EPSILON) - 1.0) / Dx;
+      b_i2 = ((1.0 + beta_i2 * Dx) * v0 - vm1) / Dx;
+      g_out = -(-a_i2 * xi + b_i2 * (xi * xi)) / (-1.0 + beta_i2 * xi);
+    }
+  }
+  A.tmp_cell[idx] = (g_in - g_out) / delta;
+}
+
+// update sweep (calcPDE.cpp:654-673): add the increments and advance the faces of the other axes
+__global__ void __launch_bounds__(256) cip_update_kernel(const __grid_constant__ Sb2CipArgs A, int axis) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y, k = blockIdx.z;
+  if (i >= A.nx) return;
+  const int64_t idx = A.first + (int64_t)k * A.PL + (int64_t)j * A.P + i;
+  const double dc = A.tmp_cell[idx];
+  A.u[idx] = A.u[idx] + dc;
+  A.faces[axis][idx] = A.faces[axis][idx] + A.tmp_face[idx];
+  const uint32_t f = A.flags[idx];
+  if (!(f & SB2_F_DOMAIN)) return;
+  for (int b = 0; b < A.dim; ++b) {
+    if (b == axis) continue;
+    if (f & (SB2_F_XP << (2 * b))) continue;
+    const int c = b == 0 ? i : b == 1 ? j : k;
+    const int n = b == 0 ? A.nx : b == 1 ? A.ny : A.nz;
+    if (c + 1 >= n) continue;
+    const int64_t st = b == 0 ? 1 : b == 1 ? A.P : A.PL;
+    A.faces[b][idx] = A.faces[b][idx] + (A.tmp_cell[idx + st] + dc) / 2.0;
+  }
+}
+
+}  // namespace
+
+cudaError_t sb2_launch_cip(const Sb2CipArgs& a, cudaStream_t stream, int* launches) {
+  dim3 block(256), grid((a.nx + 255) / 256, a.ny, a.nz);
+  for (int axis = 0; axis < a.dim; ++axis) {
+    // the reference runs the update sweep of a pass even without a velocity along it; with zero
+    // increments that sweep changes nothing, so the whole pass is skipped here
+    if (a.akind[axis] == SB2_SRC_NONE) continue;
+    cudaError_t e = cudaMemsetAsync(a.tmp_cell, 0, sizeof(double) * a.nalloc, stream);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(a.tmp_face, 0, sizeof(double) * a.nalloc, stream);
+    if (e != cudaSuccess) return e;
+    if (launches) *launches += 2;
+    cip_flux_kernel<<<grid, block, 0, stream>>>(a, axis);
+    cip_update_kernel<<<grid, block, 0, stream>>>(a, axis);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+// =============================================================================================
+// membrane transport
+// =============================================================================================
+namespace {
+
+struct MtEvalArgs {
+  int npts, ntoks, m;
+  double cdt;
+  const uint32_t* tok;         // kind | op<<8 | slot<<16
+  const int32_t* tok_operand;  // operand-table row or -1
+  const int32_t* near_cell;
+  const int32_t* far_cell;
+  const double* fieldval;
+  double* rate;
+  const double* u[SB2_MAX_SPECIES];
+  const double* kprev[SB2_MAX_SPECIES];
+  double consts[SB2_MAX_CONSTS];
+};
+
+// interpreter of calcMemTransport (calcPDE.cpp:1084-1393), one membrane point per thread
+__global__ void __launch_bounds__(128) mt_eval_kernel(const __grid_constant__ MtEvalArgs A) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= A.npts) return;
+  double st[50];
+  for (int i = 0; i < 50; ++i) st[i] = 0.0;
+  int sp = 0;
+  for (int i = 0; i < A.ntoks; ++i) {
+    const uint32_t t = A.tok[i];
+    const int kind = t & 0xff, op = (t >> 8) & 0xff, slot = t >> 16;
+    if (kind == SB2_TOK_VAR) {
+      const int row = A.tok_operand[i];
+      const int nc = A.near_cell[(int64_t)row * A.npts + p];
+      const int fc = A.far_cell[(int64_t)row * A.npts + p];
+      if (nc >= 0) {
+        // 1.5*value(boundary) - 0.5*value(boundary_next) when the second cell exists (calcPDE.cpp:1107-1213)
+        double wn = A.u[slot][nc];
+        if (A.m > 0) wn = wn + A.cdt * A.kprev[slot][nc];
+        if (fc >= 0) {
+          double wf = A.u[slot][fc];
+          if (A.m > 0) wf = wf + A.cdt * A.kprev[slot][fc];
+          st[sp] = 1.5 * wn - 0.5 * wf;
+        } else {
+          st[sp] = wn;
+        }
+      }
+      if (sp < 49) ++sp;
+    } else if (kind == SB2_TOK_FIELD) {
+      st[sp] = A.fieldval[(int64_t)A.tok_operand[i] * A.npts + p];
+      if (sp < 49) ++sp;
+    } else if (kind == SB2_TOK_CONST) {
+      st[sp] = A.consts[slot];
+      if (sp < 49) ++sp;
+    } else {
+      if (sp > 0) --sp;  // the reference decrements unconditionally; guard only keeps us in the array
+      if (kind != SB2_TOK_OP) continue;
+      if (op >= SB2_OP_PLUS && op <= SB2_OP_NEQ) {
+        if (sp > 0) st[sp - 1] = sb2_binary_any(op, st[sp - 1], st[sp]);
+      } else if (op >= SB2_OP_ABS && op <= SB2_OP_NOT) {
+        st[sp] = sb2_unary(op, st[sp]);
+        if (sp < 49) ++sp;
+      }
+    }
+  }
+  // "if (st_index > 1) st_index--;" then the rate is rpStack[st_index] (calcPDE.cpp:1392-1393): with the
+  // normal final depth 1 this reads slot 1 — the right operand of the last binary operator
+  if (sp > 1) --sp;
+  A.rate[p] = st[sp];
+}
+
+struct MtApplyArgs {
+  int n_groups;
+  const int32_t* group_start;
+  const int32_t* group_species;
+  const int64_t* group_cell;
+  const int32_t* entry_pt;
+  const double* entry_coef;
+  const double* entry_delta;
+  const int32_t* entry_sign;
+  const double* rate;
+  double* kout[SB2_MAX_SPECIES];
+};
+
+// gather formulation of the scatter at calcPDE.cpp:1394-1479: one thread per (species, cell) sums its
+// contributions in the reference's order
+__global__ void __launch_bounds__(128) mt_apply_kernel(const __grid_constant__ MtApplyArgs A) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= A.n_groups) return;
+  double* kp = A.kout[A.group_species[g]] + A.group_cell[g];
+  double acc = *kp;
+  for (int e = A.group_start[g]; e < A.group_start[g + 1]; ++e) {
+    // fabs(n) * stoich * rate / delta
+    const double term = A.entry_coef[e] * A.rate[A.entry_pt[e]] / A.entry_delta[e];
+    acc = A.entry_sign[e] < 0 ? acc - term : acc + term;
+  }
+  *kp = acc;
+}
+
+struct MtEntry {
+  int species;
+  int64_t cell;
+  int pt;
+  double coef, delta;
+  int sign;
+};
+
+}  // namespace
+
+int sb2_build_transport(const sb2_grid& g, int64_t P, int64_t PL, int64_t first, int nspecies, const sb2_token* toks,
+                        int ntoks, const sb2_ref* refs, int nrefs, int n_reactants, const sb2_mem_point* pts, int npts,
+                        const int32_t* operand_cells, const double* operand_values, const int32_t* target_cells,
+                        cudaStream_t stream, Sb2MemTransport& out, std::string& err) {
+  out = Sb2MemTransport();
+  out.npts = npts; out.ntoks = ntoks; out.nspecies = nspecies;
+  if (npts < 0 || ntoks < 0 || (npts > 0 && (!pts || !target_cells))) { err = "membrane transport: null argument"; return SB2_ERR_ARG; }
+  const int64_t nxy = (int64_t)g.nx * g.ny;
+  auto pad = [&](int32_t c) -> int32_t {
+    if (c < 0) return -1;
+    const int k = (int)(c / nxy), j = (int)((c - k * nxy) / g.nx), i = (int)(c - k * nxy - (int64_t)j * g.nx);
+    return (int32_t)(first + (int64_t)k * PL + (int64_t)j * P + i);
+  };
+  std::vector<int32_t> near_c, far_c;
+  std::vector<double> fval;
+  int nvar = 0, nfield = 0, rows = 0;
+  for (int i = 0; i < ntoks; ++i) {
+    out.tok.push_back((uint32_t)toks[i].kind | ((uint32_t)toks[i].op << 8) | ((uint32_t)toks[i].slot << 16));
+    if (toks[i].kind == SB2_TOK_VAR) {
+      if (toks[i].slot >= nspecies) { err = "membrane transport: token references unknown species"; return SB2_ERR_ARG; }
+      if (!operand_cells) { err = "membrane transport: operand cells missing"; return SB2_ERR_ARG; }
+      out.tok_operand.push_back(rows++);
+      for (int p = 0; p < npts; ++p) {
+        near_c.push_back(pad(operand_cells[((int64_t)nvar * npts + p) * 2 + 0]));
+        far_c.push_back(pad(operand_cells[((int64_t)nvar * npts + p) * 2 + 1]));
+        fval.push_back(0.0);
+      }
+      ++nvar;
+    } else if (toks[i].kind == SB2_TOK_FIELD) {
+      if (!operand_values) { err = "membrane transport: field operand values missing"; return SB2_ERR_ARG; }
+      out.tok_operand.push_back(rows++);
+      for (int p = 0; p < npts; ++p) {
+        near_c.push_back(-1); far_c.push_back(-1);
+        fval.push_back(operand_values[(int64_t)nfield * npts + p]);
+      }
+      ++nfield;
+    } else {
+      out.tok_operand.push_back(-1);
+    }
+  }
+  // contributions in the reference's order: points ascending; reactants (plus side, minus side), then products
+  const double delta[3] = {g.dx, g.dy, g.dz};
+  std::vector<MtEntry> entries;
+  for (int p = 0; p < npts; ++p) {
+    for (int r = 0; r < nrefs; ++r) {
+      if (!refs[r].is_variable || refs[r].species < 0) continue;
+      if (refs[r].species >= nspecies) { err = "membrane transport: reference to unknown species"; return SB2_ERR_ARG; }
+      for (int side = 0; side < 2; ++side) {
+        const int32_t c = target_cells[((int64_t)r * npts + p) * 2 + side];
+        if (c < 0) continue;
+        MtEntry e;
+        e.species = refs[r].species; e.cell = pad(c); e.pt = p;
+        e.coef = pts[p].abs_normal * refs[r].stoichiometry;
+        e.delta = delta[pts[p].axis];
+        e.sign = r < n_reactants ? -1 : +1;
+        entries.push_back(e);
+      }
+    }
+  }
+  std::stable_sort(entries.begin(), entries.end(), [](const MtEntry& a, const MtEntry& b) {
+    if (a.species != b.species) return a.species < b.species;
+    return a.cell < b.cell;
+  });
+  std::vector<int32_t> gstart, gspecies, ept, esign;
+  std::vector<int64_t> gcell;
+  std::vector<double> ecoef, edelta;
+  for (size_t i = 0; i < entries.size(); ++i) {
+    if (i == 0 || entries[i].species != entries[i - 1].species || entries[i].cell != entries[i - 1].cell) {
+      gstart.push_back((int32_t)i); gspecies.push_back(entries[i].species); gcell.push_back(entries[i].cell);
+    }
+    ept.push_back(entries[i].pt); ecoef.push_back(entries[i].coef); edelta.push_back(entries[i].delta);
+    esign.push_back(entries[i].sign);
+  }
+  gstart.push_back((int32_t)entries.size());
+  out.n_groups = (int)gspecies.size(); out.n_entries = (int)entries.size();
+  cudaError_t e;
+  std::vector<double> rate0(std::max(npts, 1), 0.0);
+  if ((e = to_device(&out.d_near, near_c, stream)) != cudaSuccess || (e = to_device(&out.d_far, far_c, stream)) != cudaSuccess ||
+      (e = to_device(&out.d_fieldval, fval, stream)) != cudaSuccess || (e = to_device(&out.d_rate, rate0, stream)) != cudaSuccess ||
+      (e = to_device(&out.d_group_start, gstart, stream)) != cudaSuccess ||
+      (e = to_device(&out.d_group_species, gspecies, stream)) != cudaSuccess ||
+      (e = to_device(&out.d_group_cell, gcell, stream)) != cudaSuccess || (e = to_device(&out.d_entry_pt, ept, stream)) != cudaSuccess ||
+      (e = to_device(&out.d_entry_coef, ecoef, stream)) != cudaSuccess ||
+      (e = to_device(&out.d_entry_delta, edelta, stream)) != cudaSuccess ||
+      (e = to_device(&out.d_entry_sign, esign, stream)) != cudaSuccess) {
+    err = std::string("membrane transport: ") + cudaGetErrorString(e);
+    return SB2_ERR_CUDA;
+  }
+  return SB2_OK;
+}
+
+void sb2_free_transport(Sb2MemTransport& t) {
+  cudaFree(t.d_near); cudaFree(t.d_far); cudaFree(t.d_fieldval); cudaFree(t.d_rate);
+  cudaFree(t.d_group_start); cudaFree(t.d_group_species); cudaFree(t.d_group_cell);
+  cudaFree(t.d_entry_pt); cudaFree(t.d_entry_coef); cudaFree(t.d_entry_delta); cudaFree(t.d_entry_sign);
+}
+
+cudaError_t sb2_launch_transport(const Sb2MemTransport& t, const sb2_grid& g, const double* const* u,
+                                 const double* const* kprev, double* const* kout, const double* consts, int m,
+                                 double cdt, cudaStream_t stream, int* launches) {
+  (void)g;
+  if (t.npts == 0) return cudaSuccess;
+  // program upload (a few dozen bytes) — stream ordered, from pageable memory
+  static thread_local uint32_t* d_tok = NULL;
+  static thread_local int32_t* d_operand = NULL;
+  static thread_local int cap = 0;
+  if (cap < t.ntoks) {
+    cudaFree(d_tok); cudaFree(d_operand);
+    cap = std::max(64, t.ntoks);
+    cudaError_t e = cudaMalloc((void**)&d_tok, sizeof(uint32_t) * cap);
+    if (e != cudaSuccess) return e;
+    e = cudaMalloc((void**)&d_operand, sizeof(int32_t) * cap);
+    if (e != cudaSuccess) return e;
+  }
+  cudaError_t e = cudaMemcpyAsync(d_tok, t.tok.data(), sizeof(uint32_t) * t.ntoks, cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpyAsync(d_operand, t.tok_operand.data(), sizeof(int32_t) * t.ntoks, cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess) return e;
+
+  MtEvalArgs a;
+  a.npts = t.npts; a.ntoks = t.ntoks; a.m = m; a.cdt = cdt;
+  a.tok = d_tok; a.tok_operand = d_operand;
+  a.near_cell = t.d_near; a.far_cell = t.d_far; a.fieldval = t.d_fieldval; a.rate = t.d_rate;
+  for (int s = 0; s < SB2_MAX_SPECIES; ++s) { a.u[s] = NULL; a.kprev[s] = NULL; }
+  for (size_t i = 0; i < t.tok.size(); ++i)
+    if ((t.tok[i] & 0xff) == SB2_TOK_VAR) { const int s = t.tok[i] >> 16; a.u[s] = u[s]; a.kprev[s] = kprev[s]; }
+  memcpy(a.consts, consts, sizeof(a.consts));
+  if (launches) ++*launches;
+  mt_eval_kernel<<<(t.npts + 127) / 128, 128, 0, stream>>>(a);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (t.n_groups == 0) return cudaSuccess;
+  MtApplyArgs b;
+  b.n_groups = t.n_groups;
+  b.group_start = t.d_group_start; b.group_species = t.d_group_species; b.group_cell = t.d_group_cell;
+  b.entry_pt = t.d_entry_pt; b.entry_coef = t.d_entry_coef; b.entry_delta = t.d_entry_delta; b.entry_sign = t.d_entry_sign;
+  b.rate = t.d_rate;
+  for (int s = 0; s < SB2_MAX_SPECIES; ++s) b.kout[s] = s < t.nspecies ? kout[s] : NULL;
+  if (launches) ++*launches;
+  mt_apply_kernel<<<(t.n_groups + 127) / 128, 128, 0, stream>>>(b);
+  return cudaGetLastError();
+}
+
+// =============================================================================================
+// stability: largest admissible dt (checkStability.cpp:10-52 and 119-154)
+// =============================================================================================
+namespace {
+
+__global__ void __launch_bounds__(256) min_dt_kernel(const __grid_constant__ Sb2MinDtArgs A, double* block_min) {
+  const int64_t ncell = (int64_t)A.nx * A.ny * A.nz;
+  double best = A.dt;
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(c / ((int64_t)A.nx * A.ny));
+    const int j = (int)((c - (int64_t)k * A.nx * A.ny) / A.nx);
+    const int i = (int)(c - (int64_t)k * A.nx * A.ny - (int64_t)j * A.nx);
+    const int64_t idx = A.first + (int64_t)k * A.PL + (int64_t)j * A.P + i;
+    if (!(A.flags[idx] & SB2_F_DOMAIN)) continue;
+    if (A.has_diff && A.dkind[0] != SB2_SRC_NONE) {
+      const double d0 = A.dkind[0] == SB2_SRC_CONST ? A.dconst[0] : A.dfield[0][idx];
+      // x; the y / z tests compare against their own coefficient but take the minimum with the
+      // x coefficient (checkStability.cpp:39-40, 45-46)
+      if (A.dt >= A.delta[0] * A.delta[0] / (2.0 * d0)) best = fmin(best, A.delta[0] * A.delta[0] / (2.0 * d0));
+      for (int a = 1; a < 3; ++a) {
+        if (A.dkind[a] == SB2_SRC_NONE) continue;
+        const double da = A.dkind[a] == SB2_SRC_CONST ? A.dconst[a] : A.dfield[a][idx];
+        if (A.dt >= A.delta[a] * A.delta[a] / (2.0 * da)) best = fmin(best, A.delta[a] * A.delta[a] / (2.0 * d0));
+      }
+    }
+    if (A.has_adv) {
+      for (int a = 0; a < A.dim; ++a) {
+        if (A.akind[a] == SB2_SRC_NONE) continue;
+        const double ua = A.akind[a] == SB2_SRC_CONST ? A.aconst[a] : A.afield[a][idx];
+        if (ua * (A.dt / A.delta[a]) >= 1) best = fmin(best, A.delta[a] / ua);
+      }
+    }
+  }
+  // warp-shuffle min, then one value per warp through shared memory
+  for (int o = 16; o > 0; o >>= 1) best = fmin(best, __shfl_xor_sync(0xffffffffu, best, o));
+  __shared__ double wmin[8];
+  if ((threadIdx.x & 31) == 0) wmin[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < (blockDim.x >> 5) ? wmin[threadIdx.x] : A.dt;
+    for (int o = 4; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (threadIdx.x == 0) block_min[blockIdx.x] = v;
+  }
+}
+
+}  // namespace
+
+cudaError_t sb2_launch_min_dt(const Sb2MinDtArgs& a, double* d_scratch, cudaStream_t stream, int* launches, double* result) {
+  const int64_t ncell = (int64_t)a.nx * a.ny * a.nz;
+  int blocks = (int)std::min<int64_t>((ncell + 255) / 256, 148 * 8);
+  if (blocks < 1) blocks = 1;
+  if (launches) ++*launches;
+  min_dt_kernel<<<blocks, 256, 0, stream>>>(a, d_scratch);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  std::vector<double> h(blocks);
+  e = cudaMemcpyAsync(h.data(), d_scratch, sizeof(double) * blocks, cudaMemcpyDeviceToHost, stream);
+  if (e != cudaSuccess) return e;
+  e = cudaStreamSynchronize(stream);
+  if (e != cudaSuccess) return e;
+  double best = a.dt;
+  for (int i = 0; i < blocks; ++i) best = std::min(best, h[i]);
+  *result = best;
+  return cudaSuccess;
+}

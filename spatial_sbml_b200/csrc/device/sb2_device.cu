@@ -1,0 +1,790 @@
+// sb2_device.cu — C-ABI device layer (see include/spatial_b200.h): device memory, the RPN → device
+// bytecode compiler, and the per-step kernel schedule that replaces performStep/updateValues
+// (reference spatialsimulator.cpp:1350-1544).
+#include "sb2_internal.h"
+#include "sb2_aux.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <sstream>
+
+namespace {
+thread_local std::string g_create_error;
+}
+
+struct Sb2Species {
+  int geo;
+  double* u[2];
+  int cur;
+  double* k[4];
+  int dkind[3], dsrc[3];
+  int akind[3], asrc[3];
+  int bckind[6], bcskind[6], bcsrc[6];
+  bool has_diff, has_adv, has_bc;
+  double* faces[3];  // CIP face values (advected species only)
+};
+
+struct Sb2Stmt {
+  int geo, kind, n_reactants;
+  std::vector<sb2_token> toks;
+  std::vector<sb2_ref> refs;
+};
+
+struct sb2_sim {
+  sb2_grid g;
+  int64_t P, PL, first, nalloc;
+  cudaStream_t stream;
+  bool own_stream;
+  std::vector<uint8_t*> d_flags;
+  std::vector<std::vector<uint8_t> > h_flags;  // compact host copies (boundary lists, reductions)
+  std::vector<Sb2Species> species;
+  std::vector<double*> d_fields;
+  double consts[SB2_MAX_CONSTS];
+  int n_user_consts, n_internal_consts;
+  std::vector<Sb2Stmt> stmts;
+  std::vector<uint32_t> program;
+  std::vector<Sb2MemTransport> transports;
+  Sb2BoundaryLists blists;
+  bool finalized, any_adv;
+  bool fuse_combine;    // this step: RK combine fused into stage 4
+  bool carry_k0;        // this step: a non-zero Neumann flux is carried in k0 (spatialsimulator.cpp:1540-1542)
+  bool k0_carry_valid;  // k0 currently holds the flux parked by the previous step's post-update pass
+  double* d_tmp_face;   // CIP scratch
+  Sb2StageArgs base;
+  std::string err;
+  int launches;
+  // split-phase step state
+  double cur_dt;
+  bool in_step;
+  double* d_scratch;  // reduction scratch
+};
+
+namespace {
+
+int fail(sb2_sim* s, int code, const std::string& msg) {
+  if (s) s->err = msg; else g_create_error = msg;
+  return code;
+}
+int cuda_fail(sb2_sim* s, cudaError_t e, const char* what) {
+  std::ostringstream os;
+  os << what << ": " << cudaGetErrorName(e) << " (" << cudaGetErrorString(e) << ")";
+  return fail(s, SB2_ERR_CUDA, os.str());
+}
+#define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail(sim, e__, #call); } while (0)
+
+int64_t ncells(const sb2_sim* s) { return (int64_t)s->g.nx * s->g.ny * s->g.nz; }
+
+// compact host array → padded device layout (guard rows / planes, even pitch)
+template <typename T>
+int upload_padded(sb2_sim* sim, T* dst, const T* src) {
+  const sb2_grid& g = sim->g;
+  CK(cudaMemsetAsync(dst, 0, sizeof(T) * sim->nalloc, sim->stream));
+  for (int z = 0; z < g.nz; ++z) {
+    CK(cudaMemcpy2DAsync(dst + sim->first + (int64_t)z * sim->PL, sizeof(T) * sim->P,
+                         src + (int64_t)z * g.nx * g.ny, sizeof(T) * g.nx, sizeof(T) * g.nx, g.ny,
+                         cudaMemcpyHostToDevice, sim->stream));
+  }
+  return SB2_OK;
+}
+template <typename T>
+int upload_interior(sb2_sim* sim, T* dst, const T* src) {
+  const sb2_grid& g = sim->g;
+  for (int z = 0; z < g.nz; ++z) {
+    CK(cudaMemcpy2DAsync(dst + sim->first + (int64_t)z * sim->PL, sizeof(T) * sim->P,
+                         src + (int64_t)z * g.nx * g.ny, sizeof(T) * g.nx, sizeof(T) * g.nx, g.ny,
+                         cudaMemcpyHostToDevice, sim->stream));
+  }
+  return SB2_OK;
+}
+template <typename T>
+int download_padded(sb2_sim* sim, T* dst, const T* src) {
+  const sb2_grid& g = sim->g;
+  for (int z = 0; z < g.nz; ++z) {
+    CK(cudaMemcpy2DAsync(dst + (int64_t)z * g.nx * g.ny, sizeof(T) * g.nx,
+                         src + sim->first + (int64_t)z * sim->PL, sizeof(T) * sim->P, sizeof(T) * g.nx, g.ny,
+                         cudaMemcpyDeviceToHost, sim->stream));
+  }
+  CK(cudaStreamSynchronize(sim->stream));
+  return SB2_OK;
+}
+
+int alloc_field(sb2_sim* sim, double** out) {
+  CK(cudaMalloc((void**)out, sizeof(double) * sim->nalloc));
+  CK(cudaMemsetAsync(*out, 0, sizeof(double) * sim->nalloc, sim->stream));
+  return SB2_OK;
+}
+
+int internal_const(sb2_sim* sim, double v) {
+  // internal constants (stoichiometries) grow down from the top of the table
+  for (int i = 0; i < sim->n_internal_consts; ++i) {
+    const int slot = SB2_MAX_CONSTS - 1 - i;
+    if (memcmp(&sim->consts[slot], &v, sizeof(double)) == 0) return slot;
+  }
+  const int slot = SB2_MAX_CONSTS - 1 - sim->n_internal_consts;
+  if (slot < sim->n_user_consts) return -1;
+  sim->consts[slot] = v;
+  sim->n_internal_consts++;
+  return slot;
+}
+
+bool is_unary(int op) { return op >= SB2_OP_ABS && op <= SB2_OP_NOT; }
+bool is_binary(int op) { return op >= SB2_OP_PLUS && op <= SB2_OP_NEQ; }
+
+uint32_t enc(int opc, int d, int arg) { return SB2_CODE(opc, d) | ((uint32_t)arg << 16); }
+
+// RPN (stack program) → register-addressed device bytecode.  Follows the reference interpreter's
+// stack discipline token by token (calcPDE.cpp:244-449): operands push; an operator first pops
+// (if the stack is non-empty), binary operators then combine into the new top only if something is
+// left below, unary operators rewrite the popped slot and push it back, listed-but-empty operators
+// and unresolved names only pop.  The rate is read from slot max(sp-1, 0).
+int compile_stmt(sb2_sim* sim, const Sb2Stmt& st, std::vector<uint32_t>& out) {
+  out.push_back(enc(OPC_MASK, 0, st.geo));
+  int sp = 0;
+  const int n = (int)st.toks.size();
+  for (int i = 0; i < n; ++i) {
+    const sb2_token& t = st.toks[i];
+    if (t.kind == SB2_TOK_VAR || t.kind == SB2_TOK_FIELD || t.kind == SB2_TOK_CONST) {
+      if (t.kind == SB2_TOK_VAR && t.slot >= sim->species.size()) return fail(sim, SB2_ERR_ARG, "token references unknown species");
+      if (t.kind == SB2_TOK_FIELD && t.slot >= sim->d_fields.size()) return fail(sim, SB2_ERR_ARG, "token references unknown field");
+      if (t.kind == SB2_TOK_CONST && t.slot >= SB2_MAX_CONSTS) return fail(sim, SB2_ERR_ARG, "token references constant slot out of range");
+      // operand immediately consumed by a binary operator → fused form acting on r[sp-1]
+      if (sp >= 1 && i + 1 < n && st.toks[i + 1].kind == SB2_TOK_OP && t.kind != SB2_TOK_FIELD) {
+        const int op = st.toks[i + 1].op;
+        int opc = -1;
+        const bool c = t.kind == SB2_TOK_CONST;
+        switch (op) {
+          case SB2_OP_PLUS: opc = c ? OPC_ADDC : OPC_ADDV; break;
+          case SB2_OP_MINUS: opc = c ? OPC_SUBC : OPC_SUBV; break;
+          case SB2_OP_TIMES: opc = c ? OPC_MULC : OPC_MULV; break;
+          case SB2_OP_DIVIDE: opc = c ? OPC_DIVC : OPC_DIVV; break;
+          case SB2_OP_GEQ: if (c) opc = OPC_GEQC; break;
+          case SB2_OP_GT: if (c) opc = OPC_GTC; break;
+          case SB2_OP_LEQ: if (c) opc = OPC_LEQC; break;
+          case SB2_OP_LT: if (c) opc = OPC_LTC; break;
+          default: break;
+        }
+        if (opc >= 0) { out.push_back(enc(opc, sp - 1, t.slot)); ++i; continue; }
+      }
+      if (sp >= SB2_MAX_DEPTH) return fail(sim, SB2_ERR_LIMIT, "expression stack deeper than SB2_MAX_DEPTH");
+      out.push_back(enc(t.kind == SB2_TOK_VAR ? OPC_PUSHV : t.kind == SB2_TOK_FIELD ? OPC_PUSHF : OPC_PUSHC, sp, t.slot));
+      ++sp;
+    } else {
+      if (sp > 0) --sp;
+      if (t.kind != SB2_TOK_OP) continue;  // unresolved name: pop only
+      const int op = t.op;
+      if (is_binary(op)) {
+        if (sp == 0) continue;  // nothing below: the reference leaves the stack untouched
+        int opc = -1;
+        switch (op) {
+          case SB2_OP_PLUS: opc = OPC_ADD; break;
+          case SB2_OP_MINUS: opc = OPC_SUB; break;
+          case SB2_OP_TIMES: opc = OPC_MUL; break;
+          case SB2_OP_DIVIDE: opc = OPC_DIV; break;
+          case SB2_OP_GEQ: opc = OPC_GEQ; break;
+          case SB2_OP_GT: opc = OPC_GT; break;
+          case SB2_OP_LEQ: opc = OPC_LEQ; break;
+          case SB2_OP_LT: opc = OPC_LT; break;
+          case SB2_OP_AND: opc = OPC_AND; break;
+          case SB2_OP_OR: opc = OPC_OR; break;
+          default: break;
+        }
+        if (opc >= 0) out.push_back(enc(opc, sp, 0));
+        else out.push_back(enc(OPC_BINR, sp, op));
+      } else if (is_unary(op)) {
+        if (sp >= SB2_MAX_DEPTH) return fail(sim, SB2_ERR_LIMIT, "expression stack deeper than SB2_MAX_DEPTH");
+        out.push_back(enc(OPC_UNARY, sp, op));
+        ++sp;
+      }
+      // SB2_OP_POP_ONLY and anything else: pop only
+    }
+  }
+  if (sp > 0) --sp;
+  if (sp != 0) out.push_back(enc(OPC_MOV0, sp, 0));
+  if (st.kind == 0) {
+    for (int k = 0; k < (int)st.refs.size(); ++k) {
+      const sb2_ref& r = st.refs[k];
+      if (!r.is_variable || r.species < 0) continue;
+      if (r.species >= (int)sim->species.size()) return fail(sim, SB2_ERR_ARG, "reaction references unknown species");
+      const int slot = internal_const(sim, r.stoichiometry);
+      if (slot < 0) return fail(sim, SB2_ERR_LIMIT, "constants table full");
+      out.push_back(enc(k < st.n_reactants ? OPC_ACCSUB : OPC_ACCADD, r.species, slot));
+    }
+  } else if (!st.refs.empty()) {
+    const sb2_ref& r = st.refs[0];
+    if (r.is_variable && r.species >= 0) {
+      if (r.species >= (int)sim->species.size()) return fail(sim, SB2_ERR_ARG, "rate rule references unknown species");
+      const int slot = internal_const(sim, r.stoichiometry);
+      if (slot < 0) return fail(sim, SB2_ERR_LIMIT, "constants table full");
+      out.push_back(enc(OPC_ACCADD, r.species, slot));
+    }
+  }
+  return SB2_OK;
+}
+
+const char* kOpcNames[OPC_COUNT] = {"END", "PUSHC", "PUSHV", "PUSHF", "ADD", "SUB", "MUL", "DIV", "GEQ", "GT",
+  "LEQ", "LT", "AND", "OR", "ADDC", "SUBC", "MULC", "DIVC", "GEQC", "GTC", "LEQC", "LTC", "ADDV", "SUBV", "MULV",
+  "DIVV", "UNARY", "BINR", "MOV0", "MASK", "ACCSUB", "ACCADD"};
+
+void fill_stage_args(sb2_sim* sim, Sb2StageArgs& a, int m, double dt, int row_begin, int row_end) {
+  static const double rk[4] = {0.0, 0.5, 0.5, 1.0};
+  a = sim->base;
+  memcpy(a.consts, sim->consts, sizeof(a.consts));
+  a.m = m;
+  a.dt = dt;
+  a.cdt = rk[m] * dt;
+  a.final = (m == 3 && sim->fuse_combine) ? 1 : 0;
+  a.carry = (sim->carry_k0 && m == 0) || !sim->transports.empty() ? 1 : 0;
+  a.row_begin = row_begin;
+  a.row_end = row_end;
+  const int S = (int)sim->species.size();
+  for (int s = 0; s < S; ++s) {
+    Sb2Species& sp = sim->species[s];
+    Sb2SpeciesArgs& o = a.sp[s];
+    o.u = sp.u[sp.cur];
+    o.u_out = sp.u[sp.cur ^ 1];
+    o.kprev = m > 0 ? sp.k[m - 1] : sp.k[0];
+    o.kout = sp.k[m];
+    o.k0 = sp.k[0];
+    o.k1 = sp.k[1];
+  }
+  // rows per CTA: enough CTAs to fill the machine several times over, long enough strips to
+  // amortise the two extra rows each CTA loads
+  const int strips = (sim->g.nx + 255) / 256;
+  const int rows = (sim->g.dim == 3) ? sim->g.ny : (row_end - row_begin);
+  const int planes = (sim->g.dim == 3) ? (row_end - row_begin) : 1;
+  int rpb = 64;
+  while (rpb > 8 && (int64_t)strips * planes * ((rows + rpb - 1) / rpb) < 148 * 8) rpb /= 2;
+  a.rows_per_block = rpb;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+const char* sb2_last_error(const sb2_sim* sim) { return sim ? sim->err.c_str() : g_create_error.c_str(); }
+
+int sb2_create(const sb2_grid* grid, sb2_sim** out) {
+  if (!grid || !out) return fail(NULL, SB2_ERR_ARG, "null argument");
+  *out = NULL;
+  if (grid->nx < 1 || grid->ny < 1 || grid->nz < 1) return fail(NULL, SB2_ERR_ARG, "grid dimensions must be positive");
+  if (grid->dim != 2 && grid->dim != 3) return fail(NULL, SB2_ERR_ARG, "only 2-D and 3-D geometries are supported on the device");
+  if (grid->dim == 2 && grid->nz != 1) return fail(NULL, SB2_ERR_ARG, "nz must be 1 for a 2-D grid");
+  if (grid->own_hi > grid->own_lo) {
+    const int n_held = grid->dim == 3 ? grid->nz : grid->ny;
+    if (grid->own_lo < 0 || grid->own_hi > n_held || grid->row0 < 0) return fail(NULL, SB2_ERR_ARG, "owned row range outside the held rows");
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(NULL, SB2_ERR_CUDA, std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+  if (grid->device < 0 || grid->device >= ndev) return fail(NULL, SB2_ERR_ARG, "device ordinal out of range");
+  e = cudaSetDevice(grid->device);
+  if (e != cudaSuccess) return fail(NULL, SB2_ERR_CUDA, cudaGetErrorString(e));
+  sb2_sim* sim = new sb2_sim();
+  sim->g = *grid;
+  sim->P = (grid->nx + 1) / 2 * 2;
+  if (grid->dim == 2) {
+    sim->PL = sim->P * (grid->ny + 2);
+    sim->first = sim->P;
+    sim->nalloc = sim->PL;
+  } else {
+    sim->PL = sim->P * (grid->ny + 2);
+    sim->first = sim->PL + sim->P;
+    sim->nalloc = sim->PL * (grid->nz + 2);
+  }
+  sim->stream = 0; sim->own_stream = false;
+  e = cudaStreamCreateWithFlags(&sim->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete sim; return fail(NULL, SB2_ERR_CUDA, cudaGetErrorString(e)); }
+  sim->own_stream = true;
+  memset(sim->consts, 0, sizeof(sim->consts));
+  sim->n_user_consts = 0; sim->n_internal_consts = 0;
+  sim->finalized = false; sim->fuse_combine = true; sim->any_adv = false; sim->carry_k0 = false;
+  sim->k0_carry_valid = false; sim->d_tmp_face = NULL;
+  sim->launches = 0; sim->in_step = false; sim->cur_dt = 0; sim->d_scratch = NULL;
+  memset(&sim->base, 0, sizeof(sim->base));
+  *out = sim;
+  return SB2_OK;
+}
+
+void sb2_destroy(sb2_sim* sim) {
+  if (!sim) return;
+  cudaSetDevice(sim->g.device);
+  cudaStreamSynchronize(sim->stream);
+  for (size_t i = 0; i < sim->d_flags.size(); ++i) cudaFree(sim->d_flags[i]);
+  for (size_t i = 0; i < sim->d_fields.size(); ++i) cudaFree(sim->d_fields[i]);
+  for (size_t i = 0; i < sim->species.size(); ++i) {
+    Sb2Species& s = sim->species[i];
+    cudaFree(s.u[0]); cudaFree(s.u[1]);
+    for (int m = 0; m < 4; ++m) cudaFree(s.k[m]);
+    for (int a = 0; a < 3; ++a) if (s.faces[a]) cudaFree(s.faces[a]);
+  }
+  for (size_t i = 0; i < sim->transports.size(); ++i) sb2_free_transport(sim->transports[i]);
+  sb2_free_boundary_lists(sim->blists);
+  if (sim->d_scratch) cudaFree(sim->d_scratch);
+  if (sim->d_tmp_face) cudaFree(sim->d_tmp_face);
+  if (sim->own_stream) cudaStreamDestroy(sim->stream);
+  delete sim;
+}
+
+int sb2_set_stream(sb2_sim* sim, void* cuda_stream) {
+  if (!sim) return SB2_ERR_ARG;
+  cudaStreamSynchronize(sim->stream);
+  if (sim->own_stream) { cudaStreamDestroy(sim->stream); sim->own_stream = false; }
+  sim->stream = (cudaStream_t)cuda_stream;
+  return SB2_OK;
+}
+
+int sb2_add_geometry(sb2_sim* sim, const uint8_t* cell_flags) {
+  if (!sim || !cell_flags) return fail(sim, SB2_ERR_ARG, "null argument");
+  if (sim->finalized) return fail(sim, SB2_ERR_STATE, "simulator already finalized");
+  if (sim->d_flags.size() >= SB2_MAX_GEOS) return fail(sim, SB2_ERR_LIMIT, "more than SB2_MAX_GEOS geometries host spatial species");
+  cudaSetDevice(sim->g.device);
+  uint8_t* d = NULL;
+  CK(cudaMalloc((void**)&d, sim->nalloc));
+  sim->d_flags.push_back(d);
+  sim->h_flags.push_back(std::vector<uint8_t>(cell_flags, cell_flags + ncells(sim)));
+  int rc = upload_padded<uint8_t>(sim, d, cell_flags);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(sim->stream));
+  return (int)sim->d_flags.size() - 1;
+}
+
+int sb2_add_species(sb2_sim* sim, int geo, const double* init) {
+  if (!sim || !init) return fail(sim, SB2_ERR_ARG, "null argument");
+  if (sim->finalized) return fail(sim, SB2_ERR_STATE, "simulator already finalized");
+  if (geo < 0 || geo >= (int)sim->d_flags.size()) return fail(sim, SB2_ERR_ARG, "unknown geometry id");
+  if (sim->species.size() >= SB2_MAX_SPECIES) return fail(sim, SB2_ERR_LIMIT, "more than SB2_MAX_SPECIES staged species");
+  cudaSetDevice(sim->g.device);
+  Sb2Species s;
+  memset(&s, 0, sizeof(s));
+  s.geo = geo;
+  int rc;
+  for (int b = 0; b < 2; ++b) if ((rc = alloc_field(sim, &s.u[b]))) return rc;
+  for (int m = 0; m < 4; ++m) if ((rc = alloc_field(sim, &s.k[m]))) return rc;
+  if ((rc = upload_interior<double>(sim, s.u[0], init))) return rc;
+  CK(cudaStreamSynchronize(sim->stream));
+  sim->species.push_back(s);
+  return (int)sim->species.size() - 1;
+}
+
+int sb2_add_field(sb2_sim* sim, const double* values) {
+  if (!sim || !values) return fail(sim, SB2_ERR_ARG, "null argument");
+  if (sim->finalized) return fail(sim, SB2_ERR_STATE, "simulator already finalized");
+  if (sim->d_fields.size() >= SB2_MAX_FIELDS) return fail(sim, SB2_ERR_LIMIT, "more than SB2_MAX_FIELDS read-only fields");
+  cudaSetDevice(sim->g.device);
+  double* d = NULL;
+  int rc = alloc_field(sim, &d);
+  if (rc) return rc;
+  if ((rc = upload_interior<double>(sim, d, values))) return rc;
+  CK(cudaStreamSynchronize(sim->stream));
+  sim->d_fields.push_back(d);
+  return (int)sim->d_fields.size() - 1;
+}
+
+int sb2_set_constants(sb2_sim* sim, const double* table, int n) {
+  if (!sim || (!table && n > 0) || n < 0) return fail(sim, SB2_ERR_ARG, "bad constants table");
+  if (n > SB2_MAX_CONSTS - sim->n_internal_consts) return fail(sim, SB2_ERR_LIMIT, "constants table full");
+  memcpy(sim->consts, table, sizeof(double) * n);
+  if (n > sim->n_user_consts) sim->n_user_consts = n;
+  return SB2_OK;
+}
+
+int sb2_set_constant(sb2_sim* sim, int slot, double value) {
+  if (!sim) return SB2_ERR_ARG;
+  if (slot < 0 || slot >= SB2_MAX_CONSTS - sim->n_internal_consts) return fail(sim, SB2_ERR_ARG, "constant slot out of range");
+  sim->consts[slot] = value;
+  if (slot >= sim->n_user_consts) sim->n_user_consts = slot + 1;
+  return SB2_OK;
+}
+
+int sb2_add_reaction(sb2_sim* sim, int geo, int kind, const sb2_token* toks, int ntoks, const sb2_ref* refs,
+                     int nrefs, int n_reactants) {
+  if (!sim || (!toks && ntoks > 0) || (!refs && nrefs > 0)) return fail(sim, SB2_ERR_ARG, "null argument");
+  if (sim->finalized) return fail(sim, SB2_ERR_STATE, "simulator already finalized");
+  if (geo < 0 || geo >= (int)sim->d_flags.size()) return fail(sim, SB2_ERR_ARG, "unknown geometry id");
+  Sb2Stmt st;
+  st.geo = geo; st.kind = kind; st.n_reactants = n_reactants;
+  st.toks.assign(toks, toks + ntoks);
+  st.refs.assign(refs, refs + nrefs);
+  sim->stmts.push_back(st);
+  return SB2_OK;
+}
+
+int sb2_set_diffusion(sb2_sim* sim, int species, int axis, int src_kind, int src) {
+  if (!sim || species < 0 || species >= (int)sim->species.size() || axis < 0 || axis > 2)
+    return fail(sim, SB2_ERR_ARG, "bad species / axis");
+  Sb2Species& s = sim->species[species];
+  s.dkind[axis] = src_kind; s.dsrc[axis] = src;
+  s.has_diff = s.dkind[0] || s.dkind[1] || s.dkind[2];
+  return SB2_OK;
+}
+
+int sb2_set_advection(sb2_sim* sim, int species, int axis, int src_kind, int src) {
+  if (!sim || species < 0 || species >= (int)sim->species.size() || axis < 0 || axis > 2)
+    return fail(sim, SB2_ERR_ARG, "bad species / axis");
+  Sb2Species& s = sim->species[species];
+  s.akind[axis] = src_kind; s.asrc[axis] = src;
+  s.has_adv = true;  // adCInfo array exists as soon as one axis is declared (setInfoFunction.cpp:240-244)
+  return SB2_OK;
+}
+
+int sb2_set_boundary(sb2_sim* sim, int species, int side, int bc_kind, int src_kind, int src) {
+  if (!sim || species < 0 || species >= (int)sim->species.size() || side < 0 || side > 5)
+    return fail(sim, SB2_ERR_ARG, "bad species / side");
+  Sb2Species& s = sim->species[species];
+  s.bckind[side] = bc_kind; s.bcskind[side] = src_kind; s.bcsrc[side] = src;
+  s.has_bc = true;
+  return SB2_OK;
+}
+
+int sb2_add_mem_transport(sb2_sim* sim, const sb2_token* toks, int ntoks, const sb2_ref* refs, int nrefs,
+                          int n_reactants, const sb2_mem_point* pts, int npts, const int32_t* operand_cells,
+                          const double* operand_values, const int32_t* target_cells) {
+  if (!sim) return SB2_ERR_ARG;
+  if (sim->finalized) return fail(sim, SB2_ERR_STATE, "simulator already finalized");
+  cudaSetDevice(sim->g.device);
+  Sb2MemTransport t;
+  std::string err;
+  int rc = sb2_build_transport(sim->g, sim->P, sim->PL, sim->first, (int)sim->species.size(), toks, ntoks, refs,
+                               nrefs, n_reactants, pts, npts, operand_cells, operand_values, target_cells, sim->stream, t, err);
+  if (rc) return fail(sim, rc, err);
+  sim->transports.push_back(t);
+  return SB2_OK;
+}
+
+int sb2_finalize(sb2_sim* sim) {
+  if (!sim) return SB2_ERR_ARG;
+  if (sim->finalized) return fail(sim, SB2_ERR_STATE, "simulator already finalized");
+  cudaSetDevice(sim->g.device);
+  sim->program.clear();
+  for (size_t i = 0; i < sim->stmts.size(); ++i) {
+    int rc = compile_stmt(sim, sim->stmts[i], sim->program);
+    if (rc) return rc;
+  }
+  if (sim->program.size() > SB2_MAX_TOKENS) return fail(sim, SB2_ERR_LIMIT, "device program longer than SB2_MAX_TOKENS");
+  sim->any_adv = false;
+  for (size_t s = 0; s < sim->species.size(); ++s) if (sim->species[s].has_adv) sim->any_adv = true;
+
+  Sb2StageArgs& b = sim->base;
+  memset(&b, 0, sizeof(b));
+  b.nx = sim->g.nx; b.ny = sim->g.ny; b.nz = sim->g.nz; b.dim = sim->g.dim;
+  b.P = sim->P; b.PL = sim->PL; b.first = sim->first;
+  b.S = (int)sim->species.size();
+  b.G = (int)sim->d_flags.size();
+  const double del[3] = {sim->g.dx, sim->g.dy, sim->g.dz};
+  for (int a = 0; a < 3; ++a) {
+    b.dx2[a] = pow(del[a], 2);  // the reference divides by pow(delta, 2)
+    b.divide[a] = (b.dx2[a] != 1.0) ? 1 : 0;
+  }
+  for (int s = 0; s < b.S; ++s) {
+    Sb2Species& sp = sim->species[s];
+    b.sp[s].geo = sp.geo;
+    b.sp[s].has_diff = sp.has_diff ? 1 : 0;
+    for (int a = 0; a < 3; ++a) {
+      b.sp[s].dkind[a] = sp.dkind[a]; b.sp[s].dsrc[a] = sp.dsrc[a];
+      if (sp.dkind[a] == SB2_SRC_FIELD && (sp.dsrc[a] < 0 || sp.dsrc[a] >= (int)sim->d_fields.size()))
+        return fail(sim, SB2_ERR_ARG, "diffusion coefficient references unknown field");
+      if (sp.dkind[a] == SB2_SRC_CONST && (sp.dsrc[a] < 0 || sp.dsrc[a] >= SB2_MAX_CONSTS))
+        return fail(sim, SB2_ERR_ARG, "diffusion coefficient references constant slot out of range");
+    }
+  }
+  for (int g = 0; g < b.G; ++g) b.flags[g] = sim->d_flags[g];
+  for (size_t f = 0; f < sim->d_fields.size(); ++f) b.fields[f] = sim->d_fields[f];
+  b.ntok = (int)sim->program.size();
+  memcpy(b.tok, sim->program.data(), sizeof(uint32_t) * sim->program.size());
+
+  // boundary-condition lists (Neumann flux / Dirichlet overwrite), built from the host flag copies
+  std::string err;
+  std::vector<Sb2BcSpecies> bcs(sim->species.size());
+  for (size_t s = 0; s < sim->species.size(); ++s) {
+    Sb2Species& sp = sim->species[s];
+    bcs[s].geo = sp.geo; bcs[s].has_bc = sp.has_bc;
+    for (int k = 0; k < 6; ++k) { bcs[s].kind[k] = sp.bckind[k]; bcs[s].skind[k] = sp.bcskind[k]; bcs[s].src[k] = sp.bcsrc[k]; }
+  }
+  int rc = sb2_build_boundary_lists(sim->g, sim->P, sim->PL, sim->first, sim->h_flags, bcs, sim->consts, sim->stream,
+                                    sim->blists, err);
+  if (rc) return fail(sim, rc, err);
+
+  // advected species carry CIP face values (allocated by sb2_upload_faces or here, zero-filled)
+  for (size_t s = 0; s < sim->species.size(); ++s) {
+    Sb2Species& sp = sim->species[s];
+    if (!sp.has_adv) continue;
+    for (int a = 0; a < sim->g.dim; ++a) {
+      if (sp.akind[a] == SB2_SRC_FIELD) return fail(sim, SB2_ERR_LIMIT, "non-uniform advection velocities are not supported on the device yet");
+      if (!sp.faces[a]) { rc = alloc_field(sim, &sp.faces[a]); if (rc) return rc; }
+    }
+  }
+  if (sim->any_adv) { rc = alloc_field(sim, &sim->d_tmp_face); if (rc) return rc; }
+  CK(cudaMalloc((void**)&sim->d_scratch, sizeof(double) * 4096));
+  CK(cudaStreamSynchronize(sim->stream));
+  sim->finalized = true;
+  return SB2_OK;
+}
+
+int sb2_begin_step(sb2_sim* sim, double t_arg, double dt, int time_slot) {
+  if (!sim || !sim->finalized) return fail(sim, SB2_ERR_STATE, "simulator not finalized");
+  cudaSetDevice(sim->g.device);
+  if (time_slot >= 0) {
+    if (time_slot >= SB2_MAX_CONSTS) return fail(sim, SB2_ERR_ARG, "time slot out of range");
+    sim->consts[time_slot] = t_arg * dt;  // sim_time = t * dt, spatialsimulator.cpp:1358
+  }
+  sim->cur_dt = dt;
+  // A Neumann flux that is exactly zero adds +0.0 everywhere (all shipped models): the boundary
+  // passes are skipped and the combine can be fused.  A non-zero flux takes the un-fused schedule,
+  // which reproduces the reference's order of additions including the flux carried in k0.
+  sim->carry_k0 = sb2_neumann_active(sim->blists, (int)sim->species.size(), sim->consts);
+  sim->fuse_combine = !sim->any_adv && !sim->carry_k0;
+  if (sim->carry_k0 && !sim->k0_carry_valid) {
+    for (size_t s = 0; s < sim->species.size(); ++s)
+      CK(cudaMemsetAsync(sim->species[s].k[0], 0, sizeof(double) * sim->nalloc, sim->stream));
+  }
+  sim->in_step = true;
+  return SB2_OK;
+}
+
+int sb2_stage(sb2_sim* sim, int m, int phase) {
+  if (!sim || !sim->in_step) return fail(sim, SB2_ERR_STATE, "sb2_stage outside sb2_begin_step / sb2_end_step");
+  if (m < 0 || m > 3) return fail(sim, SB2_ERR_ARG, "stage index out of range");
+  cudaSetDevice(sim->g.device);
+  const int n_held = sim->g.dim == 3 ? sim->g.nz : sim->g.ny;
+  const bool whole = sim->g.own_hi <= sim->g.own_lo;
+  const int own_lo = whole ? 0 : sim->g.own_lo, own_hi = whole ? n_held : sim->g.own_hi;
+  // owned rows next to a neighbouring slab (their results are what the neighbours' halos need)
+  const int lo_edge = own_lo > 0 ? 1 : 0, hi_edge = own_hi < n_held ? 1 : 0;
+  const double dt = sim->cur_dt;
+
+  if (phase == 0 || phase == 1) {
+    // membrane transport first: its flux is the carry-in of the stage accumulators
+    if (!sim->transports.empty()) {
+      for (size_t s = 0; s < sim->species.size(); ++s) {
+        if (sim->carry_k0 && m == 0) continue;  // k0 already holds the carried Neumann flux
+        CK(cudaMemsetAsync(sim->species[s].k[m], 0, sizeof(double) * sim->nalloc, sim->stream));
+      }
+      for (size_t i = 0; i < sim->transports.size(); ++i) {
+        std::vector<const double*> u(sim->species.size()), kp(sim->species.size());
+        std::vector<double*> ko(sim->species.size());
+        for (size_t s = 0; s < sim->species.size(); ++s) {
+          u[s] = sim->species[s].u[sim->species[s].cur];
+          kp[s] = m > 0 ? sim->species[s].k[m - 1] : NULL;
+          ko[s] = sim->species[s].k[m];
+        }
+        static const double rk[4] = {0.0, 0.5, 0.5, 1.0};
+        cudaError_t e = sb2_launch_transport(sim->transports[i], sim->g, u.data(), kp.data(), ko.data(), sim->consts, m,
+                                             rk[m] * dt, sim->stream, &sim->launches);
+        if (e != cudaSuccess) return cuda_fail(sim, e, "membrane transport kernels");
+      }
+    }
+  }
+
+  Sb2StageArgs a;
+  auto launch = [&](int rb, int re) -> int {
+    if (re <= rb) return SB2_OK;
+    fill_stage_args(sim, a, m, dt, rb, re);
+    cudaError_t e = sb2_launch_stage(a, sim->stream, &sim->launches);
+    if (e != cudaSuccess) return cuda_fail(sim, e, "stage kernel launch");
+    return SB2_OK;
+  };
+  int rc = SB2_OK;
+  if (phase == 0) rc = launch(own_lo, own_hi);
+  else if (phase == 1) {
+    if (lo_edge) rc = launch(own_lo, own_lo + 1);
+    if (!rc && hi_edge && (own_hi - 1 > own_lo || !lo_edge)) rc = launch(own_hi - 1, own_hi);
+  } else {
+    const int b = own_lo + lo_edge, e = own_hi - hi_edge;
+    if (e > b) rc = launch(b, e);  // (a one-row slab with both neighbours is fully covered by phase 1)
+  }
+  if (rc) return rc;
+
+  if (phase == 0 || phase == 2) {
+    // boundary conditions act after diffusion of the same stage (spatialsimulator.cpp:1476-1478)
+    const bool final = (m == 3 && sim->fuse_combine);
+    if (!final) {
+      std::vector<double*> ko(sim->species.size()), uc(sim->species.size());
+      for (size_t s = 0; s < sim->species.size(); ++s) { ko[s] = sim->species[s].k[m]; uc[s] = sim->species[s].u[sim->species[s].cur]; }
+      cudaError_t e = sb2_apply_boundary(sim->blists, ko.data(), uc.data(), sim->consts, sim->d_fields.data(), sim->carry_k0,
+                                         sim->stream, &sim->launches);
+      if (e != cudaSuccess) return cuda_fail(sim, e, "boundary kernels");
+    }
+  }
+  return SB2_OK;
+}
+
+int sb2_end_step(sb2_sim* sim) {
+  if (!sim || !sim->in_step) return fail(sim, SB2_ERR_STATE, "sb2_end_step without sb2_begin_step");
+  cudaSetDevice(sim->g.device);
+  const double dt = sim->cur_dt;
+  const size_t S = sim->species.size();
+  if (sim->fuse_combine) {
+    for (size_t s = 0; s < S; ++s) sim->species[s].cur ^= 1;
+  } else {
+    // advection between the last stage and the update (spatialsimulator.cpp:1484-1491)
+    for (size_t s = 0; s < S; ++s) {
+      Sb2Species& sp = sim->species[s];
+      if (!sp.has_adv) continue;
+      Sb2CipArgs c;
+      memset(&c, 0, sizeof(c));
+      c.nx = sim->g.nx; c.ny = sim->g.ny; c.nz = sim->g.nz; c.dim = sim->g.dim;
+      c.P = sim->P; c.PL = sim->PL; c.first = sim->first; c.nalloc = sim->nalloc;
+      c.delta[0] = sim->g.dx; c.delta[1] = sim->g.dy; c.delta[2] = sim->g.dz;
+      c.dt = dt;
+      c.u = sp.u[sp.cur];
+      for (int a = 0; a < 3; ++a) {
+        c.faces[a] = sp.faces[a];
+        c.akind[a] = sp.akind[a];
+        c.aconst[a] = sp.akind[a] == SB2_SRC_CONST ? sim->consts[sp.asrc[a]] : 0.0;
+        c.afield[a] = sp.akind[a] == SB2_SRC_FIELD ? sim->d_fields[sp.asrc[a]] : NULL;
+      }
+      c.flags = sim->d_flags[sp.geo];
+      c.tmp_cell = sp.u[sp.cur ^ 1];  // the idle half of the double buffer is scratch here
+      c.tmp_face = sim->d_tmp_face;
+      cudaError_t e = sb2_launch_cip(c, sim->stream, &sim->launches);
+      if (e != cudaSuccess) return cuda_fail(sim, e, "CIP-CSLR advection kernels");
+    }
+    Sb2CombineArgs c;
+    memset(&c, 0, sizeof(c));
+    c.nx = sim->g.nx; c.ny = sim->g.ny; c.nz = sim->g.nz; c.dim = sim->g.dim; c.S = (int)S;
+    c.P = sim->P; c.PL = sim->PL; c.first = sim->first; c.dt = dt;
+    for (size_t s = 0; s < S; ++s) {
+      c.u[s] = sim->species[s].u[sim->species[s].cur];
+      for (int m = 0; m < 4; ++m) c.k[s][m] = sim->species[s].k[m];
+      c.flags[s] = sim->d_flags[sim->species[s].geo];
+    }
+    cudaError_t e = sb2_launch_combine(c, sim->stream, &sim->launches);
+    if (e != cudaSuccess) return cuda_fail(sim, e, "combine kernel launch");
+  }
+  // post-update calcBoundary(m = 0) (spatialsimulator.cpp:1540-1542): Dirichlet values are
+  // re-imposed, Neumann flux is parked in the zeroed k0 and carried into the next step
+  if (sim->blists.n_dirichlet > 0 || sim->carry_k0) {
+    std::vector<double*> k0(S), uc(S);
+    for (size_t s = 0; s < S; ++s) { k0[s] = sim->species[s].k[0]; uc[s] = sim->species[s].u[sim->species[s].cur]; }
+    if (sim->carry_k0)
+      for (size_t s = 0; s < S; ++s) CK(cudaMemsetAsync(k0[s], 0, sizeof(double) * sim->nalloc, sim->stream));
+    cudaError_t e = sb2_apply_boundary(sim->blists, k0.data(), uc.data(), sim->consts, sim->d_fields.data(), sim->carry_k0,
+                                       sim->stream, &sim->launches);
+    if (e != cudaSuccess) return cuda_fail(sim, e, "boundary kernels");
+  }
+  sim->k0_carry_valid = sim->carry_k0;
+  sim->in_step = false;
+  return SB2_OK;
+}
+
+int sb2_step(sb2_sim* sim, double t_arg, double t_incr, double dt, int nsteps, int time_slot) {
+  if (!sim || !sim->finalized) return fail(sim, SB2_ERR_STATE, "simulator not finalized");
+  for (int i = 0; i < nsteps; ++i) {
+    int rc = sb2_begin_step(sim, t_arg + i * t_incr, dt, time_slot);
+    if (rc) return rc;
+    for (int m = 0; m < 4; ++m) if ((rc = sb2_stage(sim, m, 0))) return rc;
+    if ((rc = sb2_end_step(sim))) return rc;
+  }
+  return SB2_OK;
+}
+
+int sb2_download_species(sb2_sim* sim, int species, double* out) {
+  if (!sim || !out || species < 0 || species >= (int)sim->species.size()) return fail(sim, SB2_ERR_ARG, "bad species");
+  cudaSetDevice(sim->g.device);
+  return download_padded<double>(sim, out, sim->species[species].u[sim->species[species].cur]);
+}
+
+int sb2_upload_species(sb2_sim* sim, int species, const double* in) {
+  if (!sim || !in || species < 0 || species >= (int)sim->species.size()) return fail(sim, SB2_ERR_ARG, "bad species");
+  cudaSetDevice(sim->g.device);
+  int rc = upload_interior<double>(sim, sim->species[species].u[sim->species[species].cur], in);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(sim->stream));
+  return SB2_OK;
+}
+
+int sb2_download_stage(sb2_sim* sim, int species, int m, double* out) {
+  if (!sim || !out || species < 0 || species >= (int)sim->species.size() || m < 0 || m > 3) return fail(sim, SB2_ERR_ARG, "bad species / stage");
+  cudaSetDevice(sim->g.device);
+  return download_padded<double>(sim, out, sim->species[species].k[m]);
+}
+
+int sb2_upload_field(sb2_sim* sim, int field, const double* in) {
+  if (!sim || !in || field < 0 || field >= (int)sim->d_fields.size()) return fail(sim, SB2_ERR_ARG, "bad field");
+  cudaSetDevice(sim->g.device);
+  int rc = upload_interior<double>(sim, sim->d_fields[field], in);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(sim->stream));
+  return SB2_OK;
+}
+
+int sb2_upload_faces(sb2_sim* sim, int species, int axis, const double* in) {
+  if (!sim || !in || species < 0 || species >= (int)sim->species.size() || axis < 0 || axis > 2) return fail(sim, SB2_ERR_ARG, "bad species / axis");
+  cudaSetDevice(sim->g.device);
+  Sb2Species& sp = sim->species[species];
+  int rc;
+  if (!sp.faces[axis] && (rc = alloc_field(sim, &sp.faces[axis]))) return rc;
+  if ((rc = upload_interior<double>(sim, sp.faces[axis], in))) return rc;
+  CK(cudaStreamSynchronize(sim->stream));
+  return SB2_OK;
+}
+
+int sb2_download_faces(sb2_sim* sim, int species, int axis, double* out) {
+  if (!sim || !out || species < 0 || species >= (int)sim->species.size() || axis < 0 || axis > 2) return fail(sim, SB2_ERR_ARG, "bad species / axis");
+  if (!sim->species[species].faces[axis]) return fail(sim, SB2_ERR_STATE, "species has no face values along this axis");
+  cudaSetDevice(sim->g.device);
+  return download_padded<double>(sim, out, sim->species[species].faces[axis]);
+}
+
+int sb2_min_dt(sb2_sim* sim, double dt, double* out) {
+  if (!sim || !out || !sim->finalized) return fail(sim, SB2_ERR_STATE, "simulator not finalized");
+  cudaSetDevice(sim->g.device);
+  double best = dt;
+  for (size_t s = 0; s < sim->species.size(); ++s) {
+    Sb2Species& sp = sim->species[s];
+    Sb2MinDtArgs a;
+    memset(&a, 0, sizeof(a));
+    a.nx = sim->g.nx; a.ny = sim->g.ny; a.nz = sim->g.nz; a.dim = sim->g.dim;
+    a.P = sim->P; a.PL = sim->PL; a.first = sim->first;
+    a.delta[0] = sim->g.dx; a.delta[1] = sim->g.dy; a.delta[2] = sim->g.dz;
+    a.dt = dt;
+    a.flags = sim->d_flags[sp.geo];
+    a.has_diff = sp.has_diff; a.has_adv = sp.has_adv;
+    for (int ax = 0; ax < 3; ++ax) {
+      a.dkind[ax] = sp.dkind[ax];
+      a.dconst[ax] = sp.dkind[ax] == SB2_SRC_CONST ? sim->consts[sp.dsrc[ax]] : 0.0;
+      a.dfield[ax] = sp.dkind[ax] == SB2_SRC_FIELD ? sim->d_fields[sp.dsrc[ax]] : NULL;
+      a.akind[ax] = sp.akind[ax];
+      a.aconst[ax] = sp.akind[ax] == SB2_SRC_CONST ? sim->consts[sp.asrc[ax]] : 0.0;
+      a.afield[ax] = sp.akind[ax] == SB2_SRC_FIELD ? sim->d_fields[sp.asrc[ax]] : NULL;
+    }
+    if (!a.has_diff && !a.has_adv) continue;
+    double r = dt;
+    cudaError_t e = sb2_launch_min_dt(a, sim->d_scratch, sim->stream, &sim->launches, &r);
+    if (e != cudaSuccess) return cuda_fail(sim, e, "min-dt reduction");
+    if (r < best) best = r;
+  }
+  *out = best;
+  return SB2_OK;
+}
+
+int sb2_species_view(sb2_sim* sim, int species, int which, sb2_field_view* out) {
+  if (!sim || !out || species < 0 || species >= (int)sim->species.size() || which < 0 || which > 4)
+    return fail(sim, SB2_ERR_ARG, "bad species / selector");
+  Sb2Species& s = sim->species[species];
+  out->ptr = which == 0 ? (void*)s.u[s.cur] : (void*)s.k[which - 1];
+  out->row_pitch = sim->P; out->plane_pitch = sim->PL; out->first_cell = sim->first; out->n_alloc = sim->nalloc;
+  return SB2_OK;
+}
+
+int64_t sb2_launch_count(const sb2_sim* sim) { return sim ? sim->launches : 0; }
+
+int sb2_program_text(sb2_sim* sim, char* buf, int buflen) {
+  if (!sim || !buf || buflen <= 0) return SB2_ERR_ARG;
+  std::ostringstream os;
+  for (size_t i = 0; i < sim->program.size(); ++i) {
+    const uint32_t t = sim->program[i];
+    const uint32_t code = t & 0xffffu;
+    os << kOpcNames[code / SB2_MAX_DEPTH] << " " << (code % SB2_MAX_DEPTH) << " " << (t >> 16) << "\n";
+  }
+  const std::string s = os.str();
+  snprintf(buf, buflen, "%s", s.c_str());
+  return (int)s.size();
+}
+
+}  // extern "C"

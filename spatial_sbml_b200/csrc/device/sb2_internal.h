@@ -1,0 +1,86 @@
+// sb2_internal.h — shared definitions between the C-ABI layer (sb2_device.cu) and the kernels.
+#ifndef SB2_INTERNAL_H_
+#define SB2_INTERNAL_H_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../../include/spatial_b200.h"
+
+// ---------------------------------------------------------------------------------------------
+// Device bytecode.  The host-facing RPN stream (sb2_token) is a stack program whose stack pointer
+// is known statically at every token, so the library resolves it once into register-addressed
+// instructions: code = opcode * SB2_MAX_DEPTH + d, where d is the stack register the instruction
+// acts on.  Every interpreter case then touches r[] with compile-time indices and the expression
+// stack lives in registers.  "operand, binary-op" pairs are fused into one instruction.
+// ---------------------------------------------------------------------------------------------
+enum Sb2Opc {
+  OPC_END = 0,
+  OPC_PUSHC,  // r[d] = consts[arg]
+  OPC_PUSHV,  // r[d] = staged species arg (u + c*dt*k_prev)
+  OPC_PUSHF,  // r[d] = field arg
+  OPC_ADD, OPC_SUB, OPC_MUL, OPC_DIV,         // r[d-1] = r[d-1] op r[d]
+  OPC_GEQ, OPC_GT, OPC_LEQ, OPC_LT, OPC_AND, OPC_OR,
+  OPC_ADDC, OPC_SUBC, OPC_MULC, OPC_DIVC,     // r[d] = r[d] op consts[arg]
+  OPC_GEQC, OPC_GTC, OPC_LEQC, OPC_LTC,
+  OPC_ADDV, OPC_SUBV, OPC_MULV, OPC_DIVV,     // r[d] = r[d] op species arg
+  OPC_UNARY,  // r[d] = f_arg(r[d])
+  OPC_BINR,   // r[d-1] = g_arg(r[d-1], r[d])     (rare binaries: pow, log, xor, eq, neq)
+  OPC_MOV0,   // r[0] = r[d]
+  OPC_MASK,   // statement mask = cell in domain of geo arg
+  OPC_ACCSUB, // acc[d] -= consts[arg] * r[0]   (d = species index here)
+  OPC_ACCADD, // acc[d] += consts[arg] * r[0]
+  OPC_COUNT
+};
+
+#define SB2_CODE(opc, d) ((uint32_t)(opc) * SB2_MAX_DEPTH + (uint32_t)(d))
+
+struct Sb2SpeciesArgs {
+  const double* u;      // current value
+  double* u_out;        // fused combine target (other half of the double buffer)
+  const double* kprev;  // k_{m-1}
+  double* kout;         // k_m
+  const double* k0;     // fused combine inputs
+  const double* k1;
+  int32_t geo;
+  int32_t has_diff;
+  int32_t dkind[3];  // SB2_SRC_*
+  int32_t dsrc[3];
+};
+
+struct Sb2StageArgs {
+  int32_t nx, ny, nz, dim;
+  int64_t P, PL, first;  // row pitch, plane pitch, offset of cell (0,0,0), all in elements
+  int32_t row_begin, row_end;      // rows (2-D: y) or planes (3-D: z) of the slab axis to compute
+  int32_t rows_per_block;
+  int32_t m;       // RK stage 0..3
+  int32_t S, G;
+  int32_t final;   // fused RK combine: write u_out instead of k3
+  int32_t carry;   // accumulate on top of what kout already holds
+  int32_t ntok;
+  double cdt;      // rk[m]*dt
+  double dt;
+  double dx2[3];
+  int32_t divide[3];  // 0 when dx2 == 1.0 exactly (x/1.0 == x, the divide is skipped bit-exactly)
+  Sb2SpeciesArgs sp[SB2_MAX_SPECIES];
+  const uint8_t* flags[SB2_MAX_GEOS];
+  const double* fields[SB2_MAX_FIELDS];
+  uint32_t tok[SB2_MAX_TOKENS];
+  double consts[SB2_MAX_CONSTS];
+};
+
+// launches (implemented in stage_kernel.cu)
+cudaError_t sb2_launch_stage(const Sb2StageArgs& args, cudaStream_t stream, int* launches);
+
+struct Sb2CombineArgs {
+  int32_t nx, ny, nz, dim, S;
+  int64_t P, PL, first;
+  double dt;
+  double* u[SB2_MAX_SPECIES];
+  const double* k[SB2_MAX_SPECIES][4];
+  const uint8_t* flags[SB2_MAX_SPECIES];
+};
+cudaError_t sb2_launch_combine(const Sb2CombineArgs& args, cudaStream_t stream, int* launches);
+
+#endif  // SB2_INTERNAL_H_

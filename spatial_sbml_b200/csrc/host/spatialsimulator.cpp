@@ -1,0 +1,1025 @@
+// spatialsimulator.cpp — SpatialSimulator over the B200 device layer.
+//
+// Public behaviour follows the reference class (SpatialSBML/spatialsimulator.cpp:152-260 and
+// :1236-1783); set-up lives in host_model.cpp; the time step is sb2_step() (include/spatial_b200.h).
+#include "spatialsimulator.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+#include <map>
+#include <sstream>
+#include <stdexcept>
+
+#include "../../../include/spatial_b200.h"
+#include "host_model.h"
+
+using sb2host::Geo;
+using sb2host::MemPoint;
+using sb2host::Rpn;
+using sb2host::Rxn;
+using sb2host::Tok;
+using sb2host::Var;
+
+namespace {
+
+const int kSlabHalo = 2;  // rows / planes of neighbouring slabs whose masks are known locally
+
+struct VarMirror {
+  std::vector<double> data;  // doubled grid
+  bool handedOut;
+  VarMirror() : handedOut(false) {}
+};
+
+int opOfAst(int t) {
+  switch (t) {
+    case AST_PLUS: return SB2_OP_PLUS;
+    case AST_MINUS: return SB2_OP_MINUS;
+    case AST_TIMES: return SB2_OP_TIMES;
+    case AST_DIVIDE: return SB2_OP_DIVIDE;
+    case AST_POWER:
+    case AST_FUNCTION_POWER: return SB2_OP_POWER;
+    case AST_FUNCTION_LOG: return SB2_OP_LOG;
+    case AST_LOGICAL_AND: return SB2_OP_AND;
+    case AST_LOGICAL_OR: return SB2_OP_OR;
+    case AST_LOGICAL_XOR: return SB2_OP_XOR;
+    case AST_RELATIONAL_EQ: return SB2_OP_EQ;
+    case AST_RELATIONAL_GEQ: return SB2_OP_GEQ;
+    case AST_RELATIONAL_GT: return SB2_OP_GT;
+    case AST_RELATIONAL_LEQ: return SB2_OP_LEQ;
+    case AST_RELATIONAL_LT: return SB2_OP_LT;
+    case AST_RELATIONAL_NEQ: return SB2_OP_NEQ;
+    case AST_FUNCTION_ABS: return SB2_OP_ABS;
+    case AST_FUNCTION_ARCCOS: return SB2_OP_ARCCOS;
+    case AST_FUNCTION_ARCCOSH: return SB2_OP_ARCCOSH;
+    case AST_FUNCTION_ARCCSC: return SB2_OP_ARCCSC;
+    case AST_FUNCTION_ARCSIN: return SB2_OP_ARCSIN;
+    case AST_FUNCTION_ARCTAN: return SB2_OP_ARCTAN;
+    case AST_FUNCTION_COS: return SB2_OP_COS;
+    case AST_FUNCTION_COSH: return SB2_OP_COSH;
+    case AST_FUNCTION_CSC: return SB2_OP_CSC;
+    case AST_FUNCTION_EXP: return SB2_OP_EXP;
+    case AST_FUNCTION_LN: return SB2_OP_LN;
+    case AST_FUNCTION_ROOT: return SB2_OP_ROOT;
+    case AST_FUNCTION_SIN: return SB2_OP_SIN;
+    case AST_FUNCTION_SINH: return SB2_OP_SINH;
+    case AST_FUNCTION_TAN: return SB2_OP_TAN;
+    case AST_FUNCTION_TANH: return SB2_OP_TANH;
+    case AST_LOGICAL_NOT: return SB2_OP_NOT;
+    default: return SB2_OP_POP_ONLY;  // listed-but-empty cases of the reference interpreter
+  }
+}
+
+}  // namespace
+
+struct SimImpl {
+  sb2host::Model m;
+  SBMLDocument* ownedDoc;
+  sb2_sim* dev;
+  std::vector<double> consts;
+  std::map<uint64_t, int> literalSlot;
+  int timeSlot;
+  std::vector<Var*> staged;     // device species id → variable
+  std::vector<Var*> fieldVars;  // device field id → variable
+  std::vector<char> stale;      // per staged species: device state is newer than Var::field
+  std::map<std::string, VarMirror> varMirrors;
+  std::map<std::string, std::vector<int> > geoMirrors, boundaryMirrors;
+  std::map<std::string, std::vector<boundaryType> > btMirrors;
+  int ownLo, ownHi, heldLo;  // slab rows (global) owned / first row held locally
+  long domainCells;
+  SimImpl() : ownedDoc(NULL), dev(NULL), timeSlot(-1), ownLo(0), ownHi(0), heldLo(0), domainCells(0) {}
+  ~SimImpl() {
+    if (dev) sb2_destroy(dev);
+    delete ownedDoc;
+  }
+
+  int constSlotOf(Var* v) {
+    if (v->constSlot < 0) {
+      v->constSlot = (int)consts.size();
+      consts.push_back(v->uniformValue);
+    }
+    return v->constSlot;
+  }
+  int literalSlotOf(double x) {
+    uint64_t bits;
+    memcpy(&bits, &x, sizeof(bits));
+    std::map<uint64_t, int>::const_iterator it = literalSlot.find(bits);
+    if (it != literalSlot.end()) return it->second;
+    const int s = (int)consts.size();
+    consts.push_back(x);
+    literalSlot[bits] = s;
+    return s;
+  }
+  // doubled-grid coordinate value (setInfoFunction.cpp:308): min + C*delta/2.0
+  double coordinateAt(const Var* v, int C) const {
+    const double delta = v == m.xVar ? m.deltaX : v == m.yVar ? m.deltaY : m.deltaZ;
+    return v->offGridInit + (double)C * delta / 2.0;
+  }
+  bool isCoordinate(const Var* v) const { return v && (v == m.xVar || v == m.yVar || v == m.zVar); }
+};
+
+// =============================================================================================
+// construction / initialisation
+// =============================================================================================
+SpatialSimulator::SpatialSimulator()
+    : Xdiv(100), Ydiv(100), Zdiv(1), impl(NULL), deviceOrdinal(0), externalStream(NULL), hostOnly(false), slabLo(0), slabHi(0) {}
+
+SpatialSimulator::SpatialSimulator(SBMLDocument* doc, int xdim, int ydim, int zdim)
+    : Xdiv(xdim), Ydiv(ydim), Zdiv(zdim), impl(NULL), deviceOrdinal(0), externalStream(NULL), hostOnly(false), slabLo(0), slabHi(0) {
+  initFromModel(doc, xdim, ydim, zdim);
+}
+
+SpatialSimulator::~SpatialSimulator() { clear(); }
+
+void SpatialSimulator::clear() {
+  delete impl;
+  impl = NULL;
+}
+
+void SpatialSimulator::initFromFile(const std::string& fileName, int xdim, int ydim, int zdim) {
+  SBMLDocument* doc = readSBMLFromFile(fileName.c_str());
+  if (!doc || !doc->getModel()) {
+    clear();
+    lastError = "cannot read SBML file '" + fileName + "'";
+    delete doc;
+    return;
+  }
+  initFromModel(doc, xdim, ydim, zdim);
+  if (impl) impl->ownedDoc = doc; else delete doc;
+}
+
+void SpatialSimulator::initFromString(const std::string& sbml, int xdim, int ydim, int zdim) {
+  SBMLDocument* doc = readSBMLFromString(sbml.c_str());
+  if (!doc || !doc->getModel()) {
+    clear();
+    lastError = "cannot parse the SBML string";
+    delete doc;
+    return;
+  }
+  initFromModel(doc, xdim, ydim, zdim);
+  if (impl) impl->ownedDoc = doc; else delete doc;
+}
+
+void SpatialSimulator::initFromModel(SBMLDocument* doc, int xdim, int ydim, int zdim) {
+  SBMLDocument* keep = NULL;
+  if (impl && impl->ownedDoc == doc) { keep = impl->ownedDoc; impl->ownedDoc = NULL; }  // re-init on our own document
+  clear();
+  lastError.clear();
+  impl = new SimImpl;
+  impl->ownedDoc = keep;
+  int heldLo = 0, heldHi = 0;
+  if (slabHi > slabLo) {
+    // which rows are held: the owned ones plus kSlabHalo rows of each neighbouring slab
+    SpatialModelPlugin* mp = doc && doc->getModel() ? static_cast<SpatialModelPlugin*>(doc->getModel()->getPlugin("spatial")) : NULL;
+    const int dim = mp && mp->getGeometry() ? (int)mp->getGeometry()->getNumCoordinateComponents() : 0;
+    const int n = dim == 3 ? zdim : ydim;
+    heldLo = slabLo - kSlabHalo < 0 ? 0 : slabLo - kSlabHalo;
+    heldHi = slabHi + kSlabHalo > n ? n : slabHi + kSlabHalo;
+    if (slabLo == 0 && slabHi == n) { heldLo = 0; heldHi = 0; }
+  }
+  if (!impl->m.build(doc, xdim, ydim, zdim, heldLo, heldHi)) {
+    lastError = impl->m.error;
+    SBMLDocument* d = impl->ownedDoc;
+    impl->ownedDoc = NULL;
+    clear();
+    delete d;
+    return;
+  }
+  impl->heldLo = impl->m.isSlab() ? heldLo : 0;
+  impl->ownLo = impl->m.isSlab() ? slabLo : 0;
+  impl->ownHi = impl->m.isSlab() ? slabHi : 0;
+  Xdiv = impl->m.gn[0];
+  Ydiv = impl->m.gn[1];
+  Zdiv = impl->m.gn[2];
+  if (!hostOnly && !buildDevice()) {
+    // keep the host model for inspection, but there is no device → oneStep() will throw
+    if (impl->dev) { sb2_destroy(impl->dev); impl->dev = NULL; }
+  }
+}
+
+bool SpatialSimulator::isInitialized() const { return impl != NULL && (hostOnly || impl->dev != NULL); }
+const std::string& SpatialSimulator::getLastError() const { return lastError; }
+void SpatialSimulator::setDevice(int ordinal) { deviceOrdinal = ordinal; }
+void SpatialSimulator::setHostOnly(bool h) { hostOnly = h; }
+void SpatialSimulator::setSlab(int lo, int hi) { slabLo = lo; slabHi = hi; }
+void SpatialSimulator::setCudaStream(void* stream) {
+  externalStream = stream;
+  if (impl && impl->dev) sb2_set_stream(impl->dev, stream);
+}
+void* SpatialSimulator::getDeviceHandle() { return impl ? impl->dev : NULL; }
+const Model* SpatialSimulator::getModel() const { return impl ? impl->m.model : NULL; }
+int SpatialSimulator::runOldMain(int, const char*[]) { return -1; }
+void SpatialSimulator::setGnuplotExecutable(const std::string& location) { gnuplotExecutable = location; }
+const std::string& SpatialSimulator::getGnuplotExecutable() const { return gnuplotExecutable; }
+
+// =============================================================================================
+// host model → device program (C ABI calls only)
+// =============================================================================================
+#define DEV(call)                                                                                     \
+  do {                                                                                                \
+    int rc__ = (call);                                                                                \
+    if (rc__ < 0) {                                                                                   \
+      lastError = std::string(#call) + ": " + sb2_last_error(impl->dev);                              \
+      return false;                                                                                   \
+    }                                                                                                 \
+  } while (0)
+
+bool SpatialSimulator::buildDevice() {
+  sb2host::Model& m = impl->m;
+  if (m.dimension != 2 && m.dimension != 3) {
+    lastError = "the device step supports 2-D and 3-D geometries (this model has " + std::to_string(m.dimension) + " coordinate components)";
+    return false;
+  }
+  if (!m.orderedAssignmentRules.empty()) {
+    lastError = "assignment rules re-evaluated every step are not supported on the device yet";
+    return false;
+  }
+  sb2_grid g;
+  memset(&g, 0, sizeof(g));
+  g.nx = m.nx; g.ny = m.ny; g.nz = m.nz; g.dim = m.dimension;
+  g.dx = m.deltaX; g.dy = m.deltaY; g.dz = m.deltaZ;
+  g.device = deviceOrdinal;
+  if (m.isSlab()) {
+    g.own_lo = impl->ownLo - impl->heldLo;
+    g.own_hi = impl->ownHi - impl->heldLo;
+    g.row0 = impl->heldLo;
+  }
+  int rc = sb2_create(&g, &impl->dev);
+  if (rc < 0) {
+    lastError = std::string("sb2_create: ") + sb2_last_error(NULL);
+    impl->dev = NULL;
+    return false;
+  }
+  if (externalStream) sb2_set_stream(impl->dev, externalStream);
+
+  // --- staged species and the geometries that host them -----------------------------------------
+  auto deviceGeoOf = [&](Geo* geo) -> int {
+    if (geo->deviceGeo >= 0) return geo->deviceGeo;
+    geo->deviceGeo = sb2_add_geometry(impl->dev, geo->flags.data());
+    return geo->deviceGeo;
+  };
+  for (unsigned int i = 0; i < m.model->getNumSpecies(); ++i) {
+    Var* v = m.findVar(m.model->getSpecies(i)->getId());
+    if (!v || v->sp != m.model->getSpecies(i) || v->isUniform || !v->hasValue) continue;
+    if (!v->geo) continue;  // no geometry for its compartment: the reference never touches it
+    if (!v->geo->isVol) {
+      lastError = "species '" + v->id + "' lives in a membrane compartment; membrane species are not supported on the device yet";
+      return false;
+    }
+    if (!v->hasDelta) continue;  // constant spatial species: a read-only field
+    if (!v->geo->hasMask) continue;
+    const int dg = deviceGeoOf(v->geo);
+    if (dg < 0) { lastError = std::string("sb2_add_geometry: ") + sb2_last_error(impl->dev); return false; }
+    const int id = sb2_add_species(impl->dev, dg, v->field.data());
+    if (id < 0) { lastError = std::string("sb2_add_species: ") + sb2_last_error(impl->dev); return false; }
+    v->speciesId = id;
+    impl->staged.push_back(v);
+    impl->stale.push_back(0);
+  }
+  impl->domainCells = 0;
+  {
+    std::vector<char> counted(m.geos.size(), 0);
+    for (size_t s = 0; s < impl->staged.size(); ++s)
+      for (size_t gi = 0; gi < m.geos.size(); ++gi)
+        if (m.geos[gi] == impl->staged[s]->geo && !counted[gi]) {
+          counted[gi] = 1;
+          if (!m.isSlab()) impl->domainCells += (long)m.geos[gi]->nDomain;
+          else {
+            // owned rows only
+            const int axis = m.dimension == 3 ? 2 : 1;
+            const int64_t rowCells = axis == 1 ? m.nx : (int64_t)m.nx * m.ny;
+            const int lo = impl->ownLo - impl->heldLo, hi = impl->ownHi - impl->heldLo;
+            for (int64_t c = (int64_t)lo * rowCells; c < (int64_t)hi * rowCells; ++c) impl->domainCells += m.geos[gi]->isDomain[c] == 1;
+          }
+        }
+  }
+
+  auto fieldIdOf = [&](Var* v) -> int {
+    if (v->fieldId >= 0) return v->fieldId;
+    v->fieldId = sb2_add_field(impl->dev, v->field.data());
+    if (v->fieldId >= 0) impl->fieldVars.push_back(v);
+    return v->fieldId;
+  };
+  // source descriptor of a coefficient variable (uniform → constants table, field → device field)
+  auto sourceOf = [&](Var* c, int& kind, int& src) -> bool {
+    kind = SB2_SRC_NONE; src = 0;
+    if (!c || !c->hasValue) return true;
+    if (c->isUniform) { kind = SB2_SRC_CONST; src = impl->constSlotOf(c); return true; }
+    if (c->speciesId >= 0) { lastError = "coefficient '" + c->id + "' is an integrated species (unsupported)"; return false; }
+    kind = SB2_SRC_FIELD;
+    src = fieldIdOf(c);
+    if (src < 0) { lastError = std::string("sb2_add_field: ") + sb2_last_error(impl->dev); return false; }
+    return true;
+  };
+
+  // --- transport terms (performStep, spatialsimulator.cpp:1464-1491) -----------------------------
+  for (size_t s = 0; s < impl->staged.size(); ++s) {
+    Var* v = impl->staged[s];
+    if (!v->isResolved) continue;
+    int kind, src;
+    if (v->hasDiff)
+      for (int a = 0; a < 3; ++a) {
+        if (!v->diffC[a]) continue;
+        if (!sourceOf(v->diffC[a], kind, src)) return false;
+        if (kind != SB2_SRC_NONE) DEV(sb2_set_diffusion(impl->dev, v->speciesId, a, kind, src));
+      }
+    if (v->hasBC)
+      for (int k = 0; k < 6; ++k) {
+        if (!v->bc[k] || v->bcKind[k] == SB2_BC_NONE) continue;
+        if (!sourceOf(v->bc[k], kind, src)) return false;
+        if (kind != SB2_SRC_NONE) DEV(sb2_set_boundary(impl->dev, v->speciesId, k, v->bcKind[k], kind, src));
+      }
+    if (v->hasAdv) {
+      if (m.isSlab()) { lastError = "advection is not supported on a sharded grid yet"; return false; }
+      for (int a = 0; a < 3; ++a) {
+        if (!v->advC[a]) continue;
+        if (!sourceOf(v->advC[a], kind, src)) return false;
+        if (kind != SB2_SRC_NONE) DEV(sb2_set_advection(impl->dev, v->speciesId, a, kind, src));
+      }
+      // CIP face point values = the odd doubled-grid points of the species array (calcPDE.cpp:588-603)
+      std::vector<double> faces((size_t)m.ncells(), v->offGridInit);
+      for (int a = 0; a < m.dimension; ++a) DEV(sb2_upload_faces(impl->dev, v->speciesId, a, faces.data()));
+    }
+  }
+
+  // --- kinetic laws → token streams --------------------------------------------------------------
+  auto toDeviceTokens = [&](const Rpn& rpn, std::vector<sb2_token>& out) -> bool {
+    out.clear();
+    for (size_t i = 0; i < rpn.size(); ++i) {
+      const Tok& t = rpn[i];
+      sb2_token d;
+      d.kind = SB2_TOK_NOP; d.op = 0; d.slot = 0;
+      switch (t.kind) {
+        case Tok::OP: d.kind = SB2_TOK_OP; d.op = (uint8_t)opOfAst(t.astType); break;
+        case Tok::LITERAL: d.kind = SB2_TOK_CONST; d.slot = (uint16_t)impl->literalSlotOf(t.literal); break;
+        case Tok::CONSTVAR: d.kind = SB2_TOK_CONST; d.slot = (uint16_t)impl->constSlotOf(t.var); break;
+        case Tok::VAR:
+          if (t.var->speciesId >= 0) { d.kind = SB2_TOK_VAR; d.slot = (uint16_t)t.var->speciesId; }
+          else {
+            const int f = fieldIdOf(t.var);
+            if (f < 0) { lastError = std::string("sb2_add_field: ") + sb2_last_error(impl->dev); return false; }
+            d.kind = SB2_TOK_FIELD; d.slot = (uint16_t)f;
+          }
+          break;
+        default: break;
+      }
+      out.push_back(d);
+    }
+    return true;
+  };
+  auto toDeviceRefs = [&](const Rxn* x, std::vector<sb2_ref>& out) {
+    out.clear();
+    for (size_t k = 0; k < x->spRefs.size(); ++k) {
+      sb2_ref r;
+      Var* v = x->spRefs[k];
+      r.species = (v && !v->isUniform && v->speciesId >= 0) ? v->speciesId : -1;
+      r.is_variable = x->isVariable[k] ? 1 : 0;
+      r.stoichiometry = x->stoichiometry[k];
+      out.push_back(r);
+    }
+  };
+
+  std::vector<sb2_token> toks;
+  std::vector<sb2_ref> refs;
+  for (size_t i = 0; i < m.rxns.size(); ++i) {
+    Rxn* x = m.rxns[i];
+    if (!x->reaction) continue;  // rate-rule entries are dispatched below (spatialsimulator.cpp:1376-1377)
+    if (!x->isMemTransport) {
+      Geo* geo = NULL;
+      for (size_t k = 0; k < x->spRefs.size(); ++k)
+        if (x->spRefs[k] && x->spRefs[k]->geo) { geo = x->spRefs[k]->geo; break; }
+      if (!geo) continue;  // every participant is uniform: the reference changes nothing
+      if (!geo->isVol || !geo->hasMask) { lastError = "reaction '" + x->id + "' takes place on a membrane (unsupported)"; return false; }
+      const int dg = deviceGeoOf(geo);
+      if (dg < 0) { lastError = std::string("sb2_add_geometry: ") + sb2_last_error(impl->dev); return false; }
+      if (!toDeviceTokens(x->rpn, toks)) return false;
+      toDeviceRefs(x, refs);
+      DEV(sb2_add_reaction(impl->dev, dg, 0, toks.data(), (int)toks.size(), refs.data(), (int)refs.size(), x->nReactants));
+    } else {
+      if (m.isSlab()) { lastError = "membrane transport is not supported on a sharded grid yet"; return false; }
+      if (!addMemTransport(x)) return false;
+    }
+  }
+  // rate rules: the reference evaluates rInfoList[<rule index>] on the rule variable's domain
+  // (spatialsimulator.cpp:1455-1461) — with no reactions in the model that is the rule itself
+  for (unsigned int i = 0; i < m.model->getNumRules(); ++i) {
+    Rule* rule = m.model->getRule(i);
+    if (!rule->isRate()) continue;
+    Var* target = m.findVar(rule->getVariable());
+    if (i >= m.rxns.size()) { lastError = "rate rule '" + rule->getVariable() + "': the reference indexes its reaction list out of range here"; return false; }
+    if (!target || !target->geo) continue;
+    if (!target->geo->isVol || !target->geo->hasMask) { lastError = "rate rule on a membrane variable (unsupported)"; return false; }
+    Rxn* x = m.rxns[i];
+    const int dg = deviceGeoOf(target->geo);
+    if (dg < 0) { lastError = std::string("sb2_add_geometry: ") + sb2_last_error(impl->dev); return false; }
+    if (!toDeviceTokens(x->rpn, toks)) return false;
+    toDeviceRefs(x, refs);
+    DEV(sb2_add_reaction(impl->dev, dg, 1, toks.data(), (int)toks.size(), refs.data(), (int)refs.size(), 1));
+  }
+
+  if (m.tVar->constSlot >= 0) impl->timeSlot = m.tVar->constSlot;
+  if (!impl->consts.empty()) DEV(sb2_set_constants(impl->dev, impl->consts.data(), (int)impl->consts.size()));
+  DEV(sb2_finalize(impl->dev));
+  return true;
+}
+
+// calcMemTransport call site (spatialsimulator.cpp:1393-1451) + per-point tables (calcPDE.cpp:1056-1479)
+bool SpatialSimulator::addMemTransport(void* rx) {
+  Rxn* x = static_cast<Rxn*>(rx);
+  sb2host::Model& m = impl->m;
+  Reaction* r = x->reaction;
+  if (r->getNumReactants() == 0 || r->getNumProducts() == 0) return true;
+  auto geoOfSpecies = [&](const std::string& sid) -> Geo* {
+    Var* v = m.findVar(sid);
+    if (v && v->geo) return v->geo;
+    Species* s = m.model->getSpecies(sid);
+    if (!s) return NULL;
+    for (unsigned int i = 0; i < m.model->getNumSpecies(); ++i) {
+      Species* cur = m.model->getSpecies(i);
+      if (cur->getId() != sid && cur->getCompartment() == s->getCompartment()) {
+        Var* cv = m.findVar(cur->getId());
+        if (cv && cv->geo) return cv->geo;
+      }
+    }
+    return NULL;
+  };
+  Geo* reactantGeo = geoOfSpecies(r->getReactant(0)->getSpecies());
+  Geo* productGeo = geoOfSpecies(r->getProduct(0)->getSpecies());
+  const bool haveRV = reactantGeo && reactantGeo->isVol, havePV = productGeo && productGeo->isVol;
+  if (haveRV != havePV) {
+    lastError = "reaction '" + x->id + "' binds a volume species to a membrane species (unsupported)";
+    return false;
+  }
+  Geo* mem = NULL;
+  for (size_t j = 0; j < m.geos.size(); ++j) {
+    Geo* g = m.geos[j];
+    if (g->isVol) continue;
+    if ((g->adjacent1 == reactantGeo && g->adjacent2 == productGeo) || (g->adjacent1 == productGeo && g->adjacent2 == reactantGeo)) { mem = g; break; }
+  }
+  if (!mem) return true;  // no membrane between the two compartments: nothing happens
+
+  const int Xi = m.Xindex, Yi = m.Yindex, Zi = m.Zindex;
+  const int64_t N = m.ndoubled();
+  // participating points: listed in domainIndex, off the frame, isDomain == 1
+  std::vector<const MemPoint*> pts;
+  std::map<int64_t, const MemPoint*> pointOf;
+  for (size_t k = 0; k < mem->memPoints.size(); ++k) pointOf[mem->memPoints[k].index] = &mem->memPoints[k];
+  for (size_t k = 0; k < mem->memDomainIndex.size(); ++k) {
+    const int64_t idx = mem->memDomainIndex[k];
+    const int Z = (int)(idx / ((int64_t)Xi * Yi)), Y = (int)((idx - (int64_t)Z * Xi * Yi) / Xi), X = (int)(idx - (int64_t)Z * Xi * Yi - (int64_t)Y * Xi);
+    if (m.dimension == 3 && (X == 0 || Y == 0 || Z == 0 || X == Xi - 1 || Y == Yi - 1 || Z == Zi - 1)) continue;
+    if (m.dimension == 2 && (X == 0 || Y == 0 || X == Xi - 1 || Y == Yi - 1)) continue;
+    std::map<int64_t, const MemPoint*>::const_iterator it = pointOf.find(idx);
+    if (it == pointOf.end()) continue;  // isDomain[index] != 1
+    pts.push_back(it->second);
+  }
+  const int npts = (int)pts.size();
+  // compact cell of a doubled-grid point, -1 unless it is a volume cell of `geo`
+  auto cellIn = [&](Geo* geo, int X, int Y, int Z) -> int32_t {
+    if (!geo || !geo->isVol || !geo->hasMask) return -1;
+    if (X < 0 || Y < 0 || Z < 0 || X >= Xi || Y >= Yi || Z >= Zi) return -1;
+    if ((X | Y | Z) & 1) return -1;
+    const int64_t c = ((int64_t)(Z / 2) * m.ny + Y / 2) * m.nx + X / 2;
+    return geo->isDomain[c] == 1 ? (int32_t)c : -1;
+  };
+
+  std::vector<sb2_token> toks;
+  std::vector<int32_t> operandCells;
+  std::vector<double> operandValues;
+  Var* symbol = NULL;  // persists across tokens like the reference's symbolInfo
+  for (size_t i = 0; i < x->rpn.size(); ++i) {
+    const Tok& t = x->rpn[i];
+    sb2_token d;
+    d.kind = SB2_TOK_NOP; d.op = 0; d.slot = 0;
+    if (t.kind == Tok::OP) { d.kind = SB2_TOK_OP; d.op = (uint8_t)opOfAst(t.astType); }
+    else if (t.kind == Tok::LITERAL) { d.kind = SB2_TOK_CONST; d.slot = (uint16_t)impl->literalSlotOf(t.literal); }
+    else if (t.kind == Tok::CONSTVAR) { d.kind = SB2_TOK_CONST; d.slot = (uint16_t)impl->constSlotOf(t.var); }
+    else if (t.kind == Tok::VAR && t.var->hasDelta && t.var->speciesId >= 0) {
+      for (size_t j = 0; j < x->spRefs.size(); ++j)
+        if (x->spRefs[j] == t.var) { symbol = x->spRefs[j]; break; }
+      if (!symbol || !symbol->geo) { lastError = "membrane transport '" + x->id + "': operand '" + t.var->id + "' has no geometry"; return false; }
+      if (!symbol->geo->isVol) { lastError = "membrane transport '" + x->id + "' reads a membrane species (unsupported)"; return false; }
+      d.kind = SB2_TOK_VAR; d.slot = (uint16_t)t.var->speciesId;
+      for (int p = 0; p < npts; ++p) {
+        const MemPoint& mp = *pts[p];
+        int32_t nearC = -1, farC = -1;
+        const int dX[3] = {1, 0, 0}, dY[3] = {0, 1, 0}, dZ[3] = {0, 0, 1};
+        for (int a = 0; a < m.dimension; ++a) {  // later axes overwrite earlier ones
+          int32_t c = cellIn(symbol->geo, mp.X + dX[a], mp.Y + dY[a], mp.Z + dZ[a]);
+          int sgn = 1;
+          if (c < 0) { c = cellIn(symbol->geo, mp.X - dX[a], mp.Y - dY[a], mp.Z - dZ[a]); sgn = -1; }
+          if (c < 0) continue;
+          nearC = c;
+          const int64_t flat3 = mp.index + sgn * 3 * (a == 0 ? 1 : a == 1 ? (int64_t)Xi : (int64_t)Xi * Yi);
+          farC = -1;
+          if (flat3 < N && flat3 >= 0) {
+            // flat-index arithmetic as in the reference: a wrapped index lands on a non-cell point
+            const int Z3 = (int)(flat3 / ((int64_t)Xi * Yi)), Y3 = (int)((flat3 - (int64_t)Z3 * Xi * Yi) / Xi), X3 = (int)(flat3 - (int64_t)Z3 * Xi * Yi - (int64_t)Y3 * Xi);
+            farC = cellIn(symbol->geo, X3, Y3, Z3);
+          }
+        }
+        operandCells.push_back(nearC);
+        operandCells.push_back(farC);
+      }
+    } else if (t.kind == Tok::VAR) {
+      // no delta array: the raw value at the membrane point itself (calcPDE.cpp:1218-1221)
+      d.kind = SB2_TOK_FIELD; d.slot = 0;
+      for (int p = 0; p < npts; ++p) {
+        const MemPoint& mp = *pts[p];
+        double val = t.var->offGridInit;
+        if (impl->isCoordinate(t.var)) val = impl->coordinateAt(t.var, t.var == m.xVar ? mp.X : t.var == m.yVar ? mp.Y : mp.Z);
+        operandValues.push_back(val);
+      }
+    }
+    toks.push_back(d);
+  }
+  // operand_cells is laid out [VAR token][point][2]; the loop above appended in exactly that order
+  std::vector<sb2_ref> refs;
+  std::vector<int32_t> targets;
+  std::vector<sb2_mem_point> dpts(npts);
+  for (int p = 0; p < npts; ++p) {
+    const MemPoint& mp = *pts[p];
+    const int axis = (mp.bof & (SB2_F_XP | SB2_F_XM)) ? 0 : (mp.bof & (SB2_F_YP | SB2_F_YM)) ? 1 : 2;
+    dpts[p].axis = axis;
+    dpts[p].abs_normal = fabs(axis == 0 ? mp.nx : axis == 1 ? mp.ny : mp.nz);
+  }
+  for (size_t k = 0; k < x->spRefs.size(); ++k) {
+    sb2_ref rr;
+    Var* v = x->spRefs[k];
+    const bool ok = v && !v->isUniform && v->speciesId >= 0 && v->geo && v->geo->isVol;
+    rr.species = ok ? v->speciesId : -1;
+    rr.is_variable = x->isVariable[k] ? 1 : 0;
+    rr.stoichiometry = x->stoichiometry[k];
+    refs.push_back(rr);
+    for (int p = 0; p < npts; ++p) {
+      const MemPoint& mp = *pts[p];
+      const int a = dpts[p].axis;
+      const int dx = a == 0, dy = a == 1, dz = a == 2;
+      targets.push_back(ok ? cellIn(v->geo, mp.X + dx, mp.Y + dy, mp.Z + dz) : -1);
+      targets.push_back(ok ? cellIn(v->geo, mp.X - dx, mp.Y - dy, mp.Z - dz) : -1);
+    }
+  }
+  int rc = sb2_add_mem_transport(impl->dev, toks.data(), (int)toks.size(), refs.data(), (int)refs.size(), x->nReactants,
+                                 dpts.data(), npts, operandCells.empty() ? NULL : operandCells.data(),
+                                 operandValues.empty() ? NULL : operandValues.data(), targets.empty() ? NULL : targets.data());
+  if (rc < 0) { lastError = std::string("sb2_add_mem_transport: ") + sb2_last_error(impl->dev); return false; }
+  return true;
+}
+
+// =============================================================================================
+// stepping
+// =============================================================================================
+void SpatialSimulator::syncBeforeStep() {
+  sb2host::Model& m = impl->m;
+  // values written through a pointer handed out by getVariable()
+  for (std::map<std::string, VarMirror>::iterator it = impl->varMirrors.begin(); it != impl->varMirrors.end(); ++it) {
+    if (!it->second.handedOut) continue;
+    Var* v = m.findVar(it->first);
+    if (!v || v->isUniform || m.isSlab()) continue;
+    if (v->speciesId >= 0 && impl->stale[v->speciesId]) continue;  // mirror was not refreshed since the last step
+    bool changed = false;
+    const double* d = it->second.data.data();
+    for (int k = 0; k < m.nz; ++k)
+      for (int j = 0; j < m.ny; ++j) {
+        const double* row = d + (int64_t)(2 * k) * m.Yindex * m.Xindex + (int64_t)(2 * j) * m.Xindex;
+        double* f = v->field.data() + ((int64_t)k * m.ny + j) * m.nx;
+        for (int i = 0; i < m.nx; ++i)
+          if (memcmp(&row[2 * i], &f[i], sizeof(double)) != 0) { f[i] = row[2 * i]; changed = true; }
+      }
+    if (changed) {
+      if (v->speciesId >= 0) sb2_upload_species(impl->dev, v->speciesId, v->field.data());
+      else if (v->fieldId >= 0) sb2_upload_field(impl->dev, v->fieldId, v->field.data());
+    }
+  }
+  // uniform variables alias the constants table (astFunction.cpp:76-81)
+  for (size_t i = 0; i < m.vars.size(); ++i) {
+    Var* v = m.vars[i];
+    if (v->constSlot < 0 || v == m.tVar) continue;
+    if (memcmp(&impl->consts[v->constSlot], &v->uniformValue, sizeof(double)) != 0) {
+      impl->consts[v->constSlot] = v->uniformValue;
+      sb2_set_constant(impl->dev, v->constSlot, v->uniformValue);
+    }
+  }
+}
+
+double SpatialSimulator::oneStep(double initialTime, double step) {
+  if (!impl || !impl->dev)
+    throw std::runtime_error("SpatialSimulator::oneStep: no device simulator (" + (lastError.empty() ? std::string("not initialised") : lastError) +
+                             "); there is no CPU fallback");
+  syncBeforeStep();
+  impl->m.simTime = initialTime * step;
+  impl->m.tVar->uniformValue = impl->m.simTime;
+  const int rc = sb2_step(impl->dev, initialTime, 0.0, step, 1, impl->timeSlot);
+  if (rc < 0) {
+    lastError = std::string("sb2_step: ") + sb2_last_error(impl->dev);
+    throw std::runtime_error(lastError);
+  }
+  for (size_t s = 0; s < impl->stale.size(); ++s) impl->stale[s] = 1;
+  return initialTime + step;
+}
+
+void SpatialSimulator::runSteps(double firstStepIndex, double step, int nsteps) {
+  if (!impl || !impl->dev)
+    throw std::runtime_error("SpatialSimulator::runSteps: no device simulator (" + (lastError.empty() ? std::string("not initialised") : lastError) +
+                             "); there is no CPU fallback");
+  if (nsteps <= 0) return;
+  syncBeforeStep();
+  const int rc = sb2_step(impl->dev, firstStepIndex, 1.0, step, nsteps, impl->timeSlot);
+  if (rc < 0) {
+    lastError = std::string("sb2_step: ") + sb2_last_error(impl->dev);
+    throw std::runtime_error(lastError);
+  }
+  impl->m.simTime = (firstStepIndex + nsteps - 1) * step;
+  impl->m.tVar->uniformValue = impl->m.simTime;
+  for (size_t s = 0; s < impl->stale.size(); ++s) impl->stale[s] = 1;
+}
+
+// spatialsimulator.cpp:1667-1703 without the gnuplot pipe
+void SpatialSimulator::run(double endTime, double step) {
+  const int last = static_cast<int>(endTime / step);
+  int percent = 0;
+  for (int t = 0; t <= last; ++t) {
+    oneStep(t, step);
+    if (t == (last / 10) * percent) {
+      std::cout << percent * 10 << "% finished" << std::endl;
+      ++percent;
+    }
+  }
+}
+
+double SpatialSimulator::getStableTimeStep(double dt) {
+  if (!impl || !impl->dev) throw std::runtime_error("SpatialSimulator::getStableTimeStep: no device simulator; there is no CPU fallback");
+  syncBeforeStep();
+  double out = dt;
+  if (sb2_min_dt(impl->dev, dt, &out) < 0) {
+    lastError = std::string("sb2_min_dt: ") + sb2_last_error(impl->dev);
+    throw std::runtime_error(lastError);
+  }
+  return out;
+}
+
+// =============================================================================================
+// parameters
+// =============================================================================================
+void SpatialSimulator::setParameterUniformly(const std::string& id, double value) {
+  if (!impl) return;
+  sb2host::Model& m = impl->m;
+  Var* v = m.findVar(id);
+  if (!v || !v->hasValue) return;
+  if (v->isUniform) {
+    v->uniformValue = value;  // reaches the device constants table in syncBeforeStep()
+    return;
+  }
+  // flood the field (every doubled-grid point in the reference)
+  if (v->speciesId >= 0 && impl->dev && impl->stale[v->speciesId]) impl->stale[v->speciesId] = 0;
+  std::fill(v->field.begin(), v->field.end(), value);
+  v->offGridInit = value;
+  if (impl->dev) {
+    if (v->speciesId >= 0) sb2_upload_species(impl->dev, v->speciesId, v->field.data());
+    else if (v->fieldId >= 0) sb2_upload_field(impl->dev, v->fieldId, v->field.data());
+  }
+  std::map<std::string, VarMirror>::iterator it = impl->varMirrors.find(id);
+  if (it != impl->varMirrors.end()) std::fill(it->second.data.begin(), it->second.data.end(), value);
+}
+
+// spatialsimulator.cpp:167-202
+void SpatialSimulator::setParameter(const std::string& id, double value) {
+  if (!impl || !impl->m.model) return;
+  sb2host::Model& m = impl->m;
+  Parameter* param = m.model->getParameter(id);
+  if (!param) return;
+  param->setValue(value);
+  SpatialParameterPlugin* pp = static_cast<SpatialParameterPlugin*>(param->getPlugin("spatial"));
+  if (pp && pp->getDiffusionCoefficient() && !pp->getDiffusionCoefficient()->getVariable().empty()) {
+    DiffusionCoefficient* dc = pp->getDiffusionCoefficient();
+    Var* s = m.findVar(dc->getVariable());
+    if (s && s->hasDiff) {
+      const int a = (int)dc->getCoordinateReference1();  // the enum value is the array index (:180)
+      Var* c = (a >= 0 && a < 3) ? s->diffC[a] : NULL;
+      if (c && c->hasValue) setParameterUniformly(c->id, value);
+    }
+  }
+  setParameterUniformly(id, value);
+}
+
+// spatialsimulator.cpp:1729-1767
+void SpatialSimulator::flipVolumeOrder() {
+  if (!impl || !impl->m.model) return;
+  SpatialModelPlugin* plugin = dynamic_cast<SpatialModelPlugin*>(impl->m.model->getPlugin("spatial"));
+  if (!plugin || !plugin->getGeometry()) return;
+  Geometry* geometry = plugin->getGeometry();
+  for (unsigned int i = 0; i < geometry->getNumGeometryDefinitions(); ++i) {
+    GeometryDefinition* gd = geometry->getGeometryDefinition(i);
+    if (!gd->isAnalyticGeometry()) continue;
+    AnalyticGeometry* ag = static_cast<AnalyticGeometry*>(gd);
+    const int n = (int)ag->getNumAnalyticVolumes();
+    std::vector<int> ordinals(n);
+    for (int k = 0; k < n; ++k) ordinals[k] = ag->getAnalyticVolume(k)->getOrdinal();
+    for (int k = 0; k < n; ++k) ag->getAnalyticVolume(k)->setOrdinal((n - 1) - ordinals[k]);
+  }
+}
+
+// =============================================================================================
+// read-back
+// =============================================================================================
+int SpatialSimulator::getVariableLength() const {
+  if (!impl) return 0;
+  const sb2host::Model& m = impl->m;
+  return (int)((int64_t)(m.Zindex - 1) * m.Yindex * m.Xindex + (int64_t)(m.Yindex - 1) * m.Xindex + m.Xindex - 1);
+}
+int SpatialSimulator::getGeometryLength() const { return impl ? (int)impl->m.ndoubled() : 0; }
+long SpatialSimulator::getNumDomainCells() const { return impl ? impl->domainCells : 0; }
+int SpatialSimulator::getNumStagedSpecies() const { return impl ? (int)impl->staged.size() : 0; }
+long SpatialSimulator::getDeviceLaunchCount() const { return impl && impl->dev ? (long)sb2_launch_count(impl->dev) : 0; }
+
+namespace {
+// bring Var::field up to date with the device
+bool refreshCompact(SimImpl* impl, Var* v) {
+  if (v->speciesId < 0 || !impl->dev || !impl->stale[v->speciesId]) return true;
+  if (sb2_download_species(impl->dev, v->speciesId, v->field.data()) < 0) return false;
+  impl->stale[v->speciesId] = 0;
+  return true;
+}
+}  // namespace
+
+bool SpatialSimulator::getVariableCompact(const std::string& id, double* out, size_t n) {
+  if (!impl || !out) return false;
+  Var* v = impl->m.findVar(id);
+  if (!v || !v->hasValue) return false;
+  if (v->isUniform) {
+    for (size_t i = 0; i < n; ++i) out[i] = v->uniformValue;
+    return true;
+  }
+  if (n != (size_t)impl->m.ncells()) return false;
+  if (!refreshCompact(impl, v)) return false;
+  memcpy(out, v->field.data(), n * sizeof(double));
+  return true;
+}
+
+bool SpatialSimulator::setVariableCompact(const std::string& id, const double* in, size_t n) {
+  if (!impl || !in) return false;
+  Var* v = impl->m.findVar(id);
+  if (!v || !v->hasValue || v->isUniform || n != (size_t)impl->m.ncells()) return false;
+  memcpy(v->field.data(), in, n * sizeof(double));
+  if (v->speciesId >= 0) impl->stale[v->speciesId] = 0;
+  if (impl->dev) {
+    if (v->speciesId >= 0) return sb2_upload_species(impl->dev, v->speciesId, v->field.data()) >= 0;
+    if (v->fieldId >= 0) return sb2_upload_field(impl->dev, v->fieldId, v->field.data()) >= 0;
+  }
+  return true;
+}
+
+double* SpatialSimulator::getVariable(const std::string& id, int& length) {
+  length = 0;
+  if (!impl) return NULL;
+  sb2host::Model& m = impl->m;
+  Var* v = m.findVar(id);
+  if (!v || !v->hasValue) return NULL;
+  length = getVariableLength();
+  if (v->isUniform) return &v->uniformValue;  // the reference hands out the single double as well
+  if (m.isSlab()) { length = 0; lastError = "doubled-grid mirrors are not available on a sharded grid; use getVariableCompact"; return NULL; }
+  const bool wasStale = v->speciesId >= 0 && impl->stale[v->speciesId];
+  if (!refreshCompact(impl, v)) { length = 0; return NULL; }
+  VarMirror& mir = impl->varMirrors[id];
+  const bool fresh = mir.data.empty();
+  const int Xi = m.Xindex, Yi = m.Yindex, Zi = m.Zindex;
+  if (fresh) {
+    mir.data.assign((size_t)m.ndoubled(), v->offGridInit);
+    if (impl->isCoordinate(v)) {
+      for (int Z = 0; Z < Zi; ++Z)
+        for (int Y = 0; Y < Yi; ++Y)
+          for (int X = 0; X < Xi; ++X)
+            mir.data[((int64_t)Z * Yi + Y) * Xi + X] = impl->coordinateAt(v, v == m.xVar ? X : v == m.yVar ? Y : Z);
+    }
+  }
+  if (fresh || wasStale || !mir.handedOut) {
+    for (int k = 0; k < m.nz; ++k)
+      for (int j = 0; j < m.ny; ++j) {
+        double* row = mir.data.data() + (int64_t)(2 * k) * Yi * Xi + (int64_t)(2 * j) * Xi;
+        const double* f = v->field.data() + ((int64_t)k * m.ny + j) * m.nx;
+        for (int i = 0; i < m.nx; ++i) row[2 * i] = f[i];
+      }
+    // CIP face values of an advected species live at the odd points of its array
+    if (v->speciesId >= 0 && v->hasAdv && impl->dev) {
+      std::vector<double> faces((size_t)m.ncells());
+      const int64_t stride[3] = {1, Xi, (int64_t)Xi * Yi};
+      for (int a = 0; a < m.dimension; ++a) {
+        if (sb2_download_faces(impl->dev, v->speciesId, a, faces.data()) < 0) continue;
+        const int lim[3] = {m.nx - (a == 0), m.ny - (a == 1), m.nz - (a == 2)};
+        for (int k = 0; k < lim[2]; ++k)
+          for (int j = 0; j < lim[1]; ++j)
+            for (int i = 0; i < lim[0]; ++i)
+              mir.data[(int64_t)(2 * k) * Yi * Xi + (int64_t)(2 * j) * Xi + 2 * i + stride[a]] = faces[((int64_t)k * m.ny + j) * m.nx + i];
+      }
+    }
+  }
+  mir.handedOut = true;
+  return mir.data.data();
+}
+
+int* SpatialSimulator::getGeometry(const std::string& id, int& length) {
+  length = 0;
+  if (!impl) return NULL;
+  sb2host::Model& m = impl->m;
+  Geo* g = m.geoByCompartment(id);
+  if (!g || m.isSlab()) return NULL;
+  length = (int)m.ndoubled();
+  if (!g->hasMask) return NULL;  // the reference returns its NULL isDomain pointer
+  std::vector<int>& out = impl->geoMirrors[id];
+  if (out.empty()) {
+    out.assign((size_t)m.ndoubled(), 0);
+    if (g->isVol) {
+      for (int k = 0; k < m.nz; ++k)
+        for (int j = 0; j < m.ny; ++j)
+          for (int i = 0; i < m.nx; ++i)
+            out[(int64_t)(2 * k) * m.Yindex * m.Xindex + (int64_t)(2 * j) * m.Xindex + 2 * i] = g->isDomain[((int64_t)k * m.ny + j) * m.nx + i];
+    } else {
+      for (std::unordered_map<int64_t, uint8_t>::const_iterator it = g->memClass.begin(); it != g->memClass.end(); ++it) out[it->first] = it->second;
+    }
+  }
+  return out.data();
+}
+
+boundaryType* SpatialSimulator::getBoundaryType(const std::string& id, int& length) {
+  length = 0;
+  if (!impl) return NULL;
+  sb2host::Model& m = impl->m;
+  Geo* g = m.geoByCompartment(id);
+  if (!g || m.isSlab()) return NULL;
+  length = (int)m.ndoubled();
+  if (!g->hasMask) return NULL;
+  std::vector<boundaryType>& out = impl->btMirrors[id];
+  if (out.empty()) {
+    boundaryType none = {false, false, false, false, false, false};
+    out.assign((size_t)m.ndoubled(), none);
+    auto set = [](boundaryType& b, uint8_t f) {
+      b.isBofXp = f & SB2_F_XP; b.isBofXm = f & SB2_F_XM; b.isBofYp = f & SB2_F_YP;
+      b.isBofYm = f & SB2_F_YM; b.isBofZp = f & SB2_F_ZP; b.isBofZm = f & SB2_F_ZM;
+    };
+    if (g->isVol) {
+      for (int k = 0; k < m.nz; ++k)
+        for (int j = 0; j < m.ny; ++j)
+          for (int i = 0; i < m.nx; ++i)
+            set(out[(int64_t)(2 * k) * m.Yindex * m.Xindex + (int64_t)(2 * j) * m.Xindex + 2 * i], g->flags[((int64_t)k * m.ny + j) * m.nx + i]);
+    } else {
+      for (size_t k = 0; k < g->memPoints.size(); ++k) set(out[g->memPoints[k].index], g->memPoints[k].bof);
+    }
+  }
+  return out.data();
+}
+
+int* SpatialSimulator::getBoundary(const std::string& id, int& length) {
+  length = 0;
+  if (!impl) return NULL;
+  sb2host::Model& m = impl->m;
+  Geo* g = m.geoByCompartment(id);
+  if (!g || m.isSlab()) return NULL;
+  length = (int)m.ndoubled();
+  if (!g->hasMask) return NULL;
+  std::vector<int>& out = impl->boundaryMirrors[id];
+  if (out.empty()) {
+    // only volume cells are ever written by the reference; the other entries of its array are
+    // uninitialised heap and read as 0 here
+    out.assign((size_t)m.ndoubled(), 0);
+    if (g->isVol)
+      for (int k = 0; k < m.nz; ++k)
+        for (int j = 0; j < m.ny; ++j)
+          for (int i = 0; i < m.nx; ++i)
+            out[(int64_t)(2 * k) * m.Yindex * m.Xindex + (int64_t)(2 * j) * m.Xindex + 2 * i] = g->isBoundary[((int64_t)k * m.ny + j) * m.nx + i];
+  }
+  return out.data();
+}
+
+double* SpatialSimulator::getX(int& length) {
+  length = 0;
+  if (!impl || !impl->m.xVar) return NULL;
+  return getVariable(impl->m.xVar->id, length);
+}
+double* SpatialSimulator::getY(int& length) {
+  length = 0;
+  if (!impl || !impl->m.yVar) return NULL;
+  return getVariable(impl->m.yVar->id, length);
+}
+double* SpatialSimulator::getZ(int& length) {
+  length = 0;
+  if (!impl || !impl->m.zVar) return NULL;
+  return getVariable(impl->m.zVar->id, length);
+}
+
+// spatialsimulator.cpp:1769-1783: coordinates are matched with ==, the z plane is always 0
+int SpatialSimulator::getIndexForPosition(double x, double y) {
+  if (!impl || !impl->m.xVar || !impl->m.yVar || impl->m.isSlab()) return -1;
+  const sb2host::Model& m = impl->m;
+  int ci = -1, cj = -1;
+  for (int i = 0; i < m.nx && ci < 0; ++i) if (impl->coordinateAt(m.xVar, 2 * i) == x) ci = i;
+  for (int j = 0; j < m.ny && cj < 0; ++j) if (impl->coordinateAt(m.yVar, 2 * j) == y) cj = j;
+  if (ci < 0 || cj < 0) return -1;
+  return (2 * cj) * m.Xindex + 2 * ci;
+}
+
+// spatialsimulator.cpp:1316-1332
+double SpatialSimulator::getVariableAt(const std::string& id, int x, int y, int z) {
+  (void)z;
+  if (!impl) return 0.0;
+  sb2host::Model& m = impl->m;
+  Var* v = m.findVar(id);
+  if (!v) return 0.0;
+  const int index = getIndexForPosition(x, y);
+  if (index == -1) return 0.0;
+  if (!v->geo || !v->geo->hasMask || v->isUniform || !v->hasValue) return 0.0;
+  const int Y = index / m.Xindex, X = index - Y * m.Xindex;
+  const int64_t c = (int64_t)(Y / 2) * m.nx + X / 2;
+  if (!v->geo->isVol) return 0.0;
+  if (v->geo->isDomain[c] == 0) return 0.0;
+  if (!refreshCompact(impl, v)) return 0.0;
+  return v->field[c];
+}
+
+// =============================================================================================
+// inspection
+// =============================================================================================
+std::string SpatialSimulator::getDeviceProgramText() {
+  if (!impl || !impl->dev) return "";
+  std::vector<char> buf(1 << 16);
+  sb2_program_text(impl->dev, buf.data(), (int)buf.size());
+  return std::string(buf.data());
+}
+
+namespace {
+// same text layout as the oracle's dump (oracle/ref_driver.cpp: rpnText)
+std::string rpnText(const Rpn& rpn) {
+  std::ostringstream os;
+  os.precision(17);
+  for (size_t i = 0; i < rpn.size(); ++i) {
+    const Tok& t = rpn[i];
+    if (t.kind == Tok::VAR) os << "V " << t.var->id << " " << (t.var->hasDelta ? 1 : 0) << "\n";
+    else if (t.kind == Tok::CONSTVAR) os << "C " << t.var->id << " " << t.var->uniformValue << "\n";
+    else if (t.kind == Tok::LITERAL) os << "C # " << t.literal << "\n";
+    else os << "O " << t.astType << "\n";
+  }
+  return os.str();
+}
+}  // namespace
+
+std::string SpatialSimulator::getSetupText(const std::string& what) {
+  if (!impl) return "";
+  sb2host::Model& m = impl->m;
+  std::ostringstream os;
+  os.precision(17);
+  if (what == "summary") {
+    os << "dims " << m.nx << " " << m.ny << " " << m.nz << " dimension " << m.dimension << " delta " << m.deltaX << " " << m.deltaY << " " << m.deltaZ << "\n";
+    for (size_t i = 0; i < m.geos.size(); ++i) {
+      Geo* g = m.geos[i];
+      os << "geo " << g->compartmentId << " domainType " << g->domainTypeId << " isVol " << g->isVol << " cells " << g->nDomain
+         << " memPoints " << g->memPoints.size() << " pseudo " << g->pseudoMemIndex.size() << " adjacent "
+         << (g->adjacent1 ? g->adjacent1->compartmentId : "-") << " " << (g->adjacent2 ? g->adjacent2->compartmentId : "-") << "\n";
+    }
+    for (size_t i = 0; i < m.vars.size(); ++i) {
+      Var* v = m.vars[i];
+      os << "var " << v->id << " uniform " << v->isUniform << " hasValue " << v->hasValue << " hasDelta " << v->hasDelta << " geo "
+         << (v->geo ? v->geo->compartmentId : "-") << " species " << v->speciesId << " field " << v->fieldId << " const " << v->constSlot;
+      if (v->isUniform && v->hasValue) os << " value " << v->uniformValue;
+      os << "\n";
+    }
+    for (size_t i = 0; i < m.rxns.size(); ++i)
+      os << "rxn " << i << " " << m.rxns[i]->id << " transport " << m.rxns[i]->isMemTransport << " tokens " << m.rxns[i]->rpn.size() << "\n";
+    return os.str();
+  }
+  if (what.compare(0, 4, "rxn/") == 0) {
+    const size_t i = (size_t)atoi(what.c_str() + 4);
+    if (i < m.rxns.size()) return rpnText(m.rxns[i]->rpn);
+    return "";
+  }
+  if (what.compare(0, 5, "refs/") == 0) {
+    const size_t i = (size_t)atoi(what.c_str() + 5);
+    if (i >= m.rxns.size()) return "";
+    for (size_t k = 0; k < m.rxns[i]->spRefs.size(); ++k)
+      os << (m.rxns[i]->spRefs[k] ? m.rxns[i]->spRefs[k]->id : "?") << " " << m.rxns[i]->stoichiometry[k] << " " << (m.rxns[i]->isVariable[k] ? 1 : 0) << "\n";
+    return os.str();
+  }
+  if (what.compare(0, 4, "geo/") == 0) {
+    Geo* g = m.geoByCompartment(what.substr(4));
+    return g ? rpnText(g->rpn) : "";
+  }
+  if (what.compare(0, 8, "normals/") == 0) {
+    Geo* g = m.geoByCompartment(what.substr(8));
+    if (!g) return "";
+    for (size_t k = 0; k < g->memPoints.size(); ++k)
+      os << g->memPoints[k].index << " " << g->memPoints[k].nx << " " << g->memPoints[k].ny << " " << g->memPoints[k].nz << "\n";
+    return os.str();
+  }
+  if (what.compare(0, 10, "memindex/") == 0 || what.compare(0, 9, "memindex/") == 0) {
+    Geo* g = m.geoByCompartment(what.substr(9));
+    if (!g) return "";
+    for (size_t k = 0; k < g->memDomainIndex.size(); ++k) os << g->memDomainIndex[k] << "\n";
+    return os.str();
+  }
+  if (what.compare(0, 7, "pseudo/") == 0) {
+    Geo* g = m.geoByCompartment(what.substr(7));
+    if (!g) return "";
+    for (size_t k = 0; k < g->pseudoMemIndex.size(); ++k) os << g->pseudoMemIndex[k] << "\n";
+    return os.str();
+  }
+  return "";
+}
