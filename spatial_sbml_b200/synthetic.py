@@ -1,0 +1,162 @@
+"""Synthetic SBML-spatial models for the sharded / large-grid benchmarks and tests.
+
+BASELINE.json config 5 ("synthetic turing.xml at 8192x8192 and 512^3"): the 2-species Turing model
+of the reference's examples/turing.xml (same kinetic laws with literal constants, D = 4 / 0.4,
+Neumann-0 boundaries, blob initial condition) and the Brusselator of examples/The_Brusselator.xml,
+written for an arbitrary grid with boundaryMax = n-1 so that deltaX = 1, an all-ones background
+volume (ordinal 0) and the reaction domain 1 <= x,y(,z) <= n-2 (ordinal 1).  The membrane
+compartment of the example files is left out (no species lives on it).
+These files are written from scratch here; nothing is read from the reference at run time.
+"""
+
+SPATIAL_NS = "http://www.sbml.org/sbml/level3/version1/spatial/version1"
+_MATH = 'xmlns="http://www.w3.org/1998/Math/MathML"'
+
+
+def _cn(v):
+    if isinstance(v, int):
+        return '<cn type="integer"> %d </cn>' % v
+    return "<cn> %r </cn>" % float(v)
+
+
+def _ci(n):
+    return "<ci> %s </ci>" % n
+
+
+def _apply(op, *args):
+    return "<apply><%s/>%s</apply>" % (op, "".join(args))
+
+
+def _box(axes, lo, hi):
+    """and(x>=lo, x<=hi, y>=lo, ...) as one n-ary <and/>, like the example files."""
+    terms = []
+    for a, h in zip(axes, hi):
+        terms.append(_apply("geq", _ci(a), _cn(lo)))
+        terms.append(_apply("leq", _ci(a), _cn(h)))
+    return _apply("and", *terms)
+
+
+def _piecewise(value, cond, otherwise):
+    return "<piecewise><piece>%s%s</piece><otherwise>%s</otherwise></piecewise>" % (value, cond, otherwise)
+
+
+def _param(pid, value, inner=""):
+    return '<parameter id="%s" value="%r" constant="true">%s</parameter>' % (pid, float(value), inner)
+
+
+def _transport_params(species, D, axes, bc_values=None, bc_type="Neumann"):
+    out = []
+    kinds = {"x": "cartesianX", "y": "cartesianY", "z": "cartesianZ"}
+    for a in axes:
+        out.append(_param("%s_diff_%s" % (species, a), D,
+                          '<spatial:diffusionCoefficient spatial:variable="%s" spatial:type="isotropic" '
+                          'spatial:coordinateReference1="%s"/>' % (species, kinds[a])))
+    for a in axes:
+        for side in ("min", "max"):
+            b = "%s%s" % (a.upper(), side)
+            v = 0.0 if not bc_values else bc_values.get((species, b), 0.0)
+            out.append(_param("%s_BC_%s" % (species, b), v,
+                              '<spatial:boundaryCondition spatial:variable="%s" spatial:type="%s" '
+                              'spatial:coordinateBoundary="%s"/>' % (species, bc_type, b)))
+    return out
+
+
+def _reaction(rid, reactants, products, math):
+    def refs(tag, lst):
+        if not lst:
+            return ""
+        return "<%s>%s</%s>" % (tag, "".join('<speciesReference species="%s" stoichiometry="%r" constant="true"/>' % (s, float(st))
+                                               for s, st in lst), tag)
+    return ('<reaction id="%s" reversible="false" fast="false">%s%s<kineticLaw><math %s>%s</math></kineticLaw></reaction>'
+            % (rid, refs("listOfReactants", reactants), refs("listOfProducts", products), _MATH, math))
+
+
+def _geometry(axes, dims, lo, hi):
+    kinds = {"x": "cartesianX", "y": "cartesianY", "z": "cartesianZ"}
+    cc = "".join('<spatial:coordinateComponent spatial:id="%s" spatial:type="%s">'
+                 '<spatial:boundaryMin spatial:id="%smin" spatial:value="0"/>'
+                 '<spatial:boundaryMax spatial:id="%smax" spatial:value="%d"/></spatial:coordinateComponent>'
+                 % (a, kinds[a], a.upper(), a.upper(), n - 1) for a, n in zip(axes, dims))
+    inside = _piecewise(_cn(1), _box(axes, lo, hi), _cn(0))
+    return ('<spatial:geometry spatial:id="geometry" spatial:coordinateSystem="cartesian">'
+            '<spatial:listOfCoordinateComponents>%s</spatial:listOfCoordinateComponents>'
+            '<spatial:listOfDomainTypes><spatial:domainType spatial:id="dt_in" spatial:spatialDimensions="3"/>'
+            '<spatial:domainType spatial:id="dt_out" spatial:spatialDimensions="3"/></spatial:listOfDomainTypes>'
+            '<spatial:listOfDomains><spatial:domain spatial:id="dom_in" spatial:domainType="dt_in"/>'
+            '<spatial:domain spatial:id="dom_out" spatial:domainType="dt_out"/></spatial:listOfDomains>'
+            '<spatial:listOfGeometryDefinitions><spatial:analyticGeometry spatial:id="ag" spatial:isActive="true">'
+            '<spatial:listOfAnalyticVolumes>'
+            '<spatial:analyticVolume spatial:id="av_in" spatial:functionType="layered" spatial:ordinal="1" spatial:domainType="dt_in">'
+            '<math %s>%s</math></spatial:analyticVolume>'
+            '<spatial:analyticVolume spatial:id="av_out" spatial:functionType="layered" spatial:ordinal="0" spatial:domainType="dt_out">'
+            '<math %s>%s</math></spatial:analyticVolume>'
+            '</spatial:listOfAnalyticVolumes></spatial:analyticGeometry></spatial:listOfGeometryDefinitions>'
+            '</spatial:geometry>' % (cc, _MATH, inside, _MATH, _cn(1)))
+
+
+def _document(model_id, axes, dims, species, params, assignments, reactions, lo=1, hi=None):
+    hi = hi or [n - 2 for n in dims]
+    comps = ('<compartment id="inside" spatialDimensions="3" size="1" constant="true">'
+             '<spatial:compartmentMapping spatial:id="m_in" spatial:domainType="dt_in" spatial:unitSize="1"/></compartment>'
+             '<compartment id="outside" spatialDimensions="3" size="1" constant="true">'
+             '<spatial:compartmentMapping spatial:id="m_out" spatial:domainType="dt_out" spatial:unitSize="1"/></compartment>')
+    sp = "".join('<species id="%s" compartment="inside" hasOnlySubstanceUnits="false" boundaryCondition="false" '
+                 'constant="false" spatial:isSpatial="true"%s/>' % (s, (' initialConcentration="%r"' % float(c)) if c is not None else "")
+                 for s, c in species)
+    coords = "".join(_param(a, 0.0, '<spatial:spatialSymbolReference spatial:spatialRef="%s"/>' % a) for a in axes)
+    ia = "".join('<initialAssignment symbol="%s"><math %s>%s</math></initialAssignment>' % (s, _MATH, m) for s, m in assignments)
+    return ('<?xml version="1.0" encoding="UTF-8"?>\n'
+            '<sbml xmlns="http://www.sbml.org/sbml/level3/version1/core" xmlns:spatial="%s" level="3" version="1" '
+            'spatial:required="true"><model id="%s"><listOfCompartments>%s</listOfCompartments>'
+            '<listOfSpecies>%s</listOfSpecies><listOfParameters>%s%s</listOfParameters>%s'
+            '<listOfReactions>%s</listOfReactions>%s</model></sbml>\n'
+            % (SPATIAL_NS, model_id, comps, sp, coords, "".join(params),
+               ("<listOfInitialAssignments>%s</listOfInitialAssignments>" % ia) if ia else "",
+               "".join(reactions), _geometry(axes, dims, lo, hi)))
+
+
+def turing(nx, ny, nz=None, blob=True, bc_values=None, D=(4.0, 0.4)):
+    """2-species Turing model (examples/turing.xml) on an nx x ny (x nz) grid; dt 0.07 in the reference's annotation."""
+    dims = [nx, ny] + ([nz] if nz else [])
+    axes = ["x", "y", "z"][:len(dims)]
+    params = _transport_params("species_1", D[0], axes, bc_values) + _transport_params("species_2", D[1], axes, bc_values)
+    if blob:
+        cond = []
+        rng = {"x": (0.20, 0.25), "y": (0.70, 0.85), "z": (0.40, 0.60)}
+        for a, n in zip(axes, dims):
+            L = n - 1
+            cond.append(_apply("gt", _ci(a), _cn(rng[a][0] * L)))
+            cond.append(_apply("lt", _ci(a), _cn(rng[a][1] * L)))
+        ia1 = _piecewise(_cn(20.0), _apply("and", *cond), _cn(0.5))
+    else:
+        ia1 = _cn(0.5)
+    assignments = [("species_1", ia1), ("species_2", _cn(0.1))]
+    rx = [
+        _reaction("reaction_1", [("species_1", 1)], [("species_2", 1)], _apply("times", _cn(1.0), _ci("species_1"), _ci("species_2"))),
+        _reaction("reaction_2", [], [("species_1", 1)], _cn(0.12)),
+        _reaction("reaction_3", [], [("species_2", 1)], _cn(0.06)),
+        _reaction("reaction_4", [("species_2", 1)], [],
+                  _apply("times", _cn(0.5), _ci("species_2"), _apply("divide", _cn(1.0), _apply("plus", _cn(0.1), _ci("species_2"))))),
+    ]
+    return _document("synthetic_turing", axes, dims, [("species_1", None), ("species_2", None)], params, assignments, rx)
+
+
+def brusselator(nx, ny, nz=None, bc_values=None, perturb=False):
+    """Brusselator (examples/The_Brusselator.xml: k = 0.1, A = 2.5, B = 5.24, D = 0.16 / 0.8); dt 0.1."""
+    dims = [nx, ny] + ([nz] if nz else [])
+    axes = ["x", "y", "z"][:len(dims)]
+    params = _transport_params("X", 0.16, axes, bc_values) + _transport_params("Y", 0.8, axes, bc_values)
+    params += [_param("k", 0.1), _param("A", 2.5), _param("B", 5.24)]
+    assignments = []
+    species = [("X", 2.5), ("Y", 2.0)]
+    if perturb:
+        # smooth, non-uniform start so that diffusion terms are exercised: X = 2.5 + 0.01*x
+        species = [("X", None), ("Y", 2.0)]
+        assignments = [("X", _apply("plus", _cn(2.5), _apply("times", _cn(0.01), _ci("x"))))]
+    rx = [
+        _reaction("J0", [], [("X", 1)], _apply("times", _ci("k"), _ci("A"))),
+        _reaction("J1", [("Y", 1)], [("X", 1)], _apply("times", _ci("k"), _ci("X"), _ci("X"), _ci("Y"))),
+        _reaction("J2", [("X", 1)], [("Y", 1)], _apply("times", _ci("k"), _ci("X"), _ci("B"))),
+        _reaction("J3", [("X", 1)], [], _apply("times", _ci("k"), _ci("X"))),
+    ]
+    return _document("synthetic_brusselator", axes, dims, species, params, assignments, rx)
