@@ -184,8 +184,10 @@ SB2_API int sb2_download_faces(sb2_sim* sim, int species, int axis, double* out)
 SB2_API int sb2_min_dt(sb2_sim* sim, double dt, double* out);
 
 /* Device pointers for callers that exchange slab halos themselves (multi-GPU).
- * which: 0 = u, 1..4 = k0..k3.  row_pitch / plane_pitch in doubles; first_cell = offset of
- * compact cell (0,0,0) inside the allocation (one guard row / plane precedes it). */
+ * which: 0 = u (current), 1..4 = k0..k3, 5 = the other half of u's double buffer (where a fused
+ * last stage writes the new u before sb2_end_step makes it current).  row_pitch / plane_pitch in
+ * doubles; first_cell = offset of compact cell (0,0,0) inside the allocation (one guard row / plane
+ * precedes it). */
 typedef struct {
   void* ptr;
   int64_t row_pitch, plane_pitch, first_cell, n_alloc;
@@ -197,6 +199,9 @@ SB2_API int sb2_species_view(sb2_sim* sim, int species, int which, sb2_field_vie
 SB2_API int sb2_begin_step(sb2_sim* sim, double t_arg, double dt, int time_slot);
 SB2_API int sb2_stage(sb2_sim* sim, int m, int phase);
 SB2_API int sb2_end_step(sb2_sim* sim);
+/* After sb2_begin_step: 1 when the RK combine of this step is fused into stage 3 (the new u is
+ * written to view 5 by sb2_stage(3, ...)), 0 when sb2_end_step computes it in place. */
+SB2_API int sb2_combine_is_fused(const sb2_sim* sim);
 
 /* Counters: kernels launched by this handle since creation. */
 SB2_API int64_t sb2_launch_count(const sb2_sim* sim);

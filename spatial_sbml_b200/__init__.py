@@ -85,6 +85,7 @@ def _proto(lib):
         "sb2_begin_step": (ci, [vp, cd, cd, ci]),
         "sb2_stage": (ci, [vp, ci, ci]),
         "sb2_end_step": (ci, [vp]),
+        "sb2_combine_is_fused": (ci, [vp]),
         "sb2_launch_count": (C.c_int64, [vp]),
         "sb2_program_text": (ci, [vp, C.c_char_p, ci]),
         # --- include/spatial_sim_c.h

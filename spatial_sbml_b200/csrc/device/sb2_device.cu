@@ -250,7 +250,8 @@ void fill_stage_args(sb2_sim* sim, Sb2StageArgs& a, int m, double dt, int row_be
   }
   // rows per CTA: enough CTAs to fill the machine several times over, long enough strips to
   // amortise the two extra rows each CTA loads
-  const int strips = (sim->g.nx + 255) / 256;
+  a.np = sb2_stage_pairs(sim->g.nx, S);
+  const int strips = (sim->g.nx + 256 * a.np - 1) / (256 * a.np);
   const int rows = (sim->g.dim == 3) ? sim->g.ny : (row_end - row_begin);
   const int planes = (sim->g.dim == 3) ? (row_end - row_begin) : 1;
   int rpb = 64;
@@ -495,6 +496,12 @@ int sb2_finalize(sb2_sim* sim) {
   for (int g = 0; g < b.G; ++g) b.flags[g] = sim->d_flags[g];
   for (size_t f = 0; f < sim->d_fields.size(); ++f) b.fields[f] = sim->d_fields[f];
   b.ntok = (int)sim->program.size();
+  b.depth = 1;
+  for (size_t i = 0; i < sim->program.size(); ++i) {
+    const uint32_t code = sim->program[i] & 0xffffu;
+    const int opc = (int)(code / SB2_MAX_DEPTH), d = (int)(code % SB2_MAX_DEPTH);
+    if (opc != OPC_MASK && opc != OPC_ACCSUB && opc != OPC_ACCADD && d + 1 > b.depth) b.depth = d + 1;
+  }
   memcpy(b.tok, sim->program.data(), sizeof(uint32_t) * sim->program.size());
 
   // boundary-condition lists (Neumann flux / Dirichlet overwrite), built from the host flag copies
@@ -764,13 +771,15 @@ int sb2_min_dt(sb2_sim* sim, double dt, double* out) {
 }
 
 int sb2_species_view(sb2_sim* sim, int species, int which, sb2_field_view* out) {
-  if (!sim || !out || species < 0 || species >= (int)sim->species.size() || which < 0 || which > 4)
+  if (!sim || !out || species < 0 || species >= (int)sim->species.size() || which < 0 || which > 5)
     return fail(sim, SB2_ERR_ARG, "bad species / selector");
   Sb2Species& s = sim->species[species];
-  out->ptr = which == 0 ? (void*)s.u[s.cur] : (void*)s.k[which - 1];
+  out->ptr = which == 0 ? (void*)s.u[s.cur] : which == 5 ? (void*)s.u[s.cur ^ 1] : (void*)s.k[which - 1];
   out->row_pitch = sim->P; out->plane_pitch = sim->PL; out->first_cell = sim->first; out->n_alloc = sim->nalloc;
   return SB2_OK;
 }
+
+int sb2_combine_is_fused(const sb2_sim* sim) { return sim && sim->fuse_combine ? 1 : 0; }
 
 int64_t sb2_launch_count(const sb2_sim* sim) { return sim ? sim->launches : 0; }
 

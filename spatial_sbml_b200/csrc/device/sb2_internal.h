@@ -54,11 +54,13 @@ struct Sb2StageArgs {
   int64_t P, PL, first;  // row pitch, plane pitch, offset of cell (0,0,0), all in elements
   int32_t row_begin, row_end;      // rows (2-D: y) or planes (3-D: z) of the slab axis to compute
   int32_t rows_per_block;
+  int32_t np;      // cell pairs per thread of the kernel variant (strip width = 256*np cells)
   int32_t m;       // RK stage 0..3
   int32_t S, G;
   int32_t final;   // fused RK combine: write u_out instead of k3
   int32_t carry;   // accumulate on top of what kout already holds
   int32_t ntok;
+  int32_t depth;   // deepest expression-stack slot the program touches + 1
   double cdt;      // rk[m]*dt
   double dt;
   double dx2[3];
@@ -72,6 +74,7 @@ struct Sb2StageArgs {
 
 // launches (implemented in stage_kernel.cu)
 cudaError_t sb2_launch_stage(const Sb2StageArgs& args, cudaStream_t stream, int* launches);
+int sb2_stage_pairs(int nx, int nspecies);
 
 struct Sb2CombineArgs {
   int32_t nx, ny, nz, dim, S;

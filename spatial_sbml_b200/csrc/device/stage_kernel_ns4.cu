@@ -1,0 +1,7 @@
+// stage_kernel_ns4.cu — instantiates the fused RK-stage kernel (stage_kernel.cuh) for up to 4 staged species.
+#include "stage_kernel.cuh"
+
+cudaError_t sb2_launch_stage_ns4(const Sb2StageArgs& a, cudaStream_t stream) {
+  if (a.np == 2) return launch_depth<4, 2>(a, stream);
+  return launch_depth<4, 1>(a, stream);
+}

@@ -752,7 +752,9 @@ bool SpatialSimulator::getVariableCompact(const std::string& id, double* out, si
     return true;
   }
   if (n != (size_t)impl->m.ncells()) return false;
-  if (!refreshCompact(impl, v)) return false;
+  // device state newer than the host copy: copy straight into the caller's buffer (which may be
+  // pinned) instead of going through the host copy
+  if (v->speciesId >= 0 && impl->dev && impl->stale[v->speciesId]) return sb2_download_species(impl->dev, v->speciesId, out) >= 0;
   memcpy(out, v->field.data(), n * sizeof(double));
   return true;
 }
@@ -761,12 +763,14 @@ bool SpatialSimulator::setVariableCompact(const std::string& id, const double* i
   if (!impl || !in) return false;
   Var* v = impl->m.findVar(id);
   if (!v || !v->hasValue || v->isUniform || n != (size_t)impl->m.ncells()) return false;
-  memcpy(v->field.data(), in, n * sizeof(double));
-  if (v->speciesId >= 0) impl->stale[v->speciesId] = 0;
-  if (impl->dev) {
-    if (v->speciesId >= 0) return sb2_upload_species(impl->dev, v->speciesId, v->field.data()) >= 0;
-    if (v->fieldId >= 0) return sb2_upload_field(impl->dev, v->fieldId, v->field.data()) >= 0;
+  if (impl->dev && v->speciesId >= 0) {
+    // upload straight from the caller's buffer; the host copy is refreshed on demand
+    if (sb2_upload_species(impl->dev, v->speciesId, in) < 0) return false;
+    impl->stale[v->speciesId] = 1;
+    return true;
   }
+  memcpy(v->field.data(), in, n * sizeof(double));
+  if (impl->dev && v->fieldId >= 0) return sb2_upload_field(impl->dev, v->fieldId, v->field.data()) >= 0;
   return true;
 }
 
