@@ -138,8 +138,35 @@ uint32_t enc(int opc, int d, int arg) { return SB2_CODE(opc, d) | ((uint32_t)arg
 // (if the stack is non-empty), binary operators then combine into the new top only if something is
 // left below, unary operators rewrite the popped slot and push it back, listed-but-empty operators
 // and unresolved names only pop.  The rate is read from slot max(sp-1, 0).
-int compile_stmt(sb2_sim* sim, const Sb2Stmt& st, std::vector<uint32_t>& out) {
-  out.push_back(enc(OPC_MASK, 0, st.geo));
+int compile_stmt(sb2_sim* sim, const Sb2Stmt& st, std::vector<uint32_t>& prog) {
+  // accumulation targets first: a law that changes nothing is not evaluated at all
+  struct Target { int species; bool subtract; double stoich; };
+  std::vector<Target> targets;
+  if (st.kind == 0) {
+    for (int k = 0; k < (int)st.refs.size(); ++k) {
+      const sb2_ref& r = st.refs[k];
+      if (!r.is_variable || r.species < 0) continue;
+      if (r.species >= (int)sim->species.size()) return fail(sim, SB2_ERR_ARG, "reaction references unknown species");
+      Target t = {r.species, k < st.n_reactants, r.stoichiometry};
+      targets.push_back(t);
+    }
+  } else if (!st.refs.empty()) {
+    const sb2_ref& r = st.refs[0];
+    if (r.is_variable && r.species >= 0) {
+      if (r.species >= (int)sim->species.size()) return fail(sim, SB2_ERR_ARG, "rate rule references unknown species");
+      Target t = {r.species, false, r.stoichiometry};
+      targets.push_back(t);
+    }
+  }
+  if (targets.empty()) return SB2_OK;
+  // The law acts on the cells of its own domain (spatialsimulator.cpp:1381-1390).  When every target
+  // species lives in that same domain the kernel's output select already discards the other cells,
+  // so no mask is needed.
+  bool need_mask = false;
+  for (size_t k = 0; k < targets.size(); ++k) need_mask = need_mask || sim->species[targets[k].species].geo != st.geo;
+
+  std::vector<uint32_t> out;
+  if (need_mask) out.push_back(enc(OPC_MASK, 0, st.geo));
   int sp = 0;
   const int n = (int)st.toks.size();
   for (int i = 0; i < n; ++i) {
@@ -201,30 +228,31 @@ int compile_stmt(sb2_sim* sim, const Sb2Stmt& st, std::vector<uint32_t>& out) {
   }
   if (sp > 0) --sp;
   if (sp != 0) out.push_back(enc(OPC_MOV0, sp, 0));
-  if (st.kind == 0) {
-    for (int k = 0; k < (int)st.refs.size(); ++k) {
-      const sb2_ref& r = st.refs[k];
-      if (!r.is_variable || r.species < 0) continue;
-      if (r.species >= (int)sim->species.size()) return fail(sim, SB2_ERR_ARG, "reaction references unknown species");
-      const int slot = internal_const(sim, r.stoichiometry);
+  // a law that is a single constant with unit stoichiometries needs no stack at all
+  const bool const_law = !need_mask && out.size() == 1 && (out[0] & 0xffffu) == SB2_CODE(OPC_PUSHC, 0);
+  bool all_unit = true;
+  for (size_t k = 0; k < targets.size(); ++k) all_unit = all_unit && targets[k].stoich == 1.0;
+  if (const_law && all_unit) {
+    const int cslot = (int)(out[0] >> 16);
+    out.clear();
+    for (size_t k = 0; k < targets.size(); ++k) out.push_back(enc(targets[k].subtract ? OPC_ACCSUBC1 : OPC_ACCADDC1, targets[k].species, cslot));
+  } else {
+    for (size_t k = 0; k < targets.size(); ++k) {
+      const Target& t = targets[k];
+      if (!need_mask && t.stoich == 1.0) { out.push_back(enc(t.subtract ? OPC_ACCSUB1 : OPC_ACCADD1, t.species, 0)); continue; }
+      const int slot = internal_const(sim, t.stoich);
       if (slot < 0) return fail(sim, SB2_ERR_LIMIT, "constants table full");
-      out.push_back(enc(k < st.n_reactants ? OPC_ACCSUB : OPC_ACCADD, r.species, slot));
-    }
-  } else if (!st.refs.empty()) {
-    const sb2_ref& r = st.refs[0];
-    if (r.is_variable && r.species >= 0) {
-      if (r.species >= (int)sim->species.size()) return fail(sim, SB2_ERR_ARG, "rate rule references unknown species");
-      const int slot = internal_const(sim, r.stoichiometry);
-      if (slot < 0) return fail(sim, SB2_ERR_LIMIT, "constants table full");
-      out.push_back(enc(OPC_ACCADD, r.species, slot));
+      if (need_mask) out.push_back(enc(t.subtract ? OPC_ACCSUBM : OPC_ACCADDM, t.species, slot));
+      else out.push_back(enc(t.subtract ? OPC_ACCSUB : OPC_ACCADD, t.species, slot));
     }
   }
+  prog.insert(prog.end(), out.begin(), out.end());
   return SB2_OK;
 }
 
 const char* kOpcNames[OPC_COUNT] = {"END", "PUSHC", "PUSHV", "PUSHF", "ADD", "SUB", "MUL", "DIV", "GEQ", "GT",
   "LEQ", "LT", "AND", "OR", "ADDC", "SUBC", "MULC", "DIVC", "GEQC", "GTC", "LEQC", "LTC", "ADDV", "SUBV", "MULV",
-  "DIVV", "UNARY", "BINR", "MOV0", "MASK", "ACCSUB", "ACCADD"};
+  "DIVV", "UNARY", "BINR", "MOV0", "MASK", "ACCSUB", "ACCADD", "ACCSUB1", "ACCADD1", "ACCSUBC1", "ACCADDC1", "ACCSUBM", "ACCADDM"};
 
 void fill_stage_args(sb2_sim* sim, Sb2StageArgs& a, int m, double dt, int row_begin, int row_end) {
   static const double rk[4] = {0.0, 0.5, 0.5, 1.0};
@@ -485,6 +513,8 @@ int sb2_finalize(sb2_sim* sim) {
     Sb2Species& sp = sim->species[s];
     b.sp[s].geo = sp.geo;
     b.sp[s].has_diff = sp.has_diff ? 1 : 0;
+    b.sp[s].fast2d = (sp.has_diff && sim->g.dim == 2 && sp.dkind[0] == SB2_SRC_CONST && sp.dkind[1] == SB2_SRC_CONST &&
+                      !b.divide[0] && !b.divide[1]) ? 1 : 0;
     for (int a = 0; a < 3; ++a) {
       b.sp[s].dkind[a] = sp.dkind[a]; b.sp[s].dsrc[a] = sp.dsrc[a];
       if (sp.dkind[a] == SB2_SRC_FIELD && (sp.dsrc[a] < 0 || sp.dsrc[a] >= (int)sim->d_fields.size()))
@@ -500,9 +530,10 @@ int sb2_finalize(sb2_sim* sim) {
   for (size_t i = 0; i < sim->program.size(); ++i) {
     const uint32_t code = sim->program[i] & 0xffffu;
     const int opc = (int)(code / SB2_MAX_DEPTH), d = (int)(code % SB2_MAX_DEPTH);
-    if (opc != OPC_MASK && opc != OPC_ACCSUB && opc != OPC_ACCADD && d + 1 > b.depth) b.depth = d + 1;
+    if (opc < OPC_MASK && d + 1 > b.depth) b.depth = d + 1;
   }
   memcpy(b.tok, sim->program.data(), sizeof(uint32_t) * sim->program.size());
+  b.tok[sim->program.size()] = enc(OPC_END, 0, 0);
 
   // boundary-condition lists (Neumann flux / Dirichlet overwrite), built from the host flag copies
   std::string err;

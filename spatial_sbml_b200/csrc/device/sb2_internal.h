@@ -31,6 +31,9 @@ enum Sb2Opc {
   OPC_MASK,   // statement mask = cell in domain of geo arg
   OPC_ACCSUB, // acc[d] -= consts[arg] * r[0]   (d = species index here)
   OPC_ACCADD, // acc[d] += consts[arg] * r[0]
+  OPC_ACCSUB1, OPC_ACCADD1,    // stoichiometry exactly 1.0: acc[d] -/+= r[0]   (1.0 * x == x bit for bit)
+  OPC_ACCSUBC1, OPC_ACCADDC1,  // constant law, stoichiometry 1.0: acc[d] -/+= consts[arg]
+  OPC_ACCSUBM, OPC_ACCADDM,    // like ACCSUB / ACCADD, but only on the cells selected by the last MASK
   OPC_COUNT
 };
 
@@ -45,6 +48,7 @@ struct Sb2SpeciesArgs {
   const double* k1;
   int32_t geo;
   int32_t has_diff;
+  int32_t fast2d;    // 2-D, uniform coefficients on both axes, dx^2 == dy^2 == 1: straight-line interior stencil
   int32_t dkind[3];  // SB2_SRC_*
   int32_t dsrc[3];
 };
@@ -68,7 +72,7 @@ struct Sb2StageArgs {
   Sb2SpeciesArgs sp[SB2_MAX_SPECIES];
   const uint8_t* flags[SB2_MAX_GEOS];
   const double* fields[SB2_MAX_FIELDS];
-  uint32_t tok[SB2_MAX_TOKENS];
+  uint32_t tok[SB2_MAX_TOKENS + 1];  // + trailing OPC_END (the interpreter fetches one token ahead)
   double consts[SB2_MAX_CONSTS];
 };
 

@@ -27,8 +27,8 @@ __global__ void __launch_bounds__(256) combine_kernel(const __grid_constant__ Sb
     const double2 k1 = *reinterpret_cast<const double2*>(A.k[s][1] + idx);
     const double2 k2 = *reinterpret_cast<const double2*>(A.k[s][2] + idx);
     const double2 k3 = *reinterpret_cast<const double2*>(A.k[s][3] + idx);
-    if (f.x & SB2_F_DOMAIN) u.x = dadd(u.x, ddiv(dmul(A.dt, dadd(dadd(dadd(k0.x, dmul(2.0, k1.x)), dmul(2.0, k2.x)), k3.x)), 6.0));
-    if (f.y & SB2_F_DOMAIN) u.y = dadd(u.y, ddiv(dmul(A.dt, dadd(dadd(dadd(k0.y, dmul(2.0, k1.y)), dmul(2.0, k2.y)), k3.y)), 6.0));
+    if (f.x & SB2_F_DOMAIN) u.x = dadd(u.x, ddiv_pos(dmul(A.dt, dadd(dadd(dadd(k0.x, dmul(2.0, k1.x)), dmul(2.0, k2.x)), k3.x)), 6.0));
+    if (f.y & SB2_F_DOMAIN) u.y = dadd(u.y, ddiv_pos(dmul(A.dt, dadd(dadd(dadd(k0.y, dmul(2.0, k1.y)), dmul(2.0, k2.y)), k3.y)), 6.0));
     *reinterpret_cast<double2*>(A.u[s] + idx) = u;
   }
 }

@@ -155,10 +155,13 @@ __global__ void __launch_bounds__(NT, (NS * NP <= 2) ? 5 : (NS * NP <= 4) ? 3 : 
       fetch_flags(y + 1, fn);
     }
 
-    uint32_t anyf = 0;
+    uint32_t anyf = 0, allf = 0xffffffffu;
 #pragma unroll
-    for (int c = 0; c < NC; ++c) anyf |= fl[c];
+    for (int c = 0; c < NC; ++c) { anyf |= fl[c]; allf &= fl[c]; }
     const bool mine = (anyf & 0x01010101u) != 0;
+    // every cell of this thread is an interior cell of every geometry: flag byte == SB2_F_DOMAIN, no
+    // boundary bit anywhere → the stencil and the output run without a single per-cell test
+    const bool interior = (anyf == allf) && (anyf == (0x01010101u >> (8 * (4 - A.G))));
     // rows / warps entirely outside every domain skip the arithmetic (masked geometries)
     if (__any_sync(0xffffffffu, mine)) {
       const int slot = y & (RING - 1);
@@ -184,14 +187,16 @@ __global__ void __launch_bounds__(NT, (NS * NP <= 2) ? 5 : (NS * NP <= 4) ? 3 : 
       for (int d = 0; d < DEPTH; ++d)
 #pragma unroll
         for (int c = 0; c < NC; ++c) r[d][c] = 0.0;
-      bool mk[NC];
+      bool mk[NC];  // set by MASK, read by the ACC*M forms only
 #pragma unroll
-      for (int c = 0; c < NC; ++c) mk[c] = true;
+      for (int c = 0; c < NC; ++c) mk[c] = false;
       const double* wrow = wsm + slot * TXP + 2 + 2 * tx;  // + s*RING*TXP selects the species, + p*2*NT the pair
 
+      uint32_t tnext = A.tok[0];
 #pragma unroll 1
       for (int pc = 0; pc < A.ntok; ++pc) {
-        const uint32_t t = A.tok[pc];
+        const uint32_t t = tnext;
+        tnext = A.tok[pc + 1];  // the stream ends with OPC_END, so this is always a valid fetch
         const uint32_t arg = t >> 16;
         switch (t & 0xffffu) {
 #define LOADV(v, p) const double2 v = *reinterpret_cast<const double2*>(wrow + arg * (RING * TXP) + (p) * 2 * NT)
@@ -243,11 +248,24 @@ __global__ void __launch_bounds__(NT, (NS * NP <= 2) ? 5 : (NS * NP <= 4) ? 3 : 
             for (int c = 0; c < NC; ++c) mk[c] = (fl[c] >> (8 * arg)) & 1u;
           } break;
           // delta -= stoich*rate (reactants) / += (products, rate rules); calcPDE.cpp:432-449
+#define SI(s) ((s) < NS ? (s) : 0)
 #define C_ACC(s) \
   case SB2_CODE(OPC_ACCSUB, s): if (s < NS) { const double st = A.consts[arg]; \
-      _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) if (mk[c_]) acc[s < NS ? s : 0][c_] = dsub(acc[s < NS ? s : 0][c_], dmul(st, RD(0)[c_])); } break; \
+      _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) acc[SI(s)][c_] = dsub(acc[SI(s)][c_], dmul(st, RD(0)[c_])); } break; \
   case SB2_CODE(OPC_ACCADD, s): if (s < NS) { const double st = A.consts[arg]; \
-      _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) if (mk[c_]) acc[s < NS ? s : 0][c_] = dadd(acc[s < NS ? s : 0][c_], dmul(st, RD(0)[c_])); } break;
+      _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) acc[SI(s)][c_] = dadd(acc[SI(s)][c_], dmul(st, RD(0)[c_])); } break; \
+  case SB2_CODE(OPC_ACCSUB1, s): if (s < NS) { \
+      _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) acc[SI(s)][c_] = dsub(acc[SI(s)][c_], RD(0)[c_]); } break; \
+  case SB2_CODE(OPC_ACCADD1, s): if (s < NS) { \
+      _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) acc[SI(s)][c_] = dadd(acc[SI(s)][c_], RD(0)[c_]); } break; \
+  case SB2_CODE(OPC_ACCSUBC1, s): if (s < NS) { const double cv = A.consts[arg]; \
+      _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) acc[SI(s)][c_] = dsub(acc[SI(s)][c_], cv); } break; \
+  case SB2_CODE(OPC_ACCADDC1, s): if (s < NS) { const double cv = A.consts[arg]; \
+      _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) acc[SI(s)][c_] = dadd(acc[SI(s)][c_], cv); } break; \
+  case SB2_CODE(OPC_ACCSUBM, s): if (s < NS) { const double st = A.consts[arg]; \
+      _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) if (mk[c_]) acc[SI(s)][c_] = dsub(acc[SI(s)][c_], dmul(st, RD(0)[c_])); } break; \
+  case SB2_CODE(OPC_ACCADDM, s): if (s < NS) { const double st = A.consts[arg]; \
+      _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) if (mk[c_]) acc[SI(s)][c_] = dadd(acc[SI(s)][c_], dmul(st, RD(0)[c_])); } break;
           REP_D0(C_ACC)
           // every code of the dense range gets a case, so that the switch compiles to one jump table
 #define C_NONE0(opc) case SB2_CODE(opc, 0): break;
@@ -288,6 +306,30 @@ __global__ void __launch_bounds__(NT, (NS * NP <= 2) ? 5 : (NS * NP <= 4) ? 3 : 
           const double* cur = base + slot * TXP;
           const double* up = base + ((y + 1) & (RING - 1)) * TXP;
           const double* dn = base + ((y - 1) & (RING - 1)) * TXP;
+          if (interior && (sp.fast2d || !sp.has_diff) && MODE != MODE_FINAL) {
+            // straight-line 5-point stencil, additions in the reference's order Xp, Xm, Yp, Ym
+            const double dcx = sp.has_diff ? A.consts[sp.dsrc[0]] : 0.0, dcy = sp.has_diff ? A.consts[sp.dsrc[1]] : 0.0;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+              double a0 = acc[s][2 * p], a1 = acc[s][2 * p + 1];
+              if (sp.has_diff) {
+                const double2 wc = *reinterpret_cast<const double2*>(cur + p * 2 * NT);
+                const double wl = cur[p * 2 * NT - 1], wr = cur[p * 2 * NT + 2];
+                const double2 wu = *reinterpret_cast<const double2*>(up + p * 2 * NT);
+                const double2 wd = *reinterpret_cast<const double2*>(dn + p * 2 * NT);
+                a0 = dadd(a0, dmul(dcx, dsub(wc.y, wc.x)));
+                a0 = dadd(a0, dmul(dcx, dsub(wl, wc.x)));
+                a0 = dadd(a0, dmul(dcy, dsub(wu.x, wc.x)));
+                a0 = dadd(a0, dmul(dcy, dsub(wd.x, wc.x)));
+                a1 = dadd(a1, dmul(dcx, dsub(wr, wc.y)));
+                a1 = dadd(a1, dmul(dcx, dsub(wc.x, wc.y)));
+                a1 = dadd(a1, dmul(dcy, dsub(wu.y, wc.y)));
+                a1 = dadd(a1, dmul(dcy, dsub(wd.y, wc.y)));
+              }
+              *reinterpret_cast<double2*>(sp.kout + idx0 + p * 2 * NT) = make_double2(a0, a1);
+            }
+            continue;
+          }
 #pragma unroll
           for (int p = 0; p < NP; ++p) {
             const int64_t idx = idx0 + p * 2 * NT;
@@ -304,7 +346,7 @@ __global__ void __launch_bounds__(NT, (NS * NP <= 2) ? 5 : (NS * NP <= 4) ? 3 : 
                 const double wl = cur[p * 2 * NT - 1], wr = cur[p * 2 * NT + 2];
                 auto term = [&](double dc, double wn, double w0) {
                   double t = dmul(dc, dsub(wn, w0));
-                  if (A.divide[0]) t = ddiv(t, A.dx2[0]);
+                  if (A.divide[0]) t = ddiv_pos(t, A.dx2[0]);
                   return t;
                 };
                 if (f0 & SB2_F_DOMAIN) {
@@ -325,7 +367,7 @@ __global__ void __launch_bounds__(NT, (NS * NP <= 2) ? 5 : (NS * NP <= 4) ? 3 : 
                 const double2 wd = *reinterpret_cast<const double2*>(dn + p * 2 * NT);
                 auto term = [&](double dc, double wn, double w0) {
                   double t = dmul(dc, dsub(wn, w0));
-                  if (A.divide[1]) t = ddiv(t, A.dx2[1]);
+                  if (A.divide[1]) t = ddiv_pos(t, A.dx2[1]);
                   return t;
                 };
                 if (f0 & SB2_F_DOMAIN) {
@@ -351,7 +393,7 @@ __global__ void __launch_bounds__(NT, (NS * NP <= 2) ? 5 : (NS * NP <= 4) ? 3 : 
                 }
                 auto term = [&](double dc, double wn, double w0) {
                   double t = dmul(dc, dsub(wn, w0));
-                  if (A.divide[2]) t = ddiv(t, A.dx2[2]);
+                  if (A.divide[2]) t = ddiv_pos(t, A.dx2[2]);
                   return t;
                 };
                 if (f0 & SB2_F_DOMAIN) {
@@ -376,8 +418,8 @@ __global__ void __launch_bounds__(NT, (NS * NP <= 2) ? 5 : (NS * NP <= 4) ? 3 : 
                 // value += dt*(k0 + 2.0*k1 + 2.0*k2 + k3)/6.0, spatialsimulator.cpp:1535
                 const double2 u = cu[s][p], k0 = ck0[s][p], k1 = ck1[s][p], k2 = ck2[s][p];
                 double2 o = u;
-                if (in0) o.x = dadd(u.x, ddiv(dmul(A.dt, dadd(dadd(dadd(k0.x, dmul(2.0, k1.x)), dmul(2.0, k2.x)), a0)), 6.0));
-                if (in1) o.y = dadd(u.y, ddiv(dmul(A.dt, dadd(dadd(dadd(k0.y, dmul(2.0, k1.y)), dmul(2.0, k2.y)), a1)), 6.0));
+                if (in0) o.x = dadd(u.x, ddiv_pos(dmul(A.dt, dadd(dadd(dadd(k0.x, dmul(2.0, k1.x)), dmul(2.0, k2.x)), a0)), 6.0));
+                if (in1) o.y = dadd(u.y, ddiv_pos(dmul(A.dt, dadd(dadd(dadd(k0.y, dmul(2.0, k1.y)), dmul(2.0, k2.y)), a1)), 6.0));
                 *reinterpret_cast<double2*>(sp.u_out + idx) = o;
               }
             }
