@@ -1,0 +1,67 @@
+// rd_dispatch.cu — variant table of the rd_stage kernel family and the strip-class map kernel.
+#include "sb2_internal.h"
+
+cudaError_t sb2_rd_launch_v0(const Sb2StageArgs& a, cudaStream_t stream);
+cudaError_t sb2_rd_launch_v1(const Sb2StageArgs& a, cudaStream_t stream);
+cudaError_t sb2_rd_launch_v2(const Sb2StageArgs& a, cudaStream_t stream);
+cudaError_t sb2_rd_launch_v3(const Sb2StageArgs& a, cudaStream_t stream);
+cudaError_t sb2_rd_launch_v4(const Sb2StageArgs& a, cudaStream_t stream);
+
+namespace {
+// id, max species, cell pairs per thread, warps per CTA, expression stack depth
+const Sb2RdVariant kVariants[] = {
+  {0, 2, 4, 4, 2}, {1, 2, 2, 8, 4}, {2, 2, 1, 8, 8}, {3, 4, 2, 4, 4}, {4, 4, 1, 4, 8},
+};
+
+// One warp per (row, strip): class 1 when every cell of the strip row carries exactly SB2_F_DOMAIN in every
+// geometry (interior cell, no boundary bit), class 2 when no cell is in any domain, else 0.
+__global__ void __launch_bounds__(256) classify_kernel(const uint8_t* f0, const uint8_t* f1, const uint8_t* f2, const uint8_t* f3,
+                                                       int G, int nx, int nrows, int64_t P, int64_t first, int sw, uint8_t* cls, int nstrips) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= nrows * nstrips) return;
+  const int row = warp / nstrips, strip = warp % nstrips;
+  const uint8_t* fl[4] = {f0, f1, f2, f3};
+  bool all_interior = true, any_domain = false;
+  for (int i = lane; i < sw; i += 32) {
+    const int x = strip * sw + i;
+    for (int g = 0; g < G; ++g) {
+      const uint8_t v = x < nx ? fl[g][first + (int64_t)row * P + x] : 0;
+      all_interior = all_interior && v == SB2_F_DOMAIN;
+      any_domain = any_domain || (v & SB2_F_DOMAIN);
+    }
+  }
+  all_interior = __all_sync(0xffffffffu, all_interior);
+  any_domain = __any_sync(0xffffffffu, any_domain);
+  if (lane == 0) cls[warp] = all_interior ? 1 : any_domain ? 0 : 2;
+}
+}  // namespace
+
+int sb2_rd_pick_variant(int dim, int nx, int nspecies, int depth, Sb2RdVariant* out) {
+  if (dim != 2 || nspecies < 1 || nspecies > 4) return -1;
+  int id;
+  if (nspecies <= 2) id = (depth <= 2 && nx >= 1024) ? 0 : (depth <= 4 && nx >= 192) ? 1 : 2;
+  else id = (depth <= 4 && nx >= 192) ? 3 : 4;
+  if (depth > kVariants[id].depth) return -1;
+  if (out) *out = kVariants[id];
+  return id;
+}
+
+cudaError_t sb2_rd_launch(const Sb2StageArgs& a, cudaStream_t stream) {
+  switch (a.rd_variant) {
+    case 0: return sb2_rd_launch_v0(a, stream);
+    case 1: return sb2_rd_launch_v1(a, stream);
+    case 2: return sb2_rd_launch_v2(a, stream);
+    case 3: return sb2_rd_launch_v3(a, stream);
+    case 4: return sb2_rd_launch_v4(a, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t sb2_rd_classify(const uint8_t* const* flags, int G, int nx, int nrows, int64_t P, int64_t first, int sw,
+                            uint8_t* cls, int nstrips, cudaStream_t stream) {
+  const int64_t warps = (int64_t)nrows * nstrips;
+  const int blocks = (int)((warps * 32 + 255) / 256);
+  classify_kernel<<<blocks, 256, 0, stream>>>(flags[0], G > 1 ? flags[1] : nullptr, G > 2 ? flags[2] : nullptr,
+                                               G > 3 ? flags[3] : nullptr, G, nx, nrows, P, first, sw, cls, nstrips);
+  return cudaGetLastError();
+}

@@ -1,0 +1,555 @@
+// rd_stage.cuh — the fused reaction–diffusion RK-stage kernel for 2-D grids (sm_100a), second design.
+//
+// One launch computes, for every volume cell of the slab and every staged species,
+//     k_m = sum over reactions / rate rules (bytecode interpreter)  +  diffusion stencil
+// and, on the last stage, the RK4 combine u_new = u + dt*(k0 + 2k1 + 2k2 + k3)/6 — the work the
+// reference spreads over reversePolishRK (calcPDE.cpp:224-451), calcDiffusion (calcPDE.cpp:453-562)
+// and updateSpecies (spatialsimulator.cpp:1518-1544), one full-grid pass per reaction and per
+// species.  Each species field is read once per stage from HBM.
+//
+// Data movement and schedule
+//   * A CTA of W warps owns a strip of SW = 64*NP consecutive x cells and a range of rows; it walks the
+//     rows in batches of W.  In batch b warp j
+//       (1) waits for the raw row  y+1  (y = Y_b + j) that the TMA unit copied into the warp's private
+//           slot of shared memory (cp.async.bulk global→shared, completion on the warp's mbarrier),
+//       (2) turns it into the stage input  w = u + rk[m]*dt*k_{m-1}  (calcPDE.cpp:247-248), ONCE per
+//           cell, and parks it in a ring of w rows shared by the CTA,
+//       (3) re-arms its mbarrier and issues the bulk copy of the row it needs in the next batch, which
+//           is in flight during everything that follows,
+//       (4) __syncthreads()  — the only CTA-wide synchronisation, once per W rows —
+//       (5) evaluates the reaction bytecode and the 5-point stencil of row y from the w ring (rows
+//           y-1, y, y+1) and stores k_m (or the new u) straight from registers with 16-byte stores.
+//     The ring holds 2W+2 rows, so a warp that runs ahead into step (2) of the next batch never
+//     overwrites a row another warp still reads in step (5).
+//   * Each thread owns NP pairs of adjacent cells; pair p of lane l sits at x0 + 64p + 2l, so every
+//     16-byte shared or global access of a warp covers 512 contiguous bytes.
+//   * A per-(row, strip) class byte, computed once at finalize, says whether every cell of the strip row
+//     is an interior cell of every geometry (class 1: straight-line stencil, no per-cell test), lies
+//     outside every domain (class 2: nothing to compute) or needs the per-cell flag logic (class 0).
+//   * The token stream and the constants table arrive as a __grid_constant__ kernel parameter, i.e. in
+//     constant memory.  The program counter is warp-uniform: a token fetch is a uniform constant load
+//     and the dispatch one indexed branch through a dense jump table; each case acts on all 2*NP cells
+//     of the thread with compile-time register indices (tokens carry their stack slot).
+//   * The last stage reads u, k0, k1, k2 of its own cells with plain 16-byte loads; lane 0 asks for the
+//     k0 / k1 rows one batch ahead with cp.async.bulk.prefetch.L2, u and k2 were just staged through L2.
+//
+// Arithmetic follows the reference's evaluation order with explicit round-to-nearest intrinsics
+// (never contracted into FMAs), so results are bit-identical to the CPU code for + - * / and
+// comparisons.
+#ifndef SB2_RD_STAGE_CUH_
+#define SB2_RD_STAGE_CUH_
+#include "sb2_internal.h"
+#include "sb2_ops.cuh"
+
+namespace {
+namespace rd {
+
+enum { MODE_FIRST = 0, MODE_MIDDLE = 1, MODE_FINAL = 2 };
+
+// ---------------------------------------------------------------------------------------------
+// PTX: mbarrier + bulk asynchronous copy (TMA, non-tensor form)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+// Bounded wait: a copy that never lands (a bug) ends in wrong results and a failed test, not in a hung GPU.
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return true;
+    if (clock64() - t0 > 400000000LL) return false;  // ~0.2 s
+  }
+}
+
+template <int NP, int W>
+struct Geo {
+  static constexpr int NC = 2 * NP;     // cells per thread
+  static constexpr int SW = 64 * NP;    // cells per strip row
+  static constexpr int SWP = SW + 4;    // [pad][left halo][SW cells][right halo][pad]; cell i at index i + 2
+  static constexpr int RW = 2 * W + 2;  // rows of the w ring
+};
+
+// Division by 6.0 for the RK combine: q = RN(x * RN(1/6)), r = x - 6q (exact in an FMA), q' = RN(q + r*RN(1/6))
+// is the correctly rounded quotient whenever no intermediate leaves the normal range (Markstein 1990; the
+// significand of 6.0 is not all ones).  Outside a generous exponent window the true division runs.
+__device__ __forceinline__ double div6(double x) {
+  const int hi = __double2hiint(x) & 0x7ff00000;
+  if (hi > 0x08000000 && hi < 0x78000000) {
+    const double y = 0.16666666666666666;  // RN(1/6)
+    const double q = __dmul_rn(x, y);
+    const double r = __fma_rn(-q, 6.0, x);
+    return __fma_rn(r, y, q);
+  }
+  return ddiv_pos(x, 6.0);
+}
+
+#define RD_REP_D0(M) M(0) M(1) M(2) M(3) M(4) M(5) M(6) M(7)
+#define RD_REP_D1(M) M(1) M(2) M(3) M(4) M(5) M(6) M(7)
+
+template <int NS, int NP, int W, int MODE, int DEPTH, int MINB>
+__global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_constant__ Sb2StageArgs A) {
+  using G = Geo<NP, W>;
+  constexpr int NC = G::NC, SW = G::SW, SWP = G::SWP, RW = G::RW;
+  constexpr int NARR = (MODE == MODE_FIRST) ? 1 : 2;  // arrays per species in a raw slot: u (, k_{m-1})
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // [W mbarriers, 128 B] [w ring: S x RW x SWP] [raw slots: W x S x NARR x SWP]
+  const int S = A.S;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  double* wring = reinterpret_cast<double*>(smem_raw + 128);
+  double* rawbase = wring + (size_t)S * RW * SWP;
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int x0 = blockIdx.x * SW;
+  const int yb = A.row_begin + blockIdx.y * A.rows_per_block;
+  const int ye = min(yb + A.rows_per_block, A.row_end);
+  if (yb >= ye) return;
+
+  double* myraw = rawbase + (size_t)warp * S * NARR * SWP;
+  const uint32_t mybar = smem_addr(&bars[warp]);
+  const uint32_t myraw_s = smem_addr(myraw);
+  const uint32_t row_bytes = SWP * sizeof(double);
+
+  if (lane == 0) {
+    mbar_init(mybar, 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+
+  // lane 0: bulk copy of raw row r (u and k_{m-1} of every species, halo columns included) into the warp's slot
+  auto issue_row = [&](int r) {
+    mbar_expect_tx(mybar, row_bytes * NARR * S);
+    const int64_t g = A.first + (int64_t)r * A.P + x0 - 2;
+    for (int s = 0; s < S; ++s) {
+      bulk_g2s(myraw_s + (s * NARR) * row_bytes, A.sp[s].u + g, row_bytes, mybar);
+      if (MODE != MODE_FIRST) bulk_g2s(myraw_s + (s * NARR + 1) * row_bytes, A.sp[s].kprev + g, row_bytes, mybar);
+    }
+  };
+  auto prefetch_combine = [&](int r) {
+    const int64_t g = A.first + (int64_t)r * A.P + x0;
+    for (int s = 0; s < S; ++s) {
+      bulk_prefetch_l2(A.sp[s].k0 + g, SW * sizeof(double));
+      bulk_prefetch_l2(A.sp[s].k1 + g, SW * sizeof(double));
+    }
+  };
+
+  bool active[NP];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) active[p] = x0 + p * 64 + 2 * lane < A.nx;
+
+  // batch b = -1 is the prologue: warps W-2 and W-1 stage rows yb-1 and yb, nobody computes
+  int wrow = yb - W + warp + 1;  // row this warp turns into w in the current batch
+  if (wrow >= yb - 1 && wrow <= ye && lane == 0) issue_row(wrow);
+  uint32_t parity = 0;
+
+  for (int Y = yb - W; Y < ye; Y += W, wrow += W) {
+    const int srow = Y + warp;  // row this warp computes in the current batch
+    const bool compute = (Y >= yb) && (srow < ye);
+    int cls = 2;
+    if (compute) cls = A.carry ? 0 : (int)A.cls[(int64_t)srow * A.nstrips + blockIdx.x];
+
+    // (1) + (2): raw row → w ring
+    if (wrow >= yb - 1 && wrow <= ye) {
+      if (!mbar_wait(mybar, parity) && A.dbg && lane == 0) {
+        if (atomicAdd(&A.dbg[0], 1u) == 0) { A.dbg[1] = blockIdx.x; A.dbg[2] = blockIdx.y; A.dbg[3] = warp; A.dbg[4] = (uint32_t)wrow; A.dbg[5] = parity; A.dbg[6] = (uint32_t)yb; A.dbg[7] = (uint32_t)ye; }
+      }
+      parity ^= 1;
+      const int wslot = (wrow - (yb - 1)) % RW;
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        if (s < S) {
+          const double* ru = myraw + (s * NARR) * SWP;
+          const double* rk = ru + SWP;
+          double* wr = wring + ((size_t)s * RW + wslot) * SWP;
+#pragma unroll
+          for (int p = 0; p < NP; ++p) {
+            const int i = 2 + p * 64 + 2 * lane;
+            double2 w = *reinterpret_cast<const double2*>(ru + i);
+            if (MODE != MODE_FIRST) {
+              const double2 k = *reinterpret_cast<const double2*>(rk + i);
+              w.x = dadd(w.x, dmul(A.cdt, k.x));  // u + ((rk[m]*dt) * k), calcPDE.cpp:247-248
+              w.y = dadd(w.y, dmul(A.cdt, k.y));
+            }
+            *reinterpret_cast<double2*>(wr + i) = w;
+          }
+          if (lane < 2) {  // halo columns x0-1 and x0+SW
+            const int i = lane == 0 ? 1 : SW + 2;
+            double w = ru[i];
+            if (MODE != MODE_FIRST) w = dadd(w, dmul(A.cdt, rk[i]));
+            wr[i] = w;
+          }
+        }
+      }
+      __syncwarp();
+    }
+    // (3) the slot is free again: fetch the row of the next batch (in the prologue this is the first fetch of
+    // the warps that had nothing to stage yet)
+    if (lane == 0) {
+      const int nrow = wrow + W;
+      if (nrow >= yb - 1 && nrow <= ye) issue_row(nrow);
+      if (MODE == MODE_FINAL && srow + W >= yb && srow + W < ye) prefetch_combine(srow + W);
+    }
+
+    // per-cell flag bytes of all geometries (byte g = geometry g); only class-0 rows look at them
+    uint32_t fl[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) fl[c] = 0x01010101u;
+    if (cls == 0) {
+      const int64_t base = A.first + (int64_t)srow * A.P + x0 + 2 * lane;
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        fl[2 * p] = 0; fl[2 * p + 1] = 0;
+        if (active[p]) {
+#pragma unroll
+          for (int g = 0; g < SB2_MAX_GEOS; ++g) {
+            if (g < A.G) {
+              const uchar2 v = *reinterpret_cast<const uchar2*>(A.flags[g] + base + p * 64);
+              fl[2 * p] |= (uint32_t)v.x << (8 * g);
+              fl[2 * p + 1] |= (uint32_t)v.y << (8 * g);
+            }
+          }
+        }
+      }
+    }
+
+    __syncthreads();  // (4)
+    if (!compute) continue;
+
+    const int64_t idx0 = A.first + (int64_t)srow * A.P + x0 + 2 * lane;  // + 64p for pair p
+    if (cls == 2) {
+      // nothing of this strip row lies in a domain: k_m = 0 / u unchanged
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        if (s < S) {
+#pragma unroll
+          for (int p = 0; p < NP; ++p) {
+            if (!active[p]) continue;
+            const int64_t idx = idx0 + p * 64;
+            if (MODE != MODE_FINAL) *reinterpret_cast<double2*>(A.sp[s].kout + idx) = make_double2(0.0, 0.0);
+            else *reinterpret_cast<double2*>(A.sp[s].u_out + idx) = *reinterpret_cast<const double2*>(A.sp[s].u + idx);
+          }
+        }
+      }
+      continue;
+    }
+    if (cls == 0) {
+      uint32_t anyf = 0;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) anyf |= fl[c];
+      if (!__any_sync(0xffffffffu, (anyf & 0x01010101u) != 0) && !A.carry) {
+        // this warp's cells are all outside (a class-0 strip row is mixed only as a whole)
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          if (s < S) {
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+              if (!active[p]) continue;
+              const int64_t idx = idx0 + p * 64;
+              if (MODE != MODE_FINAL) *reinterpret_cast<double2*>(A.sp[s].kout + idx) = make_double2(0.0, 0.0);
+              else *reinterpret_cast<double2*>(A.sp[s].u_out + idx) = *reinterpret_cast<const double2*>(A.sp[s].u + idx);
+            }
+          }
+        }
+        continue;
+      }
+    }
+
+    const int q = srow - (yb - 1);  // >= 1
+    const int slot_c = q % RW, slot_u = (q + 1) % RW, slot_d = (q - 1) % RW;
+
+    double acc[NS][NC];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        acc[s][2 * p] = 0.0; acc[s][2 * p + 1] = 0.0;
+        if (A.carry && s < S && active[p]) {
+          const double2 c = *reinterpret_cast<const double2*>(A.sp[s].kout + idx0 + p * 64);
+          acc[s][2 * p] = c.x; acc[s][2 * p + 1] = c.y;
+        }
+      }
+    }
+
+    // ---------------- reaction / rate-rule bytecode ----------------
+    {
+      double r[DEPTH][NC];  // RD(d): slot d of the expression stack; slots >= DEPTH do not exist in this variant
+#define RD(d) r[(d) < DEPTH ? (d) : 0]
+#define LIVE(d) if ((d) < DEPTH)
+      bool mk[NC];  // set by MASK, read by the ACC*M forms only
+#pragma unroll
+      for (int c = 0; c < NC; ++c) mk[c] = false;
+      const double* wop = wring + slot_c * SWP + 2 + 2 * lane;  // + s*RW*SWP selects the species, + 64p the pair
+
+      uint32_t tnext = A.tok[0];
+      int pc = 0;
+#pragma unroll 1
+      for (;;) {
+        const uint32_t t = tnext;
+        tnext = A.tok[++pc];  // the stream ends with OPC_END, whose successor slot exists
+        const uint32_t arg = t >> 16;
+        switch (t & 0xffffu) {
+#define LOADV(v, p) const double2 v = *reinterpret_cast<const double2*>(wop + arg * (RW * SWP) + (p) * 64)
+#define C_PUSHC(d) case SB2_CODE(OPC_PUSHC, d): LIVE(d) { const double c = A.consts[arg]; _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) RD(d)[c_] = c; } break;
+          RD_REP_D0(C_PUSHC)
+#define C_PUSHV(d) case SB2_CODE(OPC_PUSHV, d): LIVE(d) { _Pragma("unroll") for (int p = 0; p < NP; ++p) { LOADV(v, p); RD(d)[2 * p] = v.x; RD(d)[2 * p + 1] = v.y; } } break;
+          RD_REP_D0(C_PUSHV)
+#define C_PUSHF(d) case SB2_CODE(OPC_PUSHF, d): LIVE(d) { _Pragma("unroll") for (int p = 0; p < NP; ++p) { double2 v = make_double2(0.0, 0.0); if (active[p]) v = *reinterpret_cast<const double2*>(A.fields[arg] + idx0 + p * 64); RD(d)[2 * p] = v.x; RD(d)[2 * p + 1] = v.y; } } break;
+          RD_REP_D0(C_PUSHF)
+#define C_BIN(opc, d, EXPR) case SB2_CODE(opc, d): LIVE(d) { _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) { const double a = RD(d - 1)[c_], b = RD(d)[c_]; RD(d - 1)[c_] = (EXPR); } } break;
+#define C_ADD(d) C_BIN(OPC_ADD, d, dadd(a, b))
+#define C_SUB(d) C_BIN(OPC_SUB, d, dsub(a, b))
+#define C_MUL(d) C_BIN(OPC_MUL, d, dmul(a, b))
+#define C_DIV(d) C_BIN(OPC_DIV, d, ddiv(a, b))
+#define C_GEQ(d) C_BIN(OPC_GEQ, d, (a >= b) ? 1.0 : 0.0)
+#define C_GT(d) C_BIN(OPC_GT, d, (a > b) ? 1.0 : 0.0)
+#define C_LEQ(d) C_BIN(OPC_LEQ, d, (a <= b) ? 1.0 : 0.0)
+#define C_LT(d) C_BIN(OPC_LT, d, (a < b) ? 1.0 : 0.0)
+#define C_AND(d) C_BIN(OPC_AND, d, logic_and(a, b))
+#define C_OR(d) C_BIN(OPC_OR, d, logic_or(a, b))
+          RD_REP_D1(C_ADD) RD_REP_D1(C_SUB) RD_REP_D1(C_MUL) RD_REP_D1(C_DIV)
+          RD_REP_D1(C_GEQ) RD_REP_D1(C_GT) RD_REP_D1(C_LEQ) RD_REP_D1(C_LT) RD_REP_D1(C_AND) RD_REP_D1(C_OR)
+#define C_BINC(opc, d, EXPR) case SB2_CODE(opc, d): LIVE(d) { const double b = A.consts[arg]; _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) { const double a = RD(d)[c_]; RD(d)[c_] = (EXPR); } } break;
+#define C_ADDC(d) C_BINC(OPC_ADDC, d, dadd(a, b))
+#define C_SUBC(d) C_BINC(OPC_SUBC, d, dsub(a, b))
+#define C_MULC(d) C_BINC(OPC_MULC, d, dmul(a, b))
+#define C_DIVC(d) C_BINC(OPC_DIVC, d, ddiv(a, b))
+#define C_RSUBC(d) C_BINC(OPC_RSUBC, d, dsub(b, a))
+#define C_RDIVC(d) C_BINC(OPC_RDIVC, d, ddiv(b, a))
+#define C_GEQC(d) C_BINC(OPC_GEQC, d, (a >= b) ? 1.0 : 0.0)
+#define C_GTC(d) C_BINC(OPC_GTC, d, (a > b) ? 1.0 : 0.0)
+#define C_LEQC(d) C_BINC(OPC_LEQC, d, (a <= b) ? 1.0 : 0.0)
+#define C_LTC(d) C_BINC(OPC_LTC, d, (a < b) ? 1.0 : 0.0)
+          RD_REP_D0(C_ADDC) RD_REP_D0(C_SUBC) RD_REP_D0(C_MULC) RD_REP_D0(C_DIVC) RD_REP_D0(C_RSUBC) RD_REP_D0(C_RDIVC)
+          RD_REP_D0(C_GEQC) RD_REP_D0(C_GTC) RD_REP_D0(C_LEQC) RD_REP_D0(C_LTC)
+#define C_BINV(opc, d, EXPR) case SB2_CODE(opc, d): LIVE(d) { _Pragma("unroll") for (int p = 0; p < NP; ++p) { LOADV(v, p); { const double a = RD(d)[2 * p], b = v.x; RD(d)[2 * p] = (EXPR); } { const double a = RD(d)[2 * p + 1], b = v.y; RD(d)[2 * p + 1] = (EXPR); } } } break;
+#define C_ADDV(d) C_BINV(OPC_ADDV, d, dadd(a, b))
+#define C_SUBV(d) C_BINV(OPC_SUBV, d, dsub(a, b))
+#define C_MULV(d) C_BINV(OPC_MULV, d, dmul(a, b))
+#define C_DIVV(d) C_BINV(OPC_DIVV, d, ddiv(a, b))
+          RD_REP_D0(C_ADDV) RD_REP_D0(C_SUBV) RD_REP_D0(C_MULV) RD_REP_D0(C_DIVV)
+#define C_UNARY(d) case SB2_CODE(OPC_UNARY, d): LIVE(d) { _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) RD(d)[c_] = sb2_unary((int)arg, RD(d)[c_]); } break;
+          RD_REP_D0(C_UNARY)
+#define C_BINR(d) case SB2_CODE(OPC_BINR, d): LIVE(d) { _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) RD(d - 1)[c_] = sb2_binary((int)arg, RD(d - 1)[c_], RD(d)[c_]); } break;
+          RD_REP_D1(C_BINR)
+#define C_MOV0(d) case SB2_CODE(OPC_MOV0, d): LIVE(d) { _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) RD(0)[c_] = RD(d)[c_]; } break;
+          RD_REP_D1(C_MOV0)
+#define C_MOVUP(d) case SB2_CODE(OPC_MOVUP, d): LIVE(d + 1) { _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) RD(d + 1)[c_] = RD(d)[c_]; } break;
+          RD_REP_D0(C_MOVUP)
+          // statement mask: the law only acts on cells of its own domain (spatialsimulator.cpp:1381-1390)
+          case SB2_CODE(OPC_MASK, 0): {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) mk[c] = (fl[c] >> (8 * arg)) & 1u;
+          } break;
+          // delta -= stoich*rate (reactants) / += (products, rate rules); calcPDE.cpp:432-449
+#define SI(s) ((s) < NS ? (s) : 0)
+#define C_ACC(s) \
+  case SB2_CODE(OPC_ACCSUB, s): if (s < NS) { const double st = A.consts[arg]; \
+      _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) acc[SI(s)][c_] = dsub(acc[SI(s)][c_], dmul(st, RD(0)[c_])); } break; \
+  case SB2_CODE(OPC_ACCADD, s): if (s < NS) { const double st = A.consts[arg]; \
+      _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) acc[SI(s)][c_] = dadd(acc[SI(s)][c_], dmul(st, RD(0)[c_])); } break; \
+  case SB2_CODE(OPC_ACCSUB1, s): if (s < NS) { \
+      _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) acc[SI(s)][c_] = dsub(acc[SI(s)][c_], RD(0)[c_]); } break; \
+  case SB2_CODE(OPC_ACCADD1, s): if (s < NS) { \
+      _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) acc[SI(s)][c_] = dadd(acc[SI(s)][c_], RD(0)[c_]); } break; \
+  case SB2_CODE(OPC_ACCSUBC1, s): if (s < NS) { const double cv = A.consts[arg]; \
+      _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) acc[SI(s)][c_] = dsub(acc[SI(s)][c_], cv); } break; \
+  case SB2_CODE(OPC_ACCADDC1, s): if (s < NS) { const double cv = A.consts[arg]; \
+      _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) acc[SI(s)][c_] = dadd(acc[SI(s)][c_], cv); } break; \
+  case SB2_CODE(OPC_ACCSUBM, s): if (s < NS) { const double st = A.consts[arg]; \
+      _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) if (mk[c_]) acc[SI(s)][c_] = dsub(acc[SI(s)][c_], dmul(st, RD(0)[c_])); } break; \
+  case SB2_CODE(OPC_ACCADDM, s): if (s < NS) { const double st = A.consts[arg]; \
+      _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) if (mk[c_]) acc[SI(s)][c_] = dadd(acc[SI(s)][c_], dmul(st, RD(0)[c_])); } break;
+          RD_REP_D0(C_ACC)
+          case SB2_CODE(OPC_END, 0): goto program_done;
+          default: break;
+        }
+      }
+    program_done:;
+#undef RD
+#undef LIVE
+    }
+
+    // ---------------- diffusion (calcPDE.cpp:484-559) + output ----------------
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      if (s < S) {
+        const Sb2SpeciesArgs& sp = A.sp[s];
+        const double* base = wring + (size_t)s * RW * SWP + 2 + 2 * lane;
+        const double* cur = base + slot_c * SWP;
+        const double* up = base + slot_u * SWP;
+        const double* dn = base + slot_d * SWP;
+        if (cls == 1 && (sp.fast2d || !sp.has_diff)) {
+          // every cell is an interior cell: straight-line 5-point stencil, additions in the reference's
+          // order Xp, Xm, Yp, Ym
+          const double dcx = sp.has_diff ? A.consts[sp.dsrc[0]] : 0.0, dcy = sp.has_diff ? A.consts[sp.dsrc[1]] : 0.0;
+          double2 cu[NP], ck0[NP], ck1[NP], ck2[NP];
+          if (MODE == MODE_FINAL) {
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+              const int64_t i = idx0 + p * 64;
+              cu[p] = *reinterpret_cast<const double2*>(sp.u + i);
+              ck0[p] = *reinterpret_cast<const double2*>(sp.k0 + i);
+              ck1[p] = *reinterpret_cast<const double2*>(sp.k1 + i);
+              ck2[p] = *reinterpret_cast<const double2*>(sp.kprev + i);
+            }
+          }
+#pragma unroll
+          for (int p = 0; p < NP; ++p) {
+            double a0 = acc[s][2 * p], a1 = acc[s][2 * p + 1];
+            if (sp.has_diff) {
+              const double2 wc = *reinterpret_cast<const double2*>(cur + p * 64);
+              const double wl = cur[p * 64 - 1], wr = cur[p * 64 + 2];
+              const double2 wu = *reinterpret_cast<const double2*>(up + p * 64);
+              const double2 wd = *reinterpret_cast<const double2*>(dn + p * 64);
+              a0 = dadd(a0, dmul(dcx, dsub(wc.y, wc.x)));
+              a0 = dadd(a0, dmul(dcx, dsub(wl, wc.x)));
+              a0 = dadd(a0, dmul(dcy, dsub(wu.x, wc.x)));
+              a0 = dadd(a0, dmul(dcy, dsub(wd.x, wc.x)));
+              a1 = dadd(a1, dmul(dcx, dsub(wr, wc.y)));
+              a1 = dadd(a1, dmul(dcx, dsub(wc.x, wc.y)));
+              a1 = dadd(a1, dmul(dcy, dsub(wu.y, wc.y)));
+              a1 = dadd(a1, dmul(dcy, dsub(wd.y, wc.y)));
+            }
+            if (MODE != MODE_FINAL) {
+              *reinterpret_cast<double2*>(sp.kout + idx0 + p * 64) = make_double2(a0, a1);
+            } else {
+              // value += dt*(k0 + 2.0*k1 + 2.0*k2 + k3)/6.0, spatialsimulator.cpp:1535
+              double2 o;
+              o.x = dadd(cu[p].x, div6(dmul(A.dt, dadd(dadd(dadd(ck0[p].x, dmul(2.0, ck1[p].x)), dmul(2.0, ck2[p].x)), a0))));
+              o.y = dadd(cu[p].y, div6(dmul(A.dt, dadd(dadd(dadd(ck0[p].y, dmul(2.0, ck1[p].y)), dmul(2.0, ck2[p].y)), a1))));
+              *reinterpret_cast<double2*>(sp.u_out + idx0 + p * 64) = o;
+            }
+          }
+          continue;
+        }
+        // general path: per-cell domain / boundary flags, field-valued coefficients, dx^2 != 1
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          const int64_t idx = idx0 + p * 64;
+          const uint32_t f0 = (fl[2 * p] >> (8 * sp.geo)) & 0xffu;
+          const uint32_t f1 = (fl[2 * p + 1] >> (8 * sp.geo)) & 0xffu;
+          double a0 = acc[s][2 * p], a1 = acc[s][2 * p + 1];
+          if (sp.has_diff && ((f0 | f1) & SB2_F_DOMAIN)) {
+            const double2 wc = *reinterpret_cast<const double2*>(cur + p * 64);
+            if (sp.dkind[0] != SB2_SRC_NONE) {  // axis 0: x
+              double d0, d1;
+              if (sp.dkind[0] == SB2_SRC_CONST) { d0 = d1 = A.consts[sp.dsrc[0]]; }
+              else { const double2 dv = *reinterpret_cast<const double2*>(A.fields[sp.dsrc[0]] + idx); d0 = dv.x; d1 = dv.y; }
+              const double wl = cur[p * 64 - 1], wr = cur[p * 64 + 2];
+              auto term = [&](double dc, double wn, double w0) {
+                double t = dmul(dc, dsub(wn, w0));
+                if (A.divide[0]) t = ddiv_pos(t, A.dx2[0]);
+                return t;
+              };
+              if (f0 & SB2_F_DOMAIN) {
+                if (!(f0 & SB2_F_XP)) a0 = dadd(a0, term(d0, wc.y, wc.x));
+                if (!(f0 & SB2_F_XM)) a0 = dadd(a0, term(d0, wl, wc.x));
+              }
+              if (f1 & SB2_F_DOMAIN) {
+                if (!(f1 & SB2_F_XP)) a1 = dadd(a1, term(d1, wr, wc.y));
+                if (!(f1 & SB2_F_XM)) a1 = dadd(a1, term(d1, wc.x, wc.y));
+              }
+            }
+            if (sp.dkind[1] != SB2_SRC_NONE) {  // axis 1: y
+              double d0, d1;
+              if (sp.dkind[1] == SB2_SRC_CONST) { d0 = d1 = A.consts[sp.dsrc[1]]; }
+              else { const double2 dv = *reinterpret_cast<const double2*>(A.fields[sp.dsrc[1]] + idx); d0 = dv.x; d1 = dv.y; }
+              const double2 wu = *reinterpret_cast<const double2*>(up + p * 64);
+              const double2 wd = *reinterpret_cast<const double2*>(dn + p * 64);
+              auto term = [&](double dc, double wn, double w0) {
+                double t = dmul(dc, dsub(wn, w0));
+                if (A.divide[1]) t = ddiv_pos(t, A.dx2[1]);
+                return t;
+              };
+              if (f0 & SB2_F_DOMAIN) {
+                if (!(f0 & SB2_F_YP)) a0 = dadd(a0, term(d0, wu.x, wc.x));
+                if (!(f0 & SB2_F_YM)) a0 = dadd(a0, term(d0, wd.x, wc.x));
+              }
+              if (f1 & SB2_F_DOMAIN) {
+                if (!(f1 & SB2_F_YP)) a1 = dadd(a1, term(d1, wu.y, wc.y));
+                if (!(f1 & SB2_F_YM)) a1 = dadd(a1, term(d1, wd.y, wc.y));
+              }
+            }
+          }
+          if (active[p]) {
+            const bool in0 = f0 & SB2_F_DOMAIN, in1 = f1 & SB2_F_DOMAIN;
+            if (MODE != MODE_FINAL) {
+              double2 o;
+              o.x = in0 ? a0 : 0.0;
+              o.y = in1 ? a1 : 0.0;
+              *reinterpret_cast<double2*>(sp.kout + idx) = o;
+            } else {
+              const double2 u = *reinterpret_cast<const double2*>(sp.u + idx);
+              double2 o = u;
+              if (in0 || in1) {
+                const double2 k0 = *reinterpret_cast<const double2*>(sp.k0 + idx);
+                const double2 k1 = *reinterpret_cast<const double2*>(sp.k1 + idx);
+                const double2 k2 = *reinterpret_cast<const double2*>(sp.kprev + idx);
+                if (in0) o.x = dadd(u.x, div6(dmul(A.dt, dadd(dadd(dadd(k0.x, dmul(2.0, k1.x)), dmul(2.0, k2.x)), a0))));
+                if (in1) o.y = dadd(u.y, div6(dmul(A.dt, dadd(dadd(dadd(k0.y, dmul(2.0, k1.y)), dmul(2.0, k2.y)), a1))));
+              }
+              *reinterpret_cast<double2*>(sp.u_out + idx) = o;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int NS, int NP, int W, int MODE, int DEPTH, int MINB>
+cudaError_t launch_variant(const Sb2StageArgs& a, cudaStream_t stream) {
+  using G = Geo<NP, W>;
+  const int narr = (MODE == MODE_FIRST) ? 1 : 2;
+  const size_t smem = 128 + sizeof(double) * ((size_t)a.S * G::RW * G::SWP + (size_t)W * a.S * narr * G::SWP);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(rd_stage_kernel<NS, NP, W, MODE, DEPTH, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  dim3 grid;
+  grid.x = (a.nx + G::SW - 1) / G::SW;
+  grid.y = (a.row_end - a.row_begin + a.rows_per_block - 1) / a.rows_per_block;
+  grid.z = 1;
+  if (grid.y == 0) return cudaSuccess;
+  rd_stage_kernel<NS, NP, W, MODE, DEPTH, MINB><<<grid, W * 32, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
+template <int NS, int NP, int W, int DEPTH, int MINB>
+cudaError_t launch_mode(const Sb2StageArgs& a, cudaStream_t stream) {
+  if (a.m == 0) return launch_variant<NS, NP, W, MODE_FIRST, DEPTH, MINB>(a, stream);
+  if (a.final) return launch_variant<NS, NP, W, MODE_FINAL, DEPTH, MINB>(a, stream);
+  return launch_variant<NS, NP, W, MODE_MIDDLE, DEPTH, MINB>(a, stream);
+}
+
+}  // namespace rd
+}  // namespace
+#endif  // SB2_RD_STAGE_CUH_

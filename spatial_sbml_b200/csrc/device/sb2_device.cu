@@ -6,6 +6,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <sstream>
 
@@ -58,6 +59,13 @@ struct sb2_sim {
   double cur_dt;
   bool in_step;
   double* d_scratch;  // reduction scratch
+  // rd_stage kernel (2-D): variant chosen at finalize and its strip-class map
+  Sb2RdVariant rd;
+  int rd_id;          // -1: first-generation stage kernel
+  uint8_t* d_cls;
+  int nstrips;
+  uint32_t* d_dbg;    // SB2_DEBUG=1: device debug words, checked after every stage launch
+  bool trace;         // SB2_TRACE=1: entry points report to stderr
 };
 
 namespace {
@@ -137,7 +145,12 @@ uint32_t enc(int opc, int d, int arg) { return SB2_CODE(opc, d) | ((uint32_t)arg
 // stack discipline token by token (calcPDE.cpp:244-449): operands push; an operator first pops
 // (if the stack is non-empty), binary operators then combine into the new top only if something is
 // left below, unary operators rewrite the popped slot and push it back, listed-but-empty operators
-// and unresolved names only pop.  The rate is read from slot max(sp-1, 0).
+// and unresolved names only pop.  The rate is the top of the stack.
+//
+// Constants are pushed lazily: a constant operand never occupies a stack register, it is folded into
+// the instruction that consumes it (r op c, or the commuted / reversed forms c + r, c * r, c - r,
+// c / r, c < r ...; IEEE addition and multiplication commute bit for bit).  Registers are positional:
+// the register of a materialised entry is the number of materialised entries below it.
 int compile_stmt(sb2_sim* sim, const Sb2Stmt& st, std::vector<uint32_t>& prog) {
   // accumulation targets first: a law that changes nothing is not evaluated at all
   struct Target { int species; bool subtract; double stoich; };
@@ -167,7 +180,19 @@ int compile_stmt(sb2_sim* sim, const Sb2Stmt& st, std::vector<uint32_t>& prog) {
 
   std::vector<uint32_t> out;
   if (need_mask) out.push_back(enc(OPC_MASK, 0, st.geo));
-  int sp = 0;
+  struct Ent { bool lazy; int cslot; };
+  std::vector<Ent> stk;
+  int nmat = 0;  // materialised entries on the stack
+  bool too_deep = false;
+  auto emit = [&](int opc, int d, int arg) {
+    if (d < 0 || d >= SB2_MAX_DEPTH || (opc == OPC_MOVUP && d + 1 >= SB2_MAX_DEPTH)) too_deep = true;
+    out.push_back(enc(opc, d < 0 ? 0 : d, arg));
+  };
+  auto push_mat = [&]() { Ent e = {false, 0}; stk.push_back(e); ++nmat; };
+  auto pop = [&]() { if (!stk.back().lazy) --nmat; stk.pop_back(); };
+  const int zero_slot = internal_const(sim, 0.0);
+  if (zero_slot < 0) return fail(sim, SB2_ERR_LIMIT, "constants table full");
+
   const int n = (int)st.toks.size();
   for (int i = 0; i < n; ++i) {
     const sb2_token& t = st.toks[i];
@@ -175,68 +200,86 @@ int compile_stmt(sb2_sim* sim, const Sb2Stmt& st, std::vector<uint32_t>& prog) {
       if (t.kind == SB2_TOK_VAR && t.slot >= sim->species.size()) return fail(sim, SB2_ERR_ARG, "token references unknown species");
       if (t.kind == SB2_TOK_FIELD && t.slot >= sim->d_fields.size()) return fail(sim, SB2_ERR_ARG, "token references unknown field");
       if (t.kind == SB2_TOK_CONST && t.slot >= SB2_MAX_CONSTS) return fail(sim, SB2_ERR_ARG, "token references constant slot out of range");
-      // operand immediately consumed by a binary operator → fused form acting on r[sp-1]
-      if (sp >= 1 && i + 1 < n && st.toks[i + 1].kind == SB2_TOK_OP && t.kind != SB2_TOK_FIELD) {
-        const int op = st.toks[i + 1].op;
+      if (t.kind == SB2_TOK_CONST) { Ent e = {true, (int)t.slot}; stk.push_back(e); continue; }
+      // species operand immediately consumed by + - * / on a materialised top → fused form acting on that register
+      if (t.kind == SB2_TOK_VAR && !stk.empty() && !stk.back().lazy && i + 1 < n && st.toks[i + 1].kind == SB2_TOK_OP) {
         int opc = -1;
-        const bool c = t.kind == SB2_TOK_CONST;
-        switch (op) {
-          case SB2_OP_PLUS: opc = c ? OPC_ADDC : OPC_ADDV; break;
-          case SB2_OP_MINUS: opc = c ? OPC_SUBC : OPC_SUBV; break;
-          case SB2_OP_TIMES: opc = c ? OPC_MULC : OPC_MULV; break;
-          case SB2_OP_DIVIDE: opc = c ? OPC_DIVC : OPC_DIVV; break;
-          case SB2_OP_GEQ: if (c) opc = OPC_GEQC; break;
-          case SB2_OP_GT: if (c) opc = OPC_GTC; break;
-          case SB2_OP_LEQ: if (c) opc = OPC_LEQC; break;
-          case SB2_OP_LT: if (c) opc = OPC_LTC; break;
+        switch (st.toks[i + 1].op) {
+          case SB2_OP_PLUS: opc = OPC_ADDV; break;
+          case SB2_OP_MINUS: opc = OPC_SUBV; break;
+          case SB2_OP_TIMES: opc = OPC_MULV; break;
+          case SB2_OP_DIVIDE: opc = OPC_DIVV; break;
           default: break;
         }
-        if (opc >= 0) { out.push_back(enc(opc, sp - 1, t.slot)); ++i; continue; }
+        if (opc >= 0) { emit(opc, nmat - 1, t.slot); ++i; continue; }
       }
-      if (sp >= SB2_MAX_DEPTH) return fail(sim, SB2_ERR_LIMIT, "expression stack deeper than SB2_MAX_DEPTH");
-      out.push_back(enc(t.kind == SB2_TOK_VAR ? OPC_PUSHV : t.kind == SB2_TOK_FIELD ? OPC_PUSHF : OPC_PUSHC, sp, t.slot));
-      ++sp;
-    } else {
-      if (sp > 0) --sp;
-      if (t.kind != SB2_TOK_OP) continue;  // unresolved name: pop only
-      const int op = t.op;
-      if (is_binary(op)) {
-        if (sp == 0) continue;  // nothing below: the reference leaves the stack untouched
-        int opc = -1;
-        switch (op) {
-          case SB2_OP_PLUS: opc = OPC_ADD; break;
-          case SB2_OP_MINUS: opc = OPC_SUB; break;
-          case SB2_OP_TIMES: opc = OPC_MUL; break;
-          case SB2_OP_DIVIDE: opc = OPC_DIV; break;
-          case SB2_OP_GEQ: opc = OPC_GEQ; break;
-          case SB2_OP_GT: opc = OPC_GT; break;
-          case SB2_OP_LEQ: opc = OPC_LEQ; break;
-          case SB2_OP_LT: opc = OPC_LT; break;
-          case SB2_OP_AND: opc = OPC_AND; break;
-          case SB2_OP_OR: opc = OPC_OR; break;
-          default: break;
-        }
-        if (opc >= 0) out.push_back(enc(opc, sp, 0));
-        else out.push_back(enc(OPC_BINR, sp, op));
-      } else if (is_unary(op)) {
-        if (sp >= SB2_MAX_DEPTH) return fail(sim, SB2_ERR_LIMIT, "expression stack deeper than SB2_MAX_DEPTH");
-        out.push_back(enc(OPC_UNARY, sp, op));
-        ++sp;
-      }
-      // SB2_OP_POP_ONLY and anything else: pop only
+      emit(t.kind == SB2_TOK_VAR ? OPC_PUSHV : OPC_PUSHF, nmat, t.slot);
+      push_mat();
+      continue;
     }
+    // operator (or unresolved name): pops the top first, whatever follows
+    const bool had_top = !stk.empty();
+    Ent b = {false, 0};
+    if (had_top) { b = stk.back(); pop(); }
+    if (t.kind != SB2_TOK_OP) continue;  // unresolved name: pop only
+    const int op = t.op;
+    if (is_binary(op)) {
+      if (!had_top || stk.empty()) continue;  // nothing below: the popped value is lost, the stack stays as it is
+      Ent a = stk.back();
+      int opc_rr = -1, opc_rc = -1, opc_cr = -1;  // reg op reg, reg op const, const op reg
+      switch (op) {
+        case SB2_OP_PLUS: opc_rr = OPC_ADD; opc_rc = OPC_ADDC; opc_cr = OPC_ADDC; break;
+        case SB2_OP_MINUS: opc_rr = OPC_SUB; opc_rc = OPC_SUBC; opc_cr = OPC_RSUBC; break;
+        case SB2_OP_TIMES: opc_rr = OPC_MUL; opc_rc = OPC_MULC; opc_cr = OPC_MULC; break;
+        case SB2_OP_DIVIDE: opc_rr = OPC_DIV; opc_rc = OPC_DIVC; opc_cr = OPC_RDIVC; break;
+        case SB2_OP_GEQ: opc_rr = OPC_GEQ; opc_rc = OPC_GEQC; opc_cr = OPC_LEQC; break;  // c >= r  <=>  r <= c
+        case SB2_OP_GT: opc_rr = OPC_GT; opc_rc = OPC_GTC; opc_cr = OPC_LTC; break;
+        case SB2_OP_LEQ: opc_rr = OPC_LEQ; opc_rc = OPC_LEQC; opc_cr = OPC_GEQC; break;
+        case SB2_OP_LT: opc_rr = OPC_LT; opc_rc = OPC_LTC; opc_cr = OPC_GTC; break;
+        case SB2_OP_AND: opc_rr = OPC_AND; break;
+        case SB2_OP_OR: opc_rr = OPC_OR; break;
+        default: break;
+      }
+      // nmat counts the entries still on the stack (b has been popped)
+      if (a.lazy && b.lazy) {  // materialise a, then r op c
+        emit(OPC_PUSHC, nmat, a.cslot);
+        stk.back().lazy = false; ++nmat;
+        a = stk.back();
+      }
+      if (!a.lazy && !b.lazy) {  // a in register nmat-1, b in register nmat
+        if (opc_rr >= 0) emit(opc_rr, nmat, 0); else emit(OPC_BINR, nmat, op);
+      } else if (!a.lazy && b.lazy) {
+        if (opc_rc >= 0) emit(opc_rc, nmat - 1, b.cslot);
+        else { emit(OPC_PUSHC, nmat, b.cslot); if (opc_rr >= 0) emit(opc_rr, nmat, 0); else emit(OPC_BINR, nmat, op); }
+      } else {  // a lazy, b in register nmat (it sits where a would have been)
+        if (opc_cr >= 0) emit(opc_cr, nmat, a.cslot);
+        else { emit(OPC_MOVUP, nmat, 0); emit(OPC_PUSHC, nmat, a.cslot); if (opc_rr >= 0) emit(opc_rr, nmat + 1, 0); else emit(OPC_BINR, nmat + 1, op); }
+        stk.back().lazy = false; ++nmat;
+      }
+    } else if (is_unary(op)) {
+      // st--; s[st] = f(s[st]); st++  (an empty stack leaves a stale slot 0 in the reference; 0.0 here)
+      if (!had_top) emit(OPC_PUSHC, nmat, zero_slot);
+      else if (b.lazy) emit(OPC_PUSHC, nmat, b.cslot);
+      emit(OPC_UNARY, nmat, op);
+      push_mat();
+    }
+    // SB2_OP_POP_ONLY and anything else: pop only
   }
-  if (sp > 0) --sp;
-  if (sp != 0) out.push_back(enc(OPC_MOV0, sp, 0));
-  // a law that is a single constant with unit stoichiometries needs no stack at all
-  const bool const_law = !need_mask && out.size() == 1 && (out[0] & 0xffffu) == SB2_CODE(OPC_PUSHC, 0);
+  // rate = top of the stack
+  bool const_rate = false;
+  int rate_cslot = zero_slot;
+  if (stk.empty()) const_rate = true;
+  else if (stk.back().lazy) { const_rate = true; rate_cslot = stk.back().cslot; }
+  else if (nmat - 1 != 0) emit(OPC_MOV0, nmat - 1, 0);
+  if (too_deep) return fail(sim, SB2_ERR_LIMIT, "expression stack deeper than SB2_MAX_DEPTH");
+
   bool all_unit = true;
   for (size_t k = 0; k < targets.size(); ++k) all_unit = all_unit && targets[k].stoich == 1.0;
-  if (const_law && all_unit) {
-    const int cslot = (int)(out[0] >> 16);
-    out.clear();
-    for (size_t k = 0; k < targets.size(); ++k) out.push_back(enc(targets[k].subtract ? OPC_ACCSUBC1 : OPC_ACCADDC1, targets[k].species, cslot));
+  if (const_rate && all_unit && !need_mask) {
+    // a law that is a single constant with unit stoichiometries needs no stack at all
+    for (size_t k = 0; k < targets.size(); ++k) out.push_back(enc(targets[k].subtract ? OPC_ACCSUBC1 : OPC_ACCADDC1, targets[k].species, rate_cslot));
   } else {
+    if (const_rate) out.push_back(enc(OPC_PUSHC, 0, rate_cslot));
     for (size_t k = 0; k < targets.size(); ++k) {
       const Target& t = targets[k];
       if (!need_mask && t.stoich == 1.0) { out.push_back(enc(t.subtract ? OPC_ACCSUB1 : OPC_ACCADD1, t.species, 0)); continue; }
@@ -251,8 +294,8 @@ int compile_stmt(sb2_sim* sim, const Sb2Stmt& st, std::vector<uint32_t>& prog) {
 }
 
 const char* kOpcNames[OPC_COUNT] = {"END", "PUSHC", "PUSHV", "PUSHF", "ADD", "SUB", "MUL", "DIV", "GEQ", "GT",
-  "LEQ", "LT", "AND", "OR", "ADDC", "SUBC", "MULC", "DIVC", "GEQC", "GTC", "LEQC", "LTC", "ADDV", "SUBV", "MULV",
-  "DIVV", "UNARY", "BINR", "MOV0", "MASK", "ACCSUB", "ACCADD", "ACCSUB1", "ACCADD1", "ACCSUBC1", "ACCADDC1", "ACCSUBM", "ACCADDM"};
+  "LEQ", "LT", "AND", "OR", "ADDC", "SUBC", "MULC", "DIVC", "RSUBC", "RDIVC", "GEQC", "GTC", "LEQC", "LTC", "ADDV", "SUBV", "MULV",
+  "DIVV", "UNARY", "BINR", "MOV0", "MOVUP", "MASK", "ACCSUB", "ACCADD", "ACCSUB1", "ACCADD1", "ACCSUBC1", "ACCADDC1", "ACCSUBM", "ACCADDM"};
 
 void fill_stage_args(sb2_sim* sim, Sb2StageArgs& a, int m, double dt, int row_begin, int row_end) {
   static const double rk[4] = {0.0, 0.5, 0.5, 1.0};
@@ -278,6 +321,16 @@ void fill_stage_args(sb2_sim* sim, Sb2StageArgs& a, int m, double dt, int row_be
   }
   // rows per CTA: enough CTAs to fill the machine several times over, long enough strips to
   // amortise the two extra rows each CTA loads
+  if (sim->rd_id >= 0) {
+    // a CTA walks its rows in batches of W: long tiles amortise the prologue batch, enough tiles fill the SMs
+    const int W = sim->rd.w;
+    const int rows = row_end - row_begin;
+    int rpb = 16 * W;
+    while (rpb > W && (int64_t)sim->nstrips * ((rows + rpb - 1) / rpb) < 148 * 6) rpb -= W;
+    a.rows_per_block = rpb;
+    a.np = sim->rd.np;
+    return;
+  }
   a.np = sb2_stage_pairs(sim->g.nx, S);
   const int strips = (sim->g.nx + 256 * a.np - 1) / (256 * a.np);
   const int rows = (sim->g.dim == 3) ? sim->g.ny : (row_end - row_begin);
@@ -315,16 +368,14 @@ int sb2_create(const sb2_grid* grid, sb2_sim** out) {
   if (e != cudaSuccess) return fail(NULL, SB2_ERR_CUDA, cudaGetErrorString(e));
   sb2_sim* sim = new sb2_sim();
   sim->g = *grid;
-  sim->P = (grid->nx + 1) / 2 * 2;
-  if (grid->dim == 2) {
-    sim->PL = sim->P * (grid->ny + 2);
-    sim->first = sim->P;
-    sim->nalloc = sim->PL;
-  } else {
-    sim->PL = sim->P * (grid->ny + 2);
-    sim->first = sim->PL + sim->P;
-    sim->nalloc = sim->PL * (grid->nz + 2);
-  }
+  // Rows start on 32-byte boundaries (pitch a multiple of 4 doubles), one zero guard row before and after
+  // every plane, one guard plane either side in 3-D.  The stage kernel's bulk row copies start two cells
+  // left of a strip and may run past the end of the last strip, so a front pad and a tail pad keep every
+  // copy inside the allocation.
+  sim->P = (grid->nx + 3) / 4 * 4;
+  sim->PL = sim->P * (grid->ny + 2);
+  sim->first = (grid->dim == 2 ? sim->P : sim->PL + sim->P) + SB2_FRONT_PAD;
+  sim->nalloc = SB2_FRONT_PAD + (grid->dim == 2 ? sim->PL : sim->PL * (grid->nz + 2)) + SB2_TAIL_PAD;
   sim->stream = 0; sim->own_stream = false;
   e = cudaStreamCreateWithFlags(&sim->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete sim; return fail(NULL, SB2_ERR_CUDA, cudaGetErrorString(e)); }
@@ -334,6 +385,8 @@ int sb2_create(const sb2_grid* grid, sb2_sim** out) {
   sim->finalized = false; sim->fuse_combine = true; sim->any_adv = false; sim->carry_k0 = false;
   sim->k0_carry_valid = false; sim->d_tmp_face = NULL;
   sim->launches = 0; sim->in_step = false; sim->cur_dt = 0; sim->d_scratch = NULL;
+  sim->rd_id = -1; sim->d_cls = NULL; sim->nstrips = 0; sim->d_dbg = NULL;
+  sim->trace = getenv("SB2_TRACE") != NULL;
   memset(&sim->base, 0, sizeof(sim->base));
   *out = sim;
   return SB2_OK;
@@ -354,6 +407,8 @@ void sb2_destroy(sb2_sim* sim) {
   for (size_t i = 0; i < sim->transports.size(); ++i) sb2_free_transport(sim->transports[i]);
   sb2_free_boundary_lists(sim->blists);
   if (sim->d_scratch) cudaFree(sim->d_scratch);
+  if (sim->d_cls) cudaFree(sim->d_cls);
+  if (sim->d_dbg) cudaFree(sim->d_dbg);
   if (sim->d_tmp_face) cudaFree(sim->d_tmp_face);
   if (sim->own_stream) cudaStreamDestroy(sim->stream);
   delete sim;
@@ -530,10 +585,36 @@ int sb2_finalize(sb2_sim* sim) {
   for (size_t i = 0; i < sim->program.size(); ++i) {
     const uint32_t code = sim->program[i] & 0xffffu;
     const int opc = (int)(code / SB2_MAX_DEPTH), d = (int)(code % SB2_MAX_DEPTH);
-    if (opc < OPC_MASK && d + 1 > b.depth) b.depth = d + 1;
+    if (opc < OPC_MASK && d + 1 + (opc == OPC_MOVUP ? 1 : 0) > b.depth) b.depth = d + 1 + (opc == OPC_MOVUP ? 1 : 0);
   }
   memcpy(b.tok, sim->program.data(), sizeof(uint32_t) * sim->program.size());
   b.tok[sim->program.size()] = enc(OPC_END, 0, 0);
+  b.tok[sim->program.size() + 1] = enc(OPC_END, 0, 0);
+
+  // 2-D models with up to four staged species run the rd_stage kernel; SB2_STAGE_KERNEL=gen1 forces the
+  // first-generation kernel (kept for 3-D grids and more species, and as a cross-check in the tests)
+  const char* force = getenv("SB2_STAGE_KERNEL");
+  sim->rd_id = (force && !strcmp(force, "gen1")) ? -1 : sb2_rd_pick_variant(sim->g.dim, sim->g.nx, b.S, b.depth, &sim->rd);
+  b.rd_variant = sim->rd_id;
+  if (sim->rd_id >= 0) {
+    const int sw = 64 * sim->rd.np;
+    if (sw + 4 > SB2_TAIL_PAD) return fail(sim, SB2_ERR_STATE, "strip wider than the tail pad of the field layout");
+    sim->nstrips = (sim->g.nx + sw - 1) / sw;
+    CK(cudaMalloc((void**)&sim->d_cls, (size_t)sim->nstrips * sim->g.ny));
+    const uint8_t* fl[SB2_MAX_GEOS] = {0, 0, 0, 0};
+    for (int g = 0; g < b.G; ++g) fl[g] = sim->d_flags[g];
+    cudaError_t ce = sb2_rd_classify(fl, b.G, sim->g.nx, sim->g.ny, sim->P, sim->first, sw, sim->d_cls, sim->nstrips, sim->stream);
+    if (ce != cudaSuccess) return cuda_fail(sim, ce, "strip classification kernel");
+    b.cls = sim->d_cls;
+    b.nstrips = sim->nstrips;
+    if (getenv("SB2_DEBUG")) {
+      CK(cudaMalloc((void**)&sim->d_dbg, 64 * sizeof(uint32_t)));
+      CK(cudaMemsetAsync(sim->d_dbg, 0, 64 * sizeof(uint32_t), sim->stream));
+      b.dbg = sim->d_dbg;
+    }
+    if (sim->trace) fprintf(stderr, "[sb2] rd_stage variant %d (np %d, w %d, depth %d), %d strips, program depth %d, %d tokens\n",
+                            sim->rd_id, sim->rd.np, sim->rd.w, sim->rd.depth, sim->nstrips, b.depth, b.ntok);
+  }
 
   // boundary-condition lists (Neumann flux / Dirichlet overwrite), built from the host flag copies
   std::string err;
@@ -622,8 +703,20 @@ int sb2_stage(sb2_sim* sim, int m, int phase) {
   auto launch = [&](int rb, int re) -> int {
     if (re <= rb) return SB2_OK;
     fill_stage_args(sim, a, m, dt, rb, re);
+    if (sim->trace) fprintf(stderr, "[sb2] stage m=%d rows [%d,%d) rpb %d final %d carry %d\n", m, rb, re, a.rows_per_block, a.final, a.carry);
     cudaError_t e = sb2_launch_stage(a, sim->stream, &sim->launches);
     if (e != cudaSuccess) return cuda_fail(sim, e, "stage kernel launch");
+    if (sim->d_dbg) {
+      uint32_t h[8];
+      CK(cudaStreamSynchronize(sim->stream));
+      CK(cudaMemcpy(h, sim->d_dbg, sizeof(h), cudaMemcpyDeviceToHost));
+      if (h[0]) {
+        std::ostringstream os;
+        os << "rd_stage: " << h[0] << " bulk-copy waits timed out; first: strip " << h[1] << " tile " << h[2] << " warp " << h[3]
+           << " row " << (int)h[4] << " parity " << h[5] << " tile rows [" << (int)h[6] << "," << (int)h[7] << ")";
+        return fail(sim, SB2_ERR_CUDA, os.str());
+      }
+    }
     return SB2_OK;
   };
   int rc = SB2_OK;

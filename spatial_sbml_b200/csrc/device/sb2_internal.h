@@ -23,11 +23,13 @@ enum Sb2Opc {
   OPC_ADD, OPC_SUB, OPC_MUL, OPC_DIV,         // r[d-1] = r[d-1] op r[d]
   OPC_GEQ, OPC_GT, OPC_LEQ, OPC_LT, OPC_AND, OPC_OR,
   OPC_ADDC, OPC_SUBC, OPC_MULC, OPC_DIVC,     // r[d] = r[d] op consts[arg]
+  OPC_RSUBC, OPC_RDIVC,                       // r[d] = consts[arg] op r[d]
   OPC_GEQC, OPC_GTC, OPC_LEQC, OPC_LTC,
   OPC_ADDV, OPC_SUBV, OPC_MULV, OPC_DIVV,     // r[d] = r[d] op species arg
   OPC_UNARY,  // r[d] = f_arg(r[d])
   OPC_BINR,   // r[d-1] = g_arg(r[d-1], r[d])     (rare binaries: pow, log, xor, eq, neq)
   OPC_MOV0,   // r[0] = r[d]
+  OPC_MOVUP,  // r[d+1] = r[d]
   OPC_MASK,   // statement mask = cell in domain of geo arg
   OPC_ACCSUB, // acc[d] -= consts[arg] * r[0]   (d = species index here)
   OPC_ACCADD, // acc[d] += consts[arg] * r[0]
@@ -36,6 +38,10 @@ enum Sb2Opc {
   OPC_ACCSUBM, OPC_ACCADDM,    // like ACCSUB / ACCADD, but only on the cells selected by the last MASK
   OPC_COUNT
 };
+
+// field layout pads (in elements) around the guard rows, see sb2_create
+#define SB2_FRONT_PAD 4
+#define SB2_TAIL_PAD 264
 
 #define SB2_CODE(opc, d) ((uint32_t)(opc) * SB2_MAX_DEPTH + (uint32_t)(d))
 
@@ -72,13 +78,26 @@ struct Sb2StageArgs {
   Sb2SpeciesArgs sp[SB2_MAX_SPECIES];
   const uint8_t* flags[SB2_MAX_GEOS];
   const double* fields[SB2_MAX_FIELDS];
-  uint32_t tok[SB2_MAX_TOKENS + 1];  // + trailing OPC_END (the interpreter fetches one token ahead)
+  const uint8_t* cls;  // rd_stage: class byte per (row, strip): 0 mixed, 1 all interior, 2 all outside
+  int32_t nstrips;     // strips per row of the class map
+  uint32_t* dbg;       // rd_stage: debug words (SB2_DEBUG=1), else NULL; [0] = mbarrier waits that timed out
+  int32_t rd_variant;  // rd_stage kernel variant chosen at finalize (-1: the first-generation kernel runs)
+  uint32_t tok[SB2_MAX_TOKENS + 2];  // + trailing OPC_END (the interpreter fetches one token ahead)
   double consts[SB2_MAX_CONSTS];
 };
 
 // launches (implemented in stage_kernel.cu)
 cudaError_t sb2_launch_stage(const Sb2StageArgs& args, cudaStream_t stream, int* launches);
 int sb2_stage_pairs(int nx, int nspecies);
+
+// rd_stage kernel family (rd_stage.cuh, instantiated in rd_stage_ns*.cu)
+struct Sb2RdVariant { int id, ns, np, w, depth; };
+// picks the variant for a 2-D model (returns id or -1 when only the first-generation kernel applies)
+int sb2_rd_pick_variant(int dim, int nx, int nspecies, int depth, Sb2RdVariant* out);
+cudaError_t sb2_rd_launch(const Sb2StageArgs& a, cudaStream_t stream);
+// class map: cls[row * nstrips + strip] for strips of sw cells, rows = every held row (2-D: ny)
+cudaError_t sb2_rd_classify(const uint8_t* const* flags, int G, int nx, int nrows, int64_t P, int64_t first, int sw,
+                            uint8_t* cls, int nstrips, cudaStream_t stream);
 
 struct Sb2CombineArgs {
   int32_t nx, ny, nz, dim, S;

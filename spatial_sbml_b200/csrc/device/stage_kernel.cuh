@@ -228,7 +228,9 @@ __global__ void __launch_bounds__(NT, (NS * NP <= 2) ? 5 : (NS * NP <= 4) ? 3 : 
 #define C_GTC(d) C_BINC(OPC_GTC, d, (a > b) ? 1.0 : 0.0)
 #define C_LEQC(d) C_BINC(OPC_LEQC, d, (a <= b) ? 1.0 : 0.0)
 #define C_LTC(d) C_BINC(OPC_LTC, d, (a < b) ? 1.0 : 0.0)
-          REP_D0(C_ADDC) REP_D0(C_SUBC) REP_D0(C_MULC) REP_D0(C_DIVC)
+#define C_RSUBC(d) C_BINC(OPC_RSUBC, d, dsub(b, a))
+#define C_RDIVC(d) C_BINC(OPC_RDIVC, d, ddiv(b, a))
+          REP_D0(C_ADDC) REP_D0(C_SUBC) REP_D0(C_MULC) REP_D0(C_DIVC) REP_D0(C_RSUBC) REP_D0(C_RDIVC)
           REP_D0(C_GEQC) REP_D0(C_GTC) REP_D0(C_LEQC) REP_D0(C_LTC)
 #define C_BINV(opc, d, EXPR) case SB2_CODE(opc, d): LIVE(d) { _Pragma("unroll") for (int p = 0; p < NP; ++p) { LOADV(v, p); { const double a = RD(d)[2 * p], b = v.x; RD(d)[2 * p] = (EXPR); } { const double a = RD(d)[2 * p + 1], b = v.y; RD(d)[2 * p + 1] = (EXPR); } } } break;
 #define C_ADDV(d) C_BINV(OPC_ADDV, d, dadd(a, b))
@@ -242,6 +244,8 @@ __global__ void __launch_bounds__(NT, (NS * NP <= 2) ? 5 : (NS * NP <= 4) ? 3 : 
           REP_D1(C_BINR)
 #define C_MOV0(d) case SB2_CODE(OPC_MOV0, d): LIVE(d) { _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) RD(0)[c_] = RD(d)[c_]; } break;
           REP_D1(C_MOV0)
+#define C_MOVUP(d) case SB2_CODE(OPC_MOVUP, d): LIVE(d + 1) { _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) RD(d + 1)[c_] = RD(d)[c_]; } break;
+          REP_D0(C_MOVUP)
           // statement mask: the law only acts on cells of its own domain (spatialsimulator.cpp:1381-1390)
           case SB2_CODE(OPC_MASK, 0): {
 #pragma unroll
