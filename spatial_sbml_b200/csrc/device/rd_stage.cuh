@@ -65,8 +65,21 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
-__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+// L2 prefetch that keeps the lines until they are used: the default priority of a bulk prefetch is evict-first,
+// and under a stream of several TB/s such lines were gone again before the loads of the next batch arrived
+// (ncu: the k0 / k1 rows were read from DRAM twice).
+__device__ __forceinline__ uint64_t l2_policy_keep() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes, uint64_t policy) {
+  asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(src), "r"(bytes), "l"(policy) : "memory");
 }
 // Bounded wait: a copy that never lands (a bug) ends in wrong results and a failed test, not in a hung GPU.
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
@@ -142,20 +155,28 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
   }
   __syncwarp();
 
+  // The last stage reads u and k2 of its own cells a second time for the combine, one batch after the bulk copy
+  // staged them: those copies (and the k0 / k1 prefetches) ask L2 to keep the lines.
+  const uint64_t keep = (MODE == MODE_FINAL) ? l2_policy_keep() : 0;
   // lane 0: bulk copy of raw row r (u and k_{m-1} of every species, halo columns included) into the warp's slot
   auto issue_row = [&](int r) {
     mbar_expect_tx(mybar, row_bytes * NARR * S);
     const int64_t g = A.first + (int64_t)r * A.P + x0 - 2;
     for (int s = 0; s < S; ++s) {
-      bulk_g2s(myraw_s + (s * NARR) * row_bytes, A.sp[s].u + g, row_bytes, mybar);
-      if (MODE != MODE_FIRST) bulk_g2s(myraw_s + (s * NARR + 1) * row_bytes, A.sp[s].kprev + g, row_bytes, mybar);
+      if (MODE == MODE_FINAL) {
+        bulk_g2s_hint(myraw_s + (s * NARR) * row_bytes, A.sp[s].u + g, row_bytes, mybar, keep);
+        bulk_g2s_hint(myraw_s + (s * NARR + 1) * row_bytes, A.sp[s].kprev + g, row_bytes, mybar, keep);
+      } else {
+        bulk_g2s(myraw_s + (s * NARR) * row_bytes, A.sp[s].u + g, row_bytes, mybar);
+        if (MODE != MODE_FIRST) bulk_g2s(myraw_s + (s * NARR + 1) * row_bytes, A.sp[s].kprev + g, row_bytes, mybar);
+      }
     }
   };
   auto prefetch_combine = [&](int r) {
     const int64_t g = A.first + (int64_t)r * A.P + x0;
     for (int s = 0; s < S; ++s) {
-      bulk_prefetch_l2(A.sp[s].k0 + g, SW * sizeof(double));
-      bulk_prefetch_l2(A.sp[s].k1 + g, SW * sizeof(double));
+      bulk_prefetch_l2(A.sp[s].k0 + g, SW * sizeof(double), keep);
+      bulk_prefetch_l2(A.sp[s].k1 + g, SW * sizeof(double), keep);
     }
   };
 
@@ -332,6 +353,8 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
 #define C_LT(d) C_BIN(OPC_LT, d, (a < b) ? 1.0 : 0.0)
 #define C_AND(d) C_BIN(OPC_AND, d, logic_and(a, b))
 #define C_OR(d) C_BIN(OPC_OR, d, logic_or(a, b))
+#undef C_DIV
+#define C_DIV(d) case SB2_CODE(OPC_DIV, d): LIVE(d) { ddiv_batch<NC>(RD(d - 1), RD(d), RD(d - 1)); } break;
           RD_REP_D1(C_ADD) RD_REP_D1(C_SUB) RD_REP_D1(C_MUL) RD_REP_D1(C_DIV)
           RD_REP_D1(C_GEQ) RD_REP_D1(C_GT) RD_REP_D1(C_LEQ) RD_REP_D1(C_LT) RD_REP_D1(C_AND) RD_REP_D1(C_OR)
 #define C_BINC(opc, d, EXPR) case SB2_CODE(opc, d): LIVE(d) { const double b = A.consts[arg]; _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) { const double a = RD(d)[c_]; RD(d)[c_] = (EXPR); } } break;
@@ -345,6 +368,10 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
 #define C_GTC(d) C_BINC(OPC_GTC, d, (a > b) ? 1.0 : 0.0)
 #define C_LEQC(d) C_BINC(OPC_LEQC, d, (a <= b) ? 1.0 : 0.0)
 #define C_LTC(d) C_BINC(OPC_LTC, d, (a < b) ? 1.0 : 0.0)
+#undef C_DIVC
+#undef C_RDIVC
+#define C_DIVC(d) case SB2_CODE(OPC_DIVC, d): LIVE(d) { double b[NC]; const double c = A.consts[arg]; _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) b[c_] = c; ddiv_batch<NC>(RD(d), b, RD(d)); } break;
+#define C_RDIVC(d) case SB2_CODE(OPC_RDIVC, d): LIVE(d) { double a[NC]; const double c = A.consts[arg]; _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) a[c_] = c; ddiv_batch<NC>(a, RD(d), RD(d)); } break;
           RD_REP_D0(C_ADDC) RD_REP_D0(C_SUBC) RD_REP_D0(C_MULC) RD_REP_D0(C_DIVC) RD_REP_D0(C_RSUBC) RD_REP_D0(C_RDIVC)
           RD_REP_D0(C_GEQC) RD_REP_D0(C_GTC) RD_REP_D0(C_LEQC) RD_REP_D0(C_LTC)
 #define C_BINV(opc, d, EXPR) case SB2_CODE(opc, d): LIVE(d) { _Pragma("unroll") for (int p = 0; p < NP; ++p) { LOADV(v, p); { const double a = RD(d)[2 * p], b = v.x; RD(d)[2 * p] = (EXPR); } { const double a = RD(d)[2 * p + 1], b = v.y; RD(d)[2 * p + 1] = (EXPR); } } } break;
@@ -352,6 +379,8 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
 #define C_SUBV(d) C_BINV(OPC_SUBV, d, dsub(a, b))
 #define C_MULV(d) C_BINV(OPC_MULV, d, dmul(a, b))
 #define C_DIVV(d) C_BINV(OPC_DIVV, d, ddiv(a, b))
+#undef C_DIVV
+#define C_DIVV(d) case SB2_CODE(OPC_DIVV, d): LIVE(d) { double b[NC]; _Pragma("unroll") for (int p = 0; p < NP; ++p) { LOADV(v, p); b[2 * p] = v.x; b[2 * p + 1] = v.y; } ddiv_batch<NC>(RD(d), b, RD(d)); } break;
           RD_REP_D0(C_ADDV) RD_REP_D0(C_SUBV) RD_REP_D0(C_MULV) RD_REP_D0(C_DIVV)
 #define C_UNARY(d) case SB2_CODE(OPC_UNARY, d): LIVE(d) { _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) RD(d)[c_] = sb2_unary((int)arg, RD(d)[c_]); } break;
           RD_REP_D0(C_UNARY)
@@ -387,7 +416,9 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
       _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) if (mk[c_]) acc[SI(s)][c_] = dadd(acc[SI(s)][c_], dmul(st, RD(0)[c_])); } break;
           RD_REP_D0(C_ACC)
           case SB2_CODE(OPC_END, 0): goto program_done;
-          default: break;
+          // the library only emits codes this variant implements (sb2_finalize checks depth and species count),
+          // so the dispatch needs no range check
+          default: __builtin_unreachable();
         }
       }
     program_done:;
