@@ -1,0 +1,296 @@
+"""ORACLE / TEST INFRASTRUCTURE — numpy restatement of the reference's explicit reaction-diffusion step.
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline leg may import this module; the product
+(spatial_sbml_b200/) never does.
+
+What is restated, in the reference's own evaluation order (all file:line relative to /root/reference/SpatialSBML):
+  * the RK4 stage loop of performStep            spatialsimulator.cpp:1350-1492
+  * reversePolishRK, the per-cell RPN evaluator   calcPDE.cpp:224-451  (stack discipline, operator semantics,
+                                                  reactant -= / product += accumulation)
+  * calcDiffusion                                 calcPDE.cpp:453-562
+  * updateSpecies (RK4 combine, k := 0)           spatialsimulator.cpp:1518-1544
+Neumann conditions with value 0 add +0.0 (calcPDE.cpp:994-1027) and are therefore omitted; models with advection
+(cipCSLR), membrane transport, Dirichlet or non-zero Neumann conditions raise NotImplementedError — the goldens made
+by the reference itself (oracle/_ref) cover those.
+
+Pinned: tests/test_oracle_cpu.py checks this restatement BIT FOR BIT against the fields the unmodified reference
+produced (tests/golden/*.npz) for the Turing, Brusselator, fish and synthetic 2-D / 3-D models.
+
+Every array is COMPACT (nz, ny, nx): volume cells only; compact cell (i,j,k) is the reference's doubled-grid point
+(2i,2j,2k) (spatialsimulator.cpp:354-358), so the reference's index +-2 is +-1 here.
+"""
+import xml.etree.ElementTree as ET
+
+import numpy as np
+
+CORE = "{http://www.sbml.org/sbml/level3/version1/core}"
+SPATIAL = "{http://www.sbml.org/sbml/level3/version1/spatial/version1}"
+
+# libSBML ASTNodeType_t values as they appear in the dumped streams ("O <type>")
+AST_PLUS, AST_MINUS, AST_TIMES, AST_DIVIDE, AST_POWER = 43, 45, 42, 47, 94
+AST_FUNCTION_ABS, AST_FUNCTION_ARCCOS, AST_FUNCTION_ARCCOSH = 269, 270, 271
+AST_FUNCTION_ARCCSC, AST_FUNCTION_ARCSIN, AST_FUNCTION_ARCTAN = 274, 278, 280
+AST_FUNCTION_COS, AST_FUNCTION_COSH, AST_FUNCTION_CSC, AST_FUNCTION_EXP = 283, 284, 287, 290
+AST_FUNCTION_LN, AST_FUNCTION_LOG, AST_FUNCTION_POWER, AST_FUNCTION_ROOT = 293, 294, 296, 297
+AST_FUNCTION_SIN, AST_FUNCTION_SINH, AST_FUNCTION_TAN, AST_FUNCTION_TANH = 300, 301, 302, 303
+AST_LOGICAL_AND, AST_LOGICAL_NOT, AST_LOGICAL_OR, AST_LOGICAL_XOR = 304, 305, 306, 307
+AST_RELATIONAL_EQ, AST_RELATIONAL_GEQ, AST_RELATIONAL_GT = 308, 309, 310
+AST_RELATIONAL_LEQ, AST_RELATIONAL_LT, AST_RELATIONAL_NEQ = 311, 312, 313
+
+UNARY = {
+    AST_FUNCTION_ABS: np.fabs, AST_FUNCTION_ARCCOS: np.arccos, AST_FUNCTION_ARCCOSH: np.arccosh,
+    AST_FUNCTION_ARCCSC: lambda x: np.arcsin(1.0 / x), AST_FUNCTION_ARCSIN: np.arcsin, AST_FUNCTION_ARCTAN: np.arctan,
+    AST_FUNCTION_COS: np.cos, AST_FUNCTION_COSH: np.cosh, AST_FUNCTION_CSC: lambda x: 1.0 / np.sin(x),
+    AST_FUNCTION_EXP: np.exp, AST_FUNCTION_LN: np.log,
+    AST_FUNCTION_ROOT: np.sqrt,  # sqrt whatever the degree (calcPDE.cpp:355)
+    AST_FUNCTION_SIN: np.sin, AST_FUNCTION_SINH: np.sinh, AST_FUNCTION_TAN: np.tan, AST_FUNCTION_TANH: np.tanh,
+    AST_LOGICAL_NOT: lambda x: np.where(x.astype(np.int64) == 0, 1.0, 0.0),  # calcPDE.cpp:385-388
+}
+
+
+def _as_int(x):
+    with np.errstate(invalid="ignore"):
+        return np.nan_to_num(x, nan=0.0, posinf=0.0, neginf=0.0).astype(np.int64)
+
+
+BINARY = {
+    AST_PLUS: lambda a, b: a + b, AST_MINUS: lambda a, b: a - b, AST_TIMES: lambda a, b: a * b, AST_DIVIDE: lambda a, b: a / b,
+    AST_POWER: np.power, AST_FUNCTION_POWER: np.power,
+    AST_FUNCTION_LOG: lambda a, b: np.log(b) / np.log(a),  # calcPDE.cpp:349-352
+    # static_cast<int>(a) == 1 && static_cast<int>(b == 1)   — calcPDE.cpp:383, 391, 395
+    AST_LOGICAL_AND: lambda a, b: np.where((_as_int(a) == 1) & (b == 1.0), 1.0, 0.0),
+    AST_LOGICAL_OR: lambda a, b: np.where((_as_int(a) == 1) | (b == 1.0), 1.0, 0.0),
+    AST_LOGICAL_XOR: lambda a, b: np.where(((_as_int(a) == 1) & (b == 0.0)) | ((_as_int(a) == 0) & (b == 1.0)), 1.0, 0.0),
+    AST_RELATIONAL_EQ: lambda a, b: np.where(a == b, 1.0, 0.0), AST_RELATIONAL_GEQ: lambda a, b: np.where(a >= b, 1.0, 0.0),
+    AST_RELATIONAL_GT: lambda a, b: np.where(a > b, 1.0, 0.0), AST_RELATIONAL_LEQ: lambda a, b: np.where(a <= b, 1.0, 0.0),
+    AST_RELATIONAL_LT: lambda a, b: np.where(a < b, 1.0, 0.0), AST_RELATIONAL_NEQ: lambda a, b: np.where(a != b, 1.0, 0.0),
+}
+
+
+def parse_stream(text):
+    """'V name hasDelta' / 'C name value' / 'C # literal' / 'O astType' lines → token tuples."""
+    toks = []
+    for line in text.splitlines():
+        p = line.split()
+        if not p:
+            continue
+        if p[0] == "V":
+            toks.append(("V", p[1], int(p[2])))
+        elif p[0] == "C":
+            toks.append(("C", p[1], float(p[2])))
+        else:
+            toks.append(("O", int(p[1])))
+    return toks
+
+
+def eval_stream(toks, operand, consts, shape):
+    """calcPDE.cpp:244-431 on whole arrays: the same stack discipline for every cell, so the stack is a list of arrays.
+    operand(name, has_delta) → array; consts: name → current value (literal tokens carry their value)."""
+    stack = []
+    for t in toks:
+        if t[0] == "V":
+            stack.append(operand(t[1], t[2]))
+        elif t[0] == "C":
+            v = consts.get(t[1], t[2]) if t[1] != "#" else t[2]
+            stack.append(np.full(shape, v, dtype=np.float64))
+        else:
+            op = t[1]
+            top = stack.pop() if stack else None  # if (st_index > 0) st_index--
+            if op in BINARY:
+                if top is not None and stack:  # if (st_index > 0) s[st-1] op= s[st]
+                    stack[-1] = BINARY[op](stack[-1], top)
+            elif op in UNARY:
+                x = top if top is not None else np.zeros(shape)  # (an empty stack leaves a stale slot in the reference)
+                stack.append(UNARY[op](x))
+            # every other operator only pops (calcPDE.cpp:297-302, 379-380, 399-400 ...)
+    return stack[-1] if stack else np.zeros(shape)  # if (st_index > 0) st_index--; rate = s[st_index]
+
+
+class Species(object):
+    def __init__(self, name, u, domain, btype, D):
+        self.name, self.u = name, np.array(u, dtype=np.float64)
+        self.domain = np.asarray(domain, dtype=bool)       # isDomain == 1 of the species' compartment
+        self.btype = np.asarray(btype, dtype=np.uint8)     # bits 1..6 = isBofXp, Xm, Yp, Ym, Zp, Zm
+        self.D = D                                         # per axis: float or None (diffCInfo[a] == 0)
+        self.k = [np.zeros_like(self.u) for _ in range(4)]
+
+
+class Reaction(object):
+    def __init__(self, toks, refs, n_reactants, domain, is_reaction=True):
+        self.toks, self.refs, self.n_reactants, self.domain, self.is_reaction = toks, refs, n_reactants, domain, is_reaction
+
+
+class RDOracle(object):
+    """State + oneStep of the restated path."""
+
+    def __init__(self, species, reactions, consts, delta, dimension):
+        self.sp = {s.name: s for s in species}
+        self.order = [s.name for s in species]
+        self.rx = reactions
+        self.consts = dict(consts)
+        self.delta = delta
+        self.dimension = dimension
+        self.shape = species[0].u.shape
+
+    def _w(self, s, m, dt):
+        rk = (0.0, 0.5, 0.5, 1.0)
+        if m == 0:
+            return s.u
+        return s.u + (rk[m] * dt) * s.k[m - 1]  # val + rk[m]*dt*d[(m-1)N + i], calcPDE.cpp:247-248
+
+    def one_step(self, t, dt):
+        self.consts["t"] = t * dt  # sim_time = t * dt, spatialsimulator.cpp:1358
+        with np.errstate(all="ignore"):
+            for m in range(4):
+                w = {n: self._w(self.sp[n], m, dt) for n in self.order}
+
+                def operand(name, has_delta):
+                    if name in w:
+                        return w[name] if has_delta else self.sp[name].u
+                    raise NotImplementedError("field operand %s" % name)
+
+                for r in self.rx:  # document order, spatialsimulator.cpp:1374-1390
+                    rate = eval_stream(r.toks, operand, self.consts, self.shape)
+                    for k, (name, stoich, is_var) in enumerate(r.refs):
+                        if not is_var or name not in self.sp:
+                            continue
+                        km = self.sp[name].k[m]
+                        if not r.is_reaction:
+                            if k == 0:
+                                km[r.domain] += (stoich * rate)[r.domain]  # calcPDE.cpp:447-449
+                        elif k < r.n_reactants:
+                            km[r.domain] -= (stoich * rate)[r.domain]      # calcPDE.cpp:432-438
+                        else:
+                            km[r.domain] += (stoich * rate)[r.domain]      # calcPDE.cpp:439-446
+                for n in self.order:  # species order, spatialsimulator.cpp:1464-1478
+                    s = self.sp[n]
+                    self._diffusion(s, w[n], m)
+            for n in self.order:  # updateSpecies, spatialsimulator.cpp:1535-1536
+                s = self.sp[n]
+                inc = dt * (s.k[0] + 2.0 * s.k[1] + 2.0 * s.k[2] + s.k[3]) / 6.0
+                s.u[s.domain] += inc[s.domain]
+                for m in range(4):
+                    s.k[m][s.domain] = 0.0
+        return t + dt
+
+    def _diffusion(self, s, w, m):
+        """calcPDE.cpp:484-559: Xp, Xm, Yp, Ym, Zp, Zm, each skipped where the boundary-type flag is set."""
+        axes = [(2, self.delta[0], 1, 2), (1, self.delta[1], 3, 4), (0, self.delta[2], 5, 6)]  # (array axis, delta, bit+, bit-)
+        for a, (ax, dl, bp, bm) in enumerate(axes):
+            if s.D[a] is None or (a == 2 and self.dimension <= 2):
+                continue
+            d2 = np.power(dl, 2)
+            for sign, bit in ((+1, bp), (-1, bm)):
+                nb = np.roll(w, -sign, axis=ax)  # neighbour value; wrapped entries are masked by the boundary flag
+                ok = s.domain & ((s.btype >> bit) & 1 == 0)
+                # the grid edge always carries the flag in a domain cell; guard anyway
+                idx = [slice(None)] * 3
+                idx[ax] = -1 if sign > 0 else 0
+                ok = ok.copy()
+                ok[tuple(idx)] = False
+                term = s.D[a] * (nb - w) / d2
+                s.k[m][ok] += term[ok]
+
+
+def model_parameters(xml_text):
+    """Diffusion coefficients (species → [Dx, Dy, Dz] parameter ids), uniform values, compartments."""
+    root = ET.fromstring(xml_text)
+    values, diff, features = {}, {}, set()
+    for p in root.iter(CORE + "parameter"):
+        pid = p.get("id")
+        if p.get("value") is not None:
+            values[pid] = float(p.get("value"))
+        dc = p.find(SPATIAL + "diffusionCoefficient")
+        if dc is not None:
+            var = dc.get(SPATIAL + "variable") or dc.get("variable")
+            ref = dc.get(SPATIAL + "coordinateReference1") or dc.get(SPATIAL + "coordinateIndex")
+            kind = dc.get(SPATIAL + "type")
+            slots = diff.setdefault(var, [None, None, None])
+            if ref in ("cartesianX", "0"):
+                slots[0] = pid
+            elif ref in ("cartesianY", "1"):
+                slots[1] = pid
+            elif ref in ("cartesianZ", "2"):
+                slots[2] = pid
+            else:  # no coordinate reference: every axis (setInfoFunction.cpp:216-227)
+                for a in range(3):
+                    slots[a] = pid
+            del kind
+        if p.find(SPATIAL + "advectionCoefficient") is not None:
+            features.add("advection")
+        bc = p.find(SPATIAL + "boundaryCondition")
+        if bc is not None:
+            kind = (bc.get(SPATIAL + "type") or "").lower()
+            if "dirichlet" in kind or kind == "value":
+                features.add("dirichlet")
+            elif values.get(pid, 0.0) != 0.0:
+                features.add("neumann")
+    for c in root.iter(CORE + "compartment"):
+        values[c.get("id")] = float(c.get("size")) if c.get("size") is not None else 1.0
+    return values, diff, features
+
+
+def from_simulator(sim, xml_text, dims):
+    """Build the oracle state from the HOST set-up of a (host-only or device) SpatialSimulator: masks, boundary types,
+    token streams and initial fields — each of which the CPU tests pin bit for bit to the reference separately."""
+    nx, ny, nz = dims
+
+    def even(a):
+        return np.ascontiguousarray(a.reshape(2 * nz - 1, 2 * ny - 1, 2 * nx - 1)[::2, ::2, ::2])
+
+    values, diff, features = model_parameters(xml_text)
+    summary = sim.getSetupText("summary").splitlines()
+    head = summary[0].split()
+    delta = [float(head[7]), float(head[8]), float(head[9])]
+    dimension = int(head[5])
+    var_geo, uniform = {}, {}
+    for line in summary:
+        p = line.split()
+        if p[0] == "var":
+            if p[3] == "0" and p[7] == "1":  # non-uniform with delta: a spatial species
+                var_geo[p[1]] = p[9]
+            if p[3] == "1" and "value" in p:
+                uniform[p[1]] = float(p[p.index("value") + 1])
+    for line in summary:
+        p = line.split()
+        if p[0] == "rxn" and p[4] == "1":
+            features.add("membrane transport")
+    if features:
+        raise NotImplementedError("not restated here: " + ", ".join(sorted(features)))
+    masks, btypes = {}, {}
+    for comp in set(var_geo.values()):
+        masks[comp] = even(sim.getGeometry(comp)) == 1
+        bt = sim.getBoundaryType(comp)
+        btypes[comp] = even(sum((bt[:, k].astype(np.uint8) << (k + 1)) for k in range(6)).astype(np.uint8))
+    species = []
+    for name, comp in var_geo.items():
+        D = [uniform.get(pid) if pid is not None else None for pid in diff.get(name, [None, None, None])]
+        species.append(Species(name, even(sim.getVariable(name)), masks[comp], btypes[comp], D))
+    reactions = []
+    i = 0
+    while True:
+        text = sim.getSetupText("rxn/%d" % i)
+        refs_text = sim.getSetupText("refs/%d" % i)
+        if not text and not refs_text:
+            break
+        refs = []
+        for line in refs_text.splitlines():
+            p = line.split()
+            refs.append((p[0], float(p[1]), p[2] == "1"))
+        n_reactants = _count_reactants(xml_text, i)
+        dom = None
+        for name, _, _ in refs:  # geometry of the first species reference that has one (spatialsimulator.cpp:1381-1390)
+            if name in var_geo:
+                dom = masks[var_geo[name]]
+                break
+        if dom is not None:
+            reactions.append(Reaction(parse_stream(text), refs, n_reactants, dom))
+        i += 1
+    return RDOracle(species, reactions, uniform, delta, dimension)
+
+
+def _count_reactants(xml_text, index):
+    root = ET.fromstring(xml_text)
+    rx = [r for r in root.iter(CORE + "reaction") if r.get("fast") != "true"]
+    lor = rx[index].find(CORE + "listOfReactants")
+    return 0 if lor is None else len(list(lor))

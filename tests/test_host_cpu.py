@@ -1,0 +1,199 @@
+"""CPU tests (no GPU): the host half of the drop-in — SBML reading, geometry / membrane classification,
+boundary types, reverse-polish streams, initial fields — against what the reference itself produced for the
+same models (tests/golden/*.npz, written by tests/golden/make_golden.py from the unmodified reference
+sources), plus the C ABI surface.
+
+The bar for everything here is bit-exact (integer masks, index lists, token streams, initial values).
+"""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import REPO, golden_cases, load_golden, model_path
+
+import spatial_sbml_b200 as sb
+
+
+def host_sim(case):
+    g = load_golden(case)
+    nx, ny, nz = [int(v) for v in g["dims"]]
+    sim = sb.SpatialSimulator(host_only=True)
+    sim.initFromFile(model_path(case), nx, ny, nz)
+    return sim, g, (nx, ny, nz)
+
+
+def even(a, dims):
+    nx, ny, nz = dims
+    return a.reshape(2 * nz - 1, 2 * ny - 1, 2 * nx - 1)[::2, ::2, ::2]
+
+
+def test_library_exports_every_declared_symbol(lib):
+    """include/*.h is the drop-in boundary: every SB2_API / SSB_API declaration must be exported."""
+    names = []
+    for h in ("spatial_b200.h", "spatial_sim_c.h"):
+        text = open(os.path.join(REPO, "include", h)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names += re.findall(r"S[SB][B2]_API\s+[\w\s\*]+?\b(\w+)\s*\(", text)
+    assert len(names) > 60, names
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, "declared in include/ but not exported: %s" % missing
+    # and the ctypes prototypes of the Python binding cover exactly that surface
+    assert sorted(lib._prototypes) == sorted(set(names))
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device a simulator that is not host-only must refuse to initialise (or, on a GPU box,
+    initialise on the device): there is no CPU stepping path."""
+    import torch
+    sim = sb.SpatialSimulator()
+    if torch.cuda.is_available():
+        sim.initFromFile(model_path("turing_tiny"), 22, 22, 1)
+        assert sim.getDeviceLaunchCount() == 0
+    else:
+        with pytest.raises(RuntimeError, match="CUDA"):
+            sim.initFromFile(model_path("turing_tiny"), 22, 22, 1)
+    sim.close()
+
+
+def test_host_only_cannot_step():
+    sim = sb.SpatialSimulator(host_only=True)
+    sim.initFromFile(model_path("turing_tiny"), 22, 22, 1)
+    with pytest.raises(RuntimeError):
+        sim.oneStep(0, 0.07)
+    sim.close()
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_volume_masks_bit_exact(case):
+    """isDomain, isBoundary and the six boundary-type flags of every volume compartment
+    (reference spatialsimulator.cpp:411-717, boundaryFunction.cpp:13-217)."""
+    sim, g, dims = host_sim(case)
+    assert sim.getXDim() == dims[0] and sim.getYDim() == dims[1] and sim.getZDim() == dims[2]
+    n_checked = 0
+    for name in [str(s) for s in g["geo_names"]]:
+        if not int(g["geo/%s/isVol" % name]):
+            continue
+        dom = sim.getGeometry(name)
+        assert dom is not None, name
+        assert dom.size == sim.getGeometryLength()
+        assert np.array_equal(even(dom, dims).astype(np.int8), g["geo/%s/isDomain" % name]), "%s isDomain" % name
+        # nothing may be set off the volume cells
+        assert int(dom.sum()) == int(g["geo/%s/isDomain" % name].sum())
+        bnd = sim.getBoundary(name)
+        assert np.array_equal(even(bnd, dims).astype(np.int8), g["geo/%s/isBoundary" % name]), "%s isBoundary" % name
+        bt = sim.getBoundaryType(name)
+        bits = sum((bt[:, k].astype(np.uint8) << (k + 1)) for k in range(6))
+        assert np.array_equal(even(bits, dims), g["geo/%s/bType" % name]), "%s bType" % name
+        n_checked += 1
+    assert n_checked >= 1
+    sim.close()
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_membrane_classification_bit_exact(case):
+    """Membrane points (isDomain 1), pseudo-membrane corners (isDomain 2), their boundary types and the two index
+    lists (reference spatialsimulator.cpp:721-1038)."""
+    sim, g, dims = host_sim(case)
+    for name in [str(s) for s in g["geo_names"]]:
+        if int(g["geo/%s/isVol" % name]):
+            continue
+        dom = sim.getGeometry(name)
+        assert dom is not None, name
+        pts = np.flatnonzero(dom)
+        assert np.array_equal(pts, g["geo/%s/points" % name]), "%s membrane points" % name
+        assert np.array_equal(dom[pts].astype(np.int8), g["geo/%s/class" % name]), "%s membrane classes" % name
+        bt = sim.getBoundaryType(name)
+        bits = sum((bt[pts, k].astype(np.uint8) << (k + 1)) for k in range(6)).astype(np.uint8)
+        assert np.array_equal(bits, g["geo/%s/bTypeAtPoints" % name]), "%s membrane bType" % name
+        mem = np.array([int(v) for v in sim.getSetupText("memindex/" + name).split()], dtype=np.int64)
+        assert np.array_equal(mem, g["geo/%s/domainIndex" % name]), "%s domainIndex" % name
+        pseudo = np.array([int(v) for v in sim.getSetupText("pseudo/" + name).split()], dtype=np.int64)
+        assert np.array_equal(pseudo, g["geo/%s/pseudoMemIndex" % name]), "%s pseudoMemIndex" % name
+    sim.close()
+
+
+@pytest.mark.parametrize("case", ["transport", "transport_rate"])
+def test_membrane_normals_bit_exact(case):
+    """nuVec at the membrane points of the models whose transport reactions read it
+    (reference setInfoFunction.cpp:495-1546)."""
+    sim, g, dims = host_sim(case)
+    checked = 0
+    for name in [str(s) for s in g["geo_names"]]:
+        key = "geo/%s/nuVec" % name
+        if int(g["geo/%s/isVol" % name]) or key not in g.files:
+            continue
+        rows = [l.split() for l in sim.getSetupText("normals/" + name).splitlines()]
+        if not rows:
+            continue
+        idx = np.array([int(r[0]) for r in rows])
+        ours = np.array([[float(v) for v in r[1:4]] for r in rows])
+        order = {int(v): k for k, v in enumerate(g["geo/%s/domainIndex" % name])}  # the dump lists nuVec in domainIndex order
+        assert all(int(i) in order for i in idx), "%s: membrane point unknown to the reference" % name
+        ref = g[key][[order[int(i)] for i in idx]]
+        if not ours.any():
+            continue  # normals are only built for membranes a transport reaction crosses
+        assert np.array_equal(ours, ref), "%s normals" % name
+        checked += 1
+    assert checked >= 1
+    sim.close()
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_reverse_polish_streams_match_reference(case):
+    """rearrangeAST + parseAST (reference astFunction.cpp:18-235): the token streams of every kinetic law and of every
+    analytic-geometry expression, token for token, and the species references with stoichiometry / isVariable."""
+    sim, g, dims = host_sim(case)
+    i = 0
+    while "rxn/%d/rpn" % i in g.files:
+        assert sim.getSetupText("rxn/%d" % i) == str(g["rxn/%d/rpn" % i]), "reaction %d stream" % i
+        assert sim.getSetupText("refs/%d" % i) == str(g["rxn/%d/refs" % i]), "reaction %d references" % i
+        i += 1
+    for name in [str(s) for s in g["geo_names"]]:
+        key = "geo/%s/rpn" % name
+        if key in g.files:
+            assert sim.getSetupText("geo/" + name) == str(g[key]), "%s geometry stream" % name
+    sim.close()
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_initial_fields_bit_exact(case):
+    """Initial concentrations incl. initial assignments (reference setInfoFunction.cpp:93-155,
+    spatialsimulator.cpp:1051-1153) at the volume cells."""
+    sim, g, dims = host_sim(case)
+    for sp in [str(s) for s in g["species"]]:
+        full = sim.getVariable(sp)
+        assert full is not None, sp
+        assert np.array_equal(even(full, dims), g["step/0/" + sp]), "initial field of %s" % sp
+        got = sim.getVariableCompact(sp)
+        assert np.array_equal(got, g["step/0/" + sp])
+    sim.close()
+
+
+def test_get_variable_at_and_index_for_position():
+    """getVariableAt takes coordinates, getIndexForPosition maps them to the doubled grid
+    (reference spatialsimulator.cpp:1769-1783, :116)."""
+    sim, g, dims = host_sim("turing_blob")
+    u = g["step/0/species_1"]
+    for (x, y) in [(0, 0), (10, 20), (50, 50), (100, 100)]:
+        idx = sim.getIndexForPosition(x, y)
+        assert idx == (2 * y) * (2 * dims[0] - 1) + 2 * x
+        v = sim.getVariableAt("species_1", x, y, 0)
+        dom = g["geo/%s/isDomain" % [str(s) for s in g["geo_names"] if int(g["geo/%s/isVol" % s])][0]][0, y, x]
+        assert v == (u[0, y, x] if dom else 0.0)
+    assert sim.getVariableAt("no_such_species", 1, 1, 0) == 0.0
+    assert sim.getVariableLength() == sim.getGeometryLength() - 1  # the reference's N-1 (spatialsimulator.cpp:1341)
+    sim.close()
+
+
+def test_set_parameter_reaches_uniform_variables():
+    sim, g, dims = host_sim("turing_tiny")
+    text = sim.getSetupText("summary")
+    assert "var " in text
+    for name in ("k1", "Km", "species_2_diff"):  # kinetic constants and a diffusion coefficient (spatialsimulator.cpp:167-202)
+        sim.setParameter(name, 123.25)
+        line = [l for l in sim.getSetupText("summary").splitlines() if l.startswith("var %s " % name)][0]
+        assert line.endswith("value 123.25"), line
+    sim.setParameter("no_such_parameter", 1.0)  # unknown ids are ignored, as in the reference
+    sim.close()

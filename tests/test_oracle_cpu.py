@@ -1,0 +1,76 @@
+"""CPU tests of the checkers themselves (no GPU).
+
+  * oracle/rd_oracle.py — the numpy restatement of the reference's reaction-diffusion step — against the fields the
+    UNMODIFIED reference produced (tests/golden/*.npz): bit for bit, every stored step.
+  * oracle/_ref/ref_driver — the reference's own sources compiled in place — re-run here on a small model must
+    reproduce the committed golden exactly (skipped where the binary has not been built).
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import REPO, load_golden, model_path
+
+sys.path.insert(0, os.path.join(REPO, "oracle"))
+import rd_oracle  # noqa: E402
+from sbd import read_sbd  # noqa: E402
+
+import spatial_sbml_b200 as sb
+
+# case -> last stored step the restatement is run to (all stored steps up to it are compared)
+RESTATED = {"turing_tiny": 1000, "turing_tiny_cl": 100, "turing_uniform": 100, "turing_blob": 100, "turing_50": 100,
+            "brusselator": 100, "brusselator_nonunit": 100, "brusselator_300": 1, "fish": 10, "fish_300": 1,
+            "syn_turing_2d": 100, "syn_turing_3d": 50, "syn_brusselator_3d": 20}
+
+
+def build(case):
+    g = load_golden(case)
+    dims = tuple(int(v) for v in g["dims"])
+    sim = sb.SpatialSimulator(host_only=True)
+    sim.initFromFile(model_path(case), *dims)
+    orc = rd_oracle.from_simulator(sim, open(model_path(case)).read(), dims)
+    sim.close()
+    return orc, g
+
+
+@pytest.mark.parametrize("case", sorted(RESTATED))
+def test_restatement_matches_reference_bit_for_bit(case):
+    orc, g = build(case)
+    dt = float(g["dt"])
+    done = 0
+    for target in [int(s) for s in g["steps"] if int(s) <= RESTATED[case]]:
+        for t in range(done, target):
+            assert orc.one_step(t, dt) == t + dt
+        done = target
+        for sp in [str(s) for s in g["species"]]:
+            ref = g["step/%d/%s" % (target, sp)]
+            got = orc.sp[sp].u
+            assert np.array_equal(got, ref), "%s step %d species %s: max abs diff %.3e" % (case, target, sp, np.abs(got - ref).max())
+    assert done > 0
+
+
+@pytest.mark.parametrize("case", ["advection", "transport", "fish_dirichlet", "turing_tiny_flux"])
+def test_restatement_refuses_what_it_does_not_cover(case):
+    with pytest.raises(NotImplementedError):
+        build(case)
+
+
+@pytest.mark.parametrize("case", ["turing_tiny", "syn_turing_3d"])
+def test_reference_build_reproduces_the_golden(case, tmp_path):
+    drv = os.path.join(REPO, "oracle", "_ref", "ref_driver")
+    if not os.path.exists(drv):
+        pytest.skip("oracle/_ref/ref_driver is not built (needs /root/reference; __graft_entry__.build() makes it)")
+    g = load_golden(case)
+    nx, ny, nz = [int(v) for v in g["dims"]]
+    steps = [int(s) for s in g["steps"]][:2]
+    out = str(tmp_path / "dump.sbd")
+    subprocess.run([drv, "dump", model_path(case), str(nx), str(ny), str(nz), repr(float(g["dt"])), out] + [str(s) for s in steps],
+                   check=True, stdout=subprocess.DEVNULL)
+    d = read_sbd(out)
+    for s in [0] + steps:
+        for sp in [str(v) for v in g["species"]]:
+            full = d["step/%d/%s" % (s, sp)].reshape(2 * nz - 1, 2 * ny - 1, 2 * nx - 1)
+            assert np.array_equal(full[::2, ::2, ::2], g["step/%d/%s" % (s, sp)]), "%s step %d %s" % (case, s, sp)
