@@ -100,6 +100,8 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+__host__ __device__ inline int tok_bytes(int nrd) { return ((nrd + 2) * 16 + 127) / 128 * 128; }
+
 template <int NP, int W>
 struct Geo {
   static constexpr int NC = 2 * NP;     // cells per thread
@@ -131,11 +133,14 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
   constexpr int NC = G::NC, SW = G::SW, SWP = G::SWP, RW = G::RW;
   constexpr int NARR = (MODE == MODE_FIRST) ? 1 : 2;  // arrays per species in a raw slot: u (, k_{m-1})
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  // [W mbarriers, 128 B] [w ring: S x RW x SWP] [raw slots: W x S x NARR x SWP]
+  // [2W mbarriers, 128 B] [token records] [w ring: S x RW x SWP] [raw slots: W x S x NARR x SWP]
+  // [last stage: k0 / k1 slots: W x S x 2 x SW]
   const int S = A.S;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
-  double* wring = reinterpret_cast<double*>(smem_raw + 128);
+  const uint4* toks = reinterpret_cast<const uint4*>(smem_raw + 128);
+  double* wring = reinterpret_cast<double*>(smem_raw + 128 + tok_bytes(A.nrd));
   double* rawbase = wring + (size_t)S * RW * SWP;
+  double* cbase = rawbase + (size_t)W * S * NARR * SWP;
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -149,9 +154,18 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
   const uint32_t myraw_s = smem_addr(myraw);
   const uint32_t row_bytes = SWP * sizeof(double);
 
+  double* mycs = cbase + (size_t)warp * S * 2 * SW;  // last stage: k0 / k1 of the row this warp computes next
+  const uint32_t mycbar = smem_addr(&bars[W + warp]);
+  const uint32_t mycs_s = smem_addr(mycs);
   if (lane == 0) {
     mbar_init(mybar, 1);
+    if (MODE == MODE_FINAL) mbar_init(mycbar, 1);
     mbar_fence_init();
+  }
+  // the token records move from the kernel parameters to shared memory once (first read after the first barrier)
+  for (int i = threadIdx.x; i < A.nrd + 2; i += W * 32) {
+    const Sb2RdTok t = A.rdtok[i];
+    reinterpret_cast<uint4*>(smem_raw + 128)[i] = make_uint4(t.code, t.arg, (uint32_t)__double2loint(t.c), (uint32_t)__double2hiint(t.c));
   }
   __syncwarp();
 
@@ -172,13 +186,16 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
       }
     }
   };
-  auto prefetch_combine = [&](int r) {
+  // last stage, lane 0: bulk copy of the k0 / k1 rows (own cells) the combine of row r needs, one batch ahead
+  auto issue_combine = [&](int r) {
+    mbar_expect_tx(mycbar, SW * sizeof(double) * 2 * S);
     const int64_t g = A.first + (int64_t)r * A.P + x0;
     for (int s = 0; s < S; ++s) {
-      bulk_prefetch_l2(A.sp[s].k0 + g, SW * sizeof(double), keep);
-      bulk_prefetch_l2(A.sp[s].k1 + g, SW * sizeof(double), keep);
+      bulk_g2s(mycs_s + (s * 2) * SW * sizeof(double), A.sp[s].k0 + g, SW * sizeof(double), mycbar);
+      bulk_g2s(mycs_s + (s * 2 + 1) * SW * sizeof(double), A.sp[s].k1 + g, SW * sizeof(double), mycbar);
     }
   };
+  uint32_t cparity = 0;
 
   bool active[NP];
 #pragma unroll
@@ -234,8 +251,18 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
     if (lane == 0) {
       const int nrow = wrow + W;
       if (nrow >= yb - 1 && nrow <= ye) issue_row(nrow);
-      if (MODE == MODE_FINAL && srow + W >= yb && srow + W < ye) prefetch_combine(srow + W);
+      // the first k0 / k1 rows; later ones are requested as soon as the combine has read the previous ones
+      if (MODE == MODE_FINAL && Y < yb && srow + W < ye) issue_combine(srow + W);
     }
+    // row srow's k0 / k1 have been requested one batch ago: whoever leaves this iteration without the combine
+    // still has to wait for them and to request the next row
+    auto combine_done = [&](bool waited) {
+      if (MODE != MODE_FINAL) return;
+      if (!waited) { mbar_wait(mycbar, cparity); }
+      cparity ^= 1;
+      __syncwarp();
+      if (lane == 0 && srow + W < ye) issue_combine(srow + W);
+    };
 
     // per-cell flag bytes of all geometries (byte g = geometry g); only class-0 rows look at them
     uint32_t fl[NC];
@@ -277,6 +304,7 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
           }
         }
       }
+      combine_done(false);
       continue;
     }
     if (cls == 0) {
@@ -297,6 +325,7 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
             }
           }
         }
+        combine_done(false);
         continue;
       }
     }
@@ -327,16 +356,17 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
       for (int c = 0; c < NC; ++c) mk[c] = false;
       const double* wop = wring + slot_c * SWP + 2 + 2 * lane;  // + s*RW*SWP selects the species, + 64p the pair
 
-      uint32_t tnext = A.tok[0];
+      uint4 tnext = toks[0];
       int pc = 0;
 #pragma unroll 1
       for (;;) {
-        const uint32_t t = tnext;
-        tnext = A.tok[++pc];  // the stream ends with OPC_END, whose successor slot exists
-        const uint32_t arg = t >> 16;
-        switch (t & 0xffffu) {
+        const uint4 t = tnext;
+        tnext = toks[++pc];  // one record ahead; the stream ends with two OPC_END records
+        const uint32_t arg = t.y;
+        const double cv = __hiloint2double((int)t.w, (int)t.z);  // inline constant of the C forms
+        switch (t.x) {
 #define LOADV(v, p) const double2 v = *reinterpret_cast<const double2*>(wop + arg * (RW * SWP) + (p) * 64)
-#define C_PUSHC(d) case SB2_CODE(OPC_PUSHC, d): LIVE(d) { const double c = A.consts[arg]; _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) RD(d)[c_] = c; } break;
+#define C_PUSHC(d) case SB2_CODE(OPC_PUSHC, d): LIVE(d) { _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) RD(d)[c_] = cv; } break;
           RD_REP_D0(C_PUSHC)
 #define C_PUSHV(d) case SB2_CODE(OPC_PUSHV, d): LIVE(d) { _Pragma("unroll") for (int p = 0; p < NP; ++p) { LOADV(v, p); RD(d)[2 * p] = v.x; RD(d)[2 * p + 1] = v.y; } } break;
           RD_REP_D0(C_PUSHV)
@@ -357,7 +387,7 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
 #define C_DIV(d) case SB2_CODE(OPC_DIV, d): LIVE(d) { ddiv_batch<NC>(RD(d - 1), RD(d), RD(d - 1)); } break;
           RD_REP_D1(C_ADD) RD_REP_D1(C_SUB) RD_REP_D1(C_MUL) RD_REP_D1(C_DIV)
           RD_REP_D1(C_GEQ) RD_REP_D1(C_GT) RD_REP_D1(C_LEQ) RD_REP_D1(C_LT) RD_REP_D1(C_AND) RD_REP_D1(C_OR)
-#define C_BINC(opc, d, EXPR) case SB2_CODE(opc, d): LIVE(d) { const double b = A.consts[arg]; _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) { const double a = RD(d)[c_]; RD(d)[c_] = (EXPR); } } break;
+#define C_BINC(opc, d, EXPR) case SB2_CODE(opc, d): LIVE(d) { const double b = cv; _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) { const double a = RD(d)[c_]; RD(d)[c_] = (EXPR); } } break;
 #define C_ADDC(d) C_BINC(OPC_ADDC, d, dadd(a, b))
 #define C_SUBC(d) C_BINC(OPC_SUBC, d, dsub(a, b))
 #define C_MULC(d) C_BINC(OPC_MULC, d, dmul(a, b))
@@ -370,8 +400,8 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
 #define C_LTC(d) C_BINC(OPC_LTC, d, (a < b) ? 1.0 : 0.0)
 #undef C_DIVC
 #undef C_RDIVC
-#define C_DIVC(d) case SB2_CODE(OPC_DIVC, d): LIVE(d) { double b[NC]; const double c = A.consts[arg]; _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) b[c_] = c; ddiv_batch<NC>(RD(d), b, RD(d)); } break;
-#define C_RDIVC(d) case SB2_CODE(OPC_RDIVC, d): LIVE(d) { double a[NC]; const double c = A.consts[arg]; _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) a[c_] = c; ddiv_batch<NC>(a, RD(d), RD(d)); } break;
+#define C_DIVC(d) case SB2_CODE(OPC_DIVC, d): LIVE(d) { double b[NC]; _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) b[c_] = cv; ddiv_batch<NC>(RD(d), b, RD(d)); } break;
+#define C_RDIVC(d) case SB2_CODE(OPC_RDIVC, d): LIVE(d) { double a[NC]; _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) a[c_] = cv; ddiv_batch<NC>(a, RD(d), RD(d)); } break;
           RD_REP_D0(C_ADDC) RD_REP_D0(C_SUBC) RD_REP_D0(C_MULC) RD_REP_D0(C_DIVC) RD_REP_D0(C_RSUBC) RD_REP_D0(C_RDIVC)
           RD_REP_D0(C_GEQC) RD_REP_D0(C_GTC) RD_REP_D0(C_LEQC) RD_REP_D0(C_LTC)
 #define C_BINV(opc, d, EXPR) case SB2_CODE(opc, d): LIVE(d) { _Pragma("unroll") for (int p = 0; p < NP; ++p) { LOADV(v, p); { const double a = RD(d)[2 * p], b = v.x; RD(d)[2 * p] = (EXPR); } { const double a = RD(d)[2 * p + 1], b = v.y; RD(d)[2 * p + 1] = (EXPR); } } } break;
@@ -382,6 +412,24 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
 #undef C_DIVV
 #define C_DIVV(d) case SB2_CODE(OPC_DIVV, d): LIVE(d) { double b[NC]; _Pragma("unroll") for (int p = 0; p < NP; ++p) { LOADV(v, p); b[2 * p] = v.x; b[2 * p + 1] = v.y; } ddiv_batch<NC>(RD(d), b, RD(d)); } break;
           RD_REP_D0(C_ADDV) RD_REP_D0(C_SUBV) RD_REP_D0(C_MULV) RD_REP_D0(C_DIVV)
+          // fused forms of the lowering pass: species operand and inline constant, or two species operands
+#define LOADVS(v, sidx, p) const double2 v = *reinterpret_cast<const double2*>(wop + (sidx) * (RW * SWP) + (p) * 64)
+#define C_BINVC(opc, d, EXPR) case SB2_CODE(opc, d): LIVE(d) { const double b = cv; _Pragma("unroll") for (int p = 0; p < NP; ++p) { LOADV(v, p); { const double a = v.x; RD(d)[2 * p] = (EXPR); } { const double a = v.y; RD(d)[2 * p + 1] = (EXPR); } } } break;
+#define C_ADDVC(d) C_BINVC(OPC_ADDVC, d, dadd(a, b))
+#define C_SUBVC(d) C_BINVC(OPC_SUBVC, d, dsub(a, b))
+#define C_RSUBVC(d) C_BINVC(OPC_RSUBVC, d, dsub(b, a))
+#define C_MULVC(d) C_BINVC(OPC_MULVC, d, dmul(a, b))
+          RD_REP_D0(C_ADDVC) RD_REP_D0(C_SUBVC) RD_REP_D0(C_RSUBVC) RD_REP_D0(C_MULVC)
+#define C_DIVVC(d) case SB2_CODE(OPC_DIVVC, d): LIVE(d) { double a[NC], b[NC]; _Pragma("unroll") for (int p = 0; p < NP; ++p) { LOADV(v, p); a[2 * p] = v.x; a[2 * p + 1] = v.y; b[2 * p] = cv; b[2 * p + 1] = cv; } ddiv_batch<NC>(a, b, RD(d)); } break;
+#define C_RDIVVC(d) case SB2_CODE(OPC_RDIVVC, d): LIVE(d) { double a[NC], b[NC]; _Pragma("unroll") for (int p = 0; p < NP; ++p) { LOADV(v, p); b[2 * p] = v.x; b[2 * p + 1] = v.y; a[2 * p] = cv; a[2 * p + 1] = cv; } ddiv_batch<NC>(a, b, RD(d)); } break;
+          RD_REP_D0(C_DIVVC) RD_REP_D0(C_RDIVVC)
+#define C_BINVV(opc, d, EXPR) case SB2_CODE(opc, d): LIVE(d) { const uint32_t s1_ = arg & 0xffu, s2_ = arg >> 8; _Pragma("unroll") for (int p = 0; p < NP; ++p) { LOADVS(v1, s1_, p); LOADVS(v2, s2_, p); { const double a = v1.x, b = v2.x; RD(d)[2 * p] = (EXPR); } { const double a = v1.y, b = v2.y; RD(d)[2 * p + 1] = (EXPR); } } } break;
+#define C_ADDVV(d) C_BINVV(OPC_ADDVV, d, dadd(a, b))
+#define C_SUBVV(d) C_BINVV(OPC_SUBVV, d, dsub(a, b))
+#define C_MULVV(d) C_BINVV(OPC_MULVV, d, dmul(a, b))
+          RD_REP_D0(C_ADDVV) RD_REP_D0(C_SUBVV) RD_REP_D0(C_MULVV)
+#define C_DIVVV(d) case SB2_CODE(OPC_DIVVV, d): LIVE(d) { const uint32_t s1_ = arg & 0xffu, s2_ = arg >> 8; double a[NC], b[NC]; _Pragma("unroll") for (int p = 0; p < NP; ++p) { LOADVS(v1, s1_, p); LOADVS(v2, s2_, p); a[2 * p] = v1.x; a[2 * p + 1] = v1.y; b[2 * p] = v2.x; b[2 * p + 1] = v2.y; } ddiv_batch<NC>(a, b, RD(d)); } break;
+          RD_REP_D0(C_DIVVV)
 #define C_UNARY(d) case SB2_CODE(OPC_UNARY, d): LIVE(d) { _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) RD(d)[c_] = sb2_unary((int)arg, RD(d)[c_]); } break;
           RD_REP_D0(C_UNARY)
 #define C_BINR(d) case SB2_CODE(OPC_BINR, d): LIVE(d) { _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) RD(d - 1)[c_] = sb2_binary((int)arg, RD(d - 1)[c_], RD(d)[c_]); } break;
@@ -398,23 +446,29 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
           // delta -= stoich*rate (reactants) / += (products, rate rules); calcPDE.cpp:432-449
 #define SI(s) ((s) < NS ? (s) : 0)
 #define C_ACC(s) \
-  case SB2_CODE(OPC_ACCSUB, s): if (s < NS) { const double st = A.consts[arg]; \
+  case SB2_CODE(OPC_ACCSUB, s): if (s < NS) { const double st = cv; \
       _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) acc[SI(s)][c_] = dsub(acc[SI(s)][c_], dmul(st, RD(0)[c_])); } break; \
-  case SB2_CODE(OPC_ACCADD, s): if (s < NS) { const double st = A.consts[arg]; \
+  case SB2_CODE(OPC_ACCADD, s): if (s < NS) { const double st = cv; \
       _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) acc[SI(s)][c_] = dadd(acc[SI(s)][c_], dmul(st, RD(0)[c_])); } break; \
   case SB2_CODE(OPC_ACCSUB1, s): if (s < NS) { \
       _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) acc[SI(s)][c_] = dsub(acc[SI(s)][c_], RD(0)[c_]); } break; \
   case SB2_CODE(OPC_ACCADD1, s): if (s < NS) { \
       _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) acc[SI(s)][c_] = dadd(acc[SI(s)][c_], RD(0)[c_]); } break; \
-  case SB2_CODE(OPC_ACCSUBC1, s): if (s < NS) { const double cv = A.consts[arg]; \
+  case SB2_CODE(OPC_ACCSUBC1, s): if (s < NS) { \
       _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) acc[SI(s)][c_] = dsub(acc[SI(s)][c_], cv); } break; \
-  case SB2_CODE(OPC_ACCADDC1, s): if (s < NS) { const double cv = A.consts[arg]; \
+  case SB2_CODE(OPC_ACCADDC1, s): if (s < NS) { \
       _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) acc[SI(s)][c_] = dadd(acc[SI(s)][c_], cv); } break; \
-  case SB2_CODE(OPC_ACCSUBM, s): if (s < NS) { const double st = A.consts[arg]; \
+  case SB2_CODE(OPC_ACCSUBM, s): if (s < NS) { const double st = cv; \
       _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) if (mk[c_]) acc[SI(s)][c_] = dsub(acc[SI(s)][c_], dmul(st, RD(0)[c_])); } break; \
-  case SB2_CODE(OPC_ACCADDM, s): if (s < NS) { const double st = A.consts[arg]; \
+  case SB2_CODE(OPC_ACCADDM, s): if (s < NS) { const double st = cv; \
       _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) if (mk[c_]) acc[SI(s)][c_] = dadd(acc[SI(s)][c_], dmul(st, RD(0)[c_])); } break;
           RD_REP_D0(C_ACC)
+          // reactant and product of a unit-stoichiometry law in one token: acc[s] -= r0; acc[arg] += r0
+#define C_XFER(s) case SB2_CODE(OPC_XFER, s): if (s < NS) { \
+      _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) acc[SI(s)][c_] = dsub(acc[SI(s)][c_], RD(0)[c_]); \
+      _Pragma("unroll") for (int s2_ = 0; s2_ < NS; ++s2_) if (arg == (uint32_t)s2_) { \
+        _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) acc[s2_][c_] = dadd(acc[s2_][c_], RD(0)[c_]); } } break;
+          RD_REP_D0(C_XFER)
           case SB2_CODE(OPC_END, 0): goto program_done;
           // the library only emits codes this variant implements (sb2_finalize checks depth and species count),
           // so the dispatch needs no range check
@@ -427,6 +481,7 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
     }
 
     // ---------------- diffusion (calcPDE.cpp:484-559) + output ----------------
+    if (MODE == MODE_FINAL) mbar_wait(mycbar, cparity);  // k0 / k1 of this row (requested one batch ago)
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
       if (s < S) {
@@ -438,16 +493,16 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
         if (cls == 1 && (sp.fast2d || !sp.has_diff)) {
           // every cell is an interior cell: straight-line 5-point stencil, additions in the reference's
           // order Xp, Xm, Yp, Ym
-          const double dcx = sp.has_diff ? A.consts[sp.dsrc[0]] : 0.0, dcy = sp.has_diff ? A.consts[sp.dsrc[1]] : 0.0;
+          const double dcx = sp.dconst[0], dcy = sp.dconst[1];
           double2 cu[NP], ck0[NP], ck1[NP], ck2[NP];
           if (MODE == MODE_FINAL) {
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
               const int64_t i = idx0 + p * 64;
-              cu[p] = *reinterpret_cast<const double2*>(sp.u + i);
-              ck0[p] = *reinterpret_cast<const double2*>(sp.k0 + i);
-              ck1[p] = *reinterpret_cast<const double2*>(sp.k1 + i);
+              cu[p] = *reinterpret_cast<const double2*>(sp.u + i);        // L2 hits: staged through L2 one batch ago
               ck2[p] = *reinterpret_cast<const double2*>(sp.kprev + i);
+              ck0[p] = *reinterpret_cast<const double2*>(mycs + (s * 2) * SW + p * 64 + 2 * lane);
+              ck1[p] = *reinterpret_cast<const double2*>(mycs + (s * 2 + 1) * SW + p * 64 + 2 * lane);
             }
           }
 #pragma unroll
@@ -490,7 +545,7 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
             const double2 wc = *reinterpret_cast<const double2*>(cur + p * 64);
             if (sp.dkind[0] != SB2_SRC_NONE) {  // axis 0: x
               double d0, d1;
-              if (sp.dkind[0] == SB2_SRC_CONST) { d0 = d1 = A.consts[sp.dsrc[0]]; }
+              if (sp.dkind[0] == SB2_SRC_CONST) { d0 = d1 = sp.dconst[0]; }
               else { const double2 dv = *reinterpret_cast<const double2*>(A.fields[sp.dsrc[0]] + idx); d0 = dv.x; d1 = dv.y; }
               const double wl = cur[p * 64 - 1], wr = cur[p * 64 + 2];
               auto term = [&](double dc, double wn, double w0) {
@@ -509,7 +564,7 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
             }
             if (sp.dkind[1] != SB2_SRC_NONE) {  // axis 1: y
               double d0, d1;
-              if (sp.dkind[1] == SB2_SRC_CONST) { d0 = d1 = A.consts[sp.dsrc[1]]; }
+              if (sp.dkind[1] == SB2_SRC_CONST) { d0 = d1 = sp.dconst[1]; }
               else { const double2 dv = *reinterpret_cast<const double2*>(A.fields[sp.dsrc[1]] + idx); d0 = dv.x; d1 = dv.y; }
               const double2 wu = *reinterpret_cast<const double2*>(up + p * 64);
               const double2 wd = *reinterpret_cast<const double2*>(dn + p * 64);
@@ -539,8 +594,8 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
               const double2 u = *reinterpret_cast<const double2*>(sp.u + idx);
               double2 o = u;
               if (in0 || in1) {
-                const double2 k0 = *reinterpret_cast<const double2*>(sp.k0 + idx);
-                const double2 k1 = *reinterpret_cast<const double2*>(sp.k1 + idx);
+                const double2 k0 = *reinterpret_cast<const double2*>(mycs + (s * 2) * SW + p * 64 + 2 * lane);
+                const double2 k1 = *reinterpret_cast<const double2*>(mycs + (s * 2 + 1) * SW + p * 64 + 2 * lane);
                 const double2 k2 = *reinterpret_cast<const double2*>(sp.kprev + idx);
                 if (in0) o.x = dadd(u.x, div6(dmul(A.dt, dadd(dadd(dadd(k0.x, dmul(2.0, k1.x)), dmul(2.0, k2.x)), a0))));
                 if (in1) o.y = dadd(u.y, div6(dmul(A.dt, dadd(dadd(dadd(k0.y, dmul(2.0, k1.y)), dmul(2.0, k2.y)), a1))));
@@ -551,6 +606,7 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
         }
       }
     }
+    combine_done(true);
   }
 }
 
@@ -558,7 +614,8 @@ template <int NS, int NP, int W, int MODE, int DEPTH, int MINB>
 cudaError_t launch_variant(const Sb2StageArgs& a, cudaStream_t stream) {
   using G = Geo<NP, W>;
   const int narr = (MODE == MODE_FIRST) ? 1 : 2;
-  const size_t smem = 128 + sizeof(double) * ((size_t)a.S * G::RW * G::SWP + (size_t)W * a.S * narr * G::SWP);
+  const size_t smem = 128 + tok_bytes(a.nrd) + sizeof(double) * ((size_t)a.S * G::RW * G::SWP + (size_t)W * a.S * narr * G::SWP +
+                                                                  (MODE == MODE_FINAL ? (size_t)W * a.S * 2 * G::SW : 0));
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(rd_stage_kernel<NS, NP, W, MODE, DEPTH, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

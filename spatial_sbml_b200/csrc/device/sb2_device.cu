@@ -64,6 +64,8 @@ struct sb2_sim {
   int rd_id;          // -1: first-generation stage kernel
   uint8_t* d_cls;
   int nstrips;
+  std::vector<Sb2RdTok> rdprog;  // lowered token records (constants patched per launch from rdslot)
+  std::vector<int> rdslot;       // constants-table slot of each record's inline constant, -1 = none
   uint32_t* d_dbg;    // SB2_DEBUG=1: device debug words, checked after every stage launch
   bool trace;         // SB2_TRACE=1: entry points report to stderr
 };
@@ -293,6 +295,59 @@ int compile_stmt(sb2_sim* sim, const Sb2Stmt& st, std::vector<uint32_t>& prog) {
   return SB2_OK;
 }
 
+// Lowering of the register bytecode for the rd_stage kernel: 16-byte records whose constants travel inline, and
+// three peephole fusions that save a dispatch each —
+//   PUSHV d v ; <op>C d c   →  <op>VC d v c      (r[d] = v op c, or c op v for the reversed forms)
+//   PUSHV d v1 ; <op>V d v2 →  <op>VV d v1 v2
+//   ACCSUB1 s1 ; ACCADD1 s2 →  XFER s1 s2        (reactant and product of a unit-stoichiometry law)
+void rd_lower(const std::vector<uint32_t>& prog, std::vector<Sb2RdTok>& out, std::vector<int>& slots) {
+  out.clear(); slots.clear();
+  auto opc_of = [](uint32_t t) { return (int)((t & 0xffffu) / SB2_MAX_DEPTH); };
+  auto d_of = [](uint32_t t) { return (int)((t & 0xffffu) % SB2_MAX_DEPTH); };
+  auto emit = [&](int opc, int d, uint32_t arg, int slot) {
+    Sb2RdTok r; r.code = SB2_CODE(opc, d); r.arg = arg; r.c = 0.0;
+    out.push_back(r); slots.push_back(slot);
+  };
+  auto has_const = [](int opc) {
+    return opc == OPC_PUSHC || (opc >= OPC_ADDC && opc <= OPC_LTC) || opc == OPC_ACCSUB || opc == OPC_ACCADD ||
+           opc == OPC_ACCSUBC1 || opc == OPC_ACCADDC1 || opc == OPC_ACCSUBM || opc == OPC_ACCADDM;
+  };
+  for (size_t i = 0; i < prog.size(); ++i) {
+    const uint32_t t = prog[i];
+    const int opc = opc_of(t), d = d_of(t);
+    const uint32_t arg = t >> 16;
+    if (i + 1 < prog.size()) {
+      const uint32_t n = prog[i + 1];
+      const int nopc = opc_of(n), nd = d_of(n);
+      const uint32_t narg = n >> 16;
+      if (opc == OPC_PUSHV && nd == d) {
+        int f = -1;
+        switch (nopc) {
+          case OPC_ADDC: f = OPC_ADDVC; break;
+          case OPC_SUBC: f = OPC_SUBVC; break;
+          case OPC_RSUBC: f = OPC_RSUBVC; break;
+          case OPC_MULC: f = OPC_MULVC; break;
+          case OPC_DIVC: f = OPC_DIVVC; break;
+          case OPC_RDIVC: f = OPC_RDIVVC; break;
+          default: break;
+        }
+        if (f >= 0) { emit(f, d, arg, (int)narg); ++i; continue; }
+        switch (nopc) {
+          case OPC_ADDV: f = OPC_ADDVV; break;
+          case OPC_SUBV: f = OPC_SUBVV; break;
+          case OPC_MULV: f = OPC_MULVV; break;
+          case OPC_DIVV: f = OPC_DIVVV; break;
+          default: break;
+        }
+        if (f >= 0) { emit(f, d, arg | (narg << 8), -1); ++i; continue; }
+      }
+      if (opc == OPC_ACCSUB1 && nopc == OPC_ACCADD1) { emit(OPC_XFER, d, (uint32_t)nd, -1); ++i; continue; }
+    }
+    if (has_const(opc)) emit(opc, d, 0, (int)arg);
+    else emit(opc, d, arg, -1);
+  }
+}
+
 const char* kOpcNames[OPC_COUNT] = {"END", "PUSHC", "PUSHV", "PUSHF", "ADD", "SUB", "MUL", "DIV", "GEQ", "GT",
   "LEQ", "LT", "AND", "OR", "ADDC", "SUBC", "MULC", "DIVC", "RSUBC", "RDIVC", "GEQC", "GTC", "LEQC", "LTC", "ADDV", "SUBV", "MULV",
   "DIVV", "UNARY", "BINR", "MOV0", "MOVUP", "MASK", "ACCSUB", "ACCADD", "ACCSUB1", "ACCADD1", "ACCSUBC1", "ACCADDC1", "ACCSUBM", "ACCADDM"};
@@ -308,10 +363,13 @@ void fill_stage_args(sb2_sim* sim, Sb2StageArgs& a, int m, double dt, int row_be
   a.carry = (sim->carry_k0 && m == 0) || !sim->transports.empty() ? 1 : 0;
   a.row_begin = row_begin;
   a.row_end = row_end;
+  for (size_t i = 0; i < sim->rdslot.size(); ++i)
+    if (sim->rdslot[i] >= 0) a.rdtok[i].c = sim->consts[sim->rdslot[i]];
   const int S = (int)sim->species.size();
   for (int s = 0; s < S; ++s) {
     Sb2Species& sp = sim->species[s];
     Sb2SpeciesArgs& o = a.sp[s];
+    for (int ax = 0; ax < 3; ++ax) o.dconst[ax] = sp.dkind[ax] == SB2_SRC_CONST ? sim->consts[sp.dsrc[ax]] : 0.0;
     o.u = sp.u[sp.cur];
     o.u_out = sp.u[sp.cur ^ 1];
     o.kprev = m > 0 ? sp.k[m - 1] : sp.k[0];
@@ -595,8 +653,15 @@ int sb2_finalize(sb2_sim* sim) {
   // first-generation kernel (kept for 3-D grids and more species, and as a cross-check in the tests)
   const char* force = getenv("SB2_STAGE_KERNEL");
   sim->rd_id = (force && !strcmp(force, "gen1")) ? -1 : sb2_rd_pick_variant(sim->g.dim, sim->g.nx, b.S, b.depth, &sim->rd);
+  if (sim->rd_id >= 0) {
+    rd_lower(sim->program, sim->rdprog, sim->rdslot);
+    if (sim->rdprog.size() > SB2_RD_MAX_TOKENS) sim->rd_id = -1;  // very long programs stay on the first-generation kernel
+  }
   b.rd_variant = sim->rd_id;
   if (sim->rd_id >= 0) {
+    b.nrd = (int)sim->rdprog.size();
+    memset(b.rdtok, 0, sizeof(b.rdtok));
+    memcpy(b.rdtok, sim->rdprog.data(), sizeof(Sb2RdTok) * sim->rdprog.size());
     const int sw = 64 * sim->rd.np;
     if (sw + 4 > SB2_TAIL_PAD) return fail(sim, SB2_ERR_STATE, "strip wider than the tail pad of the field layout");
     sim->nstrips = (sim->g.nx + sw - 1) / sw;

@@ -36,7 +36,12 @@ enum Sb2Opc {
   OPC_ACCSUB1, OPC_ACCADD1,    // stoichiometry exactly 1.0: acc[d] -/+= r[0]   (1.0 * x == x bit for bit)
   OPC_ACCSUBC1, OPC_ACCADDC1,  // constant law, stoichiometry 1.0: acc[d] -/+= consts[arg]
   OPC_ACCSUBM, OPC_ACCADDM,    // like ACCSUB / ACCADD, but only on the cells selected by the last MASK
-  OPC_COUNT
+  OPC_COUNT,
+  // ---- rd_stage only: fused forms produced by the lowering pass (sb2_rd_lower); arg = species, c = inline constant
+  OPC_ADDVC = OPC_COUNT, OPC_SUBVC, OPC_RSUBVC, OPC_MULVC, OPC_DIVVC, OPC_RDIVVC,  // r[d] = v op c   (R: c op v)
+  OPC_ADDVV, OPC_SUBVV, OPC_MULVV, OPC_DIVVV,                                      // r[d] = v1 op v2  (arg = v1 | v2 << 8)
+  OPC_XFER,                                                                        // acc[d] -= r[0]; acc[arg] += r[0]
+  OPC_RD_COUNT
 };
 
 // field layout pads (in elements) around the guard rows, see sb2_create
@@ -44,6 +49,10 @@ enum Sb2Opc {
 #define SB2_TAIL_PAD 264
 
 #define SB2_CODE(opc, d) ((uint32_t)(opc) * SB2_MAX_DEPTH + (uint32_t)(d))
+
+// rd_stage token record: 16 bytes, fetched with one shared-memory load; constants travel inline
+struct Sb2RdTok { uint32_t code; uint32_t arg; double c; };
+#define SB2_RD_MAX_TOKENS 384
 
 struct Sb2SpeciesArgs {
   const double* u;      // current value
@@ -57,6 +66,7 @@ struct Sb2SpeciesArgs {
   int32_t fast2d;    // 2-D, uniform coefficients on both axes, dx^2 == dy^2 == 1: straight-line interior stencil
   int32_t dkind[3];  // SB2_SRC_*
   int32_t dsrc[3];
+  double dconst[3];  // value of a uniform coefficient at launch time
 };
 
 struct Sb2StageArgs {
@@ -82,7 +92,9 @@ struct Sb2StageArgs {
   int32_t nstrips;     // strips per row of the class map
   uint32_t* dbg;       // rd_stage: debug words (SB2_DEBUG=1), else NULL; [0] = mbarrier waits that timed out
   int32_t rd_variant;  // rd_stage kernel variant chosen at finalize (-1: the first-generation kernel runs)
+  int32_t nrd;         // rd_stage: token records (without the trailing OPC_END pair)
   uint32_t tok[SB2_MAX_TOKENS + 2];  // + trailing OPC_END (the interpreter fetches one token ahead)
+  Sb2RdTok rdtok[SB2_RD_MAX_TOKENS + 2];
   double consts[SB2_MAX_CONSTS];
 };
 
