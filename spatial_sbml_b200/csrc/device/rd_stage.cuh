@@ -50,6 +50,18 @@ enum { MODE_FIRST = 0, MODE_MIDDLE = 1, MODE_FINAL = 2 };
 // PTX: mbarrier + bulk asynchronous copy (TMA, non-tensor form)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// one lane of the (converged) warp, chosen by the hardware: code under it may use the uniform datapath
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -82,22 +94,28 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes
   asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(src), "r"(bytes), "l"(policy) : "memory");
 }
 // Bounded wait: a copy that never lands (a bug) ends in wrong results and a failed test, not in a hung GPU.
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done;
+}
+__device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
-  for (;;) {
-    uint32_t done;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) return true;
+  while (!mbar_try_wait(bar, parity))
     if (clock64() - t0 > 400000000LL) return false;  // ~0.2 s
-  }
+  return true;
+}
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return true;  // the copy was issued a whole batch ago: normally it has landed
+  return mbar_wait_slow(bar, parity);
 }
 
 __host__ __device__ inline int tok_bytes(int nrd) { return ((nrd + 2) * 16 + 127) / 128 * 128; }
@@ -143,7 +161,9 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
   double* cbase = rawbase + (size_t)W * S * NARR * SWP;
 
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
+  // broadcast from lane 0: the compiler then knows the warp index (and every row / slot address derived from it)
+  // is warp-uniform and issues the bulk copies from uniform registers instead of a per-lane waterfall loop
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int x0 = blockIdx.x * SW;
   const int yb = A.row_begin + blockIdx.y * A.rows_per_block;
   const int ye = min(yb + A.rows_per_block, A.row_end);
@@ -203,14 +223,16 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
 
   // batch b = -1 is the prologue: warps W-2 and W-1 stage rows yb-1 and yb, nobody computes
   int wrow = yb - W + warp + 1;  // row this warp turns into w in the current batch
-  if (wrow >= yb - 1 && wrow <= ye && lane == 0) issue_row(wrow);
+  if (wrow >= yb - 1 && wrow <= ye && elect_one()) issue_row(wrow);
   uint32_t parity = 0;
+  int slot_w = warp + 2 - W;  // (wrow - (yb - 1)) mod RW, carried from batch to batch
+  if (slot_w < 0) slot_w += RW;
 
-  for (int Y = yb - W; Y < ye; Y += W, wrow += W) {
+  for (int Y = yb - W; Y < ye; Y += W, wrow += W, slot_w = slot_w + W >= RW ? slot_w + W - RW : slot_w + W) {
     const int srow = Y + warp;  // row this warp computes in the current batch
     const bool compute = (Y >= yb) && (srow < ye);
     int cls = 2;
-    if (compute) cls = A.carry ? 0 : (int)A.cls[(int64_t)srow * A.nstrips + blockIdx.x];
+    if (compute) cls = A.carry ? 0 : (int)A.cls[(uint32_t)srow * (uint32_t)A.nstrips + blockIdx.x];
 
     // (1) + (2): raw row → w ring
     if (wrow >= yb - 1 && wrow <= ye) {
@@ -218,7 +240,7 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
         if (atomicAdd(&A.dbg[0], 1u) == 0) { A.dbg[1] = blockIdx.x; A.dbg[2] = blockIdx.y; A.dbg[3] = warp; A.dbg[4] = (uint32_t)wrow; A.dbg[5] = parity; A.dbg[6] = (uint32_t)yb; A.dbg[7] = (uint32_t)ye; }
       }
       parity ^= 1;
-      const int wslot = (wrow - (yb - 1)) % RW;
+      const int wslot = slot_w;
 #pragma unroll
       for (int s = 0; s < NS; ++s) {
         if (s < S) {
@@ -248,7 +270,7 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
     }
     // (3) the slot is free again: fetch the row of the next batch (in the prologue this is the first fetch of
     // the warps that had nothing to stage yet)
-    if (lane == 0) {
+    if (elect_one()) {
       const int nrow = wrow + W;
       if (nrow >= yb - 1 && nrow <= ye) issue_row(nrow);
       // the first k0 / k1 rows; later ones are requested as soon as the combine has read the previous ones
@@ -261,7 +283,7 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
       if (!waited) { mbar_wait(mycbar, cparity); }
       cparity ^= 1;
       __syncwarp();
-      if (lane == 0 && srow + W < ye) issue_combine(srow + W);
+      if (srow + W < ye && elect_one()) issue_combine(srow + W);
     };
 
     // per-cell flag bytes of all geometries (byte g = geometry g); only class-0 rows look at them
@@ -330,8 +352,8 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
       }
     }
 
-    const int q = srow - (yb - 1);  // >= 1
-    const int slot_c = q % RW, slot_u = (q + 1) % RW, slot_d = (q - 1) % RW;
+    // ring slots of rows srow, srow + 1, srow - 1 (row srow + 1 is the one this warp just staged)
+    const int slot_u = slot_w, slot_c = slot_w == 0 ? RW - 1 : slot_w - 1, slot_d = slot_c == 0 ? RW - 1 : slot_c - 1;
 
     double acc[NS][NC];
 #pragma unroll
