@@ -130,16 +130,34 @@ struct Geo {
 
 // Division by 6.0 for the RK combine: q = RN(x * RN(1/6)), r = x - 6q (exact in an FMA), q' = RN(q + r*RN(1/6))
 // is the correctly rounded quotient whenever no intermediate leaves the normal range (Markstein 1990; the
-// significand of 6.0 is not all ones).  Outside a generous exponent window the true division runs.
-__device__ __forceinline__ double div6(double x) {
-  const int hi = __double2hiint(x) & 0x7ff00000;
-  if (hi > 0x08000000 && hi < 0x78000000) {
-    const double y = 0.16666666666666666;  // RN(1/6)
-    const double q = __dmul_rn(x, y);
-    const double r = __fma_rn(-q, 6.0, x);
-    return __fma_rn(r, y, q);
+// significand of 6.0 is not all ones).  N numerators at once: the three-instruction chains overlap, one range test
+// covers them all, and only if some numerator lies outside a generous exponent window (or is a NaN / infinity) the
+// true division runs for every one of them.  A zero numerator returns itself (x / 6 == x bit for bit, sign included).
+template <int N>
+__device__ __forceinline__ void div6_batch(double (&x)[N]) {
+  const double y = 0.16666666666666666;  // RN(1/6)
+  double q[N];
+  bool ok = true;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const uint32_t e = (uint32_t)__double2hiint(x[i]) & 0x7ff00000u;
+    const bool zero = x[i] == 0.0;
+    ok = ok && (zero || (e - 0x08100000u) < 0x6fe00000u);
+    const double q0 = __dmul_rn(x[i], y);
+    const double r = __fma_rn(-q0, 6.0, x[i]);
+    q[i] = zero ? x[i] : __fma_rn(r, y, q0);
   }
-  return ddiv_pos(x, 6.0);
+  if (!ok) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) q[i] = ddiv_pos(x[i], 6.0);
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) x[i] = q[i];
+}
+__device__ __forceinline__ double div6(double x) {
+  double a[1] = {x};
+  div6_batch<1>(a);
+  return a[0];
 }
 
 #define RD_REP_D0(M) M(0) M(1) M(2) M(3) M(4) M(5) M(6) M(7)
@@ -155,7 +173,9 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
   // [last stage: k0 / k1 slots: W x S x 2 x SW]
   const int S = A.S;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
-  const uint4* toks = reinterpret_cast<const uint4*>(smem_raw + 128);
+  // token stream, two parallel arrays: code | arg << 16 (4 bytes each) and the inline constants (8 bytes each)
+  const double* tokc = reinterpret_cast<const double*>(smem_raw + 128);
+  const uint32_t* toks = reinterpret_cast<const uint32_t*>(smem_raw + 128 + (A.nrd + 2) * 8);
   double* wring = reinterpret_cast<double*>(smem_raw + 128 + tok_bytes(A.nrd));
   double* rawbase = wring + (size_t)S * RW * SWP;
   double* cbase = rawbase + (size_t)W * S * NARR * SWP;
@@ -185,7 +205,8 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
   // the token records move from the kernel parameters to shared memory once (first read after the first barrier)
   for (int i = threadIdx.x; i < A.nrd + 2; i += W * 32) {
     const Sb2RdTok t = A.rdtok[i];
-    reinterpret_cast<uint4*>(smem_raw + 128)[i] = make_uint4(t.code, t.arg, (uint32_t)__double2loint(t.c), (uint32_t)__double2hiint(t.c));
+    reinterpret_cast<double*>(smem_raw + 128)[i] = t.c;
+    reinterpret_cast<uint32_t*>(smem_raw + 128 + (A.nrd + 2) * 8)[i] = t.code | (t.arg << 16);
   }
   __syncwarp();
 
@@ -373,20 +394,19 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
       double r[DEPTH][NC];  // RD(d): slot d of the expression stack; slots >= DEPTH do not exist in this variant
 #define RD(d) r[(d) < DEPTH ? (d) : 0]
 #define LIVE(d) if ((d) < DEPTH)
-      bool mk[NC];  // set by MASK, read by the ACC*M forms only
-#pragma unroll
-      for (int c = 0; c < NC; ++c) mk[c] = false;
+      uint32_t mask_bit = 0;  // set by MASK (bit of the law's geometry in the flag words), read by the ACC*M forms only
       const double* wop = wring + slot_c * SWP + 2 + 2 * lane;  // + s*RW*SWP selects the species, + 64p the pair
 
-      uint4 tnext = toks[0];
+      uint32_t tnext = toks[0];
       int pc = 0;
 #pragma unroll 1
       for (;;) {
-        const uint4 t = tnext;
-        tnext = toks[++pc];  // one record ahead; the stream ends with two OPC_END records
-        const uint32_t arg = t.y;
-        const double cv = __hiloint2double((int)t.w, (int)t.z);  // inline constant of the C forms
-        switch (t.x) {
+        const uint32_t t = tnext;
+        const double* cvp = tokc + pc;  // inline constant of the C forms, loaded by the cases that use it
+        tnext = toks[++pc];  // one token ahead; the stream ends with two OPC_END tokens
+        const uint32_t arg = t >> 16;
+#define cv (*cvp)
+        switch (t & 0xffffu) {
 #define LOADV(v, p) const double2 v = *reinterpret_cast<const double2*>(wop + arg * (RW * SWP) + (p) * 64)
 #define C_PUSHC(d) case SB2_CODE(OPC_PUSHC, d): LIVE(d) { _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) RD(d)[c_] = cv; } break;
           RD_REP_D0(C_PUSHC)
@@ -461,10 +481,7 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
 #define C_MOVUP(d) case SB2_CODE(OPC_MOVUP, d): LIVE(d + 1) { _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) RD(d + 1)[c_] = RD(d)[c_]; } break;
           RD_REP_D0(C_MOVUP)
           // statement mask: the law only acts on cells of its own domain (spatialsimulator.cpp:1381-1390)
-          case SB2_CODE(OPC_MASK, 0): {
-#pragma unroll
-            for (int c = 0; c < NC; ++c) mk[c] = (fl[c] >> (8 * arg)) & 1u;
-          } break;
+          case SB2_CODE(OPC_MASK, 0): mask_bit = 1u << (8 * arg); break;
           // delta -= stoich*rate (reactants) / += (products, rate rules); calcPDE.cpp:432-449
 #define SI(s) ((s) < NS ? (s) : 0)
 #define C_ACC(s) \
@@ -481,9 +498,9 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
   case SB2_CODE(OPC_ACCADDC1, s): if (s < NS) { \
       _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) acc[SI(s)][c_] = dadd(acc[SI(s)][c_], cv); } break; \
   case SB2_CODE(OPC_ACCSUBM, s): if (s < NS) { const double st = cv; \
-      _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) if (mk[c_]) acc[SI(s)][c_] = dsub(acc[SI(s)][c_], dmul(st, RD(0)[c_])); } break; \
+      _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) if (fl[c_] & mask_bit) acc[SI(s)][c_] = dsub(acc[SI(s)][c_], dmul(st, RD(0)[c_])); } break; \
   case SB2_CODE(OPC_ACCADDM, s): if (s < NS) { const double st = cv; \
-      _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) if (mk[c_]) acc[SI(s)][c_] = dadd(acc[SI(s)][c_], dmul(st, RD(0)[c_])); } break;
+      _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) if (fl[c_] & mask_bit) acc[SI(s)][c_] = dadd(acc[SI(s)][c_], dmul(st, RD(0)[c_])); } break;
           RD_REP_D0(C_ACC)
           // reactant and product of a unit-stoichiometry law in one token: acc[s] -= r0; acc[arg] += r0
 #define C_XFER(s) case SB2_CODE(OPC_XFER, s): if (s < NS) { \
@@ -498,6 +515,7 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
         }
       }
     program_done:;
+#undef cv
 #undef RD
 #undef LIVE
     }
@@ -548,10 +566,11 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
               *reinterpret_cast<double2*>(sp.kout + idx0 + p * 64) = make_double2(a0, a1);
             } else {
               // value += dt*(k0 + 2.0*k1 + 2.0*k2 + k3)/6.0, spatialsimulator.cpp:1535
-              double2 o;
-              o.x = dadd(cu[p].x, div6(dmul(A.dt, dadd(dadd(dadd(ck0[p].x, dmul(2.0, ck1[p].x)), dmul(2.0, ck2[p].x)), a0))));
-              o.y = dadd(cu[p].y, div6(dmul(A.dt, dadd(dadd(dadd(ck0[p].y, dmul(2.0, ck1[p].y)), dmul(2.0, ck2[p].y)), a1))));
-              *reinterpret_cast<double2*>(sp.u_out + idx0 + p * 64) = o;
+              double inc[2];
+              inc[0] = dmul(A.dt, dadd(dadd(dadd(ck0[p].x, dmul(2.0, ck1[p].x)), dmul(2.0, ck2[p].x)), a0));
+              inc[1] = dmul(A.dt, dadd(dadd(dadd(ck0[p].y, dmul(2.0, ck1[p].y)), dmul(2.0, ck2[p].y)), a1));
+              div6_batch<2>(inc);
+              *reinterpret_cast<double2*>(sp.u_out + idx0 + p * 64) = make_double2(dadd(cu[p].x, inc[0]), dadd(cu[p].y, inc[1]));
             }
           }
           continue;
