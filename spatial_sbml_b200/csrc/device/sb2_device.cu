@@ -380,10 +380,13 @@ void fill_stage_args(sb2_sim* sim, Sb2StageArgs& a, int m, double dt, int row_be
   // rows per CTA: enough CTAs to fill the machine several times over, long enough strips to
   // amortise the two extra rows each CTA loads
   if (sim->rd_id >= 0) {
-    // a CTA walks its rows in batches of W: long tiles amortise the prologue batch, enough tiles fill the SMs
+    // a CTA walks its rows in batches of W.  Measured at 8192^2 (ms per step): 3, 4, 6, 8, 16, 32, 64 batches per tile →
+    // 3.53, 3.43, 3.33, 3.33, 3.40, 3.75, 4.31: short tiles keep the rows in flight close together in memory and the
+    // waves even, the prologue batch they pay for is cheap
     const int W = sim->rd.w;
     const int rows = row_end - row_begin;
-    int rpb = 16 * W;
+    static const int rpb_batches = getenv("SB2_RD_BATCHES") ? atoi(getenv("SB2_RD_BATCHES")) : 8;
+    int rpb = rpb_batches * W;
     while (rpb > W && (int64_t)sim->nstrips * ((rows + rpb - 1) / rpb) < 148 * 6) rpb -= W;
     a.rows_per_block = rpb;
     a.np = sim->rd.np;
