@@ -138,6 +138,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=int(os.environ.get("BENCH_N", "8192")))
+    ap.add_argument("--dim", type=int, default=2, choices=[2, 3], help="3: the n^3 variant of the workload (default n 512), z-slabs")
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -145,7 +146,16 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     n = args.n
-    config = {"workload": "synthetic Turing (examples/turing.xml kinetics) %dx%d cells per GPU, 2 species, fp64, dt %.2f, RK4" % (n, n, DT),
+    if args.dim == 3 and n == 8192:
+        n = 512
+    dt = DT if args.dim == 2 else 0.02  # 3-D: six neighbours, D = 4 → explicit stability limit dx^2 / (2 d D) = 0.0208
+    if args.dim == 3:
+        config = {"workload": "synthetic Turing (examples/turing.xml kinetics + z axis) %dx%dx%d cells per GPU, 2 species, fp64, dt %.2f, RK4" % (n, n, n, dt),
+                  "grid": [n, n, n * world], "cells_per_gpu": n ** 3,
+                  "parallelism": "z-slabs x%d, NCCL halo exchange per RK stage" % world if world > 1 else "1 GPU",
+                  "l2": "per-step working set %.1f GB per GPU, far larger than the 126 MB L2 (no flush needed)" % (6 * S * n ** 3 * 8 / 1e9)}
+    else:
+      config = {"workload": "synthetic Turing (examples/turing.xml kinetics) %dx%d cells per GPU, 2 species, fp64, dt %.2f, RK4" % (n, n, DT),
               "grid": [n, n * world], "cells_per_gpu": n * n, "parallelism": "y-slabs x%d, NCCL halo exchange per RK stage" % world if world > 1 else "1 GPU",
               "l2": "per-step working set %.1f GB per GPU, far larger than the 126 MB L2 (no flush needed)" % (6 * S * n * n * 8 / 1e9)}
 
@@ -185,8 +195,12 @@ def main():
     K, W = args.steps, max(args.warmup, 3)
 
     t_init = time.time()
-    model = synthetic.turing(n, n * world)
-    shard = ShardedSimulator(model, n, n * world, 1, dim=2, device=local_rank)
+    if args.dim == 3:
+        model = synthetic.turing(n, n, n * world)
+        shard = ShardedSimulator(model, n, n, n * world, dim=3, device=local_rank)
+    else:
+        model = synthetic.turing(n, n * world)
+        shard = ShardedSimulator(model, n, n * world, 1, dim=2, device=local_rank)
     init_s = time.time() - t_init
     cells = shard.num_domain_cells()
 
@@ -196,13 +210,13 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    shard.run_steps(0, DT, W)
+    shard.run_steps(0, dt, W)
     sync_all()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = shard.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    shard.run_steps(W, DT, K)
+    shard.run_steps(W, dt, K)
     ev1.record()
     sync_all()
     ms = ev0.elapsed_time(ev1)
@@ -239,7 +253,7 @@ def main():
         for i in range(Ke):
             for b, name in zip(hbuf, names):
                 sim.setVariableCompact(name, b)          # H2D from pinned memory
-            sim.oneStep(W + K + i, DT)
+            sim.oneStep(W + K + i, dt)
             for b, name in zip(hbuf, names):
                 sim.getVariableCompact(name, out=b)      # D2H into pinned memory
         e1.record()
@@ -256,7 +270,7 @@ def main():
         for i in range(Ke):
             for b, name in zip(hbuf, names):
                 sim.setVariableCompact(name, b)
-            shard.step(W + K + i, DT)
+            shard.step(W + K + i, dt)
             for b, name in zip(hbuf, names):
                 sim.getVariableCompact(name, out=b)
         e1.record()

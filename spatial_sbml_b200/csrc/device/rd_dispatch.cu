@@ -18,16 +18,18 @@ const Sb2RdVariant kVariants[] = {
 // One warp per (row, strip): class 1 when every cell of the strip row carries exactly SB2_F_DOMAIN in every
 // geometry (interior cell, no boundary bit), class 2 when no cell is in any domain, else 0.
 __global__ void __launch_bounds__(256) classify_kernel(const uint8_t* f0, const uint8_t* f1, const uint8_t* f2, const uint8_t* f3,
-                                                       int G, int nx, int nrows, int64_t P, int64_t first, int sw, uint8_t* cls, int nstrips) {
+                                                       int G, int nx, int ny, int nz, int64_t P, int64_t PL, int64_t first, int sw, uint8_t* cls,
+                                                       int nstrips) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= nrows * nstrips) return;
+  if (warp >= ny * nz * nstrips) return;
   const int row = warp / nstrips, strip = warp % nstrips;
+  const int64_t row0 = first + (int64_t)(row / ny) * PL + (int64_t)(row % ny) * P;
   const uint8_t* fl[4] = {f0, f1, f2, f3};
   bool all_interior = true, any_domain = false;
   for (int i = lane; i < sw; i += 32) {
     const int x = strip * sw + i;
     for (int g = 0; g < G; ++g) {
-      const uint8_t v = x < nx ? fl[g][first + (int64_t)row * P + x] : 0;
+      const uint8_t v = x < nx ? fl[g][row0 + x] : 0;
       all_interior = all_interior && v == SB2_F_DOMAIN;
       any_domain = any_domain || (v & SB2_F_DOMAIN);
     }
@@ -39,7 +41,7 @@ __global__ void __launch_bounds__(256) classify_kernel(const uint8_t* f0, const 
 }  // namespace
 
 int sb2_rd_pick_variant(int dim, int nx, int nspecies, int depth, Sb2RdVariant* out) {
-  if (dim != 2 || nspecies < 1 || nspecies > 4) return -1;
+  if ((dim != 2 && dim != 3) || nspecies < 1 || nspecies > 4) return -1;
   int id;
   if (nspecies <= 2) id = (depth <= 4 && nx >= 192) ? 1 : 2;  // (measured at 8192^2: variant 1 beats 0 and 5)
   else id = (depth <= 4 && nx >= 192) ? 3 : 4;
@@ -62,11 +64,11 @@ cudaError_t sb2_rd_launch(const Sb2StageArgs& a, cudaStream_t stream) {
   }
 }
 
-cudaError_t sb2_rd_classify(const uint8_t* const* flags, int G, int nx, int nrows, int64_t P, int64_t first, int sw,
-                            uint8_t* cls, int nstrips, cudaStream_t stream) {
-  const int64_t warps = (int64_t)nrows * nstrips;
+cudaError_t sb2_rd_classify(const uint8_t* const* flags, int G, int nx, int ny, int nz, int64_t P, int64_t PL, int64_t first,
+                            int sw, uint8_t* cls, int nstrips, cudaStream_t stream) {
+  const int64_t warps = (int64_t)ny * nz * nstrips;
   const int blocks = (int)((warps * 32 + 255) / 256);
   classify_kernel<<<blocks, 256, 0, stream>>>(flags[0], G > 1 ? flags[1] : nullptr, G > 2 ? flags[2] : nullptr,
-                                               G > 3 ? flags[3] : nullptr, G, nx, nrows, P, first, sw, cls, nstrips);
+                                               G > 3 ? flags[3] : nullptr, G, nx, ny, nz, P, PL, first, sw, cls, nstrips);
   return cudaGetLastError();
 }

@@ -1,4 +1,4 @@
-// rd_stage.cuh — the fused reaction–diffusion RK-stage kernel for 2-D grids (sm_100a), second design.
+// rd_stage.cuh — the fused reaction–diffusion RK-stage kernel (sm_100a), second design; 2-D and 3-D grids.
 //
 // One launch computes, for every volume cell of the slab and every staged species,
 //     k_m = sum over reactions / rate rules (bytecode interpreter)  +  diffusion stencil
@@ -163,7 +163,7 @@ __device__ __forceinline__ double div6(double x) {
 #define RD_REP_D0(M) M(0) M(1) M(2) M(3) M(4) M(5) M(6) M(7)
 #define RD_REP_D1(M) M(1) M(2) M(3) M(4) M(5) M(6) M(7)
 
-template <int NS, int NP, int W, int MODE, int DEPTH, int MINB>
+template <int NS, int NP, int W, int MODE, int DEPTH, int MINB, bool D3>
 __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_constant__ Sb2StageArgs A) {
   using G = Geo<NP, W>;
   constexpr int NC = G::NC, SW = G::SW, SWP = G::SWP, RW = G::RW;
@@ -185,9 +185,14 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
   // is warp-uniform and issues the bulk copies from uniform registers instead of a per-lane waterfall loop
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int x0 = blockIdx.x * SW;
-  const int yb = A.row_begin + blockIdx.y * A.rows_per_block;
-  const int ye = min(yb + A.rows_per_block, A.row_end);
+  // 2-D: the slab axis is y, a tile is a range of the slab's rows.  3-D: the slab axis is z, a tile is a range of the
+  // rows of one plane; the z neighbours of a row are read straight from global memory (L2: the planes either side
+  // have just been, or are about to be, staged by the CTAs of the neighbouring planes).
+  const int z = D3 ? A.row_begin + (int)blockIdx.z : 0;
+  const int yb = D3 ? (int)blockIdx.y * A.rows_per_block : A.row_begin + (int)blockIdx.y * A.rows_per_block;
+  const int ye = min(yb + A.rows_per_block, D3 ? A.ny : A.row_end);
   if (yb >= ye) return;
+  const int64_t plane0 = A.first + (D3 ? (int64_t)z * A.PL : 0);
 
   double* myraw = rawbase + (size_t)warp * S * NARR * SWP;
   const uint32_t mybar = smem_addr(&bars[warp]);
@@ -216,7 +221,7 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
   // lane 0: bulk copy of raw row r (u and k_{m-1} of every species, halo columns included) into the warp's slot
   auto issue_row = [&](int r) {
     mbar_expect_tx(mybar, row_bytes * NARR * S);
-    const int64_t g = A.first + (int64_t)r * A.P + x0 - 2;
+    const int64_t g = plane0 + (int64_t)r * A.P + x0 - 2;
     for (int s = 0; s < S; ++s) {
       if (MODE == MODE_FINAL) {
         bulk_g2s_hint(myraw_s + (s * NARR) * row_bytes, A.sp[s].u + g, row_bytes, mybar, keep);
@@ -230,7 +235,7 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
   // last stage, lane 0: bulk copy of the k0 / k1 rows (own cells) the combine of row r needs, one batch ahead
   auto issue_combine = [&](int r) {
     mbar_expect_tx(mycbar, SW * sizeof(double) * 2 * S);
-    const int64_t g = A.first + (int64_t)r * A.P + x0;
+    const int64_t g = plane0 + (int64_t)r * A.P + x0;
     for (int s = 0; s < S; ++s) {
       bulk_g2s(mycs_s + (s * 2) * SW * sizeof(double), A.sp[s].k0 + g, SW * sizeof(double), mycbar);
       bulk_g2s(mycs_s + (s * 2 + 1) * SW * sizeof(double), A.sp[s].k1 + g, SW * sizeof(double), mycbar);
@@ -253,7 +258,7 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
     const int srow = Y + warp;  // row this warp computes in the current batch
     const bool compute = (Y >= yb) && (srow < ye);
     int cls = 2;
-    if (compute) cls = A.carry ? 0 : (int)A.cls[(uint32_t)srow * (uint32_t)A.nstrips + blockIdx.x];
+    if (compute) cls = A.carry ? 0 : (int)A.cls[((uint32_t)z * (uint32_t)A.ny + (uint32_t)srow) * (uint32_t)A.nstrips + blockIdx.x];
 
     // (1) + (2): raw row → w ring
     if (wrow >= yb - 1 && wrow <= ye) {
@@ -312,7 +317,7 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
 #pragma unroll
     for (int c = 0; c < NC; ++c) fl[c] = 0x01010101u;
     if (cls == 0) {
-      const int64_t base = A.first + (int64_t)srow * A.P + x0 + 2 * lane;
+      const int64_t base = plane0 + (int64_t)srow * A.P + x0 + 2 * lane;
 #pragma unroll
       for (int p = 0; p < NP; ++p) {
         fl[2 * p] = 0; fl[2 * p + 1] = 0;
@@ -332,7 +337,7 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
     __syncthreads();  // (4)
     if (!compute) continue;
 
-    const int64_t idx0 = A.first + (int64_t)srow * A.P + x0 + 2 * lane;  // + 64p for pair p
+    const int64_t idx0 = plane0 + (int64_t)srow * A.P + x0 + 2 * lane;  // + 64p for pair p
     if (cls == 2) {
       // nothing of this strip row lies in a domain: k_m = 0 / u unchanged
 #pragma unroll
@@ -530,7 +535,7 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
         const double* cur = base + slot_c * SWP;
         const double* up = base + slot_u * SWP;
         const double* dn = base + slot_d * SWP;
-        if (cls == 1 && (sp.fast2d || !sp.has_diff)) {
+        if (cls == 1 && (sp.fastpath || !sp.has_diff)) {
           // every cell is an interior cell: straight-line 5-point stencil, additions in the reference's
           // order Xp, Xm, Yp, Ym
           const double dcx = sp.dconst[0], dcy = sp.dconst[1];
@@ -561,6 +566,22 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
               a1 = dadd(a1, dmul(dcx, dsub(wc.x, wc.y)));
               a1 = dadd(a1, dmul(dcy, dsub(wu.y, wc.y)));
               a1 = dadd(a1, dmul(dcy, dsub(wd.y, wc.y)));
+              if (D3) {  // Zp, Zm
+                const double dcz = sp.dconst[2];
+                const int64_t i = idx0 + p * 64;
+                double2 wzp = *reinterpret_cast<const double2*>(sp.u + i + A.PL);
+                double2 wzm = *reinterpret_cast<const double2*>(sp.u + i - A.PL);
+                if (MODE != MODE_FIRST) {
+                  const double2 kzp = *reinterpret_cast<const double2*>(sp.kprev + i + A.PL);
+                  const double2 kzm = *reinterpret_cast<const double2*>(sp.kprev + i - A.PL);
+                  wzp.x = dadd(wzp.x, dmul(A.cdt, kzp.x)); wzp.y = dadd(wzp.y, dmul(A.cdt, kzp.y));
+                  wzm.x = dadd(wzm.x, dmul(A.cdt, kzm.x)); wzm.y = dadd(wzm.y, dmul(A.cdt, kzm.y));
+                }
+                a0 = dadd(a0, dmul(dcz, dsub(wzp.x, wc.x)));
+                a0 = dadd(a0, dmul(dcz, dsub(wzm.x, wc.x)));
+                a1 = dadd(a1, dmul(dcz, dsub(wzp.y, wc.y)));
+                a1 = dadd(a1, dmul(dcz, dsub(wzm.y, wc.y)));
+              }
             }
             if (MODE != MODE_FINAL) {
               *reinterpret_cast<double2*>(sp.kout + idx0 + p * 64) = make_double2(a0, a1);
@@ -623,6 +644,32 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
                 if (!(f1 & SB2_F_YM)) a1 = dadd(a1, term(d1, wd.y, wc.y));
               }
             }
+            if (D3 && sp.dkind[2] != SB2_SRC_NONE && active[p]) {  // axis 2: z
+              double d0, d1;
+              if (sp.dkind[2] == SB2_SRC_CONST) { d0 = d1 = sp.dconst[2]; }
+              else { const double2 dv = *reinterpret_cast<const double2*>(A.fields[sp.dsrc[2]] + idx); d0 = dv.x; d1 = dv.y; }
+              double2 wzp = *reinterpret_cast<const double2*>(sp.u + idx + A.PL);
+              double2 wzm = *reinterpret_cast<const double2*>(sp.u + idx - A.PL);
+              if (MODE != MODE_FIRST) {
+                const double2 kzp = *reinterpret_cast<const double2*>(sp.kprev + idx + A.PL);
+                const double2 kzm = *reinterpret_cast<const double2*>(sp.kprev + idx - A.PL);
+                wzp.x = dadd(wzp.x, dmul(A.cdt, kzp.x)); wzp.y = dadd(wzp.y, dmul(A.cdt, kzp.y));
+                wzm.x = dadd(wzm.x, dmul(A.cdt, kzm.x)); wzm.y = dadd(wzm.y, dmul(A.cdt, kzm.y));
+              }
+              auto term = [&](double dc, double wn, double w0) {
+                double t = dmul(dc, dsub(wn, w0));
+                if (A.divide[2]) t = ddiv_pos(t, A.dx2[2]);
+                return t;
+              };
+              if (f0 & SB2_F_DOMAIN) {
+                if (!(f0 & SB2_F_ZP)) a0 = dadd(a0, term(d0, wzp.x, wc.x));
+                if (!(f0 & SB2_F_ZM)) a0 = dadd(a0, term(d0, wzm.x, wc.x));
+              }
+              if (f1 & SB2_F_DOMAIN) {
+                if (!(f1 & SB2_F_ZP)) a1 = dadd(a1, term(d1, wzp.y, wc.y));
+                if (!(f1 & SB2_F_ZM)) a1 = dadd(a1, term(d1, wzm.y, wc.y));
+              }
+            }
           }
           if (active[p]) {
             const bool in0 = f0 & SB2_F_DOMAIN, in1 = f1 & SB2_F_DOMAIN;
@@ -651,7 +698,7 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
   }
 }
 
-template <int NS, int NP, int W, int MODE, int DEPTH, int MINB>
+template <int NS, int NP, int W, int MODE, int DEPTH, int MINB, bool D3>
 cudaError_t launch_variant(const Sb2StageArgs& a, cudaStream_t stream) {
   using G = Geo<NP, W>;
   const int narr = (MODE == MODE_FIRST) ? 1 : 2;
@@ -659,24 +706,35 @@ cudaError_t launch_variant(const Sb2StageArgs& a, cudaStream_t stream) {
                                                                   (MODE == MODE_FINAL ? (size_t)W * a.S * 2 * G::SW : 0));
   static size_t configured = 0;
   if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(rd_stage_kernel<NS, NP, W, MODE, DEPTH, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(rd_stage_kernel<NS, NP, W, MODE, DEPTH, MINB, D3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = smem;
   }
   dim3 grid;
   grid.x = (a.nx + G::SW - 1) / G::SW;
-  grid.y = (a.row_end - a.row_begin + a.rows_per_block - 1) / a.rows_per_block;
-  grid.z = 1;
-  if (grid.y == 0) return cudaSuccess;
-  rd_stage_kernel<NS, NP, W, MODE, DEPTH, MINB><<<grid, W * 32, smem, stream>>>(a);
+  if (D3) {
+    grid.y = (a.ny + a.rows_per_block - 1) / a.rows_per_block;
+    grid.z = a.row_end - a.row_begin;
+  } else {
+    grid.y = (a.row_end - a.row_begin + a.rows_per_block - 1) / a.rows_per_block;
+    grid.z = 1;
+  }
+  if (grid.y == 0 || grid.z == 0) return cudaSuccess;
+  rd_stage_kernel<NS, NP, W, MODE, DEPTH, MINB, D3><<<grid, W * 32, smem, stream>>>(a);
   return cudaGetLastError();
+}
+
+template <int NS, int NP, int W, int DEPTH, int MINB, bool D3>
+cudaError_t launch_dim(const Sb2StageArgs& a, cudaStream_t stream) {
+  if (a.m == 0) return launch_variant<NS, NP, W, MODE_FIRST, DEPTH, MINB, D3>(a, stream);
+  if (a.final) return launch_variant<NS, NP, W, MODE_FINAL, DEPTH, MINB, D3>(a, stream);
+  return launch_variant<NS, NP, W, MODE_MIDDLE, DEPTH, MINB, D3>(a, stream);
 }
 
 template <int NS, int NP, int W, int DEPTH, int MINB>
 cudaError_t launch_mode(const Sb2StageArgs& a, cudaStream_t stream) {
-  if (a.m == 0) return launch_variant<NS, NP, W, MODE_FIRST, DEPTH, MINB>(a, stream);
-  if (a.final) return launch_variant<NS, NP, W, MODE_FINAL, DEPTH, MINB>(a, stream);
-  return launch_variant<NS, NP, W, MODE_MIDDLE, DEPTH, MINB>(a, stream);
+  if (a.dim == 3) return launch_dim<NS, NP, W, DEPTH, MINB, true>(a, stream);
+  return launch_dim<NS, NP, W, DEPTH, MINB, false>(a, stream);
 }
 
 }  // namespace rd

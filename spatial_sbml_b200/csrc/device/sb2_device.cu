@@ -384,10 +384,11 @@ void fill_stage_args(sb2_sim* sim, Sb2StageArgs& a, int m, double dt, int row_be
     // 3.53, 3.43, 3.33, 3.33, 3.40, 3.75, 4.31: short tiles keep the rows in flight close together in memory and the
     // waves even, the prologue batch they pay for is cheap
     const int W = sim->rd.w;
-    const int rows = row_end - row_begin;
+    const int rows = sim->g.dim == 3 ? sim->g.ny : row_end - row_begin;
+    const int planes = sim->g.dim == 3 ? row_end - row_begin : 1;
     static const int rpb_batches = getenv("SB2_RD_BATCHES") ? atoi(getenv("SB2_RD_BATCHES")) : 8;
     int rpb = rpb_batches * W;
-    while (rpb > W && (int64_t)sim->nstrips * ((rows + rpb - 1) / rpb) < 148 * 6) rpb -= W;
+    while (rpb > W && (int64_t)sim->nstrips * planes * ((rows + rpb - 1) / rpb) < 148 * 6) rpb -= W;
     a.rows_per_block = rpb;
     a.np = sim->rd.np;
     return;
@@ -631,6 +632,9 @@ int sb2_finalize(sb2_sim* sim) {
     b.sp[s].has_diff = sp.has_diff ? 1 : 0;
     b.sp[s].fast2d = (sp.has_diff && sim->g.dim == 2 && sp.dkind[0] == SB2_SRC_CONST && sp.dkind[1] == SB2_SRC_CONST &&
                       !b.divide[0] && !b.divide[1]) ? 1 : 0;
+    b.sp[s].fastpath = sp.has_diff ? 1 : 0;
+    for (int a = 0; a < sim->g.dim; ++a)
+      if (sp.dkind[a] != SB2_SRC_CONST || b.divide[a]) b.sp[s].fastpath = 0;
     for (int a = 0; a < 3; ++a) {
       b.sp[s].dkind[a] = sp.dkind[a]; b.sp[s].dsrc[a] = sp.dsrc[a];
       if (sp.dkind[a] == SB2_SRC_FIELD && (sp.dsrc[a] < 0 || sp.dsrc[a] >= (int)sim->d_fields.size()))
@@ -668,10 +672,11 @@ int sb2_finalize(sb2_sim* sim) {
     const int sw = 64 * sim->rd.np;
     if (sw + 4 > SB2_TAIL_PAD) return fail(sim, SB2_ERR_STATE, "strip wider than the tail pad of the field layout");
     sim->nstrips = (sim->g.nx + sw - 1) / sw;
-    CK(cudaMalloc((void**)&sim->d_cls, (size_t)sim->nstrips * sim->g.ny));
+    const int nrows = sim->g.ny * sim->g.nz;  // every row of every held plane
+    CK(cudaMalloc((void**)&sim->d_cls, (size_t)sim->nstrips * nrows));
     const uint8_t* fl[SB2_MAX_GEOS] = {0, 0, 0, 0};
     for (int g = 0; g < b.G; ++g) fl[g] = sim->d_flags[g];
-    cudaError_t ce = sb2_rd_classify(fl, b.G, sim->g.nx, sim->g.ny, sim->P, sim->first, sw, sim->d_cls, sim->nstrips, sim->stream);
+    cudaError_t ce = sb2_rd_classify(fl, b.G, sim->g.nx, sim->g.ny, sim->g.nz, sim->P, sim->PL, sim->first, sw, sim->d_cls, sim->nstrips, sim->stream);
     if (ce != cudaSuccess) return cuda_fail(sim, ce, "strip classification kernel");
     b.cls = sim->d_cls;
     b.nstrips = sim->nstrips;

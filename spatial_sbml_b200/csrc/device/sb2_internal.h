@@ -63,7 +63,8 @@ struct Sb2SpeciesArgs {
   const double* k1;
   int32_t geo;
   int32_t has_diff;
-  int32_t fast2d;    // 2-D, uniform coefficients on both axes, dx^2 == dy^2 == 1: straight-line interior stencil
+  int32_t fast2d;    // gen1 kernel: 2-D, uniform coefficients on both axes, dx^2 == dy^2 == 1: straight-line interior stencil
+  int32_t fastpath;  // rd_stage: uniform coefficients on every axis of the grid and no division by delta^2
   int32_t dkind[3];  // SB2_SRC_*
   int32_t dsrc[3];
   double dconst[3];  // value of a uniform coefficient at launch time
@@ -107,9 +108,9 @@ struct Sb2RdVariant { int id, ns, np, w, depth; };
 // picks the variant for a 2-D model (returns id or -1 when only the first-generation kernel applies)
 int sb2_rd_pick_variant(int dim, int nx, int nspecies, int depth, Sb2RdVariant* out);
 cudaError_t sb2_rd_launch(const Sb2StageArgs& a, cudaStream_t stream);
-// class map: cls[row * nstrips + strip] for strips of sw cells, rows = every held row (2-D: ny)
-cudaError_t sb2_rd_classify(const uint8_t* const* flags, int G, int nx, int nrows, int64_t P, int64_t first, int sw,
-                            uint8_t* cls, int nstrips, cudaStream_t stream);
+// class map: cls[(z * ny + y) * nstrips + strip] for strips of sw cells, every held row of every held plane
+cudaError_t sb2_rd_classify(const uint8_t* const* flags, int G, int nx, int ny, int nz, int64_t P, int64_t PL, int64_t first,
+                            int sw, uint8_t* cls, int nstrips, cudaStream_t stream);
 
 struct Sb2CombineArgs {
   int32_t nx, ny, nz, dim, S;
