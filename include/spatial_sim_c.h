@@ -71,6 +71,8 @@ SSB_API long ssb_get_num_domain_cells(ssb_sim* s);
 SSB_API int ssb_get_num_staged_species(ssb_sim* s);
 SSB_API long ssb_get_device_launch_count(ssb_sim* s);
 SSB_API void* ssb_get_device_handle(ssb_sim* s);                  /* sb2_sim* of include/spatial_b200.h */
+/* after stepping the device handle directly (split-phase API of the slab-sharded path): host mirrors are out of date */
+SSB_API void ssb_device_state_changed(ssb_sim* s);
 /* text is copied into buf (NUL terminated, truncated to buflen); returns the full length */
 SSB_API int ssb_get_device_program_text(ssb_sim* s, char* buf, int buflen);
 SSB_API int ssb_get_setup_text(ssb_sim* s, const char* what, char* buf, int buflen);

@@ -126,6 +126,7 @@ def _proto(lib):
         "ssb_get_num_staged_species": (ci, [vp]),
         "ssb_get_device_launch_count": (C.c_long, [vp]),
         "ssb_get_device_handle": (vp, [vp]),
+        "ssb_device_state_changed": (None, [vp]),
         "ssb_get_device_program_text": (ci, [vp, C.c_char_p, ci]),
         "ssb_get_setup_text": (ci, [vp, cs, C.c_char_p, ci]),
     }
@@ -311,6 +312,9 @@ class SpatialSimulator(object):
 
     def getDeviceHandle(self):
         return self._lib.ssb_get_device_handle(self._h)
+
+    def deviceStateChanged(self):
+        self._lib.ssb_device_state_changed(self._h)
 
     def setCudaStream(self, stream):
         self._stream = stream

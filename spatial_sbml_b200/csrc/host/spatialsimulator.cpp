@@ -635,6 +635,11 @@ void SpatialSimulator::runSteps(double firstStepIndex, double step, int nsteps) 
   for (size_t s = 0; s < impl->stale.size(); ++s) impl->stale[s] = 1;
 }
 
+void SpatialSimulator::deviceStateChanged() {
+  if (!impl) return;
+  for (size_t s = 0; s < impl->stale.size(); ++s) impl->stale[s] = 1;
+}
+
 // spatialsimulator.cpp:1667-1703 without the gnuplot pipe
 void SpatialSimulator::run(double endTime, double step) {
   const int last = static_cast<int>(endTime / step);

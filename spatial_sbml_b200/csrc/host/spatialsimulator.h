@@ -90,6 +90,9 @@ class __attribute__((visibility("default"))) SpatialSimulator {
   long getNumDomainCells() const;  // volume cells that carry at least one staged species
   int getNumStagedSpecies() const;
   long getDeviceLaunchCount() const;
+  // the caller stepped the device simulator itself (split-phase sb2_begin_step / sb2_stage / sb2_end_step of the
+  // slab-sharded path): the host mirrors of the species fields are out of date
+  void deviceStateChanged();
   void setCudaStream(void* stream);
   void setDevice(int ordinal);  // before init
   // Slab of a larger grid (multi-GPU): this simulator owns rows [lo, hi) of the slab

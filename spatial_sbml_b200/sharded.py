@@ -132,6 +132,7 @@ class ShardedSimulator(object):
                 pending = self._exchange([self._u(s, current=False) for s in range(self.S)], ev)
             self._ck(lib.sb2_stage(h, m, 2))      # ... then the interior while they travel
         self._ck(lib.sb2_end_step(h))
+        self.sim.deviceStateChanged()  # the host mirrors of the species are stale now
         if fused:
             self.cur ^= 1
         else:

@@ -1,0 +1,51 @@
+"""Run under torchrun (one rank per GPU): the slab-sharded step must be BIT-IDENTICAL to the single-GPU step
+(no reduction inside the step).  usage: torchrun --nproc-per-node N tools/sharded_check.py [2|3] [steps]"""
+import os
+import sys
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from spatial_sbml_b200 import synthetic
+from spatial_sbml_b200.sharded import ShardedSimulator
+import spatial_sbml_b200 as sb
+
+dim = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 12
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+if dim == 2:
+    dims = (700, 96 * world + 5, 1)
+    model, dt = synthetic.turing(dims[0], dims[1]), 0.07
+else:
+    dims = (200, 40, 6 * world + 3)
+    model, dt = synthetic.turing(*dims), 0.02
+shard = ShardedSimulator(model, dims[0], dims[1], dims[2], dim=dim, device=local)
+shard.run_steps(0, dt, steps)
+torch.cuda.synchronize()
+ok = True
+ref = sb.SpatialSimulator(device=local)
+ref.initFromString(model, *dims)
+ref.runSteps(0, dt, steps)
+for name in ("species_1", "species_2"):
+    whole = ref.getVariableCompact(name)
+    mine = shard.owned(name)
+    want = whole[shard.lo:shard.hi] if dim == 3 else whole[:, shard.lo:shard.hi]
+    same = np.array_equal(mine, want)
+    if not same:
+        bad = np.argwhere(mine != want)
+        rows = sorted(set(int(b[0 if dim == 3 else 1]) for b in bad))
+        print("rank %d %s differs: max abs %.3e, %d cells, local owned rows %s ... %s (owned %d rows), x range %d..%d" % (
+            rank, name, np.abs(mine - want).max(), len(bad), rows[:6], rows[-3:], mine.shape[0 if dim == 3 else 1],
+            bad[:, 2].min(), bad[:, 2].max()), flush=True)
+    ok = ok and same
+t = torch.tensor([1 if ok else 0], device="cuda")
+dist.all_reduce(t, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("sharded_check dim %d world %d steps %d rows [%d,%d): %s" % (dim, world, steps, shard.lo, shard.hi, "BIT-IDENTICAL" if int(t[0]) else "MISMATCH"), flush=True)
+dist.destroy_process_group()
+sys.exit(0 if int(t[0]) else 1)
