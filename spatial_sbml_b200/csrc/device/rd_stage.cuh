@@ -222,13 +222,16 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
   auto issue_row = [&](int r) {
     mbar_expect_tx(mybar, row_bytes * NARR * S);
     const int64_t g = plane0 + (int64_t)r * A.P + x0 - 2;
-    for (int s = 0; s < S; ++s) {
-      if (MODE == MODE_FINAL) {
-        bulk_g2s_hint(myraw_s + (s * NARR) * row_bytes, A.sp[s].u + g, row_bytes, mybar, keep);
-        bulk_g2s_hint(myraw_s + (s * NARR + 1) * row_bytes, A.sp[s].kprev + g, row_bytes, mybar, keep);
-      } else {
-        bulk_g2s(myraw_s + (s * NARR) * row_bytes, A.sp[s].u + g, row_bytes, mybar);
-        if (MODE != MODE_FIRST) bulk_g2s(myraw_s + (s * NARR + 1) * row_bytes, A.sp[s].kprev + g, row_bytes, mybar);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {  // compile-time s: the array pointers come from fixed parameter offsets
+      if (s < S) {
+        if (MODE == MODE_FINAL) {
+          bulk_g2s_hint(myraw_s + (s * NARR) * row_bytes, A.sp[s].u + g, row_bytes, mybar, keep);
+          bulk_g2s_hint(myraw_s + (s * NARR + 1) * row_bytes, A.sp[s].kprev + g, row_bytes, mybar, keep);
+        } else {
+          bulk_g2s(myraw_s + (s * NARR) * row_bytes, A.sp[s].u + g, row_bytes, mybar);
+          if (MODE != MODE_FIRST) bulk_g2s(myraw_s + (s * NARR + 1) * row_bytes, A.sp[s].kprev + g, row_bytes, mybar);
+        }
       }
     }
   };
@@ -236,9 +239,12 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
   auto issue_combine = [&](int r) {
     mbar_expect_tx(mycbar, SW * sizeof(double) * 2 * S);
     const int64_t g = plane0 + (int64_t)r * A.P + x0;
-    for (int s = 0; s < S; ++s) {
-      bulk_g2s(mycs_s + (s * 2) * SW * sizeof(double), A.sp[s].k0 + g, SW * sizeof(double), mycbar);
-      bulk_g2s(mycs_s + (s * 2 + 1) * SW * sizeof(double), A.sp[s].k1 + g, SW * sizeof(double), mycbar);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      if (s < S) {
+        bulk_g2s(mycs_s + (s * 2) * SW * sizeof(double), A.sp[s].k0 + g, SW * sizeof(double), mycbar);
+        bulk_g2s(mycs_s + (s * 2 + 1) * SW * sizeof(double), A.sp[s].k1 + g, SW * sizeof(double), mycbar);
+      }
     }
   };
   uint32_t cparity = 0;
