@@ -207,7 +207,33 @@ static int doTime(int argc, char** argv) {
   return 0;
 }
 
+// ref_driver stab <model.xml> <xdim> <ydim> <zdim> <dt>...
+// The reference's stability reductions (checkStability.cpp:10-52, 119-154) are not wired into its public API; the
+// oracle calls them directly for every species that diffuses / is advected and prints the smallest admissible step.
+double checkDiffusionStab(variableInfo* sInfo, double deltaX, double deltaY, double deltaZ, int Xindex, int Yindex, double dt);
+double checkAdvectionStab(variableInfo* sInfo, double deltaX, double deltaY, double deltaZ, double dt, int Xindex, int Yindex, int dimension);
+static int doStab(int argc, char** argv) {
+  if (argc < 7) return 2;
+  SpatialSimulator sim;
+  sim.initFromFile(argv[2], atoi(argv[3]), atoi(argv[4]), atoi(argv[5]));
+  printf("{");
+  for (int a = 6; a < argc; ++a) {
+    const double dt = atof(argv[a]);
+    double best = dt;
+    for (size_t k = 0; k < sim.varInfoList.size(); ++k) {
+      variableInfo* v = sim.varInfoList[k];
+      if (!v->sp || v->isUniform || !v->geoi) continue;
+      if (v->diffCInfo) best = std::min(best, checkDiffusionStab(v, sim.deltaX, sim.deltaY, sim.deltaZ, sim.Xindex, sim.Yindex, dt));
+      if (v->adCInfo) best = std::min(best, checkAdvectionStab(v, sim.deltaX, sim.deltaY, sim.deltaZ, dt, sim.Xindex, sim.Yindex, (int)sim.dimension));
+    }
+    printf("%s\"%s\": %.17g", a > 6 ? ", " : "", argv[a], best);
+  }
+  printf("}\n");
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc >= 2 && std::string(argv[1]) == "stab") return doStab(argc, argv);
   if (argc >= 2 && std::string(argv[1]) == "dump") return doDump(argc, argv);
   if (argc >= 2 && std::string(argv[1]) == "time") return doTime(argc, argv);
   fprintf(stderr, "usage: ref_driver dump|time ... (see header comment)\n");

@@ -68,3 +68,122 @@ def test_fields_match_reference(case):
     print(case, {k: "%.1e" % v for k, v in worst.items()})
     assert sim.getDeviceLaunchCount() > 0
     sim.close()
+
+
+def test_stable_time_step_matches_reference():
+    """checkDiffusionStab / checkAdvectionStab (reference checkStability.cpp:10-52, 119-154) as a device min-reduction:
+    the largest admissible step must equal what the reference's own functions return (tests/golden/stability.json,
+    written by tests/golden/make_stability.py), bit for bit, for every golden model and four step sizes."""
+    import json
+    import os
+    import spatial_sbml_b200 as sb
+    from conftest import GOLDEN
+    want = json.load(open(os.path.join(GOLDEN, "stability.json")))
+    assert len(want) >= 18
+    bad = []
+    for case in sorted(want):
+        g = load_golden(case)
+        nx, ny, nz = [int(v) for v in g["dims"]]
+        sim = sb.SpatialSimulator()
+        sim.initFromFile(model_path(case), nx, ny, nz)
+        for dt_text, ref in want[case].items():
+            got = sim.getStableTimeStep(float(dt_text))
+            if got != ref:
+                bad.append((case, dt_text, got, ref))
+        sim.close()
+    assert not bad, bad
+
+
+def test_set_parameter_takes_effect_at_the_next_step():
+    """setParameter (reference spatialsimulator.cpp:167-202): kinetic constants are aliased by the token streams, so a
+    changed value must steer the very next oneStep; changing it back must reproduce the golden trajectory exactly."""
+    import spatial_sbml_b200 as sb
+    g = load_golden("turing_tiny")
+    dt = float(g["dt"])
+    a = sb.SpatialSimulator()
+    a.initFromFile(model_path("turing_tiny"), 22, 22, 1)
+    a.setParameter("k1", 2.0)
+    a.setParameter("k1", 1.0)          # back to the model's value before the first step
+    a.oneStep(0, dt)
+    assert np.array_equal(a.getVariableCompact("species_1"), g["step/1/species_1"])
+    b = sb.SpatialSimulator()
+    b.initFromFile(model_path("turing_tiny"), 22, 22, 1)
+    b.setParameter("k1", 2.0)
+    b.setParameter("species_1_diff", 1.0)
+    b.oneStep(0, dt)
+    assert not np.array_equal(b.getVariableCompact("species_1"), g["step/1/species_1"])
+    a.close()
+    b.close()
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
+def test_every_stage_kernel_variant_matches_reference(variant, monkeypatch):
+    """Each rd_stage variant (cells per thread, warps per CTA, stack depth, species capacity) on a masked multi-compartment
+    model and on the Turing model; SB2_RD_VARIANT is read when the device program is finalized."""
+    import spatial_sbml_b200 as sb
+    monkeypatch.setenv("SB2_RD_VARIANT", str(variant))
+    for case, steps in (("turing_blob", 10), ("brusselator_300", 1), ("syn_turing_3d", 10)):
+        g = load_golden(case)
+        nx, ny, nz = [int(v) for v in g["dims"]]
+        sim = sb.SpatialSimulator()
+        sim.initFromFile(model_path(case), nx, ny, nz)
+        sim.runSteps(0, float(g["dt"]), steps)
+        for sp in [str(s) for s in g["species"]]:
+            assert rel_linf(sim.getVariableCompact(sp), g["step/%d/%s" % (steps, sp)]) <= 1e-10, (variant, case, sp)
+        sim.close()
+
+
+def test_first_generation_kernel_matches_reference(monkeypatch):
+    import spatial_sbml_b200 as sb
+    monkeypatch.setenv("SB2_STAGE_KERNEL", "gen1")
+    for case, steps in (("turing_blob", 10), ("fish", 10), ("syn_brusselator_3d", 20)):
+        g = load_golden(case)
+        nx, ny, nz = [int(v) for v in g["dims"]]
+        sim = sb.SpatialSimulator()
+        sim.initFromFile(model_path(case), nx, ny, nz)
+        sim.runSteps(0, float(g["dt"]), steps)
+        for sp in [str(s) for s in g["species"]]:
+            assert rel_linf(sim.getVariableCompact(sp), g["step/%d/%s" % (steps, sp)]) <= 1e-10, (case, sp)
+        sim.close()
+
+
+def test_large_grid_against_the_restated_oracle():
+    """At a size the golden files do not cover (1024 x 768, blob initial condition, 3 steps) the device result must equal
+    the numpy restatement of the reference's step (oracle/rd_oracle.py, itself pinned to the goldens) bit for bit."""
+    import os
+    import sys
+    import spatial_sbml_b200 as sb
+    from spatial_sbml_b200 import synthetic
+    from conftest import REPO
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import rd_oracle
+    dims = (1024, 768, 1)
+    model = synthetic.turing(dims[0], dims[1])
+    host = sb.SpatialSimulator(host_only=True)
+    host.initFromString(model, *dims)
+    orc = rd_oracle.from_simulator(host, model, dims)
+    host.close()
+    sim = sb.SpatialSimulator()
+    sim.initFromString(model, *dims)
+    for t in range(3):
+        orc.one_step(t, 0.07)
+        sim.oneStep(t, 0.07)
+    for sp in ("species_1", "species_2"):
+        assert np.array_equal(sim.getVariableCompact(sp), orc.sp[sp].u), sp
+    sim.close()
+
+
+def test_uniform_state_is_preserved_at_full_size():
+    """Size-independent property at a BASELINE-scale grid (4096 x 4096): a spatially uniform Brusselator state stays
+    uniform bit for bit (every stencil term is exactly zero, every cell sees the same reaction arithmetic), whatever
+    strip, tile or warp a cell falls into."""
+    import spatial_sbml_b200 as sb
+    from spatial_sbml_b200 import synthetic
+    n = 4096
+    sim = sb.SpatialSimulator()
+    sim.initFromString(synthetic.brusselator(n, n), n, n, 1)
+    sim.runSteps(0, 0.1, 5)
+    for sp in ("X", "Y"):
+        a = sim.getVariableCompact(sp)[0, 1:-1, 1:-1]
+        assert np.all(a == a[0, 0]), sp
+    sim.close()
