@@ -602,79 +602,60 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
           }
           continue;
         }
-        // general path: per-cell domain / boundary flags, field-valued coefficients, dx^2 != 1
+        // general path: per-cell domain / boundary flags, field-valued coefficients, dx^2 != 1.  Every stencil term
+        // is computed unconditionally (neighbour values outside the domain are finite) and added under a predicate,
+        // so the only branches are the warp-uniform ones on the coefficient kind and on dx^2 == 1.
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
           const int64_t idx = idx0 + p * 64;
           const uint32_t f0 = (fl[2 * p] >> (8 * sp.geo)) & 0xffu;
           const uint32_t f1 = (fl[2 * p + 1] >> (8 * sp.geo)) & 0xffu;
           double a0 = acc[s][2 * p], a1 = acc[s][2 * p + 1];
-          if (sp.has_diff && ((f0 | f1) & SB2_F_DOMAIN)) {
+          if (sp.has_diff) {
             const double2 wc = *reinterpret_cast<const double2*>(cur + p * 64);
-            if (sp.dkind[0] != SB2_SRC_NONE) {  // axis 0: x
+            // one axis: the plus / minus neighbours of both cells, the flag bits that switch each term off
+            auto axis = [&](int ax, double n0p, double n0m, double n1p, double n1m, uint32_t bitp, uint32_t bitm) {
+              if (sp.dkind[ax] == SB2_SRC_NONE) return;
               double d0, d1;
-              if (sp.dkind[0] == SB2_SRC_CONST) { d0 = d1 = sp.dconst[0]; }
-              else { const double2 dv = *reinterpret_cast<const double2*>(A.fields[sp.dsrc[0]] + idx); d0 = dv.x; d1 = dv.y; }
+              if (sp.dkind[ax] == SB2_SRC_CONST) { d0 = d1 = sp.dconst[ax]; }
+              else {
+                double2 dv = make_double2(0.0, 0.0);
+                if (active[p]) dv = *reinterpret_cast<const double2*>(A.fields[sp.dsrc[ax]] + idx);
+                d0 = dv.x; d1 = dv.y;
+              }
+              double t0p = dmul(d0, dsub(n0p, wc.x)), t0m = dmul(d0, dsub(n0m, wc.x));
+              double t1p = dmul(d1, dsub(n1p, wc.y)), t1m = dmul(d1, dsub(n1m, wc.y));
+              if (A.divide[ax]) {
+                t0p = ddiv_pos(t0p, A.dx2[ax]); t0m = ddiv_pos(t0m, A.dx2[ax]);
+                t1p = ddiv_pos(t1p, A.dx2[ax]); t1m = ddiv_pos(t1m, A.dx2[ax]);
+              }
+              if ((f0 & (SB2_F_DOMAIN | bitp)) == SB2_F_DOMAIN) a0 = dadd(a0, t0p);
+              if ((f0 & (SB2_F_DOMAIN | bitm)) == SB2_F_DOMAIN) a0 = dadd(a0, t0m);
+              if ((f1 & (SB2_F_DOMAIN | bitp)) == SB2_F_DOMAIN) a1 = dadd(a1, t1p);
+              if ((f1 & (SB2_F_DOMAIN | bitm)) == SB2_F_DOMAIN) a1 = dadd(a1, t1m);
+            };
+            {
               const double wl = cur[p * 64 - 1], wr = cur[p * 64 + 2];
-              auto term = [&](double dc, double wn, double w0) {
-                double t = dmul(dc, dsub(wn, w0));
-                if (A.divide[0]) t = ddiv_pos(t, A.dx2[0]);
-                return t;
-              };
-              if (f0 & SB2_F_DOMAIN) {
-                if (!(f0 & SB2_F_XP)) a0 = dadd(a0, term(d0, wc.y, wc.x));
-                if (!(f0 & SB2_F_XM)) a0 = dadd(a0, term(d0, wl, wc.x));
-              }
-              if (f1 & SB2_F_DOMAIN) {
-                if (!(f1 & SB2_F_XP)) a1 = dadd(a1, term(d1, wr, wc.y));
-                if (!(f1 & SB2_F_XM)) a1 = dadd(a1, term(d1, wc.x, wc.y));
-              }
+              axis(0, wc.y, wl, wr, wc.x, SB2_F_XP, SB2_F_XM);
             }
-            if (sp.dkind[1] != SB2_SRC_NONE) {  // axis 1: y
-              double d0, d1;
-              if (sp.dkind[1] == SB2_SRC_CONST) { d0 = d1 = sp.dconst[1]; }
-              else { const double2 dv = *reinterpret_cast<const double2*>(A.fields[sp.dsrc[1]] + idx); d0 = dv.x; d1 = dv.y; }
+            {
               const double2 wu = *reinterpret_cast<const double2*>(up + p * 64);
               const double2 wd = *reinterpret_cast<const double2*>(dn + p * 64);
-              auto term = [&](double dc, double wn, double w0) {
-                double t = dmul(dc, dsub(wn, w0));
-                if (A.divide[1]) t = ddiv_pos(t, A.dx2[1]);
-                return t;
-              };
-              if (f0 & SB2_F_DOMAIN) {
-                if (!(f0 & SB2_F_YP)) a0 = dadd(a0, term(d0, wu.x, wc.x));
-                if (!(f0 & SB2_F_YM)) a0 = dadd(a0, term(d0, wd.x, wc.x));
-              }
-              if (f1 & SB2_F_DOMAIN) {
-                if (!(f1 & SB2_F_YP)) a1 = dadd(a1, term(d1, wu.y, wc.y));
-                if (!(f1 & SB2_F_YM)) a1 = dadd(a1, term(d1, wd.y, wc.y));
-              }
+              axis(1, wu.x, wd.x, wu.y, wd.y, SB2_F_YP, SB2_F_YM);
             }
-            if (D3 && sp.dkind[2] != SB2_SRC_NONE && active[p]) {  // axis 2: z
-              double d0, d1;
-              if (sp.dkind[2] == SB2_SRC_CONST) { d0 = d1 = sp.dconst[2]; }
-              else { const double2 dv = *reinterpret_cast<const double2*>(A.fields[sp.dsrc[2]] + idx); d0 = dv.x; d1 = dv.y; }
-              double2 wzp = *reinterpret_cast<const double2*>(sp.u + idx + A.PL);
-              double2 wzm = *reinterpret_cast<const double2*>(sp.u + idx - A.PL);
-              if (MODE != MODE_FIRST) {
-                const double2 kzp = *reinterpret_cast<const double2*>(sp.kprev + idx + A.PL);
-                const double2 kzm = *reinterpret_cast<const double2*>(sp.kprev + idx - A.PL);
-                wzp.x = dadd(wzp.x, dmul(A.cdt, kzp.x)); wzp.y = dadd(wzp.y, dmul(A.cdt, kzp.y));
-                wzm.x = dadd(wzm.x, dmul(A.cdt, kzm.x)); wzm.y = dadd(wzm.y, dmul(A.cdt, kzm.y));
+            if (D3) {
+              double2 wzp = make_double2(0.0, 0.0), wzm = wzp;
+              if (active[p] && sp.dkind[2] != SB2_SRC_NONE) {
+                wzp = *reinterpret_cast<const double2*>(sp.u + idx + A.PL);
+                wzm = *reinterpret_cast<const double2*>(sp.u + idx - A.PL);
+                if (MODE != MODE_FIRST) {
+                  const double2 kzp = *reinterpret_cast<const double2*>(sp.kprev + idx + A.PL);
+                  const double2 kzm = *reinterpret_cast<const double2*>(sp.kprev + idx - A.PL);
+                  wzp.x = dadd(wzp.x, dmul(A.cdt, kzp.x)); wzp.y = dadd(wzp.y, dmul(A.cdt, kzp.y));
+                  wzm.x = dadd(wzm.x, dmul(A.cdt, kzm.x)); wzm.y = dadd(wzm.y, dmul(A.cdt, kzm.y));
+                }
               }
-              auto term = [&](double dc, double wn, double w0) {
-                double t = dmul(dc, dsub(wn, w0));
-                if (A.divide[2]) t = ddiv_pos(t, A.dx2[2]);
-                return t;
-              };
-              if (f0 & SB2_F_DOMAIN) {
-                if (!(f0 & SB2_F_ZP)) a0 = dadd(a0, term(d0, wzp.x, wc.x));
-                if (!(f0 & SB2_F_ZM)) a0 = dadd(a0, term(d0, wzm.x, wc.x));
-              }
-              if (f1 & SB2_F_DOMAIN) {
-                if (!(f1 & SB2_F_ZP)) a1 = dadd(a1, term(d1, wzp.y, wc.y));
-                if (!(f1 & SB2_F_ZM)) a1 = dadd(a1, term(d1, wzm.y, wc.y));
-              }
+              axis(2, wzp.x, wzm.x, wzp.y, wzm.y, SB2_F_ZP, SB2_F_ZM);
             }
           }
           if (active[p]) {
