@@ -294,7 +294,8 @@ def main():
     traffic = ncu_traffic()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
-                "kernel": "stage_kernel<2> (fused RK stage: bytecode reactions + diffusion stencil, RK combine in stage 4)",
+                "kernel": "rd_stage_kernel (fused RK stage: TMA-staged rows, bytecode reactions + diffusion stencil, RK combine in stage 4); "
+                          "4 launches per step, figures are the average over the four",
                 "algorithmic_bytes_per_launch": cells * BYTES_PER_CELL_UPDATE / 4.0,
                 "avg_launch_ms": ms / (4.0 * K), "peak_source": peak_src, "rank": 0}
 
