@@ -187,3 +187,21 @@ def test_uniform_state_is_preserved_at_full_size():
         a = sim.getVariableCompact(sp)[0, 1:-1, 1:-1]
         assert np.all(a == a[0, 0]), sp
     sim.close()
+
+
+def test_cli_driver_writes_the_reference_trajectory(tmp_path):
+    """python -m spatial_sbml_b200.cli (the role of SpatialCL/main.cpp): run()'s step loop and the volume CSV columns."""
+    import subprocess
+    import sys
+    from conftest import REPO
+    g = load_golden("turing_tiny")
+    out = str(tmp_path / "csv")
+    r = subprocess.run([sys.executable, "-m", "spatial_sbml_b200.cli", model_path("turing_tiny"), "--dims", "22", "22", "--end", "0.63",
+                        "--dt", "0.07", "--out", out], cwd=REPO, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "100% finished" in r.stdout or "finished" not in r.stdout
+    rows = np.loadtxt(out + "/10.csv", delimiter=",", comments="#")
+    assert rows.shape == (22 * 22, 4)
+    assert np.array_equal(rows[:, 2].reshape(22, 22), g["step/10/species_1"][0])
+    assert np.array_equal(rows[:, 3].reshape(22, 22), g["step/10/species_2"][0])
+    assert np.array_equal(rows[:22, 0], np.arange(22.0)) and np.all(rows[:22, 1] == 0.0)
