@@ -171,6 +171,14 @@ SB2_API int sb2_finalize(sb2_sim* sim);
  * (spatialsimulator.cpp:1358).  time_slot < 0: model does not use time. */
 SB2_API int sb2_step(sb2_sim* sim, double t_arg, double t_incr, double dt, int nsteps, int time_slot);
 
+/* One oneStep whose inputs and outputs are HOST arrays (compact nx*ny*nz per staged species, ideally pinned; in[s] /
+ * out[s] may be NULL to skip that species' upload / download): the grid is cut into nslabs slabs of the slowest axis
+ * (<= 0: 16) and upload, the four stages and download of successive slabs overlap on three streams.  Replaces the
+ * sequence "write through getVariable pointers, oneStep, read them back" (spatialsimulator.h:88, :209) for callers
+ * that exchange the whole state with the host every step.  Only for models on the fused schedule (no advection,
+ * membrane transport, Dirichlet or non-zero flux conditions): SB2_ERR_STATE otherwise, and the caller falls back. */
+SB2_API int sb2_step_host(sb2_sim* sim, double t_arg, double dt, int time_slot, const double* const* in, double* const* out, int nslabs);
+
 SB2_API int sb2_download_species(sb2_sim* sim, int species, double* out);      /* compact nx*ny*nz */
 SB2_API int sb2_upload_species(sb2_sim* sim, int species, const double* in);
 SB2_API int sb2_download_stage(sb2_sim* sim, int species, int m, double* out); /* k_m, for tests */

@@ -42,6 +42,10 @@ SSB_API int ssb_init_from_string(ssb_sim* s, const char* sbml, int xdim, int ydi
 /* :88 — returns initialTime + step (NaN on failure) */
 SSB_API double ssb_one_step(ssb_sim* s, double initial_time, double step);
 SSB_API int ssb_run_steps(ssb_sim* s, double first_step_index, double step, int nsteps);
+/* oneStep with the values of n species taken from / returned to caller-owned compact host arrays (nx*ny*nz doubles each,
+ * ideally pinned; in[i] / out[i] may be NULL); upload, compute and download are pipelined over nslabs slabs (<= 0: 16) */
+SSB_API double ssb_one_step_host(ssb_sim* s, double initial_time, double step, int n, const char* const* ids,
+                                 const double* const* in, double* const* out, int nslabs);
 SSB_API int ssb_run(ssb_sim* s, double end_time, double step);                                /* :286 */
 
 SSB_API void ssb_set_parameter(ssb_sim* s, const char* id, double value);                     /* :107 */

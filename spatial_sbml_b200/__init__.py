@@ -74,6 +74,7 @@ def _proto(lib):
                                        C.POINTER(C.c_int32), dp, C.POINTER(C.c_int32)]),
         "sb2_finalize": (ci, [vp]),
         "sb2_step": (ci, [vp, cd, cd, cd, ci, ci]),
+        "sb2_step_host": (ci, [vp, cd, cd, ci, C.POINTER(dp), C.POINTER(dp), ci]),
         "sb2_download_species": (ci, [vp, ci, dp]),
         "sb2_upload_species": (ci, [vp, ci, dp]),
         "sb2_download_stage": (ci, [vp, ci, ci, dp]),
@@ -101,6 +102,7 @@ def _proto(lib):
         "ssb_init_from_string": (ci, [vp, cs, ci, ci, ci]),
         "ssb_one_step": (cd, [vp, cd, cd]),
         "ssb_run_steps": (ci, [vp, cd, cd, ci]),
+        "ssb_one_step_host": (cd, [vp, cd, cd, ci, C.POINTER(C.c_char_p), C.POINTER(dp), C.POINTER(dp), ci]),
         "ssb_run": (ci, [vp, cd, cd]),
         "ssb_set_parameter": (None, [vp, cs, cd]),
         "ssb_set_parameter_uniformly": (None, [vp, cs, cd]),
@@ -197,6 +199,24 @@ class SpatialSimulator(object):
         r = self._lib.ssb_one_step(self._h, float(initial_time), float(step))
         if r != r:
             raise RuntimeError("oneStep failed: " + self._err())
+        return r
+
+    def oneStepHost(self, initial_time, step, inputs=None, outputs=None, nslabs=0):
+        """oneStep with species values taken from / returned to host arrays: inputs / outputs map species id → contiguous
+        float64 array of localShape() (pinned memory makes the copies asynchronous).  Upload, the four RK stages and
+        download are pipelined over slabs of the slowest axis."""
+        inputs, outputs = inputs or {}, outputs or {}
+        ids = sorted(set(inputs) | set(outputs))
+        n = len(ids)
+        c_ids = (C.c_char_p * n)(*[i.encode() for i in ids])
+        dp = C.POINTER(C.c_double)
+        c_in = (dp * n)(*[_dptr(inputs[i]) if i in inputs else dp() for i in ids])
+        c_out = (dp * n)(*[_dptr(outputs[i]) if i in outputs else dp() for i in ids])
+        for a in list(inputs.values()) + list(outputs.values()):
+            assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"] and a.size == int(np.prod(self.localShape()))
+        r = self._lib.ssb_one_step_host(self._h, float(initial_time), float(step), n, c_ids, c_in, c_out, int(nslabs))
+        if r != r:
+            raise RuntimeError("oneStepHost failed: " + self._err())
         return r
 
     def runSteps(self, first_step_index, step, nsteps):

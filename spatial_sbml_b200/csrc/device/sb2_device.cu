@@ -64,6 +64,10 @@ struct sb2_sim {
   int rd_id;          // -1: first-generation stage kernel
   uint8_t* d_cls;
   int nstrips;
+  // sb2_step_host: copy streams and events of the slab pipeline (created on first use)
+  cudaStream_t h2d, d2h;
+  std::vector<cudaEvent_t> ev_up, ev_done;
+  cudaEvent_t ev_start;
   std::vector<Sb2RdTok> rdprog;  // lowered token records (constants patched per launch from rdslot)
   std::vector<int> rdslot;       // constants-table slot of each record's inline constant, -1 = none
   uint32_t* d_dbg;    // SB2_DEBUG=1: device debug words, checked after every stage launch
@@ -448,6 +452,7 @@ int sb2_create(const sb2_grid* grid, sb2_sim** out) {
   sim->k0_carry_valid = false; sim->d_tmp_face = NULL;
   sim->launches = 0; sim->in_step = false; sim->cur_dt = 0; sim->d_scratch = NULL;
   sim->rd_id = -1; sim->d_cls = NULL; sim->nstrips = 0; sim->d_dbg = NULL;
+  sim->h2d = NULL; sim->d2h = NULL; sim->ev_start = NULL;
   sim->trace = getenv("SB2_TRACE") != NULL;
   memset(&sim->base, 0, sizeof(sim->base));
   *out = sim;
@@ -470,6 +475,11 @@ void sb2_destroy(sb2_sim* sim) {
   sb2_free_boundary_lists(sim->blists);
   if (sim->d_scratch) cudaFree(sim->d_scratch);
   if (sim->d_cls) cudaFree(sim->d_cls);
+  if (sim->h2d) cudaStreamDestroy(sim->h2d);
+  if (sim->d2h) cudaStreamDestroy(sim->d2h);
+  if (sim->ev_start) cudaEventDestroy(sim->ev_start);
+  for (size_t i = 0; i < sim->ev_up.size(); ++i) cudaEventDestroy(sim->ev_up[i]);
+  for (size_t i = 0; i < sim->ev_done.size(); ++i) cudaEventDestroy(sim->ev_done[i]);
   if (sim->d_dbg) cudaFree(sim->d_dbg);
   if (sim->d_tmp_face) cudaFree(sim->d_tmp_face);
   if (sim->own_stream) cudaStreamDestroy(sim->stream);
@@ -884,6 +894,91 @@ int sb2_step(sb2_sim* sim, double t_arg, double t_incr, double dt, int nsteps, i
     for (int m = 0; m < 4; ++m) if ((rc = sb2_stage(sim, m, 0))) return rc;
     if ((rc = sb2_end_step(sim))) return rc;
   }
+  return SB2_OK;
+}
+
+// One step with HOST inputs and outputs, pipelined over slabs of the slowest axis: while slab j is computed (all four
+// stages, on a row range that shrinks by one row per stage so that every stage finds its neighbours' values computed:
+// rows [r0-3+m, r1+3-m) in stage m), slab j+1 is uploaded and slab j-1 is downloaded, each on its own stream.  The
+// redundant apron rows cost 12 row-stages per slab.  The result is the same step, bit for bit.
+int sb2_step_host(sb2_sim* sim, double t_arg, double dt, int time_slot, const double* const* in, double* const* out, int nslabs) {
+  if (!sim || !sim->finalized) return fail(sim, SB2_ERR_STATE, "simulator not finalized");
+  if (!in || !out) return fail(sim, SB2_ERR_ARG, "null argument");
+  cudaSetDevice(sim->g.device);
+  const int S = (int)sim->species.size();
+  const bool d3 = sim->g.dim == 3;
+  const int n = d3 ? sim->g.nz : sim->g.ny;  // rows (2-D) / planes (3-D) of the slab axis
+  if (sim->g.own_hi > sim->g.own_lo) return fail(sim, SB2_ERR_STATE, "sb2_step_host needs a handle that owns its whole grid");
+  int rc = sb2_begin_step(sim, t_arg, dt, time_slot);
+  if (rc) return rc;
+  if (!sim->fuse_combine || !sim->transports.empty() || sim->blists.n_dirichlet > 0) {
+    sim->in_step = false;
+    return fail(sim, SB2_ERR_STATE, "sb2_step_host: the model needs the unfused schedule (advection, membrane transport, non-zero flux or Dirichlet)");
+  }
+  if (nslabs < 1) nslabs = 16;
+  if (nslabs > n / 8) nslabs = n / 8 > 0 ? n / 8 : 1;
+  if (!sim->h2d) {
+    CK(cudaStreamCreateWithFlags(&sim->h2d, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&sim->d2h, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&sim->ev_start, cudaEventDisableTiming));
+  }
+  while ((int)sim->ev_up.size() < nslabs) {
+    cudaEvent_t a, b;
+    CK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    sim->ev_up.push_back(a); sim->ev_done.push_back(b);
+  }
+  const sb2_grid& g = sim->g;
+  const int64_t plane_cells = (int64_t)g.nx * g.ny;
+  auto copy_rows = [&](double* dev, double* host, int r0, int r1, bool up, cudaStream_t st) -> cudaError_t {
+    // rows [r0, r1) of the slab axis between a compact host array and the padded device array
+    if (!d3) {
+      double* d = dev + sim->first + (int64_t)r0 * sim->P;
+      double* h = host + (int64_t)r0 * g.nx;
+      return up ? cudaMemcpy2DAsync(d, sizeof(double) * sim->P, h, sizeof(double) * g.nx, sizeof(double) * g.nx, r1 - r0, cudaMemcpyHostToDevice, st)
+                : cudaMemcpy2DAsync(h, sizeof(double) * g.nx, d, sizeof(double) * sim->P, sizeof(double) * g.nx, r1 - r0, cudaMemcpyDeviceToHost, st);
+    }
+    for (int z = r0; z < r1; ++z) {
+      double* d = dev + sim->first + (int64_t)z * sim->PL;
+      double* h = host + (int64_t)z * plane_cells;
+      cudaError_t e = up ? cudaMemcpy2DAsync(d, sizeof(double) * sim->P, h, sizeof(double) * g.nx, sizeof(double) * g.nx, g.ny, cudaMemcpyHostToDevice, st)
+                         : cudaMemcpy2DAsync(h, sizeof(double) * g.nx, d, sizeof(double) * sim->P, sizeof(double) * g.nx, g.ny, cudaMemcpyDeviceToHost, st);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  };
+  // the copy streams start after whatever the compute stream still has queued (previous steps, uploads)
+  CK(cudaEventRecord(sim->ev_start, sim->stream));
+  CK(cudaStreamWaitEvent(sim->h2d, sim->ev_start, 0));
+  CK(cudaStreamWaitEvent(sim->d2h, sim->ev_start, 0));
+  auto lo_of = [&](int j) { return (int)((int64_t)j * n / nslabs); };
+  for (int j = 0; j < nslabs; ++j) {  // all uploads are queued up front, in slab order
+    for (int s = 0; s < S; ++s)
+      if (in[s]) CK(copy_rows(sim->species[s].u[sim->species[s].cur], const_cast<double*>(in[s]), lo_of(j), lo_of(j + 1), true, sim->h2d));
+    CK(cudaEventRecord(sim->ev_up[j], sim->h2d));
+  }
+  Sb2StageArgs a;
+  for (int j = 0; j < nslabs; ++j) {
+    const int r0 = lo_of(j), r1 = lo_of(j + 1);
+    CK(cudaStreamWaitEvent(sim->stream, sim->ev_up[j + 1 < nslabs ? j + 1 : j], 0));  // the apron rows lie in the next slab
+    for (int m = 0; m < 4; ++m) {
+      int b = r0 - (3 - m), e = r1 + (3 - m);
+      if (b < 0) b = 0;
+      if (e > n) e = n;
+      fill_stage_args(sim, a, m, dt, b, e);
+      cudaError_t ce = sb2_launch_stage(a, sim->stream, &sim->launches);
+      if (ce != cudaSuccess) return cuda_fail(sim, ce, "stage kernel launch");
+    }
+    CK(cudaEventRecord(sim->ev_done[j], sim->stream));
+    CK(cudaStreamWaitEvent(sim->d2h, sim->ev_done[j], 0));
+    for (int s = 0; s < S; ++s)
+      if (out[s]) CK(copy_rows(sim->species[s].u[sim->species[s].cur ^ 1], out[s], r0, r1, false, sim->d2h));
+  }
+  for (int s = 0; s < S; ++s) sim->species[s].cur ^= 1;
+  sim->k0_carry_valid = false;
+  sim->in_step = false;
+  CK(cudaStreamSynchronize(sim->d2h));
+  CK(cudaStreamSynchronize(sim->stream));
   return SB2_OK;
 }
 

@@ -52,6 +52,10 @@ double ssb_one_step(ssb_sim* s, double t, double dt) {
   if (!s) return NAN;
   try { return s->sim.oneStep(t, dt); } catch (const std::exception& e) { s->error = e.what(); return NAN; }
 }
+double ssb_one_step_host(ssb_sim* s, double t, double dt, int n, const char* const* ids, const double* const* in, double* const* out, int nslabs) {
+  if (!s) return NAN;
+  try { return s->sim.oneStepHost(t, dt, n, ids, in, out, nslabs); } catch (const std::exception& e) { s->error = e.what(); return NAN; }
+}
 int ssb_run_steps(ssb_sim* s, double first, double dt, int n) {
   if (!s) return -1;
   try { s->sim.runSteps(first, dt, n); } catch (const std::exception& e) { s->error = e.what(); return -1; }

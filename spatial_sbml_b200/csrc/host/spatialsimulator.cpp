@@ -619,6 +619,44 @@ double SpatialSimulator::oneStep(double initialTime, double step) {
   return initialTime + step;
 }
 
+double SpatialSimulator::oneStepHost(double initialTime, double step, int n, const char* const* ids, const double* const* in,
+                                     double* const* out, int nslabs) {
+  if (!impl || !impl->dev)
+    throw std::runtime_error("SpatialSimulator::oneStepHost: no device simulator (" + (lastError.empty() ? std::string("not initialised") : lastError) +
+                             "); there is no CPU fallback");
+  syncBeforeStep();
+  impl->m.simTime = initialTime * step;
+  impl->m.tVar->uniformValue = impl->m.simTime;
+  const size_t S = impl->stale.size();
+  std::vector<const double*> din(S, (const double*)NULL);
+  std::vector<double*> dout(S, (double*)NULL);
+  std::vector<Var*> vars(n, (Var*)NULL);
+  bool staged_only = true;
+  for (int i = 0; i < n; ++i) {
+    Var* v = impl->m.findVar(ids[i]);
+    vars[i] = v;
+    if (!v || v->speciesId < 0) { staged_only = false; continue; }
+    din[v->speciesId] = in ? in[i] : NULL;
+    dout[v->speciesId] = out ? out[i] : NULL;
+  }
+  int rc = staged_only ? sb2_step_host(impl->dev, initialTime, step, impl->timeSlot, din.data(), dout.data(), nslabs) : SB2_ERR_STATE;
+  if (rc == SB2_ERR_STATE) {
+    // unfused schedule (or a variable that is not a staged species): the plain sequence
+    for (int i = 0; i < n; ++i)
+      if (in && in[i] && !setVariableCompact(ids[i], in[i], (size_t)impl->m.ncells())) throw std::runtime_error(std::string("oneStepHost: cannot set ") + ids[i]);
+    oneStep(initialTime, step);
+    for (int i = 0; i < n; ++i)
+      if (out && out[i] && !getVariableCompact(ids[i], out[i], (size_t)impl->m.ncells())) throw std::runtime_error(std::string("oneStepHost: cannot read ") + ids[i]);
+    return initialTime + step;
+  }
+  if (rc < 0) {
+    lastError = std::string("sb2_step_host: ") + sb2_last_error(impl->dev);
+    throw std::runtime_error(lastError);
+  }
+  for (size_t s = 0; s < S; ++s) impl->stale[s] = 1;
+  return initialTime + step;
+}
+
 void SpatialSimulator::runSteps(double firstStepIndex, double step, int nsteps) {
   if (!impl || !impl->dev)
     throw std::runtime_error("SpatialSimulator::runSteps: no device simulator (" + (lastError.empty() ? std::string("not initialised") : lastError) +

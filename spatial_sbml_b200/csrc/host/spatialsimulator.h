@@ -82,6 +82,10 @@ class __attribute__((visibility("default"))) SpatialSimulator {
   const std::string& getLastError() const;
   // n steps with the step-counter time convention of run(): oneStep(firstStepIndex + i, step)
   void runSteps(double firstStepIndex, double step, int nsteps);
+  // oneStep whose species values come from / go to caller-owned COMPACT host arrays (nx*ny*nz each, ideally pinned):
+  // upload, the four stages and download are pipelined over slabs (sb2_step_host).  ids[i] names the species of
+  // in[i] / out[i] (either may be NULL).  Falls back to upload + oneStep + download for models off the fused schedule.
+  double oneStepHost(double initialTime, double step, int n, const char* const* ids, const double* const* in, double* const* out, int nslabs);
   // compact (volume cells only, nx*ny*nz) copy of a species / field, without the doubled mirror
   bool getVariableCompact(const std::string& id, double* out, size_t n);
   bool setVariableCompact(const std::string& id, const double* in, size_t n);
