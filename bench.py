@@ -250,13 +250,14 @@ def main():
         # the user-facing call for "state lives on the host": oneStepHost = upload, the four stages and download of
         # successive slabs pipelined on three streams (sb2_step_host); the output of a step is the input of the next
         hout = [torch.empty((nzl, nyl, nxl), dtype=torch.float64).pin_memory().numpy() for _ in range(S)]
-        sim.oneStepHost(W + K, dt, dict(zip(names, hbuf)), dict(zip(names, hout)))  # warm-up: streams, events
+        nsl = int(os.environ.get("BENCH_SLABS", "0"))
+        sim.oneStepHost(W + K, dt, dict(zip(names, hbuf)), dict(zip(names, hout)), nsl)  # warm-up: streams, events
         hbuf, hout = hout, hbuf
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(Ke):
-            sim.oneStepHost(W + K + 1 + i, dt, dict(zip(names, hbuf)), dict(zip(names, hout)))
+            sim.oneStepHost(W + K + 1 + i, dt, dict(zip(names, hbuf)), dict(zip(names, hout)), nsl)
             hbuf, hout = hout, hbuf
         e1.record()
         torch.cuda.synchronize()
