@@ -2,12 +2,12 @@
 #include "sb2_internal.h"
 #include <cstdlib>
 
-cudaError_t sb2_rd_launch_v0(const Sb2StageArgs& a, cudaStream_t stream);
-cudaError_t sb2_rd_launch_v1(const Sb2StageArgs& a, cudaStream_t stream);
-cudaError_t sb2_rd_launch_v2(const Sb2StageArgs& a, cudaStream_t stream);
-cudaError_t sb2_rd_launch_v3(const Sb2StageArgs& a, cudaStream_t stream);
-cudaError_t sb2_rd_launch_v4(const Sb2StageArgs& a, cudaStream_t stream);
-cudaError_t sb2_rd_launch_v5(const Sb2StageArgs& a, cudaStream_t stream);
+cudaError_t sb2_rd_launch_v0(const Sb2RdArgs& a, cudaStream_t stream);
+cudaError_t sb2_rd_launch_v1(const Sb2RdArgs& a, cudaStream_t stream);
+cudaError_t sb2_rd_launch_v2(const Sb2RdArgs& a, cudaStream_t stream);
+cudaError_t sb2_rd_launch_v3(const Sb2RdArgs& a, cudaStream_t stream);
+cudaError_t sb2_rd_launch_v4(const Sb2RdArgs& a, cudaStream_t stream);
+cudaError_t sb2_rd_launch_v5(const Sb2RdArgs& a, cudaStream_t stream);
 
 namespace {
 // id, max species, cell pairs per thread, warps per CTA, expression stack depth
@@ -52,7 +52,7 @@ int sb2_rd_pick_variant(int dim, int nx, int nspecies, int depth, Sb2RdVariant* 
   return id;
 }
 
-cudaError_t sb2_rd_launch(const Sb2StageArgs& a, cudaStream_t stream) {
+cudaError_t sb2_rd_launch(const Sb2RdArgs& a, cudaStream_t stream) {
   switch (a.rd_variant) {
     case 0: return sb2_rd_launch_v0(a, stream);
     case 1: return sb2_rd_launch_v1(a, stream);

@@ -164,7 +164,7 @@ __device__ __forceinline__ double div6(double x) {
 #define RD_REP_D1(M) M(1) M(2) M(3) M(4) M(5) M(6) M(7)
 
 template <int NS, int NP, int W, int MODE, int DEPTH, int MINB, bool D3>
-__global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_constant__ Sb2StageArgs A) {
+__global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_constant__ Sb2RdArgs A) {
   using G = Geo<NP, W>;
   constexpr int NC = G::NC, SW = G::SW, SWP = G::SWP, RW = G::RW;
   constexpr int NARR = (MODE == MODE_FIRST) ? 1 : 2;  // arrays per species in a raw slot: u (, k_{m-1})
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
     if (MODE == MODE_FINAL) mbar_init(mycbar, 1);
     mbar_fence_init();
   }
-  // the token records move from the kernel parameters to shared memory once (first read after the first barrier)
+  // the token records move from their device buffer to shared memory once (first read after the first barrier)
   for (int i = threadIdx.x; i < A.nrd + 2; i += W * 32) {
     const Sb2RdTok t = A.rdtok[i];
     reinterpret_cast<double*>(smem_raw + 128)[i] = t.c;
@@ -686,7 +686,7 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
 }
 
 template <int NS, int NP, int W, int MODE, int DEPTH, int MINB, bool D3>
-cudaError_t launch_variant(const Sb2StageArgs& a, cudaStream_t stream) {
+cudaError_t launch_variant(const Sb2RdArgs& a, cudaStream_t stream) {
   using G = Geo<NP, W>;
   const int narr = (MODE == MODE_FIRST) ? 1 : 2;
   const size_t smem = 128 + tok_bytes(a.nrd) + sizeof(double) * ((size_t)a.S * G::RW * G::SWP + (size_t)W * a.S * narr * G::SWP +
@@ -712,14 +712,14 @@ cudaError_t launch_variant(const Sb2StageArgs& a, cudaStream_t stream) {
 }
 
 template <int NS, int NP, int W, int DEPTH, int MINB, bool D3>
-cudaError_t launch_dim(const Sb2StageArgs& a, cudaStream_t stream) {
+cudaError_t launch_dim(const Sb2RdArgs& a, cudaStream_t stream) {
   if (a.m == 0) return launch_variant<NS, NP, W, MODE_FIRST, DEPTH, MINB, D3>(a, stream);
   if (a.final) return launch_variant<NS, NP, W, MODE_FINAL, DEPTH, MINB, D3>(a, stream);
   return launch_variant<NS, NP, W, MODE_MIDDLE, DEPTH, MINB, D3>(a, stream);
 }
 
 template <int NS, int NP, int W, int DEPTH, int MINB>
-cudaError_t launch_mode(const Sb2StageArgs& a, cudaStream_t stream) {
+cudaError_t launch_mode(const Sb2RdArgs& a, cudaStream_t stream) {
   if (a.dim == 3) return launch_dim<NS, NP, W, DEPTH, MINB, true>(a, stream);
   return launch_dim<NS, NP, W, DEPTH, MINB, false>(a, stream);
 }

@@ -2,4 +2,4 @@
 // 4 warps per CTA, expression stack depth 2.
 #include "rd_stage.cuh"
 
-cudaError_t sb2_rd_launch_v0(const Sb2StageArgs& a, cudaStream_t stream) { return rd::launch_mode<2, 4, 4, 2, 3>(a, stream); }
+cudaError_t sb2_rd_launch_v0(const Sb2RdArgs& a, cudaStream_t stream) { return rd::launch_mode<2, 4, 4, 2, 3>(a, stream); }

@@ -2,4 +2,4 @@
 // 8 warps per CTA, expression stack depth 4.
 #include "rd_stage.cuh"
 
-cudaError_t sb2_rd_launch_v1(const Sb2StageArgs& a, cudaStream_t stream) { return rd::launch_mode<2, 2, 8, 4, 2>(a, stream); }
+cudaError_t sb2_rd_launch_v1(const Sb2RdArgs& a, cudaStream_t stream) { return rd::launch_mode<2, 2, 8, 4, 2>(a, stream); }

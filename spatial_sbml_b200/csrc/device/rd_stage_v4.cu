@@ -2,4 +2,4 @@
 // 4 warps per CTA, expression stack depth 8.
 #include "rd_stage.cuh"
 
-cudaError_t sb2_rd_launch_v4(const Sb2StageArgs& a, cudaStream_t stream) { return rd::launch_mode<4, 1, 4, 8, 2>(a, stream); }
+cudaError_t sb2_rd_launch_v4(const Sb2RdArgs& a, cudaStream_t stream) { return rd::launch_mode<4, 1, 4, 8, 2>(a, stream); }

@@ -52,7 +52,10 @@ struct sb2_sim {
   bool carry_k0;        // this step: a non-zero Neumann flux is carried in k0 (spatialsimulator.cpp:1540-1542)
   bool k0_carry_valid;  // k0 currently holds the flux parked by the previous step's post-update pass
   double* d_tmp_face;   // CIP scratch
-  Sb2StageArgs base;
+  Sb2StageCore base;
+  uint32_t base_tok[SB2_MAX_TOKENS + 2];  // first-generation program (kernel parameter)
+  Sb2RdTok* d_rdtok;                      // rd_stage token records on the device
+  std::vector<Sb2RdTok> rd_uploaded;      // what d_rdtok currently holds
   std::string err;
   int launches;
   // split-phase step state
@@ -356,10 +359,9 @@ const char* kOpcNames[OPC_COUNT] = {"END", "PUSHC", "PUSHV", "PUSHF", "ADD", "SU
   "LEQ", "LT", "AND", "OR", "ADDC", "SUBC", "MULC", "DIVC", "RSUBC", "RDIVC", "GEQC", "GTC", "LEQC", "LTC", "ADDV", "SUBV", "MULV",
   "DIVV", "UNARY", "BINR", "MOV0", "MOVUP", "MASK", "ACCSUB", "ACCADD", "ACCSUB1", "ACCADD1", "ACCSUBC1", "ACCADDC1", "ACCSUBM", "ACCADDM"};
 
-void fill_stage_args(sb2_sim* sim, Sb2StageArgs& a, int m, double dt, int row_begin, int row_end) {
+void fill_stage_args(sb2_sim* sim, Sb2StageCore& a, int m, double dt, int row_begin, int row_end) {
   static const double rk[4] = {0.0, 0.5, 0.5, 1.0};
   a = sim->base;
-  memcpy(a.consts, sim->consts, sizeof(a.consts));
   a.m = m;
   a.dt = dt;
   a.cdt = rk[m] * dt;
@@ -367,8 +369,6 @@ void fill_stage_args(sb2_sim* sim, Sb2StageArgs& a, int m, double dt, int row_be
   a.carry = (sim->carry_k0 && m == 0) || !sim->transports.empty() ? 1 : 0;
   a.row_begin = row_begin;
   a.row_end = row_end;
-  for (size_t i = 0; i < sim->rdslot.size(); ++i)
-    if (sim->rdslot[i] >= 0) a.rdtok[i].c = sim->consts[sim->rdslot[i]];
   const int S = (int)sim->species.size();
   for (int s = 0; s < S; ++s) {
     Sb2Species& sp = sim->species[s];
@@ -404,6 +404,50 @@ void fill_stage_args(sb2_sim* sim, Sb2StageArgs& a, int m, double dt, int row_be
   int rpb = 64;
   while (rpb > 8 && (int64_t)strips * planes * ((rows + rpb - 1) / rpb) < 148 * 8) rpb /= 2;
   a.rows_per_block = rpb;
+}
+
+// One stage on rows [row_begin, row_end) of the slab axis with whichever kernel family the model runs on.
+int launch_stage_rows(sb2_sim* sim, int m, double dt, int row_begin, int row_end) {
+  if (row_end <= row_begin) return SB2_OK;
+  cudaError_t e;
+  if (sim->rd_id >= 0) {
+    Sb2RdArgs a;
+    fill_stage_args(sim, a, m, dt, row_begin, row_end);
+    // inline constants of the token records = current values of the constants table; upload only when they changed
+    std::vector<Sb2RdTok> cur(sim->rdprog);
+    for (size_t i = 0; i < sim->rdslot.size(); ++i)
+      if (sim->rdslot[i] >= 0) cur[i].c = sim->consts[sim->rdslot[i]];
+    Sb2RdTok end; end.code = 0; end.arg = 0; end.c = 0.0;
+    cur.push_back(end); cur.push_back(end);
+    if (cur.size() != sim->rd_uploaded.size() || memcmp(cur.data(), sim->rd_uploaded.data(), sizeof(Sb2RdTok) * cur.size()) != 0) {
+      e = cudaMemcpyAsync(sim->d_rdtok, cur.data(), sizeof(Sb2RdTok) * cur.size(), cudaMemcpyHostToDevice, sim->stream);  // pageable: staged before return
+      if (e != cudaSuccess) return cuda_fail(sim, e, "token upload");
+      sim->rd_uploaded.swap(cur);
+    }
+    a.rdtok = sim->d_rdtok;
+    if (sim->trace) fprintf(stderr, "[sb2] stage m=%d rows [%d,%d) rpb %d final %d carry %d\n", m, row_begin, row_end, a.rows_per_block, a.final, a.carry);
+    ++sim->launches;
+    e = sb2_rd_launch(a, sim->stream);
+  } else {
+    Sb2StageArgs a;
+    fill_stage_args(sim, a, m, dt, row_begin, row_end);
+    memcpy(a.tok, sim->base_tok, sizeof(a.tok));
+    memcpy(a.consts, sim->consts, sizeof(a.consts));
+    e = sb2_launch_stage(a, sim->stream, &sim->launches);
+  }
+  if (e != cudaSuccess) return cuda_fail(sim, e, "stage kernel launch");
+  if (sim->d_dbg) {
+    uint32_t h[8];
+    CK(cudaStreamSynchronize(sim->stream));
+    CK(cudaMemcpy(h, sim->d_dbg, sizeof(h), cudaMemcpyDeviceToHost));
+    if (h[0]) {
+      std::ostringstream os;
+      os << "rd_stage: " << h[0] << " bulk-copy waits timed out; first: strip " << h[1] << " tile " << h[2] << " warp " << h[3]
+         << " row " << (int)h[4] << " parity " << h[5] << " tile rows [" << (int)h[6] << "," << (int)h[7] << ")";
+      return fail(sim, SB2_ERR_CUDA, os.str());
+    }
+  }
+  return SB2_OK;
 }
 
 }  // namespace
@@ -452,7 +496,7 @@ int sb2_create(const sb2_grid* grid, sb2_sim** out) {
   sim->k0_carry_valid = false; sim->d_tmp_face = NULL;
   sim->launches = 0; sim->in_step = false; sim->cur_dt = 0; sim->d_scratch = NULL;
   sim->rd_id = -1; sim->d_cls = NULL; sim->nstrips = 0; sim->d_dbg = NULL;
-  sim->h2d = NULL; sim->d2h = NULL; sim->ev_start = NULL;
+  sim->h2d = NULL; sim->d2h = NULL; sim->ev_start = NULL; sim->d_rdtok = NULL;
   sim->trace = getenv("SB2_TRACE") != NULL;
   memset(&sim->base, 0, sizeof(sim->base));
   *out = sim;
@@ -475,6 +519,7 @@ void sb2_destroy(sb2_sim* sim) {
   sb2_free_boundary_lists(sim->blists);
   if (sim->d_scratch) cudaFree(sim->d_scratch);
   if (sim->d_cls) cudaFree(sim->d_cls);
+  if (sim->d_rdtok) cudaFree(sim->d_rdtok);
   if (sim->h2d) cudaStreamDestroy(sim->h2d);
   if (sim->d2h) cudaStreamDestroy(sim->d2h);
   if (sim->ev_start) cudaEventDestroy(sim->ev_start);
@@ -625,7 +670,7 @@ int sb2_finalize(sb2_sim* sim) {
   sim->any_adv = false;
   for (size_t s = 0; s < sim->species.size(); ++s) if (sim->species[s].has_adv) sim->any_adv = true;
 
-  Sb2StageArgs& b = sim->base;
+  Sb2StageCore& b = sim->base;
   memset(&b, 0, sizeof(b));
   b.nx = sim->g.nx; b.ny = sim->g.ny; b.nz = sim->g.nz; b.dim = sim->g.dim;
   b.P = sim->P; b.PL = sim->PL; b.first = sim->first;
@@ -662,9 +707,10 @@ int sb2_finalize(sb2_sim* sim) {
     const int opc = (int)(code / SB2_MAX_DEPTH), d = (int)(code % SB2_MAX_DEPTH);
     if (opc < OPC_MASK && d + 1 + (opc == OPC_MOVUP ? 1 : 0) > b.depth) b.depth = d + 1 + (opc == OPC_MOVUP ? 1 : 0);
   }
-  memcpy(b.tok, sim->program.data(), sizeof(uint32_t) * sim->program.size());
-  b.tok[sim->program.size()] = enc(OPC_END, 0, 0);
-  b.tok[sim->program.size() + 1] = enc(OPC_END, 0, 0);
+  memset(sim->base_tok, 0, sizeof(sim->base_tok));
+  memcpy(sim->base_tok, sim->program.data(), sizeof(uint32_t) * sim->program.size());
+  sim->base_tok[sim->program.size()] = enc(OPC_END, 0, 0);
+  sim->base_tok[sim->program.size() + 1] = enc(OPC_END, 0, 0);
 
   // 2-D models with up to four staged species run the rd_stage kernel; SB2_STAGE_KERNEL=gen1 forces the
   // first-generation kernel (kept for 3-D grids and more species, and as a cross-check in the tests)
@@ -677,8 +723,8 @@ int sb2_finalize(sb2_sim* sim) {
   b.rd_variant = sim->rd_id;
   if (sim->rd_id >= 0) {
     b.nrd = (int)sim->rdprog.size();
-    memset(b.rdtok, 0, sizeof(b.rdtok));
-    memcpy(b.rdtok, sim->rdprog.data(), sizeof(Sb2RdTok) * sim->rdprog.size());
+    CK(cudaMalloc((void**)&sim->d_rdtok, sizeof(Sb2RdTok) * (SB2_RD_MAX_TOKENS + 2)));
+    sim->rd_uploaded.clear();
     const int sw = 64 * sim->rd.np;
     if (sw + 4 > SB2_TAIL_PAD) return fail(sim, SB2_ERR_STATE, "strip wider than the tail pad of the field layout");
     sim->nstrips = (sim->g.nx + sw - 1) / sw;
@@ -782,26 +828,7 @@ int sb2_stage(sb2_sim* sim, int m, int phase) {
     }
   }
 
-  Sb2StageArgs a;
-  auto launch = [&](int rb, int re) -> int {
-    if (re <= rb) return SB2_OK;
-    fill_stage_args(sim, a, m, dt, rb, re);
-    if (sim->trace) fprintf(stderr, "[sb2] stage m=%d rows [%d,%d) rpb %d final %d carry %d\n", m, rb, re, a.rows_per_block, a.final, a.carry);
-    cudaError_t e = sb2_launch_stage(a, sim->stream, &sim->launches);
-    if (e != cudaSuccess) return cuda_fail(sim, e, "stage kernel launch");
-    if (sim->d_dbg) {
-      uint32_t h[8];
-      CK(cudaStreamSynchronize(sim->stream));
-      CK(cudaMemcpy(h, sim->d_dbg, sizeof(h), cudaMemcpyDeviceToHost));
-      if (h[0]) {
-        std::ostringstream os;
-        os << "rd_stage: " << h[0] << " bulk-copy waits timed out; first: strip " << h[1] << " tile " << h[2] << " warp " << h[3]
-           << " row " << (int)h[4] << " parity " << h[5] << " tile rows [" << (int)h[6] << "," << (int)h[7] << ")";
-        return fail(sim, SB2_ERR_CUDA, os.str());
-      }
-    }
-    return SB2_OK;
-  };
+  auto launch = [&](int rb, int re) -> int { return launch_stage_rows(sim, m, dt, rb, re); };
   int rc = SB2_OK;
   if (phase == 0) rc = launch(own_lo, own_hi);
   else if (phase == 1) {
@@ -957,7 +984,6 @@ int sb2_step_host(sb2_sim* sim, double t_arg, double dt, int time_slot, const do
       if (in[s]) CK(copy_rows(sim->species[s].u[sim->species[s].cur], const_cast<double*>(in[s]), lo_of(j), lo_of(j + 1), true, sim->h2d));
     CK(cudaEventRecord(sim->ev_up[j], sim->h2d));
   }
-  Sb2StageArgs a;
   for (int j = 0; j < nslabs; ++j) {
     const int r0 = lo_of(j), r1 = lo_of(j + 1);
     CK(cudaStreamWaitEvent(sim->stream, sim->ev_up[j + 1 < nslabs ? j + 1 : j], 0));  // the apron rows lie in the next slab
@@ -965,9 +991,7 @@ int sb2_step_host(sb2_sim* sim, double t_arg, double dt, int time_slot, const do
       int b = r0 - (3 - m), e = r1 + (3 - m);
       if (b < 0) b = 0;
       if (e > n) e = n;
-      fill_stage_args(sim, a, m, dt, b, e);
-      cudaError_t ce = sb2_launch_stage(a, sim->stream, &sim->launches);
-      if (ce != cudaSuccess) return cuda_fail(sim, ce, "stage kernel launch");
+      if ((rc = launch_stage_rows(sim, m, dt, b, e))) return rc;
     }
     CK(cudaEventRecord(sim->ev_done[j], sim->stream));
     CK(cudaStreamWaitEvent(sim->d2h, sim->ev_done[j], 0));

@@ -70,7 +70,8 @@ struct Sb2SpeciesArgs {
   double dconst[3];  // value of a uniform coefficient at launch time
 };
 
-struct Sb2StageArgs {
+// what both stage-kernel families need; small enough to keep kernel launches cheap
+struct Sb2StageCore {
   int32_t nx, ny, nz, dim;
   int64_t P, PL, first;  // row pitch, plane pitch, offset of cell (0,0,0), all in elements
   int32_t row_begin, row_end;      // rows (2-D: y) or planes (3-D: z) of the slab axis to compute
@@ -94,9 +95,18 @@ struct Sb2StageArgs {
   uint32_t* dbg;       // rd_stage: debug words (SB2_DEBUG=1), else NULL; [0] = mbarrier waits that timed out
   int32_t rd_variant;  // rd_stage kernel variant chosen at finalize (-1: the first-generation kernel runs)
   int32_t nrd;         // rd_stage: token records (without the trailing OPC_END pair)
+};
+
+// first-generation kernel: program and constants table travel in the kernel parameters (constant memory)
+struct Sb2StageArgs : Sb2StageCore {
   uint32_t tok[SB2_MAX_TOKENS + 2];  // + trailing OPC_END (the interpreter fetches one token ahead)
-  Sb2RdTok rdtok[SB2_RD_MAX_TOKENS + 2];
   double consts[SB2_MAX_CONSTS];
+};
+
+// rd_stage kernel: the token records live in a small device buffer (re-uploaded only when a constant changed) and are
+// copied to shared memory by every CTA; 1 KB of parameters instead of 15 KB keeps the launch cheap on small grids
+struct Sb2RdArgs : Sb2StageCore {
+  const Sb2RdTok* rdtok;
 };
 
 // launches (implemented in stage_kernel.cu)
@@ -107,7 +117,7 @@ int sb2_stage_pairs(int nx, int nspecies);
 struct Sb2RdVariant { int id, ns, np, w, depth; };
 // picks the variant for a 2-D model (returns id or -1 when only the first-generation kernel applies)
 int sb2_rd_pick_variant(int dim, int nx, int nspecies, int depth, Sb2RdVariant* out);
-cudaError_t sb2_rd_launch(const Sb2StageArgs& a, cudaStream_t stream);
+cudaError_t sb2_rd_launch(const Sb2RdArgs& a, cudaStream_t stream);
 // class map: cls[(z * ny + y) * nstrips + strip] for strips of sw cells, every held row of every held plane
 cudaError_t sb2_rd_classify(const uint8_t* const* flags, int G, int nx, int ny, int nz, int64_t P, int64_t PL, int64_t first,
                             int sw, uint8_t* cls, int nstrips, cudaStream_t stream);

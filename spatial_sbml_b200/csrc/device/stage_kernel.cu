@@ -41,7 +41,6 @@ int sb2_stage_pairs(int nx, int nspecies) { return (nspecies <= 4 && nx > 256) ?
 cudaError_t sb2_launch_stage(const Sb2StageArgs& a, cudaStream_t stream, int* launches) {
   if (a.row_end <= a.row_begin) return cudaSuccess;
   if (launches) ++*launches;
-  if (a.rd_variant >= 0) return sb2_rd_launch(a, stream);
   if (a.S <= 2) return sb2_launch_stage_ns2(a, stream);
   if (a.S <= 4) return sb2_launch_stage_ns4(a, stream);
   return sb2_launch_stage_ns8(a, stream);
