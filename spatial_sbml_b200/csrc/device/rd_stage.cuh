@@ -25,13 +25,16 @@
 //     16-byte shared or global access of a warp covers 512 contiguous bytes.
 //   * A per-(row, strip) class byte, computed once at finalize, says whether every cell of the strip row
 //     is an interior cell of every geometry (class 1: straight-line stencil, no per-cell test), lies
-//     outside every domain (class 2: nothing to compute) or needs the per-cell flag logic (class 0).
-//   * The token stream and the constants table arrive as a __grid_constant__ kernel parameter, i.e. in
-//     constant memory.  The program counter is warp-uniform: a token fetch is a uniform constant load
-//     and the dispatch one indexed branch through a dense jump table; each case acts on all 2*NP cells
-//     of the thread with compile-time register indices (tokens carry their stack slot).
-//   * The last stage reads u, k0, k1, k2 of its own cells with plain 16-byte loads; lane 0 asks for the
-//     k0 / k1 rows one batch ahead with cp.async.bulk.prefetch.L2, u and k2 were just staged through L2.
+//     outside every domain (class 2: nothing to compute) or needs the per-cell flag logic (class 0: every
+//     stencil term is computed and added under a predicate, no data-dependent branch).
+//   * The token stream (4-byte code words and 8-byte inline constants, two parallel arrays) is copied from a small
+//     device buffer to shared memory once per CTA and fetched one token ahead.  The program counter is
+//     warp-uniform: the dispatch is one indexed branch through a dense jump table without a range check; each
+//     case acts on all 2*NP cells of the thread with compile-time register indices (tokens carry their stack slot).
+//   * The last stage fuses the RK4 combine: the k0 / k1 rows of a warp's row arrive through a second per-warp TMA slot
+//     requested one batch ahead; u and k2 of its own cells are re-read with plain 16-byte loads that hit L2, because the
+//     bulk copies that staged them one batch earlier carry an L2::evict_last hint.
+//   * 3-D: a tile is a range of rows of ONE plane; the z neighbours are read from global memory (L2).
 //
 // Arithmetic follows the reference's evaluation order with explicit round-to-nearest intrinsics
 // (never contracted into FMAs), so results are bit-identical to the CPU code for + - * / and
@@ -77,9 +80,8 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
-// L2 prefetch that keeps the lines until they are used: the default priority of a bulk prefetch is evict-first,
-// and under a stream of several TB/s such lines were gone again before the loads of the next batch arrived
-// (ncu: the k0 / k1 rows were read from DRAM twice).
+// L2 policy for rows that are read a second time one batch later (the last stage re-reads u and k2 for the combine):
+// without it ncu showed the re-reads served from DRAM (6.5 GB instead of 4.4 GB per launch at 8192^2).
 __device__ __forceinline__ uint64_t l2_policy_keep() {
   uint64_t pol;
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
@@ -89,9 +91,6 @@ __device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uin
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar), "l"(policy)
                : "memory");
-}
-__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes, uint64_t policy) {
-  asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(src), "r"(bytes), "l"(policy) : "memory");
 }
 // Bounded wait: a copy that never lands (a bug) ends in wrong results and a failed test, not in a hung GPU.
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
