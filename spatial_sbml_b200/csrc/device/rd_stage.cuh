@@ -16,11 +16,12 @@
 //           cell, and parks it in a ring of w rows shared by the CTA,
 //       (3) re-arms its mbarrier and issues the bulk copy of the row it needs in the next batch, which
 //           is in flight during everything that follows,
-//       (4) __syncthreads()  — the only CTA-wide synchronisation, once per W rows —
+//       (4) waits, on two row-ready mbarriers, for exactly the two ring rows other warps stage for it (rows y-1 and y);
+//           there is no CTA-wide barrier in the loop, so staging, token dispatch and stencil of different warps overlap,
 //       (5) evaluates the reaction bytecode and the 5-point stencil of row y from the w ring (rows
 //           y-1, y, y+1) and stores k_m (or the new u) straight from registers with 16-byte stores.
-//     The ring holds 2W+2 rows, so a warp that runs ahead into step (2) of the next batch never
-//     overwrites a row another warp still reads in step (5).
+//     The ring holds 2W+2 rows: the warp that re-stages a slot has, through the chain of step-(4) waits, seen the three
+//     rows around the old content computed (see the comment at the wait).
 //   * Each thread owns NP pairs of adjacent cells; pair p of lane l sits at x0 + 64p + 2l, so every
 //     16-byte shared or global access of a warp covers 512 contiguous bytes.
 //   * A per-(row, strip) class byte, computed once at finalize, says whether every cell of the strip row
@@ -72,6 +73,9 @@ __device__ __forceinline__ void mbar_fence_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -118,6 +122,12 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
 }
 
 __host__ __device__ inline int tok_bytes(int nrd) { return ((nrd + 2) * 16 + 127) / 128 * 128; }
+
+// Shared-memory header: W bulk-copy barriers, W combine barriers, RW row-ready barriers (8 bytes each)
+constexpr int HDR = 512;
+#ifndef SB2_RD_P2P
+#define SB2_RD_P2P 1  // 1: warps wait for the two ring rows they need (row-ready mbarriers); 0: one __syncthreads() per batch
+#endif
 
 template <int NP, int W>
 struct Geo {
@@ -173,9 +183,9 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
   const int S = A.S;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
   // token stream, two parallel arrays: code | arg << 16 (4 bytes each) and the inline constants (8 bytes each)
-  const double* tokc = reinterpret_cast<const double*>(smem_raw + 128);
-  const uint32_t* toks = reinterpret_cast<const uint32_t*>(smem_raw + 128 + (A.nrd + 2) * 8);
-  double* wring = reinterpret_cast<double*>(smem_raw + 128 + tok_bytes(A.nrd));
+  const double* tokc = reinterpret_cast<const double*>(smem_raw + HDR);
+  const uint32_t* toks = reinterpret_cast<const uint32_t*>(smem_raw + HDR + (A.nrd + 2) * 8);
+  double* wring = reinterpret_cast<double*>(smem_raw + HDR + tok_bytes(A.nrd));
   double* rawbase = wring + (size_t)S * RW * SWP;
   double* cbase = rawbase + (size_t)W * S * NARR * SWP;
 
@@ -201,18 +211,22 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
   double* mycs = cbase + (size_t)warp * S * 2 * SW;  // last stage: k0 / k1 of the row this warp computes next
   const uint32_t mycbar = smem_addr(&bars[W + warp]);
   const uint32_t mycs_s = smem_addr(mycs);
+  const uint32_t rowbar0 = smem_addr(&bars[2 * W]);  // row-ready barrier of ring slot q at rowbar0 + 8q
   if (lane == 0) {
     mbar_init(mybar, 1);
     if (MODE == MODE_FINAL) mbar_init(mycbar, 1);
+    if (SB2_RD_P2P && warp == 0)
+      for (int q = 0; q < RW; ++q) mbar_init(rowbar0 + 8 * q, 1);
     mbar_fence_init();
   }
   // the token records move from their device buffer to shared memory once (first read after the first barrier)
   for (int i = threadIdx.x; i < A.nrd + 2; i += W * 32) {
     const Sb2RdTok t = A.rdtok[i];
-    reinterpret_cast<double*>(smem_raw + 128)[i] = t.c;
-    reinterpret_cast<uint32_t*>(smem_raw + 128 + (A.nrd + 2) * 8)[i] = t.code | (t.arg << 16);
+    reinterpret_cast<double*>(smem_raw + HDR)[i] = t.c;
+    reinterpret_cast<uint32_t*>(smem_raw + HDR + (A.nrd + 2) * 8)[i] = t.code | (t.arg << 16);
   }
   __syncwarp();
+  if (SB2_RD_P2P) __syncthreads();  // once: row barriers and token stream are in place
 
   // The last stage reads u and k2 of its own cells a second time for the combine, one batch after the bulk copy
   // staged them: those copies (and the k0 / k1 prefetches) ask L2 to keep the lines.
@@ -298,6 +312,8 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
         }
       }
       __syncwarp();
+      // the row is in the ring: the warps that compute the rows around it may go ahead
+      if (SB2_RD_P2P && lane == 0) mbar_arrive(rowbar0 + 8 * wslot);
     }
     // (3) the slot is free again: fetch the row of the next batch (in the prologue this is the first fetch of
     // the warps that had nothing to stage yet)
@@ -339,8 +355,21 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
       }
     }
 
-    __syncthreads();  // (4)
+    if (!SB2_RD_P2P) __syncthreads();  // (4)
     if (!compute) continue;
+    if (SB2_RD_P2P) {
+      // (4) rows srow - 1 and srow have been staged by other warps (srow + 1 by this one): wait for exactly those.  The
+      // k-th use of a ring slot completes phase k of its barrier.  Rows that turn out to need no arithmetic wait too:
+      // a warp may only re-stage a ring slot after the rows around the old content have been computed, and that
+      // ordering is carried from warp to warp by these waits.
+      const uint32_t q = (uint32_t)(srow - (yb - 1));  // >= 1
+      const uint32_t qc = q % RW, qd = (q - 1) % RW;
+      bool ok = mbar_wait(rowbar0 + 8 * qd, ((q - 1) / RW) & 1u);
+      ok = mbar_wait(rowbar0 + 8 * qc, (q / RW) & 1u) && ok;
+      if (!ok && A.dbg && lane == 0) {
+        if (atomicAdd(&A.dbg[0], 1u) == 0) { A.dbg[1] = blockIdx.x; A.dbg[2] = blockIdx.y; A.dbg[3] = warp; A.dbg[4] = (uint32_t)srow; A.dbg[5] = 99; A.dbg[6] = (uint32_t)yb; A.dbg[7] = (uint32_t)ye; }
+      }
+    }
 
     const int64_t idx0 = plane0 + (int64_t)srow * A.P + x0 + 2 * lane;  // + 64p for pair p
     if (cls == 2) {
@@ -688,7 +717,7 @@ template <int NS, int NP, int W, int MODE, int DEPTH, int MINB, bool D3>
 cudaError_t launch_variant(const Sb2RdArgs& a, cudaStream_t stream) {
   using G = Geo<NP, W>;
   const int narr = (MODE == MODE_FIRST) ? 1 : 2;
-  const size_t smem = 128 + tok_bytes(a.nrd) + sizeof(double) * ((size_t)a.S * G::RW * G::SWP + (size_t)W * a.S * narr * G::SWP +
+  const size_t smem = HDR + tok_bytes(a.nrd) + sizeof(double) * ((size_t)a.S * G::RW * G::SWP + (size_t)W * a.S * narr * G::SWP +
                                                                   (MODE == MODE_FINAL ? (size_t)W * a.S * 2 * G::SW : 0));
   static size_t configured = 0;
   if (smem > configured) {
