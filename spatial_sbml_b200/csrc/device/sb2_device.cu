@@ -384,13 +384,14 @@ void fill_stage_args(sb2_sim* sim, Sb2StageCore& a, int m, double dt, int row_be
   // rows per CTA: enough CTAs to fill the machine several times over, long enough strips to
   // amortise the two extra rows each CTA loads
   if (sim->rd_id >= 0) {
-    // a CTA walks its rows in batches of W.  Measured at 8192^2 (ms per step): 3, 4, 6, 8, 16, 32, 64 batches per tile →
-    // 3.53, 3.43, 3.33, 3.33, 3.40, 3.75, 4.31: short tiles keep the rows in flight close together in memory and the
-    // waves even, the prologue batch they pay for is cheap
+    // a CTA walks its rows in batches of W.  Measured at 8192^2 (ms per step): with the per-batch CTA barrier 3, 4, 6, 8,
+    // 16, 32, 64 batches per tile → 3.53, 3.43, 3.33, 3.33, 3.40, 3.75, 4.31; with row-ready barriers 4, 6, 8, 12, 16 →
+    // 3.13, 3.00, 2.97, 2.94, 2.99: short tiles keep the rows in flight close together in memory and the waves even,
+    // the prologue batch they pay for is cheap
     const int W = sim->rd.w;
     const int rows = sim->g.dim == 3 ? sim->g.ny : row_end - row_begin;
     const int planes = sim->g.dim == 3 ? row_end - row_begin : 1;
-    static const int rpb_batches = getenv("SB2_RD_BATCHES") ? atoi(getenv("SB2_RD_BATCHES")) : 8;
+    static const int rpb_batches = getenv("SB2_RD_BATCHES") ? atoi(getenv("SB2_RD_BATCHES")) : 12;
     int rpb = rpb_batches * W;
     while (rpb > W && (int64_t)sim->nstrips * planes * ((rows + rpb - 1) / rpb) < 148 * 6) rpb -= W;
     a.rows_per_block = rpb;
