@@ -211,8 +211,10 @@ def main():
             torch.cuda.synchronize()
 
     shard.run_steps(0, dt, W)
-    sync_all()
+    # the sampler (NVML init, thread start) costs rank 0 a few ms: set it up BEFORE the barrier, or the other ranks' timed
+    # regions start early and then include waiting for rank 0's first halo rows
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    sync_all()
     launches0 = shard.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()

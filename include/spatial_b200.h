@@ -206,6 +206,7 @@ SB2_API int sb2_species_view(sb2_sim* sim, int species, int which, sb2_field_vie
  * rows / planes next to a neighbouring slab (what the neighbours need next), 2 = the other owned rows. */
 SB2_API int sb2_begin_step(sb2_sim* sim, double t_arg, double dt, int time_slot);
 SB2_API int sb2_stage(sb2_sim* sim, int m, int phase);
+SB2_API int sb2_stage_on(sb2_sim* sim, int m, int phase, void* cuda_stream); /* the same on another stream (ordering: caller's events) */
 SB2_API int sb2_end_step(sb2_sim* sim);
 /* After sb2_begin_step: 1 when the RK combine of this step is fused into stage 3 (the new u is
  * written to view 5 by sb2_stage(3, ...)), 0 when sb2_end_step computes it in place. */

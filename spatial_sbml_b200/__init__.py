@@ -85,6 +85,7 @@ def _proto(lib):
         "sb2_species_view": (ci, [vp, ci, ci, C.POINTER(FieldView)]),
         "sb2_begin_step": (ci, [vp, cd, cd, ci]),
         "sb2_stage": (ci, [vp, ci, ci]),
+        "sb2_stage_on": (ci, [vp, ci, ci, vp]),
         "sb2_end_step": (ci, [vp]),
         "sb2_combine_is_fused": (ci, [vp]),
         "sb2_launch_count": (C.c_int64, [vp]),

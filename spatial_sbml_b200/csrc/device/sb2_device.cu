@@ -54,7 +54,9 @@ struct sb2_sim {
   double* d_tmp_face;   // CIP scratch
   Sb2StageCore base;
   uint32_t base_tok[SB2_MAX_TOKENS + 2];  // first-generation program (kernel parameter)
-  Sb2RdTok* d_rdtok;                      // rd_stage token records on the device
+  Sb2RdTok* d_rdtok;                      // rd_stage token records on the device: two buffers, used alternately
+  int rd_buf;                             // half of d_rdtok the current records live in
+  bool multi_stream;                      // stages have been launched on more than one stream (sb2_stage_on)
   std::vector<Sb2RdTok> rd_uploaded;      // what d_rdtok currently holds
   std::string err;
   int launches;
@@ -421,11 +423,16 @@ int launch_stage_rows(sb2_sim* sim, int m, double dt, int row_begin, int row_end
     Sb2RdTok end; end.code = 0; end.arg = 0; end.c = 0.0;
     cur.push_back(end); cur.push_back(end);
     if (cur.size() != sim->rd_uploaded.size() || memcmp(cur.data(), sim->rd_uploaded.data(), sizeof(Sb2RdTok) * cur.size()) != 0) {
-      e = cudaMemcpyAsync(sim->d_rdtok, cur.data(), sizeof(Sb2RdTok) * cur.size(), cudaMemcpyHostToDevice, sim->stream);  // pageable: staged before return
+      // new records go to the other half: kernels already queued keep reading the half they were launched with
+      sim->rd_buf ^= 1;
+      e = cudaMemcpyAsync(sim->d_rdtok + sim->rd_buf * (SB2_RD_MAX_TOKENS + 2), cur.data(), sizeof(Sb2RdTok) * cur.size(),
+                          cudaMemcpyHostToDevice, sim->stream);  // pageable source: staged before the call returns
       if (e != cudaSuccess) return cuda_fail(sim, e, "token upload");
+      // kernels of this stage may run on another stream: they must not start before the records have landed
+      if (sim->multi_stream) CK(cudaStreamSynchronize(sim->stream));
       sim->rd_uploaded.swap(cur);
     }
-    a.rdtok = sim->d_rdtok;
+    a.rdtok = sim->d_rdtok + sim->rd_buf * (SB2_RD_MAX_TOKENS + 2);
     if (sim->trace) fprintf(stderr, "[sb2] stage m=%d rows [%d,%d) rpb %d final %d carry %d\n", m, row_begin, row_end, a.rows_per_block, a.final, a.carry);
     ++sim->launches;
     e = sb2_rd_launch(a, sim->stream);
@@ -497,7 +504,7 @@ int sb2_create(const sb2_grid* grid, sb2_sim** out) {
   sim->k0_carry_valid = false; sim->d_tmp_face = NULL;
   sim->launches = 0; sim->in_step = false; sim->cur_dt = 0; sim->d_scratch = NULL;
   sim->rd_id = -1; sim->d_cls = NULL; sim->nstrips = 0; sim->d_dbg = NULL;
-  sim->h2d = NULL; sim->d2h = NULL; sim->ev_start = NULL; sim->d_rdtok = NULL;
+  sim->h2d = NULL; sim->d2h = NULL; sim->ev_start = NULL; sim->d_rdtok = NULL; sim->rd_buf = 0; sim->multi_stream = false;
   sim->trace = getenv("SB2_TRACE") != NULL;
   memset(&sim->base, 0, sizeof(sim->base));
   *out = sim;
@@ -724,7 +731,7 @@ int sb2_finalize(sb2_sim* sim) {
   b.rd_variant = sim->rd_id;
   if (sim->rd_id >= 0) {
     b.nrd = (int)sim->rdprog.size();
-    CK(cudaMalloc((void**)&sim->d_rdtok, sizeof(Sb2RdTok) * (SB2_RD_MAX_TOKENS + 2)));
+    CK(cudaMalloc((void**)&sim->d_rdtok, sizeof(Sb2RdTok) * (SB2_RD_MAX_TOKENS + 2) * 2));
     sim->rd_uploaded.clear();
     const int sw = 64 * sim->rd.np;
     if (sw + 4 > SB2_TAIL_PAD) return fail(sim, SB2_ERR_STATE, "strip wider than the tail pad of the field layout");
@@ -853,6 +860,18 @@ int sb2_stage(sb2_sim* sim, int m, int phase) {
     }
   }
   return SB2_OK;
+}
+
+// sb2_stage on another stream (cudaStream_t as void*): lets the caller run the edge rows and the interior rows of a
+// stage concurrently.  Ordering between the streams is the caller's business (events).
+int sb2_stage_on(sb2_sim* sim, int m, int phase, void* cuda_stream) {
+  if (!sim) return SB2_ERR_ARG;
+  cudaStream_t keep = sim->stream;
+  sim->multi_stream = true;
+  sim->stream = (cudaStream_t)cuda_stream;
+  const int rc = sb2_stage(sim, m, phase);
+  sim->stream = keep;
+  return rc;
 }
 
 int sb2_end_step(sb2_sim* sim) {

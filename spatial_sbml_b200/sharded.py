@@ -64,6 +64,7 @@ class ShardedSimulator(object):
         self.lib = load_library()
         self.compute = torch.cuda.current_stream()
         self.comm = torch.cuda.Stream()
+        self.edge = torch.cuda.Stream(priority=-1)  # the slab's edge rows run beside the interior kernel
         self.sim = SpatialSimulator(device=device, slab=(self.lo, self.hi) if self.world > 1 else None,
                                     stream=self.compute.cuda_stream)
         self.sim.initFromString(sbml, xdim, ydim, zdim)
@@ -90,6 +91,7 @@ class ShardedSimulator(object):
             # view 0 / 5 name "current" / "other" at creation time; track which buffer is current
             self.cur = 0
         self.time_slot_steps = 0
+        self.halo_ready = None
 
     def _u(self, s, current):
         which = 0 if (self.cur == 0) == current else 5
@@ -118,19 +120,33 @@ class ShardedSimulator(object):
         # the model of the sharded benchmarks does not use `time`; pass no time slot
         self._ck(lib.sb2_begin_step(h, float(step_index), float(dt), -1))
         fused = lib.sb2_combine_is_fused(h) == 1
-        pending = None
+        # Per stage: the two edge rows on their own stream (they need the neighbours' halo rows of the previous stage),
+        # the interior rows on the compute stream (they need only this rank's rows), the halo exchange of the new edge
+        # rows on the communication stream as soon as the edge kernel is done — all three overlap.
+        pending = self.halo_ready      # halos of u from the previous step (None at the first step)
+        prev_interior = None
+        prev_edge = None
         for m in range(4):
             if pending is not None:
-                self.compute.wait_event(pending)  # halos of k_{m-1} (and of u at m = 0) have arrived
-                pending = None
-            self._ck(lib.sb2_stage(h, m, 1))      # edge rows first ...
+                self.edge.wait_event(pending)
+            if prev_interior is not None:
+                self.edge.wait_event(prev_interior)
+            else:
+                self.edge.wait_stream(self.compute)
+            if prev_edge is not None:
+                self.compute.wait_event(prev_edge)
+            self._ck(lib.sb2_stage_on(h, m, 1, C.c_void_p(self.edge.cuda_stream)))
             ev = torch.cuda.Event()
-            ev.record(self.compute)
+            ev.record(self.edge)
+            prev_edge = ev
             if m < 3:
                 pending = self._exchange([self.views[(s, 1 + m)] for s in range(self.S)], ev)
             elif fused:
                 pending = self._exchange([self._u(s, current=False) for s in range(self.S)], ev)
-            self._ck(lib.sb2_stage(h, m, 2))      # ... then the interior while they travel
+            self._ck(lib.sb2_stage(h, m, 2))      # interior rows
+            prev_interior = torch.cuda.Event()
+            prev_interior.record(self.compute)
+        self.compute.wait_event(prev_edge)
         self._ck(lib.sb2_end_step(h))
         self.sim.deviceStateChanged()  # the host mirrors of the species are stale now
         if fused:
@@ -139,6 +155,7 @@ class ShardedSimulator(object):
             ev = torch.cuda.Event()
             ev.record(self.compute)
             pending = self._exchange([self._u(s, current=True) for s in range(self.S)], ev)
+        self.halo_ready = pending
         if pending is not None:
             self.compute.wait_event(pending)
 
