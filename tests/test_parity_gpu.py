@@ -268,3 +268,29 @@ def test_two_kernel_generations_agree_bit_for_bit_at_size(dims, dt, monkeypatch)
     for a, b in zip(out["rd"], out["gen1"]):
         assert np.isfinite(a).all() and a.std() > 0
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("dims", [(64, 64, 1), (65, 33, 1), (127, 9, 1), (129, 8, 1), (256, 7, 1), (63, 130, 1), (193, 17, 1), (20, 9, 7), (66, 10, 9)])
+def test_awkward_grid_sizes_against_the_restated_oracle(dims):
+    """Strip, tile and batch edges: widths around multiples of 64, tiles shorter than a batch, one-warp grids."""
+    import os
+    import sys
+    import spatial_sbml_b200 as sb
+    from spatial_sbml_b200 import synthetic
+    from conftest import REPO
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import rd_oracle
+    dt = 0.07 if dims[2] == 1 else 0.02
+    model = synthetic.turing(dims[0], dims[1], dims[2] if dims[2] > 1 else None)
+    host = sb.SpatialSimulator(host_only=True)
+    host.initFromString(model, *dims)
+    orc = rd_oracle.from_simulator(host, model, dims)
+    host.close()
+    sim = sb.SpatialSimulator()
+    sim.initFromString(model, *dims)
+    for t in range(4):
+        orc.one_step(t, dt)
+        sim.oneStep(t, dt)
+    for sp in ("species_1", "species_2"):
+        assert np.array_equal(sim.getVariableCompact(sp), orc.sp[sp].u), (dims, sp)
+    sim.close()
