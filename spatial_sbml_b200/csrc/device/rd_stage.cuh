@@ -96,7 +96,6 @@ __device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uin
                "l"(src), "r"(bytes), "r"(bar), "l"(policy)
                : "memory");
 }
-// Bounded wait: a copy that never lands (a bug) ends in wrong results and a failed test, not in a hung GPU.
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
   asm volatile(
@@ -110,15 +109,21 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return done;
 }
-__device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity) {
+// A wait that does not complete within ~0.2 s is a bug (a copy that never lands, a broken dependency chain).  With
+// debug words attached (SB2_DEBUG=1) the caller records where and carries on; otherwise the kernel traps: the launch
+// fails loudly at the next synchronisation instead of handing back fields computed from stale rows.
+__device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, bool may_trap) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity))
-    if (clock64() - t0 > 400000000LL) return false;  // ~0.2 s
+    if (clock64() - t0 > 400000000LL) {
+      if (may_trap) __trap();
+      return false;
+    }
   return true;
 }
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, bool may_trap) {
   if (mbar_try_wait(bar, parity)) return true;  // the copy was issued a whole batch ago: normally it has landed
-  return mbar_wait_slow(bar, parity);
+  return mbar_wait_slow(bar, parity, may_trap);
 }
 
 __host__ __device__ inline int tok_bytes(int nrd) { return ((nrd + 2) * 16 + 127) / 128 * 128; }
@@ -281,7 +286,7 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
 
     // (1) + (2): raw row → w ring
     if (wrow >= yb - 1 && wrow <= ye) {
-      if (!mbar_wait(mybar, parity) && A.dbg && lane == 0) {
+      if (!mbar_wait(mybar, parity, A.dbg == nullptr) && A.dbg && lane == 0) {
         if (atomicAdd(&A.dbg[0], 1u) == 0) { A.dbg[1] = blockIdx.x; A.dbg[2] = blockIdx.y; A.dbg[3] = warp; A.dbg[4] = (uint32_t)wrow; A.dbg[5] = parity; A.dbg[6] = (uint32_t)yb; A.dbg[7] = (uint32_t)ye; }
       }
       parity ^= 1;
@@ -327,7 +332,7 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
     // still has to wait for them and to request the next row
     auto combine_done = [&](bool waited) {
       if (MODE != MODE_FINAL) return;
-      if (!waited) { mbar_wait(mycbar, cparity); }
+      if (!waited) { mbar_wait(mycbar, cparity, A.dbg == nullptr); }
       cparity ^= 1;
       __syncwarp();
       if (srow + W < ye && elect_one()) issue_combine(srow + W);
@@ -364,8 +369,8 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
       // ordering is carried from warp to warp by these waits.
       const uint32_t q = (uint32_t)(srow - (yb - 1));  // >= 1
       const uint32_t qc = q % RW, qd = (q - 1) % RW;
-      bool ok = mbar_wait(rowbar0 + 8 * qd, ((q - 1) / RW) & 1u);
-      ok = mbar_wait(rowbar0 + 8 * qc, (q / RW) & 1u) && ok;
+      bool ok = mbar_wait(rowbar0 + 8 * qd, ((q - 1) / RW) & 1u, A.dbg == nullptr);
+      ok = mbar_wait(rowbar0 + 8 * qc, (q / RW) & 1u, A.dbg == nullptr) && ok;
       if (!ok && A.dbg && lane == 0) {
         if (atomicAdd(&A.dbg[0], 1u) == 0) { A.dbg[1] = blockIdx.x; A.dbg[2] = blockIdx.y; A.dbg[3] = warp; A.dbg[4] = (uint32_t)srow; A.dbg[5] = 99; A.dbg[6] = (uint32_t)yb; A.dbg[7] = (uint32_t)ye; }
       }
@@ -560,7 +565,7 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
     }
 
     // ---------------- diffusion (calcPDE.cpp:484-559) + output ----------------
-    if (MODE == MODE_FINAL) mbar_wait(mycbar, cparity);  // k0 / k1 of this row (requested one batch ago)
+    if (MODE == MODE_FINAL) mbar_wait(mycbar, cparity, A.dbg == nullptr);  // k0 / k1 of this row (requested one batch ago)
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
       if (s < S) {
