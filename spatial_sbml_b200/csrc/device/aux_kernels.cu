@@ -535,6 +535,14 @@ int sb2_build_transport(const sb2_grid& g, int64_t P, int64_t PL, int64_t first,
     err = std::string("membrane transport: ") + cudaGetErrorString(e);
     return SB2_ERR_CUDA;
   }
+  // the program itself: uploaded once (it never changes; the constants it reads travel with every launch)
+  std::vector<uint32_t> tokv(out.tok);
+  std::vector<int32_t> opv(out.tok_operand);
+  if (tokv.empty()) { tokv.push_back(0); opv.push_back(-1); }
+  if ((e = to_device(&out.d_tok, tokv, stream)) != cudaSuccess || (e = to_device(&out.d_operand, opv, stream)) != cudaSuccess) {
+    err = std::string("membrane transport: ") + cudaGetErrorString(e);
+    return SB2_ERR_CUDA;
+  }
   return SB2_OK;
 }
 
@@ -542,6 +550,7 @@ void sb2_free_transport(Sb2MemTransport& t) {
   cudaFree(t.d_near); cudaFree(t.d_far); cudaFree(t.d_fieldval); cudaFree(t.d_rate);
   cudaFree(t.d_group_start); cudaFree(t.d_group_species); cudaFree(t.d_group_cell);
   cudaFree(t.d_entry_pt); cudaFree(t.d_entry_coef); cudaFree(t.d_entry_delta); cudaFree(t.d_entry_sign);
+  cudaFree(t.d_tok); cudaFree(t.d_operand);
 }
 
 cudaError_t sb2_launch_transport(const Sb2MemTransport& t, const sb2_grid& g, const double* const* u,
@@ -549,26 +558,10 @@ cudaError_t sb2_launch_transport(const Sb2MemTransport& t, const sb2_grid& g, co
                                  double cdt, cudaStream_t stream, int* launches) {
   (void)g;
   if (t.npts == 0) return cudaSuccess;
-  // program upload (a few dozen bytes) — stream ordered, from pageable memory
-  static thread_local uint32_t* d_tok = NULL;
-  static thread_local int32_t* d_operand = NULL;
-  static thread_local int cap = 0;
-  if (cap < t.ntoks) {
-    cudaFree(d_tok); cudaFree(d_operand);
-    cap = std::max(64, t.ntoks);
-    cudaError_t e = cudaMalloc((void**)&d_tok, sizeof(uint32_t) * cap);
-    if (e != cudaSuccess) return e;
-    e = cudaMalloc((void**)&d_operand, sizeof(int32_t) * cap);
-    if (e != cudaSuccess) return e;
-  }
-  cudaError_t e = cudaMemcpyAsync(d_tok, t.tok.data(), sizeof(uint32_t) * t.ntoks, cudaMemcpyHostToDevice, stream);
-  if (e != cudaSuccess) return e;
-  e = cudaMemcpyAsync(d_operand, t.tok_operand.data(), sizeof(int32_t) * t.ntoks, cudaMemcpyHostToDevice, stream);
-  if (e != cudaSuccess) return e;
-
+  cudaError_t e;
   MtEvalArgs a;
   a.npts = t.npts; a.ntoks = t.ntoks; a.m = m; a.cdt = cdt;
-  a.tok = d_tok; a.tok_operand = d_operand;
+  a.tok = t.d_tok; a.tok_operand = t.d_operand;
   a.near_cell = t.d_near; a.far_cell = t.d_far; a.fieldval = t.d_fieldval; a.rate = t.d_rate;
   for (int s = 0; s < SB2_MAX_SPECIES; ++s) { a.u[s] = NULL; a.kprev[s] = NULL; }
   for (size_t i = 0; i < t.tok.size(); ++i)

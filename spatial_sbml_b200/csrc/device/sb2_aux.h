@@ -60,6 +60,8 @@ struct Sb2MemTransport {
   // program (host copy is passed by value to the kernel)
   std::vector<uint32_t> tok;        // kind | op<<8 | slot<<16
   std::vector<int32_t> tok_operand; // per token: operand-table row (VAR / FIELD tokens), else -1
+  uint32_t* d_tok;    // device copy of tok
+  int32_t* d_operand; // device copy of tok_operand
   int32_t* d_near;    // [n_operand_rows][npts] padded cell index or -1
   int32_t* d_far;     // [n_operand_rows][npts]
   double* d_fieldval; // [n_operand_rows][npts] value of FIELD operands at the membrane point

@@ -73,6 +73,12 @@ struct sb2_sim {
   cudaStream_t h2d, d2h;
   std::vector<cudaEvent_t> ev_up, ev_done;
   cudaEvent_t ev_start;
+  // sb2_step: CUDA graph of two consecutive steps (one per buffer parity) for small, launch-latency-bound grids
+  cudaGraphExec_t gexec[2];
+  double g_dt[2];
+  uint64_t g_version[2];
+  int g_launches[2];
+  uint64_t version;  // bumped by everything that can change a kernel argument (constants, uploads that allocate)
   std::vector<Sb2RdTok> rdprog;  // lowered token records (constants patched per launch from rdslot)
   std::vector<int> rdslot;       // constants-table slot of each record's inline constant, -1 = none
   uint32_t* d_dbg;    // SB2_DEBUG=1: device debug words, checked after every stage launch
@@ -505,6 +511,7 @@ int sb2_create(const sb2_grid* grid, sb2_sim** out) {
   sim->launches = 0; sim->in_step = false; sim->cur_dt = 0; sim->d_scratch = NULL;
   sim->rd_id = -1; sim->d_cls = NULL; sim->nstrips = 0; sim->d_dbg = NULL;
   sim->h2d = NULL; sim->d2h = NULL; sim->ev_start = NULL; sim->d_rdtok = NULL; sim->rd_buf = 0; sim->multi_stream = false;
+  sim->gexec[0] = sim->gexec[1] = NULL; sim->version = 1;
   sim->trace = getenv("SB2_TRACE") != NULL;
   memset(&sim->base, 0, sizeof(sim->base));
   *out = sim;
@@ -528,6 +535,7 @@ void sb2_destroy(sb2_sim* sim) {
   if (sim->d_scratch) cudaFree(sim->d_scratch);
   if (sim->d_cls) cudaFree(sim->d_cls);
   if (sim->d_rdtok) cudaFree(sim->d_rdtok);
+  for (int p = 0; p < 2; ++p) if (sim->gexec[p]) cudaGraphExecDestroy(sim->gexec[p]);
   if (sim->h2d) cudaStreamDestroy(sim->h2d);
   if (sim->d2h) cudaStreamDestroy(sim->d2h);
   if (sim->ev_start) cudaEventDestroy(sim->ev_start);
@@ -541,6 +549,7 @@ void sb2_destroy(sb2_sim* sim) {
 
 int sb2_set_stream(sb2_sim* sim, void* cuda_stream) {
   if (!sim) return SB2_ERR_ARG;
+  ++sim->version;
   cudaStreamSynchronize(sim->stream);
   if (sim->own_stream) { cudaStreamDestroy(sim->stream); sim->own_stream = false; }
   sim->stream = (cudaStream_t)cuda_stream;
@@ -596,6 +605,7 @@ int sb2_add_field(sb2_sim* sim, const double* values) {
 
 int sb2_set_constants(sb2_sim* sim, const double* table, int n) {
   if (!sim || (!table && n > 0) || n < 0) return fail(sim, SB2_ERR_ARG, "bad constants table");
+  ++sim->version;
   if (n > SB2_MAX_CONSTS - sim->n_internal_consts) return fail(sim, SB2_ERR_LIMIT, "constants table full");
   memcpy(sim->consts, table, sizeof(double) * n);
   if (n > sim->n_user_consts) sim->n_user_consts = n;
@@ -604,6 +614,7 @@ int sb2_set_constants(sb2_sim* sim, const double* table, int n) {
 
 int sb2_set_constant(sb2_sim* sim, int slot, double value) {
   if (!sim) return SB2_ERR_ARG;
+  ++sim->version;
   if (slot < 0 || slot >= SB2_MAX_CONSTS - sim->n_internal_consts) return fail(sim, SB2_ERR_ARG, "constant slot out of range");
   sim->consts[slot] = value;
   if (slot >= sim->n_user_consts) sim->n_user_consts = slot + 1;
@@ -933,14 +944,70 @@ int sb2_end_step(sb2_sim* sim) {
   return SB2_OK;
 }
 
+namespace {
+int one_plain_step(sb2_sim* sim, double t_arg, double dt, int time_slot) {
+  int rc = sb2_begin_step(sim, t_arg, dt, time_slot);
+  if (rc) return rc;
+  for (int m = 0; m < 4; ++m) if ((rc = sb2_stage(sim, m, 0))) return rc;
+  return sb2_end_step(sim);
+}
+}  // namespace
+
 int sb2_step(sb2_sim* sim, double t_arg, double t_incr, double dt, int nsteps, int time_slot) {
   if (!sim || !sim->finalized) return fail(sim, SB2_ERR_STATE, "simulator not finalized");
-  for (int i = 0; i < nsteps; ++i) {
-    int rc = sb2_begin_step(sim, t_arg + i * t_incr, dt, time_slot);
-    if (rc) return rc;
-    for (int m = 0; m < 4; ++m) if ((rc = sb2_stage(sim, m, 0))) return rc;
-    if ((rc = sb2_end_step(sim))) return rc;
+  int i = 0, rc;
+  // Small grids are bound by launch latency (a step is 4 - 13 tiny kernels): run two ordinary steps (token records
+  // uploaded, carried-flux state settled), capture the next two - one per parity of the u double buffer - into a CUDA
+  // graph and replay it.  Only for models whose steps are all alike: no `time` symbol, nothing reading debug words.
+  static const bool no_graph = getenv("SB2_NO_GRAPH") != NULL;
+  const bool graphable = !no_graph && sim->own_stream && !sim->d_dbg && !sim->trace && time_slot < 0 &&
+                         ncells(sim) <= (1 << 18) && nsteps >= 12;
+  if (graphable) {
+    for (; i < 2; ++i) if ((rc = one_plain_step(sim, t_arg + i * t_incr, dt, time_slot))) return rc;
+    const int pairs = (nsteps - i) / 2;
+    const int par = sim->species.empty() ? 0 : sim->species[0].cur;
+    bool fresh = false;
+    if (!sim->gexec[par] || sim->g_dt[par] != dt || sim->g_version[par] != sim->version) {
+      if (sim->gexec[par]) { cudaGraphExecDestroy(sim->gexec[par]); sim->gexec[par] = NULL; }
+      // host-side state the two captured steps will advance
+      std::vector<int> cur0(sim->species.size());
+      for (size_t s = 0; s < sim->species.size(); ++s) cur0[s] = sim->species[s].cur;
+      const bool carry_valid0 = sim->k0_carry_valid;
+      const int launches0 = sim->launches;
+      cudaGraph_t graph = NULL;
+      cudaError_t e = cudaStreamBeginCapture(sim->stream, cudaStreamCaptureModeThreadLocal);
+      rc = SB2_OK;
+      if (e == cudaSuccess) {
+        for (int k = 0; k < 2 && !rc; ++k) rc = one_plain_step(sim, t_arg + (i + k) * t_incr, dt, time_slot);
+        e = cudaStreamEndCapture(sim->stream, &graph);
+      }
+      if (e == cudaSuccess && !rc && graph) e = cudaGraphInstantiate(&sim->gexec[par], graph, 0);
+      if (graph) cudaGraphDestroy(graph);
+      if (e != cudaSuccess || rc || !sim->gexec[par]) {
+        // not capturable after all: put the host state back and take the ordinary path
+        cudaGetLastError();
+        sim->gexec[par] = NULL;
+        for (size_t s = 0; s < sim->species.size(); ++s) sim->species[s].cur = cur0[s];
+        sim->k0_carry_valid = carry_valid0;
+        sim->launches = launches0;
+        sim->in_step = false;
+      } else {
+        sim->g_dt[par] = dt; sim->g_version[par] = sim->version; sim->g_launches[par] = sim->launches - launches0;
+        fresh = true;  // the host state already stands two steps further
+      }
+    }
+    if (sim->gexec[par] && pairs > 0) {
+      for (int r = 0; r < pairs; ++r) CK(cudaGraphLaunch(sim->gexec[par], sim->stream));
+      sim->launches += sim->g_launches[par] * (pairs - (fresh ? 1 : 0));
+      i += 2 * pairs;
+    } else if (fresh) {
+      // captured but nothing to replay (cannot happen with nsteps >= 12): execute the captured pair once
+      CK(cudaGraphLaunch(sim->gexec[par], sim->stream));
+      i += 2;
+    }
   }
+  for (; i < nsteps; ++i)
+    if ((rc = one_plain_step(sim, t_arg + i * t_incr, dt, time_slot))) return rc;
   return SB2_OK;
 }
 
@@ -1061,6 +1128,7 @@ int sb2_upload_faces(sb2_sim* sim, int species, int axis, const double* in) {
   cudaSetDevice(sim->g.device);
   Sb2Species& sp = sim->species[species];
   int rc;
+  ++sim->version;
   if (!sp.faces[axis] && (rc = alloc_field(sim, &sp.faces[axis]))) return rc;
   if ((rc = upload_interior<double>(sim, sp.faces[axis], in))) return rc;
   CK(cudaStreamSynchronize(sim->stream));

@@ -1,5 +1,9 @@
-"""ms per oneStep of the example models (BASELINE configs 1-4) on the GPU: python tools/bench_examples.py [steps]"""
+"""The reference's example models (BASELINE configs 1-4) and small synthetic grids: µs per oneStep and cell-updates/s on
+the GPU, next to the reference's own serial CPU step (oracle/_ref/ref_driver) timed in the same run on the same box.
+usage: python tools/bench_examples.py [gpu steps] [--json out.json]"""
+import json
 import os
+import subprocess
 import sys
 import time
 
@@ -9,13 +13,17 @@ import numpy as np
 import torch
 import spatial_sbml_b200 as sb
 
-steps = int(sys.argv[1]) if len(sys.argv) > 1 else 400
-for case in ("turing_tiny", "turing_tiny_cl", "brusselator_300", "fish_300", "advection", "transport", "syn_turing_3d"):
+steps = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 400
+out_json = sys.argv[sys.argv.index("--json") + 1] if "--json" in sys.argv else None
+DRIVER = os.path.join(REPO, "oracle", "_ref", "ref_driver")
+rows = []
+for case in ("turing_tiny", "turing_tiny_cl", "turing_blob", "brusselator_300", "fish_300", "advection", "transport", "syn_turing_3d"):
     g = np.load(os.path.join(REPO, "tests", "golden", case + ".npz"))
     nx, ny, nz = [int(v) for v in g["dims"]]
     dt = float(g["dt"])
+    model = os.path.join(REPO, "tests", "golden", "models", case + ".xml")
     sim = sb.SpatialSimulator()
-    sim.initFromFile(os.path.join(REPO, "tests", "golden", "models", case + ".xml"), nx, ny, nz)
+    sim.initFromFile(model, nx, ny, nz)
     sim.runSteps(0, dt, 20)
     torch.cuda.synchronize()
     l0 = sim.getDeviceLaunchCount()
@@ -24,6 +32,21 @@ for case in ("turing_tiny", "turing_tiny_cl", "brusselator_300", "fish_300", "ad
     sim.getVariableCompact(str(g["species"][0]))  # forces completion
     t1 = time.time()
     cells = sim.getNumDomainCells()
-    print("%-16s %4dx%4dx%3d  %7.1f us/step  %5.1f launches/step  %8.2f M cell-updates/s" % (
-        case, nx, ny, nz, 1e6 * (t1 - t0) / steps, (sim.getDeviceLaunchCount() - l0) / steps, cells * steps / (t1 - t0) / 1e6), flush=True)
+    gpu_us = 1e6 * (t1 - t0) / steps
+    launches = (sim.getDeviceLaunchCount() - l0) / steps
     sim.close()
+    cpu = None
+    if os.path.exists(DRIVER):
+        csteps = max(3, min(200, int(2.0e6 * 3.0 / max(cells, 1))))  # about 3 s of CPU work
+        r = subprocess.run([DRIVER, "time", model, str(nx), str(ny), str(nz), repr(dt), "2", str(csteps)], capture_output=True, text=True)
+        line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if line:
+            cpu = json.loads(line[-1])
+    cpu_us = 1e6 * cpu["seconds"] / cpu["steps"] if cpu else float("nan")
+    rows.append({"case": case, "dims": [nx, ny, nz], "cells": int(cells), "gpu_us_per_step": gpu_us, "launches_per_step": launches,
+                 "gpu_cell_updates_per_s": cells / (gpu_us * 1e-6), "cpu_us_per_step": cpu_us,
+                 "cpu_cell_updates_per_s": cells / (cpu_us * 1e-6) if cpu else None, "speedup": cpu_us / gpu_us if cpu else None})
+    print("%-16s %4dx%4dx%3d  GPU %8.1f us/step (%4.1f launches) %9.2f M cu/s | reference CPU (1 thread) %10.1f us/step %6.2f M cu/s | x%.0f" % (
+        case, nx, ny, nz, gpu_us, launches, cells / gpu_us, cpu_us, cells / cpu_us if cpu else 0.0, cpu_us / gpu_us if cpu else 0.0), flush=True)
+if out_json:
+    json.dump({"host_cores": os.cpu_count(), "rows": rows}, open(out_json, "w"), indent=1)
