@@ -44,6 +44,7 @@
 #define SB2_RD_STAGE_CUH_
 #include "sb2_internal.h"
 #include "sb2_ops.cuh"
+#include <type_traits>
 
 namespace {
 namespace rd {
@@ -574,65 +575,85 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
         const double* cur = base + slot_c * SWP;
         const double* up = base + slot_u * SWP;
         const double* dn = base + slot_d * SWP;
-        if (cls == 1 && (sp.fastpath || !sp.has_diff)) {
-          // every cell is an interior cell: straight-line 5-point stencil, additions in the reference's
-          // order Xp, Xm, Yp, Ym
+        // Uniform coefficients, no division by dx^2: straight-line stencil, additions in the reference's order Xp, Xm, Yp,
+        // Ym (, Zp, Zm).  MASKED = false: every cell of the strip row is an interior cell, no per-cell test at all.
+        // MASKED = true (mixed strip rows): the same arithmetic, every addition under a predicate built from the cell's
+        // flag byte, outputs selected by the domain bit (neighbour values outside a domain are finite, never used).
+        auto straight = [&](auto masked_tag) {
+          constexpr bool MASKED = decltype(masked_tag)::value;
           const double dcx = sp.dconst[0], dcy = sp.dconst[1];
           double2 cu[NP], ck0[NP], ck1[NP], ck2[NP];
           if (MODE == MODE_FINAL) {
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
               const int64_t i = idx0 + p * 64;
-              cu[p] = *reinterpret_cast<const double2*>(sp.u + i);        // L2 hits: staged through L2 one batch ago
-              ck2[p] = *reinterpret_cast<const double2*>(sp.kprev + i);
+              cu[p] = ck2[p] = make_double2(0.0, 0.0);
+              if (!MASKED || active[p]) {
+                cu[p] = *reinterpret_cast<const double2*>(sp.u + i);        // L2 hits: staged through L2 one batch ago
+                ck2[p] = *reinterpret_cast<const double2*>(sp.kprev + i);
+              }
               ck0[p] = *reinterpret_cast<const double2*>(mycs + (s * 2) * SW + p * 64 + 2 * lane);
               ck1[p] = *reinterpret_cast<const double2*>(mycs + (s * 2 + 1) * SW + p * 64 + 2 * lane);
             }
           }
 #pragma unroll
           for (int p = 0; p < NP; ++p) {
+            const uint32_t f0 = MASKED ? (fl[2 * p] >> (8 * sp.geo)) & 0xffu : (uint32_t)SB2_F_DOMAIN;
+            const uint32_t f1 = MASKED ? (fl[2 * p + 1] >> (8 * sp.geo)) & 0xffu : (uint32_t)SB2_F_DOMAIN;
+#define RD_ADD(acc_, f_, bit_, term_) if (!MASKED || ((f_) & (SB2_F_DOMAIN | (bit_))) == SB2_F_DOMAIN) acc_ = dadd(acc_, term_)
             double a0 = acc[s][2 * p], a1 = acc[s][2 * p + 1];
             if (sp.has_diff) {
               const double2 wc = *reinterpret_cast<const double2*>(cur + p * 64);
               const double wl = cur[p * 64 - 1], wr = cur[p * 64 + 2];
               const double2 wu = *reinterpret_cast<const double2*>(up + p * 64);
               const double2 wd = *reinterpret_cast<const double2*>(dn + p * 64);
-              a0 = dadd(a0, dmul(dcx, dsub(wc.y, wc.x)));
-              a0 = dadd(a0, dmul(dcx, dsub(wl, wc.x)));
-              a0 = dadd(a0, dmul(dcy, dsub(wu.x, wc.x)));
-              a0 = dadd(a0, dmul(dcy, dsub(wd.x, wc.x)));
-              a1 = dadd(a1, dmul(dcx, dsub(wr, wc.y)));
-              a1 = dadd(a1, dmul(dcx, dsub(wc.x, wc.y)));
-              a1 = dadd(a1, dmul(dcy, dsub(wu.y, wc.y)));
-              a1 = dadd(a1, dmul(dcy, dsub(wd.y, wc.y)));
+              RD_ADD(a0, f0, SB2_F_XP, dmul(dcx, dsub(wc.y, wc.x)));
+              RD_ADD(a0, f0, SB2_F_XM, dmul(dcx, dsub(wl, wc.x)));
+              RD_ADD(a0, f0, SB2_F_YP, dmul(dcy, dsub(wu.x, wc.x)));
+              RD_ADD(a0, f0, SB2_F_YM, dmul(dcy, dsub(wd.x, wc.x)));
+              RD_ADD(a1, f1, SB2_F_XP, dmul(dcx, dsub(wr, wc.y)));
+              RD_ADD(a1, f1, SB2_F_XM, dmul(dcx, dsub(wc.x, wc.y)));
+              RD_ADD(a1, f1, SB2_F_YP, dmul(dcy, dsub(wu.y, wc.y)));
+              RD_ADD(a1, f1, SB2_F_YM, dmul(dcy, dsub(wd.y, wc.y)));
               if (D3) {  // Zp, Zm
                 const double dcz = sp.dconst[2];
                 const int64_t i = idx0 + p * 64;
-                double2 wzp = *reinterpret_cast<const double2*>(sp.u + i + A.PL);
-                double2 wzm = *reinterpret_cast<const double2*>(sp.u + i - A.PL);
-                if (MODE != MODE_FIRST) {
-                  const double2 kzp = *reinterpret_cast<const double2*>(sp.kprev + i + A.PL);
-                  const double2 kzm = *reinterpret_cast<const double2*>(sp.kprev + i - A.PL);
-                  wzp.x = dadd(wzp.x, dmul(A.cdt, kzp.x)); wzp.y = dadd(wzp.y, dmul(A.cdt, kzp.y));
-                  wzm.x = dadd(wzm.x, dmul(A.cdt, kzm.x)); wzm.y = dadd(wzm.y, dmul(A.cdt, kzm.y));
+                double2 wzp = make_double2(0.0, 0.0), wzm = wzp;
+                if (!MASKED || active[p]) {
+                  wzp = *reinterpret_cast<const double2*>(sp.u + i + A.PL);
+                  wzm = *reinterpret_cast<const double2*>(sp.u + i - A.PL);
+                  if (MODE != MODE_FIRST) {
+                    const double2 kzp = *reinterpret_cast<const double2*>(sp.kprev + i + A.PL);
+                    const double2 kzm = *reinterpret_cast<const double2*>(sp.kprev + i - A.PL);
+                    wzp.x = dadd(wzp.x, dmul(A.cdt, kzp.x)); wzp.y = dadd(wzp.y, dmul(A.cdt, kzp.y));
+                    wzm.x = dadd(wzm.x, dmul(A.cdt, kzm.x)); wzm.y = dadd(wzm.y, dmul(A.cdt, kzm.y));
+                  }
                 }
-                a0 = dadd(a0, dmul(dcz, dsub(wzp.x, wc.x)));
-                a0 = dadd(a0, dmul(dcz, dsub(wzm.x, wc.x)));
-                a1 = dadd(a1, dmul(dcz, dsub(wzp.y, wc.y)));
-                a1 = dadd(a1, dmul(dcz, dsub(wzm.y, wc.y)));
+                RD_ADD(a0, f0, SB2_F_ZP, dmul(dcz, dsub(wzp.x, wc.x)));
+                RD_ADD(a0, f0, SB2_F_ZM, dmul(dcz, dsub(wzm.x, wc.x)));
+                RD_ADD(a1, f1, SB2_F_ZP, dmul(dcz, dsub(wzp.y, wc.y)));
+                RD_ADD(a1, f1, SB2_F_ZM, dmul(dcz, dsub(wzm.y, wc.y)));
               }
             }
+#undef RD_ADD
+            const bool in0 = !MASKED || (f0 & SB2_F_DOMAIN), in1 = !MASKED || (f1 & SB2_F_DOMAIN);
+            if (MASKED && !active[p]) continue;
             if (MODE != MODE_FINAL) {
-              *reinterpret_cast<double2*>(sp.kout + idx0 + p * 64) = make_double2(a0, a1);
+              *reinterpret_cast<double2*>(sp.kout + idx0 + p * 64) = make_double2(in0 ? a0 : 0.0, in1 ? a1 : 0.0);
             } else {
               // value += dt*(k0 + 2.0*k1 + 2.0*k2 + k3)/6.0, spatialsimulator.cpp:1535
               double inc[2];
               inc[0] = dmul(A.dt, dadd(dadd(dadd(ck0[p].x, dmul(2.0, ck1[p].x)), dmul(2.0, ck2[p].x)), a0));
               inc[1] = dmul(A.dt, dadd(dadd(dadd(ck0[p].y, dmul(2.0, ck1[p].y)), dmul(2.0, ck2[p].y)), a1));
               div6_batch<2>(inc);
-              *reinterpret_cast<double2*>(sp.u_out + idx0 + p * 64) = make_double2(dadd(cu[p].x, inc[0]), dadd(cu[p].y, inc[1]));
+              *reinterpret_cast<double2*>(sp.u_out + idx0 + p * 64) =
+                  make_double2(in0 ? dadd(cu[p].x, inc[0]) : cu[p].x, in1 ? dadd(cu[p].y, inc[1]) : cu[p].y);
             }
           }
+        };
+        if (sp.fastpath || !sp.has_diff) {
+          if (cls == 1) straight(std::false_type());
+          else straight(std::true_type());
           continue;
         }
         // general path: per-cell domain / boundary flags, field-valued coefficients, dx^2 != 1.  Every stencil term

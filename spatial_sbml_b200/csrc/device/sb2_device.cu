@@ -753,6 +753,7 @@ int sb2_finalize(sb2_sim* sim) {
     for (int g = 0; g < b.G; ++g) fl[g] = sim->d_flags[g];
     cudaError_t ce = sb2_rd_classify(fl, b.G, sim->g.nx, sim->g.ny, sim->g.nz, sim->P, sim->PL, sim->first, sw, sim->d_cls, sim->nstrips, sim->stream);
     if (ce != cudaSuccess) return cuda_fail(sim, ce, "strip classification kernel");
+    if (getenv("SB2_RD_ALL_GENERAL")) CK(cudaMemsetAsync(sim->d_cls, 0, (size_t)sim->nstrips * nrows, sim->stream));  // experiments: per-cell flag path everywhere
     b.cls = sim->d_cls;
     b.nstrips = sim->nstrips;
     if (getenv("SB2_DEBUG")) {
