@@ -57,7 +57,7 @@ class ClockSampler(object):
     """SM clock and throttle reasons sampled through NVML from a thread while the timed region runs
     (an external `nvidia-smi -lms` poller was measured to slow the kernels themselves down)."""
 
-    def __init__(self, index, period=0.05):
+    def __init__(self, index, period=0.01):
         import threading
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self.stop_flag = False
