@@ -105,16 +105,16 @@ class ClockSampler(object):
                 "samples": len(self.samples)}
 
 
-def run_reference_cpu(n, warmup, steps):
+def run_reference_cpu(n, warmup, steps, model="turing", dt=DT):
     """The reference's serial CPU step on an n x n sample of the workload; returns (cell-updates/s, info)."""
     from spatial_sbml_b200 import synthetic
     if not os.path.exists(REF_DRIVER):
         return None, "oracle/_ref/ref_driver is not built"
     path = tempfile.mktemp(suffix=".xml")
     with open(path, "w") as f:
-        f.write(synthetic.turing(n, n))
+        f.write(getattr(synthetic, model)(n, n))
     try:
-        r = subprocess.run([REF_DRIVER, "time", path, str(n), str(n), "1", repr(DT), str(warmup), str(steps)],
+        r = subprocess.run([REF_DRIVER, "time", path, str(n), str(n), "1", repr(dt), str(warmup), str(steps)],
                            capture_output=True, text=True, timeout=1500)
         line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
         return json.loads(line), None
@@ -122,6 +122,10 @@ def run_reference_cpu(n, warmup, steps):
         return None, "reference run failed: %r" % (e,)
     finally:
         os.remove(path)
+
+
+def synthetic_model(name):
+    return lambda synthetic: getattr(synthetic, name)
 
 
 def pick_sample_n(total_steps, budget_s=100.0):
@@ -139,6 +143,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=int(os.environ.get("BENCH_N", "8192")))
     ap.add_argument("--dim", type=int, default=2, choices=[2, 3], help="3: the n^3 variant of the workload (default n 512), z-slabs")
+    ap.add_argument("--model", default="turing", choices=["turing", "brusselator"],
+                    help="synthetic model (the headline metric is quoted on turing; brusselator: examples/The_Brusselator.xml kinetics, dt 0.1)")
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -149,27 +155,33 @@ def main():
     if args.dim == 3 and n == 8192:
         n = 512
     dt = DT if args.dim == 2 else 0.02  # 3-D: six neighbours, D = 4 → explicit stability limit dx^2 / (2 d D) = 0.0208
+    make_model = synthetic_model(args.model)
+    names = ["species_1", "species_2"] if args.model == "turing" else ["X", "Y"]
+    if args.model == "brusselator":
+        dt = 0.1 if args.dim == 2 else 0.05
+    label = "Turing (examples/turing.xml kinetics)" if args.model == "turing" else "Brusselator (examples/The_Brusselator.xml kinetics)"
     if args.dim == 3:
-        config = {"workload": "synthetic Turing (examples/turing.xml kinetics + z axis) %dx%dx%d cells per GPU, 2 species, fp64, dt %.2f, RK4" % (n, n, n, dt),
+        config = {"workload": "synthetic %s + z axis, %dx%dx%d cells per GPU, 2 species, fp64, dt %.2f, RK4" % (label, n, n, n, dt),
                   "grid": [n, n, n * world], "cells_per_gpu": n ** 3,
                   "parallelism": "z-slabs x%d, NCCL halo exchange per RK stage" % world if world > 1 else "1 GPU",
                   "l2": "per-step working set %.1f GB per GPU, far larger than the 126 MB L2 (no flush needed)" % (6 * S * n ** 3 * 8 / 1e9)}
     else:
-      config = {"workload": "synthetic Turing (examples/turing.xml kinetics) %dx%d cells per GPU, 2 species, fp64, dt %.2f, RK4" % (n, n, DT),
-              "grid": [n, n * world], "cells_per_gpu": n * n, "parallelism": "y-slabs x%d, NCCL halo exchange per RK stage" % world if world > 1 else "1 GPU",
-              "l2": "per-step working set %.1f GB per GPU, far larger than the 126 MB L2 (no flush needed)" % (6 * S * n * n * 8 / 1e9)}
+        config = {"workload": "synthetic %s %dx%d cells per GPU, 2 species, fp64, dt %.2f, RK4" % (label, n, n, dt),
+                  "grid": [n, n * world], "cells_per_gpu": n * n,
+                  "parallelism": "y-slabs x%d, NCCL halo exchange per RK stage" % world if world > 1 else "1 GPU",
+                  "l2": "per-step working set %.1f GB per GPU, far larger than the 126 MB L2 (no flush needed)" % (6 * S * n * n * 8 / 1e9)}
 
     if args.impl == "reference":
         if rank != 0:
             return
         total = args.steps + args.warmup
         sn = pick_sample_n(total)
-        res, err = run_reference_cpu(sn, args.warmup, args.steps)
+        res, err = run_reference_cpu(sn, args.warmup, args.steps, args.model, dt if args.dim == 2 else (DT if args.model == "turing" else 0.1))
         if res is None:
             print(json.dumps({"impl": "reference", "unavailable": err}))
             return
         v = res["cell_updates_per_s"]
-        sample = "%dx%d cells of the same synthetic Turing model, %d timed oneStep calls after %d warm-up, 1 thread (the reference is serial)" % (sn, sn, args.steps, args.warmup)
+        sample = "%dx%d cells of the same synthetic model (2-D), %d timed oneStep calls after %d warm-up, 1 thread (the reference is serial)" % (sn, sn, args.steps, args.warmup)
         print(json.dumps({
             "impl": "reference", "metric": "cell-updates/sec", "value": v, "unit": "cell-updates/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * res["seconds"] / max(res["steps"], 1),
@@ -196,10 +208,10 @@ def main():
 
     t_init = time.time()
     if args.dim == 3:
-        model = synthetic.turing(n, n, n * world)
+        model = make_model(synthetic)(n, n, n * world)
         shard = ShardedSimulator(model, n, n, n * world, dim=3, device=local_rank)
     else:
-        model = synthetic.turing(n, n * world)
+        model = make_model(synthetic)(n, n * world)
         shard = ShardedSimulator(model, n, n * world, 1, dim=2, device=local_rank)
     init_s = time.time() - t_init
     cells = shard.num_domain_cells()
@@ -236,7 +248,7 @@ def main():
     value = cells_total * K / (ms_max * 1e-3)
 
     # field sanity
-    u = shard.owned("species_1")
+    u = shard.owned(names[0])
     assert np.isfinite(u).all(), "non-finite concentrations after the timed run"
 
     # ---- end to end through the SpatialSimulator binding with pinned host buffers -------------------
@@ -244,7 +256,6 @@ def main():
     sim = shard.sim
     nzl, nyl, nxl = sim.localShape()
     hbuf = [torch.empty((nzl, nyl, nxl), dtype=torch.float64).pin_memory().numpy() for _ in range(S)]
-    names = ["species_1", "species_2"]
     for b, name in zip(hbuf, names):
         sim.getVariableCompact(name, out=b)
     e2e = None
@@ -308,10 +319,10 @@ def main():
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        res, err = run_reference_cpu(512, 3, 80)
+        res, err = run_reference_cpu(512, 3, 80, args.model, dt if args.dim == 2 else (DT if args.model == "turing" else 0.1))
         if res is not None:
             cpu_baseline = {"value": res["cell_updates_per_s"], "unit": "cell-updates/s", "cores": 1, "kind": "reference",
-                            "sample": "512x512 cells of the same synthetic Turing model, 80 timed oneStep calls after 3 warm-up; the reference's own "
+                            "sample": "512x512 cells of the same synthetic model (2-D), 80 timed oneStep calls after 3 warm-up; the reference's own "
                                       "serial code (oracle/_ref), 1 of %d host cores" % (os.cpu_count() or 1),
                             "seconds": res["seconds"], "init_s": res["init_s"]}
         else:
