@@ -217,6 +217,24 @@ SB2_API int64_t sb2_launch_count(const sb2_sim* sim);
 /* Human readable listing of the compiled device program (for tests / debugging). */
 SB2_API int sb2_program_text(sb2_sim* sim, char* buf, int buflen);
 
+
+/* Model-specialised stage kernel.  The reference interprets a reaction's reverse-polish stream at every grid
+ * point (reversePolishRK, calcPDE.cpp:224-451).  Large grids (>= 2^20 cells, or SB2_JIT=1; SB2_JIT=0 turns it off,
+ * SB2_JIT=require makes a failed build an error) get, at sb2_finalize, a build of the stage kernel in which the
+ * model's token records are expanded into straight-line code, compiled for sm_100a with the CUDA run-time compiler
+ * (libnvrtc, loaded with dlopen).  Results are bit-identical to the interpreter kernel, which keeps running when
+ * the run-time compiler is not available.
+ * sb2_specialized: 1 when the handle runs the specialised kernel.  sb2_specialize_info: text describing what
+ * happened (library used, build time, or why the interpreter runs); returns the full length. */
+SB2_API int sb2_specialized(const sb2_sim* sim);
+SB2_API int sb2_specialize_info(const sb2_sim* sim, char* buf, int buflen);
+/* Builds the specialised kernel for a list of n token records (code = opcode * SB2_MAX_DEPTH + slot, arg) without
+ * touching a GPU and writes the sm_100a cubin to cubin_path (may be NULL): build check and tests.  ns / np / w /
+ * depth / minb / d3: species, cell pairs per thread, warps per CTA, stack depth, CTAs per SM, 3-D grid.
+ * The compiler log (or the reason of a failure) is copied into log.  Returns 0 on success. */
+SB2_API int sb2_specialize_dry_run(const uint32_t* code, const uint32_t* arg, int n, int ns, int np, int w, int depth,
+                                   int minb, int d3, const char* cubin_path, char* log, int loglen);
+
 #ifdef __cplusplus
 }
 #endif

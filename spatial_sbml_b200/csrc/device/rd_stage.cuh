@@ -44,7 +44,6 @@
 #define SB2_RD_STAGE_CUH_
 #include "sb2_internal.h"
 #include "sb2_ops.cuh"
-#include <type_traits>
 
 namespace {
 namespace rd {
@@ -135,6 +134,9 @@ constexpr int HDR = 512;
 #define SB2_RD_P2P 1  // 1: warps wait for the two ring rows they need (row-ready mbarriers); 0: one __syncthreads() per batch
 #endif
 
+template <bool B>
+struct BoolTag { static constexpr bool value = B; };
+
 template <int NP, int W>
 struct Geo {
   static constexpr int NC = 2 * NP;     // cells per thread
@@ -178,8 +180,10 @@ __device__ __forceinline__ double div6(double x) {
 #define RD_REP_D0(M) M(0) M(1) M(2) M(3) M(4) M(5) M(6) M(7)
 #define RD_REP_D1(M) M(1) M(2) M(3) M(4) M(5) M(6) M(7)
 
-template <int NS, int NP, int W, int MODE, int DEPTH, int MINB, bool D3>
-__global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_constant__ Sb2RdArgs A) {
+// SB2_RD_PROGRAM (model-specialised build, rd_jit.cpp): the bytecode interpreter is replaced by the straight-line
+// expansion of one model's token records; KC(i) is the inline constant of record i, read from the kernel parameters.
+template <int NS, int NP, int W, int MODE, int DEPTH, bool D3>
+__device__ __forceinline__ void rd_stage_body(const Sb2RdArgs& A, const double* __restrict__ kc) {
   using G = Geo<NP, W>;
   constexpr int NC = G::NC, SW = G::SW, SWP = G::SWP, RW = G::RW;
   constexpr int NARR = (MODE == MODE_FIRST) ? 1 : 2;  // arrays per species in a raw slot: u (, k_{m-1})
@@ -188,10 +192,11 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
   // [last stage: k0 / k1 slots: W x S x 2 x SW]
   const int S = A.S;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
-  // token stream, two parallel arrays: code | arg << 16 (4 bytes each) and the inline constants (8 bytes each)
-  const double* tokc = reinterpret_cast<const double*>(smem_raw + HDR);
-  const uint32_t* toks = reinterpret_cast<const uint32_t*>(smem_raw + HDR + (A.nrd + 2) * 8);
+#ifdef SB2_RD_PROGRAM
+  double* wring = reinterpret_cast<double*>(smem_raw + HDR);  // no token records in a model-specialised build
+#else
   double* wring = reinterpret_cast<double*>(smem_raw + HDR + tok_bytes(A.nrd));
+#endif
   double* rawbase = wring + (size_t)S * RW * SWP;
   double* cbase = rawbase + (size_t)W * S * NARR * SWP;
 
@@ -225,6 +230,7 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
       for (int q = 0; q < RW; ++q) mbar_init(rowbar0 + 8 * q, 1);
     mbar_fence_init();
   }
+#ifndef SB2_RD_PROGRAM
   // the token records move from their device buffer to shared memory once (first read after the first barrier)
   for (int i = threadIdx.x; i < A.nrd + 2; i += W * 32) {
     const Sb2RdTok t = A.rdtok[i];
@@ -232,6 +238,7 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
     reinterpret_cast<uint32_t*>(smem_raw + HDR + (A.nrd + 2) * 8)[i] = t.code | (t.arg << 16);
   }
   __syncwarp();
+#endif
   if (SB2_RD_P2P) __syncthreads();  // once: row barriers and token stream are in place
 
   // The last stage reads u and k2 of its own cells a second time for the combine, one batch after the bulk copy
@@ -442,6 +449,86 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
       uint32_t mask_bit = 0;  // set by MASK (bit of the law's geometry in the flag words), read by the ACC*M forms only
       const double* wop = wring + slot_c * SWP + 2 + 2 * lane;  // + s*RW*SWP selects the species, + 64p the pair
 
+      // What each instruction does to the 2*NP cells of the thread: B_<op>(d, arg, cv) with d the stack slot (compile
+      // time), arg the operand field and cv the inline constant.  The interpreter passes the fields of the fetched
+      // record, a model-specialised build passes literals.
+#define LOADVS(v, sidx, p) const double2 v = *reinterpret_cast<const double2*>(wop + (sidx) * (RW * SWP) + (p) * 64)
+#define FORC _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_)
+#define FORP _Pragma("unroll") for (int p = 0; p < NP; ++p)
+#define B_PUSHC(d, arg, cv) { const double b_ = (cv); FORC RD(d)[c_] = b_; }
+#define B_PUSHV(d, arg, cv) { FORP { LOADVS(v, arg, p); RD(d)[2 * p] = v.x; RD(d)[2 * p + 1] = v.y; } }
+#define B_PUSHF(d, arg, cv) { FORP { double2 v = make_double2(0.0, 0.0); if (active[p]) v = *reinterpret_cast<const double2*>(A.fields[arg] + idx0 + p * 64); RD(d)[2 * p] = v.x; RD(d)[2 * p + 1] = v.y; } }
+      // r[d-1] = r[d-1] op r[d]
+#define B_BIN(d, EXPR) { FORC { const double a = RD(d - 1)[c_], b = RD(d)[c_]; RD(d - 1)[c_] = (EXPR); } }
+#define B_ADD(d, arg, cv) B_BIN(d, dadd(a, b))
+#define B_SUB(d, arg, cv) B_BIN(d, dsub(a, b))
+#define B_MUL(d, arg, cv) B_BIN(d, dmul(a, b))
+#define B_DIV(d, arg, cv) { ddiv_batch<NC>(RD(d - 1), RD(d), RD(d - 1)); }
+#define B_GEQ(d, arg, cv) B_BIN(d, (a >= b) ? 1.0 : 0.0)
+#define B_GT(d, arg, cv) B_BIN(d, (a > b) ? 1.0 : 0.0)
+#define B_LEQ(d, arg, cv) B_BIN(d, (a <= b) ? 1.0 : 0.0)
+#define B_LT(d, arg, cv) B_BIN(d, (a < b) ? 1.0 : 0.0)
+#define B_AND(d, arg, cv) B_BIN(d, logic_and(a, b))
+#define B_OR(d, arg, cv) B_BIN(d, logic_or(a, b))
+      // r[d] = r[d] op c   (R forms: c op r[d])
+#define B_BINC(d, cv, EXPR) { const double b = (cv); FORC { const double a = RD(d)[c_]; RD(d)[c_] = (EXPR); } }
+#define B_ADDC(d, arg, cv) B_BINC(d, cv, dadd(a, b))
+#define B_SUBC(d, arg, cv) B_BINC(d, cv, dsub(a, b))
+#define B_MULC(d, arg, cv) B_BINC(d, cv, dmul(a, b))
+#define B_RSUBC(d, arg, cv) B_BINC(d, cv, dsub(b, a))
+#define B_DIVC(d, arg, cv) { double b[NC]; FORC b[c_] = (cv); ddiv_batch<NC>(RD(d), b, RD(d)); }
+#define B_RDIVC(d, arg, cv) { double a[NC]; FORC a[c_] = (cv); ddiv_batch<NC>(a, RD(d), RD(d)); }
+#define B_GEQC(d, arg, cv) B_BINC(d, cv, (a >= b) ? 1.0 : 0.0)
+#define B_GTC(d, arg, cv) B_BINC(d, cv, (a > b) ? 1.0 : 0.0)
+#define B_LEQC(d, arg, cv) B_BINC(d, cv, (a <= b) ? 1.0 : 0.0)
+#define B_LTC(d, arg, cv) B_BINC(d, cv, (a < b) ? 1.0 : 0.0)
+      // r[d] = r[d] op species arg
+#define B_BINV(d, arg, EXPR) { FORP { LOADVS(v, arg, p); { const double a = RD(d)[2 * p], b = v.x; RD(d)[2 * p] = (EXPR); } { const double a = RD(d)[2 * p + 1], b = v.y; RD(d)[2 * p + 1] = (EXPR); } } }
+#define B_ADDV(d, arg, cv) B_BINV(d, arg, dadd(a, b))
+#define B_SUBV(d, arg, cv) B_BINV(d, arg, dsub(a, b))
+#define B_MULV(d, arg, cv) B_BINV(d, arg, dmul(a, b))
+#define B_DIVV(d, arg, cv) { double b[NC]; FORP { LOADVS(v, arg, p); b[2 * p] = v.x; b[2 * p + 1] = v.y; } ddiv_batch<NC>(RD(d), b, RD(d)); }
+      // fused forms of the lowering pass: r[d] = species op constant, r[d] = species op species
+#define B_BINVC(d, arg, cv, EXPR) { const double b = (cv); FORP { LOADVS(v, arg, p); { const double a = v.x; RD(d)[2 * p] = (EXPR); } { const double a = v.y; RD(d)[2 * p + 1] = (EXPR); } } }
+#define B_ADDVC(d, arg, cv) B_BINVC(d, arg, cv, dadd(a, b))
+#define B_SUBVC(d, arg, cv) B_BINVC(d, arg, cv, dsub(a, b))
+#define B_RSUBVC(d, arg, cv) B_BINVC(d, arg, cv, dsub(b, a))
+#define B_MULVC(d, arg, cv) B_BINVC(d, arg, cv, dmul(a, b))
+#define B_DIVVC(d, arg, cv) { double a[NC], b[NC]; FORP { LOADVS(v, arg, p); a[2 * p] = v.x; a[2 * p + 1] = v.y; b[2 * p] = (cv); b[2 * p + 1] = (cv); } ddiv_batch<NC>(a, b, RD(d)); }
+#define B_RDIVVC(d, arg, cv) { double a[NC], b[NC]; FORP { LOADVS(v, arg, p); b[2 * p] = v.x; b[2 * p + 1] = v.y; a[2 * p] = (cv); a[2 * p + 1] = (cv); } ddiv_batch<NC>(a, b, RD(d)); }
+#define B_BINVV(d, arg, EXPR) { const uint32_t s1_ = (arg) & 0xffu, s2_ = (arg) >> 8; FORP { LOADVS(v1, s1_, p); LOADVS(v2, s2_, p); { const double a = v1.x, b = v2.x; RD(d)[2 * p] = (EXPR); } { const double a = v1.y, b = v2.y; RD(d)[2 * p + 1] = (EXPR); } } }
+#define B_ADDVV(d, arg, cv) B_BINVV(d, arg, dadd(a, b))
+#define B_SUBVV(d, arg, cv) B_BINVV(d, arg, dsub(a, b))
+#define B_MULVV(d, arg, cv) B_BINVV(d, arg, dmul(a, b))
+#define B_DIVVV(d, arg, cv) { const uint32_t s1_ = (arg) & 0xffu, s2_ = (arg) >> 8; double a[NC], b[NC]; FORP { LOADVS(v1, s1_, p); LOADVS(v2, s2_, p); a[2 * p] = v1.x; a[2 * p + 1] = v1.y; b[2 * p] = v2.x; b[2 * p + 1] = v2.y; } ddiv_batch<NC>(a, b, RD(d)); }
+#define B_UNARY(d, arg, cv) { FORC RD(d)[c_] = sb2_unary((int)(arg), RD(d)[c_]); }
+#define B_BINR(d, arg, cv) { FORC RD(d - 1)[c_] = sb2_binary((int)(arg), RD(d - 1)[c_], RD(d)[c_]); }
+#define B_MOV0(d, arg, cv) { FORC RD(0)[c_] = RD(d)[c_]; }
+#define B_MOVUP(d, arg, cv) { FORC RD(d + 1)[c_] = RD(d)[c_]; }
+      // statement mask: the law only acts on cells of its own domain (spatialsimulator.cpp:1381-1390)
+#define B_MASK(d, arg, cv) { mask_bit = 1u << (8 * (arg)); }
+      // delta -= stoich*rate (reactants) / += (products, rate rules); calcPDE.cpp:432-449.  Here d is the species.
+#define SI(s) ((s) < NS ? (s) : 0)
+#define B_ACCSUB(s, arg, cv) { const double st = (cv); FORC acc[SI(s)][c_] = dsub(acc[SI(s)][c_], dmul(st, RD(0)[c_])); }
+#define B_ACCADD(s, arg, cv) { const double st = (cv); FORC acc[SI(s)][c_] = dadd(acc[SI(s)][c_], dmul(st, RD(0)[c_])); }
+#define B_ACCSUB1(s, arg, cv) { FORC acc[SI(s)][c_] = dsub(acc[SI(s)][c_], RD(0)[c_]); }
+#define B_ACCADD1(s, arg, cv) { FORC acc[SI(s)][c_] = dadd(acc[SI(s)][c_], RD(0)[c_]); }
+#define B_ACCSUBC1(s, arg, cv) { const double st = (cv); FORC acc[SI(s)][c_] = dsub(acc[SI(s)][c_], st); }
+#define B_ACCADDC1(s, arg, cv) { const double st = (cv); FORC acc[SI(s)][c_] = dadd(acc[SI(s)][c_], st); }
+#define B_ACCSUBM(s, arg, cv) { const double st = (cv); FORC if (fl[c_] & mask_bit) acc[SI(s)][c_] = dsub(acc[SI(s)][c_], dmul(st, RD(0)[c_])); }
+#define B_ACCADDM(s, arg, cv) { const double st = (cv); FORC if (fl[c_] & mask_bit) acc[SI(s)][c_] = dadd(acc[SI(s)][c_], dmul(st, RD(0)[c_])); }
+      // reactant and product of a unit-stoichiometry law in one record: acc[s] -= r0; acc[arg] += r0
+#define B_XFER(s, arg, cv) { FORC acc[SI(s)][c_] = dsub(acc[SI(s)][c_], RD(0)[c_]); \
+      _Pragma("unroll") for (int s2_ = 0; s2_ < NS; ++s2_) if ((arg) == (uint32_t)s2_) { FORC acc[s2_][c_] = dadd(acc[s2_][c_], RD(0)[c_]); } }
+
+#ifdef SB2_RD_PROGRAM
+#define KC(i) kc[i]
+      SB2_RD_PROGRAM
+#undef KC
+#else
+      // token stream, two parallel arrays: code | arg << 16 (4 bytes each) and the inline constants (8 bytes each)
+      const double* tokc = reinterpret_cast<const double*>(smem_raw + HDR);
+      const uint32_t* toks = reinterpret_cast<const uint32_t*>(smem_raw + HDR + (A.nrd + 2) * 8);
       uint32_t tnext = toks[0];
       int pc = 0;
 #pragma unroll 1
@@ -450,109 +537,26 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
         const double* cvp = tokc + pc;  // inline constant of the C forms, loaded by the cases that use it
         tnext = toks[++pc];  // one token ahead; the stream ends with two OPC_END tokens
         const uint32_t arg = t >> 16;
-#define cv (*cvp)
         switch (t & 0xffffu) {
-#define LOADV(v, p) const double2 v = *reinterpret_cast<const double2*>(wop + arg * (RW * SWP) + (p) * 64)
-#define C_PUSHC(d) case SB2_CODE(OPC_PUSHC, d): LIVE(d) { _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) RD(d)[c_] = cv; } break;
-          RD_REP_D0(C_PUSHC)
-#define C_PUSHV(d) case SB2_CODE(OPC_PUSHV, d): LIVE(d) { _Pragma("unroll") for (int p = 0; p < NP; ++p) { LOADV(v, p); RD(d)[2 * p] = v.x; RD(d)[2 * p + 1] = v.y; } } break;
-          RD_REP_D0(C_PUSHV)
-#define C_PUSHF(d) case SB2_CODE(OPC_PUSHF, d): LIVE(d) { _Pragma("unroll") for (int p = 0; p < NP; ++p) { double2 v = make_double2(0.0, 0.0); if (active[p]) v = *reinterpret_cast<const double2*>(A.fields[arg] + idx0 + p * 64); RD(d)[2 * p] = v.x; RD(d)[2 * p + 1] = v.y; } } break;
-          RD_REP_D0(C_PUSHF)
-#define C_BIN(opc, d, EXPR) case SB2_CODE(opc, d): LIVE(d) { _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) { const double a = RD(d - 1)[c_], b = RD(d)[c_]; RD(d - 1)[c_] = (EXPR); } } break;
-#define C_ADD(d) C_BIN(OPC_ADD, d, dadd(a, b))
-#define C_SUB(d) C_BIN(OPC_SUB, d, dsub(a, b))
-#define C_MUL(d) C_BIN(OPC_MUL, d, dmul(a, b))
-#define C_DIV(d) C_BIN(OPC_DIV, d, ddiv(a, b))
-#define C_GEQ(d) C_BIN(OPC_GEQ, d, (a >= b) ? 1.0 : 0.0)
-#define C_GT(d) C_BIN(OPC_GT, d, (a > b) ? 1.0 : 0.0)
-#define C_LEQ(d) C_BIN(OPC_LEQ, d, (a <= b) ? 1.0 : 0.0)
-#define C_LT(d) C_BIN(OPC_LT, d, (a < b) ? 1.0 : 0.0)
-#define C_AND(d) C_BIN(OPC_AND, d, logic_and(a, b))
-#define C_OR(d) C_BIN(OPC_OR, d, logic_or(a, b))
-#undef C_DIV
-#define C_DIV(d) case SB2_CODE(OPC_DIV, d): LIVE(d) { ddiv_batch<NC>(RD(d - 1), RD(d), RD(d - 1)); } break;
-          RD_REP_D1(C_ADD) RD_REP_D1(C_SUB) RD_REP_D1(C_MUL) RD_REP_D1(C_DIV)
-          RD_REP_D1(C_GEQ) RD_REP_D1(C_GT) RD_REP_D1(C_LEQ) RD_REP_D1(C_LT) RD_REP_D1(C_AND) RD_REP_D1(C_OR)
-#define C_BINC(opc, d, EXPR) case SB2_CODE(opc, d): LIVE(d) { const double b = cv; _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) { const double a = RD(d)[c_]; RD(d)[c_] = (EXPR); } } break;
-#define C_ADDC(d) C_BINC(OPC_ADDC, d, dadd(a, b))
-#define C_SUBC(d) C_BINC(OPC_SUBC, d, dsub(a, b))
-#define C_MULC(d) C_BINC(OPC_MULC, d, dmul(a, b))
-#define C_DIVC(d) C_BINC(OPC_DIVC, d, ddiv(a, b))
-#define C_RSUBC(d) C_BINC(OPC_RSUBC, d, dsub(b, a))
-#define C_RDIVC(d) C_BINC(OPC_RDIVC, d, ddiv(b, a))
-#define C_GEQC(d) C_BINC(OPC_GEQC, d, (a >= b) ? 1.0 : 0.0)
-#define C_GTC(d) C_BINC(OPC_GTC, d, (a > b) ? 1.0 : 0.0)
-#define C_LEQC(d) C_BINC(OPC_LEQC, d, (a <= b) ? 1.0 : 0.0)
-#define C_LTC(d) C_BINC(OPC_LTC, d, (a < b) ? 1.0 : 0.0)
-#undef C_DIVC
-#undef C_RDIVC
-#define C_DIVC(d) case SB2_CODE(OPC_DIVC, d): LIVE(d) { double b[NC]; _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) b[c_] = cv; ddiv_batch<NC>(RD(d), b, RD(d)); } break;
-#define C_RDIVC(d) case SB2_CODE(OPC_RDIVC, d): LIVE(d) { double a[NC]; _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) a[c_] = cv; ddiv_batch<NC>(a, RD(d), RD(d)); } break;
-          RD_REP_D0(C_ADDC) RD_REP_D0(C_SUBC) RD_REP_D0(C_MULC) RD_REP_D0(C_DIVC) RD_REP_D0(C_RSUBC) RD_REP_D0(C_RDIVC)
-          RD_REP_D0(C_GEQC) RD_REP_D0(C_GTC) RD_REP_D0(C_LEQC) RD_REP_D0(C_LTC)
-#define C_BINV(opc, d, EXPR) case SB2_CODE(opc, d): LIVE(d) { _Pragma("unroll") for (int p = 0; p < NP; ++p) { LOADV(v, p); { const double a = RD(d)[2 * p], b = v.x; RD(d)[2 * p] = (EXPR); } { const double a = RD(d)[2 * p + 1], b = v.y; RD(d)[2 * p + 1] = (EXPR); } } } break;
-#define C_ADDV(d) C_BINV(OPC_ADDV, d, dadd(a, b))
-#define C_SUBV(d) C_BINV(OPC_SUBV, d, dsub(a, b))
-#define C_MULV(d) C_BINV(OPC_MULV, d, dmul(a, b))
-#define C_DIVV(d) C_BINV(OPC_DIVV, d, ddiv(a, b))
-#undef C_DIVV
-#define C_DIVV(d) case SB2_CODE(OPC_DIVV, d): LIVE(d) { double b[NC]; _Pragma("unroll") for (int p = 0; p < NP; ++p) { LOADV(v, p); b[2 * p] = v.x; b[2 * p + 1] = v.y; } ddiv_batch<NC>(RD(d), b, RD(d)); } break;
-          RD_REP_D0(C_ADDV) RD_REP_D0(C_SUBV) RD_REP_D0(C_MULV) RD_REP_D0(C_DIVV)
-          // fused forms of the lowering pass: species operand and inline constant, or two species operands
-#define LOADVS(v, sidx, p) const double2 v = *reinterpret_cast<const double2*>(wop + (sidx) * (RW * SWP) + (p) * 64)
-#define C_BINVC(opc, d, EXPR) case SB2_CODE(opc, d): LIVE(d) { const double b = cv; _Pragma("unroll") for (int p = 0; p < NP; ++p) { LOADV(v, p); { const double a = v.x; RD(d)[2 * p] = (EXPR); } { const double a = v.y; RD(d)[2 * p + 1] = (EXPR); } } } break;
-#define C_ADDVC(d) C_BINVC(OPC_ADDVC, d, dadd(a, b))
-#define C_SUBVC(d) C_BINVC(OPC_SUBVC, d, dsub(a, b))
-#define C_RSUBVC(d) C_BINVC(OPC_RSUBVC, d, dsub(b, a))
-#define C_MULVC(d) C_BINVC(OPC_MULVC, d, dmul(a, b))
-          RD_REP_D0(C_ADDVC) RD_REP_D0(C_SUBVC) RD_REP_D0(C_RSUBVC) RD_REP_D0(C_MULVC)
-#define C_DIVVC(d) case SB2_CODE(OPC_DIVVC, d): LIVE(d) { double a[NC], b[NC]; _Pragma("unroll") for (int p = 0; p < NP; ++p) { LOADV(v, p); a[2 * p] = v.x; a[2 * p + 1] = v.y; b[2 * p] = cv; b[2 * p + 1] = cv; } ddiv_batch<NC>(a, b, RD(d)); } break;
-#define C_RDIVVC(d) case SB2_CODE(OPC_RDIVVC, d): LIVE(d) { double a[NC], b[NC]; _Pragma("unroll") for (int p = 0; p < NP; ++p) { LOADV(v, p); b[2 * p] = v.x; b[2 * p + 1] = v.y; a[2 * p] = cv; a[2 * p + 1] = cv; } ddiv_batch<NC>(a, b, RD(d)); } break;
-          RD_REP_D0(C_DIVVC) RD_REP_D0(C_RDIVVC)
-#define C_BINVV(opc, d, EXPR) case SB2_CODE(opc, d): LIVE(d) { const uint32_t s1_ = arg & 0xffu, s2_ = arg >> 8; _Pragma("unroll") for (int p = 0; p < NP; ++p) { LOADVS(v1, s1_, p); LOADVS(v2, s2_, p); { const double a = v1.x, b = v2.x; RD(d)[2 * p] = (EXPR); } { const double a = v1.y, b = v2.y; RD(d)[2 * p + 1] = (EXPR); } } } break;
-#define C_ADDVV(d) C_BINVV(OPC_ADDVV, d, dadd(a, b))
-#define C_SUBVV(d) C_BINVV(OPC_SUBVV, d, dsub(a, b))
-#define C_MULVV(d) C_BINVV(OPC_MULVV, d, dmul(a, b))
-          RD_REP_D0(C_ADDVV) RD_REP_D0(C_SUBVV) RD_REP_D0(C_MULVV)
-#define C_DIVVV(d) case SB2_CODE(OPC_DIVVV, d): LIVE(d) { const uint32_t s1_ = arg & 0xffu, s2_ = arg >> 8; double a[NC], b[NC]; _Pragma("unroll") for (int p = 0; p < NP; ++p) { LOADVS(v1, s1_, p); LOADVS(v2, s2_, p); a[2 * p] = v1.x; a[2 * p + 1] = v1.y; b[2 * p] = v2.x; b[2 * p + 1] = v2.y; } ddiv_batch<NC>(a, b, RD(d)); } break;
-          RD_REP_D0(C_DIVVV)
-#define C_UNARY(d) case SB2_CODE(OPC_UNARY, d): LIVE(d) { _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) RD(d)[c_] = sb2_unary((int)arg, RD(d)[c_]); } break;
-          RD_REP_D0(C_UNARY)
-#define C_BINR(d) case SB2_CODE(OPC_BINR, d): LIVE(d) { _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) RD(d - 1)[c_] = sb2_binary((int)arg, RD(d - 1)[c_], RD(d)[c_]); } break;
-          RD_REP_D1(C_BINR)
-#define C_MOV0(d) case SB2_CODE(OPC_MOV0, d): LIVE(d) { _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) RD(0)[c_] = RD(d)[c_]; } break;
-          RD_REP_D1(C_MOV0)
-#define C_MOVUP(d) case SB2_CODE(OPC_MOVUP, d): LIVE(d + 1) { _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) RD(d + 1)[c_] = RD(d)[c_]; } break;
-          RD_REP_D0(C_MOVUP)
-          // statement mask: the law only acts on cells of its own domain (spatialsimulator.cpp:1381-1390)
-          case SB2_CODE(OPC_MASK, 0): mask_bit = 1u << (8 * arg); break;
-          // delta -= stoich*rate (reactants) / += (products, rate rules); calcPDE.cpp:432-449
-#define SI(s) ((s) < NS ? (s) : 0)
-#define C_ACC(s) \
-  case SB2_CODE(OPC_ACCSUB, s): if (s < NS) { const double st = cv; \
-      _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) acc[SI(s)][c_] = dsub(acc[SI(s)][c_], dmul(st, RD(0)[c_])); } break; \
-  case SB2_CODE(OPC_ACCADD, s): if (s < NS) { const double st = cv; \
-      _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) acc[SI(s)][c_] = dadd(acc[SI(s)][c_], dmul(st, RD(0)[c_])); } break; \
-  case SB2_CODE(OPC_ACCSUB1, s): if (s < NS) { \
-      _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) acc[SI(s)][c_] = dsub(acc[SI(s)][c_], RD(0)[c_]); } break; \
-  case SB2_CODE(OPC_ACCADD1, s): if (s < NS) { \
-      _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) acc[SI(s)][c_] = dadd(acc[SI(s)][c_], RD(0)[c_]); } break; \
-  case SB2_CODE(OPC_ACCSUBC1, s): if (s < NS) { \
-      _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) acc[SI(s)][c_] = dsub(acc[SI(s)][c_], cv); } break; \
-  case SB2_CODE(OPC_ACCADDC1, s): if (s < NS) { \
-      _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) acc[SI(s)][c_] = dadd(acc[SI(s)][c_], cv); } break; \
-  case SB2_CODE(OPC_ACCSUBM, s): if (s < NS) { const double st = cv; \
-      _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) if (fl[c_] & mask_bit) acc[SI(s)][c_] = dsub(acc[SI(s)][c_], dmul(st, RD(0)[c_])); } break; \
-  case SB2_CODE(OPC_ACCADDM, s): if (s < NS) { const double st = cv; \
-      _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) if (fl[c_] & mask_bit) acc[SI(s)][c_] = dadd(acc[SI(s)][c_], dmul(st, RD(0)[c_])); } break;
-          RD_REP_D0(C_ACC)
-          // reactant and product of a unit-stoichiometry law in one token: acc[s] -= r0; acc[arg] += r0
-#define C_XFER(s) case SB2_CODE(OPC_XFER, s): if (s < NS) { \
-      _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) acc[SI(s)][c_] = dsub(acc[SI(s)][c_], RD(0)[c_]); \
-      _Pragma("unroll") for (int s2_ = 0; s2_ < NS; ++s2_) if (arg == (uint32_t)s2_) { \
-        _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_) acc[s2_][c_] = dadd(acc[s2_][c_], RD(0)[c_]); } } break;
-          RD_REP_D0(C_XFER)
+          // slot d must exist in this variant (DL: the deepest slot the instruction touches)
+#define CASE(OP, d, DL) case SB2_CODE(OPC_##OP, d): LIVE(DL) B_##OP(d, arg, *cvp) break;
+#define CASE_D(OP) CASE(OP, 0, 0) CASE(OP, 1, 1) CASE(OP, 2, 2) CASE(OP, 3, 3) CASE(OP, 4, 4) CASE(OP, 5, 5) CASE(OP, 6, 6) CASE(OP, 7, 7)
+#define CASE_D1(OP) CASE(OP, 1, 1) CASE(OP, 2, 2) CASE(OP, 3, 3) CASE(OP, 4, 4) CASE(OP, 5, 5) CASE(OP, 6, 6) CASE(OP, 7, 7)
+#define CASE_UP(OP) CASE(OP, 0, 1) CASE(OP, 1, 2) CASE(OP, 2, 3) CASE(OP, 3, 4) CASE(OP, 4, 5) CASE(OP, 5, 6) CASE(OP, 6, 7) CASE(OP, 7, 8)
+#define CASE_S(OP) CASE(OP, 0, 0) CASE(OP, 1, (1 < NS ? 0 : DEPTH)) CASE(OP, 2, (2 < NS ? 0 : DEPTH)) CASE(OP, 3, (3 < NS ? 0 : DEPTH)) \
+  CASE(OP, 4, (4 < NS ? 0 : DEPTH)) CASE(OP, 5, (5 < NS ? 0 : DEPTH)) CASE(OP, 6, (6 < NS ? 0 : DEPTH)) CASE(OP, 7, (7 < NS ? 0 : DEPTH))
+          CASE_D(PUSHC) CASE_D(PUSHV) CASE_D(PUSHF)
+          CASE_D1(ADD) CASE_D1(SUB) CASE_D1(MUL) CASE_D1(DIV)
+          CASE_D1(GEQ) CASE_D1(GT) CASE_D1(LEQ) CASE_D1(LT) CASE_D1(AND) CASE_D1(OR)
+          CASE_D(ADDC) CASE_D(SUBC) CASE_D(MULC) CASE_D(DIVC) CASE_D(RSUBC) CASE_D(RDIVC)
+          CASE_D(GEQC) CASE_D(GTC) CASE_D(LEQC) CASE_D(LTC)
+          CASE_D(ADDV) CASE_D(SUBV) CASE_D(MULV) CASE_D(DIVV)
+          CASE_D(ADDVC) CASE_D(SUBVC) CASE_D(RSUBVC) CASE_D(MULVC) CASE_D(DIVVC) CASE_D(RDIVVC)
+          CASE_D(ADDVV) CASE_D(SUBVV) CASE_D(MULVV) CASE_D(DIVVV)
+          CASE_D(UNARY) CASE_D1(BINR) CASE_D1(MOV0) CASE_UP(MOVUP)
+          CASE(MASK, 0, 0)
+          CASE_S(ACCSUB) CASE_S(ACCADD) CASE_S(ACCSUB1) CASE_S(ACCADD1) CASE_S(ACCSUBC1) CASE_S(ACCADDC1)
+          CASE_S(ACCSUBM) CASE_S(ACCADDM) CASE_S(XFER)
           case SB2_CODE(OPC_END, 0): goto program_done;
           // the library only emits codes this variant implements (sb2_finalize checks depth and species count),
           // so the dispatch needs no range check
@@ -560,7 +564,7 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
         }
       }
     program_done:;
-#undef cv
+#endif
 #undef RD
 #undef LIVE
     }
@@ -652,8 +656,8 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
           }
         };
         if (sp.fastpath || !sp.has_diff) {
-          if (cls == 1) straight(std::false_type());
-          else straight(std::true_type());
+          if (cls == 1) straight(BoolTag<false>());
+          else straight(BoolTag<true>());
           continue;
         }
         // general path: per-cell domain / boundary flags, field-valued coefficients, dx^2 != 1.  Every stencil term
@@ -739,6 +743,19 @@ __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_con
   }
 }
 
+#ifdef SB2_RD_PROGRAM
+// model-specialised build: entry points with C names (expanded at global scope by the generated translation unit),
+// parameters = the stage arguments followed by the constants
+struct Sb2RdJitParams { Sb2RdArgs a; double kc[SB2_RD_NKC]; };
+#define RD_JIT_ENTRY(name, MODE) \
+  extern "C" __global__ void __launch_bounds__(SB2_RD_W * 32, SB2_RD_MINB) name(const __grid_constant__ rd::Sb2RdJitParams P) { \
+    rd::rd_stage_body<SB2_RD_NS, SB2_RD_NP, SB2_RD_W, MODE, SB2_RD_DEPTH, SB2_RD_D3>(P.a, P.kc); }
+#else
+template <int NS, int NP, int W, int MODE, int DEPTH, int MINB, bool D3>
+__global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_constant__ Sb2RdArgs A) {
+  rd_stage_body<NS, NP, W, MODE, DEPTH, D3>(A, nullptr);
+}
+
 template <int NS, int NP, int W, int MODE, int DEPTH, int MINB, bool D3>
 cudaError_t launch_variant(const Sb2RdArgs& a, cudaStream_t stream) {
   using G = Geo<NP, W>;
@@ -777,6 +794,8 @@ cudaError_t launch_mode(const Sb2RdArgs& a, cudaStream_t stream) {
   if (a.dim == 3) return launch_dim<NS, NP, W, DEPTH, MINB, true>(a, stream);
   return launch_dim<NS, NP, W, DEPTH, MINB, false>(a, stream);
 }
+
+#endif  // SB2_RD_PROGRAM
 
 }  // namespace rd
 }  // namespace

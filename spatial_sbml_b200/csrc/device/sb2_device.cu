@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <sstream>
 
 namespace {
@@ -81,6 +82,8 @@ struct sb2_sim {
   uint64_t version;  // bumped by everything that can change a kernel argument (constants, uploads that allocate)
   std::vector<Sb2RdTok> rdprog;  // lowered token records (constants patched per launch from rdslot)
   std::vector<int> rdslot;       // constants-table slot of each record's inline constant, -1 = none
+  Sb2RdJit* jit;      // model-specialised build of the rd_stage kernel (rd_jit.cu), NULL: the interpreter kernel runs
+  std::string jit_info;
   uint32_t* d_dbg;    // SB2_DEBUG=1: device debug words, checked after every stage launch
   bool trace;         // SB2_TRACE=1: entry points report to stderr
 };
@@ -422,6 +425,19 @@ int launch_stage_rows(sb2_sim* sim, int m, double dt, int row_begin, int row_end
   if (sim->rd_id >= 0) {
     Sb2RdArgs a;
     fill_stage_args(sim, a, m, dt, row_begin, row_end);
+    if (sim->jit) {
+      // specialised kernel: the constants of the records travel in the kernel parameters
+      double kc[SB2_RD_MAX_TOKENS];
+      const int n = (int)sim->rdprog.size();
+      for (int i = 0; i < n; ++i) kc[i] = sim->rdslot[i] >= 0 ? sim->consts[sim->rdslot[i]] : 0.0;
+      a.rdtok = NULL;
+      if (sim->trace) fprintf(stderr, "[sb2] stage m=%d rows [%d,%d) rpb %d final %d carry %d (specialised)\n", m, row_begin, row_end, a.rows_per_block, a.final, a.carry);
+      ++sim->launches;
+      e = sb2_rd_jit_launch(sim->jit, a, kc, n, sim->stream);
+      if (e != cudaSuccess) return cuda_fail(sim, e, "specialised stage kernel launch");
+      goto launched;
+    }
+    {
     // inline constants of the token records = current values of the constants table; upload only when they changed
     std::vector<Sb2RdTok> cur(sim->rdprog);
     for (size_t i = 0; i < sim->rdslot.size(); ++i)
@@ -442,6 +458,7 @@ int launch_stage_rows(sb2_sim* sim, int m, double dt, int row_begin, int row_end
     if (sim->trace) fprintf(stderr, "[sb2] stage m=%d rows [%d,%d) rpb %d final %d carry %d\n", m, row_begin, row_end, a.rows_per_block, a.final, a.carry);
     ++sim->launches;
     e = sb2_rd_launch(a, sim->stream);
+    }
   } else {
     Sb2StageArgs a;
     fill_stage_args(sim, a, m, dt, row_begin, row_end);
@@ -450,6 +467,7 @@ int launch_stage_rows(sb2_sim* sim, int m, double dt, int row_begin, int row_end
     e = sb2_launch_stage(a, sim->stream, &sim->launches);
   }
   if (e != cudaSuccess) return cuda_fail(sim, e, "stage kernel launch");
+launched:
   if (sim->d_dbg) {
     uint32_t h[8];
     CK(cudaStreamSynchronize(sim->stream));
@@ -511,7 +529,7 @@ int sb2_create(const sb2_grid* grid, sb2_sim** out) {
   sim->launches = 0; sim->in_step = false; sim->cur_dt = 0; sim->d_scratch = NULL;
   sim->rd_id = -1; sim->d_cls = NULL; sim->nstrips = 0; sim->d_dbg = NULL;
   sim->h2d = NULL; sim->d2h = NULL; sim->ev_start = NULL; sim->d_rdtok = NULL; sim->rd_buf = 0; sim->multi_stream = false;
-  sim->gexec[0] = sim->gexec[1] = NULL; sim->version = 1;
+  sim->gexec[0] = sim->gexec[1] = NULL; sim->version = 1; sim->jit = NULL;
   sim->trace = getenv("SB2_TRACE") != NULL;
   memset(&sim->base, 0, sizeof(sim->base));
   *out = sim;
@@ -535,6 +553,7 @@ void sb2_destroy(sb2_sim* sim) {
   if (sim->d_scratch) cudaFree(sim->d_scratch);
   if (sim->d_cls) cudaFree(sim->d_cls);
   if (sim->d_rdtok) cudaFree(sim->d_rdtok);
+  sb2_rd_jit_free(sim->jit);
   for (int p = 0; p < 2; ++p) if (sim->gexec[p]) cudaGraphExecDestroy(sim->gexec[p]);
   if (sim->h2d) cudaStreamDestroy(sim->h2d);
   if (sim->d2h) cudaStreamDestroy(sim->d2h);
@@ -760,6 +779,28 @@ int sb2_finalize(sb2_sim* sim) {
       CK(cudaMalloc((void**)&sim->d_dbg, 64 * sizeof(uint32_t)));
       CK(cudaMemsetAsync(sim->d_dbg, 0, 64 * sizeof(uint32_t), sim->stream));
       b.dbg = sim->d_dbg;
+    }
+    // model-specialised build (include/spatial_b200.h, sb2_specialized)
+    {
+      const char* jenv = getenv("SB2_JIT");
+      const bool off = jenv && !strcmp(jenv, "0"), require = jenv && !strcmp(jenv, "require");
+      const bool want = !off && (jenv ? true : ncells(sim) >= (1 << 20));
+      if (off) sim->jit_info = "interpreter kernel: SB2_JIT=0";
+      else if (!want) sim->jit_info = "interpreter kernel: grid below 2^20 cells (SB2_JIT=1 forces the specialised build)";
+      else {
+        Sb2RdJitSpec spec;
+        spec.ns = b.S; spec.np = sim->rd.np; spec.w = sim->rd.w; spec.depth = b.depth; spec.minb = 2; spec.d3 = sim->g.dim == 3;
+        std::string jerr;
+        const auto t0 = std::chrono::steady_clock::now();
+        sim->jit = sb2_rd_jit_build(spec, sim->rdprog, &jerr);
+        const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        std::ostringstream os;
+        if (sim->jit) os << "specialised kernel: " << sim->rdprog.size() << " records compiled in " << secs << " s with " << sb2_rd_jit_library();
+        else os << "interpreter kernel: specialised build failed: " << jerr;
+        sim->jit_info = os.str();
+        if (!sim->jit && require) return fail(sim, SB2_ERR_STATE, sim->jit_info);
+      }
+      if (sim->trace) fprintf(stderr, "[sb2] %s\n", sim->jit_info.c_str());
     }
     if (sim->trace) fprintf(stderr, "[sb2] rd_stage variant %d (np %d, w %d, depth %d), %d strips, program depth %d, %d tokens\n",
                             sim->rd_id, sim->rd.np, sim->rd.w, sim->rd.depth, sim->nstrips, b.depth, b.ntok);
@@ -1187,6 +1228,36 @@ int sb2_species_view(sb2_sim* sim, int species, int which, sb2_field_view* out) 
 int sb2_combine_is_fused(const sb2_sim* sim) { return sim && sim->fuse_combine ? 1 : 0; }
 
 int64_t sb2_launch_count(const sb2_sim* sim) { return sim ? sim->launches : 0; }
+
+int sb2_specialized(const sb2_sim* sim) { return sim && sim->jit ? 1 : 0; }
+
+int sb2_specialize_info(const sb2_sim* sim, char* buf, int buflen) {
+  if (!sim || !buf || buflen <= 0) return SB2_ERR_ARG;
+  const std::string s = sim->jit_info.empty() ? std::string("interpreter kernel: first-generation stage kernel") : sim->jit_info;
+  snprintf(buf, buflen, "%s", s.c_str());
+  return (int)s.size();
+}
+
+int sb2_specialize_dry_run(const uint32_t* code, const uint32_t* arg, int n, int ns, int np, int w, int depth, int minb, int d3,
+                           const char* cubin_path, char* log, int loglen) {
+  if (n < 0 || (n > 0 && (!code || !arg)) || n > SB2_RD_MAX_TOKENS) return SB2_ERR_ARG;
+  std::vector<Sb2RdTok> prog(n);
+  for (int i = 0; i < n; ++i) { prog[i].code = code[i]; prog[i].arg = arg[i]; prog[i].c = 0.0; }
+  Sb2RdJitSpec spec;
+  spec.ns = ns; spec.np = np; spec.w = w; spec.depth = depth; spec.minb = minb; spec.d3 = d3;
+  std::vector<char> cubin;
+  std::string l;
+  const int rc = sb2_rd_jit_compile(sb2_rd_jit_source(spec, prog), &cubin, &l);
+  if (log && loglen > 0) snprintf(log, loglen, "%s", l.c_str());
+  if (rc != 0) return SB2_ERR_STATE;
+  if (cubin_path) {
+    FILE* f = fopen(cubin_path, "wb");
+    if (!f) return SB2_ERR_ARG;
+    fwrite(cubin.data(), 1, cubin.size(), f);
+    fclose(f);
+  }
+  return SB2_OK;
+}
 
 int sb2_program_text(sb2_sim* sim, char* buf, int buflen) {
   if (!sim || !buf || buflen <= 0) return SB2_ERR_ARG;

@@ -2,10 +2,12 @@
 #ifndef SB2_INTERNAL_H_
 #define SB2_INTERNAL_H_
 
+#ifndef __CUDACC_RTC__  // the run-time compiler (rd_jit.cpp) gets the fixed-width types and the public header from its own prelude
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
 #include <vector>
+#endif
 #include "../../../include/spatial_b200.h"
 
 // ---------------------------------------------------------------------------------------------
@@ -109,6 +111,7 @@ struct Sb2RdArgs : Sb2StageCore {
   const Sb2RdTok* rdtok;
 };
 
+#ifndef __CUDACC_RTC__
 // launches (implemented in stage_kernel.cu)
 cudaError_t sb2_launch_stage(const Sb2StageArgs& args, cudaStream_t stream, int* launches);
 int sb2_stage_pairs(int nx, int nspecies);
@@ -122,6 +125,16 @@ cudaError_t sb2_rd_launch(const Sb2RdArgs& a, cudaStream_t stream);
 cudaError_t sb2_rd_classify(const uint8_t* const* flags, int G, int nx, int ny, int nz, int64_t P, int64_t PL, int64_t first,
                             int sw, uint8_t* cls, int nstrips, cudaStream_t stream);
 
+// model-specialised rd_stage kernels built at run time (rd_jit.cu)
+struct Sb2RdJitSpec { int ns, np, w, depth, minb, d3; };
+struct Sb2RdJit;
+std::string sb2_rd_jit_source(const Sb2RdJitSpec& spec, const std::vector<Sb2RdTok>& prog);
+int sb2_rd_jit_compile(const std::string& src, std::vector<char>* cubin, std::string* log);  // needs no GPU
+Sb2RdJit* sb2_rd_jit_build(const Sb2RdJitSpec& spec, const std::vector<Sb2RdTok>& prog, std::string* err);
+cudaError_t sb2_rd_jit_launch(Sb2RdJit* j, const Sb2RdArgs& a, const double* kc, int nkc, cudaStream_t stream);
+void sb2_rd_jit_free(Sb2RdJit* j);
+const char* sb2_rd_jit_library();  // path of the NVRTC library in use ("" when none was found)
+
 struct Sb2CombineArgs {
   int32_t nx, ny, nz, dim, S;
   int64_t P, PL, first;
@@ -131,5 +144,7 @@ struct Sb2CombineArgs {
   const uint8_t* flags[SB2_MAX_SPECIES];
 };
 cudaError_t sb2_launch_combine(const Sb2CombineArgs& args, cudaStream_t stream, int* launches);
+
+#endif  // __CUDACC_RTC__
 
 #endif  // SB2_INTERNAL_H_
