@@ -306,14 +306,19 @@ def main():
         return
 
     peak, peak_src = measured_peak()
+    specialised = bool(shard.sim.isSpecialized())
     # dominant kernel = the fused stage kernel: 4 launches per step; algorithmic bytes of one step
     # spread over its launches ÷ the average launch duration (the timed region holds nothing else)
     achieved = cells * BYTES_PER_CELL_UPDATE * K / (ms * 1e-3) / 1e9
     traffic = ncu_traffic()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
-                "kernel": "rd_stage_kernel (fused RK stage: TMA-staged rows, bytecode reactions + diffusion stencil, RK combine in stage 4); "
+                "kernel": ("rd_jit_first / rd_jit_middle / rd_jit_final (rd_stage kernel compiled for this model's kinetics at set-up: "
+                           "TMA-staged rows, straight-line reactions + diffusion stencil, RK combine in stage 4); "
+                           if specialised else
+                           "rd_stage_kernel (fused RK stage: TMA-staged rows, bytecode reactions + diffusion stencil, RK combine in stage 4); ") +
                           "4 launches per step, figures are the average over the four",
+                "specialised": specialised, "specialise_info": shard.sim.getSpecializeInfo(),
                 "algorithmic_bytes_per_launch": cells * BYTES_PER_CELL_UPDATE / 4.0,
                 "avg_launch_ms": ms / (4.0 * K), "peak_source": peak_src, "rank": 0}
 

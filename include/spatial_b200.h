@@ -227,6 +227,12 @@ SB2_API int sb2_program_text(sb2_sim* sim, char* buf, int buflen);
  * sb2_specialized: 1 when the handle runs the specialised kernel.  sb2_specialize_info: text describing what
  * happened (library used, build time, or why the interpreter runs); returns the full length. */
 SB2_API int sb2_specialized(const sb2_sim* sim);
+/* Smaller grids get the same build from a background thread once the simulator has taken 256 steps (a short-lived
+ * simulator never pays for it); the kernel is swapped in at a step boundary, results unchanged.  SB2_JIT=background
+ * starts that build at sb2_finalize.  sb2_specialize_now: build (or wait for the running build) and install the kernel
+ * before returning; 1 when the specialised kernel is in place, 0 when the interpreter kernel stays (see
+ * sb2_specialize_info), negative on misuse. */
+SB2_API int sb2_specialize_now(sb2_sim* sim);
 SB2_API int sb2_specialize_info(const sb2_sim* sim, char* buf, int buflen);
 /* Builds the specialised kernel for a list of n token records (code = opcode * SB2_MAX_DEPTH + slot, arg) without
  * touching a GPU and writes the sm_100a cubin to cubin_path (may be NULL): build check and tests.  ns / np / w /

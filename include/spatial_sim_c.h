@@ -79,6 +79,10 @@ SSB_API void* ssb_get_device_handle(ssb_sim* s);                  /* sb2_sim* of
 SSB_API void ssb_device_state_changed(ssb_sim* s);
 /* text is copied into buf (NUL terminated, truncated to buflen); returns the full length */
 SSB_API int ssb_get_device_program_text(ssb_sim* s, char* buf, int buflen);
+/* model-specialised stage kernel (spatial_b200.h, sb2_specialized / sb2_specialize_info) */
+SSB_API int ssb_is_specialized(ssb_sim* s);
+SSB_API int ssb_get_specialize_info(ssb_sim* s, char* buf, int buflen);
+SSB_API int ssb_specialize_now(ssb_sim* s);   /* 1: specialised kernel in place, 0: interpreter kernel stays */
 SSB_API int ssb_get_setup_text(ssb_sim* s, const char* what, char* buf, int buflen);
 
 #ifdef __cplusplus

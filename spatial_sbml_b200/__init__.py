@@ -90,6 +90,10 @@ def _proto(lib):
         "sb2_combine_is_fused": (ci, [vp]),
         "sb2_launch_count": (C.c_int64, [vp]),
         "sb2_program_text": (ci, [vp, C.c_char_p, ci]),
+        "sb2_specialized": (ci, [vp]),
+        "sb2_specialize_info": (ci, [vp, C.c_char_p, ci]),
+        "sb2_specialize_now": (ci, [vp]),
+        "sb2_specialize_dry_run": (ci, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), ci, ci, ci, ci, ci, ci, ci, cs, C.c_char_p, ci]),
         # --- include/spatial_sim_c.h
         "ssb_new": (vp, []),
         "ssb_free": (None, [vp]),
@@ -131,6 +135,9 @@ def _proto(lib):
         "ssb_get_device_handle": (vp, [vp]),
         "ssb_device_state_changed": (None, [vp]),
         "ssb_get_device_program_text": (ci, [vp, C.c_char_p, ci]),
+        "ssb_is_specialized": (ci, [vp]),
+        "ssb_get_specialize_info": (ci, [vp, C.c_char_p, ci]),
+        "ssb_specialize_now": (ci, [vp]),
         "ssb_get_setup_text": (ci, [vp, cs, C.c_char_p, ci]),
     }
     for name, (res, args) in P.items():
@@ -150,6 +157,27 @@ def load_library():
         lib._prototypes = _proto(lib)
         _lib = lib
     return _lib
+
+
+# opcodes of the device bytecode (enum Sb2Opc, csrc/device/sb2_internal.h; the tests compare the two)
+RD_OPCODES = ["END", "PUSHC", "PUSHV", "PUSHF", "ADD", "SUB", "MUL", "DIV", "GEQ", "GT", "LEQ", "LT", "AND", "OR",
+              "ADDC", "SUBC", "MULC", "DIVC", "RSUBC", "RDIVC", "GEQC", "GTC", "LEQC", "LTC", "ADDV", "SUBV", "MULV", "DIVV",
+              "UNARY", "BINR", "MOV0", "MOVUP", "MASK", "ACCSUB", "ACCADD", "ACCSUB1", "ACCADD1", "ACCSUBC1", "ACCADDC1",
+              "ACCSUBM", "ACCADDM", "ADDVC", "SUBVC", "RSUBVC", "MULVC", "DIVVC", "RDIVVC", "ADDVV", "SUBVV", "MULVV", "DIVVV", "XFER"]
+SB2_MAX_DEPTH = 8
+
+
+def specialize_dry_run(records, ns, np_, w, depth, minb=2, d3=False, cubin_path=None):
+    """Builds the model-specialised stage kernel for a list of (opcode name, slot, arg) records with the CUDA
+    run-time compiler, without a GPU (sb2_specialize_dry_run).  Returns (rc, compiler log)."""
+    lib = load_library()
+    n = len(records)
+    code = (C.c_uint32 * max(n, 1))(*[RD_OPCODES.index(o) * SB2_MAX_DEPTH + d for o, d, a in records])
+    arg = (C.c_uint32 * max(n, 1))(*[a for o, d, a in records])
+    log = C.create_string_buffer(1 << 16)
+    rc = lib.sb2_specialize_dry_run(code, arg, n, ns, np_, w, depth, minb, 1 if d3 else 0,
+                                    cubin_path.encode() if cubin_path else None, log, len(log))
+    return rc, log.value.decode(errors="replace")
 
 
 def _dptr(a):
@@ -346,6 +374,17 @@ class SpatialSimulator(object):
         buf = C.create_string_buffer(n + 1)
         fn(self._h, *args, buf, n + 1)
         return buf.value.decode()
+
+    def isSpecialized(self):
+        """True when the stage kernel was built for this model's kinetics at set-up (NVRTC); the results are the same either way."""
+        return bool(self._lib.ssb_is_specialized(self._h))
+
+    def specializeNow(self):
+        """Builds (or waits for the background build of) the model-specialised stage kernel; True when it is in place."""
+        return self._lib.ssb_specialize_now(self._h) == 1
+
+    def getSpecializeInfo(self):
+        return self._text(self._lib.ssb_get_specialize_info)
 
     def getDeviceProgramText(self):
         return self._text(self._lib.ssb_get_device_program_text)

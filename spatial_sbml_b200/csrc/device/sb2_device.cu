@@ -83,6 +83,10 @@ struct sb2_sim {
   std::vector<Sb2RdTok> rdprog;  // lowered token records (constants patched per launch from rdslot)
   std::vector<int> rdslot;       // constants-table slot of each record's inline constant, -1 = none
   Sb2RdJit* jit;      // model-specialised build of the rd_stage kernel (rd_jit.cu), NULL: the interpreter kernel runs
+  Sb2RdJitJob* jit_job;  // build running in the background (picked up at a step boundary)
+  int jit_mode;          // 0 off, 1 build at finalize, 2 build in the background once the simulator has stepped for a while
+  int64_t steps_seen;
+  bool capturing;        // inside the stream capture of sb2_step
   std::string jit_info;
   uint32_t* d_dbg;    // SB2_DEBUG=1: device debug words, checked after every stage launch
   bool trace;         // SB2_TRACE=1: entry points report to stderr
@@ -418,6 +422,44 @@ void fill_stage_args(sb2_sim* sim, Sb2StageCore& a, int m, double dt, int row_be
   a.rows_per_block = rpb;
 }
 
+// Model-specialised stage kernel (rd_jit.cu).  background = false: build now (about a second).  background = true:
+// start the build on another thread, or - when one is running - install its result if it is ready (wait = true: block
+// until it is).  Installing bumps `version`: captured step graphs are rebuilt with the new kernel.
+Sb2RdJitSpec jit_spec(const sb2_sim* sim) {
+  Sb2RdJitSpec spec;
+  spec.ns = sim->base.S; spec.np = sim->rd.np; spec.w = sim->rd.w; spec.depth = sim->base.depth; spec.minb = 2; spec.d3 = sim->g.dim == 3;
+  return spec;
+}
+int specialise(sb2_sim* sim, bool background, bool wait) {
+  if (sim->jit || sim->rd_id < 0) return SB2_OK;
+  std::ostringstream os;
+  std::string jerr;
+  if (!background && !sim->jit_job) {
+    const auto t0 = std::chrono::steady_clock::now();
+    sim->jit = sb2_rd_jit_build(jit_spec(sim), sim->rdprog, &jerr);
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (sim->jit) os << "specialised kernel: " << sim->rdprog.size() << " records compiled in " << secs << " s with " << sb2_rd_jit_library();
+    else { os << "interpreter kernel: specialised build failed: " << jerr; sim->jit_mode = 0; }
+  } else {
+    if (!sim->jit_job) {
+      sim->jit_job = sb2_rd_jit_start(jit_spec(sim), sim->rdprog);
+      sim->jit_info = "interpreter kernel: specialised build running in the background";
+      if (!wait) return SB2_OK;
+    }
+    if (!wait && sb2_rd_jit_poll(sim->jit_job) == 0) return SB2_OK;
+    double secs = 0;
+    sim->jit = sb2_rd_jit_finish(sim->jit_job, &jerr, &secs);
+    sim->jit_job = NULL;
+    if (sim->jit) os << "specialised kernel: " << sim->rdprog.size() << " records compiled in " << secs << " s in the background with "
+                     << sb2_rd_jit_library() << ", in use from step " << sim->steps_seen;
+    else { os << "interpreter kernel: specialised build failed: " << jerr; sim->jit_mode = 0; }
+  }
+  sim->jit_info = os.str();
+  if (sim->jit) ++sim->version;
+  if (sim->trace) fprintf(stderr, "[sb2] %s\n", sim->jit_info.c_str());
+  return SB2_OK;
+}
+
 // One stage on rows [row_begin, row_end) of the slab axis with whichever kernel family the model runs on.
 int launch_stage_rows(sb2_sim* sim, int m, double dt, int row_begin, int row_end) {
   if (row_end <= row_begin) return SB2_OK;
@@ -530,6 +572,7 @@ int sb2_create(const sb2_grid* grid, sb2_sim** out) {
   sim->rd_id = -1; sim->d_cls = NULL; sim->nstrips = 0; sim->d_dbg = NULL;
   sim->h2d = NULL; sim->d2h = NULL; sim->ev_start = NULL; sim->d_rdtok = NULL; sim->rd_buf = 0; sim->multi_stream = false;
   sim->gexec[0] = sim->gexec[1] = NULL; sim->version = 1; sim->jit = NULL;
+  sim->jit_job = NULL; sim->jit_mode = 0; sim->steps_seen = 0; sim->capturing = false;
   sim->trace = getenv("SB2_TRACE") != NULL;
   memset(&sim->base, 0, sizeof(sim->base));
   *out = sim;
@@ -554,6 +597,7 @@ void sb2_destroy(sb2_sim* sim) {
   if (sim->d_cls) cudaFree(sim->d_cls);
   if (sim->d_rdtok) cudaFree(sim->d_rdtok);
   sb2_rd_jit_free(sim->jit);
+  if (sim->jit_job) sb2_rd_jit_abandon(sim->jit_job);
   for (int p = 0; p < 2; ++p) if (sim->gexec[p]) cudaGraphExecDestroy(sim->gexec[p]);
   if (sim->h2d) cudaStreamDestroy(sim->h2d);
   if (sim->d2h) cudaStreamDestroy(sim->d2h);
@@ -783,22 +827,17 @@ int sb2_finalize(sb2_sim* sim) {
     // model-specialised build (include/spatial_b200.h, sb2_specialized)
     {
       const char* jenv = getenv("SB2_JIT");
-      const bool off = jenv && !strcmp(jenv, "0"), require = jenv && !strcmp(jenv, "require");
-      const bool want = !off && (jenv ? true : ncells(sim) >= (1 << 20));
-      if (off) sim->jit_info = "interpreter kernel: SB2_JIT=0";
-      else if (!want) sim->jit_info = "interpreter kernel: grid below 2^20 cells (SB2_JIT=1 forces the specialised build)";
-      else {
-        Sb2RdJitSpec spec;
-        spec.ns = b.S; spec.np = sim->rd.np; spec.w = sim->rd.w; spec.depth = b.depth; spec.minb = 2; spec.d3 = sim->g.dim == 3;
-        std::string jerr;
-        const auto t0 = std::chrono::steady_clock::now();
-        sim->jit = sb2_rd_jit_build(spec, sim->rdprog, &jerr);
-        const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        std::ostringstream os;
-        if (sim->jit) os << "specialised kernel: " << sim->rdprog.size() << " records compiled in " << secs << " s with " << sb2_rd_jit_library();
-        else os << "interpreter kernel: specialised build failed: " << jerr;
-        sim->jit_info = os.str();
+      const bool require = jenv && !strcmp(jenv, "require");
+      if (jenv && !strcmp(jenv, "0")) { sim->jit_mode = 0; sim->jit_info = "interpreter kernel: SB2_JIT=0"; }
+      else if (jenv && !strcmp(jenv, "background")) sim->jit_mode = 2;
+      else if (jenv) sim->jit_mode = 1;
+      else sim->jit_mode = ncells(sim) >= (1 << 20) ? 1 : 2;
+      if (sim->jit_mode == 1) {
+        specialise(sim, false, true);
         if (!sim->jit && require) return fail(sim, SB2_ERR_STATE, sim->jit_info);
+      } else if (sim->jit_mode == 2) {
+        if (jenv) specialise(sim, true, false);  // SB2_JIT=background: start right away
+        else sim->jit_info = "interpreter kernel: the specialised build starts in the background after 256 steps";
       }
       if (sim->trace) fprintf(stderr, "[sb2] %s\n", sim->jit_info.c_str());
     }
@@ -842,6 +881,10 @@ int sb2_begin_step(sb2_sim* sim, double t_arg, double dt, int time_slot) {
     sim->consts[time_slot] = t_arg * dt;  // sim_time = t * dt, spatialsimulator.cpp:1358
   }
   sim->cur_dt = dt;
+  // tiered specialisation: a simulator that keeps stepping gets its own stage kernel, built in the background and
+  // picked up here, at a step boundary (never inside a stream capture)
+  ++sim->steps_seen;
+  if (sim->jit_mode == 2 && !sim->jit && !sim->capturing && (sim->jit_job || sim->steps_seen > 256)) specialise(sim, true, false);
   // A Neumann flux that is exactly zero adds +0.0 everywhere (all shipped models): the boundary
   // passes are skipped and the combine can be fused.  A non-zero flux takes the un-fused schedule,
   // which reproduces the reference's order of additions including the flux carried in k0.
@@ -1020,7 +1063,9 @@ int sb2_step(sb2_sim* sim, double t_arg, double t_incr, double dt, int nsteps, i
       cudaError_t e = cudaStreamBeginCapture(sim->stream, cudaStreamCaptureModeThreadLocal);
       rc = SB2_OK;
       if (e == cudaSuccess) {
+        sim->capturing = true;
         for (int k = 0; k < 2 && !rc; ++k) rc = one_plain_step(sim, t_arg + (i + k) * t_incr, dt, time_slot);
+        sim->capturing = false;
         e = cudaStreamEndCapture(sim->stream, &graph);
       }
       if (e == cudaSuccess && !rc && graph) e = cudaGraphInstantiate(&sim->gexec[par], graph, 0);
@@ -1041,6 +1086,7 @@ int sb2_step(sb2_sim* sim, double t_arg, double t_incr, double dt, int nsteps, i
     if (sim->gexec[par] && pairs > 0) {
       for (int r = 0; r < pairs; ++r) CK(cudaGraphLaunch(sim->gexec[par], sim->stream));
       sim->launches += sim->g_launches[par] * (pairs - (fresh ? 1 : 0));
+      sim->steps_seen += 2 * (pairs - (fresh ? 1 : 0));
       i += 2 * pairs;
     } else if (fresh) {
       // captured but nothing to replay (cannot happen with nsteps >= 12): execute the captured pair once
@@ -1230,6 +1276,15 @@ int sb2_combine_is_fused(const sb2_sim* sim) { return sim && sim->fuse_combine ?
 int64_t sb2_launch_count(const sb2_sim* sim) { return sim ? sim->launches : 0; }
 
 int sb2_specialized(const sb2_sim* sim) { return sim && sim->jit ? 1 : 0; }
+
+int sb2_specialize_now(sb2_sim* sim) {
+  if (!sim || !sim->finalized) return fail(sim, SB2_ERR_STATE, "simulator not finalized");
+  if (sim->in_step) return fail(sim, SB2_ERR_STATE, "sb2_specialize_now inside a step");
+  cudaSetDevice(sim->g.device);
+  if (sim->rd_id < 0 || (sim->jit_mode == 0 && !sim->jit)) return 0;  // SB2_JIT=0, or an earlier build failed
+  specialise(sim, sim->jit_job != NULL, true);
+  return sim->jit ? 1 : 0;
+}
 
 int sb2_specialize_info(const sb2_sim* sim, char* buf, int buflen) {
   if (!sim || !buf || buflen <= 0) return SB2_ERR_ARG;

@@ -133,6 +133,13 @@ int sb2_rd_jit_compile(const std::string& src, std::vector<char>* cubin, std::st
 Sb2RdJit* sb2_rd_jit_build(const Sb2RdJitSpec& spec, const std::vector<Sb2RdTok>& prog, std::string* err);
 cudaError_t sb2_rd_jit_launch(Sb2RdJit* j, const Sb2RdArgs& a, const double* kc, int nkc, cudaStream_t stream);
 void sb2_rd_jit_free(Sb2RdJit* j);
+// the same build on a background thread: start, poll (0 running, 1 compiled, -1 failed), finish (waits, loads, frees the
+// job) or abandon (the thread finishes on its own)
+struct Sb2RdJitJob;
+Sb2RdJitJob* sb2_rd_jit_start(const Sb2RdJitSpec& spec, const std::vector<Sb2RdTok>& prog);
+int sb2_rd_jit_poll(Sb2RdJitJob* job);
+Sb2RdJit* sb2_rd_jit_finish(Sb2RdJitJob* job, std::string* err, double* secs);
+void sb2_rd_jit_abandon(Sb2RdJitJob* job);
 const char* sb2_rd_jit_library();  // path of the NVRTC library in use ("" when none was found)
 
 struct Sb2CombineArgs {

@@ -117,6 +117,9 @@ int ssb_get_num_staged_species(ssb_sim* s) { return s ? s->sim.getNumStagedSpeci
 long ssb_get_device_launch_count(ssb_sim* s) { return s ? s->sim.getDeviceLaunchCount() : 0; }
 void ssb_device_state_changed(ssb_sim* s) { if (s) s->sim.deviceStateChanged(); }
 void* ssb_get_device_handle(ssb_sim* s) { return s ? s->sim.getDeviceHandle() : NULL; }
+int ssb_is_specialized(ssb_sim* s) { return s && s->sim.isSpecialized() ? 1 : 0; }
+int ssb_specialize_now(ssb_sim* s) { return s && s->sim.specializeNow() ? 1 : 0; }
+int ssb_get_specialize_info(ssb_sim* s, char* buf, int buflen) { return s ? copyText(s->sim.getSpecializeInfo(), buf, buflen) : 0; }
 int ssb_get_device_program_text(ssb_sim* s, char* buf, int buflen) { return s ? copyText(s->sim.getDeviceProgramText(), buf, buflen) : 0; }
 int ssb_get_setup_text(ssb_sim* s, const char* what, char* buf, int buflen) { return s && what ? copyText(s->sim.getSetupText(what), buf, buflen) : 0; }
 

@@ -986,6 +986,17 @@ double SpatialSimulator::getVariableAt(const std::string& id, int x, int y, int 
 // =============================================================================================
 // inspection
 // =============================================================================================
+bool SpatialSimulator::specializeNow() { return impl && impl->dev && sb2_specialize_now(impl->dev) == 1; }
+
+bool SpatialSimulator::isSpecialized() { return impl && impl->dev && sb2_specialized(impl->dev) == 1; }
+
+std::string SpatialSimulator::getSpecializeInfo() {
+  if (!impl || !impl->dev) return "";
+  std::vector<char> buf(1 << 14);
+  sb2_specialize_info(impl->dev, buf.data(), (int)buf.size());
+  return std::string(buf.data());
+}
+
 std::string SpatialSimulator::getDeviceProgramText() {
   if (!impl || !impl->dev) return "";
   std::vector<char> buf(1 << 16);

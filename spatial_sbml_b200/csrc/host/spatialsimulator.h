@@ -106,6 +106,10 @@ class __attribute__((visibility("default"))) SpatialSimulator {
   // oneStep() then throws.
   void setHostOnly(bool hostOnly);
   std::string getDeviceProgramText();
+  // model-specialised stage kernel (include/spatial_b200.h, sb2_specialized): whether it runs, and what happened at set-up
+  bool isSpecialized();
+  bool specializeNow();  // build it (or wait for the background build) before returning
+  std::string getSpecializeInfo();
   std::string getSetupText(const std::string& what);  // "rxn/<i>", "geo/<compartment>", "summary"
   void* getDeviceHandle();  // sb2_sim*
   SimImpl* getImpl() { return impl; }

@@ -197,3 +197,86 @@ def test_set_parameter_reaches_uniform_variables():
         assert line.endswith("value 123.25"), line
     sim.setParameter("no_such_parameter", 1.0)  # unknown ids are ignored, as in the reference
     sim.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# model-specialised stage kernel: the run-time build needs no GPU, only libnvrtc
+# ---------------------------------------------------------------------------------------------
+TURING_RECORDS = [("MULVC", 0, 0), ("MULV", 0, 1), ("XFER", 0, 1), ("ACCADDC1", 0, 0), ("ACCADDC1", 1, 0),
+                  ("MULVC", 0, 1), ("ADDVC", 1, 1), ("RDIVC", 1, 0), ("MUL", 1, 0), ("ACCSUB1", 1, 0)]
+
+
+def test_python_opcode_table_matches_the_device_header():
+    text = open(os.path.join(REPO, "spatial_sbml_b200", "csrc", "device", "sb2_internal.h")).read()
+    body = re.sub(r"//[^\n]*", "", re.search(r"enum Sb2Opc \{(.*?)\};", text, re.S).group(1))
+    values, v = {}, -1
+    for item in [i.strip() for i in body.split(",") if i.strip()]:
+        if "=" in item:
+            name, expr = [x.strip() for x in item.split("=")]
+            v = values[expr] if expr in values else int(expr)
+        else:
+            name, v = item, v + 1
+        values[name] = v
+    for i, name in enumerate(sb.RD_OPCODES):
+        assert values["OPC_" + name] == i, name
+    assert values["OPC_RD_COUNT"] == len(sb.RD_OPCODES)
+    assert "#define SB2_MAX_DEPTH %d " % sb.SB2_MAX_DEPTH in open(os.path.join(REPO, "include", "spatial_b200.h")).read()
+
+
+def _nvrtc_present():
+    import ctypes
+    for name in (os.environ.get("SB2_NVRTC_LIB"), "libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12"):
+        if not name:
+            continue
+        try:
+            ctypes.CDLL(name)
+            return True
+        except OSError:
+            pass
+    return False
+
+
+@pytest.mark.skipif(not _nvrtc_present(), reason="libnvrtc.so.12 not installed")
+@pytest.mark.parametrize("d3", [False, True])
+def test_specialised_kernel_builds_without_a_gpu(tmp_path, d3):
+    """The Turing law (as the lowering pass emits it) expands to straight-line code that NVRTC compiles for sm_100a."""
+    cubin = str(tmp_path / "turing.cubin")
+    rc, log = sb.specialize_dry_run(TURING_RECORDS, ns=2, np_=2, w=8, depth=2, minb=2, d3=d3, cubin_path=cubin)
+    assert rc == 0, log
+    assert "error" not in log.lower(), log
+    data = open(cubin, "rb").read()
+    assert data[:4] == b"\x7fELF"
+    for name in (b"rd_jit_first", b"rd_jit_middle", b"rd_jit_final"):
+        assert name in data
+
+
+@pytest.mark.skipif(not _nvrtc_present(), reason="libnvrtc.so.12 not installed")
+def test_specialised_build_covers_every_opcode():
+    """One record of every instruction form (stack slots chosen so that the program is well formed) compiles."""
+    recs = [("PUSHC", 0, 0), ("PUSHV", 1, 0), ("PUSHF", 2, 3)]
+    for op in ("ADD", "SUB", "MUL", "DIV", "GEQ", "GT", "LEQ", "LT", "AND", "OR"):
+        recs += [("PUSHV", 2, 1), (op, 2, 0)]
+    for op in ("ADDC", "SUBC", "MULC", "DIVC", "RSUBC", "RDIVC", "GEQC", "GTC", "LEQC", "LTC"):
+        recs.append((op, 1, 0))
+    for op in ("ADDV", "SUBV", "MULV", "DIVV"):
+        recs.append((op, 1, 1))
+    for op in ("ADDVC", "SUBVC", "RSUBVC", "MULVC", "DIVVC", "RDIVVC"):
+        recs.append((op, 2, 1))
+    for op in ("ADDVV", "SUBVV", "MULVV", "DIVVV"):
+        recs.append((op, 2, 0 | (1 << 8)))
+    for fn in (sb.OPS["EXP"], sb.OPS["NOT"], sb.OPS["ROOT"]):
+        recs.append(("UNARY", 2, fn))
+    for fn in (sb.OPS["POWER"], sb.OPS["LOG"], sb.OPS["XOR"], sb.OPS["EQ"], sb.OPS["NEQ"]):
+        recs += [("PUSHV", 3, 0), ("BINR", 3, fn)]
+    recs += [("MOVUP", 2, 0), ("MOV0", 3, 0), ("MASK", 0, 1)]
+    for op in ("ACCSUB", "ACCADD", "ACCSUB1", "ACCADD1", "ACCSUBC1", "ACCADDC1", "ACCSUBM", "ACCADDM"):
+        recs.append((op, 1, 0))
+    recs.append(("XFER", 0, 2))
+    assert {r[0] for r in recs} == set(sb.RD_OPCODES) - {"END"}
+    rc, log = sb.specialize_dry_run(recs, ns=3, np_=2, w=4, depth=4)
+    assert rc == 0, log
+
+
+def test_specialised_build_rejects_oversized_programs():
+    rc, log = sb.specialize_dry_run([("ADDC", 0, 0)] * 385, ns=2, np_=2, w=8, depth=1)  # SB2_RD_MAX_TOKENS = 384
+    assert rc == -1

@@ -294,3 +294,143 @@ def test_awkward_grid_sizes_against_the_restated_oracle(dims):
     for sp in ("species_1", "species_2"):
         assert np.array_equal(sim.getVariableCompact(sp), orc.sp[sp].u), (dims, sp)
     sim.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# model-specialised stage kernel (NVRTC build of the model's token records, csrc/device/rd_jit.cu)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["turing_blob", "brusselator_nonunit", "fish_dirichlet", "transport_rate", "advection",
+                                  "syn_brusselator_3d", "syn_turing_3d", "turing_tiny_flux"])
+def test_specialised_kernel_matches_reference(case, monkeypatch):
+    """SB2_JIT=require: the stage kernel is compiled for the model's own kinetics at set-up (a failed build is an error);
+    the trajectory must match the reference's golden fields like the interpreter kernel's does."""
+    import spatial_sbml_b200 as sb
+    monkeypatch.setenv("SB2_JIT", "require")
+    g = load_golden(case)
+    nx, ny, nz = [int(v) for v in g["dims"]]
+    dt = float(g["dt"])
+    sim = sb.SpatialSimulator()
+    sim.initFromFile(model_path(case), nx, ny, nz)
+    assert sim.isSpecialized(), sim.getSpecializeInfo()
+    assert sim.getSpecializeInfo().startswith("specialised kernel")
+    done = 0
+    for target in [int(s) for s in g["steps"]]:
+        if target > 100:
+            break
+        sim.runSteps(done, dt, target - done)
+        done = target
+        tol = LOOSE.get(case, {}).get(target, 1e-10)
+        for sp in [str(s) for s in g["species"]]:
+            assert rel_linf(sim.getVariableCompact(sp), g["step/%d/%s" % (target, sp)]) <= tol, (case, target, sp)
+    sim.close()
+
+
+@pytest.mark.parametrize("dims,dt", [((1536, 1024, 1), 0.07), ((1000, 515, 1), 0.07), ((160, 96, 72), 0.02)])
+def test_specialised_and_interpreter_kernels_agree_bit_for_bit(dims, dt, monkeypatch):
+    """Same arithmetic in the same order (the interpreter's cases and the generated code are expansions of the same
+    macros): identical fields after 6 steps, with a kinetic constant changed on the way (no rebuild needed: the
+    constants travel in the kernel parameters)."""
+    import spatial_sbml_b200 as sb
+    from spatial_sbml_b200 import synthetic
+    model = synthetic.brusselator(dims[0], dims[1], dims[2] if dims[2] > 1 else None, perturb=True)
+    out = {}
+    for mode in ("require", "0"):
+        monkeypatch.setenv("SB2_JIT", mode)
+        sim = sb.SpatialSimulator()
+        sim.initFromString(model, *dims)
+        assert sim.isSpecialized() == (mode == "require"), sim.getSpecializeInfo()
+        sim.runSteps(0, dt, 3)
+        sim.setParameter("B", 4.0)
+        for t in range(3, 6):
+            sim.oneStep(t, dt)
+        out[mode] = [sim.getVariableCompact(sp) for sp in ("X", "Y")]
+        sim.close()
+    for a, b in zip(out["require"], out["0"]):
+        assert np.isfinite(a).all() and a.std() > 0
+        assert np.array_equal(a, b)
+
+
+def test_specialised_kernel_is_the_default_on_large_grids(monkeypatch):
+    """>= 2^20 cells: built at set-up without being asked for; below: the interpreter kernel first (a background build
+    follows once the simulator has stepped for a while); SB2_JIT=0 always turns it off."""
+    import spatial_sbml_b200 as sb
+    from spatial_sbml_b200 import synthetic
+    monkeypatch.delenv("SB2_JIT", raising=False)
+    big = sb.SpatialSimulator()
+    big.initFromString(synthetic.turing(1024, 1024), 1024, 1024, 1)
+    assert big.isSpecialized(), big.getSpecializeInfo()
+    big.close()
+    small = sb.SpatialSimulator()
+    small.initFromString(synthetic.turing(512, 512), 512, 512, 1)
+    assert not small.isSpecialized()
+    assert "after 256 steps" in small.getSpecializeInfo()
+    small.close()
+    monkeypatch.setenv("SB2_JIT", "0")
+    off = sb.SpatialSimulator()
+    off.initFromString(synthetic.turing(1024, 1024), 1024, 1024, 1)
+    assert not off.isSpecialized()
+    assert not off.specializeNow()
+    off.close()
+
+
+@pytest.mark.parametrize("chunk", [50, 1])
+def test_background_specialisation_swaps_kernels_without_changing_results(chunk, monkeypatch):
+    """A small grid that keeps stepping: after 256 steps the specialised build starts on a background thread and is
+    swapped in at a later step boundary (with chunk = 50 under CUDA-graph replay, whose graphs are re-captured).
+    Whenever the swap happens, the trajectory is the interpreter kernel's, bit for bit."""
+    import time
+    import spatial_sbml_b200 as sb
+    g = load_golden("brusselator_300")
+    nx, ny, nz = [int(v) for v in g["dims"]]
+    dt = float(g["dt"])
+    monkeypatch.delenv("SB2_JIT", raising=False)
+    a = sb.SpatialSimulator()
+    a.initFromFile(model_path("brusselator_300"), nx, ny, nz)
+    assert not a.isSpecialized()
+    done = 0
+    t_end = time.time() + 60
+    while not a.isSpecialized() and time.time() < t_end:
+        if chunk > 1:
+            a.runSteps(done, dt, chunk)
+        else:
+            a.oneStep(done, dt)
+        done += chunk
+        if done > 300 and chunk == 1:
+            time.sleep(0.001)
+    assert a.isSpecialized(), a.getSpecializeInfo()
+    assert "in the background" in a.getSpecializeInfo()
+    assert done > 256
+    extra = 100 - done % 100 + 100  # some steps on the new kernel
+    a.runSteps(done, dt, extra)
+    done += extra
+    monkeypatch.setenv("SB2_JIT", "0")
+    b = sb.SpatialSimulator()
+    b.initFromFile(model_path("brusselator_300"), nx, ny, nz)
+    b.runSteps(0, dt, done)
+    assert not b.isSpecialized()
+    for sp in [str(s) for s in g["species"]]:
+        assert np.array_equal(a.getVariableCompact(sp), b.getVariableCompact(sp)), (sp, done)
+    a.close()
+    b.close()
+
+
+def test_specialize_now_installs_the_kernel_between_steps(monkeypatch):
+    import spatial_sbml_b200 as sb
+    g = load_golden("turing_blob")
+    nx, ny, nz = [int(v) for v in g["dims"]]
+    dt = float(g["dt"])
+    for mode in (None, "background"):
+        if mode:
+            monkeypatch.setenv("SB2_JIT", mode)
+        else:
+            monkeypatch.delenv("SB2_JIT", raising=False)
+        sim = sb.SpatialSimulator()
+        sim.initFromFile(model_path("turing_blob"), nx, ny, nz)
+        assert not sim.isSpecialized()
+        sim.runSteps(0, dt, 5)
+        assert sim.specializeNow(), sim.getSpecializeInfo()
+        assert sim.isSpecialized()
+        sim.runSteps(5, dt, 5)
+        for sp in [str(s) for s in g["species"]]:
+            assert rel_linf(sim.getVariableCompact(sp), g["step/10/%s" % sp]) <= 1e-10
+        sim.close()
