@@ -8,12 +8,14 @@ cudaError_t sb2_rd_launch_v2(const Sb2RdArgs& a, cudaStream_t stream);
 cudaError_t sb2_rd_launch_v3(const Sb2RdArgs& a, cudaStream_t stream);
 cudaError_t sb2_rd_launch_v4(const Sb2RdArgs& a, cudaStream_t stream);
 cudaError_t sb2_rd_launch_v5(const Sb2RdArgs& a, cudaStream_t stream);
+cudaError_t sb2_rd_launch_v6(const Sb2RdArgs& a, cudaStream_t stream);
 
 namespace {
 // id, max species, cell pairs per thread, warps per CTA, expression stack depth
 const Sb2RdVariant kVariants[] = {
-  {0, 2, 4, 4, 2}, {1, 2, 2, 8, 4}, {2, 2, 1, 8, 8}, {3, 4, 2, 4, 4}, {4, 4, 1, 4, 8}, {5, 2, 2, 8, 2},
+  {0, 2, 4, 4, 2}, {1, 2, 2, 8, 4}, {2, 2, 1, 8, 8}, {3, 4, 2, 4, 4}, {4, 4, 1, 4, 8}, {5, 2, 2, 8, 2}, {6, 4, 1, 8, 8},
 };
+const int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
 
 // One warp per (row, strip): class 1 when every cell of the strip row carries exactly SB2_F_DOMAIN in every
 // geometry (interior cell, no boundary bit), class 2 when no cell is in any domain, else 0.
@@ -43,10 +45,14 @@ __global__ void __launch_bounds__(256) classify_kernel(const uint8_t* f0, const 
 int sb2_rd_pick_variant(int dim, int nx, int nspecies, int depth, Sb2RdVariant* out) {
   if ((dim != 2 && dim != 3) || nspecies < 1 || nspecies > 4) return -1;
   int id;
-  if (nspecies <= 2) id = (depth <= 4 && nx >= 192) ? 1 : 2;  // (measured at 8192^2: variant 1 beats 0 and 5)
+  if (dim == 3) {
+    // the z-marching kernel keeps four plane tiles of W + 2 rows in shared memory: 8 warps and 2 cells per thread leave
+    // room for three CTAs per SM with two species
+    id = nspecies <= 2 ? 2 : 6;
+  } else if (nspecies <= 2) id = (depth <= 4 && nx >= 192) ? 1 : 2;  // (measured at 8192^2: variant 1 beats 0 and 5)
   else id = (depth <= 4 && nx >= 192) ? 3 : 4;
   const char* force = getenv("SB2_RD_VARIANT");  // experiments: force a variant that fits the model
-  if (force && atoi(force) >= 0 && atoi(force) < 6 && kVariants[atoi(force)].ns >= nspecies) id = atoi(force);
+  if (force && atoi(force) >= 0 && atoi(force) < kNumVariants && kVariants[atoi(force)].ns >= nspecies) id = atoi(force);
   if (depth > kVariants[id].depth) return -1;
   if (out) *out = kVariants[id];
   return id;
@@ -60,6 +66,7 @@ cudaError_t sb2_rd_launch(const Sb2RdArgs& a, cudaStream_t stream) {
     case 3: return sb2_rd_launch_v3(a, stream);
     case 4: return sb2_rd_launch_v4(a, stream);
     case 5: return sb2_rd_launch_v5(a, stream);
+    case 6: return sb2_rd_launch_v6(a, stream);
     default: return cudaErrorInvalidValue;
   }
 }

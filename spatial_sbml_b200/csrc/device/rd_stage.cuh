@@ -180,6 +180,388 @@ __device__ __forceinline__ double div6(double x) {
 #define RD_REP_D0(M) M(0) M(1) M(2) M(3) M(4) M(5) M(6) M(7)
 #define RD_REP_D1(M) M(1) M(2) M(3) M(4) M(5) M(6) M(7)
 
+// Diffusion stencil (calcPDE.cpp:484-559) and output of one strip row: k_m, or on the last stage the new u.
+// acc holds the reaction terms of the thread's cells; cur0 / up0 / dn0 (and, with ZS, zp0 / zm0) point at this lane's
+// first cell in the w rows y, y+1, y-1 (z+1, z-1) of species 0, species s sits sstride doubles further.
+template <int NS, int NP, int MODE, bool D3, bool ZS>
+__device__ __forceinline__ void rd_emit_row(const Sb2RdArgs& A, const int S, const int cls, const int lane, const bool (&active)[NP],
+                                            const uint32_t (&fl)[2 * NP], double (&acc)[NS][2 * NP], const int64_t idx0,
+                                            const double* mycs, const double* cur0, const double* up0, const double* dn0,
+                                            const double* zp0, const double* zm0, const int sstride) {
+  constexpr int SW = 64 * NP;
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    if (s < S) {
+      const Sb2SpeciesArgs& sp = A.sp[s];
+      const double* cur = cur0 + s * sstride;
+      const double* up = up0 + s * sstride;
+      const double* dn = dn0 + s * sstride;
+      const double* zp = ZS ? zp0 + s * sstride : nullptr;  // ZS: the z neighbours' w rows are in shared memory too
+      const double* zm = ZS ? zm0 + s * sstride : nullptr;
+      // Uniform coefficients, no division by dx^2: straight-line stencil, additions in the reference's order Xp, Xm, Yp,
+      // Ym (, Zp, Zm).  MASKED = false: every cell of the strip row is an interior cell, no per-cell test at all.
+      // MASKED = true (mixed strip rows): the same arithmetic, every addition under a predicate built from the cell's
+      // flag byte, outputs selected by the domain bit (neighbour values outside a domain are finite, never used).
+      auto straight = [&](auto masked_tag) {
+        constexpr bool MASKED = decltype(masked_tag)::value;
+        const double dcx = sp.dconst[0], dcy = sp.dconst[1];
+        double2 cu[NP], ck0[NP], ck1[NP], ck2[NP];
+        if (MODE == MODE_FINAL) {
+#pragma unroll
+          for (int p = 0; p < NP; ++p) {
+            const int64_t i = idx0 + p * 64;
+            cu[p] = ck2[p] = make_double2(0.0, 0.0);
+            if (!MASKED || active[p]) {
+              cu[p] = *reinterpret_cast<const double2*>(sp.u + i);        // L2 hits: staged through L2 one batch ago
+              ck2[p] = *reinterpret_cast<const double2*>(sp.kprev + i);
+            }
+            ck0[p] = *reinterpret_cast<const double2*>(mycs + (s * 2) * SW + p * 64 + 2 * lane);
+            ck1[p] = *reinterpret_cast<const double2*>(mycs + (s * 2 + 1) * SW + p * 64 + 2 * lane);
+          }
+        }
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          const uint32_t f0 = MASKED ? (fl[2 * p] >> (8 * sp.geo)) & 0xffu : (uint32_t)SB2_F_DOMAIN;
+          const uint32_t f1 = MASKED ? (fl[2 * p + 1] >> (8 * sp.geo)) & 0xffu : (uint32_t)SB2_F_DOMAIN;
+#define RD_ADD(acc_, f_, bit_, term_) if (!MASKED || ((f_) & (SB2_F_DOMAIN | (bit_))) == SB2_F_DOMAIN) acc_ = dadd(acc_, term_)
+          double a0 = acc[s][2 * p], a1 = acc[s][2 * p + 1];
+          if (sp.has_diff) {
+            const double2 wc = *reinterpret_cast<const double2*>(cur + p * 64);
+            const double wl = cur[p * 64 - 1], wr = cur[p * 64 + 2];
+            const double2 wu = *reinterpret_cast<const double2*>(up + p * 64);
+            const double2 wd = *reinterpret_cast<const double2*>(dn + p * 64);
+            RD_ADD(a0, f0, SB2_F_XP, dmul(dcx, dsub(wc.y, wc.x)));
+            RD_ADD(a0, f0, SB2_F_XM, dmul(dcx, dsub(wl, wc.x)));
+            RD_ADD(a0, f0, SB2_F_YP, dmul(dcy, dsub(wu.x, wc.x)));
+            RD_ADD(a0, f0, SB2_F_YM, dmul(dcy, dsub(wd.x, wc.x)));
+            RD_ADD(a1, f1, SB2_F_XP, dmul(dcx, dsub(wr, wc.y)));
+            RD_ADD(a1, f1, SB2_F_XM, dmul(dcx, dsub(wc.x, wc.y)));
+            RD_ADD(a1, f1, SB2_F_YP, dmul(dcy, dsub(wu.y, wc.y)));
+            RD_ADD(a1, f1, SB2_F_YM, dmul(dcy, dsub(wd.y, wc.y)));
+            if (D3) {  // Zp, Zm
+              const double dcz = sp.dconst[2];
+              const int64_t i = idx0 + p * 64;
+              double2 wzp = make_double2(0.0, 0.0), wzm = wzp;
+              if (ZS) {
+                wzp = *reinterpret_cast<const double2*>(zp + p * 64);
+                wzm = *reinterpret_cast<const double2*>(zm + p * 64);
+              } else if (!MASKED || active[p]) {
+                wzp = *reinterpret_cast<const double2*>(sp.u + i + A.PL);
+                wzm = *reinterpret_cast<const double2*>(sp.u + i - A.PL);
+                if (MODE != MODE_FIRST) {
+                  const double2 kzp = *reinterpret_cast<const double2*>(sp.kprev + i + A.PL);
+                  const double2 kzm = *reinterpret_cast<const double2*>(sp.kprev + i - A.PL);
+                  wzp.x = dadd(wzp.x, dmul(A.cdt, kzp.x)); wzp.y = dadd(wzp.y, dmul(A.cdt, kzp.y));
+                  wzm.x = dadd(wzm.x, dmul(A.cdt, kzm.x)); wzm.y = dadd(wzm.y, dmul(A.cdt, kzm.y));
+                }
+              }
+              RD_ADD(a0, f0, SB2_F_ZP, dmul(dcz, dsub(wzp.x, wc.x)));
+              RD_ADD(a0, f0, SB2_F_ZM, dmul(dcz, dsub(wzm.x, wc.x)));
+              RD_ADD(a1, f1, SB2_F_ZP, dmul(dcz, dsub(wzp.y, wc.y)));
+              RD_ADD(a1, f1, SB2_F_ZM, dmul(dcz, dsub(wzm.y, wc.y)));
+            }
+          }
+#undef RD_ADD
+          const bool in0 = !MASKED || (f0 & SB2_F_DOMAIN), in1 = !MASKED || (f1 & SB2_F_DOMAIN);
+          if (MASKED && !active[p]) continue;
+          if (MODE != MODE_FINAL) {
+            *reinterpret_cast<double2*>(sp.kout + idx0 + p * 64) = make_double2(in0 ? a0 : 0.0, in1 ? a1 : 0.0);
+          } else {
+            // value += dt*(k0 + 2.0*k1 + 2.0*k2 + k3)/6.0, spatialsimulator.cpp:1535
+            double inc[2];
+            inc[0] = dmul(A.dt, dadd(dadd(dadd(ck0[p].x, dmul(2.0, ck1[p].x)), dmul(2.0, ck2[p].x)), a0));
+            inc[1] = dmul(A.dt, dadd(dadd(dadd(ck0[p].y, dmul(2.0, ck1[p].y)), dmul(2.0, ck2[p].y)), a1));
+            div6_batch<2>(inc);
+            *reinterpret_cast<double2*>(sp.u_out + idx0 + p * 64) =
+                make_double2(in0 ? dadd(cu[p].x, inc[0]) : cu[p].x, in1 ? dadd(cu[p].y, inc[1]) : cu[p].y);
+          }
+        }
+      };
+      if (sp.fastpath || !sp.has_diff) {
+        if (cls == 1) straight(BoolTag<false>());
+        else straight(BoolTag<true>());
+        continue;
+      }
+      // general path: per-cell domain / boundary flags, field-valued coefficients, dx^2 != 1.  Every stencil term
+      // is computed unconditionally (neighbour values outside the domain are finite) and added under a predicate,
+      // so the only branches are the warp-uniform ones on the coefficient kind and on dx^2 == 1.
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        const int64_t idx = idx0 + p * 64;
+        const uint32_t f0 = (fl[2 * p] >> (8 * sp.geo)) & 0xffu;
+        const uint32_t f1 = (fl[2 * p + 1] >> (8 * sp.geo)) & 0xffu;
+        double a0 = acc[s][2 * p], a1 = acc[s][2 * p + 1];
+        if (sp.has_diff) {
+          const double2 wc = *reinterpret_cast<const double2*>(cur + p * 64);
+          // one axis: the plus / minus neighbours of both cells, the flag bits that switch each term off
+          auto axis = [&](int ax, double n0p, double n0m, double n1p, double n1m, uint32_t bitp, uint32_t bitm) {
+            if (sp.dkind[ax] == SB2_SRC_NONE) return;
+            double d0, d1;
+            if (sp.dkind[ax] == SB2_SRC_CONST) { d0 = d1 = sp.dconst[ax]; }
+            else {
+              double2 dv = make_double2(0.0, 0.0);
+              if (active[p]) dv = *reinterpret_cast<const double2*>(A.fields[sp.dsrc[ax]] + idx);
+              d0 = dv.x; d1 = dv.y;
+            }
+            double t0p = dmul(d0, dsub(n0p, wc.x)), t0m = dmul(d0, dsub(n0m, wc.x));
+            double t1p = dmul(d1, dsub(n1p, wc.y)), t1m = dmul(d1, dsub(n1m, wc.y));
+            if (A.divide[ax]) {
+              t0p = ddiv_pos(t0p, A.dx2[ax]); t0m = ddiv_pos(t0m, A.dx2[ax]);
+              t1p = ddiv_pos(t1p, A.dx2[ax]); t1m = ddiv_pos(t1m, A.dx2[ax]);
+            }
+            if ((f0 & (SB2_F_DOMAIN | bitp)) == SB2_F_DOMAIN) a0 = dadd(a0, t0p);
+            if ((f0 & (SB2_F_DOMAIN | bitm)) == SB2_F_DOMAIN) a0 = dadd(a0, t0m);
+            if ((f1 & (SB2_F_DOMAIN | bitp)) == SB2_F_DOMAIN) a1 = dadd(a1, t1p);
+            if ((f1 & (SB2_F_DOMAIN | bitm)) == SB2_F_DOMAIN) a1 = dadd(a1, t1m);
+          };
+          {
+            const double wl = cur[p * 64 - 1], wr = cur[p * 64 + 2];
+            axis(0, wc.y, wl, wr, wc.x, SB2_F_XP, SB2_F_XM);
+          }
+          {
+            const double2 wu = *reinterpret_cast<const double2*>(up + p * 64);
+            const double2 wd = *reinterpret_cast<const double2*>(dn + p * 64);
+            axis(1, wu.x, wd.x, wu.y, wd.y, SB2_F_YP, SB2_F_YM);
+          }
+          if (D3) {
+            double2 wzp = make_double2(0.0, 0.0), wzm = wzp;
+            if (ZS) {
+              wzp = *reinterpret_cast<const double2*>(zp + p * 64);
+              wzm = *reinterpret_cast<const double2*>(zm + p * 64);
+            } else if (active[p] && sp.dkind[2] != SB2_SRC_NONE) {
+              wzp = *reinterpret_cast<const double2*>(sp.u + idx + A.PL);
+              wzm = *reinterpret_cast<const double2*>(sp.u + idx - A.PL);
+              if (MODE != MODE_FIRST) {
+                const double2 kzp = *reinterpret_cast<const double2*>(sp.kprev + idx + A.PL);
+                const double2 kzm = *reinterpret_cast<const double2*>(sp.kprev + idx - A.PL);
+                wzp.x = dadd(wzp.x, dmul(A.cdt, kzp.x)); wzp.y = dadd(wzp.y, dmul(A.cdt, kzp.y));
+                wzm.x = dadd(wzm.x, dmul(A.cdt, kzm.x)); wzm.y = dadd(wzm.y, dmul(A.cdt, kzm.y));
+              }
+            }
+            axis(2, wzp.x, wzm.x, wzp.y, wzm.y, SB2_F_ZP, SB2_F_ZM);
+          }
+        }
+        if (active[p]) {
+          const bool in0 = f0 & SB2_F_DOMAIN, in1 = f1 & SB2_F_DOMAIN;
+          if (MODE != MODE_FINAL) {
+            double2 o;
+            o.x = in0 ? a0 : 0.0;
+            o.y = in1 ? a1 : 0.0;
+            *reinterpret_cast<double2*>(sp.kout + idx) = o;
+          } else {
+            const double2 u = *reinterpret_cast<const double2*>(sp.u + idx);
+            double2 o = u;
+            if (in0 || in1) {
+              const double2 k0 = *reinterpret_cast<const double2*>(mycs + (s * 2) * SW + p * 64 + 2 * lane);
+              const double2 k1 = *reinterpret_cast<const double2*>(mycs + (s * 2 + 1) * SW + p * 64 + 2 * lane);
+              const double2 k2 = *reinterpret_cast<const double2*>(sp.kprev + idx);
+              if (in0) o.x = dadd(u.x, div6(dmul(A.dt, dadd(dadd(dadd(k0.x, dmul(2.0, k1.x)), dmul(2.0, k2.x)), a0))));
+              if (in1) o.y = dadd(u.y, div6(dmul(A.dt, dadd(dadd(dadd(k0.y, dmul(2.0, k1.y)), dmul(2.0, k2.y)), a1))));
+            }
+            *reinterpret_cast<double2*>(sp.u_out + idx) = o;
+          }
+        }
+      }
+    }
+  }
+}
+
+// Everything a warp does for one strip row once its w rows are in shared memory: reaction program, stencil, output.
+// cur0 / up0 / dn0 (/ zp0 / zm0): this lane's first cell in the w rows y, y+1, y-1 (z+1, z-1) of species 0; species s
+// sits SSTRIDE doubles further.  tokbase: the token records in shared memory (interpreter build).  Returns false when
+// the row needed no arithmetic (the caller still has to wait for the k0 / k1 rows it requested), true otherwise.
+template <int NS, int NP, int MODE, int DEPTH, bool D3, bool ZS, int SSTRIDE>
+__device__ __forceinline__ bool rd_compute_row(const Sb2RdArgs& A, const double* __restrict__ kc, const unsigned char* tokbase,
+                                               const int S, const int cls, const int lane, const bool (&active)[NP],
+                                               const uint32_t (&fl)[2 * NP], const int64_t idx0, const double* cur0,
+                                               const double* up0, const double* dn0, const double* zp0, const double* zm0,
+                                               const double* mycs, const uint32_t mycbar, const uint32_t cparity) {
+  constexpr int NC = 2 * NP;
+  if (cls == 2) {
+    // nothing of this strip row lies in a domain: k_m = 0 / u unchanged
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      if (s < S) {
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          if (!active[p]) continue;
+          const int64_t idx = idx0 + p * 64;
+          if (MODE != MODE_FINAL) *reinterpret_cast<double2*>(A.sp[s].kout + idx) = make_double2(0.0, 0.0);
+          else *reinterpret_cast<double2*>(A.sp[s].u_out + idx) = *reinterpret_cast<const double2*>(A.sp[s].u + idx);
+        }
+      }
+    }
+    return false;
+  }
+  if (cls == 0) {
+    uint32_t anyf = 0;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) anyf |= fl[c];
+    if (!__any_sync(0xffffffffu, (anyf & 0x01010101u) != 0) && !A.carry) {
+      // this warp's cells are all outside (a class-0 strip row is mixed only as a whole)
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        if (s < S) {
+#pragma unroll
+          for (int p = 0; p < NP; ++p) {
+            if (!active[p]) continue;
+            const int64_t idx = idx0 + p * 64;
+            if (MODE != MODE_FINAL) *reinterpret_cast<double2*>(A.sp[s].kout + idx) = make_double2(0.0, 0.0);
+            else *reinterpret_cast<double2*>(A.sp[s].u_out + idx) = *reinterpret_cast<const double2*>(A.sp[s].u + idx);
+          }
+        }
+      }
+      return false;
+    }
+  }
+
+  double acc[NS][NC];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      acc[s][2 * p] = 0.0; acc[s][2 * p + 1] = 0.0;
+      if (A.carry && s < S && active[p]) {
+        const double2 c = *reinterpret_cast<const double2*>(A.sp[s].kout + idx0 + p * 64);
+        acc[s][2 * p] = c.x; acc[s][2 * p + 1] = c.y;
+      }
+    }
+  }
+
+  // ---------------- reaction / rate-rule bytecode ----------------
+  {
+    double r[DEPTH][NC];  // RD(d): slot d of the expression stack; slots >= DEPTH do not exist in this variant
+#define RD(d) r[(d) < DEPTH ? (d) : 0]
+#define LIVE(d) if ((d) < DEPTH)
+    uint32_t mask_bit = 0;  // set by MASK (bit of the law's geometry in the flag words), read by the ACC*M forms only
+    const double* wop = cur0;  // + s*SSTRIDE selects the species, + 64p the pair
+
+    // What each instruction does to the 2*NP cells of the thread: B_<op>(d, arg, cv) with d the stack slot (compile
+    // time), arg the operand field and cv the inline constant.  The interpreter passes the fields of the fetched
+    // record, a model-specialised build passes literals.
+#define LOADVS(v, sidx, p) const double2 v = *reinterpret_cast<const double2*>(wop + (sidx) * SSTRIDE + (p) * 64)
+#define FORC _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_)
+#define FORP _Pragma("unroll") for (int p = 0; p < NP; ++p)
+#define B_PUSHC(d, arg, cv) { const double b_ = (cv); FORC RD(d)[c_] = b_; }
+#define B_PUSHV(d, arg, cv) { FORP { LOADVS(v, arg, p); RD(d)[2 * p] = v.x; RD(d)[2 * p + 1] = v.y; } }
+#define B_PUSHF(d, arg, cv) { FORP { double2 v = make_double2(0.0, 0.0); if (active[p]) v = *reinterpret_cast<const double2*>(A.fields[arg] + idx0 + p * 64); RD(d)[2 * p] = v.x; RD(d)[2 * p + 1] = v.y; } }
+    // r[d-1] = r[d-1] op r[d]
+#define B_BIN(d, EXPR) { FORC { const double a = RD(d - 1)[c_], b = RD(d)[c_]; RD(d - 1)[c_] = (EXPR); } }
+#define B_ADD(d, arg, cv) B_BIN(d, dadd(a, b))
+#define B_SUB(d, arg, cv) B_BIN(d, dsub(a, b))
+#define B_MUL(d, arg, cv) B_BIN(d, dmul(a, b))
+#define B_DIV(d, arg, cv) { ddiv_batch<NC>(RD(d - 1), RD(d), RD(d - 1)); }
+#define B_GEQ(d, arg, cv) B_BIN(d, (a >= b) ? 1.0 : 0.0)
+#define B_GT(d, arg, cv) B_BIN(d, (a > b) ? 1.0 : 0.0)
+#define B_LEQ(d, arg, cv) B_BIN(d, (a <= b) ? 1.0 : 0.0)
+#define B_LT(d, arg, cv) B_BIN(d, (a < b) ? 1.0 : 0.0)
+#define B_AND(d, arg, cv) B_BIN(d, logic_and(a, b))
+#define B_OR(d, arg, cv) B_BIN(d, logic_or(a, b))
+    // r[d] = r[d] op c   (R forms: c op r[d])
+#define B_BINC(d, cv, EXPR) { const double b = (cv); FORC { const double a = RD(d)[c_]; RD(d)[c_] = (EXPR); } }
+#define B_ADDC(d, arg, cv) B_BINC(d, cv, dadd(a, b))
+#define B_SUBC(d, arg, cv) B_BINC(d, cv, dsub(a, b))
+#define B_MULC(d, arg, cv) B_BINC(d, cv, dmul(a, b))
+#define B_RSUBC(d, arg, cv) B_BINC(d, cv, dsub(b, a))
+#define B_DIVC(d, arg, cv) { double b[NC]; FORC b[c_] = (cv); ddiv_batch<NC>(RD(d), b, RD(d)); }
+#define B_RDIVC(d, arg, cv) { double a[NC]; FORC a[c_] = (cv); ddiv_batch<NC>(a, RD(d), RD(d)); }
+#define B_GEQC(d, arg, cv) B_BINC(d, cv, (a >= b) ? 1.0 : 0.0)
+#define B_GTC(d, arg, cv) B_BINC(d, cv, (a > b) ? 1.0 : 0.0)
+#define B_LEQC(d, arg, cv) B_BINC(d, cv, (a <= b) ? 1.0 : 0.0)
+#define B_LTC(d, arg, cv) B_BINC(d, cv, (a < b) ? 1.0 : 0.0)
+    // r[d] = r[d] op species arg
+#define B_BINV(d, arg, EXPR) { FORP { LOADVS(v, arg, p); { const double a = RD(d)[2 * p], b = v.x; RD(d)[2 * p] = (EXPR); } { const double a = RD(d)[2 * p + 1], b = v.y; RD(d)[2 * p + 1] = (EXPR); } } }
+#define B_ADDV(d, arg, cv) B_BINV(d, arg, dadd(a, b))
+#define B_SUBV(d, arg, cv) B_BINV(d, arg, dsub(a, b))
+#define B_MULV(d, arg, cv) B_BINV(d, arg, dmul(a, b))
+#define B_DIVV(d, arg, cv) { double b[NC]; FORP { LOADVS(v, arg, p); b[2 * p] = v.x; b[2 * p + 1] = v.y; } ddiv_batch<NC>(RD(d), b, RD(d)); }
+    // fused forms of the lowering pass: r[d] = species op constant, r[d] = species op species
+#define B_BINVC(d, arg, cv, EXPR) { const double b = (cv); FORP { LOADVS(v, arg, p); { const double a = v.x; RD(d)[2 * p] = (EXPR); } { const double a = v.y; RD(d)[2 * p + 1] = (EXPR); } } }
+#define B_ADDVC(d, arg, cv) B_BINVC(d, arg, cv, dadd(a, b))
+#define B_SUBVC(d, arg, cv) B_BINVC(d, arg, cv, dsub(a, b))
+#define B_RSUBVC(d, arg, cv) B_BINVC(d, arg, cv, dsub(b, a))
+#define B_MULVC(d, arg, cv) B_BINVC(d, arg, cv, dmul(a, b))
+#define B_DIVVC(d, arg, cv) { double a[NC], b[NC]; FORP { LOADVS(v, arg, p); a[2 * p] = v.x; a[2 * p + 1] = v.y; b[2 * p] = (cv); b[2 * p + 1] = (cv); } ddiv_batch<NC>(a, b, RD(d)); }
+#define B_RDIVVC(d, arg, cv) { double a[NC], b[NC]; FORP { LOADVS(v, arg, p); b[2 * p] = v.x; b[2 * p + 1] = v.y; a[2 * p] = (cv); a[2 * p + 1] = (cv); } ddiv_batch<NC>(a, b, RD(d)); }
+#define B_BINVV(d, arg, EXPR) { const uint32_t s1_ = (arg) & 0xffu, s2_ = (arg) >> 8; FORP { LOADVS(v1, s1_, p); LOADVS(v2, s2_, p); { const double a = v1.x, b = v2.x; RD(d)[2 * p] = (EXPR); } { const double a = v1.y, b = v2.y; RD(d)[2 * p + 1] = (EXPR); } } }
+#define B_ADDVV(d, arg, cv) B_BINVV(d, arg, dadd(a, b))
+#define B_SUBVV(d, arg, cv) B_BINVV(d, arg, dsub(a, b))
+#define B_MULVV(d, arg, cv) B_BINVV(d, arg, dmul(a, b))
+#define B_DIVVV(d, arg, cv) { const uint32_t s1_ = (arg) & 0xffu, s2_ = (arg) >> 8; double a[NC], b[NC]; FORP { LOADVS(v1, s1_, p); LOADVS(v2, s2_, p); a[2 * p] = v1.x; a[2 * p + 1] = v1.y; b[2 * p] = v2.x; b[2 * p + 1] = v2.y; } ddiv_batch<NC>(a, b, RD(d)); }
+#define B_UNARY(d, arg, cv) { FORC RD(d)[c_] = sb2_unary((int)(arg), RD(d)[c_]); }
+#define B_BINR(d, arg, cv) { FORC RD(d - 1)[c_] = sb2_binary((int)(arg), RD(d - 1)[c_], RD(d)[c_]); }
+#define B_MOV0(d, arg, cv) { FORC RD(0)[c_] = RD(d)[c_]; }
+#define B_MOVUP(d, arg, cv) { FORC RD(d + 1)[c_] = RD(d)[c_]; }
+    // statement mask: the law only acts on cells of its own domain (spatialsimulator.cpp:1381-1390)
+#define B_MASK(d, arg, cv) { mask_bit = 1u << (8 * (arg)); }
+    // delta -= stoich*rate (reactants) / += (products, rate rules); calcPDE.cpp:432-449.  Here d is the species.
+#define SI(s) ((s) < NS ? (s) : 0)
+#define B_ACCSUB(s, arg, cv) { const double st = (cv); FORC acc[SI(s)][c_] = dsub(acc[SI(s)][c_], dmul(st, RD(0)[c_])); }
+#define B_ACCADD(s, arg, cv) { const double st = (cv); FORC acc[SI(s)][c_] = dadd(acc[SI(s)][c_], dmul(st, RD(0)[c_])); }
+#define B_ACCSUB1(s, arg, cv) { FORC acc[SI(s)][c_] = dsub(acc[SI(s)][c_], RD(0)[c_]); }
+#define B_ACCADD1(s, arg, cv) { FORC acc[SI(s)][c_] = dadd(acc[SI(s)][c_], RD(0)[c_]); }
+#define B_ACCSUBC1(s, arg, cv) { const double st = (cv); FORC acc[SI(s)][c_] = dsub(acc[SI(s)][c_], st); }
+#define B_ACCADDC1(s, arg, cv) { const double st = (cv); FORC acc[SI(s)][c_] = dadd(acc[SI(s)][c_], st); }
+#define B_ACCSUBM(s, arg, cv) { const double st = (cv); FORC if (fl[c_] & mask_bit) acc[SI(s)][c_] = dsub(acc[SI(s)][c_], dmul(st, RD(0)[c_])); }
+#define B_ACCADDM(s, arg, cv) { const double st = (cv); FORC if (fl[c_] & mask_bit) acc[SI(s)][c_] = dadd(acc[SI(s)][c_], dmul(st, RD(0)[c_])); }
+    // reactant and product of a unit-stoichiometry law in one record: acc[s] -= r0; acc[arg] += r0
+#define B_XFER(s, arg, cv) { FORC acc[SI(s)][c_] = dsub(acc[SI(s)][c_], RD(0)[c_]); \
+    _Pragma("unroll") for (int s2_ = 0; s2_ < NS; ++s2_) if ((arg) == (uint32_t)s2_) { FORC acc[s2_][c_] = dadd(acc[s2_][c_], RD(0)[c_]); } }
+
+#ifdef SB2_RD_PROGRAM
+#define KC(i) kc[i]
+    SB2_RD_PROGRAM
+#undef KC
+#else
+    // token stream, two parallel arrays: code | arg << 16 (4 bytes each) and the inline constants (8 bytes each)
+    const double* tokc = reinterpret_cast<const double*>(tokbase);
+    const uint32_t* toks = reinterpret_cast<const uint32_t*>(tokbase + (A.nrd + 2) * 8);
+    uint32_t tnext = toks[0];
+    int pc = 0;
+#pragma unroll 1
+    for (;;) {
+      const uint32_t t = tnext;
+      const double* cvp = tokc + pc;  // inline constant of the C forms, loaded by the cases that use it
+      tnext = toks[++pc];  // one token ahead; the stream ends with two OPC_END tokens
+      const uint32_t arg = t >> 16;
+      switch (t & 0xffffu) {
+        // slot d must exist in this variant (DL: the deepest slot the instruction touches)
+#define CASE(OP, d, DL) case SB2_CODE(OPC_##OP, d): LIVE(DL) B_##OP(d, arg, *cvp) break;
+#define CASE_D(OP) CASE(OP, 0, 0) CASE(OP, 1, 1) CASE(OP, 2, 2) CASE(OP, 3, 3) CASE(OP, 4, 4) CASE(OP, 5, 5) CASE(OP, 6, 6) CASE(OP, 7, 7)
+#define CASE_D1(OP) CASE(OP, 1, 1) CASE(OP, 2, 2) CASE(OP, 3, 3) CASE(OP, 4, 4) CASE(OP, 5, 5) CASE(OP, 6, 6) CASE(OP, 7, 7)
+#define CASE_UP(OP) CASE(OP, 0, 1) CASE(OP, 1, 2) CASE(OP, 2, 3) CASE(OP, 3, 4) CASE(OP, 4, 5) CASE(OP, 5, 6) CASE(OP, 6, 7) CASE(OP, 7, 8)
+#define CASE_S(OP) CASE(OP, 0, 0) CASE(OP, 1, (1 < NS ? 0 : DEPTH)) CASE(OP, 2, (2 < NS ? 0 : DEPTH)) CASE(OP, 3, (3 < NS ? 0 : DEPTH)) \
+CASE(OP, 4, (4 < NS ? 0 : DEPTH)) CASE(OP, 5, (5 < NS ? 0 : DEPTH)) CASE(OP, 6, (6 < NS ? 0 : DEPTH)) CASE(OP, 7, (7 < NS ? 0 : DEPTH))
+        CASE_D(PUSHC) CASE_D(PUSHV) CASE_D(PUSHF)
+        CASE_D1(ADD) CASE_D1(SUB) CASE_D1(MUL) CASE_D1(DIV)
+        CASE_D1(GEQ) CASE_D1(GT) CASE_D1(LEQ) CASE_D1(LT) CASE_D1(AND) CASE_D1(OR)
+        CASE_D(ADDC) CASE_D(SUBC) CASE_D(MULC) CASE_D(DIVC) CASE_D(RSUBC) CASE_D(RDIVC)
+        CASE_D(GEQC) CASE_D(GTC) CASE_D(LEQC) CASE_D(LTC)
+        CASE_D(ADDV) CASE_D(SUBV) CASE_D(MULV) CASE_D(DIVV)
+        CASE_D(ADDVC) CASE_D(SUBVC) CASE_D(RSUBVC) CASE_D(MULVC) CASE_D(DIVVC) CASE_D(RDIVVC)
+        CASE_D(ADDVV) CASE_D(SUBVV) CASE_D(MULVV) CASE_D(DIVVV)
+        CASE_D(UNARY) CASE_D1(BINR) CASE_D1(MOV0) CASE_UP(MOVUP)
+        CASE(MASK, 0, 0)
+        CASE_S(ACCSUB) CASE_S(ACCADD) CASE_S(ACCSUB1) CASE_S(ACCADD1) CASE_S(ACCSUBC1) CASE_S(ACCADDC1)
+        CASE_S(ACCSUBM) CASE_S(ACCADDM) CASE_S(XFER)
+        case SB2_CODE(OPC_END, 0): goto program_done;
+        // the library only emits codes this variant implements (sb2_finalize checks depth and species count),
+        // so the dispatch needs no range check
+        default: __builtin_unreachable();
+      }
+    }
+  program_done:;
+#endif
+#undef RD
+#undef LIVE
+  }
+
+  // ---------------- diffusion (calcPDE.cpp:484-559) + output ----------------
+  if (MODE == MODE_FINAL) mbar_wait(mycbar, cparity, A.dbg == nullptr);  // k0 / k1 of this row (requested one batch ago)
+  rd_emit_row<NS, NP, MODE, D3, ZS>(A, S, cls, lane, active, fl, acc, idx0, mycs, cur0, up0, dn0, zp0, zm0, SSTRIDE);
+  return true;
+}
+
 // SB2_RD_PROGRAM (model-specialised build, rd_jit.cpp): the bytecode interpreter is replaced by the straight-line
 // expansion of one model's token records; KC(i) is the inline constant of record i, read from the kernel parameters.
 template <int NS, int NP, int W, int MODE, int DEPTH, bool D3>
@@ -385,362 +767,254 @@ __device__ __forceinline__ void rd_stage_body(const Sb2RdArgs& A, const double* 
     }
 
     const int64_t idx0 = plane0 + (int64_t)srow * A.P + x0 + 2 * lane;  // + 64p for pair p
-    if (cls == 2) {
-      // nothing of this strip row lies in a domain: k_m = 0 / u unchanged
-#pragma unroll
-      for (int s = 0; s < NS; ++s) {
-        if (s < S) {
-#pragma unroll
-          for (int p = 0; p < NP; ++p) {
-            if (!active[p]) continue;
-            const int64_t idx = idx0 + p * 64;
-            if (MODE != MODE_FINAL) *reinterpret_cast<double2*>(A.sp[s].kout + idx) = make_double2(0.0, 0.0);
-            else *reinterpret_cast<double2*>(A.sp[s].u_out + idx) = *reinterpret_cast<const double2*>(A.sp[s].u + idx);
-          }
-        }
-      }
-      combine_done(false);
-      continue;
-    }
-    if (cls == 0) {
-      uint32_t anyf = 0;
-#pragma unroll
-      for (int c = 0; c < NC; ++c) anyf |= fl[c];
-      if (!__any_sync(0xffffffffu, (anyf & 0x01010101u) != 0) && !A.carry) {
-        // this warp's cells are all outside (a class-0 strip row is mixed only as a whole)
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
-          if (s < S) {
-#pragma unroll
-            for (int p = 0; p < NP; ++p) {
-              if (!active[p]) continue;
-              const int64_t idx = idx0 + p * 64;
-              if (MODE != MODE_FINAL) *reinterpret_cast<double2*>(A.sp[s].kout + idx) = make_double2(0.0, 0.0);
-              else *reinterpret_cast<double2*>(A.sp[s].u_out + idx) = *reinterpret_cast<const double2*>(A.sp[s].u + idx);
-            }
-          }
-        }
-        combine_done(false);
-        continue;
-      }
-    }
-
     // ring slots of rows srow, srow + 1, srow - 1 (row srow + 1 is the one this warp just staged)
     const int slot_u = slot_w, slot_c = slot_w == 0 ? RW - 1 : slot_w - 1, slot_d = slot_c == 0 ? RW - 1 : slot_c - 1;
+    const double* base = wring + 2 + 2 * lane;
+    const bool waited = rd_compute_row<NS, NP, MODE, DEPTH, D3, false, RW * SWP>(A, kc, smem_raw + HDR, S, cls, lane, active, fl, idx0, base + slot_c * SWP,
+                                                                                 base + slot_u * SWP, base + slot_d * SWP, nullptr, nullptr,
+                                                                                 mycs, mycbar, cparity);
+    combine_done(waited);
+  }
+}
 
-    double acc[NS][NC];
-#pragma unroll
-    for (int s = 0; s < NS; ++s) {
-#pragma unroll
-      for (int p = 0; p < NP; ++p) {
-        acc[s][2 * p] = 0.0; acc[s][2 * p + 1] = 0.0;
-        if (A.carry && s < S && active[p]) {
-          const double2 c = *reinterpret_cast<const double2*>(A.sp[s].kout + idx0 + p * 64);
-          acc[s][2 * p] = c.x; acc[s][2 * p + 1] = c.y;
-        }
-      }
-    }
+// ---------------------------------------------------------------------------------------------
+// 3-D grids: the same stage, marching along z.
+//
+// A CTA of W warps owns a strip of SW = 64*NP cells in x, W consecutive rows in y and a range of planes in z; warp j
+// owns row y0 + j of every plane.  The w values live in a ring of NSLOT = 4 plane tiles of W + 2 rows (the tile rows plus
+// the row below and the row above), so all six neighbours of a cell are read from shared memory and every u / k_{m-1}
+// value is fetched from global memory once per CTA (the reference and a row-marching kernel read the z neighbours from
+// two planes away in memory).  In iteration z warp j
+//   (1) waits for the bulk copy of its raw row of plane z+1 (issued one iteration earlier), turns it into w and parks
+//       it in ring slot (z+1) mod 4; warps 0 and W-1 do the same for the halo rows y0-1 and y0+W, which only they read,
+//   (2) requests the raw rows of plane z+2,
+//   (3) waits on the row-ready barriers of rows j-1 and j+1 of plane z (its own rows of planes z-1, z, z+1 it staged
+//       itself): the only synchronisation in the loop,
+//   (4) evaluates reactions and the 7-point stencil of row j of plane z and stores k_m (or the new u).
+// Four slots suffice: seeing rows j±1 of plane z staged proves that warps j±1 have finished computing plane z-2, and
+// the slot warp j overwrites next (plane z+2 over plane z-2) was last read by exactly those warps and by warp j itself.
+// ---------------------------------------------------------------------------------------------
+template <int NP, int W>
+struct Geo3 {
+  static constexpr int NC = 2 * NP;
+  static constexpr int SW = 64 * NP;
+  static constexpr int SWP = SW + 4;
+  static constexpr int NR = W + 2;   // ring rows per plane tile: y0-1, y0 .. y0+W-1, y0+W
+  static constexpr int NSLOT = 4;    // plane tiles in the ring
+};
 
-    // ---------------- reaction / rate-rule bytecode ----------------
-    {
-      double r[DEPTH][NC];  // RD(d): slot d of the expression stack; slots >= DEPTH do not exist in this variant
-#define RD(d) r[(d) < DEPTH ? (d) : 0]
-#define LIVE(d) if ((d) < DEPTH)
-      uint32_t mask_bit = 0;  // set by MASK (bit of the law's geometry in the flag words), read by the ACC*M forms only
-      const double* wop = wring + slot_c * SWP + 2 + 2 * lane;  // + s*RW*SWP selects the species, + 64p the pair
-
-      // What each instruction does to the 2*NP cells of the thread: B_<op>(d, arg, cv) with d the stack slot (compile
-      // time), arg the operand field and cv the inline constant.  The interpreter passes the fields of the fetched
-      // record, a model-specialised build passes literals.
-#define LOADVS(v, sidx, p) const double2 v = *reinterpret_cast<const double2*>(wop + (sidx) * (RW * SWP) + (p) * 64)
-#define FORC _Pragma("unroll") for (int c_ = 0; c_ < NC; ++c_)
-#define FORP _Pragma("unroll") for (int p = 0; p < NP; ++p)
-#define B_PUSHC(d, arg, cv) { const double b_ = (cv); FORC RD(d)[c_] = b_; }
-#define B_PUSHV(d, arg, cv) { FORP { LOADVS(v, arg, p); RD(d)[2 * p] = v.x; RD(d)[2 * p + 1] = v.y; } }
-#define B_PUSHF(d, arg, cv) { FORP { double2 v = make_double2(0.0, 0.0); if (active[p]) v = *reinterpret_cast<const double2*>(A.fields[arg] + idx0 + p * 64); RD(d)[2 * p] = v.x; RD(d)[2 * p + 1] = v.y; } }
-      // r[d-1] = r[d-1] op r[d]
-#define B_BIN(d, EXPR) { FORC { const double a = RD(d - 1)[c_], b = RD(d)[c_]; RD(d - 1)[c_] = (EXPR); } }
-#define B_ADD(d, arg, cv) B_BIN(d, dadd(a, b))
-#define B_SUB(d, arg, cv) B_BIN(d, dsub(a, b))
-#define B_MUL(d, arg, cv) B_BIN(d, dmul(a, b))
-#define B_DIV(d, arg, cv) { ddiv_batch<NC>(RD(d - 1), RD(d), RD(d - 1)); }
-#define B_GEQ(d, arg, cv) B_BIN(d, (a >= b) ? 1.0 : 0.0)
-#define B_GT(d, arg, cv) B_BIN(d, (a > b) ? 1.0 : 0.0)
-#define B_LEQ(d, arg, cv) B_BIN(d, (a <= b) ? 1.0 : 0.0)
-#define B_LT(d, arg, cv) B_BIN(d, (a < b) ? 1.0 : 0.0)
-#define B_AND(d, arg, cv) B_BIN(d, logic_and(a, b))
-#define B_OR(d, arg, cv) B_BIN(d, logic_or(a, b))
-      // r[d] = r[d] op c   (R forms: c op r[d])
-#define B_BINC(d, cv, EXPR) { const double b = (cv); FORC { const double a = RD(d)[c_]; RD(d)[c_] = (EXPR); } }
-#define B_ADDC(d, arg, cv) B_BINC(d, cv, dadd(a, b))
-#define B_SUBC(d, arg, cv) B_BINC(d, cv, dsub(a, b))
-#define B_MULC(d, arg, cv) B_BINC(d, cv, dmul(a, b))
-#define B_RSUBC(d, arg, cv) B_BINC(d, cv, dsub(b, a))
-#define B_DIVC(d, arg, cv) { double b[NC]; FORC b[c_] = (cv); ddiv_batch<NC>(RD(d), b, RD(d)); }
-#define B_RDIVC(d, arg, cv) { double a[NC]; FORC a[c_] = (cv); ddiv_batch<NC>(a, RD(d), RD(d)); }
-#define B_GEQC(d, arg, cv) B_BINC(d, cv, (a >= b) ? 1.0 : 0.0)
-#define B_GTC(d, arg, cv) B_BINC(d, cv, (a > b) ? 1.0 : 0.0)
-#define B_LEQC(d, arg, cv) B_BINC(d, cv, (a <= b) ? 1.0 : 0.0)
-#define B_LTC(d, arg, cv) B_BINC(d, cv, (a < b) ? 1.0 : 0.0)
-      // r[d] = r[d] op species arg
-#define B_BINV(d, arg, EXPR) { FORP { LOADVS(v, arg, p); { const double a = RD(d)[2 * p], b = v.x; RD(d)[2 * p] = (EXPR); } { const double a = RD(d)[2 * p + 1], b = v.y; RD(d)[2 * p + 1] = (EXPR); } } }
-#define B_ADDV(d, arg, cv) B_BINV(d, arg, dadd(a, b))
-#define B_SUBV(d, arg, cv) B_BINV(d, arg, dsub(a, b))
-#define B_MULV(d, arg, cv) B_BINV(d, arg, dmul(a, b))
-#define B_DIVV(d, arg, cv) { double b[NC]; FORP { LOADVS(v, arg, p); b[2 * p] = v.x; b[2 * p + 1] = v.y; } ddiv_batch<NC>(RD(d), b, RD(d)); }
-      // fused forms of the lowering pass: r[d] = species op constant, r[d] = species op species
-#define B_BINVC(d, arg, cv, EXPR) { const double b = (cv); FORP { LOADVS(v, arg, p); { const double a = v.x; RD(d)[2 * p] = (EXPR); } { const double a = v.y; RD(d)[2 * p + 1] = (EXPR); } } }
-#define B_ADDVC(d, arg, cv) B_BINVC(d, arg, cv, dadd(a, b))
-#define B_SUBVC(d, arg, cv) B_BINVC(d, arg, cv, dsub(a, b))
-#define B_RSUBVC(d, arg, cv) B_BINVC(d, arg, cv, dsub(b, a))
-#define B_MULVC(d, arg, cv) B_BINVC(d, arg, cv, dmul(a, b))
-#define B_DIVVC(d, arg, cv) { double a[NC], b[NC]; FORP { LOADVS(v, arg, p); a[2 * p] = v.x; a[2 * p + 1] = v.y; b[2 * p] = (cv); b[2 * p + 1] = (cv); } ddiv_batch<NC>(a, b, RD(d)); }
-#define B_RDIVVC(d, arg, cv) { double a[NC], b[NC]; FORP { LOADVS(v, arg, p); b[2 * p] = v.x; b[2 * p + 1] = v.y; a[2 * p] = (cv); a[2 * p + 1] = (cv); } ddiv_batch<NC>(a, b, RD(d)); }
-#define B_BINVV(d, arg, EXPR) { const uint32_t s1_ = (arg) & 0xffu, s2_ = (arg) >> 8; FORP { LOADVS(v1, s1_, p); LOADVS(v2, s2_, p); { const double a = v1.x, b = v2.x; RD(d)[2 * p] = (EXPR); } { const double a = v1.y, b = v2.y; RD(d)[2 * p + 1] = (EXPR); } } }
-#define B_ADDVV(d, arg, cv) B_BINVV(d, arg, dadd(a, b))
-#define B_SUBVV(d, arg, cv) B_BINVV(d, arg, dsub(a, b))
-#define B_MULVV(d, arg, cv) B_BINVV(d, arg, dmul(a, b))
-#define B_DIVVV(d, arg, cv) { const uint32_t s1_ = (arg) & 0xffu, s2_ = (arg) >> 8; double a[NC], b[NC]; FORP { LOADVS(v1, s1_, p); LOADVS(v2, s2_, p); a[2 * p] = v1.x; a[2 * p + 1] = v1.y; b[2 * p] = v2.x; b[2 * p + 1] = v2.y; } ddiv_batch<NC>(a, b, RD(d)); }
-#define B_UNARY(d, arg, cv) { FORC RD(d)[c_] = sb2_unary((int)(arg), RD(d)[c_]); }
-#define B_BINR(d, arg, cv) { FORC RD(d - 1)[c_] = sb2_binary((int)(arg), RD(d - 1)[c_], RD(d)[c_]); }
-#define B_MOV0(d, arg, cv) { FORC RD(0)[c_] = RD(d)[c_]; }
-#define B_MOVUP(d, arg, cv) { FORC RD(d + 1)[c_] = RD(d)[c_]; }
-      // statement mask: the law only acts on cells of its own domain (spatialsimulator.cpp:1381-1390)
-#define B_MASK(d, arg, cv) { mask_bit = 1u << (8 * (arg)); }
-      // delta -= stoich*rate (reactants) / += (products, rate rules); calcPDE.cpp:432-449.  Here d is the species.
-#define SI(s) ((s) < NS ? (s) : 0)
-#define B_ACCSUB(s, arg, cv) { const double st = (cv); FORC acc[SI(s)][c_] = dsub(acc[SI(s)][c_], dmul(st, RD(0)[c_])); }
-#define B_ACCADD(s, arg, cv) { const double st = (cv); FORC acc[SI(s)][c_] = dadd(acc[SI(s)][c_], dmul(st, RD(0)[c_])); }
-#define B_ACCSUB1(s, arg, cv) { FORC acc[SI(s)][c_] = dsub(acc[SI(s)][c_], RD(0)[c_]); }
-#define B_ACCADD1(s, arg, cv) { FORC acc[SI(s)][c_] = dadd(acc[SI(s)][c_], RD(0)[c_]); }
-#define B_ACCSUBC1(s, arg, cv) { const double st = (cv); FORC acc[SI(s)][c_] = dsub(acc[SI(s)][c_], st); }
-#define B_ACCADDC1(s, arg, cv) { const double st = (cv); FORC acc[SI(s)][c_] = dadd(acc[SI(s)][c_], st); }
-#define B_ACCSUBM(s, arg, cv) { const double st = (cv); FORC if (fl[c_] & mask_bit) acc[SI(s)][c_] = dsub(acc[SI(s)][c_], dmul(st, RD(0)[c_])); }
-#define B_ACCADDM(s, arg, cv) { const double st = (cv); FORC if (fl[c_] & mask_bit) acc[SI(s)][c_] = dadd(acc[SI(s)][c_], dmul(st, RD(0)[c_])); }
-      // reactant and product of a unit-stoichiometry law in one record: acc[s] -= r0; acc[arg] += r0
-#define B_XFER(s, arg, cv) { FORC acc[SI(s)][c_] = dsub(acc[SI(s)][c_], RD(0)[c_]); \
-      _Pragma("unroll") for (int s2_ = 0; s2_ < NS; ++s2_) if ((arg) == (uint32_t)s2_) { FORC acc[s2_][c_] = dadd(acc[s2_][c_], RD(0)[c_]); } }
-
+template <int NS, int NP, int W, int MODE, int DEPTH>
+__device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double* __restrict__ kc) {
+  using G = Geo3<NP, W>;
+  constexpr int NC = G::NC, SW = G::SW, SWP = G::SWP, NR = G::NR, NSLOT = G::NSLOT;
+  constexpr int NARR = (MODE == MODE_FIRST) ? 1 : 2;  // arrays per species in a raw slot: u (, k_{m-1})
+  constexpr int SSTRIDE = NSLOT * NR * SWP;           // doubles between the w tiles of consecutive species
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // [W bulk-copy barriers, W combine barriers, NSLOT*W row-ready barriers] [token records] [w ring: S x NSLOT x NR x SWP]
+  // [raw slots: (W + 2) x S x NARR x SWP] [last stage: k0 / k1 slots: W x S x 2 x SW]
+  const int S = A.S;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
 #ifdef SB2_RD_PROGRAM
-#define KC(i) kc[i]
-      SB2_RD_PROGRAM
-#undef KC
+  double* wring = reinterpret_cast<double*>(smem_raw + HDR);
 #else
-      // token stream, two parallel arrays: code | arg << 16 (4 bytes each) and the inline constants (8 bytes each)
-      const double* tokc = reinterpret_cast<const double*>(smem_raw + HDR);
-      const uint32_t* toks = reinterpret_cast<const uint32_t*>(smem_raw + HDR + (A.nrd + 2) * 8);
-      uint32_t tnext = toks[0];
-      int pc = 0;
-#pragma unroll 1
-      for (;;) {
-        const uint32_t t = tnext;
-        const double* cvp = tokc + pc;  // inline constant of the C forms, loaded by the cases that use it
-        tnext = toks[++pc];  // one token ahead; the stream ends with two OPC_END tokens
-        const uint32_t arg = t >> 16;
-        switch (t & 0xffffu) {
-          // slot d must exist in this variant (DL: the deepest slot the instruction touches)
-#define CASE(OP, d, DL) case SB2_CODE(OPC_##OP, d): LIVE(DL) B_##OP(d, arg, *cvp) break;
-#define CASE_D(OP) CASE(OP, 0, 0) CASE(OP, 1, 1) CASE(OP, 2, 2) CASE(OP, 3, 3) CASE(OP, 4, 4) CASE(OP, 5, 5) CASE(OP, 6, 6) CASE(OP, 7, 7)
-#define CASE_D1(OP) CASE(OP, 1, 1) CASE(OP, 2, 2) CASE(OP, 3, 3) CASE(OP, 4, 4) CASE(OP, 5, 5) CASE(OP, 6, 6) CASE(OP, 7, 7)
-#define CASE_UP(OP) CASE(OP, 0, 1) CASE(OP, 1, 2) CASE(OP, 2, 3) CASE(OP, 3, 4) CASE(OP, 4, 5) CASE(OP, 5, 6) CASE(OP, 6, 7) CASE(OP, 7, 8)
-#define CASE_S(OP) CASE(OP, 0, 0) CASE(OP, 1, (1 < NS ? 0 : DEPTH)) CASE(OP, 2, (2 < NS ? 0 : DEPTH)) CASE(OP, 3, (3 < NS ? 0 : DEPTH)) \
-  CASE(OP, 4, (4 < NS ? 0 : DEPTH)) CASE(OP, 5, (5 < NS ? 0 : DEPTH)) CASE(OP, 6, (6 < NS ? 0 : DEPTH)) CASE(OP, 7, (7 < NS ? 0 : DEPTH))
-          CASE_D(PUSHC) CASE_D(PUSHV) CASE_D(PUSHF)
-          CASE_D1(ADD) CASE_D1(SUB) CASE_D1(MUL) CASE_D1(DIV)
-          CASE_D1(GEQ) CASE_D1(GT) CASE_D1(LEQ) CASE_D1(LT) CASE_D1(AND) CASE_D1(OR)
-          CASE_D(ADDC) CASE_D(SUBC) CASE_D(MULC) CASE_D(DIVC) CASE_D(RSUBC) CASE_D(RDIVC)
-          CASE_D(GEQC) CASE_D(GTC) CASE_D(LEQC) CASE_D(LTC)
-          CASE_D(ADDV) CASE_D(SUBV) CASE_D(MULV) CASE_D(DIVV)
-          CASE_D(ADDVC) CASE_D(SUBVC) CASE_D(RSUBVC) CASE_D(MULVC) CASE_D(DIVVC) CASE_D(RDIVVC)
-          CASE_D(ADDVV) CASE_D(SUBVV) CASE_D(MULVV) CASE_D(DIVVV)
-          CASE_D(UNARY) CASE_D1(BINR) CASE_D1(MOV0) CASE_UP(MOVUP)
-          CASE(MASK, 0, 0)
-          CASE_S(ACCSUB) CASE_S(ACCADD) CASE_S(ACCSUB1) CASE_S(ACCADD1) CASE_S(ACCSUBC1) CASE_S(ACCADDC1)
-          CASE_S(ACCSUBM) CASE_S(ACCADDM) CASE_S(XFER)
-          case SB2_CODE(OPC_END, 0): goto program_done;
-          // the library only emits codes this variant implements (sb2_finalize checks depth and species count),
-          // so the dispatch needs no range check
-          default: __builtin_unreachable();
-        }
-      }
-    program_done:;
+  double* wring = reinterpret_cast<double*>(smem_raw + HDR + tok_bytes(A.nrd));
 #endif
-#undef RD
-#undef LIVE
-    }
+  double* rawbase = wring + (size_t)S * SSTRIDE;
+  double* cbase = rawbase + (size_t)(W + 2) * S * NARR * SWP;
 
-    // ---------------- diffusion (calcPDE.cpp:484-559) + output ----------------
-    if (MODE == MODE_FINAL) mbar_wait(mycbar, cparity, A.dbg == nullptr);  // k0 / k1 of this row (requested one batch ago)
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler (uniform datapath)
+  const int x0 = blockIdx.x * SW;
+  const int y0 = (int)blockIdx.y * W;
+  const int y = y0 + warp;
+  const int zb = A.row_begin + (int)blockIdx.z * A.rows_per_block;
+  const int ze = min(zb + A.rows_per_block, A.row_end);
+  if (zb >= ze) return;
+
+  const uint32_t mybar = smem_addr(&bars[warp]);
+  const uint32_t mycbar = smem_addr(&bars[W + warp]);
+  const uint32_t rowbar0 = smem_addr(&bars[2 * W]);  // row-ready barrier of (slot q, warp j) at rowbar0 + 8 * (q * W + j)
+  if (lane == 0) {
+    mbar_init(mybar, 1);
+    if (MODE == MODE_FINAL) mbar_init(mycbar, 1);
+    if (warp == 0)
+      for (int q = 0; q < NSLOT * W; ++q) mbar_init(rowbar0 + 8 * q, 1);
+    mbar_fence_init();
+  }
+#ifndef SB2_RD_PROGRAM
+  for (int i = threadIdx.x; i < A.nrd + 2; i += W * 32) {
+    const Sb2RdTok t = A.rdtok[i];
+    reinterpret_cast<double*>(smem_raw + HDR)[i] = t.c;
+    reinterpret_cast<uint32_t*>(smem_raw + HDR + (A.nrd + 2) * 8)[i] = t.code | (t.arg << 16);
+  }
+#endif
+  __syncthreads();  // once: barriers and token records are in place
+  if (y > A.ny) return;  // rows past the guard row above the plane: nothing to stage, nothing to compute
+
+  // the halo row this warp stages besides its own: y0-1 (warp 0), y0+W (warp W-1, when that row exists)
+  const bool halo_lo = warp == 0, halo_hi = warp == W - 1 && y0 + W <= A.ny;
+  const int nrows = 1 + (halo_lo ? 1 : 0) + (halo_hi ? 1 : 0);
+  double* myraw = rawbase + (size_t)warp * S * NARR * SWP;
+  double* hraw = rawbase + (size_t)(halo_lo ? W : W + 1) * S * NARR * SWP;  // W >= 2: a warp has at most one halo row
+  const uint32_t myraw_s = smem_addr(myraw), hraw_s = smem_addr(hraw);
+  const uint32_t row_bytes = SWP * sizeof(double);
+  double* mycs = cbase + (size_t)warp * S * 2 * SW;
+  const uint32_t mycs_s = smem_addr(mycs);
+  const bool computes = y < A.ny;
+  const bool wait_lo = warp > 0, wait_hi = warp < W - 1 && y + 1 <= A.ny;  // neighbours that stage rows this warp reads
+
+  const uint64_t keep = (MODE == MODE_FINAL) ? l2_policy_keep() : 0;
+  // one lane: bulk copies of the raw rows (u and k_{m-1} of every species, halo columns included) of plane pz
+  auto issue_rows = [&](int pz) {
+    mbar_expect_tx(mybar, row_bytes * NARR * S * nrows);
+    const int64_t g = A.first + (int64_t)pz * A.PL + (int64_t)y * A.P + x0 - 2;
+    const int64_t gh = A.first + (int64_t)pz * A.PL + (int64_t)(halo_lo ? y0 - 1 : y0 + W) * A.P + x0 - 2;
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
       if (s < S) {
-        const Sb2SpeciesArgs& sp = A.sp[s];
-        const double* base = wring + (size_t)s * RW * SWP + 2 + 2 * lane;
-        const double* cur = base + slot_c * SWP;
-        const double* up = base + slot_u * SWP;
-        const double* dn = base + slot_d * SWP;
-        // Uniform coefficients, no division by dx^2: straight-line stencil, additions in the reference's order Xp, Xm, Yp,
-        // Ym (, Zp, Zm).  MASKED = false: every cell of the strip row is an interior cell, no per-cell test at all.
-        // MASKED = true (mixed strip rows): the same arithmetic, every addition under a predicate built from the cell's
-        // flag byte, outputs selected by the domain bit (neighbour values outside a domain are finite, never used).
-        auto straight = [&](auto masked_tag) {
-          constexpr bool MASKED = decltype(masked_tag)::value;
-          const double dcx = sp.dconst[0], dcy = sp.dconst[1];
-          double2 cu[NP], ck0[NP], ck1[NP], ck2[NP];
-          if (MODE == MODE_FINAL) {
-#pragma unroll
-            for (int p = 0; p < NP; ++p) {
-              const int64_t i = idx0 + p * 64;
-              cu[p] = ck2[p] = make_double2(0.0, 0.0);
-              if (!MASKED || active[p]) {
-                cu[p] = *reinterpret_cast<const double2*>(sp.u + i);        // L2 hits: staged through L2 one batch ago
-                ck2[p] = *reinterpret_cast<const double2*>(sp.kprev + i);
-              }
-              ck0[p] = *reinterpret_cast<const double2*>(mycs + (s * 2) * SW + p * 64 + 2 * lane);
-              ck1[p] = *reinterpret_cast<const double2*>(mycs + (s * 2 + 1) * SW + p * 64 + 2 * lane);
-            }
-          }
-#pragma unroll
-          for (int p = 0; p < NP; ++p) {
-            const uint32_t f0 = MASKED ? (fl[2 * p] >> (8 * sp.geo)) & 0xffu : (uint32_t)SB2_F_DOMAIN;
-            const uint32_t f1 = MASKED ? (fl[2 * p + 1] >> (8 * sp.geo)) & 0xffu : (uint32_t)SB2_F_DOMAIN;
-#define RD_ADD(acc_, f_, bit_, term_) if (!MASKED || ((f_) & (SB2_F_DOMAIN | (bit_))) == SB2_F_DOMAIN) acc_ = dadd(acc_, term_)
-            double a0 = acc[s][2 * p], a1 = acc[s][2 * p + 1];
-            if (sp.has_diff) {
-              const double2 wc = *reinterpret_cast<const double2*>(cur + p * 64);
-              const double wl = cur[p * 64 - 1], wr = cur[p * 64 + 2];
-              const double2 wu = *reinterpret_cast<const double2*>(up + p * 64);
-              const double2 wd = *reinterpret_cast<const double2*>(dn + p * 64);
-              RD_ADD(a0, f0, SB2_F_XP, dmul(dcx, dsub(wc.y, wc.x)));
-              RD_ADD(a0, f0, SB2_F_XM, dmul(dcx, dsub(wl, wc.x)));
-              RD_ADD(a0, f0, SB2_F_YP, dmul(dcy, dsub(wu.x, wc.x)));
-              RD_ADD(a0, f0, SB2_F_YM, dmul(dcy, dsub(wd.x, wc.x)));
-              RD_ADD(a1, f1, SB2_F_XP, dmul(dcx, dsub(wr, wc.y)));
-              RD_ADD(a1, f1, SB2_F_XM, dmul(dcx, dsub(wc.x, wc.y)));
-              RD_ADD(a1, f1, SB2_F_YP, dmul(dcy, dsub(wu.y, wc.y)));
-              RD_ADD(a1, f1, SB2_F_YM, dmul(dcy, dsub(wd.y, wc.y)));
-              if (D3) {  // Zp, Zm
-                const double dcz = sp.dconst[2];
-                const int64_t i = idx0 + p * 64;
-                double2 wzp = make_double2(0.0, 0.0), wzm = wzp;
-                if (!MASKED || active[p]) {
-                  wzp = *reinterpret_cast<const double2*>(sp.u + i + A.PL);
-                  wzm = *reinterpret_cast<const double2*>(sp.u + i - A.PL);
-                  if (MODE != MODE_FIRST) {
-                    const double2 kzp = *reinterpret_cast<const double2*>(sp.kprev + i + A.PL);
-                    const double2 kzm = *reinterpret_cast<const double2*>(sp.kprev + i - A.PL);
-                    wzp.x = dadd(wzp.x, dmul(A.cdt, kzp.x)); wzp.y = dadd(wzp.y, dmul(A.cdt, kzp.y));
-                    wzm.x = dadd(wzm.x, dmul(A.cdt, kzm.x)); wzm.y = dadd(wzm.y, dmul(A.cdt, kzm.y));
-                  }
-                }
-                RD_ADD(a0, f0, SB2_F_ZP, dmul(dcz, dsub(wzp.x, wc.x)));
-                RD_ADD(a0, f0, SB2_F_ZM, dmul(dcz, dsub(wzm.x, wc.x)));
-                RD_ADD(a1, f1, SB2_F_ZP, dmul(dcz, dsub(wzp.y, wc.y)));
-                RD_ADD(a1, f1, SB2_F_ZM, dmul(dcz, dsub(wzm.y, wc.y)));
-              }
-            }
-#undef RD_ADD
-            const bool in0 = !MASKED || (f0 & SB2_F_DOMAIN), in1 = !MASKED || (f1 & SB2_F_DOMAIN);
-            if (MASKED && !active[p]) continue;
-            if (MODE != MODE_FINAL) {
-              *reinterpret_cast<double2*>(sp.kout + idx0 + p * 64) = make_double2(in0 ? a0 : 0.0, in1 ? a1 : 0.0);
-            } else {
-              // value += dt*(k0 + 2.0*k1 + 2.0*k2 + k3)/6.0, spatialsimulator.cpp:1535
-              double inc[2];
-              inc[0] = dmul(A.dt, dadd(dadd(dadd(ck0[p].x, dmul(2.0, ck1[p].x)), dmul(2.0, ck2[p].x)), a0));
-              inc[1] = dmul(A.dt, dadd(dadd(dadd(ck0[p].y, dmul(2.0, ck1[p].y)), dmul(2.0, ck2[p].y)), a1));
-              div6_batch<2>(inc);
-              *reinterpret_cast<double2*>(sp.u_out + idx0 + p * 64) =
-                  make_double2(in0 ? dadd(cu[p].x, inc[0]) : cu[p].x, in1 ? dadd(cu[p].y, inc[1]) : cu[p].y);
-            }
-          }
-        };
-        if (sp.fastpath || !sp.has_diff) {
-          if (cls == 1) straight(BoolTag<false>());
-          else straight(BoolTag<true>());
-          continue;
+        if (MODE == MODE_FINAL) {
+          bulk_g2s_hint(myraw_s + (s * NARR) * row_bytes, A.sp[s].u + g, row_bytes, mybar, keep);
+          bulk_g2s_hint(myraw_s + (s * NARR + 1) * row_bytes, A.sp[s].kprev + g, row_bytes, mybar, keep);
+        } else {
+          bulk_g2s(myraw_s + (s * NARR) * row_bytes, A.sp[s].u + g, row_bytes, mybar);
+          if (MODE != MODE_FIRST) bulk_g2s(myraw_s + (s * NARR + 1) * row_bytes, A.sp[s].kprev + g, row_bytes, mybar);
         }
-        // general path: per-cell domain / boundary flags, field-valued coefficients, dx^2 != 1.  Every stencil term
-        // is computed unconditionally (neighbour values outside the domain are finite) and added under a predicate,
-        // so the only branches are the warp-uniform ones on the coefficient kind and on dx^2 == 1.
+        if (nrows > 1) {
+          bulk_g2s(hraw_s + (s * NARR) * row_bytes, A.sp[s].u + gh, row_bytes, mybar);
+          if (MODE != MODE_FIRST) bulk_g2s(hraw_s + (s * NARR + 1) * row_bytes, A.sp[s].kprev + gh, row_bytes, mybar);
+        }
+      }
+    }
+  };
+  auto issue_combine = [&](int pz) {
+    mbar_expect_tx(mycbar, SW * sizeof(double) * 2 * S);
+    const int64_t g = A.first + (int64_t)pz * A.PL + (int64_t)y * A.P + x0;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      if (s < S) {
+        bulk_g2s(mycs_s + (s * 2) * SW * sizeof(double), A.sp[s].k0 + g, SW * sizeof(double), mycbar);
+        bulk_g2s(mycs_s + (s * 2 + 1) * SW * sizeof(double), A.sp[s].k1 + g, SW * sizeof(double), mycbar);
+      }
+    }
+  };
+  // raw row → w row of the ring:  w = u + (rk[m]*dt) * k_{m-1}, calcPDE.cpp:247-248
+  auto stage = [&](const double* raw, double* wrow) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      if (s < S) {
+        const double* ru = raw + (s * NARR) * SWP;
+        const double* rk = ru + SWP;
+        double* wr = wrow + (size_t)s * SSTRIDE;
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
-          const int64_t idx = idx0 + p * 64;
-          const uint32_t f0 = (fl[2 * p] >> (8 * sp.geo)) & 0xffu;
-          const uint32_t f1 = (fl[2 * p + 1] >> (8 * sp.geo)) & 0xffu;
-          double a0 = acc[s][2 * p], a1 = acc[s][2 * p + 1];
-          if (sp.has_diff) {
-            const double2 wc = *reinterpret_cast<const double2*>(cur + p * 64);
-            // one axis: the plus / minus neighbours of both cells, the flag bits that switch each term off
-            auto axis = [&](int ax, double n0p, double n0m, double n1p, double n1m, uint32_t bitp, uint32_t bitm) {
-              if (sp.dkind[ax] == SB2_SRC_NONE) return;
-              double d0, d1;
-              if (sp.dkind[ax] == SB2_SRC_CONST) { d0 = d1 = sp.dconst[ax]; }
-              else {
-                double2 dv = make_double2(0.0, 0.0);
-                if (active[p]) dv = *reinterpret_cast<const double2*>(A.fields[sp.dsrc[ax]] + idx);
-                d0 = dv.x; d1 = dv.y;
-              }
-              double t0p = dmul(d0, dsub(n0p, wc.x)), t0m = dmul(d0, dsub(n0m, wc.x));
-              double t1p = dmul(d1, dsub(n1p, wc.y)), t1m = dmul(d1, dsub(n1m, wc.y));
-              if (A.divide[ax]) {
-                t0p = ddiv_pos(t0p, A.dx2[ax]); t0m = ddiv_pos(t0m, A.dx2[ax]);
-                t1p = ddiv_pos(t1p, A.dx2[ax]); t1m = ddiv_pos(t1m, A.dx2[ax]);
-              }
-              if ((f0 & (SB2_F_DOMAIN | bitp)) == SB2_F_DOMAIN) a0 = dadd(a0, t0p);
-              if ((f0 & (SB2_F_DOMAIN | bitm)) == SB2_F_DOMAIN) a0 = dadd(a0, t0m);
-              if ((f1 & (SB2_F_DOMAIN | bitp)) == SB2_F_DOMAIN) a1 = dadd(a1, t1p);
-              if ((f1 & (SB2_F_DOMAIN | bitm)) == SB2_F_DOMAIN) a1 = dadd(a1, t1m);
-            };
-            {
-              const double wl = cur[p * 64 - 1], wr = cur[p * 64 + 2];
-              axis(0, wc.y, wl, wr, wc.x, SB2_F_XP, SB2_F_XM);
-            }
-            {
-              const double2 wu = *reinterpret_cast<const double2*>(up + p * 64);
-              const double2 wd = *reinterpret_cast<const double2*>(dn + p * 64);
-              axis(1, wu.x, wd.x, wu.y, wd.y, SB2_F_YP, SB2_F_YM);
-            }
-            if (D3) {
-              double2 wzp = make_double2(0.0, 0.0), wzm = wzp;
-              if (active[p] && sp.dkind[2] != SB2_SRC_NONE) {
-                wzp = *reinterpret_cast<const double2*>(sp.u + idx + A.PL);
-                wzm = *reinterpret_cast<const double2*>(sp.u + idx - A.PL);
-                if (MODE != MODE_FIRST) {
-                  const double2 kzp = *reinterpret_cast<const double2*>(sp.kprev + idx + A.PL);
-                  const double2 kzm = *reinterpret_cast<const double2*>(sp.kprev + idx - A.PL);
-                  wzp.x = dadd(wzp.x, dmul(A.cdt, kzp.x)); wzp.y = dadd(wzp.y, dmul(A.cdt, kzp.y));
-                  wzm.x = dadd(wzm.x, dmul(A.cdt, kzm.x)); wzm.y = dadd(wzm.y, dmul(A.cdt, kzm.y));
-                }
-              }
-              axis(2, wzp.x, wzm.x, wzp.y, wzm.y, SB2_F_ZP, SB2_F_ZM);
-            }
+          const int i = 2 + p * 64 + 2 * lane;
+          double2 w = *reinterpret_cast<const double2*>(ru + i);
+          if (MODE != MODE_FIRST) {
+            const double2 k = *reinterpret_cast<const double2*>(rk + i);
+            w.x = dadd(w.x, dmul(A.cdt, k.x));
+            w.y = dadd(w.y, dmul(A.cdt, k.y));
           }
-          if (active[p]) {
-            const bool in0 = f0 & SB2_F_DOMAIN, in1 = f1 & SB2_F_DOMAIN;
-            if (MODE != MODE_FINAL) {
-              double2 o;
-              o.x = in0 ? a0 : 0.0;
-              o.y = in1 ? a1 : 0.0;
-              *reinterpret_cast<double2*>(sp.kout + idx) = o;
-            } else {
-              const double2 u = *reinterpret_cast<const double2*>(sp.u + idx);
-              double2 o = u;
-              if (in0 || in1) {
-                const double2 k0 = *reinterpret_cast<const double2*>(mycs + (s * 2) * SW + p * 64 + 2 * lane);
-                const double2 k1 = *reinterpret_cast<const double2*>(mycs + (s * 2 + 1) * SW + p * 64 + 2 * lane);
-                const double2 k2 = *reinterpret_cast<const double2*>(sp.kprev + idx);
-                if (in0) o.x = dadd(u.x, div6(dmul(A.dt, dadd(dadd(dadd(k0.x, dmul(2.0, k1.x)), dmul(2.0, k2.x)), a0))));
-                if (in1) o.y = dadd(u.y, div6(dmul(A.dt, dadd(dadd(dadd(k0.y, dmul(2.0, k1.y)), dmul(2.0, k2.y)), a1))));
-              }
-              *reinterpret_cast<double2*>(sp.u_out + idx) = o;
+          *reinterpret_cast<double2*>(wr + i) = w;
+        }
+        if (lane < 2) {  // halo columns x0-1 and x0+SW
+          const int i = lane == 0 ? 1 : SW + 2;
+          double w = ru[i];
+          if (MODE != MODE_FIRST) w = dadd(w, dmul(A.cdt, rk[i]));
+          wr[i] = w;
+        }
+      }
+    }
+  };
+
+  bool active[NP];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) active[p] = x0 + p * 64 + 2 * lane < A.nx;
+
+  if (elect_one()) {
+    issue_rows(zb - 1);
+    if (MODE == MODE_FINAL && computes) issue_combine(zb);
+  }
+  uint32_t parity = 0, cparity = 0;
+  // zc: the plane computed in this iteration; plane zc + 1 is staged first.  Planes zb-1 .. ze are staged (ring slot and
+  // use count of plane pz follow from pz - (zb - 1)), planes zb .. ze-1 are computed.
+  int cls_cur = 2;  // class byte of this warp's row in plane zc, fetched one iteration ahead
+  for (int zc = zb - 2; zc < ze; ++zc) {
+    const int pz = zc + 1;
+    // class byte of the next plane and, for mixed rows, the per-cell flag bytes of this one: requested before the
+    // staging work so that their latency is covered by it
+    const bool compute = computes && zc >= zb;
+    const int cls = compute ? cls_cur : 2;
+    if (computes && pz >= zb && pz < ze)
+      cls_cur = A.carry ? 0 : (int)A.cls[((uint32_t)pz * (uint32_t)A.ny + (uint32_t)y) * (uint32_t)A.nstrips + blockIdx.x];
+    const int64_t idx0 = A.first + (int64_t)zc * A.PL + (int64_t)y * A.P + x0 + 2 * lane;
+    uint32_t fl[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) fl[c] = 0x01010101u;
+    if (cls == 0) {
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        fl[2 * p] = 0; fl[2 * p + 1] = 0;
+        if (active[p]) {
+#pragma unroll
+          for (int g = 0; g < SB2_MAX_GEOS; ++g) {
+            if (g < A.G) {
+              const uchar2 v = *reinterpret_cast<const uchar2*>(A.flags[g] + idx0 + p * 64);
+              fl[2 * p] |= (uint32_t)v.x << (8 * g);
+              fl[2 * p + 1] |= (uint32_t)v.y << (8 * g);
             }
           }
         }
       }
     }
-    combine_done(true);
+    if (pz >= zb - 1) {
+      const int q = (pz - (zb - 1)) & (NSLOT - 1);
+      if (!mbar_wait(mybar, parity, A.dbg == nullptr) && A.dbg && lane == 0) {
+        if (atomicAdd(&A.dbg[0], 1u) == 0) { A.dbg[1] = blockIdx.x; A.dbg[2] = blockIdx.y; A.dbg[3] = warp; A.dbg[4] = (uint32_t)pz; A.dbg[5] = parity; A.dbg[6] = (uint32_t)zb; A.dbg[7] = (uint32_t)ze; }
+      }
+      parity ^= 1;
+      double* tile = wring + (size_t)q * NR * SWP;
+      stage(myraw, tile + (warp + 1) * SWP);
+      if (halo_lo) stage(hraw, tile);
+      if (halo_hi) stage(hraw, tile + (W + 1) * SWP);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(rowbar0 + 8 * (q * W + warp));
+      // the raw slots are free again: fetch the rows of the next plane
+      if (pz + 1 <= ze && elect_one()) issue_rows(pz + 1);
+    }
+    if (zc < zb - 1) continue;
+    // (3) rows j-1 and j+1 of plane zc; every warp that stages waits, whether it computes or not: the order in which
+    // ring slots may be overwritten is carried from warp to warp by these waits
+    {
+      const uint32_t u = (uint32_t)(zc - (zb - 1));
+      const uint32_t q = u & (NSLOT - 1), ph = (u / NSLOT) & 1u;
+      bool ok = true;
+      if (wait_lo) ok = mbar_wait(rowbar0 + 8 * (q * W + warp - 1), ph, A.dbg == nullptr);
+      if (wait_hi) ok = mbar_wait(rowbar0 + 8 * (q * W + warp + 1), ph, A.dbg == nullptr) && ok;
+      if (!ok && A.dbg && lane == 0) {
+        if (atomicAdd(&A.dbg[0], 1u) == 0) { A.dbg[1] = blockIdx.x; A.dbg[2] = blockIdx.y; A.dbg[3] = warp; A.dbg[4] = (uint32_t)zc; A.dbg[5] = 99; A.dbg[6] = (uint32_t)zb; A.dbg[7] = (uint32_t)ze; }
+      }
+    }
+    if (!compute) continue;
+    const int qc = (zc - (zb - 1)) & (NSLOT - 1), qp = (qc + 1) & (NSLOT - 1), qm = (qc + NSLOT - 1) & (NSLOT - 1);
+    const double* base = wring + (warp + 1) * SWP + 2 + 2 * lane;  // this lane's first cell in row j of tile 0
+    const double* cur = base + (size_t)qc * NR * SWP;
+    const bool waited = rd_compute_row<NS, NP, MODE, DEPTH, true, true, SSTRIDE>(
+        A, kc, smem_raw + HDR, S, cls, lane, active, fl, idx0, cur, cur + SWP, cur - SWP, base + (size_t)qp * NR * SWP,
+        base + (size_t)qm * NR * SWP, mycs, mycbar, cparity);
+    if (MODE == MODE_FINAL) {
+      if (!waited) mbar_wait(mycbar, cparity, A.dbg == nullptr);
+      cparity ^= 1;
+      __syncwarp();
+      if (zc + 1 < ze && elect_one()) issue_combine(zc + 1);
+    }
   }
+}
+
+// 2-D grids march along y, 3-D grids along z
+template <int NS, int NP, int W, int MODE, int DEPTH, bool D3>
+__device__ __forceinline__ void rd_stage_any(const Sb2RdArgs& A, const double* __restrict__ kc) {
+  if constexpr (D3) rd_stage3_body<NS, NP, W, MODE, DEPTH>(A, kc);
+  else rd_stage_body<NS, NP, W, MODE, DEPTH, false>(A, kc);
 }
 
 #ifdef SB2_RD_PROGRAM
@@ -749,33 +1023,23 @@ __device__ __forceinline__ void rd_stage_body(const Sb2RdArgs& A, const double* 
 struct Sb2RdJitParams { Sb2RdArgs a; double kc[SB2_RD_NKC]; };
 #define RD_JIT_ENTRY(name, MODE) \
   extern "C" __global__ void __launch_bounds__(SB2_RD_W * 32, SB2_RD_MINB) name(const __grid_constant__ rd::Sb2RdJitParams P) { \
-    rd::rd_stage_body<SB2_RD_NS, SB2_RD_NP, SB2_RD_W, MODE, SB2_RD_DEPTH, SB2_RD_D3>(P.a, P.kc); }
+    rd::rd_stage_any<SB2_RD_NS, SB2_RD_NP, SB2_RD_W, MODE, SB2_RD_DEPTH, SB2_RD_D3>(P.a, P.kc); }
 #else
 template <int NS, int NP, int W, int MODE, int DEPTH, int MINB, bool D3>
 __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_constant__ Sb2RdArgs A) {
-  rd_stage_body<NS, NP, W, MODE, DEPTH, D3>(A, nullptr);
+  rd_stage_any<NS, NP, W, MODE, DEPTH, D3>(A, nullptr);
 }
 
 template <int NS, int NP, int W, int MODE, int DEPTH, int MINB, bool D3>
 cudaError_t launch_variant(const Sb2RdArgs& a, cudaStream_t stream) {
-  using G = Geo<NP, W>;
-  const int narr = (MODE == MODE_FIRST) ? 1 : 2;
-  const size_t smem = HDR + tok_bytes(a.nrd) + sizeof(double) * ((size_t)a.S * G::RW * G::SWP + (size_t)W * a.S * narr * G::SWP +
-                                                                  (MODE == MODE_FINAL ? (size_t)W * a.S * 2 * G::SW : 0));
+  dim3 grid;
+  size_t smem;
+  sb2_rd_launch_shape(a, NP, W, MODE, D3, tok_bytes(a.nrd), &grid, &smem);
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(rd_stage_kernel<NS, NP, W, MODE, DEPTH, MINB, D3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = smem;
-  }
-  dim3 grid;
-  grid.x = (a.nx + G::SW - 1) / G::SW;
-  if (D3) {
-    grid.y = (a.ny + a.rows_per_block - 1) / a.rows_per_block;
-    grid.z = a.row_end - a.row_begin;
-  } else {
-    grid.y = (a.row_end - a.row_begin + a.rows_per_block - 1) / a.rows_per_block;
-    grid.z = 1;
   }
   if (grid.y == 0 || grid.z == 0) return cudaSuccess;
   rd_stage_kernel<NS, NP, W, MODE, DEPTH, MINB, D3><<<grid, W * 32, smem, stream>>>(a);

@@ -404,13 +404,23 @@ void fill_stage_args(sb2_sim* sim, Sb2StageCore& a, int m, double dt, int row_be
     // 3.13, 3.00, 2.97, 2.94, 2.99: short tiles keep the rows in flight close together in memory and the waves even,
     // the prologue batch they pay for is cheap
     const int W = sim->rd.w;
-    const int rows = sim->g.dim == 3 ? sim->g.ny : row_end - row_begin;
-    const int planes = sim->g.dim == 3 ? row_end - row_begin : 1;
+    a.np = sim->rd.np;
+    if (sim->g.dim == 3) {
+      // 3-D: a CTA owns W rows of a strip and marches over rows_per_block planes; each CTA stages two planes it does
+      // not compute, so long marches are cheap, short ones fill the machine on small grids
+      static const int zpb_default = getenv("SB2_RD_ZPB") ? atoi(getenv("SB2_RD_ZPB")) : 32;
+      const int planes = row_end - row_begin;
+      const int64_t tiles = (int64_t)sim->nstrips * ((sim->g.ny + W - 1) / W);
+      int zpb = zpb_default < 1 ? 1 : zpb_default;
+      while (zpb > 4 && tiles * ((planes + zpb - 1) / zpb) < 148 * 6) zpb = (zpb + 1) / 2;
+      a.rows_per_block = zpb;
+      return;
+    }
+    const int rows = row_end - row_begin;
     static const int rpb_batches = getenv("SB2_RD_BATCHES") ? atoi(getenv("SB2_RD_BATCHES")) : 12;
     int rpb = rpb_batches * W;
-    while (rpb > W && (int64_t)sim->nstrips * planes * ((rows + rpb - 1) / rpb) < 148 * 6) rpb -= W;
+    while (rpb > W && (int64_t)sim->nstrips * ((rows + rpb - 1) / rpb) < 148 * 6) rpb -= W;
     a.rows_per_block = rpb;
-    a.np = sim->rd.np;
     return;
   }
   a.np = sb2_stage_pairs(sim->g.nx, S);
@@ -427,7 +437,9 @@ void fill_stage_args(sb2_sim* sim, Sb2StageCore& a, int m, double dt, int row_be
 // until it is).  Installing bumps `version`: captured step graphs are rebuilt with the new kernel.
 Sb2RdJitSpec jit_spec(const sb2_sim* sim) {
   Sb2RdJitSpec spec;
-  spec.ns = sim->base.S; spec.np = sim->rd.np; spec.w = sim->rd.w; spec.depth = sim->base.depth; spec.minb = 2; spec.d3 = sim->g.dim == 3;
+  spec.ns = sim->base.S; spec.np = sim->rd.np; spec.w = sim->rd.w; spec.depth = sim->base.depth; spec.d3 = sim->g.dim == 3;
+  spec.minb = spec.d3 && spec.np == 1 && spec.w == 8 ? 3 : 2;  // 3-D, 2 cells per thread: 80 registers, three CTAs per SM
+  if (const char* e = getenv("SB2_JIT_MINB")) spec.minb = atoi(e) > 0 ? atoi(e) : 2;  // experiments
   return spec;
 }
 int specialise(sb2_sim* sim, bool background, bool wait) {
@@ -799,6 +811,10 @@ int sb2_finalize(sb2_sim* sim) {
   const char* force = getenv("SB2_STAGE_KERNEL");
   sim->rd_id = (force && !strcmp(force, "gen1")) ? -1 : sb2_rd_pick_variant(sim->g.dim, sim->g.nx, b.S, b.depth, &sim->rd);
   if (sim->rd_id >= 0) {
+    if (const char* ge = getenv("SB2_RD_GEOM")) {  // experiments with the specialised kernel only: "np,w" (no prebuilt kernel has this shape)
+      int np = 0, w = 0;
+      if (sscanf(ge, "%d,%d", &np, &w) == 2 && np >= 1 && np <= 4 && w >= 2 && w <= 16) { sim->rd.np = np; sim->rd.w = w; }
+    }
     rd_lower(sim->program, sim->rdprog, sim->rdslot);
     if (sim->rdprog.size() > SB2_RD_MAX_TOKENS) sim->rd_id = -1;  // very long programs stay on the first-generation kernel
   }

@@ -116,6 +116,25 @@ struct Sb2RdArgs : Sb2StageCore {
 cudaError_t sb2_launch_stage(const Sb2StageArgs& args, cudaStream_t stream, int* launches);
 int sb2_stage_pairs(int nx, int nspecies);
 
+// Grid and dynamic shared memory of an rd_stage launch (rd_stage.cuh describes the layouts): np cell pairs per thread,
+// w warps per CTA, mode 0 / 1 / 2 = first / middle / last stage, tokb = bytes of token records held in shared memory.
+// 2-D: a CTA owns a strip of 64*np cells and rows_per_block rows.  3-D: a strip, w rows and rows_per_block planes.
+static inline void sb2_rd_launch_shape(const Sb2RdArgs& a, int np, int w, int mode, bool d3, int tokb, dim3* grid, size_t* smem) {
+  const int sw = 64 * np, swp = sw + 4, narr = mode == 0 ? 1 : 2;
+  const size_t ring = d3 ? (size_t)a.S * 4 * (w + 2) * swp : (size_t)a.S * (2 * w + 2) * swp;
+  const size_t raw = (size_t)(d3 ? w + 2 : w) * a.S * narr * swp;
+  const size_t cs = mode == 2 ? (size_t)w * a.S * 2 * sw : 0;
+  *smem = 512 + tokb + sizeof(double) * (ring + raw + cs);
+  grid->x = (a.nx + sw - 1) / sw;
+  if (d3) {
+    grid->y = (a.ny + w - 1) / w;
+    grid->z = (a.row_end - a.row_begin + a.rows_per_block - 1) / a.rows_per_block;
+  } else {
+    grid->y = (a.row_end - a.row_begin + a.rows_per_block - 1) / a.rows_per_block;
+    grid->z = 1;
+  }
+}
+
 // rd_stage kernel family (rd_stage.cuh, instantiated in rd_stage_ns*.cu)
 struct Sb2RdVariant { int id, ns, np, w, depth; };
 // picks the variant for a 2-D model (returns id or -1 when only the first-generation kernel applies)

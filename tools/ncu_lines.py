@@ -3,7 +3,7 @@ usage: python tools/ncu_lines.py report.ncu-rep <launch-index> [top N]"""
 import csv, io, subprocess, sys, re, collections
 rep, idx = sys.argv[1], int(sys.argv[2])
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 45
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name", "regex:stage_kernel",
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name", "regex:" + (sys.argv[4] if len(sys.argv) > 4 else "stage_kernel"),
                       "--launch-skip", str(idx), "--launch-count", "1"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 cur = None; out = []; ops = collections.Counter(); opsamp = collections.Counter()
