@@ -35,7 +35,9 @@
 //   * The last stage fuses the RK4 combine: the k0 / k1 rows of a warp's row arrive through a second per-warp TMA slot
 //     requested one batch ahead; u and k2 of its own cells are re-read with plain 16-byte loads that hit L2, because the
 //     bulk copies that staged them one batch earlier carry an L2::evict_last hint.
-//   * 3-D: a tile is a range of rows of ONE plane; the z neighbours are read from global memory (L2).
+//   * 3-D grids march along z instead, with a ring of four plane tiles (rd_stage3_body, described there).
+//   * A model-specialised build (rd_jit.cu, SB2_RD_PROGRAM) replaces the interpreter loop by the straight-line expansion
+//     of the model's token records; everything else is the same code.
 //
 // Arithmetic follows the reference's evaluation order with explicit round-to-nearest intrinsics
 // (never contracted into FMAs), so results are bit-identical to the CPU code for + - * / and
@@ -109,12 +111,27 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return done;
 }
+// the same with a suspend-time hint (ns): the warp may sleep in the barrier unit until the phase completes instead of
+// coming back to spin (ncu: a tenth of the executed instructions of the 3-D kernel were spins of the loop below)
+__device__ __forceinline__ uint32_t mbar_try_wait_sleep(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t done;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(done)
+      : "r"(bar), "r"(parity), "r"(ns)
+      : "memory");
+  return done;
+}
 // A wait that does not complete within ~0.2 s is a bug (a copy that never lands, a broken dependency chain).  With
 // debug words attached (SB2_DEBUG=1) the caller records where and carries on; otherwise the kernel traps: the launch
 // fails loudly at the next synchronisation instead of handing back fields computed from stale rows.
 __device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, bool may_trap) {
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity))
+  while (!mbar_try_wait_sleep(bar, parity, 100000u))
     if (clock64() - t0 > 400000000LL) {
       if (may_trap) __trap();
       return false;
@@ -136,6 +153,23 @@ constexpr int HDR = 512;
 
 template <bool B>
 struct BoolTag { static constexpr bool value = B; };
+
+// What never changes for a model - species and geometry counts, which species diffuse, which take the uniform-coefficient
+// stencil, the geometry a species lives in - is read from the kernel parameters by the interpreter build and is a literal
+// in a model-specialised build (rd_jit.cu defines the SB2_RD_* macros), where the tests on it fold away.
+#ifdef SB2_RD_MODEL_BITS
+#define MODEL_S(A) SB2_RD_NS
+#define MODEL_G(A) SB2_RD_G
+#define SP_HAS_DIFF(sp, s) (((SB2_RD_HASDIFF_MASK) >> (s)) & 1)
+#define SP_FASTPATH(sp, s) (((SB2_RD_FASTPATH_MASK) >> (s)) & 1)
+#define SP_GEO(sp, s) (((SB2_RD_GEO_BITS) >> (2 * (s))) & 3)
+#else
+#define MODEL_S(A) (A).S
+#define MODEL_G(A) (A).G
+#define SP_HAS_DIFF(sp, s) (sp).has_diff
+#define SP_FASTPATH(sp, s) (sp).fastpath
+#define SP_GEO(sp, s) (sp).geo
+#endif
 
 template <int NP, int W>
 struct Geo {
@@ -181,9 +215,9 @@ __device__ __forceinline__ double div6(double x) {
 #define RD_REP_D1(M) M(1) M(2) M(3) M(4) M(5) M(6) M(7)
 
 // Diffusion stencil (calcPDE.cpp:484-559) and output of one strip row: k_m, or on the last stage the new u.
-// acc holds the reaction terms of the thread's cells; cur0 / up0 / dn0 (and, with ZS, zp0 / zm0) point at this lane's
+// acc holds the reaction terms of the thread's cells; cur0 / up0 / dn0 (and, in 3-D, zp0 / zm0) point at this lane's
 // first cell in the w rows y, y+1, y-1 (z+1, z-1) of species 0, species s sits sstride doubles further.
-template <int NS, int NP, int MODE, bool D3, bool ZS>
+template <int NS, int NP, int MODE, bool D3>
 __device__ __forceinline__ void rd_emit_row(const Sb2RdArgs& A, const int S, const int cls, const int lane, const bool (&active)[NP],
                                             const uint32_t (&fl)[2 * NP], double (&acc)[NS][2 * NP], const int64_t idx0,
                                             const double* mycs, const double* cur0, const double* up0, const double* dn0,
@@ -196,8 +230,8 @@ __device__ __forceinline__ void rd_emit_row(const Sb2RdArgs& A, const int S, con
       const double* cur = cur0 + s * sstride;
       const double* up = up0 + s * sstride;
       const double* dn = dn0 + s * sstride;
-      const double* zp = ZS ? zp0 + s * sstride : nullptr;  // ZS: the z neighbours' w rows are in shared memory too
-      const double* zm = ZS ? zm0 + s * sstride : nullptr;
+      const double* zp = D3 ? zp0 + s * sstride : nullptr;
+      const double* zm = D3 ? zm0 + s * sstride : nullptr;
       // Uniform coefficients, no division by dx^2: straight-line stencil, additions in the reference's order Xp, Xm, Yp,
       // Ym (, Zp, Zm).  MASKED = false: every cell of the strip row is an interior cell, no per-cell test at all.
       // MASKED = true (mixed strip rows): the same arithmetic, every addition under a predicate built from the cell's
@@ -221,11 +255,11 @@ __device__ __forceinline__ void rd_emit_row(const Sb2RdArgs& A, const int S, con
         }
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
-          const uint32_t f0 = MASKED ? (fl[2 * p] >> (8 * sp.geo)) & 0xffu : (uint32_t)SB2_F_DOMAIN;
-          const uint32_t f1 = MASKED ? (fl[2 * p + 1] >> (8 * sp.geo)) & 0xffu : (uint32_t)SB2_F_DOMAIN;
+          const uint32_t f0 = MASKED ? (fl[2 * p] >> (8 * SP_GEO(sp, s))) & 0xffu : (uint32_t)SB2_F_DOMAIN;
+          const uint32_t f1 = MASKED ? (fl[2 * p + 1] >> (8 * SP_GEO(sp, s))) & 0xffu : (uint32_t)SB2_F_DOMAIN;
 #define RD_ADD(acc_, f_, bit_, term_) if (!MASKED || ((f_) & (SB2_F_DOMAIN | (bit_))) == SB2_F_DOMAIN) acc_ = dadd(acc_, term_)
           double a0 = acc[s][2 * p], a1 = acc[s][2 * p + 1];
-          if (sp.has_diff) {
+          if (SP_HAS_DIFF(sp, s)) {
             const double2 wc = *reinterpret_cast<const double2*>(cur + p * 64);
             const double wl = cur[p * 64 - 1], wr = cur[p * 64 + 2];
             const double2 wu = *reinterpret_cast<const double2*>(up + p * 64);
@@ -240,21 +274,8 @@ __device__ __forceinline__ void rd_emit_row(const Sb2RdArgs& A, const int S, con
             RD_ADD(a1, f1, SB2_F_YM, dmul(dcy, dsub(wd.y, wc.y)));
             if (D3) {  // Zp, Zm
               const double dcz = sp.dconst[2];
-              const int64_t i = idx0 + p * 64;
-              double2 wzp = make_double2(0.0, 0.0), wzm = wzp;
-              if (ZS) {
-                wzp = *reinterpret_cast<const double2*>(zp + p * 64);
-                wzm = *reinterpret_cast<const double2*>(zm + p * 64);
-              } else if (!MASKED || active[p]) {
-                wzp = *reinterpret_cast<const double2*>(sp.u + i + A.PL);
-                wzm = *reinterpret_cast<const double2*>(sp.u + i - A.PL);
-                if (MODE != MODE_FIRST) {
-                  const double2 kzp = *reinterpret_cast<const double2*>(sp.kprev + i + A.PL);
-                  const double2 kzm = *reinterpret_cast<const double2*>(sp.kprev + i - A.PL);
-                  wzp.x = dadd(wzp.x, dmul(A.cdt, kzp.x)); wzp.y = dadd(wzp.y, dmul(A.cdt, kzp.y));
-                  wzm.x = dadd(wzm.x, dmul(A.cdt, kzm.x)); wzm.y = dadd(wzm.y, dmul(A.cdt, kzm.y));
-                }
-              }
+              const double2 wzp = *reinterpret_cast<const double2*>(zp + p * 64);
+              const double2 wzm = *reinterpret_cast<const double2*>(zm + p * 64);
               RD_ADD(a0, f0, SB2_F_ZP, dmul(dcz, dsub(wzp.x, wc.x)));
               RD_ADD(a0, f0, SB2_F_ZM, dmul(dcz, dsub(wzm.x, wc.x)));
               RD_ADD(a1, f1, SB2_F_ZP, dmul(dcz, dsub(wzp.y, wc.y)));
@@ -277,7 +298,7 @@ __device__ __forceinline__ void rd_emit_row(const Sb2RdArgs& A, const int S, con
           }
         }
       };
-      if (sp.fastpath || !sp.has_diff) {
+      if (SP_FASTPATH(sp, s) || !SP_HAS_DIFF(sp, s)) {
         if (cls == 1) straight(BoolTag<false>());
         else straight(BoolTag<true>());
         continue;
@@ -288,10 +309,10 @@ __device__ __forceinline__ void rd_emit_row(const Sb2RdArgs& A, const int S, con
 #pragma unroll
       for (int p = 0; p < NP; ++p) {
         const int64_t idx = idx0 + p * 64;
-        const uint32_t f0 = (fl[2 * p] >> (8 * sp.geo)) & 0xffu;
-        const uint32_t f1 = (fl[2 * p + 1] >> (8 * sp.geo)) & 0xffu;
+        const uint32_t f0 = (fl[2 * p] >> (8 * SP_GEO(sp, s))) & 0xffu;
+        const uint32_t f1 = (fl[2 * p + 1] >> (8 * SP_GEO(sp, s))) & 0xffu;
         double a0 = acc[s][2 * p], a1 = acc[s][2 * p + 1];
-        if (sp.has_diff) {
+        if (SP_HAS_DIFF(sp, s)) {
           const double2 wc = *reinterpret_cast<const double2*>(cur + p * 64);
           // one axis: the plus / minus neighbours of both cells, the flag bits that switch each term off
           auto axis = [&](int ax, double n0p, double n0m, double n1p, double n1m, uint32_t bitp, uint32_t bitm) {
@@ -324,20 +345,8 @@ __device__ __forceinline__ void rd_emit_row(const Sb2RdArgs& A, const int S, con
             axis(1, wu.x, wd.x, wu.y, wd.y, SB2_F_YP, SB2_F_YM);
           }
           if (D3) {
-            double2 wzp = make_double2(0.0, 0.0), wzm = wzp;
-            if (ZS) {
-              wzp = *reinterpret_cast<const double2*>(zp + p * 64);
-              wzm = *reinterpret_cast<const double2*>(zm + p * 64);
-            } else if (active[p] && sp.dkind[2] != SB2_SRC_NONE) {
-              wzp = *reinterpret_cast<const double2*>(sp.u + idx + A.PL);
-              wzm = *reinterpret_cast<const double2*>(sp.u + idx - A.PL);
-              if (MODE != MODE_FIRST) {
-                const double2 kzp = *reinterpret_cast<const double2*>(sp.kprev + idx + A.PL);
-                const double2 kzm = *reinterpret_cast<const double2*>(sp.kprev + idx - A.PL);
-                wzp.x = dadd(wzp.x, dmul(A.cdt, kzp.x)); wzp.y = dadd(wzp.y, dmul(A.cdt, kzp.y));
-                wzm.x = dadd(wzm.x, dmul(A.cdt, kzm.x)); wzm.y = dadd(wzm.y, dmul(A.cdt, kzm.y));
-              }
-            }
+            const double2 wzp = *reinterpret_cast<const double2*>(zp + p * 64);
+            const double2 wzm = *reinterpret_cast<const double2*>(zm + p * 64);
             axis(2, wzp.x, wzm.x, wzp.y, wzm.y, SB2_F_ZP, SB2_F_ZM);
           }
         }
@@ -370,7 +379,7 @@ __device__ __forceinline__ void rd_emit_row(const Sb2RdArgs& A, const int S, con
 // cur0 / up0 / dn0 (/ zp0 / zm0): this lane's first cell in the w rows y, y+1, y-1 (z+1, z-1) of species 0; species s
 // sits SSTRIDE doubles further.  tokbase: the token records in shared memory (interpreter build).  Returns false when
 // the row needed no arithmetic (the caller still has to wait for the k0 / k1 rows it requested), true otherwise.
-template <int NS, int NP, int MODE, int DEPTH, bool D3, bool ZS, int SSTRIDE>
+template <int NS, int NP, int MODE, int DEPTH, bool D3, int SSTRIDE>
 __device__ __forceinline__ bool rd_compute_row(const Sb2RdArgs& A, const double* __restrict__ kc, const unsigned char* tokbase,
                                                const int S, const int cls, const int lane, const bool (&active)[NP],
                                                const uint32_t (&fl)[2 * NP], const int64_t idx0, const double* cur0,
@@ -558,13 +567,13 @@ CASE(OP, 4, (4 < NS ? 0 : DEPTH)) CASE(OP, 5, (5 < NS ? 0 : DEPTH)) CASE(OP, 6, 
 
   // ---------------- diffusion (calcPDE.cpp:484-559) + output ----------------
   if (MODE == MODE_FINAL) mbar_wait(mycbar, cparity, A.dbg == nullptr);  // k0 / k1 of this row (requested one batch ago)
-  rd_emit_row<NS, NP, MODE, D3, ZS>(A, S, cls, lane, active, fl, acc, idx0, mycs, cur0, up0, dn0, zp0, zm0, SSTRIDE);
+  rd_emit_row<NS, NP, MODE, D3>(A, S, cls, lane, active, fl, acc, idx0, mycs, cur0, up0, dn0, zp0, zm0, SSTRIDE);
   return true;
 }
 
 // SB2_RD_PROGRAM (model-specialised build, rd_jit.cpp): the bytecode interpreter is replaced by the straight-line
 // expansion of one model's token records; KC(i) is the inline constant of record i, read from the kernel parameters.
-template <int NS, int NP, int W, int MODE, int DEPTH, bool D3>
+template <int NS, int NP, int W, int MODE, int DEPTH>
 __device__ __forceinline__ void rd_stage_body(const Sb2RdArgs& A, const double* __restrict__ kc) {
   using G = Geo<NP, W>;
   constexpr int NC = G::NC, SW = G::SW, SWP = G::SWP, RW = G::RW;
@@ -572,7 +581,7 @@ __device__ __forceinline__ void rd_stage_body(const Sb2RdArgs& A, const double* 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // [2W mbarriers, 128 B] [token records] [w ring: S x RW x SWP] [raw slots: W x S x NARR x SWP]
   // [last stage: k0 / k1 slots: W x S x 2 x SW]
-  const int S = A.S;
+  const int S = MODEL_S(A);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
 #ifdef SB2_RD_PROGRAM
   double* wring = reinterpret_cast<double*>(smem_raw + HDR);  // no token records in a model-specialised build
@@ -587,14 +596,11 @@ __device__ __forceinline__ void rd_stage_body(const Sb2RdArgs& A, const double* 
   // is warp-uniform and issues the bulk copies from uniform registers instead of a per-lane waterfall loop
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int x0 = blockIdx.x * SW;
-  // 2-D: the slab axis is y, a tile is a range of the slab's rows.  3-D: the slab axis is z, a tile is a range of the
-  // rows of one plane; the z neighbours of a row are read straight from global memory (L2: the planes either side
-  // have just been, or are about to be, staged by the CTAs of the neighbouring planes).
-  const int z = D3 ? A.row_begin + (int)blockIdx.z : 0;
-  const int yb = D3 ? (int)blockIdx.y * A.rows_per_block : A.row_begin + (int)blockIdx.y * A.rows_per_block;
-  const int ye = min(yb + A.rows_per_block, D3 ? A.ny : A.row_end);
+  // the slab axis is y, a tile is a range of the slab's rows (3-D grids: rd_stage3_body below)
+  const int yb = A.row_begin + (int)blockIdx.y * A.rows_per_block;
+  const int ye = min(yb + A.rows_per_block, A.row_end);
   if (yb >= ye) return;
-  const int64_t plane0 = A.first + (D3 ? (int64_t)z * A.PL : 0);
+  const int64_t plane0 = A.first;
 
   double* myraw = rawbase + (size_t)warp * S * NARR * SWP;
   const uint32_t mybar = smem_addr(&bars[warp]);
@@ -672,7 +678,7 @@ __device__ __forceinline__ void rd_stage_body(const Sb2RdArgs& A, const double* 
     const int srow = Y + warp;  // row this warp computes in the current batch
     const bool compute = (Y >= yb) && (srow < ye);
     int cls = 2;
-    if (compute) cls = A.carry ? 0 : (int)A.cls[((uint32_t)z * (uint32_t)A.ny + (uint32_t)srow) * (uint32_t)A.nstrips + blockIdx.x];
+    if (compute) cls = A.carry ? 0 : (int)A.cls[(uint32_t)srow * (uint32_t)A.nstrips + blockIdx.x];
 
     // (1) + (2): raw row → w ring
     if (wrow >= yb - 1 && wrow <= ye) {
@@ -740,7 +746,7 @@ __device__ __forceinline__ void rd_stage_body(const Sb2RdArgs& A, const double* 
         if (active[p]) {
 #pragma unroll
           for (int g = 0; g < SB2_MAX_GEOS; ++g) {
-            if (g < A.G) {
+            if (g < MODEL_G(A)) {
               const uchar2 v = *reinterpret_cast<const uchar2*>(A.flags[g] + base + p * 64);
               fl[2 * p] |= (uint32_t)v.x << (8 * g);
               fl[2 * p + 1] |= (uint32_t)v.y << (8 * g);
@@ -770,7 +776,7 @@ __device__ __forceinline__ void rd_stage_body(const Sb2RdArgs& A, const double* 
     // ring slots of rows srow, srow + 1, srow - 1 (row srow + 1 is the one this warp just staged)
     const int slot_u = slot_w, slot_c = slot_w == 0 ? RW - 1 : slot_w - 1, slot_d = slot_c == 0 ? RW - 1 : slot_c - 1;
     const double* base = wring + 2 + 2 * lane;
-    const bool waited = rd_compute_row<NS, NP, MODE, DEPTH, D3, false, RW * SWP>(A, kc, smem_raw + HDR, S, cls, lane, active, fl, idx0, base + slot_c * SWP,
+    const bool waited = rd_compute_row<NS, NP, MODE, DEPTH, false, RW * SWP>(A, kc, smem_raw + HDR, S, cls, lane, active, fl, idx0, base + slot_c * SWP,
                                                                                  base + slot_u * SWP, base + slot_d * SWP, nullptr, nullptr,
                                                                                  mycs, mycbar, cparity);
     combine_done(waited);
@@ -809,15 +815,16 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
   constexpr int NC = G::NC, SW = G::SW, SWP = G::SWP, NR = G::NR, NSLOT = G::NSLOT;
   constexpr int NARR = (MODE == MODE_FIRST) ? 1 : 2;  // arrays per species in a raw slot: u (, k_{m-1})
   constexpr int SSTRIDE = NSLOT * NR * SWP;           // doubles between the w tiles of consecutive species
+  constexpr int HDRZ = ((2 + NSLOT) * W * 8 + 511) / 512 * 512;  // barriers (sb2_rd_launch_shape computes the same)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // [W bulk-copy barriers, W combine barriers, NSLOT*W row-ready barriers] [token records] [w ring: S x NSLOT x NR x SWP]
   // [raw slots: (W + 2) x S x NARR x SWP] [last stage: k0 / k1 slots: W x S x 2 x SW]
-  const int S = A.S;
+  const int S = MODEL_S(A);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
 #ifdef SB2_RD_PROGRAM
-  double* wring = reinterpret_cast<double*>(smem_raw + HDR);
+  double* wring = reinterpret_cast<double*>(smem_raw + HDRZ);
 #else
-  double* wring = reinterpret_cast<double*>(smem_raw + HDR + tok_bytes(A.nrd));
+  double* wring = reinterpret_cast<double*>(smem_raw + HDRZ + tok_bytes(A.nrd));
 #endif
   double* rawbase = wring + (size_t)S * SSTRIDE;
   double* cbase = rawbase + (size_t)(W + 2) * S * NARR * SWP;
@@ -844,8 +851,8 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
 #ifndef SB2_RD_PROGRAM
   for (int i = threadIdx.x; i < A.nrd + 2; i += W * 32) {
     const Sb2RdTok t = A.rdtok[i];
-    reinterpret_cast<double*>(smem_raw + HDR)[i] = t.c;
-    reinterpret_cast<uint32_t*>(smem_raw + HDR + (A.nrd + 2) * 8)[i] = t.code | (t.arg << 16);
+    reinterpret_cast<double*>(smem_raw + HDRZ)[i] = t.c;
+    reinterpret_cast<uint32_t*>(smem_raw + HDRZ + (A.nrd + 2) * 8)[i] = t.code | (t.arg << 16);
   }
 #endif
   __syncthreads();  // once: barriers and token records are in place
@@ -957,7 +964,7 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
         if (active[p]) {
 #pragma unroll
           for (int g = 0; g < SB2_MAX_GEOS; ++g) {
-            if (g < A.G) {
+            if (g < MODEL_G(A)) {
               const uchar2 v = *reinterpret_cast<const uchar2*>(A.flags[g] + idx0 + p * 64);
               fl[2 * p] |= (uint32_t)v.x << (8 * g);
               fl[2 * p + 1] |= (uint32_t)v.y << (8 * g);
@@ -998,8 +1005,8 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
     const int qc = (zc - (zb - 1)) & (NSLOT - 1), qp = (qc + 1) & (NSLOT - 1), qm = (qc + NSLOT - 1) & (NSLOT - 1);
     const double* base = wring + (warp + 1) * SWP + 2 + 2 * lane;  // this lane's first cell in row j of tile 0
     const double* cur = base + (size_t)qc * NR * SWP;
-    const bool waited = rd_compute_row<NS, NP, MODE, DEPTH, true, true, SSTRIDE>(
-        A, kc, smem_raw + HDR, S, cls, lane, active, fl, idx0, cur, cur + SWP, cur - SWP, base + (size_t)qp * NR * SWP,
+    const bool waited = rd_compute_row<NS, NP, MODE, DEPTH, true, SSTRIDE>(
+        A, kc, smem_raw + HDRZ, S, cls, lane, active, fl, idx0, cur, cur + SWP, cur - SWP, base + (size_t)qp * NR * SWP,
         base + (size_t)qm * NR * SWP, mycs, mycbar, cparity);
     if (MODE == MODE_FINAL) {
       if (!waited) mbar_wait(mycbar, cparity, A.dbg == nullptr);
@@ -1014,7 +1021,7 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
 template <int NS, int NP, int W, int MODE, int DEPTH, bool D3>
 __device__ __forceinline__ void rd_stage_any(const Sb2RdArgs& A, const double* __restrict__ kc) {
   if constexpr (D3) rd_stage3_body<NS, NP, W, MODE, DEPTH>(A, kc);
-  else rd_stage_body<NS, NP, W, MODE, DEPTH, false>(A, kc);
+  else rd_stage_body<NS, NP, W, MODE, DEPTH>(A, kc);
 }
 
 #ifdef SB2_RD_PROGRAM

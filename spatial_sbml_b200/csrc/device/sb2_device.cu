@@ -440,6 +440,14 @@ Sb2RdJitSpec jit_spec(const sb2_sim* sim) {
   spec.ns = sim->base.S; spec.np = sim->rd.np; spec.w = sim->rd.w; spec.depth = sim->base.depth; spec.d3 = sim->g.dim == 3;
   spec.minb = spec.d3 && spec.np == 1 && spec.w == 8 ? 3 : 2;  // 3-D, 2 cells per thread: 80 registers, three CTAs per SM
   if (const char* e = getenv("SB2_JIT_MINB")) spec.minb = atoi(e) > 0 ? atoi(e) : 2;  // experiments
+  spec.fold = getenv("SB2_JIT_NOFOLD") ? 0 : 1;
+  spec.G = sim->base.G;
+  spec.hasdiff_mask = spec.fastpath_mask = spec.geo_bits = 0;
+  for (int s = 0; s < sim->base.S; ++s) {
+    if (sim->base.sp[s].has_diff) spec.hasdiff_mask |= 1u << s;
+    if (sim->base.sp[s].fastpath) spec.fastpath_mask |= 1u << s;
+    spec.geo_bits |= (unsigned)(sim->base.sp[s].geo & 3) << (2 * s);
+  }
   return spec;
 }
 int specialise(sb2_sim* sim, bool background, bool wait) {
@@ -1316,6 +1324,8 @@ int sb2_specialize_dry_run(const uint32_t* code, const uint32_t* arg, int n, int
   for (int i = 0; i < n; ++i) { prog[i].code = code[i]; prog[i].arg = arg[i]; prog[i].c = 0.0; }
   Sb2RdJitSpec spec;
   spec.ns = ns; spec.np = np; spec.w = w; spec.depth = depth; spec.minb = minb; spec.d3 = d3;
+  // a typical model: one geometry, every species diffuses with uniform coefficients
+  spec.fold = 1; spec.G = 1; spec.hasdiff_mask = spec.fastpath_mask = (1u << ns) - 1u; spec.geo_bits = 0;
   std::vector<char> cubin;
   std::string l;
   const int rc = sb2_rd_jit_compile(sb2_rd_jit_source(spec, prog), &cubin, &l);

@@ -124,7 +124,8 @@ static inline void sb2_rd_launch_shape(const Sb2RdArgs& a, int np, int w, int mo
   const size_t ring = d3 ? (size_t)a.S * 4 * (w + 2) * swp : (size_t)a.S * (2 * w + 2) * swp;
   const size_t raw = (size_t)(d3 ? w + 2 : w) * a.S * narr * swp;
   const size_t cs = mode == 2 ? (size_t)w * a.S * 2 * sw : 0;
-  *smem = 512 + tokb + sizeof(double) * (ring + raw + cs);
+  const size_t hdr = d3 ? (size_t)(6 * w * 8 + 511) / 512 * 512 : 512;  // mbarriers
+  *smem = hdr + tokb + sizeof(double) * (ring + raw + cs);
   grid->x = (a.nx + sw - 1) / sw;
   if (d3) {
     grid->y = (a.ny + w - 1) / w;
@@ -145,7 +146,13 @@ cudaError_t sb2_rd_classify(const uint8_t* const* flags, int G, int nx, int ny, 
                             int sw, uint8_t* cls, int nstrips, cudaStream_t stream);
 
 // model-specialised rd_stage kernels built at run time (rd_jit.cu)
-struct Sb2RdJitSpec { int ns, np, w, depth, minb, d3; };
+struct Sb2RdJitSpec {
+  int ns, np, w, depth, minb, d3;
+  // model constants folded into the build when fold != 0: geometries, bit s of the masks = species s diffuses / takes the
+  // uniform-coefficient stencil, 2 bits per species = its geometry
+  int fold, G;
+  unsigned hasdiff_mask, fastpath_mask, geo_bits;
+};
 struct Sb2RdJit;
 std::string sb2_rd_jit_source(const Sb2RdJitSpec& spec, const std::vector<Sb2RdTok>& prog);
 int sb2_rd_jit_compile(const std::string& src, std::vector<char>* cubin, std::string* log);  // needs no GPU
