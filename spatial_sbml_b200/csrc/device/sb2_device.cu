@@ -412,7 +412,7 @@ void fill_stage_args(sb2_sim* sim, Sb2StageCore& a, int m, double dt, int row_be
       const int planes = row_end - row_begin;
       const int64_t tiles = (int64_t)sim->nstrips * ((sim->g.ny + W - 1) / W);
       int zpb = zpb_default < 1 ? 1 : zpb_default;
-      while (zpb > 4 && tiles * ((planes + zpb - 1) / zpb) < 148 * 6) zpb = (zpb + 1) / 2;
+      while (zpb > 1 && tiles * ((planes + zpb - 1) / zpb) < 148 * 6) zpb = (zpb + 1) / 2;
       a.rows_per_block = zpb;
       return;
     }

@@ -24,15 +24,19 @@ for case in ("turing_tiny", "turing_tiny_cl", "turing_blob", "brusselator_300", 
     model = os.path.join(REPO, "tests", "golden", "models", case + ".xml")
     sim = sb.SpatialSimulator()
     sim.initFromFile(model, nx, ny, nz)
+    def timed(first):
+        torch.cuda.synchronize()
+        t0 = time.time()
+        sim.runSteps(first, dt, steps)
+        torch.cuda.synchronize()
+        return 1e6 * (time.time() - t0) / steps
     sim.runSteps(0, dt, 20)
-    torch.cuda.synchronize()
+    interp_us = timed(20)          # first steps of a simulator: the interpreter kernel
+    specialised = sim.specializeNow()  # what a long run switches to by itself after 256 steps (background build)
+    sim.runSteps(20 + steps, dt, 20)
     l0 = sim.getDeviceLaunchCount()
-    t0 = time.time()
-    sim.runSteps(20, dt, steps)
-    sim.getVariableCompact(str(g["species"][0]))  # forces completion
-    t1 = time.time()
+    gpu_us = timed(40 + steps)
     cells = sim.getNumDomainCells()
-    gpu_us = 1e6 * (t1 - t0) / steps
     launches = (sim.getDeviceLaunchCount() - l0) / steps
     sim.close()
     cpu = None
@@ -43,10 +47,11 @@ for case in ("turing_tiny", "turing_tiny_cl", "turing_blob", "brusselator_300", 
         if line:
             cpu = json.loads(line[-1])
     cpu_us = 1e6 * cpu["seconds"] / cpu["steps"] if cpu else float("nan")
-    rows.append({"case": case, "dims": [nx, ny, nz], "cells": int(cells), "gpu_us_per_step": gpu_us, "launches_per_step": launches,
+    rows.append({"case": case, "dims": [nx, ny, nz], "cells": int(cells), "gpu_us_per_step": gpu_us, "gpu_us_per_step_interpreter": interp_us,
+                 "specialised": bool(specialised), "launches_per_step": launches,
                  "gpu_cell_updates_per_s": cells / (gpu_us * 1e-6), "cpu_us_per_step": cpu_us,
                  "cpu_cell_updates_per_s": cells / (cpu_us * 1e-6) if cpu else None, "speedup": cpu_us / gpu_us if cpu else None})
-    print("%-16s %4dx%4dx%3d  GPU %8.1f us/step (%4.1f launches) %9.2f M cu/s | reference CPU (1 thread) %10.1f us/step %6.2f M cu/s | x%.0f" % (
-        case, nx, ny, nz, gpu_us, launches, cells / gpu_us, cpu_us, cells / cpu_us if cpu else 0.0, cpu_us / gpu_us if cpu else 0.0), flush=True)
+    print("%-16s %4dx%4dx%3d  GPU %8.1f us/step (interpreter kernel %6.1f; %4.1f launches) %9.2f M cu/s | reference CPU (1 thread) %10.1f us/step %6.2f M cu/s | x%.0f" % (
+        case, nx, ny, nz, gpu_us, interp_us, launches, cells / gpu_us, cpu_us, cells / cpu_us if cpu else 0.0, cpu_us / gpu_us if cpu else 0.0), flush=True)
 if out_json:
     json.dump({"host_cores": os.cpu_count(), "rows": rows}, open(out_json, "w"), indent=1)
