@@ -257,7 +257,10 @@ __device__ __forceinline__ void rd_emit_row(const Sb2RdArgs& A, const int S, con
         for (int p = 0; p < NP; ++p) {
           const uint32_t f0 = MASKED ? (fl[2 * p] >> (8 * SP_GEO(sp, s))) & 0xffu : (uint32_t)SB2_F_DOMAIN;
           const uint32_t f1 = MASKED ? (fl[2 * p + 1] >> (8 * SP_GEO(sp, s))) & 0xffu : (uint32_t)SB2_F_DOMAIN;
-#define RD_ADD(acc_, f_, bit_, term_) if (!MASKED || ((f_) & (SB2_F_DOMAIN | (bit_))) == SB2_F_DOMAIN) acc_ = dadd(acc_, term_)
+          // a term is skipped when the cell carries the boundary bit of that side; cells outside the domain accumulate
+          // whatever their neighbours hold and are dropped at the output select (in0 / in1), so the domain bit need not
+          // be part of every term's predicate
+#define RD_ADD(acc_, f_, bit_, term_) if (!MASKED || !((f_) & (bit_))) acc_ = dadd(acc_, term_)
           double a0 = acc[s][2 * p], a1 = acc[s][2 * p + 1];
           if (SP_HAS_DIFF(sp, s)) {
             const double2 wc = *reinterpret_cast<const double2*>(cur + p * 64);

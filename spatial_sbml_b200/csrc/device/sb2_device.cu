@@ -438,7 +438,8 @@ void fill_stage_args(sb2_sim* sim, Sb2StageCore& a, int m, double dt, int row_be
 Sb2RdJitSpec jit_spec(const sb2_sim* sim) {
   Sb2RdJitSpec spec;
   spec.ns = sim->base.S; spec.np = sim->rd.np; spec.w = sim->rd.w; spec.depth = sim->base.depth; spec.d3 = sim->g.dim == 3;
-  spec.minb = spec.d3 && spec.np == 1 && spec.w == 8 ? 3 : 2;  // 3-D, 2 cells per thread: 80 registers, three CTAs per SM
+  // 3-D, 2 cells per thread: 74-80 registers, three CTAs per SM (deep expression stacks keep the room of two CTAs per SM)
+  spec.minb = spec.d3 && spec.np == 1 && spec.w == 8 && spec.depth <= 4 ? 3 : 2;
   if (const char* e = getenv("SB2_JIT_MINB")) spec.minb = atoi(e) > 0 ? atoi(e) : 2;  // experiments
   spec.fold = getenv("SB2_JIT_NOFOLD") ? 0 : 1;
   spec.G = sim->base.G;

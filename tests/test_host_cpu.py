@@ -277,6 +277,18 @@ def test_specialised_build_covers_every_opcode():
     assert rc == 0, log
 
 
+@pytest.mark.skipif(not _nvrtc_present(), reason="libnvrtc.so.12 not installed")
+def test_specialised_build_of_an_empty_and_of_a_maximal_program():
+    """A model without reactions (pure diffusion) and a program of SB2_RD_MAX_TOKENS records (3 KB of constants in the
+    kernel parameters on top of the stage arguments) both build."""
+    rc, log = sb.specialize_dry_run([], ns=1, np_=2, w=8, depth=1)
+    assert rc == 0, log
+    recs = [("PUSHV", 0, 0)] + [("ADDC", 0, 0)] * 382 + [("ACCADD1", 0, 0)]
+    assert len(recs) == 384
+    rc, log = sb.specialize_dry_run(recs, ns=1, np_=1, w=8, depth=1, minb=3, d3=True)
+    assert rc == 0, log
+
+
 def test_specialised_build_rejects_oversized_programs():
     rc, log = sb.specialize_dry_run([("ADDC", 0, 0)] * 385, ns=2, np_=2, w=8, depth=1)  # SB2_RD_MAX_TOKENS = 384
     assert rc == -1

@@ -5,11 +5,6 @@ run() { # label, env..., args
   env "$@" timeout 200 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --e2e-steps 1 $ARGS > gpurun_out/x_$label.json 2> gpurun_out/x.err || { echo "$label FAILED"; tail -n 3 gpurun_out/x.err; return; }
   echo "$label: $(python tools/show_bench.py gpurun_out/x_$label.json | cut -c1-60)"
 }
-ARGS=""
-run "2d" A=1
-run "2d_nofold" SB2_JIT_NOFOLD=1
 ARGS="--dim 3 --n 384"
 run "3d384" A=1
-run "3d384_nofold" SB2_JIT_NOFOLD=1
-ARGS="--dim 3"
-run "3d512" A=1
+run "3d384_allmasked" SB2_RD_ALL_GENERAL=1
