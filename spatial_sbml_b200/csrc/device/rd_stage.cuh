@@ -216,12 +216,13 @@ __device__ __forceinline__ double div6(double x) {
 
 // Diffusion stencil (calcPDE.cpp:484-559) and output of one strip row: k_m, or on the last stage the new u.
 // acc holds the reaction terms of the thread's cells; cur0 / up0 / dn0 (and, in 3-D, zp0 / zm0) point at this lane's
-// first cell in the w rows y, y+1, y-1 (z+1, z-1) of species 0, species s sits sstride doubles further.
+// first cell in the w rows y, y+1, y-1 (z+1, z-1) of species 0, species s sits sstride doubles further.  segmask: in a
+// mixed strip row (class 0), bit p says whether the 64-cell segment of cell pair p needs the per-cell predicates.
 template <int NS, int NP, int MODE, bool D3>
 __device__ __forceinline__ void rd_emit_row(const Sb2RdArgs& A, const int S, const int cls, const int lane, const bool (&active)[NP],
                                             const uint32_t (&fl)[2 * NP], double (&acc)[NS][2 * NP], const int64_t idx0,
                                             const double* mycs, const double* cur0, const double* up0, const double* dn0,
-                                            const double* zp0, const double* zm0, const int sstride) {
+                                            const double* zp0, const double* zm0, const int sstride, const uint32_t segmask) {
   constexpr int SW = 64 * NP;
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
@@ -253,14 +254,15 @@ __device__ __forceinline__ void rd_emit_row(const Sb2RdArgs& A, const int S, con
             ck1[p] = *reinterpret_cast<const double2*>(mycs + (s * 2 + 1) * SW + p * 64 + 2 * lane);
           }
         }
-#pragma unroll
-        for (int p = 0; p < NP; ++p) {
-          const uint32_t f0 = MASKED ? (fl[2 * p] >> (8 * SP_GEO(sp, s))) & 0xffu : (uint32_t)SB2_F_DOMAIN;
-          const uint32_t f1 = MASKED ? (fl[2 * p + 1] >> (8 * SP_GEO(sp, s))) & 0xffu : (uint32_t)SB2_F_DOMAIN;
+        // one pair of cells; PM: this pair's 64-cell segment needs the per-cell predicates (segmask, warp-uniform)
+        auto pair = [&](const int p, auto pair_tag) {
+          constexpr bool PM = decltype(pair_tag)::value;
+          const uint32_t f0 = PM ? (fl[2 * p] >> (8 * SP_GEO(sp, s))) & 0xffu : (uint32_t)SB2_F_DOMAIN;
+          const uint32_t f1 = PM ? (fl[2 * p + 1] >> (8 * SP_GEO(sp, s))) & 0xffu : (uint32_t)SB2_F_DOMAIN;
           // a term is skipped when the cell carries the boundary bit of that side; cells outside the domain accumulate
           // whatever their neighbours hold and are dropped at the output select (in0 / in1), so the domain bit need not
           // be part of every term's predicate
-#define RD_ADD(acc_, f_, bit_, term_) if (!MASKED || !((f_) & (bit_))) acc_ = dadd(acc_, term_)
+#define RD_ADD(acc_, f_, bit_, term_) if (!PM || !((f_) & (bit_))) acc_ = dadd(acc_, term_)
           double a0 = acc[s][2 * p], a1 = acc[s][2 * p + 1];
           if (SP_HAS_DIFF(sp, s)) {
             const double2 wc = *reinterpret_cast<const double2*>(cur + p * 64);
@@ -286,8 +288,8 @@ __device__ __forceinline__ void rd_emit_row(const Sb2RdArgs& A, const int S, con
             }
           }
 #undef RD_ADD
-          const bool in0 = !MASKED || (f0 & SB2_F_DOMAIN), in1 = !MASKED || (f1 & SB2_F_DOMAIN);
-          if (MASKED && !active[p]) continue;
+          const bool in0 = !PM || (f0 & SB2_F_DOMAIN), in1 = !PM || (f1 & SB2_F_DOMAIN);
+          if (PM && !active[p]) return;
           if (MODE != MODE_FINAL) {
             *reinterpret_cast<double2*>(sp.kout + idx0 + p * 64) = make_double2(in0 ? a0 : 0.0, in1 ? a1 : 0.0);
           } else {
@@ -299,6 +301,11 @@ __device__ __forceinline__ void rd_emit_row(const Sb2RdArgs& A, const int S, con
             *reinterpret_cast<double2*>(sp.u_out + idx0 + p * 64) =
                 make_double2(in0 ? dadd(cu[p].x, inc[0]) : cu[p].x, in1 ? dadd(cu[p].y, inc[1]) : cu[p].y);
           }
+        };
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          if (MASKED && ((segmask >> p) & 1u)) pair(p, BoolTag<true>());
+          else pair(p, BoolTag<false>());
         }
       };
       if (SP_FASTPATH(sp, s) || !SP_HAS_DIFF(sp, s)) {
@@ -387,7 +394,8 @@ __device__ __forceinline__ bool rd_compute_row(const Sb2RdArgs& A, const double*
                                                const int S, const int cls, const int lane, const bool (&active)[NP],
                                                const uint32_t (&fl)[2 * NP], const int64_t idx0, const double* cur0,
                                                const double* up0, const double* dn0, const double* zp0, const double* zm0,
-                                               const double* mycs, const uint32_t mycbar, const uint32_t cparity) {
+                                               const double* mycs, const uint32_t mycbar, const uint32_t cparity,
+                                               const uint32_t segmask) {
   constexpr int NC = 2 * NP;
   if (cls == 2) {
     // nothing of this strip row lies in a domain: k_m = 0 / u unchanged
@@ -570,7 +578,7 @@ CASE(OP, 4, (4 < NS ? 0 : DEPTH)) CASE(OP, 5, (5 < NS ? 0 : DEPTH)) CASE(OP, 6, 
 
   // ---------------- diffusion (calcPDE.cpp:484-559) + output ----------------
   if (MODE == MODE_FINAL) mbar_wait(mycbar, cparity, A.dbg == nullptr);  // k0 / k1 of this row (requested one batch ago)
-  rd_emit_row<NS, NP, MODE, D3>(A, S, cls, lane, active, fl, acc, idx0, mycs, cur0, up0, dn0, zp0, zm0, SSTRIDE);
+  rd_emit_row<NS, NP, MODE, D3>(A, S, cls, lane, active, fl, acc, idx0, mycs, cur0, up0, dn0, zp0, zm0, SSTRIDE, segmask);
   return true;
 }
 
@@ -781,7 +789,7 @@ __device__ __forceinline__ void rd_stage_body(const Sb2RdArgs& A, const double* 
     const double* base = wring + 2 + 2 * lane;
     const bool waited = rd_compute_row<NS, NP, MODE, DEPTH, false, RW * SWP>(A, kc, smem_raw + HDR, S, cls, lane, active, fl, idx0, base + slot_c * SWP,
                                                                                  base + slot_u * SWP, base + slot_d * SWP, nullptr, nullptr,
-                                                                                 mycs, mycbar, cparity);
+                                                                                 mycs, mycbar, cparity, 0xffffffffu);
     combine_done(waited);
   }
 }
@@ -790,18 +798,24 @@ __device__ __forceinline__ void rd_stage_body(const Sb2RdArgs& A, const double* 
 // 3-D grids: the same stage, marching along z.
 //
 // A CTA of W warps owns a strip of SW = 64*NP cells in x, W consecutive rows in y and a range of planes in z; warp j
-// owns row y0 + j of every plane.  The w values live in a ring of NSLOT = 4 plane tiles of W + 2 rows (the tile rows plus
+// owns row y0 + j of every plane.  The w values live in a ring of NSLOT = 3 plane tiles of W + 2 rows (the tile rows plus
 // the row below and the row above), so all six neighbours of a cell are read from shared memory and every u / k_{m-1}
 // value is fetched from global memory once per CTA (the reference and a row-marching kernel read the z neighbours from
 // two planes away in memory).  In iteration z warp j
-//   (1) waits for the bulk copy of its raw row of plane z+1 (issued one iteration earlier), turns it into w and parks
-//       it in ring slot (z+1) mod 4; warps 0 and W-1 do the same for the halo rows y0-1 and y0+W, which only they read,
-//   (2) requests the raw rows of plane z+2,
-//   (3) waits on the row-ready barriers of rows j-1 and j+1 of plane z (its own rows of planes z-1, z, z+1 it staged
-//       itself): the only synchronisation in the loop,
-//   (4) evaluates reactions and the 7-point stencil of row j of plane z and stores k_m (or the new u).
-// Four slots suffice: seeing rows j±1 of plane z staged proves that warps j±1 have finished computing plane z-2, and
-// the slot warp j overwrites next (plane z+2 over plane z-2) was last read by exactly those warps and by warp j itself.
+//   (1) waits on the row-computed barriers of rows j-1 and j+1 of plane z-2, whose ring slot it is about to overwrite,
+//   (2) waits for the bulk copy of its raw row of plane z+1 (issued one iteration earlier), turns it into w and parks
+//       it in ring slot (z+1) mod 3; warps 0 and W-1 do the same for the halo rows y0-1 and y0+W, which only they read,
+//   (3) requests the raw rows of plane z+2,
+//   (4) waits on the row-ready barriers of rows j-1 and j+1 of plane z (its own rows of planes z-1, z, z+1 it staged
+//       itself),
+//   (5) evaluates reactions and the 7-point stencil of row j of plane z, stores k_m (or the new u) and signals the
+//       row-computed barrier of (z, j).
+// Every wait refers to work of an earlier iteration of a neighbouring warp, so the warps of a CTA run about one plane
+// apart and the waits rarely block.  Row (p, j) of the ring is read by warps j-1, j, j+1 while they compute plane p and
+// by warp j itself for planes p-1 and p+1; (1) plus program order cover all of them.
+// The class map of a 3-D grid has one byte per 64 cells of a row whatever NP is (a strip combines NP of them), so that
+// the stages of a step may use different strip widths: two CTAs of 4 cells per thread per SM for the stages that fit,
+// three CTAs of 2 cells per thread for the last one, which also holds the k0 / k1 rows.
 // ---------------------------------------------------------------------------------------------
 template <int NP, int W>
 struct Geo3 {
@@ -809,7 +823,7 @@ struct Geo3 {
   static constexpr int SW = 64 * NP;
   static constexpr int SWP = SW + 4;
   static constexpr int NR = W + 2;   // ring rows per plane tile: y0-1, y0 .. y0+W-1, y0+W
-  static constexpr int NSLOT = 4;    // plane tiles in the ring
+  static constexpr int NSLOT = 3;    // plane tiles in the ring
 };
 
 template <int NS, int NP, int W, int MODE, int DEPTH>
@@ -818,9 +832,10 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
   constexpr int NC = G::NC, SW = G::SW, SWP = G::SWP, NR = G::NR, NSLOT = G::NSLOT;
   constexpr int NARR = (MODE == MODE_FIRST) ? 1 : 2;  // arrays per species in a raw slot: u (, k_{m-1})
   constexpr int SSTRIDE = NSLOT * NR * SWP;           // doubles between the w tiles of consecutive species
-  constexpr int HDRZ = ((2 + NSLOT) * W * 8 + 511) / 512 * 512;  // barriers (sb2_rd_launch_shape computes the same)
+  constexpr int HDRZ = ((2 + 2 * NSLOT) * W * 8 + 511) / 512 * 512;  // barriers (sb2_rd_launch_shape computes the same)
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  // [W bulk-copy barriers, W combine barriers, NSLOT*W row-ready barriers] [token records] [w ring: S x NSLOT x NR x SWP]
+  // [W bulk-copy barriers, W combine barriers, NSLOT*W row-ready, NSLOT*W row-computed barriers] [token records]
+  // [w ring: S x NSLOT x NR x SWP]
   // [raw slots: (W + 2) x S x NARR x SWP] [last stage: k0 / k1 slots: W x S x 2 x SW]
   const int S = MODEL_S(A);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
@@ -844,11 +859,12 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
   const uint32_t mybar = smem_addr(&bars[warp]);
   const uint32_t mycbar = smem_addr(&bars[W + warp]);
   const uint32_t rowbar0 = smem_addr(&bars[2 * W]);  // row-ready barrier of (slot q, warp j) at rowbar0 + 8 * (q * W + j)
+  const uint32_t donebar0 = smem_addr(&bars[(2 + NSLOT) * W]);  // row-computed barrier, same indexing
   if (lane == 0) {
     mbar_init(mybar, 1);
     if (MODE == MODE_FINAL) mbar_init(mycbar, 1);
     if (warp == 0)
-      for (int q = 0; q < NSLOT * W; ++q) mbar_init(rowbar0 + 8 * q, 1);
+      for (int q = 0; q < 2 * NSLOT * W; ++q) mbar_init(rowbar0 + 8 * q, 1);
     mbar_fence_init();
   }
 #ifndef SB2_RD_PROGRAM
@@ -872,6 +888,7 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
   const uint32_t mycs_s = smem_addr(mycs);
   const bool computes = y < A.ny;
   const bool wait_lo = warp > 0, wait_hi = warp < W - 1 && y + 1 <= A.ny;  // neighbours that stage rows this warp reads
+  const bool done_hi = warp < W - 1 && y + 1 < A.ny;  // the neighbour above computes (the one below always does)
 
   const uint64_t keep = (MODE == MODE_FINAL) ? l2_policy_keep() : 0;
   // one lane: bulk copies of the raw rows (u and k_{m-1} of every species, halo columns included) of plane pz
@@ -947,15 +964,34 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
   uint32_t parity = 0, cparity = 0;
   // zc: the plane computed in this iteration; plane zc + 1 is staged first.  Planes zb-1 .. ze are staged (ring slot and
   // use count of plane pz follow from pz - (zb - 1)), planes zb .. ze-1 are computed.
-  int cls_cur = 2;  // class byte of this warp's row in plane zc, fetched one iteration ahead
+  int cls_cur = 2;  // class of this warp's strip row in plane zc, fetched one iteration ahead
+  uint32_t seg_cur = 0xffffffffu;  // bit p: the 64-cell segment of cell pair p is not all-interior
   for (int zc = zb - 2; zc < ze; ++zc) {
     const int pz = zc + 1;
     // class byte of the next plane and, for mixed rows, the per-cell flag bytes of this one: requested before the
     // staging work so that their latency is covered by it
     const bool compute = computes && zc >= zb;
     const int cls = compute ? cls_cur : 2;
-    if (computes && pz >= zb && pz < ze)
-      cls_cur = A.carry ? 0 : (int)A.cls[((uint32_t)pz * (uint32_t)A.ny + (uint32_t)y) * (uint32_t)A.nstrips + blockIdx.x];
+    const uint32_t segmask = seg_cur;
+    if (computes && pz >= zb && pz < ze) {
+      if (A.carry) { cls_cur = 0; seg_cur = 0xffffffffu; }
+      else {
+        // one byte per 64 cells: all segments interior -> 1, all outside (or past the grid) -> 2, else mixed
+        const uint8_t* cb = A.cls + ((uint32_t)pz * (uint32_t)A.ny + (uint32_t)y) * (uint32_t)A.nstrips + blockIdx.x * NP;
+        int c = (int)cb[0];
+        uint32_t m = c == 1 ? 0u : 1u;
+#pragma unroll
+        for (int p = 1; p < NP; ++p) {
+          if ((int)blockIdx.x * NP + p < A.nstrips) {  // segments past the grid do not count
+            const int cp = (int)cb[p];
+            if (cp != c) c = 0;
+            if (cp != 1) m |= 1u << p;
+          }
+        }
+        cls_cur = c;
+        seg_cur = m;
+      }
+    }
     const int64_t idx0 = A.first + (int64_t)zc * A.PL + (int64_t)y * A.P + x0 + 2 * lane;
     uint32_t fl[NC];
 #pragma unroll
@@ -963,6 +999,7 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
     if (cls == 0) {
 #pragma unroll
       for (int p = 0; p < NP; ++p) {
+        if (!((segmask >> p) & 1u)) continue;  // an all-interior segment of a mixed strip row keeps the interior flags
         fl[2 * p] = 0; fl[2 * p + 1] = 0;
         if (active[p]) {
 #pragma unroll
@@ -977,7 +1014,18 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
       }
     }
     if (pz >= zb - 1) {
-      const int q = (pz - (zb - 1)) & (NSLOT - 1);
+      const uint32_t up = (uint32_t)(pz - (zb - 1));
+      const int q = (int)(up % NSLOT);
+      // (1) the slot still holds plane pz - NSLOT: the neighbours must have computed it
+      if (up >= NSLOT) {
+        const uint32_t ph = ((up - NSLOT) / NSLOT) & 1u;
+        bool ok = true;
+        if (wait_lo) ok = mbar_wait(donebar0 + 8 * (q * W + warp - 1), ph, A.dbg == nullptr);
+        if (done_hi) ok = mbar_wait(donebar0 + 8 * (q * W + warp + 1), ph, A.dbg == nullptr) && ok;
+        if (!ok && A.dbg && lane == 0) {
+          if (atomicAdd(&A.dbg[0], 1u) == 0) { A.dbg[1] = blockIdx.x; A.dbg[2] = blockIdx.y; A.dbg[3] = warp; A.dbg[4] = (uint32_t)pz; A.dbg[5] = 98; A.dbg[6] = (uint32_t)zb; A.dbg[7] = (uint32_t)ze; }
+        }
+      }
       if (!mbar_wait(mybar, parity, A.dbg == nullptr) && A.dbg && lane == 0) {
         if (atomicAdd(&A.dbg[0], 1u) == 0) { A.dbg[1] = blockIdx.x; A.dbg[2] = blockIdx.y; A.dbg[3] = warp; A.dbg[4] = (uint32_t)pz; A.dbg[5] = parity; A.dbg[6] = (uint32_t)zb; A.dbg[7] = (uint32_t)ze; }
       }
@@ -996,7 +1044,7 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
     // ring slots may be overwritten is carried from warp to warp by these waits
     {
       const uint32_t u = (uint32_t)(zc - (zb - 1));
-      const uint32_t q = u & (NSLOT - 1), ph = (u / NSLOT) & 1u;
+      const uint32_t q = u % NSLOT, ph = (u / NSLOT) & 1u;
       bool ok = true;
       if (wait_lo) ok = mbar_wait(rowbar0 + 8 * (q * W + warp - 1), ph, A.dbg == nullptr);
       if (wait_hi) ok = mbar_wait(rowbar0 + 8 * (q * W + warp + 1), ph, A.dbg == nullptr) && ok;
@@ -1004,19 +1052,25 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
         if (atomicAdd(&A.dbg[0], 1u) == 0) { A.dbg[1] = blockIdx.x; A.dbg[2] = blockIdx.y; A.dbg[3] = warp; A.dbg[4] = (uint32_t)zc; A.dbg[5] = 99; A.dbg[6] = (uint32_t)zb; A.dbg[7] = (uint32_t)ze; }
       }
     }
-    if (!compute) continue;
-    const int qc = (zc - (zb - 1)) & (NSLOT - 1), qp = (qc + 1) & (NSLOT - 1), qm = (qc + NSLOT - 1) & (NSLOT - 1);
+    const int qc = (int)((uint32_t)(zc - (zb - 1)) % NSLOT), qp = qc + 1 == NSLOT ? 0 : qc + 1, qm = qc == 0 ? NSLOT - 1 : qc - 1;
+    if (!compute) {
+      // plane zb-1 is never computed: its row-computed phase completes here, so that the use count of a slot is the
+      // same for both kinds of barrier
+      if (computes && lane == 0) mbar_arrive(donebar0 + 8 * (qc * W + warp));
+      continue;
+    }
     const double* base = wring + (warp + 1) * SWP + 2 + 2 * lane;  // this lane's first cell in row j of tile 0
     const double* cur = base + (size_t)qc * NR * SWP;
     const bool waited = rd_compute_row<NS, NP, MODE, DEPTH, true, SSTRIDE>(
         A, kc, smem_raw + HDRZ, S, cls, lane, active, fl, idx0, cur, cur + SWP, cur - SWP, base + (size_t)qp * NR * SWP,
-        base + (size_t)qm * NR * SWP, mycs, mycbar, cparity);
+        base + (size_t)qm * NR * SWP, mycs, mycbar, cparity, segmask);
     if (MODE == MODE_FINAL) {
       if (!waited) mbar_wait(mycbar, cparity, A.dbg == nullptr);
       cparity ^= 1;
-      __syncwarp();
-      if (zc + 1 < ze && elect_one()) issue_combine(zc + 1);
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(donebar0 + 8 * (qc * W + warp));  // (5) row (zc, j) will not be read by this warp's stencil again
+    if (MODE == MODE_FINAL && zc + 1 < ze && elect_one()) issue_combine(zc + 1);
   }
 }
 
@@ -1031,9 +1085,9 @@ __device__ __forceinline__ void rd_stage_any(const Sb2RdArgs& A, const double* _
 // model-specialised build: entry points with C names (expanded at global scope by the generated translation unit),
 // parameters = the stage arguments followed by the constants
 struct Sb2RdJitParams { Sb2RdArgs a; double kc[SB2_RD_NKC]; };
-#define RD_JIT_ENTRY(name, MODE) \
-  extern "C" __global__ void __launch_bounds__(SB2_RD_W * 32, SB2_RD_MINB) name(const __grid_constant__ rd::Sb2RdJitParams P) { \
-    rd::rd_stage_any<SB2_RD_NS, SB2_RD_NP, SB2_RD_W, MODE, SB2_RD_DEPTH, SB2_RD_D3>(P.a, P.kc); }
+#define RD_JIT_ENTRY(name, MODE, NP_, MINB_) \
+  extern "C" __global__ void __launch_bounds__(SB2_RD_W * 32, MINB_) name(const __grid_constant__ rd::Sb2RdJitParams P) { \
+    rd::rd_stage_any<SB2_RD_NS, NP_, SB2_RD_W, MODE, SB2_RD_DEPTH, SB2_RD_D3>(P.a, P.kc); }
 #else
 template <int NS, int NP, int W, int MODE, int DEPTH, int MINB, bool D3>
 __global__ void __launch_bounds__(W * 32, MINB) rd_stage_kernel(const __grid_constant__ Sb2RdArgs A) {

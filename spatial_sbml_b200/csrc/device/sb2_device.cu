@@ -410,7 +410,7 @@ void fill_stage_args(sb2_sim* sim, Sb2StageCore& a, int m, double dt, int row_be
       // not compute, so long marches are cheap, short ones fill the machine on small grids
       static const int zpb_default = getenv("SB2_RD_ZPB") ? atoi(getenv("SB2_RD_ZPB")) : 32;
       const int planes = row_end - row_begin;
-      const int64_t tiles = (int64_t)sim->nstrips * ((sim->g.ny + W - 1) / W);
+      const int64_t tiles = (int64_t)((sim->g.nx + 64 * sim->rd.np - 1) / (64 * sim->rd.np)) * ((sim->g.ny + W - 1) / W);
       int zpb = zpb_default < 1 ? 1 : zpb_default;
       while (zpb > 1 && tiles * ((planes + zpb - 1) / zpb) < 148 * 6) zpb = (zpb + 1) / 2;
       a.rows_per_block = zpb;
@@ -438,8 +438,15 @@ void fill_stage_args(sb2_sim* sim, Sb2StageCore& a, int m, double dt, int row_be
 Sb2RdJitSpec jit_spec(const sb2_sim* sim) {
   Sb2RdJitSpec spec;
   spec.ns = sim->base.S; spec.np = sim->rd.np; spec.w = sim->rd.w; spec.depth = sim->base.depth; spec.d3 = sim->g.dim == 3;
-  // 3-D, 2 cells per thread: 74-80 registers, three CTAs per SM (deep expression stacks keep the room of two CTAs per SM)
-  spec.minb = spec.d3 && spec.np == 1 && spec.w == 8 && spec.depth <= 4 ? 3 : 2;
+  spec.minb = 2; spec.np_final = 0; spec.minb_final = 0;
+  if (spec.d3 && spec.w == 8 && spec.np == 1) {
+    // 3-D (the class map has 64-cell granularity, so the strip width is free per stage).  Last stage: 2 cells per
+    // thread, 74-80 registers, three CTAs per SM (deep expression stacks keep the room of two).  Other stages, up to
+    // two species: 4 cells per thread, two CTAs per SM (106 KB of shared memory each).
+    spec.np_final = 1; spec.minb_final = spec.depth <= 4 ? 3 : 2;
+    if (spec.ns <= 2 && !getenv("SB2_JIT_NP1")) { spec.np = 2; spec.minb = 2; }
+    else spec.minb = spec.minb_final;
+  }
   if (const char* e = getenv("SB2_JIT_MINB")) spec.minb = atoi(e) > 0 ? atoi(e) : 2;  // experiments
   spec.fold = getenv("SB2_JIT_NOFOLD") ? 0 : 1;
   spec.G = sim->base.G;
@@ -832,8 +839,9 @@ int sb2_finalize(sb2_sim* sim) {
     b.nrd = (int)sim->rdprog.size();
     CK(cudaMalloc((void**)&sim->d_rdtok, sizeof(Sb2RdTok) * (SB2_RD_MAX_TOKENS + 2) * 2));
     sim->rd_uploaded.clear();
-    const int sw = 64 * sim->rd.np;
-    if (sw + 4 > SB2_TAIL_PAD) return fail(sim, SB2_ERR_STATE, "strip wider than the tail pad of the field layout");
+    // class map: one byte per strip row in 2-D, one per 64 cells of a row in 3-D (the z-marching kernel combines them)
+    const int sw = sim->g.dim == 3 ? 64 : 64 * sim->rd.np;
+    if (64 * sim->rd.np + 4 > SB2_TAIL_PAD) return fail(sim, SB2_ERR_STATE, "strip wider than the tail pad of the field layout");
     sim->nstrips = (sim->g.nx + sw - 1) / sw;
     const int nrows = sim->g.ny * sim->g.nz;  // every row of every held plane
     CK(cudaMalloc((void**)&sim->d_cls, (size_t)sim->nstrips * nrows));
@@ -1325,6 +1333,7 @@ int sb2_specialize_dry_run(const uint32_t* code, const uint32_t* arg, int n, int
   for (int i = 0; i < n; ++i) { prog[i].code = code[i]; prog[i].arg = arg[i]; prog[i].c = 0.0; }
   Sb2RdJitSpec spec;
   spec.ns = ns; spec.np = np; spec.w = w; spec.depth = depth; spec.minb = minb; spec.d3 = d3;
+  spec.np_final = 0; spec.minb_final = 0;
   // a typical model: one geometry, every species diffuses with uniform coefficients
   spec.fold = 1; spec.G = 1; spec.hasdiff_mask = spec.fastpath_mask = (1u << ns) - 1u; spec.geo_bits = 0;
   std::vector<char> cubin;

@@ -7,4 +7,7 @@ run() { # label, env..., args
 }
 ARGS="--dim 3 --n 384"
 run "3d384" A=1
-run "3d384_allmasked" SB2_RD_ALL_GENERAL=1
+ARGS="--dim 3"
+run "3d512" A=1
+ARGS=""
+run "2d" A=1
