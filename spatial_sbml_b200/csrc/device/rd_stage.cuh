@@ -976,16 +976,20 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
     if (computes && pz >= zb && pz < ze) {
       if (A.carry) { cls_cur = 0; seg_cur = 0xffffffffu; }
       else {
-        // one byte per 64 cells: all segments interior -> 1, all outside (or past the grid) -> 2, else mixed
+        // one byte per 64 cells: all segments interior -> 1, all outside -> 2, else mixed
         const uint8_t* cb = A.cls + ((uint32_t)pz * (uint32_t)A.ny + (uint32_t)y) * (uint32_t)A.nstrips + blockIdx.x * NP;
         int c = (int)cb[0];
         uint32_t m = c == 1 ? 0u : 1u;
 #pragma unroll
         for (int p = 1; p < NP; ++p) {
-          if ((int)blockIdx.x * NP + p < A.nstrips) {  // segments past the grid do not count
+          if ((int)blockIdx.x * NP + p < A.nstrips) {
             const int cp = (int)cb[p];
             if (cp != c) c = 0;
             if (cp != 1) m |= 1u << p;
+          } else {
+            // past the grid: the pair is inactive and must take the predicated path, so an interior row becomes mixed
+            m |= 1u << p;
+            if (c == 1) c = 0;
           }
         }
         cls_cur = c;

@@ -444,7 +444,7 @@ Sb2RdJitSpec jit_spec(const sb2_sim* sim) {
     // thread, 74-80 registers, three CTAs per SM (deep expression stacks keep the room of two).  Other stages, up to
     // two species: 4 cells per thread, two CTAs per SM (106 KB of shared memory each).
     spec.np_final = 1; spec.minb_final = spec.depth <= 4 ? 3 : 2;
-    if (spec.ns <= 2 && !getenv("SB2_JIT_NP1")) { spec.np = 2; spec.minb = 2; }
+    if (spec.ns <= 2 && spec.depth <= 4 && !getenv("SB2_JIT_NP1")) { spec.np = 2; spec.minb = 2; }
     else spec.minb = spec.minb_final;
   }
   if (const char* e = getenv("SB2_JIT_MINB")) spec.minb = atoi(e) > 0 ? atoi(e) : 2;  // experiments

@@ -434,3 +434,32 @@ def test_specialize_now_installs_the_kernel_between_steps(monkeypatch):
         for sp in [str(s) for s in g["species"]]:
             assert rel_linf(sim.getVariableCompact(sp), g["step/10/%s" % sp]) <= 1e-10
         sim.close()
+
+
+@pytest.mark.parametrize("dims", [(66, 10, 9), (130, 9, 5), (200, 17, 6), (257, 8, 4), (64, 64, 1), (129, 8, 1), (193, 17, 1)])
+def test_awkward_grid_sizes_with_the_specialised_kernel(dims, monkeypatch):
+    """The specialised 3-D build uses 128-cell strips for stages 1-3 and 64-cell strips for the last one: widths around
+    multiples of 64 and 128 (strips that end inside or before their second 64-cell segment), against the restated oracle."""
+    import os
+    import sys
+    import spatial_sbml_b200 as sb
+    from spatial_sbml_b200 import synthetic
+    from conftest import REPO
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import rd_oracle
+    monkeypatch.setenv("SB2_JIT", "require")
+    dt = 0.07 if dims[2] == 1 else 0.02
+    model = synthetic.turing(dims[0], dims[1], dims[2] if dims[2] > 1 else None)
+    host = sb.SpatialSimulator(host_only=True)
+    host.initFromString(model, *dims)
+    orc = rd_oracle.from_simulator(host, model, dims)
+    host.close()
+    sim = sb.SpatialSimulator()
+    sim.initFromString(model, *dims)
+    assert sim.isSpecialized(), sim.getSpecializeInfo()
+    for t in range(4):
+        orc.one_step(t, dt)
+        sim.oneStep(t, dt)
+    for sp in ("species_1", "species_2"):
+        assert np.array_equal(sim.getVariableCompact(sp), orc.sp[sp].u), (dims, sp)
+    sim.close()
