@@ -972,7 +972,11 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
     // staging work so that their latency is covered by it
     const bool compute = computes && zc >= zb;
     const int cls = compute ? cls_cur : 2;
+#ifdef SB2_RD_ROWMASK  // experiments: per-cell predicates on every segment of a mixed strip row
+    const uint32_t segmask = 0xffffffffu;
+#else
     const uint32_t segmask = seg_cur;
+#endif
     if (computes && pz >= zb && pz < ze) {
       if (A.carry) { cls_cur = 0; seg_cur = 0xffffffffu; }
       else {
