@@ -4,6 +4,11 @@
 // layout is different by design: volume masks are one byte per volume cell, membranes are sparse
 // point lists keyed by doubled-grid index, and nothing of size (2n-1)^d is ever allocated here.
 #include "host_model.h"
+#include <atomic>
+#include <chrono>
+#include <thread>
+#include <cstdio>
+#include <cstdlib>
 
 #include <algorithm>
 #include <cmath>
@@ -13,6 +18,27 @@
 #include "../../../include/spatial_b200.h"
 
 namespace sb2host {
+
+namespace {
+// f(begin, end) on disjoint ranges of [0, n), on several host threads when the range is large (set-up of 10^7 .. 10^8
+// cells); the loops it is used for write only to the cells of their own range
+template <class F>
+void parallelRanges(int64_t n, int64_t grain, F f) {
+  unsigned nthreads = std::thread::hardware_concurrency();
+  if (const char* e = getenv("SSB_HOST_THREADS")) nthreads = (unsigned)atoi(e);
+  if (nthreads > 32) nthreads = 32;
+  if (nthreads <= 1 || n < grain * 2) { f((int64_t)0, n); return; }
+  const int64_t chunk = (n + nthreads - 1) / nthreads;
+  std::vector<std::thread> pool;
+  for (unsigned t = 0; t < nthreads; ++t) {
+    const int64_t b = (int64_t)t * chunk, e = std::min<int64_t>(n, b + chunk);
+    if (b >= e) break;
+    pool.emplace_back([=] { f(b, e); });
+  }
+  for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
+}
+}  // namespace
+
 
 Var::Var()
     : sp(NULL), com(NULL), para(NULL), hasValue(false), isUniform(false), isResolved(false), inVol(true),
@@ -254,6 +280,14 @@ bool Model::setVolumeGeometries() {
   Geometry* geometry = mp->getGeometry();
   const int64_t nc = ncells();
   std::vector<double> tmp;
+  const bool timing = getenv("SSB_TIMING") != NULL;
+  auto t0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[ssb]   geo: %-18s %.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+    t0 = t1;
+  };
   for (unsigned int gi = 0; gi < geometry->getNumGeometryDefinitions(); ++gi) {
     GeometryDefinition* gd = geometry->getGeometryDefinition(gi);
     if (gd->isAnalyticGeometry()) {
@@ -275,15 +309,25 @@ bool Model::setVolumeGeometries() {
         rearrangeAst(ast);
         emitRpn(ast, *this, g->rpn);
         delete ast;
+        lap("rpn");
         tmp.assign(nc, 0.0);
+        lap("tmp.assign");
         evalRpnCompact(g->rpn, NULL, nc, tmp.data());
+        lap("eval");
         g->isDomain.resize(nc);
-        for (int64_t k = 0; k < nc; ++k) {
-          const int d = (int)tmp[k];  // isDomain[k] = (int)tmp_isDomain[k], spatialsimulator.cpp:469
-          g->isDomain[k] = d == 1 ? 1 : d == 0 ? 0 : 3;
+        {
+          const double* tp = tmp.data();
+          auto* dp = g->isDomain.data();
+          parallelRanges(nc, 1 << 18, [tp, dp](int64_t b, int64_t e) {
+            for (int64_t k = b; k < e; ++k) {
+              const int d = (int)tp[k];  // isDomain[k] = (int)tmp_isDomain[k], spatialsimulator.cpp:469
+              dp[k] = d == 1 ? 1 : d == 0 ? 0 : 3;
+            }
+          });
         }
         g->hasMask = true;
         geos.push_back(g);
+        lap("convert");
       }
     } else if (gd->isSampledFieldGeometry()) {
       // spatialsimulator.cpp:483-604: image rows are stored top-down (y flipped)
@@ -377,19 +421,29 @@ bool Model::setVolumeGeometries() {
         if (!(ex->getOrdinal() < in->getOrdinal())) continue;
         Geo* gin = geoByDomainType(in->getDomainType());
         if (!gin || !gin->hasMask) continue;
-        for (int64_t c = 0; c < nc; ++c)
-          if (gex->isDomain[c] == 1 && gin->isDomain[c] == 1) gex->isDomain[c] = 0;
+        {
+          auto* ex_d = gex->isDomain.data();
+          const auto* in_d = gin->isDomain.data();
+          parallelRanges(nc, 1 << 18, [ex_d, in_d](int64_t b, int64_t e) {
+            for (int64_t c = b; c < e; ++c)
+              if (ex_d[c] == 1 && in_d[c] == 1) ex_d[c] = 0;
+          });
+        }
       }
       // NB the reference appends to domainIndex here; a domain type listed twice would be appended twice
       gex->nDomain = 0;
       gex->isBoundary.assign(nc, 0);
       const int64_t sy = nx, sz = (int64_t)nx * ny;
-      for (int k = 0; k < nz; ++k)
-        for (int jj = 0; jj < ny; ++jj)
+      std::atomic<int64_t> domainCount(0);
+      // rows (k, jj) are independent: a row only reads isDomain and writes its own isBoundary entries
+      parallelRanges((int64_t)nz * ny, 256, [&](int64_t rb, int64_t re) {
+      int64_t localCount = 0;
+      for (int64_t row = rb; row < re; ++row) {
+          const int k = (int)(row / ny), jj = (int)(row % ny);
           for (int i = 0; i < nx; ++i) {
             const int64_t c = (int64_t)k * sz + (int64_t)jj * sy + i;
             if (gex->isDomain[c] != 1) continue;
-            gex->nDomain++;
+            ++localCount;
             bool b = false;
             const int gj = jj + off[1], gk = k + off[2];
             if (dimension == 1) {
@@ -406,6 +460,11 @@ bool Model::setVolumeGeometries() {
             }
             gex->isBoundary[c] = b ? 1 : 0;
           }
+      }
+      domainCount += localCount;
+      });
+      gex->nDomain = domainCount.load();
+      lap("layer+boundary");
     }
   }
   for (size_t g = 0; g < geos.size(); ++g)
@@ -995,19 +1054,33 @@ bool Model::build(SBMLDocument* d, int xdim, int ydim, int zdim, int slabLo, int
     else if (c->getSpatialDimensions() >= volDimension) volDimension = c->getSpatialDimensions();
     else memDimension = c->getSpatialDimensions();
   }
+  const bool timing = getenv("SSB_TIMING") != NULL;
+  auto t0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[ssb] %-22s %.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+    t0 = t1;
+  };
   setCompartments();
   setSpecies();
   if (!setParameters()) return false;
+  lap("parameters");
   tVar = new Var;
   tVar->id = "t";
   tVar->isResolved = true; tVar->isUniform = true; tVar->hasValue = true; tVar->uniformValue = 0.0;
   vars.push_back(tVar);
   if (!setVolumeGeometries()) return false;
+  lap("volume geometries");
   setMembraneGeometries();
+  lap("membrane geometries");
   if (!resolveAssignments()) return false;
+  lap("assignments");
   setBoundaryTypes();
+  lap("boundary types");
   setReactions();
   setRateRules();
+  lap("reactions");
   // Membrane normals feed only membrane transport and membrane diffusion; computing them walks the
   // whole contour per point, so skip the pass when nothing consumes it.
   bool needNormals = false;

@@ -5,6 +5,11 @@
 // set-up time only (geometry masks, initial assignments); the per-step evaluation of kinetic laws
 // is the device bytecode interpreter in csrc/device/stage_kernel.cu.
 #include "host_model.h"
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <thread>
+#include <vector>
 
 #include <cmath>
 
@@ -171,12 +176,64 @@ void collectDependence(const ASTNode* ast, const Model& m, std::vector<Var*>& de
   if (v) dep.push_back(v);
 }
 
-// calcPDE.cpp:21-222.  The stack outlives the cell loop (stale slots are visible to malformed
-// streams exactly as in the reference); a cell is written only when something is left on the stack.
+namespace {
+void evalRange(const Rpn& rpn, const uint8_t* mask, int64_t c0, int64_t c1, double* out);
+
+// A stream in which every operator finds its operands on the stack never reads a slot left over from the previous
+// cell, so its cells are independent of each other.
+bool cellsAreIndependent(const Rpn& rpn) {
+  int sp = 0;
+  for (size_t i = 0; i < rpn.size(); ++i) {
+    const Tok& t = rpn[i];
+    if (t.kind == Tok::VAR || t.kind == Tok::CONSTVAR || t.kind == Tok::LITERAL) { if (++sp > 60) return false; continue; }
+    if (t.kind != Tok::OP) return false;  // unresolved names: keep the reference's exact stale-slot behaviour
+    bool unary = false;
+    switch (t.astType) {
+      case AST_FUNCTION_ABS: case AST_FUNCTION_ARCCOS: case AST_FUNCTION_ARCCOSH: case AST_FUNCTION_ARCCSC:
+      case AST_FUNCTION_ARCSIN: case AST_FUNCTION_ARCTAN: case AST_FUNCTION_COS: case AST_FUNCTION_COSH:
+      case AST_FUNCTION_CSC: case AST_FUNCTION_EXP: case AST_FUNCTION_LN: case AST_FUNCTION_ROOT: case AST_FUNCTION_SIN:
+      case AST_FUNCTION_SINH: case AST_FUNCTION_TAN: case AST_FUNCTION_TANH: case AST_LOGICAL_NOT: unary = true; break;
+      case AST_PLUS: case AST_MINUS: case AST_TIMES: case AST_DIVIDE: case AST_POWER: case AST_FUNCTION_POWER:
+      case AST_FUNCTION_LOG: case AST_LOGICAL_AND: case AST_LOGICAL_OR: case AST_LOGICAL_XOR: case AST_RELATIONAL_EQ:
+      case AST_RELATIONAL_GEQ: case AST_RELATIONAL_GT: case AST_RELATIONAL_LEQ: case AST_RELATIONAL_LT:
+      case AST_RELATIONAL_NEQ: break;
+      default: return false;  // listed-but-empty operators
+    }
+    if (unary) { if (sp < 1) return false; }
+    else { if (sp < 2) return false; --sp; }
+  }
+  return sp >= 1;
+}
+}  // namespace
+
+// calcPDE.cpp:21-222.  Large grids with a well-formed stream are evaluated by several host threads (set-up of an
+// 8192^2 grid spends most of its time here); anything else takes the serial loop, whose stack outlives the cell loop
+// exactly as in the reference.
 void evalRpnCompact(const Rpn& rpn, const uint8_t* mask, int64_t ncells, double* out) {
+  unsigned nthreads = std::thread::hardware_concurrency();
+  if (const char* e = getenv("SSB_HOST_THREADS")) nthreads = (unsigned)atoi(e);
+  if (nthreads > 32) nthreads = 32;
+  if (nthreads > 1 && ncells >= (int64_t)1 << 18 && cellsAreIndependent(rpn)) {
+    std::vector<std::thread> pool;
+    const int64_t chunk = (ncells + nthreads - 1) / nthreads;
+    for (unsigned t = 0; t < nthreads; ++t) {
+      const int64_t c0 = (int64_t)t * chunk, c1 = std::min<int64_t>(ncells, c0 + chunk);
+      if (c0 >= c1) break;
+      pool.emplace_back([&rpn, mask, c0, c1, out] { evalRange(rpn, mask, c0, c1, out); });
+    }
+    for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
+    return;
+  }
+  evalRange(rpn, mask, 0, ncells, out);
+}
+
+namespace {
+// The stack outlives the cell loop (stale slots are visible to malformed
+// streams exactly as in the reference); a cell is written only when something is left on the stack.
+void evalRange(const Rpn& rpn, const uint8_t* mask, int64_t cbegin, int64_t cend, double* out) {
   double st[64] = {0};
   const int n = (int)rpn.size();
-  for (int64_t c = 0; c < ncells; ++c) {
+  for (int64_t c = cbegin; c < cend; ++c) {
     if (mask && !mask[c]) continue;
     int sp = 0;
     for (int i = 0; i < n; ++i) {
@@ -232,5 +289,6 @@ void evalRpnCompact(const Rpn& rpn, const uint8_t* mask, int64_t ncells, double*
     if (sp > 0) out[c] = st[--sp];
   }
 }
+}  // namespace
 
 }  // namespace sb2host

@@ -292,3 +292,24 @@ def test_specialised_build_of_an_empty_and_of_a_maximal_program():
 def test_specialised_build_rejects_oversized_programs():
     rc, log = sb.specialize_dry_run([("ADDC", 0, 0)] * 385, ns=2, np_=2, w=8, depth=1)  # SB2_RD_MAX_TOKENS = 384
     assert rc == -1
+
+
+def test_threaded_host_setup_gives_the_same_model(monkeypatch):
+    """Grids of 2^18 cells and more evaluate the geometry / initial-assignment streams and the boundary scan on several
+    host threads (SSB_HOST_THREADS, default: all cores): masks, boundary types and initial fields must not depend on it."""
+    from spatial_sbml_b200 import synthetic
+    dims = (640, 520, 1)
+    model = synthetic.turing(dims[0], dims[1])
+    out = {}
+    for threads in ("1", "7"):
+        monkeypatch.setenv("SSB_HOST_THREADS", threads)
+        sim = sb.SpatialSimulator(host_only=True)
+        sim.initFromString(model, *dims)
+        out[threads] = {"geo": sim.getGeometry("inside").copy(), "bnd": sim.getBoundary("inside").copy(),
+                        "btype": sim.getBoundaryType("inside").copy(), "u": sim.getVariable("species_1").copy(),
+                        "v": sim.getVariable("species_2").copy(), "summary": sim.getSetupText("summary")}
+        sim.close()
+    for key in ("geo", "bnd", "btype", "u", "v"):
+        assert np.array_equal(out["1"][key], out["7"][key]), key
+    assert out["1"]["summary"] == out["7"]["summary"]
+    assert out["1"]["geo"].sum() == (dims[0] - 2) * (dims[1] - 2)

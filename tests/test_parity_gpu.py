@@ -207,11 +207,16 @@ def test_cli_driver_writes_the_reference_trajectory(tmp_path):
     assert np.array_equal(rows[:22, 0], np.arange(22.0)) and np.all(rows[:22, 1] == 0.0)
 
 
-@pytest.mark.parametrize("case,nslabs", [("turing_blob", 4), ("turing_blob", 0), ("syn_turing_3d", 3), ("brusselator_300", 7), ("fish", 5)])
-def test_host_pipelined_step_is_the_same_step(case, nslabs):
+@pytest.mark.parametrize("case,nslabs,jit", [("turing_blob", 4, None), ("turing_blob", 0, None), ("syn_turing_3d", 3, None),
+                                             ("brusselator_300", 7, None), ("fish", 5, None),
+                                             ("turing_blob", 4, "require"), ("syn_turing_3d", 3, "require"), ("syn_brusselator_3d", 2, "require")])
+def test_host_pipelined_step_is_the_same_step(case, nslabs, jit, monkeypatch):
     """oneStepHost (upload / four stages / download pipelined over slabs, apron rows recomputed) must give exactly the
-    fields of oneStep, step after step, feeding its own output back as the next input."""
+    fields of oneStep, step after step, feeding its own output back as the next input; with the interpreter kernel and
+    with the specialised one (whose 3-D build uses two strip widths)."""
     import spatial_sbml_b200 as sb
+    if jit:
+        monkeypatch.setenv("SB2_JIT", jit)
     g = load_golden(case)
     nx, ny, nz = [int(v) for v in g["dims"]]
     dt = float(g["dt"])
