@@ -2,6 +2,9 @@
 // CIP-CSLR advection, membrane transport, min-dt reduction.  This translation unit is compiled
 // with -fmad=false so that plain C expressions keep the reference's operation order and rounding.
 #include "sb2_aux.h"
+#include <algorithm>
+#include <cstdlib>
+#include <thread>
 #include "sb2_ops.cuh"
 
 #include <algorithm>
@@ -96,20 +99,22 @@ int sb2_build_boundary_lists(const sb2_grid& g, int64_t P, int64_t PL, int64_t f
       if (i < 0 || j < 0 || k < 0 || i >= nx || j >= ny || k >= nz) return false;
       return fl[((int64_t)k * ny + j) * nx + i] & SB2_F_DOMAIN;
     };
-    int seq = 0;
-    auto add = [&](int side, int ai, int aj, int ak, int vi, int vj, int vk) {
-      if (bcs[s].kind[side] == SB2_BC_NONE) return;
-      const int slabc = g.dim == 3 ? ak : aj;
-      if (slabc < own_lo || slabc >= own_hi) return;
-      BcEntry e;
-      e.species = (int)s; e.cell = pad(ai, aj, ak); e.valcell = pad(vi, vj, vk); e.side = side; e.seq = seq++;
-      entries.push_back(e);
-    };
     // The loop of calcPDE.cpp:958-1033 over every even point c, restated on compact coordinates.
     // Flat-index wrap-around of the reference (X±2, X±4 leaving the row) always lands on an odd
     // row / plane, which no volume domain contains, so it reads as "not in domain" (SURVEY §8 a8').
-    for (int k = 0; k < nz; ++k)
-      for (int j = 0; j < ny; ++j)
+    // Rows are scanned by several host threads on large grids; the pieces are concatenated in row order, so the
+    // entries (and their sequence numbers) come out exactly as from one serial scan.
+    auto scan = [&](int64_t row_begin, int64_t row_end, std::vector<BcEntry>& local) {
+      auto add = [&](int side, int ai, int aj, int ak, int vi, int vj, int vk) {
+        if (bcs[s].kind[side] == SB2_BC_NONE) return;
+        const int slabc = g.dim == 3 ? ak : aj;
+        if (slabc < own_lo || slabc >= own_hi) return;
+        BcEntry e;
+        e.species = (int)s; e.cell = pad(ai, aj, ak); e.valcell = pad(vi, vj, vk); e.side = side; e.seq = 0;
+        local.push_back(e);
+      };
+      for (int64_t row = row_begin; row < row_end; ++row) {
+        const int k = (int)(row / ny), j = (int)(row % ny);
         for (int i = 0; i < nx; ++i) {
           // X: p = c+1 gets the Xmax condition when its outer neighbour is outside
           if (dom(i + 1, j, k) && !dom(i + 2, j, k)) add(SB2_XMAX, i + 1, j, k, i + 1, j, k);
@@ -133,6 +138,32 @@ int sb2_build_boundary_lists(const sb2_grid& g, int64_t P, int64_t PL, int64_t f
             }
           }
         }
+      }
+    };
+    const int64_t rows = (int64_t)nz * ny;
+    unsigned nthreads = std::thread::hardware_concurrency();
+    if (const char* e = getenv("SSB_HOST_THREADS")) nthreads = (unsigned)atoi(e);
+    if (nthreads > 32) nthreads = 32;
+    const int64_t par_min = getenv("SSB_HOST_PAR_MIN") ? atoll(getenv("SSB_HOST_PAR_MIN")) : ((int64_t)1 << 18);  // tests lower it
+    if (nthreads < 1 || rows * nx < par_min) nthreads = 1;
+    std::vector<std::vector<BcEntry> > pieces(nthreads);
+    if (nthreads == 1) scan(0, rows, pieces[0]);
+    else {
+      std::vector<std::thread> pool;
+      const int64_t chunk = (rows + nthreads - 1) / nthreads;
+      for (unsigned t = 0; t < nthreads; ++t) {
+        const int64_t b = (int64_t)t * chunk, e = std::min<int64_t>(rows, b + chunk);
+        if (b >= e) break;
+        pool.emplace_back([&scan, &pieces, t, b, e] { scan(b, e, pieces[t]); });
+      }
+      for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
+    }
+    int seq = 0;
+    for (unsigned t = 0; t < nthreads; ++t)
+      for (size_t q = 0; q < pieces[t].size(); ++q) {
+        pieces[t][q].seq = seq++;
+        entries.push_back(pieces[t][q]);
+      }
   }
   std::stable_sort(entries.begin(), entries.end(), [](const BcEntry& a, const BcEntry& b) {
     if (a.species != b.species) return a.species < b.species;
