@@ -160,3 +160,28 @@ def brusselator(nx, ny, nz=None, bc_values=None, perturb=False):
         _reaction("J3", [("X", 1)], [], _apply("times", _ci("k"), _ci("X"))),
     ]
     return _document("synthetic_brusselator", axes, dims, species, params, assignments, rx)
+
+
+def cascade3(nx, ny, nz=None):
+    """Three diffusing species in one compartment: the Brusselator pair plus a product Z that X decays into and that is
+    degraded with saturating kinetics (a division and a comparison in the law).  Exercises the three- and four-species
+    kernel variants, which the reference's own two-species synthetic models leave idle in 3-D.  dt 0.05."""
+    dims = [nx, ny] + ([nz] if nz else [])
+    axes = ["x", "y", "z"][:len(dims)]
+    params = (_transport_params("X", 0.16, axes, None) + _transport_params("Y", 0.8, axes, None) +
+              _transport_params("Z", 0.3, axes, None))
+    params += [_param("k", 0.1), _param("A", 2.5), _param("B", 5.24), _param("Vz", 0.4), _param("Kz", 0.7)]
+    species = [("X", None), ("Y", 2.0), ("Z", None)]
+    assignments = [("X", _apply("plus", _cn(2.5), _apply("times", _cn(0.01), _ci("x")))),
+                   ("Z", _apply("plus", _cn(0.2), _apply("times", _cn(0.02), _ci("y"))))]
+    rx = [
+        _reaction("J0", [], [("X", 1)], _apply("times", _ci("k"), _ci("A"))),
+        _reaction("J1", [("Y", 1)], [("X", 1)], _apply("times", _ci("k"), _ci("X"), _ci("X"), _ci("Y"))),
+        _reaction("J2", [("X", 1)], [("Y", 1)], _apply("times", _ci("k"), _ci("X"), _ci("B"))),
+        _reaction("J3", [("X", 1)], [("Z", 2)], _apply("times", _ci("k"), _ci("X"))),
+        _reaction("J4", [("Z", 1)], [],
+                  _apply("times", _apply("divide", _apply("times", _ci("Vz"), _ci("Z")), _apply("plus", _ci("Kz"), _ci("Z"))),
+                         _apply("gt", _ci("Z"), _cn(0.05)))),
+    ]
+    return _document("synthetic_cascade3", axes, dims, species, params, assignments, rx)
+

@@ -67,6 +67,9 @@ CASES = {
     "syn_turing_2d": ("synthetic:turing:48:40", (48, 40, 1), 0.07, [1, 10, 100], {}, []),
     "syn_turing_3d": ("synthetic:turing:20:16:12", (20, 16, 12), 0.02, [1, 10, 50], {}, []),
     "syn_brusselator_3d": ("synthetic:brusselator:14:12:10", (14, 12, 10), 0.1, [1, 20], {}, []),
+    # three species: the 3- / 4-species kernel variants, stoichiometry 2, a division and a comparison in a law
+    "syn_cascade3_3d": ("synthetic:cascade3:70:11:9", (70, 11, 9), 0.05, [1, 10, 40], {}, []),
+    "syn_cascade3_2d": ("synthetic:cascade3:150:40", (150, 40, 1), 0.05, [1, 10, 40], {}, []),
 }
 
 

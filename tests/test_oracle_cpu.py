@@ -23,7 +23,7 @@ import spatial_sbml_b200 as sb
 # case -> last stored step the restatement is run to (all stored steps up to it are compared)
 RESTATED = {"turing_tiny": 1000, "turing_tiny_cl": 100, "turing_uniform": 100, "turing_blob": 100, "turing_50": 100,
             "brusselator": 100, "brusselator_nonunit": 100, "brusselator_300": 1, "fish": 10, "fish_300": 1,
-            "syn_turing_2d": 100, "syn_turing_3d": 50, "syn_brusselator_3d": 20}
+            "syn_turing_2d": 100, "syn_turing_3d": 50, "syn_brusselator_3d": 20, "syn_cascade3_3d": 40, "syn_cascade3_2d": 40}
 
 
 def build(case):

@@ -305,7 +305,7 @@ def test_awkward_grid_sizes_against_the_restated_oracle(dims):
 # model-specialised stage kernel (NVRTC build of the model's token records, csrc/device/rd_jit.cu)
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("case", ["turing_blob", "brusselator_nonunit", "fish_dirichlet", "transport_rate", "advection",
-                                  "syn_brusselator_3d", "syn_turing_3d", "turing_tiny_flux"])
+                                  "syn_brusselator_3d", "syn_turing_3d", "turing_tiny_flux", "syn_cascade3_3d", "syn_cascade3_2d"])
 def test_specialised_kernel_matches_reference(case, monkeypatch):
     """SB2_JIT=require: the stage kernel is compiled for the model's own kinetics at set-up (a failed build is an error);
     the trajectory must match the reference's golden fields like the interpreter kernel's does."""
