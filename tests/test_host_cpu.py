@@ -289,6 +289,21 @@ def test_specialised_build_of_an_empty_and_of_a_maximal_program():
     assert rc == 0, log
 
 
+@pytest.mark.skipif(not _nvrtc_present(), reason="libnvrtc.so.12 not installed")
+@pytest.mark.parametrize("ns,np_,w,minb,d3", [(1, 2, 8, 2, False), (3, 2, 4, 2, False), (4, 1, 4, 2, False), (3, 1, 8, 2, True),
+                                              (4, 1, 8, 2, True), (2, 2, 8, 2, True), (2, 4, 4, 2, True)])
+def test_specialised_build_for_every_kernel_shape(ns, np_, w, minb, d3):
+    """Species counts and strip / CTA shapes the library can ask for (2-D row marching and 3-D plane marching): the
+    cascade law (a division of two registers, a comparison, stoichiometry 2) builds for each."""
+    last = ns - 1
+    recs = [("PUSHV", 0, 0), ("MULC", 0, 0), ("ACCSUB1", 0, 0), ("ACCADD", last, 0),
+            ("PUSHV", 0, last), ("MULC", 0, 0), ("PUSHV", 1, last), ("ADDC", 1, 0), ("DIV", 1, 0),
+            ("PUSHV", 1, last), ("GTC", 1, 0), ("MUL", 1, 0), ("ACCSUB1", last, 0)]
+    rc, log = sb.specialize_dry_run(recs, ns=ns, np_=np_, w=w, depth=2, minb=minb, d3=d3)
+    assert rc == 0, log
+    assert "error" not in log.lower(), log
+
+
 def test_specialised_build_rejects_oversized_programs():
     rc, log = sb.specialize_dry_run([("ADDC", 0, 0)] * 385, ns=2, np_=2, w=8, depth=1)  # SB2_RD_MAX_TOKENS = 384
     assert rc == -1
