@@ -9,8 +9,8 @@ What is restated, in the reference's own evaluation order (all file:line relativ
                                                   reactant -= / product += accumulation)
   * calcDiffusion                                 calcPDE.cpp:453-562
   * updateSpecies (RK4 combine, k := 0)           spatialsimulator.cpp:1518-1544
-Neumann conditions with value 0 add +0.0 (calcPDE.cpp:994-1027) and are therefore omitted; models with advection
-(cipCSLR), membrane transport, Dirichlet or non-zero Neumann conditions raise NotImplementedError — the goldens made
+  * calcBoundary (Neumann flux, Dirichlet value)  calcPDE.cpp:871-1034, incl. the flux carried in k0 between steps
+Models with advection (cipCSLR) or membrane transport raise NotImplementedError — the goldens made
 by the reference itself (oracle/_ref) cover those.
 
 Pinned: tests/test_oracle_cpu.py checks this restatement BIT FOR BIT against the fields the unmodified reference
@@ -107,12 +107,14 @@ def eval_stream(toks, operand, consts, shape):
 
 
 class Species(object):
-    def __init__(self, name, u, domain, btype, D):
+    def __init__(self, name, u, domain, btype, D, bc=None):
         self.name, self.u = name, np.array(u, dtype=np.float64)
         self.domain = np.asarray(domain, dtype=bool)       # isDomain == 1 of the species' compartment
         self.btype = np.asarray(btype, dtype=np.uint8)     # bits 1..6 = isBofXp, Xm, Yp, Ym, Zp, Zm
         self.D = D                                         # per axis: float or None (diffCInfo[a] == 0)
         self.k = [np.zeros_like(self.u) for _ in range(4)]
+        # boundaryInfo: None, or {"Xmax": (kind, value), ...} with kind "neumann" / "dirichlet" / other (ignored)
+        self.bc = bc
 
 
 class Reaction(object):
@@ -165,13 +167,63 @@ class RDOracle(object):
                 for n in self.order:  # species order, spatialsimulator.cpp:1464-1478
                     s = self.sp[n]
                     self._diffusion(s, w[n], m)
-            for n in self.order:  # updateSpecies, spatialsimulator.cpp:1535-1536
+                    self._boundary(s, m)
+            for n in self.order:  # updateSpecies, spatialsimulator.cpp:1535-1542
                 s = self.sp[n]
                 inc = dt * (s.k[0] + 2.0 * s.k[1] + 2.0 * s.k[2] + s.k[3]) / 6.0
                 s.u[s.domain] += inc[s.domain]
                 for m in range(4):
                     s.k[m][s.domain] = 0.0
+                # calcBoundary(m = 0) after the k's were zeroed: a non-zero flux is parked in k0 and carried into
+                # the next step, whose stage 0 adds it a second time (spatialsimulator.cpp:1540-1542)
+                self._boundary(s, 0)
         return t + dt
+
+    def _boundary(self, s, m):
+        """calcBoundary, calcPDE.cpp:871-1034, on compact coordinates.  The reference visits every even point c and
+        tests its +/-1 neighbours p (target) and +/-2 neighbours pp: p in the domain, pp not (or off the array / on a
+        wrapped odd row, which no volume domain contains) -> Neumann: delta[m][p] += -2.0*(-bc)/delta_a (:994), Dirichlet:
+        value[p] = bc (:995).  Quirks kept: the Xm test is gated by desc.Y.mOutside (:997: skipped for c on row Y = 0 of
+        plane Z = 0); coordinateDesc::set stores Z.p = xp and Z.m = xm (mystruct.h:186-187), so the Z tests hit the X
+        neighbour of c and look at c's Z+-2 point; Dirichlet-Zm writes value[Z.mm] (:1028).  A target receives at most one
+        contribution per side; their order follows the visiting order of the c's (Z, Y, X ascending; Xp, Xm, Yp, Ym, Zp,
+        Zm at each c): Ymax (c = p - row), Xmax and Zmax (c = p - 1), Xmin and Zmin (c = p + 1), Ymin (c = p + row)."""
+        if not s.bc:
+            return
+        dom = s.domain
+        nzc, nyc, nxc = dom.shape
+
+        def shifted(di, dj, dk):
+            """dom at (i + di, j + dj, k + dk), False off the grid"""
+            out = np.zeros_like(dom)
+            src = [slice(max(0, d), n + min(0, d)) for d, n in ((dk, nzc), (dj, nyc), (di, nxc))]
+            dst = [slice(max(0, -d), n + min(0, -d)) for d, n in ((dk, nzc), (dj, nyc), (di, nxc))]
+            out[tuple(dst)] = dom[tuple(src)]
+            return out
+
+        K, J, I = np.indices(dom.shape)
+        plan = []  # (side, target mask, axis delta)
+        if self.dimension >= 2:
+            plan.append(("Ymax", dom & (J >= 1) & ~shifted(0, 1, 0), self.delta[1]))
+        plan.append(("Xmax", dom & (I >= 1) & ~shifted(1, 0, 0), self.delta[0]))
+        if self.dimension >= 3:
+            plan.append(("Zmax", dom & (I >= 1) & ~shifted(-1, 0, 2), self.delta[2]))
+        plan.append(("Xmin", dom & (I <= nxc - 2) & ~shifted(-1, 0, 0) & ~((K == 0) & (J == 0)), self.delta[0]))
+        if self.dimension >= 3:
+            plan.append(("Zmin", dom & (I <= nxc - 2) & ~shifted(1, 0, -2), self.delta[2]))
+        if self.dimension >= 2:
+            plan.append(("Ymin", dom & (J <= nyc - 2) & ~shifted(0, -1, 0), self.delta[1]))
+        for side, mask, dl in plan:
+            kind, value = s.bc.get(side, (None, 0.0))
+            if kind == "neumann":
+                s.k[m][mask] += -2.0 * (-value) / dl
+            elif kind == "dirichlet":
+                if side == "Zmin":  # value[Z.mm]: the cell two planes below c = p + 1; off the array for k < 2
+                    kk, jj, ii = np.nonzero(mask)
+                    keep = kk - 2 >= 0
+                    s.u[kk[keep] - 2, jj[keep], ii[keep] + 1] = value
+                else:
+                    s.u[mask] = value
 
     def _diffusion(self, s, w, m):
         """calcPDE.cpp:484-559: Xp, Xm, Yp, Ym, Zp, Zm, each skipped where the boundary-type flag is set."""
@@ -195,7 +247,7 @@ class RDOracle(object):
 def model_parameters(xml_text):
     """Diffusion coefficients (species → [Dx, Dy, Dz] parameter ids), uniform values, compartments."""
     root = ET.fromstring(xml_text)
-    values, diff, features = {}, {}, set()
+    values, diff, features, bcs = {}, {}, set(), {}
     for p in root.iter(CORE + "parameter"):
         pid = p.get("id")
         if p.get("value") is not None:
@@ -221,13 +273,13 @@ def model_parameters(xml_text):
         bc = p.find(SPATIAL + "boundaryCondition")
         if bc is not None:
             kind = (bc.get(SPATIAL + "type") or "").lower()
-            if "dirichlet" in kind or kind == "value":
-                features.add("dirichlet")
-            elif values.get(pid, 0.0) != 0.0:
-                features.add("neumann")
+            var = bc.get(SPATIAL + "variable")
+            side = bc.get(SPATIAL + "coordinateBoundary")
+            kind = "dirichlet" if kind in ("dirichlet", "value") else "neumann" if kind in ("neumann", "flux") else kind
+            bcs.setdefault(var, {})[side] = (kind, pid)
     for c in root.iter(CORE + "compartment"):
         values[c.get("id")] = float(c.get("size")) if c.get("size") is not None else 1.0
-    return values, diff, features
+    return values, diff, features, bcs
 
 
 def from_simulator(sim, xml_text, dims):
@@ -238,7 +290,7 @@ def from_simulator(sim, xml_text, dims):
     def even(a):
         return np.ascontiguousarray(a.reshape(2 * nz - 1, 2 * ny - 1, 2 * nx - 1)[::2, ::2, ::2])
 
-    values, diff, features = model_parameters(xml_text)
+    values, diff, features, bcs = model_parameters(xml_text)
     summary = sim.getSetupText("summary").splitlines()
     head = summary[0].split()
     delta = [float(head[7]), float(head[8]), float(head[9])]
@@ -265,7 +317,14 @@ def from_simulator(sim, xml_text, dims):
     species = []
     for name, comp in var_geo.items():
         D = [uniform.get(pid) if pid is not None else None for pid in diff.get(name, [None, None, None])]
-        species.append(Species(name, even(sim.getVariable(name)), masks[comp], btypes[comp], D))
+        bc = None
+        if name in bcs:
+            bc = {}
+            for side, (kind, pid) in bcs[name].items():
+                if pid not in uniform:
+                    raise NotImplementedError("field-valued boundary condition %s" % pid)
+                bc[side] = (kind, uniform[pid])
+        species.append(Species(name, even(sim.getVariable(name)), masks[comp], btypes[comp], D, bc))
     reactions = []
     i = 0
     while True:

@@ -55,9 +55,12 @@ def _transport_params(species, D, axes, bc_values=None, bc_type="Neumann"):
         for side in ("min", "max"):
             b = "%s%s" % (a.upper(), side)
             v = 0.0 if not bc_values else bc_values.get((species, b), 0.0)
+            kind = bc_type
+            if isinstance(v, tuple):  # (value, "Dirichlet") overrides the kind of one side
+                v, kind = v
             out.append(_param("%s_BC_%s" % (species, b), v,
                               '<spatial:boundaryCondition spatial:variable="%s" spatial:type="%s" '
-                              'spatial:coordinateBoundary="%s"/>' % (species, bc_type, b)))
+                              'spatial:coordinateBoundary="%s"/>' % (species, kind, b)))
     return out
 
 
@@ -184,4 +187,15 @@ def cascade3(nx, ny, nz=None):
                          _apply("gt", _ci("Z"), _cn(0.05)))),
     ]
     return _document("synthetic_cascade3", axes, dims, species, params, assignments, rx)
+
+
+def turing_flux3d(nx, ny, nz):
+    """The 3-D Turing model with a non-zero Neumann flux on every side of species_1 and, for species_2, fluxes in x / y
+    and Dirichlet values on both z sides: the boundary pass of the reference in 3-D, including its Z-side quirks
+    (coordinateDesc stores the X neighbour in the Z slots, Dirichlet-Zmin writes two planes below).  dt 0.02."""
+    bc = {("species_1", "Xmin"): 0.3, ("species_1", "Xmax"): -0.1, ("species_1", "Ymin"): 0.2, ("species_1", "Ymax"): 0.05,
+          ("species_1", "Zmin"): 0.15, ("species_1", "Zmax"): -0.07,
+          ("species_2", "Xmin"): 0.02, ("species_2", "Ymax"): 0.04,
+          ("species_2", "Zmax"): (0.12, "Dirichlet"), ("species_2", "Zmin"): (0.09, "Dirichlet")}
+    return turing(nx, ny, nz, bc_values=bc)
 

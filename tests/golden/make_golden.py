@@ -70,6 +70,8 @@ CASES = {
     # three species: the 3- / 4-species kernel variants, stoichiometry 2, a division and a comparison in a law
     "syn_cascade3_3d": ("synthetic:cascade3:70:11:9", (70, 11, 9), 0.05, [1, 10, 40], {}, []),
     "syn_cascade3_2d": ("synthetic:cascade3:150:40", (150, 40, 1), 0.05, [1, 10, 40], {}, []),
+    # 3-D boundary pass: non-zero fluxes on all six sides, Dirichlet values on the z sides
+    "syn_turing_3d_flux": ("synthetic:turing_flux3d:18:14:10", (18, 14, 10), 0.02, [1, 2, 10, 40], {}, []),
 }
 
 
