@@ -46,7 +46,7 @@ int sb2_rd_pick_variant(int dim, int nx, int nspecies, int depth, Sb2RdVariant* 
   if ((dim != 2 && dim != 3) || nspecies < 1 || nspecies > 4) return -1;
   int id;
   if (dim == 3) {
-    // the z-marching kernel keeps four plane tiles of W + 2 rows in shared memory: 8 warps and 2 cells per thread leave
+    // the z-marching kernel keeps three plane tiles of W + 2 rows in shared memory: 8 warps and 2 cells per thread leave
     // room for three CTAs per SM with two species
     id = nspecies <= 2 ? 2 : 6;
   } else if (nspecies <= 2) id = (depth <= 4 && nx >= 192) ? 1 : 2;  // (measured at 8192^2: variant 1 beats 0 and 5)

@@ -35,7 +35,7 @@
 //   * The last stage fuses the RK4 combine: the k0 / k1 rows of a warp's row arrive through a second per-warp TMA slot
 //     requested one batch ahead; u and k2 of its own cells are re-read with plain 16-byte loads that hit L2, because the
 //     bulk copies that staged them one batch earlier carry an L2::evict_last hint.
-//   * 3-D grids march along z instead, with a ring of four plane tiles (rd_stage3_body, described there).
+//   * 3-D grids march along z instead, with a ring of three plane tiles (rd_stage3_body, described there).
 //   * A model-specialised build (rd_jit.cu, SB2_RD_PROGRAM) replaces the interpreter loop by the straight-line expansion
 //     of the model's token records; everything else is the same code.
 //
