@@ -10,7 +10,8 @@ What is restated, in the reference's own evaluation order (all file:line relativ
   * calcDiffusion                                 calcPDE.cpp:453-562
   * updateSpecies (RK4 combine, k := 0)           spatialsimulator.cpp:1518-1544
   * calcBoundary (Neumann flux, Dirichlet value)  calcPDE.cpp:871-1034, incl. the flux carried in k0 between steps
-Models with advection (cipCSLR) or membrane transport raise NotImplementedError — the goldens made
+  * cipCSLR (CIP-CSLR advection, uniform velocity)  calcPDE.cpp:564-869
+Models with membrane transport raise NotImplementedError — the goldens made
 by the reference itself (oracle/_ref) cover those.
 
 Pinned: tests/test_oracle_cpu.py checks this restatement BIT FOR BIT against the fields the unmodified reference
@@ -107,8 +108,17 @@ def eval_stream(toks, operand, consts, shape):
 
 
 class Species(object):
-    def __init__(self, name, u, domain, btype, D, bc=None):
+    def __init__(self, name, u, domain, btype, D, bc=None, adv=None, full=None, dom_d=None, btype_d=None):
         self.name, self.u = name, np.array(u, dtype=np.float64)
+        # advected species keep the reference's whole doubled grid (cell values at the even points, CIP face values at
+        # the odd ones); u is then a view of its even points
+        self.adv = adv          # per axis: uniform velocity or None (adCInfo[a] == 0); None altogether: not advected
+        self.full = None
+        if adv is not None and any(a is not None for a in adv):
+            self.full = np.array(full, dtype=np.float64)
+            self.u = self.full[::2, ::2, ::2]
+            self.dom_d = np.asarray(dom_d).reshape(-1) == 1          # isDomain == 1 on the doubled grid
+            self.btype_d = np.asarray(btype_d, dtype=np.uint8).reshape(-1)
         self.domain = np.asarray(domain, dtype=bool)       # isDomain == 1 of the species' compartment
         self.btype = np.asarray(btype, dtype=np.uint8)     # bits 1..6 = isBofXp, Xm, Yp, Ym, Zp, Zm
         self.D = D                                         # per axis: float or None (diffCInfo[a] == 0)
@@ -168,6 +178,9 @@ class RDOracle(object):
                     s = self.sp[n]
                     self._diffusion(s, w[n], m)
                     self._boundary(s, m)
+            for n in self.order:  # advection after the RK stages, before the update (spatialsimulator.cpp:1482-1491)
+                if self.sp[n].full is not None:
+                    self._cip(self.sp[n], dt)
             for n in self.order:  # updateSpecies, spatialsimulator.cpp:1535-1542
                 s = self.sp[n]
                 inc = dt * (s.k[0] + 2.0 * s.k[1] + 2.0 * s.k[2] + s.k[3]) / 6.0
@@ -178,6 +191,84 @@ class RDOracle(object):
                 # the next step, whose stage 0 adds it a second time (spatialsimulator.cpp:1540-1542)
                 self._boundary(s, 0)
         return t + dt
+
+    def _cip(self, s, dt):
+        """cipCSLR, calcPDE.cpp:564-869: CIP-CSLR rational-function advection on the doubled grid, one dimension-split
+        pass per axis; every pass reads the state before it (val) and writes val_delta, which is then added to the whole
+        grid together with the cross-axis face update (val_delta[cell + 2] + val_delta[cell]) / 2.  Uniform velocities."""
+        import math
+        full = s.full
+        nzd, nyd, nxd = full.shape
+        val = full.reshape(-1)
+        n_pts = val.size
+        strides, limits = (1, nxd, nxd * nyd), (nxd, nyd, nzd)
+        idx = np.flatnonzero(s.dom_d)  # domainIndex: the even points of the species' domain
+        coords = (idx % nxd, (idx // nxd) % nyd, idx // (nxd * nyd))
+        eps = np.finfo(np.float64).eps  # DBL_EPSILON
+        bt = s.btype_d[idx]
+        # pow(x, 2): gcc -O2 (the oracle/_ref build, like the reference's own) expands it to x * x
+
+        def in_domain(a, off):
+            c = coords[a] + off
+            ok = (c >= 0) & (c < limits[a])
+            r = np.zeros(idx.shape, dtype=bool)
+            r[ok] = s.dom_d[idx[ok] + off * strides[a]]
+            return r
+
+        for a in range(self.dimension):
+            vd = np.zeros(n_pts)
+            u = s.adv[a]
+            if u is not None:
+                st, dl = strides[a], self.delta[a]
+                d4p, d2p, d4m, d2m = in_domain(a, 4), in_domain(a, 2), in_domain(a, -4), in_domain(a, -2)
+                p1, p2, p3 = idx + st, idx + 2 * st, idx + 3 * st
+                m1, m2, m3 = idx - st, idx - 2 * st, idx - 3 * st
+                p3 = np.where(d4p, p3, np.where(d2p, p2, idx))  # :596-603 (uses the uncollapsed +2 index)
+                m3 = np.where(d4m, m3, np.where(d2m, m2, idx))
+                p1, p2 = np.where(d2p, p1, idx), np.where(d2p, p2, idx)  # :604-611
+                m1, m2 = np.where(d2m, m1, idx), np.where(d2m, m2, idx)
+                D = -math.copysign(1.0, u) * dl
+                xi = u * dt
+                pw_mxi, pw_xi = (-xi) * (-xi), xi * xi
+                v0, vp1, vp2, vp3 = val[idx], val[p1], val[p2], val[p3]
+                vm1, vm2, vm3 = val[m1], val[m2], val[m3]
+                g_in, g_out = np.zeros(idx.shape), np.zeros(idx.shape)
+                free_p = ((bt >> (1 + 2 * a)) & 1) == 0  # !isBof{X,Y,Z}p
+                free_m = ((bt >> (2 + 2 * a)) & 1) == 0
+                if u >= 0:  # :614-626 flux out through the plus face
+                    beta = ((np.abs(vp1 - v0) + eps) / (np.abs(v0 - vm1) + eps) - 1.0) / D
+                    b = ((1.0 + beta * D) * v0 - vp1) / D
+                else:       # :627-638 flux in through the plus face
+                    beta = ((np.abs(vp1 - vp2) + eps) / (np.abs(vp2 - vp3) + eps) - 1.0) / D
+                    b = ((1.0 + beta * D) * vp2 - vp1) / D
+                den = 1.0 + beta * (-xi)
+                face = (vp1 + 2 * b * (-xi) + beta * b * pw_mxi) / (den * den) - vp1
+                flux = (-vp1 * xi + b * pw_xi) / (-1.0 + beta * xi)
+                vd[p1[free_p]] = face[free_p]
+                if u >= 0:
+                    g_out[free_p] = flux[free_p]
+                else:
+                    g_in[free_p] = -flux[free_p]
+                if u >= 0:  # :639-643 flux in through the minus face
+                    beta2 = ((np.abs(vm1 - vm2) + eps) / (np.abs(vm2 - vm3) + eps) - 1.0) / D
+                    b2 = ((1.0 + beta2 * D) * vm2 - vm1) / D
+                else:       # :644-648 flux out through the minus face
+                    beta2 = ((np.abs(vm1 - v0) + eps) / (np.abs(v0 - vp1) + eps) - 1.0) / D
+                    b2 = ((1.0 + beta2 * D) * v0 - vm1) / D
+                flux2 = (-vm1 * xi + b2 * pw_xi) / (-1.0 + beta2 * xi)
+                if u >= 0:
+                    g_in[free_m] = flux2[free_m]
+                else:
+                    g_out[free_m] = -flux2[free_m]
+                vd[idx] = (g_in - g_out) / dl  # :650 (after the face value: a collapsed face index is the cell itself)
+            # :653-673: faces of the other axes move with the mean of the two cells they separate, then val += val_delta
+            for b_ax in range(self.dimension):
+                if b_ax == a:
+                    continue
+                ok = ((bt >> (1 + 2 * b_ax)) & 1) == 0
+                c = idx[ok]
+                val[c + strides[b_ax]] += (vd[c + 2 * strides[b_ax]] + vd[c]) / 2.0
+            val += vd
 
     def _boundary(self, s, m):
         """calcBoundary, calcPDE.cpp:871-1034, on compact coordinates.  The reference visits every even point c and
@@ -247,7 +338,7 @@ class RDOracle(object):
 def model_parameters(xml_text):
     """Diffusion coefficients (species → [Dx, Dy, Dz] parameter ids), uniform values, compartments."""
     root = ET.fromstring(xml_text)
-    values, diff, features, bcs = {}, {}, set(), {}
+    values, diff, features, bcs, advs = {}, {}, set(), {}, {}
     for p in root.iter(CORE + "parameter"):
         pid = p.get("id")
         if p.get("value") is not None:
@@ -268,8 +359,15 @@ def model_parameters(xml_text):
                 for a in range(3):
                     slots[a] = pid
             del kind
-        if p.find(SPATIAL + "advectionCoefficient") is not None:
-            features.add("advection")
+        ac = p.find(SPATIAL + "advectionCoefficient")
+        if ac is not None:
+            var = ac.get(SPATIAL + "variable")
+            ref = ac.get(SPATIAL + "coordinate")
+            axis = {"cartesianX": 0, "cartesianY": 1, "cartesianZ": 2}.get(ref)
+            if axis is None:
+                features.add("advection coefficient without a coordinate")
+            else:
+                advs.setdefault(var, [None, None, None])[axis] = pid
         bc = p.find(SPATIAL + "boundaryCondition")
         if bc is not None:
             kind = (bc.get(SPATIAL + "type") or "").lower()
@@ -279,7 +377,7 @@ def model_parameters(xml_text):
             bcs.setdefault(var, {})[side] = (kind, pid)
     for c in root.iter(CORE + "compartment"):
         values[c.get("id")] = float(c.get("size")) if c.get("size") is not None else 1.0
-    return values, diff, features, bcs
+    return values, diff, features, bcs, advs
 
 
 def from_simulator(sim, xml_text, dims):
@@ -290,7 +388,7 @@ def from_simulator(sim, xml_text, dims):
     def even(a):
         return np.ascontiguousarray(a.reshape(2 * nz - 1, 2 * ny - 1, 2 * nx - 1)[::2, ::2, ::2])
 
-    values, diff, features, bcs = model_parameters(xml_text)
+    values, diff, features, bcs, advs = model_parameters(xml_text)
     summary = sim.getSetupText("summary").splitlines()
     head = summary[0].split()
     delta = [float(head[7]), float(head[8]), float(head[9])]
@@ -324,7 +422,18 @@ def from_simulator(sim, xml_text, dims):
                 if pid not in uniform:
                     raise NotImplementedError("field-valued boundary condition %s" % pid)
                 bc[side] = (kind, uniform[pid])
-        species.append(Species(name, even(sim.getVariable(name)), masks[comp], btypes[comp], D, bc))
+        adv = None
+        extra = {}
+        if name in advs:
+            adv = []
+            for pid in advs[name]:
+                if pid is not None and pid not in uniform:
+                    raise NotImplementedError("field-valued advection velocity %s" % pid)
+                adv.append(uniform[pid] if pid is not None else None)
+            bt = sim.getBoundaryType(comp)
+            extra = {"full": np.asarray(sim.getVariable(name)).reshape(2 * nz - 1, 2 * ny - 1, 2 * nx - 1),
+                     "dom_d": sim.getGeometry(comp), "btype_d": sum((bt[:, k].astype(np.uint8) << (k + 1)) for k in range(6))}
+        species.append(Species(name, even(sim.getVariable(name)), masks[comp], btypes[comp], D, bc, adv, **extra))
     reactions = []
     i = 0
     while True:

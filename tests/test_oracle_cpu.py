@@ -1,6 +1,6 @@
 """CPU tests of the checkers themselves (no GPU).
 
-  * oracle/rd_oracle.py — the numpy restatement of the reference's reaction-diffusion step — against the fields the
+  * oracle/rd_oracle.py — the numpy restatement of the reference's reaction-diffusion-advection step — against the fields the
     UNMODIFIED reference produced (tests/golden/*.npz): bit for bit, every stored step.
   * oracle/_ref/ref_driver — the reference's own sources compiled in place — re-run here on a small model must
     reproduce the committed golden exactly (skipped where the binary has not been built).
@@ -25,7 +25,9 @@ RESTATED = {"turing_tiny": 1000, "turing_tiny_cl": 100, "turing_uniform": 100, "
             "brusselator": 100, "brusselator_nonunit": 100, "brusselator_300": 1, "fish": 10, "fish_300": 1,
             "syn_turing_2d": 100, "syn_turing_3d": 50, "syn_brusselator_3d": 20, "syn_cascade3_3d": 40, "syn_cascade3_2d": 40,
             # calcBoundary restated too: non-zero Neumann flux (carried in k0 between steps) and a Dirichlet side
-            "turing_tiny_flux": 100, "fish_dirichlet": 10, "syn_turing_3d_flux": 40}
+            "turing_tiny_flux": 100, "fish_dirichlet": 10, "syn_turing_3d_flux": 40,
+            # cipCSLR restated on the doubled grid (cell + face values)
+            "advection": 100}
 
 
 def build(case):
@@ -54,7 +56,7 @@ def test_restatement_matches_reference_bit_for_bit(case):
     assert done > 0
 
 
-@pytest.mark.parametrize("case", ["advection", "transport"])
+@pytest.mark.parametrize("case", ["transport", "transport_rate"])
 def test_restatement_refuses_what_it_does_not_cover(case):
     with pytest.raises(NotImplementedError):
         build(case)
