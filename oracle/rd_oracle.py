@@ -11,8 +11,8 @@ What is restated, in the reference's own evaluation order (all file:line relativ
   * updateSpecies (RK4 combine, k := 0)           spatialsimulator.cpp:1518-1544
   * calcBoundary (Neumann flux, Dirichlet value)  calcPDE.cpp:871-1034, incl. the flux carried in k0 between steps
   * cipCSLR (CIP-CSLR advection, uniform velocity)  calcPDE.cpp:564-869
-Models with membrane transport raise NotImplementedError — the goldens made
-by the reference itself (oracle/_ref) cover those.
+  * calcMemTransport (volume species on either side of a membrane, incl. the rpStack[1] rate quirk)  calcPDE.cpp:1036-1482
+Membrane species, field-valued velocities / boundary values raise NotImplementedError.
 
 Pinned: tests/test_oracle_cpu.py checks this restatement BIT FOR BIT against the fields the unmodified reference
 produced (tests/golden/*.npz) for the Turing, Brusselator, fish and synthetic 2-D / 3-D models.
@@ -128,8 +128,21 @@ class Species(object):
 
 
 class Reaction(object):
-    def __init__(self, toks, refs, n_reactants, domain, is_reaction=True):
+    def __init__(self, toks, refs, n_reactants, domain, is_reaction=True, membrane=None):
         self.toks, self.refs, self.n_reactants, self.domain, self.is_reaction = toks, refs, n_reactants, domain, is_reaction
+        self.membrane = membrane  # Membrane of a membrane-transport reaction (calcMemTransport), else None
+
+
+class Membrane(object):
+    """What calcMemTransport reads of a membrane compartment, all on the reference's doubled grid (flat indices)."""
+
+    def __init__(self, points, is_domain, btype, normals, vol_domains, shape_d):
+        self.points = points            # domainIndex of the membrane, in the reference's order
+        self.is_domain = is_domain      # isDomain of the membrane (1 membrane point, 2 pseudo membrane)
+        self.btype = btype              # per point: bits 1..6 = isBofXp, Xm, Yp, Ym, Zp, Zm
+        self.normals = normals          # flat index -> (nx, ny, nz)
+        self.vol_domains = vol_domains  # species name -> isDomain of its volume compartment (flat, doubled grid)
+        self.shape_d = shape_d          # (Zindex, Yindex, Xindex)
 
 
 class RDOracle(object):
@@ -162,6 +175,9 @@ class RDOracle(object):
                     raise NotImplementedError("field operand %s" % name)
 
                 for r in self.rx:  # document order, spatialsimulator.cpp:1374-1390
+                    if r.membrane is not None:
+                        self._mem_transport(r, m, dt)
+                        continue
                     rate = eval_stream(r.toks, operand, self.consts, self.shape)
                     for k, (name, stoich, is_var) in enumerate(r.refs):
                         if not is_var or name not in self.sp:
@@ -191,6 +207,111 @@ class RDOracle(object):
                 # the next step, whose stage 0 adds it a second time (spatialsimulator.cpp:1540-1542)
                 self._boundary(s, 0)
         return t + dt
+
+    def _mem_transport(self, r, m, dt):
+        """calcMemTransport, calcPDE.cpp:1036-1482, for volume species on either side of a membrane.  Per membrane point
+        (not on the frame, isDomain == 1): the rate law is evaluated with every volume operand taken from the adjacent cell
+        of whichever side lies in that species' domain, extrapolated 1.5*v(+-1) - 0.5*v(+-3) when the next cell is in the
+        domain too (x, then y, then z: later axes overwrite earlier ones, :1107-1213); then reactants lose and products gain
+        fabs(n_a) * stoich * rate / delta_a in their cells next to the point, along the axis of the point's boundary type
+        (:1394-1479).  Kept as in the reference: the stack outlives the points, and after the evaluation
+        `if (st_index > 1) st_index--` (:1392-1393) makes the rate rpStack[1] for a well-formed law (the stale right operand
+        of the last binary operator), not the result in rpStack[0]."""
+        import math
+        mem = r.membrane
+        nzd, nyd, nxd = mem.shape_d
+        n_pts = nxd * nyd * nzd
+        rk = (0.0, 0.5, 0.5, 1.0)
+        stack = [0.0] * 64
+
+        def cell(flat):  # even point -> compact index
+            z, rem = divmod(flat, nxd * nyd)
+            y, x = divmod(rem, nxd)
+            return (z // 2, y // 2, x // 2)
+
+        def stage_value(sp, flat):  # variable (+ rk[m]*dt*delta[m-1]) at an even point
+            c = cell(flat)
+            if m == 0:
+                return float(sp.u[c])
+            return float(sp.u[c]) + rk[m] * dt * float(sp.k[m - 1][c])
+
+        for index in mem.points:
+            z, rem = divmod(index, nxd * nyd)
+            y, x = divmod(rem, nxd)
+            on_frame = (x * y * z == 0 or x == nxd - 1 or y == nyd - 1 or z == nzd - 1) if self.dimension == 3 else \
+                       (x * y == 0 or x == nxd - 1 or y == nyd - 1)
+            if on_frame or mem.is_domain[index] != 1:
+                continue
+            strides = (1, nxd, nxd * nyd)
+            st = 0
+            for t in r.toks:
+                if t[0] == "V":
+                    name, has_delta = t[1], t[2]
+                    if name not in self.sp or not has_delta:
+                        raise NotImplementedError("membrane-transport operand %s" % name)
+                    sp = self.sp[name]
+                    dom = mem.vol_domains[name]
+                    for a in range(self.dimension):  # x, y (, z): a later axis overwrites an earlier one
+                        p1, p3, m1, m3 = index + strides[a], index + 3 * strides[a], index - strides[a], index - 3 * strides[a]
+                        if dom[p1] == 1:
+                            if p3 < n_pts and dom[p3] == 1:
+                                stack[st] = 1.5 * stage_value(sp, p1) - 0.5 * stage_value(sp, p3)
+                            else:
+                                stack[st] = stage_value(sp, p1)
+                        elif dom[m1] == 1:
+                            if m3 < n_pts and dom[m3] == 1:
+                                stack[st] = 1.5 * stage_value(sp, m1) - 0.5 * stage_value(sp, m3)
+                            else:
+                                stack[st] = stage_value(sp, m1)
+                    st += 1
+                elif t[0] == "C":
+                    stack[st] = self.consts.get(t[1], t[2]) if t[1] != "#" else t[2]
+                    st += 1
+                else:
+                    op = t[1]
+                    st -= 1
+                    a_, b_ = stack[st - 1], stack[st]
+                    if op == AST_PLUS:
+                        stack[st - 1] = a_ + b_
+                    elif op == AST_MINUS:
+                        stack[st - 1] = a_ - b_
+                    elif op == AST_TIMES:
+                        stack[st - 1] = a_ * b_
+                    elif op == AST_DIVIDE:
+                        stack[st - 1] = a_ / b_ if b_ != 0.0 else math.copysign(math.inf, a_) * math.copysign(1.0, b_) if a_ != 0.0 else math.nan
+                    elif op in (AST_POWER, AST_FUNCTION_POWER):
+                        stack[st - 1] = math.pow(a_, b_)
+                    elif op in BINARY:
+                        stack[st - 1] = float(BINARY[op](np.float64(a_), np.float64(b_)))
+                    elif op in UNARY:
+                        stack[st] = float(UNARY[op](np.float64(b_)))
+                        st += 1
+                    # every other operator only pops
+            if st > 1:
+                st -= 1
+            rate = stack[st]
+            bt = int(mem.btype[index])
+            if bt & 0x06:
+                a = 0
+            elif bt & 0x18:
+                a = 1
+            elif self.dimension == 3 and bt & 0x60:
+                a = 2
+            else:
+                continue
+            n_a = abs(mem.normals[index][a])
+            for j, (name, stoich, is_var) in enumerate(r.refs):
+                if not is_var or name not in self.sp:
+                    continue
+                sp = self.sp[name]
+                dom = mem.vol_domains[name]
+                amount = n_a * stoich * rate / self.delta[a]
+                for nb in (index + strides[a], index - strides[a]):  # plus side first, then minus side
+                    if dom[nb] == 1:
+                        if j < r.n_reactants:
+                            sp.k[m][cell(nb)] -= amount
+                        else:
+                            sp.k[m][cell(nb)] += amount
 
     def _cip(self, s, dt):
         """cipCSLR, calcPDE.cpp:564-869: CIP-CSLR rational-function advection on the doubled grid, one dimension-split
@@ -401,10 +522,14 @@ def from_simulator(sim, xml_text, dims):
                 var_geo[p[1]] = p[9]
             if p[3] == "1" and "value" in p:
                 uniform[p[1]] = float(p[p.index("value") + 1])
+    transport_rxn = set()
+    mem_adjacent = {}
     for line in summary:
         p = line.split()
         if p[0] == "rxn" and p[4] == "1":
-            features.add("membrane transport")
+            transport_rxn.add(int(p[1]))
+        if p[0] == "geo" and p[5] == "0":  # geo <compartment> domainType <dt> isVol 0 ... adjacent <a> <b>
+            mem_adjacent[p[1]] = (p[p.index("adjacent") + 1], p[p.index("adjacent") + 2])
     if features:
         raise NotImplementedError("not restated here: " + ", ".join(sorted(features)))
     masks, btypes = {}, {}
@@ -451,7 +576,29 @@ def from_simulator(sim, xml_text, dims):
             if name in var_geo:
                 dom = masks[var_geo[name]]
                 break
-        if dom is not None:
+        if i in transport_rxn:
+            # the membrane between the compartments of the first reactant and the first product (spatialsimulator.cpp:1394-1438)
+            names = [name for name, _, _ in refs]
+            if n_reactants < 1 or len(names) <= n_reactants or names[0] not in var_geo or names[n_reactants] not in var_geo:
+                raise NotImplementedError("membrane transport between species without a volume geometry")
+            pair = {var_geo[names[0]], var_geo[names[n_reactants]]}
+            comp = [c for c, adj in mem_adjacent.items() if set(adj) == pair]
+            if not comp:
+                raise NotImplementedError("no membrane between %s" % sorted(pair))
+            comp = comp[0]
+            bt = sim.getBoundaryType(comp)
+            normals = {}
+            for line in sim.getSetupText("normals/" + comp).splitlines():
+                q = line.split()
+                normals[int(q[0])] = (float(q[1]), float(q[2]), float(q[3]))
+            points = [int(v) for v in sim.getSetupText("memindex/" + comp).split()]
+            # (copies: the simulator hands out borrowed pointers into its own arrays)
+            vol_domains = {n: np.array(sim.getGeometry(var_geo[n])).reshape(-1) for n in names if n in var_geo}
+            mem = Membrane(points, np.array(sim.getGeometry(comp)).reshape(-1),
+                           sum((bt[:, k].astype(np.uint8) << (k + 1)) for k in range(6)).astype(np.uint8), normals, vol_domains,
+                           (2 * nz - 1, 2 * ny - 1, 2 * nx - 1))
+            reactions.append(Reaction(parse_stream(text), refs, n_reactants, None, membrane=mem))
+        elif dom is not None:
             reactions.append(Reaction(parse_stream(text), refs, n_reactants, dom))
         i += 1
     return RDOracle(species, reactions, uniform, delta, dimension)
