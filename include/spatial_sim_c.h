@@ -73,6 +73,7 @@ SSB_API int ssb_set_variable_compact(ssb_sim* s, const char* id, const double* i
 SSB_API double ssb_get_stable_time_step(ssb_sim* s, double dt);   /* checkStability.cpp reduction */
 SSB_API long ssb_get_num_domain_cells(ssb_sim* s);
 SSB_API int ssb_get_num_staged_species(ssb_sim* s);
+SSB_API int ssb_get_time_slot(ssb_sim* s);                      /* constants-table slot of the `time` symbol, -1: the model does not use it */
 SSB_API long ssb_get_device_launch_count(ssb_sim* s);
 SSB_API void* ssb_get_device_handle(ssb_sim* s);                  /* sb2_sim* of include/spatial_b200.h */
 /* after stepping the device handle directly (split-phase API of the slab-sharded path): host mirrors are out of date */

@@ -131,6 +131,7 @@ def _proto(lib):
         "ssb_get_stable_time_step": (cd, [vp, cd]),
         "ssb_get_num_domain_cells": (C.c_long, [vp]),
         "ssb_get_num_staged_species": (ci, [vp]),
+        "ssb_get_time_slot": (ci, [vp]),
         "ssb_get_device_launch_count": (C.c_long, [vp]),
         "ssb_get_device_handle": (vp, [vp]),
         "ssb_device_state_changed": (None, [vp]),
@@ -355,6 +356,10 @@ class SpatialSimulator(object):
 
     def getNumStagedSpecies(self):
         return self._lib.ssb_get_num_staged_species(self._h)
+
+    def getTimeSlot(self):
+        """Constants-table slot of the model's `time` symbol (what sb2_begin_step takes), -1 when unused."""
+        return self._lib.ssb_get_time_slot(self._h)
 
     def getDeviceLaunchCount(self):
         return self._lib.ssb_get_device_launch_count(self._h)

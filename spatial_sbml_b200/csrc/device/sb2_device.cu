@@ -923,6 +923,9 @@ int sb2_begin_step(sb2_sim* sim, double t_arg, double dt, int time_slot) {
   // which reproduces the reference's order of additions including the flux carried in k0.
   sim->carry_k0 = sb2_neumann_active(sim->blists, (int)sim->species.size(), sim->consts);
   sim->fuse_combine = !sim->any_adv && !sim->carry_k0;
+  if (sim->g.own_hi > sim->g.own_lo && (sim->carry_k0 || sim->blists.n_dirichlet > 0))
+    return fail(sim, SB2_ERR_STATE, "non-zero Neumann flux / Dirichlet conditions are not supported on a slab of a sharded grid yet "
+                                    "(their boundary pass is not split into edge and interior rows)");
   if (sim->carry_k0 && !sim->k0_carry_valid) {
     for (size_t s = 0; s < sim->species.size(); ++s)
       CK(cudaMemsetAsync(sim->species[s].k[0], 0, sizeof(double) * sim->nalloc, sim->stream));

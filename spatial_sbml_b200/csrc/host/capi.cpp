@@ -114,6 +114,7 @@ double ssb_get_stable_time_step(ssb_sim* s, double dt) {
 }
 long ssb_get_num_domain_cells(ssb_sim* s) { return s ? s->sim.getNumDomainCells() : 0; }
 int ssb_get_num_staged_species(ssb_sim* s) { return s ? s->sim.getNumStagedSpecies() : 0; }
+int ssb_get_time_slot(ssb_sim* s) { return s ? s->sim.getTimeSlot() : -1; }
 long ssb_get_device_launch_count(ssb_sim* s) { return s ? s->sim.getDeviceLaunchCount() : 0; }
 void ssb_device_state_changed(ssb_sim* s) { if (s) s->sim.deviceStateChanged(); }
 void* ssb_get_device_handle(ssb_sim* s) { return s ? s->sim.getDeviceHandle() : NULL; }

@@ -774,6 +774,7 @@ int SpatialSimulator::getVariableLength() const {
 int SpatialSimulator::getGeometryLength() const { return impl ? (int)impl->m.ndoubled() : 0; }
 long SpatialSimulator::getNumDomainCells() const { return impl ? impl->domainCells : 0; }
 int SpatialSimulator::getNumStagedSpecies() const { return impl ? (int)impl->staged.size() : 0; }
+int SpatialSimulator::getTimeSlot() const { return impl ? impl->timeSlot : -1; }
 long SpatialSimulator::getDeviceLaunchCount() const { return impl && impl->dev ? (long)sb2_launch_count(impl->dev) : 0; }
 
 namespace {

@@ -93,6 +93,7 @@ class __attribute__((visibility("default"))) SpatialSimulator {
   double getStableTimeStep(double dt);
   long getNumDomainCells() const;  // volume cells that carry at least one staged species
   int getNumStagedSpecies() const;
+  int getTimeSlot() const;  // constants-table slot of the `time` symbol (sb2_begin_step), -1: unused
   long getDeviceLaunchCount() const;
   // the caller stepped the device simulator itself (split-phase sb2_begin_step / sb2_stage / sb2_end_step of the
   // slab-sharded path): the host mirrors of the species fields are out of date

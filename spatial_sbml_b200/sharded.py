@@ -90,7 +90,7 @@ class ShardedSimulator(object):
                         self.unit, self.base = v.row_pitch, v.first_cell
             # view 0 / 5 name "current" / "other" at creation time; track which buffer is current
             self.cur = 0
-        self.time_slot_steps = 0
+        self.time_slot = self.sim.getTimeSlot()  # sim_time = stepIndex * dt reaches the kinetic laws through this constant
         self.halo_ready = None
 
     def _u(self, s, current):
@@ -117,8 +117,7 @@ class ShardedSimulator(object):
             self.sim.oneStep(step_index, dt)
             return
         lib, h = self.lib, self.h
-        # the model of the sharded benchmarks does not use `time`; pass no time slot
-        self._ck(lib.sb2_begin_step(h, float(step_index), float(dt), -1))
+        self._ck(lib.sb2_begin_step(h, float(step_index), float(dt), self.time_slot))
         fused = lib.sb2_combine_is_fused(h) == 1
         # Per stage: the two edge rows on their own stream (they need the neighbours' halo rows of the previous stage),
         # the interior rows on the compute stream (they need only this rank's rows), the halo exchange of the new edge

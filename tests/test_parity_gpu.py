@@ -29,17 +29,7 @@ def rel_linf(a, b):
     return np.abs(a - b).max() / scale
 
 
-# goldens generated (from the reference) after the round's GPU minutes were spent: the numpy oracle is pinned to them on
-# the CPU, the device has not been run against them yet, so a mismatch is reported as an expected failure, not hidden
-NOT_YET_RUN_ON_GPU = {"syn_turing_3d_flux": "3-D boundary pass with non-zero fluxes and Dirichlet z sides: not run on a GPU yet"}
-
-
-def _golden_params():
-    return [pytest.param(c, marks=pytest.mark.xfail(reason=NOT_YET_RUN_ON_GPU[c], strict=False)) if c in NOT_YET_RUN_ON_GPU else c
-            for c in golden_cases()]
-
-
-@pytest.mark.parametrize("case", _golden_params())
+@pytest.mark.parametrize("case", golden_cases())
 def test_fields_match_reference(case):
     import spatial_sbml_b200 as sb
     g = load_golden(case)
