@@ -221,29 +221,38 @@ class Harness(object):
             self.dist.all_reduce(t, op=op)
         return [float(v) for v in t]
 
-    def time_steps(self, shard, dt, first_step=0, sample_clocks=False):
+    def time_steps(self, shard, dt, first_step=0, sample_clocks=False, names=None):
         """W warm-up steps, then R timed regions of K steps each, every region bracketed by barrier + synchronize and
         timed with CUDA events on the launching stream; per region the MAX over ranks.  Returns (regions_ms_max_over_ranks,
         this rank's regions_ms, launches per region, next step index)."""
         torch = self.torch
         shard.run_steps(first_step, dt, self.W)
-        step = first_step + self.W
+        step0 = first_step + self.W
         mine, launches = [], 0
+        # Every region times the SAME K steps: the state after the warm-up is kept on the host and put back before each
+        # further region (outside the timed bracket).  The blob-initialised Turing model at dt 0.07 leaves the stable range of
+        # explicit RK4 after about 120 steps on a grid this large (the reference does too - the restated step is bit-identical),
+        # and non-finite values must not be what is timed.
+        snap = dict((nm, shard.sim.getVariableCompact(nm)) for nm in names) if (names and self.R > 1) else None
         # the sampler (NVML init, thread start) costs rank 0 a few ms: set it up BEFORE the first barrier, or the other
         # ranks' timed regions start early and then include waiting for rank 0's first halo rows
         self.clocks = None
         sampler = ClockSampler(self.local_rank) if (sample_clocks and self.rank == 0) else None
-        for _ in range(self.R):
+        for r in range(self.R):
+            if r > 0 and snap is not None:
+                for nm in names:
+                    shard.sim.setVariableCompact(nm, snap[nm])
             self.sync_all()
             l0 = shard.launch_count()
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
-            shard.run_steps(step, dt, self.K)
+            shard.run_steps(step0, dt, self.K)
             ev1.record()
             self.sync_all()
             mine.append(ev0.elapsed_time(ev1))
             launches = shard.launch_count() - l0
-            step += self.K
+        step = step0 + self.K
+        del snap
         if sampler:
             self.clocks = sampler.stop()
         worst = self.reduce(mine, self.dist.ReduceOp.MAX) if self.world > 1 else list(mine)
@@ -267,10 +276,10 @@ def workload(h, synthetic, ShardedSimulator, model_name, dim, n_per_gpu, scaling
         raise SystemExit("bench.py: the model-specialised stage kernel is not in use on %s (%s); refusing to report the "
                          "interpreter kernel's numbers as the benchmark" % (dims, shard.sim.getSpecializeInfo()))
     cells = shard.num_domain_cells()
-    worst, mine, launches, next_step = h.time_steps(shard, dt, sample_clocks=sample_clocks)
+    names = ["species_1", "species_2"] if model_name == "turing" else ["X", "Y"]
+    worst, mine, launches, next_step = h.time_steps(shard, dt, sample_clocks=sample_clocks, names=names)
     cells_total = h.reduce([float(cells)], h.dist.ReduceOp.SUM)[0] if world > 1 else float(cells)
     med = statistics.median(worst)
-    names = ["species_1", "species_2"] if model_name == "turing" else ["X", "Y"]
     u = shard.owned(names[0])
     assert np.isfinite(u).all(), "non-finite concentrations after the timed run"
     my_med = statistics.median(mine)
@@ -495,9 +504,11 @@ def main():
         hout = [torch.empty((nzl, nyl, nxl), dtype=torch.float64).pin_memory().numpy() for _ in range(S)]
         nsl = int(os.environ.get("BENCH_SLABS", "0"))
         step = next_step
+        h0 = [b.copy() for b in hbuf]  # every region starts from the same host state (see Harness.time_steps)
         sim.oneStepHost(step, dt, dict(zip(names, hbuf)), dict(zip(names, hout)), nsl)  # warm-up: streams, events
-        hbuf, hout = hout, hbuf
         for _ in range(h.R):
+            for b, b0 in zip(hbuf, h0):
+                np.copyto(b, b0)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -513,7 +524,10 @@ def main():
     else:
         # sharded: every rank uploads / downloads its own slab (pinned on the NUMA node of its GPU); time = max over ranks
         step = next_step
+        h0 = [b.copy() for b in hbuf]
         for _ in range(h.R):
+            for b, b0 in zip(hbuf, h0):
+                np.copyto(b, b0)
             h.sync_all()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -536,7 +550,7 @@ def main():
            "host_link_GBps_per_rank_each_way": bytes_each_way / (ems / Ke * 1e-3) / 1e9, "numa": numa}
     specialise_info = shard.sim.getSpecializeInfo()
     shard.sim.close()
-    del shard, hbuf
+    del shard, hbuf, h0
 
     # ---- secondary workloads (SURVEY.md §8d "Multi-GPU reporting", BASELINE.json configs 2-5) --------------------------
     secondary = {}

@@ -199,3 +199,91 @@ def turing_flux3d(nx, ny, nz):
           ("species_2", "Zmax"): (0.12, "Dirichlet"), ("species_2", "Zmin"): (0.09, "Dirichlet")}
     return turing(nx, ny, nz, bc_values=bc)
 
+
+
+def turing_bc(nx, ny):
+    """2-D Turing model whose boundary pass is live: non-zero Neumann fluxes on three sides of species_1 and a Dirichlet value on
+    Ymin of species_2 (the unfused schedule with the flux carried in k0).  dt 0.05."""
+    bc = {("species_1", "Xmin"): 0.3, ("species_1", "Xmax"): -0.1, ("species_1", "Ymax"): 0.05,
+          ("species_2", "Xmin"): 0.02, ("species_2", "Ymin"): (0.12, "Dirichlet")}
+    return turing(nx, ny, bc_values=bc)
+
+
+def _membrane_geometry(axes, dims, inside_math):
+    """outside (ordinal 0, everything) / cell (ordinal 1, `inside_math`) / the membrane between them, declared the way the
+    reference's transport.xml declares its compartments (domain types, domains, adjacentDomains)."""
+    kinds = {"x": "cartesianX", "y": "cartesianY", "z": "cartesianZ"}
+    cc = "".join('<spatial:coordinateComponent spatial:id="%s" spatial:type="%s">'
+                 '<spatial:boundaryMin spatial:id="%smin" spatial:value="0"/>'
+                 '<spatial:boundaryMax spatial:id="%smax" spatial:value="%d"/></spatial:coordinateComponent>'
+                 % (a, kinds[a], a.upper(), a.upper(), n - 1) for a, n in zip(axes, dims))
+    return ('<spatial:geometry spatial:id="geometry" spatial:coordinateSystem="cartesian">'
+            '<spatial:listOfCoordinateComponents>%s</spatial:listOfCoordinateComponents>'
+            '<spatial:listOfDomainTypes><spatial:domainType spatial:id="dt_cell" spatial:spatialDimensions="3"/>'
+            '<spatial:domainType spatial:id="dt_out" spatial:spatialDimensions="3"/>'
+            '<spatial:domainType spatial:id="dt_mem" spatial:spatialDimensions="2"/></spatial:listOfDomainTypes>'
+            '<spatial:listOfDomains><spatial:domain spatial:id="dom_cell" spatial:domainType="dt_cell"/>'
+            '<spatial:domain spatial:id="dom_out" spatial:domainType="dt_out"/>'
+            '<spatial:domain spatial:id="dom_mem" spatial:domainType="dt_mem"/></spatial:listOfDomains>'
+            '<spatial:listOfAdjacentDomains>'
+            '<spatial:adjacentDomains spatial:id="ad0" spatial:domain1="dom_mem" spatial:domain2="dom_cell"/>'
+            '<spatial:adjacentDomains spatial:id="ad1" spatial:domain1="dom_mem" spatial:domain2="dom_out"/>'
+            '</spatial:listOfAdjacentDomains>'
+            '<spatial:listOfGeometryDefinitions><spatial:analyticGeometry spatial:id="ag" spatial:isActive="true">'
+            '<spatial:listOfAnalyticVolumes>'
+            '<spatial:analyticVolume spatial:id="av_cell" spatial:functionType="layered" spatial:ordinal="1" spatial:domainType="dt_cell">'
+            '<math %s>%s</math></spatial:analyticVolume>'
+            '<spatial:analyticVolume spatial:id="av_out" spatial:functionType="layered" spatial:ordinal="0" spatial:domainType="dt_out">'
+            '<math %s>%s</math></spatial:analyticVolume>'
+            '</spatial:listOfAnalyticVolumes></spatial:analyticGeometry></spatial:listOfGeometryDefinitions>'
+            '</spatial:geometry>' % (cc, _MATH, inside_math, _MATH, _cn(1)))
+
+
+def membrane(nx, ny, nz=None, shape="disc", transport=True):
+    """A cell (disc / ball, or a box with shape="box") in a bath with species ON the membrane between them: what the reference
+    calls membrane diffusion (calcMemDiffusion over the Voronoi neighbours of setVoronoiInfo), binding of a volume species to
+    a membrane species (the binding branches of calcMemTransport), a reaction between membrane species (reversePolishRK over
+    the membrane's points), the pseudo-membrane fill of updateAssignmentRules, and — with transport=True — an ordinary
+    membrane transport between the two volumes beside them.  No example file of the reference has a membrane species.
+      A (cell, diffuses) --bind: kon*A--> M (membrane, surface diffusion, non-uniform start) --conv: kc*M--> N (membrane)
+      M --unbind: koff*M--> A;   A (cell) --leak: kl*A--> E (bath), a transport across the membrane.
+    dt 0.05."""
+    dims = [nx, ny] + ([nz] if nz else [])
+    axes = ["x", "y", "z"][:len(dims)]
+    c = [(n - 1) / 2.0 + 0.25 * (i + 1) for i, n in enumerate(dims)]  # slightly off the grid's symmetry axes
+    r = 0.31 * (min(dims) - 1)
+    if shape == "box":
+        inside = _piecewise(_cn(1), _box(axes, int(0.25 * (min(dims) - 1)), [int(0.7 * (n - 1)) for n in dims]), _cn(0))
+    else:
+        sq = [_apply("power", _apply("minus", _ci(a), _cn(ci)), _cn(2)) for a, ci in zip(axes, c)]
+        inside = _piecewise(_cn(1), _apply("leq", _apply("plus", *sq), _cn(r * r)), _cn(0))
+    comps = ('<compartment id="cell" spatialDimensions="3" size="1" constant="true">'
+             '<spatial:compartmentMapping spatial:id="m_cell" spatial:domainType="dt_cell" spatial:unitSize="1"/></compartment>'
+             '<compartment id="bath" spatialDimensions="3" size="1" constant="true">'
+             '<spatial:compartmentMapping spatial:id="m_out" spatial:domainType="dt_out" spatial:unitSize="1"/></compartment>'
+             '<compartment id="mem" spatialDimensions="2" size="1" constant="true">'
+             '<spatial:compartmentMapping spatial:id="m_mem" spatial:domainType="dt_mem" spatial:unitSize="1"/></compartment>')
+    def sp(sid, comp, conc):
+        return ('<species id="%s" compartment="%s" hasOnlySubstanceUnits="false" boundaryCondition="false" constant="false" '
+                'spatial:isSpatial="true"%s/>' % (sid, comp, (' initialConcentration="%r"' % float(conc)) if conc is not None else ""))
+    species = sp("A", "cell", None) + sp("E", "bath", 0.25) + sp("M", "mem", None) + sp("N", "mem", 0.0)
+    params = _transport_params("A", 0.8, axes) + _transport_params("E", 0.5, axes)
+    params.append(_param("M_diff", 0.35, '<spatial:diffusionCoefficient spatial:variable="M" spatial:type="isotropic"/>'))
+    params.append(_param("N_diff", 0.2, '<spatial:diffusionCoefficient spatial:variable="N" spatial:type="isotropic"/>'))
+    params += [_param("kon", 0.3), _param("koff", 0.05), _param("kc", 0.11), _param("kl", 0.07)]
+    coords = "".join(_param(a, 0.0, '<spatial:spatialSymbolReference spatial:spatialRef="%s"/>' % a) for a in axes)
+    ia = [("A", _apply("plus", _cn(1.0), _apply("times", _cn(0.02), _ci("x")))),
+          ("M", _apply("plus", _cn(0.5), _apply("times", _cn(0.03), _ci("y")), _apply("times", _cn(0.01), _ci("x"))))]
+    ia_xml = "".join('<initialAssignment symbol="%s"><math %s>%s</math></initialAssignment>' % (s, _MATH, m) for s, m in ia)
+    rx = [_reaction("bind", [("A", 1)], [("M", 1)], _apply("times", _ci("kon"), _ci("A"))),
+          _reaction("conv", [("M", 1)], [("N", 1)], _apply("times", _ci("kc"), _ci("M"))),
+          _reaction("unbind", [("M", 1)], [("A", 1)], _apply("times", _ci("koff"), _ci("M")))]
+    if transport:
+        rx.append(_reaction("leak", [("A", 1)], [("E", 1)], _apply("times", _ci("kl"), _ci("A"))))
+    return ('<?xml version="1.0" encoding="UTF-8"?>\n'
+            '<sbml xmlns="http://www.sbml.org/sbml/level3/version1/core" xmlns:spatial="%s" level="3" version="1" '
+            'spatial:required="true"><model id="synthetic_membrane"><listOfCompartments>%s</listOfCompartments>'
+            '<listOfSpecies>%s</listOfSpecies><listOfParameters>%s%s</listOfParameters>'
+            '<listOfInitialAssignments>%s</listOfInitialAssignments>'
+            '<listOfReactions>%s</listOfReactions>%s</model></sbml>\n'
+            % (SPATIAL_NS, comps, species, coords, "".join(params), ia_xml, "".join(rx), _membrane_geometry(axes, dims, inside)))
