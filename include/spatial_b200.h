@@ -80,6 +80,7 @@ typedef struct {
 #define SB2_TOK_FIELD 2  /* raw field value (calcPDE.cpp:249-251) */
 #define SB2_TOK_CONST 3  /* *constList[i] (calcPDE.cpp:253-255) */
 #define SB2_TOK_NOP 4    /* unresolved name: an all-zero slot, acts as a pop (astFunction.cpp:71-88) */
+#define SB2_TOK_MEMVAR 5 /* membrane species (slot = id from sb2_add_mem_species): value at the point + rk[m]*dt*k_{m-1} */
 
 /* Operator codes: our own enumeration of the cases of the interpreter switch at
  * calcPDE.cpp:259-426 (never libSBML's ASTNodeType_t values). */
@@ -103,6 +104,10 @@ typedef struct {
   int32_t is_variable;
   double stoichiometry;
 } sb2_ref;
+
+/* sb2_ref.species >= SB2_MEM_SPECIES names the membrane species (species - SB2_MEM_SPECIES) */
+#define SB2_MEM_SPECIES 0x1000
+#define SB2_MAX_MEM_SPECIES 8
 
 #define SB2_SRC_NONE 0
 #define SB2_SRC_CONST 1 /* uniform: constants-table slot */
@@ -158,11 +163,52 @@ typedef struct {
   int32_t axis;      /* 0 x, 1 y, 2 z */
   double abs_normal; /* fabs(nuVec[index].n{x,y,z}) */
 } sb2_mem_point;
+/* Binding (one side of the reaction is a membrane species, spatialsimulator.cpp:1440-1450 and the "binding" branches at
+ * calcPDE.cpp:1405-1407 etc.): a SB2_TOK_MEMVAR operand is read at the membrane point itself — operand_cells[k][p][0] holds
+ * the point's STORAGE index in the species' point set, [1] is -1 — and a reference to a membrane species (SB2_MEM_SPECIES + id)
+ * receives fabs(n) * stoich * rate / (delta / 2.0) at target_cells[r][p][0] = the point's storage index ([1] = -1). */
 SB2_API int sb2_add_mem_transport(sb2_sim* sim, const sb2_token* toks, int ntoks, const sb2_ref* refs, int nrefs,
                           int n_reactants, const sb2_mem_point* pts, int npts,
                           const int32_t* operand_cells /* [n VAR tokens][npts][2]: near, far compact cell or -1 */,
                           const double* operand_values /* [n FIELD tokens][npts]: value at the membrane point */,
                           const int32_t* target_cells /* [nrefs][npts][2]: plus side, minus side compact cell or -1 */);
+
+/* ---- species that live ON a membrane ----------------------------------------------------------------------------
+ * The reference keeps a membrane species in a full doubled-grid array and touches it only at the membrane's points
+ * (GeometryInfo::domainIndex, isDomain == 1) and pseudo-membrane points (isDomain == 2, spatialsimulator.cpp:719-1038).
+ * Here such a species is an array over a POINT SET: the host numbers the points it needs storage for (membrane points,
+ * pseudo-membrane points) 0 .. npts-1 and passes every list below in those storage indices. */
+SB2_API int sb2_add_point_set(sb2_sim* sim, int npts);                       /* returns set id */
+SB2_API int sb2_add_mem_species(sb2_sim* sim, int set, const double* init);  /* value[] + delta[4N] on the set; returns id */
+/* Reaction (kind 0) or rate rule (kind 1) between membrane species, evaluated at the listed points of the set in list
+ * order (reversePolishRK over the membrane's domainIndex, calcPDE.cpp:224-451).  Tokens: SB2_TOK_MEMVAR operands are read
+ * at the point; SB2_TOK_FIELD / SB2_TOK_VAR operands (coordinates, parameter fields, volume species, whose values at a
+ * membrane point never change) come from operand_values[k][p], k counting those tokens in stream order.  refs name
+ * membrane species (SB2_MEM_SPECIES + id); others are skipped. */
+SB2_API int sb2_add_mem_reaction(sb2_sim* sim, int set, int kind, const sb2_token* toks, int ntoks, const sb2_ref* refs, int nrefs,
+                                 int n_reactants, const int32_t* points, int npts, const double* operand_values);
+/* Surface diffusion of a membrane species (calcMemDiffusion, calcPDE.cpp:1484-1581) over the Voronoi neighbours that
+ * setVoronoiInfo (setInfoFunction.cpp:1134-1546) finds: point points[p] has the terms term_start[p] .. term_start[p+1]-1, each
+ * with a neighbour (storage index), the facet length s_ij and the distance d_ij, in the reference's order (xy, yz, xz planes, two
+ * neighbours each); area[p] = sum(d_ij * s_ij) / 2 (2-D) or / 4 (3-D).  The coefficient is a constants-table slot
+ * (SB2_SRC_CONST) or one value per listed point (SB2_SRC_FIELD, d_values). */
+SB2_API int sb2_set_mem_diffusion(sb2_sim* sim, int mem_species, int src_kind, int src, const double* d_values, const int32_t* points,
+                                  int npts, const int32_t* term_start, const int32_t* adj, const double* s_ij, const double* d_ij,
+                                  const double* area);
+/* Points a membrane species is advanced on by updateSpecies (its geometry's domainIndex, spatialsimulator.cpp:1526-1537). */
+SB2_API int sb2_set_mem_update_points(sb2_sim* sim, int mem_species, const int32_t* points, int npts);
+/* Pseudo-membrane fill after every step (updateAssignmentRules, spatialsimulator.cpp:1614-1663): for every membrane species
+ * of the set, value[target[i]] = min(value[a[i]], value[b[i]]), in list order. */
+SB2_API int sb2_set_mem_fill(sb2_sim* sim, int set, const int32_t* target, const int32_t* a, const int32_t* b, int n);
+SB2_API int sb2_download_mem_species(sb2_sim* sim, int mem_species, double* out);   /* npts of its set */
+SB2_API int sb2_upload_mem_species(sb2_sim* sim, int mem_species, const double* in);
+SB2_API int sb2_download_mem_stage(sb2_sim* sim, int mem_species, int m, double* out);
+
+/* Assignment rule re-evaluated after every step, in the order given (updateAssignmentRules, spatialsimulator.cpp:1566-1581;
+ * reversePolishInitial, calcPDE.cpp:21-222): the stream is evaluated with the raw current values (no RK offset) and written to
+ * a read-only field (target_kind 0, every cell: a rule on a parameter) or to a staged species (target_kind 1, only the cells
+ * of geometry `geo`: a rule on a species). */
+SB2_API int sb2_add_assignment_rule(sb2_sim* sim, int target_kind, int target, int geo, const sb2_token* toks, int ntoks);
 
 SB2_API int sb2_finalize(sb2_sim* sim);
 
@@ -183,6 +229,7 @@ SB2_API int sb2_download_species(sb2_sim* sim, int species, double* out);      /
 SB2_API int sb2_upload_species(sb2_sim* sim, int species, const double* in);
 SB2_API int sb2_download_stage(sb2_sim* sim, int species, int m, double* out); /* k_m, for tests */
 SB2_API int sb2_upload_field(sb2_sim* sim, int field, const double* in);
+SB2_API int sb2_download_field(sb2_sim* sim, int field, double* out);  /* fields change when an assignment rule targets them */
 /* CIP-CSLR face point values of an advected species (the odd doubled-grid points between two cells
  * along `axis`, calcPDE.cpp:588-603): faces[cell] = value at the face between cell and cell + e_axis. */
 SB2_API int sb2_upload_faces(sb2_sim* sim, int species, int axis, const double* in);

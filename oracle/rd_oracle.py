@@ -38,13 +38,30 @@ AST_LOGICAL_AND, AST_LOGICAL_NOT, AST_LOGICAL_OR, AST_LOGICAL_XOR = 304, 305, 30
 AST_RELATIONAL_EQ, AST_RELATIONAL_GEQ, AST_RELATIONAL_GT = 308, 309, 310
 AST_RELATIONAL_LEQ, AST_RELATIONAL_LT, AST_RELATIONAL_NEQ = 311, 312, 313
 
+import math
+
+
+def _libm(fn, nargs=1):
+    """The C library's function applied element by element (numpy's own vectorised exp / pow / tanh ... may differ from libm
+    in the last bit, and the reference calls libm); domain errors give NaN / inf like the C function does."""
+    def safe(*a):
+        try:
+            return fn(*a)
+        except (ValueError, ZeroDivisionError):
+            return float("nan")
+        except OverflowError:
+            return float("inf")
+    uf = np.frompyfunc(safe, nargs, 1)
+    return lambda *arrs: uf(*arrs).astype(np.float64)
+
+
 UNARY = {
-    AST_FUNCTION_ABS: np.fabs, AST_FUNCTION_ARCCOS: np.arccos, AST_FUNCTION_ARCCOSH: np.arccosh,
-    AST_FUNCTION_ARCCSC: lambda x: np.arcsin(1.0 / x), AST_FUNCTION_ARCSIN: np.arcsin, AST_FUNCTION_ARCTAN: np.arctan,
-    AST_FUNCTION_COS: np.cos, AST_FUNCTION_COSH: np.cosh, AST_FUNCTION_CSC: lambda x: 1.0 / np.sin(x),
-    AST_FUNCTION_EXP: np.exp, AST_FUNCTION_LN: np.log,
-    AST_FUNCTION_ROOT: np.sqrt,  # sqrt whatever the degree (calcPDE.cpp:355)
-    AST_FUNCTION_SIN: np.sin, AST_FUNCTION_SINH: np.sinh, AST_FUNCTION_TAN: np.tan, AST_FUNCTION_TANH: np.tanh,
+    AST_FUNCTION_ABS: np.fabs, AST_FUNCTION_ARCCOS: _libm(math.acos), AST_FUNCTION_ARCCOSH: _libm(math.acosh),
+    AST_FUNCTION_ARCCSC: lambda x: _libm(math.asin)(1.0 / x), AST_FUNCTION_ARCSIN: _libm(math.asin), AST_FUNCTION_ARCTAN: _libm(math.atan),
+    AST_FUNCTION_COS: _libm(math.cos), AST_FUNCTION_COSH: _libm(math.cosh), AST_FUNCTION_CSC: lambda x: 1.0 / _libm(math.sin)(x),
+    AST_FUNCTION_EXP: _libm(math.exp), AST_FUNCTION_LN: _libm(math.log),
+    AST_FUNCTION_ROOT: np.sqrt,  # sqrt whatever the degree (calcPDE.cpp:355); correctly rounded everywhere
+    AST_FUNCTION_SIN: _libm(math.sin), AST_FUNCTION_SINH: _libm(math.sinh), AST_FUNCTION_TAN: _libm(math.tan), AST_FUNCTION_TANH: _libm(math.tanh),
     AST_LOGICAL_NOT: lambda x: np.where(x.astype(np.int64) == 0, 1.0, 0.0),  # calcPDE.cpp:385-388
 }
 
@@ -56,8 +73,8 @@ def _as_int(x):
 
 BINARY = {
     AST_PLUS: lambda a, b: a + b, AST_MINUS: lambda a, b: a - b, AST_TIMES: lambda a, b: a * b, AST_DIVIDE: lambda a, b: a / b,
-    AST_POWER: np.power, AST_FUNCTION_POWER: np.power,
-    AST_FUNCTION_LOG: lambda a, b: np.log(b) / np.log(a),  # calcPDE.cpp:349-352
+    AST_POWER: _libm(math.pow, 2), AST_FUNCTION_POWER: _libm(math.pow, 2),
+    AST_FUNCTION_LOG: lambda a, b: _libm(math.log)(b) / _libm(math.log)(a),  # calcPDE.cpp:349-352
     # static_cast<int>(a) == 1 && static_cast<int>(b == 1)   — calcPDE.cpp:383, 391, 395
     AST_LOGICAL_AND: lambda a, b: np.where((_as_int(a) == 1) & (b == 1.0), 1.0, 0.0),
     AST_LOGICAL_OR: lambda a, b: np.where((_as_int(a) == 1) | (b == 1.0), 1.0, 0.0),
@@ -87,24 +104,32 @@ def parse_stream(text):
 def eval_stream(toks, operand, consts, shape):
     """calcPDE.cpp:244-431 on whole arrays: the same stack discipline for every cell, so the stack is a list of arrays.
     operand(name, has_delta) → array; consts: name → current value (literal tokens carry their value)."""
-    stack = []
+    # rpStack with its index: a slot keeps what was last stored in it, so a stream that runs the stack empty (every stream with a
+    # listed-but-empty operator does) yields the stale bottom slot, exactly like rpStack[st_index] with st_index == 0
+    slots = [np.zeros(shape) for _ in range(64)]
+    st = 0
     for t in toks:
         if t[0] == "V":
-            stack.append(operand(t[1], t[2]))
+            slots[st] = operand(t[1], t[2])
+            st += 1
         elif t[0] == "C":
             v = consts.get(t[1], t[2]) if t[1] != "#" else t[2]
-            stack.append(np.full(shape, v, dtype=np.float64))
+            slots[st] = np.full(shape, v, dtype=np.float64)
+            st += 1
         else:
             op = t[1]
-            top = stack.pop() if stack else None  # if (st_index > 0) st_index--
+            if st > 0:  # if (st_index > 0) st_index--
+                st -= 1
             if op in BINARY:
-                if top is not None and stack:  # if (st_index > 0) s[st-1] op= s[st]
-                    stack[-1] = BINARY[op](stack[-1], top)
+                if st > 0:  # if (st_index > 0) s[st-1] op= s[st]
+                    slots[st - 1] = BINARY[op](slots[st - 1], slots[st])
             elif op in UNARY:
-                x = top if top is not None else np.zeros(shape)  # (an empty stack leaves a stale slot in the reference)
-                stack.append(UNARY[op](x))
+                slots[st] = UNARY[op](slots[st])
+                st += 1
             # every other operator only pops (calcPDE.cpp:297-302, 379-380, 399-400 ...)
-    return stack[-1] if stack else np.zeros(shape)  # if (st_index > 0) st_index--; rate = s[st_index]
+    if st > 0:
+        st -= 1
+    return slots[st]  # if (st_index > 0) st_index--; rate = s[st_index]
 
 
 class Species(object):
@@ -148,10 +173,14 @@ class Membrane(object):
 class RDOracle(object):
     """State + oneStep of the restated path."""
 
-    def __init__(self, species, reactions, consts, delta, dimension):
+    def __init__(self, species, reactions, consts, delta, dimension, rate_rules=()):
         self.sp = {s.name: s for s in species}
         self.order = [s.name for s in species]
         self.rx = reactions
+        # (index of the rule in the model's rule list, domain mask of its variable's compartment): the reference evaluates
+        # rInfoList[that index] for a rate rule (spatialsimulator.cpp:1455-1461), which is the rule itself only in a model
+        # without reactions
+        self.rate_rules = list(rate_rules)
         self.consts = dict(consts)
         self.delta = delta
         self.dimension = dimension
@@ -175,6 +204,8 @@ class RDOracle(object):
                     raise NotImplementedError("field operand %s" % name)
 
                 for r in self.rx:  # document order, spatialsimulator.cpp:1374-1390
+                    if r is None or not r.is_reaction:
+                        continue  # entries without a Reaction (rate rules) are skipped here (:1376-1377)
                     if r.membrane is not None:
                         self._mem_transport(r, m, dt)
                         continue
@@ -183,13 +214,18 @@ class RDOracle(object):
                         if not is_var or name not in self.sp:
                             continue
                         km = self.sp[name].k[m]
-                        if not r.is_reaction:
-                            if k == 0:
-                                km[r.domain] += (stoich * rate)[r.domain]  # calcPDE.cpp:447-449
-                        elif k < r.n_reactants:
+                        if k < r.n_reactants:
                             km[r.domain] -= (stoich * rate)[r.domain]      # calcPDE.cpp:432-438
                         else:
                             km[r.domain] += (stoich * rate)[r.domain]      # calcPDE.cpp:439-446
+                for index, domain in self.rate_rules:  # spatialsimulator.cpp:1455-1461
+                    r = self.rx[index]
+                    if r is None or r.membrane is not None:
+                        raise NotImplementedError("rate rule whose rInfoList slot is a membrane transport")
+                    rate = eval_stream(r.toks, operand, self.consts, self.shape)
+                    if r.refs and r.refs[0][2] and r.refs[0][0] in self.sp:
+                        km = self.sp[r.refs[0][0]].k[m]
+                        km[domain] += (r.refs[0][1] * rate)[domain]        # calcPDE.cpp:447-449
                 for n in self.order:  # species order, spatialsimulator.cpp:1464-1478
                     s = self.sp[n]
                     self._diffusion(s, w[n], m)
@@ -571,6 +607,10 @@ def from_simulator(sim, xml_text, dims):
             p = line.split()
             refs.append((p[0], float(p[1]), p[2] == "1"))
         n_reactants = _count_reactants(xml_text, i)
+        if n_reactants is None:  # an entry past the reactions: a rate rule (setRateRuleInfo, setInfoFunction.cpp:448-494)
+            reactions.append(Reaction(parse_stream(text), refs, 1, None, is_reaction=False))
+            i += 1
+            continue
         dom = None
         for name, _, _ in refs:  # geometry of the first species reference that has one (spatialsimulator.cpp:1381-1390)
             if name in var_geo:
@@ -600,12 +640,29 @@ def from_simulator(sim, xml_text, dims):
             reactions.append(Reaction(parse_stream(text), refs, n_reactants, None, membrane=mem))
         elif dom is not None:
             reactions.append(Reaction(parse_stream(text), refs, n_reactants, dom))
+        else:
+            reactions.append(None)  # every participant is uniform: keeps the list aligned with rInfoList
         i += 1
-    return RDOracle(species, reactions, uniform, delta, dimension)
+    rate_rules = []
+    root = ET.fromstring(xml_text)
+    rules_el = [r for lr in root.iter(CORE + "listOfRules") for r in lr]
+    for index, r in enumerate(rules_el):
+        if r.tag != CORE + "rateRule":
+            continue
+        target = r.get("variable")
+        if index >= len(reactions):
+            raise NotImplementedError("rate rule %s: the reference indexes its reaction list out of range" % target)
+        if target in var_geo:
+            rate_rules.append((index, masks[var_geo[target]]))
+    if any(r.tag == CORE + "assignmentRule" for r in rules_el):
+        raise NotImplementedError("assignment rules re-evaluated every step are not restated here")
+    return RDOracle(species, reactions, uniform, delta, dimension, rate_rules)
 
 
 def _count_reactants(xml_text, index):
     root = ET.fromstring(xml_text)
     rx = [r for r in root.iter(CORE + "reaction") if r.get("fast") != "true"]
+    if index >= len(rx):
+        return None
     lor = rx[index].find(CORE + "listOfReactants")
     return 0 if lor is None else len(list(lor))

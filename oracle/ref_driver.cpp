@@ -19,6 +19,7 @@
 #undef private
 
 #include <sbml/SBMLTypes.h>
+#include <malloc.h>
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
@@ -212,6 +213,7 @@ static int doTime(int argc, char** argv) {
 // oracle calls them directly for every species that diffuses / is advected and prints the smallest admissible step.
 double checkDiffusionStab(variableInfo* sInfo, double deltaX, double deltaY, double deltaZ, int Xindex, int Yindex, double dt);
 double checkAdvectionStab(variableInfo* sInfo, double deltaX, double deltaY, double deltaZ, double dt, int Xindex, int Yindex, int dimension);
+double checkMemDiffusionStab(variableInfo* sInfo, voronoiInfo* vorI, int Xindex, int Yindex, double dt, double dimension);
 static int doStab(int argc, char** argv) {
   if (argc < 7) return 2;
   SpatialSimulator sim;
@@ -223,7 +225,10 @@ static int doStab(int argc, char** argv) {
     for (size_t k = 0; k < sim.varInfoList.size(); ++k) {
       variableInfo* v = sim.varInfoList[k];
       if (!v->sp || v->isUniform || !v->geoi) continue;
-      if (v->diffCInfo) best = std::min(best, checkDiffusionStab(v, sim.deltaX, sim.deltaY, sim.deltaZ, sim.Xindex, sim.Yindex, dt));
+      // volume species: checkDiffusionStab, species on a membrane: checkMemDiffusionStab (the dispatch of the reference's own,
+      // commented-out, call site spatialsimulator.cpp:1172-1179)
+      if (v->diffCInfo && v->geoi->isVol) best = std::min(best, checkDiffusionStab(v, sim.deltaX, sim.deltaY, sim.deltaZ, sim.Xindex, sim.Yindex, dt));
+      if (v->diffCInfo && !v->geoi->isVol && sim.vorI) best = std::min(best, checkMemDiffusionStab(v, sim.vorI, sim.Xindex, sim.Yindex, dt, (double)sim.dimension));
       if (v->adCInfo) best = std::min(best, checkAdvectionStab(v, sim.deltaX, sim.deltaY, sim.deltaZ, dt, sim.Xindex, sim.Yindex, (int)sim.dimension));
     }
     printf("%s\"%s\": %.17g", a > 6 ? ", " : "", argv[a], best);
@@ -233,6 +238,11 @@ static int doStab(int argc, char** argv) {
 }
 
 int main(int argc, char** argv) {
+  // The reference's membrane scan reads isDomain[index - Xindex*Yindex] on the Z = 0 plane of a 3-D grid (and the like on the
+  // other frame planes, spatialsimulator.cpp:929-960): a few KB before the array.  With glibc's default mmap threshold such an
+  // array is its own mapping and the read can fault, depending on the heap layout; keeping big arrays on the brk heap makes
+  // the read land in mapped memory, as it does in a typical run of the reference.
+  mallopt(M_MMAP_THRESHOLD, 1 << 30);
   if (argc >= 2 && std::string(argv[1]) == "stab") return doStab(argc, argv);
   if (argc >= 2 && std::string(argv[1]) == "dump") return doDump(argc, argv);
   if (argc >= 2 && std::string(argv[1]) == "time") return doTime(argc, argv);

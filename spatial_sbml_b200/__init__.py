@@ -21,7 +21,8 @@ _lib = None
 # against the headers)
 SB2_OK = 0
 SB2_F_DOMAIN, SB2_F_XP, SB2_F_XM, SB2_F_YP, SB2_F_YM, SB2_F_ZP, SB2_F_ZM = 1, 2, 4, 8, 16, 32, 64
-SB2_TOK_OP, SB2_TOK_VAR, SB2_TOK_FIELD, SB2_TOK_CONST, SB2_TOK_NOP = 0, 1, 2, 3, 4
+SB2_TOK_OP, SB2_TOK_VAR, SB2_TOK_FIELD, SB2_TOK_CONST, SB2_TOK_NOP, SB2_TOK_MEMVAR = 0, 1, 2, 3, 4, 5
+SB2_MEM_SPECIES = 0x1000
 SB2_SRC_NONE, SB2_SRC_CONST, SB2_SRC_FIELD = 0, 1, 2
 SB2_BC_NONE, SB2_BC_NEUMANN, SB2_BC_DIRICHLET = 0, 1, 2
 OPS = dict(PLUS=1, MINUS=2, TIMES=3, DIVIDE=4, POWER=5, LOG=6, AND=7, OR=8, XOR=9, EQ=10, GEQ=11, GT=12,
@@ -72,6 +73,16 @@ def _proto(lib):
         "sb2_set_boundary": (ci, [vp, ci, ci, ci, ci, ci]),
         "sb2_add_mem_transport": (ci, [vp, C.POINTER(Token), ci, C.POINTER(Ref), ci, ci, C.POINTER(MemPoint), ci,
                                        C.POINTER(C.c_int32), dp, C.POINTER(C.c_int32)]),
+        "sb2_add_point_set": (ci, [vp, ci]),
+        "sb2_add_mem_species": (ci, [vp, ci, dp]),
+        "sb2_add_mem_reaction": (ci, [vp, ci, ci, C.POINTER(Token), ci, C.POINTER(Ref), ci, ci, C.POINTER(C.c_int32), ci, dp]),
+        "sb2_set_mem_diffusion": (ci, [vp, ci, ci, ci, dp, C.POINTER(C.c_int32), ci, C.POINTER(C.c_int32), C.POINTER(C.c_int32), dp, dp, dp]),
+        "sb2_set_mem_update_points": (ci, [vp, ci, C.POINTER(C.c_int32), ci]),
+        "sb2_set_mem_fill": (ci, [vp, ci, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), ci]),
+        "sb2_download_mem_species": (ci, [vp, ci, dp]),
+        "sb2_upload_mem_species": (ci, [vp, ci, dp]),
+        "sb2_download_mem_stage": (ci, [vp, ci, ci, dp]),
+        "sb2_add_assignment_rule": (ci, [vp, ci, ci, ci, C.POINTER(Token), ci]),
         "sb2_finalize": (ci, [vp]),
         "sb2_step": (ci, [vp, cd, cd, cd, ci, ci]),
         "sb2_step_host": (ci, [vp, cd, cd, ci, C.POINTER(dp), C.POINTER(dp), ci]),
@@ -79,6 +90,7 @@ def _proto(lib):
         "sb2_upload_species": (ci, [vp, ci, dp]),
         "sb2_download_stage": (ci, [vp, ci, ci, dp]),
         "sb2_upload_field": (ci, [vp, ci, dp]),
+        "sb2_download_field": (ci, [vp, ci, dp]),
         "sb2_upload_faces": (ci, [vp, ci, ci, dp]),
         "sb2_download_faces": (ci, [vp, ci, ci, dp]),
         "sb2_min_dt": (ci, [vp, cd, dp]),

@@ -387,6 +387,8 @@ struct MtEvalArgs {
   double* rate;
   const double* u[SB2_MAX_SPECIES];
   const double* kprev[SB2_MAX_SPECIES];
+  const double* mu[SB2_MAX_MEM_SPECIES];      // membrane species (binding): value at the point's storage index
+  const double* mkprev[SB2_MAX_MEM_SPECIES];
   double consts[SB2_MAX_CONSTS];
 };
 
@@ -415,6 +417,15 @@ __global__ void __launch_bounds__(128) mt_eval_kernel(const __grid_constant__ Mt
         } else {
           st[sp] = wn;
         }
+      }
+      if (sp < 49) ++sp;
+    } else if (kind == SB2_TOK_MEMVAR) {
+      // symbol in the membrane: its value at the point itself (calcPDE.cpp:1214-1217)
+      const int nc = A.near_cell[(int64_t)A.tok_operand[i] * A.npts + p];
+      if (nc >= 0) {
+        double w = A.mu[slot][nc];
+        if (A.m > 0) w = w + A.cdt * A.mkprev[slot][nc];
+        st[sp] = w;
       }
       if (sp < 49) ++sp;
     } else if (kind == SB2_TOK_FIELD) {
@@ -450,7 +461,7 @@ struct MtApplyArgs {
   const double* entry_delta;
   const int32_t* entry_sign;
   const double* rate;
-  double* kout[SB2_MAX_SPECIES];
+  double* kout[SB2_MAX_SPECIES + SB2_MAX_MEM_SPECIES];  // volume species, then membrane species
 };
 
 // gather formulation of the scatter at calcPDE.cpp:1394-1479: one thread per (species, cell) sums its
@@ -496,13 +507,16 @@ int sb2_build_transport(const sb2_grid& g, int64_t P, int64_t PL, int64_t first,
   int nvar = 0, nfield = 0, rows = 0;
   for (int i = 0; i < ntoks; ++i) {
     out.tok.push_back((uint32_t)toks[i].kind | ((uint32_t)toks[i].op << 8) | ((uint32_t)toks[i].slot << 16));
-    if (toks[i].kind == SB2_TOK_VAR) {
-      if (toks[i].slot >= nspecies) { err = "membrane transport: token references unknown species"; return SB2_ERR_ARG; }
+    if (toks[i].kind == SB2_TOK_VAR || toks[i].kind == SB2_TOK_MEMVAR) {
+      const bool mem = toks[i].kind == SB2_TOK_MEMVAR;
+      if (!mem && toks[i].slot >= nspecies) { err = "membrane transport: token references unknown species"; return SB2_ERR_ARG; }
+      if (mem && toks[i].slot >= SB2_MAX_MEM_SPECIES) { err = "membrane transport: token references unknown membrane species"; return SB2_ERR_ARG; }
       if (!operand_cells) { err = "membrane transport: operand cells missing"; return SB2_ERR_ARG; }
       out.tok_operand.push_back(rows++);
       for (int p = 0; p < npts; ++p) {
-        near_c.push_back(pad(operand_cells[((int64_t)nvar * npts + p) * 2 + 0]));
-        far_c.push_back(pad(operand_cells[((int64_t)nvar * npts + p) * 2 + 1]));
+        const int32_t c0 = operand_cells[((int64_t)nvar * npts + p) * 2 + 0], c1 = operand_cells[((int64_t)nvar * npts + p) * 2 + 1];
+        near_c.push_back(mem ? c0 : pad(c0));  // membrane species: storage index of the point, as it is
+        far_c.push_back(mem ? -1 : pad(c1));
         fval.push_back(0.0);
       }
       ++nvar;
@@ -524,14 +538,22 @@ int sb2_build_transport(const sb2_grid& g, int64_t P, int64_t PL, int64_t first,
   for (int p = 0; p < npts; ++p) {
     for (int r = 0; r < nrefs; ++r) {
       if (!refs[r].is_variable || refs[r].species < 0) continue;
-      if (refs[r].species >= nspecies) { err = "membrane transport: reference to unknown species"; return SB2_ERR_ARG; }
+      const bool mem = refs[r].species >= SB2_MEM_SPECIES;
+      if (!mem && refs[r].species >= nspecies) { err = "membrane transport: reference to unknown species"; return SB2_ERR_ARG; }
+      if (mem && refs[r].species - SB2_MEM_SPECIES >= SB2_MAX_MEM_SPECIES) { err = "membrane transport: reference to unknown membrane species"; return SB2_ERR_ARG; }
       for (int side = 0; side < 2; ++side) {
         const int32_t c = target_cells[((int64_t)r * npts + p) * 2 + side];
         if (c < 0) continue;
         MtEntry e;
-        e.species = refs[r].species; e.cell = pad(c); e.pt = p;
+        e.pt = p;
         e.coef = pts[p].abs_normal * refs[r].stoichiometry;
-        e.delta = delta[pts[p].axis];
+        if (mem) {  // binding: the point itself, divided by (delta / 2.0) (calcPDE.cpp:1405-1407)
+          e.species = SB2_MAX_SPECIES + (refs[r].species - SB2_MEM_SPECIES); e.cell = c;
+          e.delta = delta[pts[p].axis] / 2.0;
+        } else {
+          e.species = refs[r].species; e.cell = pad(c);
+          e.delta = delta[pts[p].axis];
+        }
         e.sign = r < n_reactants ? -1 : +1;
         entries.push_back(e);
       }
@@ -585,7 +607,8 @@ void sb2_free_transport(Sb2MemTransport& t) {
 }
 
 cudaError_t sb2_launch_transport(const Sb2MemTransport& t, const sb2_grid& g, const double* const* u,
-                                 const double* const* kprev, double* const* kout, const double* consts, int m,
+                                 const double* const* kprev, double* const* kout, const double* const* mu,
+                                 const double* const* mkprev, double* const* mkout, const double* consts, int m,
                                  double cdt, cudaStream_t stream, int* launches) {
   (void)g;
   if (t.npts == 0) return cudaSuccess;
@@ -595,8 +618,11 @@ cudaError_t sb2_launch_transport(const Sb2MemTransport& t, const sb2_grid& g, co
   a.tok = t.d_tok; a.tok_operand = t.d_operand;
   a.near_cell = t.d_near; a.far_cell = t.d_far; a.fieldval = t.d_fieldval; a.rate = t.d_rate;
   for (int s = 0; s < SB2_MAX_SPECIES; ++s) { a.u[s] = NULL; a.kprev[s] = NULL; }
-  for (size_t i = 0; i < t.tok.size(); ++i)
+  for (int s = 0; s < SB2_MAX_MEM_SPECIES; ++s) { a.mu[s] = NULL; a.mkprev[s] = NULL; }
+  for (size_t i = 0; i < t.tok.size(); ++i) {
     if ((t.tok[i] & 0xff) == SB2_TOK_VAR) { const int s = t.tok[i] >> 16; a.u[s] = u[s]; a.kprev[s] = kprev[s]; }
+    if ((t.tok[i] & 0xff) == SB2_TOK_MEMVAR && mu) { const int s = t.tok[i] >> 16; a.mu[s] = mu[s]; a.mkprev[s] = mkprev[s]; }
+  }
   memcpy(a.consts, consts, sizeof(a.consts));
   if (launches) ++*launches;
   mt_eval_kernel<<<(t.npts + 127) / 128, 128, 0, stream>>>(a);
@@ -609,6 +635,7 @@ cudaError_t sb2_launch_transport(const Sb2MemTransport& t, const sb2_grid& g, co
   b.entry_pt = t.d_entry_pt; b.entry_coef = t.d_entry_coef; b.entry_delta = t.d_entry_delta; b.entry_sign = t.d_entry_sign;
   b.rate = t.d_rate;
   for (int s = 0; s < SB2_MAX_SPECIES; ++s) b.kout[s] = s < t.nspecies ? kout[s] : NULL;
+  for (int s = 0; s < SB2_MAX_MEM_SPECIES; ++s) b.kout[SB2_MAX_SPECIES + s] = mkout ? mkout[s] : NULL;
   if (launches) ++*launches;
   mt_apply_kernel<<<(t.n_groups + 127) / 128, 128, 0, stream>>>(b);
   return cudaGetLastError();

@@ -80,8 +80,10 @@ int sb2_build_transport(const sb2_grid& g, int64_t P, int64_t PL, int64_t first,
                         const int32_t* operand_cells, const double* operand_values, const int32_t* target_cells,
                         cudaStream_t stream, Sb2MemTransport& out, std::string& err);
 void sb2_free_transport(Sb2MemTransport& t);
+// mu / mkprev / mkout: the membrane species (binding reactions), indexed by membrane species id; may be NULL
 cudaError_t sb2_launch_transport(const Sb2MemTransport& t, const sb2_grid& g, const double* const* u,
-                                 const double* const* kprev, double* const* kout, const double* consts, int m,
+                                 const double* const* kprev, double* const* kout, const double* const* mu,
+                                 const double* const* mkprev, double* const* mkout, const double* consts, int m,
                                  double cdt, cudaStream_t stream, int* launches);
 
 // ---------------- stability (checkStability.cpp:10-52, 119-154) ----------------

@@ -3,6 +3,7 @@
 // (reference spatialsimulator.cpp:1350-1544).
 #include "sb2_internal.h"
 #include "sb2_aux.h"
+#include "sb2_mem.h"
 
 #include <cmath>
 #include <cstdio>
@@ -47,6 +48,14 @@ struct sb2_sim {
   std::vector<Sb2Stmt> stmts;
   std::vector<uint32_t> program;
   std::vector<Sb2MemTransport> transports;
+  // species on membranes (sb2_mem.h) and the order in which transports and membrane reactions were declared: the
+  // reference walks its reaction list once per stage, so contributions to a membrane species add up in that order
+  std::vector<Sb2PointSet> point_sets;
+  std::vector<Sb2MemSpecies> mem_species;
+  std::vector<Sb2MemReaction> mem_reactions;
+  struct MemOp { int type, index; };  // type 0: transports[index], 1: mem_reactions[index]
+  std::vector<MemOp> mem_ops;
+  std::vector<Sb2CellRule> cell_rules;  // assignment rules re-evaluated after every step, in dependency order
   Sb2BoundaryLists blists;
   bool finalized, any_adv;
   bool fuse_combine;    // this step: RK combine fused into stage 4
@@ -106,6 +115,26 @@ int cuda_fail(sb2_sim* s, cudaError_t e, const char* what) {
 #define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail(sim, e__, #call); } while (0)
 
 int64_t ncells(const sb2_sim* s) { return (int64_t)s->g.nx * s->g.ny * s->g.nz; }
+
+Sb2MemView mem_view(const sb2_sim* s) {
+  Sb2MemView v;
+  memset(&v, 0, sizeof(v));
+  for (size_t i = 0; i < s->mem_species.size(); ++i) {
+    v.u[i] = s->mem_species[i].u;
+    for (int m = 0; m < 4; ++m) v.k[i][m] = s->mem_species[i].k[m];
+  }
+  return v;
+}
+
+template <typename T>
+int upload_list(sb2_sim* sim, T** dptr, const T* h, size_t n) {
+  *dptr = NULL;
+  if (n == 0) return SB2_OK;
+  CK(cudaMalloc((void**)dptr, sizeof(T) * n));
+  CK(cudaMemcpyAsync(*dptr, h, sizeof(T) * n, cudaMemcpyHostToDevice, sim->stream));
+  CK(cudaStreamSynchronize(sim->stream));
+  return SB2_OK;
+}
 
 // compact host array → padded device layout (guard rows / planes, even pitch)
 template <typename T>
@@ -208,6 +237,10 @@ int compile_stmt(sb2_sim* sim, const Sb2Stmt& st, std::vector<uint32_t>& prog) {
   std::vector<Ent> stk;
   int nmat = 0;  // materialised entries on the stack
   bool too_deep = false;
+  // What the reference's rpStack[0] holds: a law whose stream runs the stack empty (any law with a listed-but-empty operator
+  // does: such an operator pops without pushing) ends with st_index == 0 and takes rpStack[0], the value last stored at the
+  // bottom of the stack, as its rate (calcPDE.cpp:430-431).  valid: something was stored there during this evaluation.
+  struct { bool valid, lazy; int cslot; } slot0 = {false, false, 0};
   auto emit = [&](int opc, int d, int arg) {
     if (d < 0 || d >= SB2_MAX_DEPTH || (opc == OPC_MOVUP && d + 1 >= SB2_MAX_DEPTH)) too_deep = true;
     out.push_back(enc(opc, d < 0 ? 0 : d, arg));
@@ -224,7 +257,10 @@ int compile_stmt(sb2_sim* sim, const Sb2Stmt& st, std::vector<uint32_t>& prog) {
       if (t.kind == SB2_TOK_VAR && t.slot >= sim->species.size()) return fail(sim, SB2_ERR_ARG, "token references unknown species");
       if (t.kind == SB2_TOK_FIELD && t.slot >= sim->d_fields.size()) return fail(sim, SB2_ERR_ARG, "token references unknown field");
       if (t.kind == SB2_TOK_CONST && t.slot >= SB2_MAX_CONSTS) return fail(sim, SB2_ERR_ARG, "token references constant slot out of range");
-      if (t.kind == SB2_TOK_CONST) { Ent e = {true, (int)t.slot}; stk.push_back(e); continue; }
+      if (t.kind == SB2_TOK_CONST) {
+        if (stk.empty()) { slot0.valid = true; slot0.lazy = true; slot0.cslot = (int)t.slot; }
+        Ent e = {true, (int)t.slot}; stk.push_back(e); continue;
+      }
       // species operand immediately consumed by + - * / on a materialised top → fused form acting on that register
       if (t.kind == SB2_TOK_VAR && !stk.empty() && !stk.back().lazy && i + 1 < n && st.toks[i + 1].kind == SB2_TOK_OP) {
         int opc = -1;
@@ -237,6 +273,7 @@ int compile_stmt(sb2_sim* sim, const Sb2Stmt& st, std::vector<uint32_t>& prog) {
         }
         if (opc >= 0) { emit(opc, nmat - 1, t.slot); ++i; continue; }
       }
+      if (stk.empty()) { slot0.valid = true; slot0.lazy = false; }
       emit(t.kind == SB2_TOK_VAR ? OPC_PUSHV : OPC_PUSHF, nmat, t.slot);
       push_mat();
       continue;
@@ -280,11 +317,13 @@ int compile_stmt(sb2_sim* sim, const Sb2Stmt& st, std::vector<uint32_t>& prog) {
         else { emit(OPC_MOVUP, nmat, 0); emit(OPC_PUSHC, nmat, a.cslot); if (opc_rr >= 0) emit(opc_rr, nmat + 1, 0); else emit(OPC_BINR, nmat + 1, op); }
         stk.back().lazy = false; ++nmat;
       }
+      if (stk.size() == 1) { slot0.valid = true; slot0.lazy = false; }  // the result sits at the bottom, in register 0
     } else if (is_unary(op)) {
       // st--; s[st] = f(s[st]); st++  (an empty stack leaves a stale slot 0 in the reference; 0.0 here)
       if (!had_top) emit(OPC_PUSHC, nmat, zero_slot);
       else if (b.lazy) emit(OPC_PUSHC, nmat, b.cslot);
       emit(OPC_UNARY, nmat, op);
+      if (stk.empty()) { slot0.valid = true; slot0.lazy = false; }
       push_mat();
     }
     // SB2_OP_POP_ONLY and anything else: pop only
@@ -292,7 +331,12 @@ int compile_stmt(sb2_sim* sim, const Sb2Stmt& st, std::vector<uint32_t>& prog) {
   // rate = top of the stack
   bool const_rate = false;
   int rate_cslot = zero_slot;
-  if (stk.empty()) const_rate = true;
+  if (stk.empty()) {
+    // stale bottom slot: a constant, or the value a materialised entry left in register 0 (nothing has overwritten it: every
+    // later store to the bottom of the stack updated slot0, and higher entries live in higher registers)
+    if (slot0.valid && slot0.lazy) { const_rate = true; rate_cslot = slot0.cslot; }
+    else if (!slot0.valid) const_rate = true;
+  }
   else if (stk.back().lazy) { const_rate = true; rate_cslot = stk.back().cslot; }
   else if (nmat - 1 != 0) emit(OPC_MOV0, nmat - 1, 0);
   if (too_deep) return fail(sim, SB2_ERR_LIMIT, "expression stack deeper than SB2_MAX_DEPTH");
@@ -621,6 +665,18 @@ void sb2_destroy(sb2_sim* sim) {
   }
   for (size_t i = 0; i < sim->transports.size(); ++i) sb2_free_transport(sim->transports[i]);
   sb2_free_boundary_lists(sim->blists);
+  for (size_t i = 0; i < sim->mem_reactions.size(); ++i) sb2_free_mem_reaction(sim->mem_reactions[i]);
+  for (size_t i = 0; i < sim->cell_rules.size(); ++i) sb2_free_cell_rule(sim->cell_rules[i]);
+  for (size_t i = 0; i < sim->point_sets.size(); ++i) {
+    cudaFree(sim->point_sets[i].d_fill_target); cudaFree(sim->point_sets[i].d_fill_a); cudaFree(sim->point_sets[i].d_fill_b);
+  }
+  for (size_t i = 0; i < sim->mem_species.size(); ++i) {
+    Sb2MemSpecies& ms = sim->mem_species[i];
+    cudaFree(ms.u);
+    for (int m = 0; m < 4; ++m) cudaFree(ms.k[m]);
+    cudaFree(ms.d_diff_pts); cudaFree(ms.d_term_start); cudaFree(ms.d_adj); cudaFree(ms.d_s); cudaFree(ms.d_d); cudaFree(ms.d_area);
+    cudaFree(ms.d_dvalues); cudaFree(ms.d_update_pts);
+  }
   if (sim->d_scratch) cudaFree(sim->d_scratch);
   if (sim->d_cls) cudaFree(sim->d_cls);
   if (sim->d_rdtok) cudaFree(sim->d_rdtok);
@@ -763,7 +819,175 @@ int sb2_add_mem_transport(sb2_sim* sim, const sb2_token* toks, int ntoks, const 
   int rc = sb2_build_transport(sim->g, sim->P, sim->PL, sim->first, (int)sim->species.size(), toks, ntoks, refs,
                                nrefs, n_reactants, pts, npts, operand_cells, operand_values, target_cells, sim->stream, t, err);
   if (rc) return fail(sim, rc, err);
+  for (int i = 0; i < ntoks; ++i)
+    if (toks[i].kind == SB2_TOK_MEMVAR && toks[i].slot >= sim->mem_species.size()) { sb2_free_transport(t); return fail(sim, SB2_ERR_ARG, "membrane transport: token references unknown membrane species"); }
+  for (int r = 0; r < nrefs; ++r)
+    if (refs[r].species >= SB2_MEM_SPECIES && refs[r].species - SB2_MEM_SPECIES >= (int)sim->mem_species.size()) { sb2_free_transport(t); return fail(sim, SB2_ERR_ARG, "membrane transport: reference to unknown membrane species"); }
   sim->transports.push_back(t);
+  sb2_sim::MemOp op = {0, (int)sim->transports.size() - 1};
+  sim->mem_ops.push_back(op);
+  return SB2_OK;
+}
+
+int sb2_add_point_set(sb2_sim* sim, int npts) {
+  if (!sim || npts < 0) return fail(sim, SB2_ERR_ARG, "bad point set");
+  if (sim->finalized) return fail(sim, SB2_ERR_STATE, "simulator already finalized");
+  if (sim->g.own_hi > sim->g.own_lo) return fail(sim, SB2_ERR_STATE, "membrane species are not supported on a slab of a sharded grid yet");
+  Sb2PointSet ps;
+  memset(&ps, 0, sizeof(ps));
+  ps.npts = npts;
+  sim->point_sets.push_back(ps);
+  return (int)sim->point_sets.size() - 1;
+}
+
+int sb2_add_mem_species(sb2_sim* sim, int set, const double* init) {
+  if (!sim || set < 0 || set >= (int)sim->point_sets.size()) return fail(sim, SB2_ERR_ARG, "unknown point set");
+  if (sim->finalized) return fail(sim, SB2_ERR_STATE, "simulator already finalized");
+  if (sim->mem_species.size() >= SB2_MAX_MEM_SPECIES) return fail(sim, SB2_ERR_LIMIT, "more than SB2_MAX_MEM_SPECIES membrane species");
+  cudaSetDevice(sim->g.device);
+  const int n = sim->point_sets[set].npts;
+  if (n > 0 && !init) return fail(sim, SB2_ERR_ARG, "null argument");
+  Sb2MemSpecies ms;
+  memset(&ms, 0, sizeof(ms));
+  ms.set = set;
+  const size_t bytes = sizeof(double) * (size_t)(n > 0 ? n : 1);
+  CK(cudaMalloc((void**)&ms.u, bytes));
+  CK(cudaMemsetAsync(ms.u, 0, bytes, sim->stream));
+  for (int m = 0; m < 4; ++m) {
+    CK(cudaMalloc((void**)&ms.k[m], bytes));
+    CK(cudaMemsetAsync(ms.k[m], 0, bytes, sim->stream));
+  }
+  if (n > 0) CK(cudaMemcpyAsync(ms.u, init, sizeof(double) * n, cudaMemcpyHostToDevice, sim->stream));
+  CK(cudaStreamSynchronize(sim->stream));
+  sim->mem_species.push_back(ms);
+  return (int)sim->mem_species.size() - 1;
+}
+
+int sb2_add_mem_reaction(sb2_sim* sim, int set, int kind, const sb2_token* toks, int ntoks, const sb2_ref* refs, int nrefs,
+                         int n_reactants, const int32_t* points, int npts, const double* operand_values) {
+  if (!sim || set < 0 || set >= (int)sim->point_sets.size()) return fail(sim, SB2_ERR_ARG, "unknown point set");
+  if (sim->finalized) return fail(sim, SB2_ERR_STATE, "simulator already finalized");
+  cudaSetDevice(sim->g.device);
+  Sb2MemReaction r;
+  std::string err;
+  int rc = sb2_build_mem_reaction(set, kind, toks, ntoks, refs, nrefs, n_reactants, points, npts, operand_values,
+                                  (int)sim->mem_species.size(), sim->point_sets[set].npts, sim->stream, r, err);
+  if (rc) return fail(sim, rc, err);
+  for (int i = 0; i < r.nrefs; ++i)
+    if (sim->mem_species[r.ref_species[i]].set != set) { sb2_free_mem_reaction(r); return fail(sim, SB2_ERR_ARG, "membrane reaction: species of another point set"); }
+  sim->mem_reactions.push_back(r);
+  sb2_sim::MemOp op = {1, (int)sim->mem_reactions.size() - 1};
+  sim->mem_ops.push_back(op);
+  return SB2_OK;
+}
+
+int sb2_set_mem_diffusion(sb2_sim* sim, int mem_species, int src_kind, int src, const double* d_values, const int32_t* points, int npts,
+                          const int32_t* term_start, const int32_t* adj, const double* s_ij, const double* d_ij, const double* area) {
+  if (!sim || mem_species < 0 || mem_species >= (int)sim->mem_species.size()) return fail(sim, SB2_ERR_ARG, "unknown membrane species");
+  if (sim->finalized) return fail(sim, SB2_ERR_STATE, "simulator already finalized");
+  if (npts < 0 || (npts > 0 && (!points || !term_start || !area))) return fail(sim, SB2_ERR_ARG, "null argument");
+  if (src_kind != SB2_SRC_CONST && src_kind != SB2_SRC_FIELD) return fail(sim, SB2_ERR_ARG, "membrane diffusion coefficient: bad source kind");
+  if (src_kind == SB2_SRC_CONST && (src < 0 || src >= SB2_MAX_CONSTS)) return fail(sim, SB2_ERR_ARG, "membrane diffusion coefficient: constant slot out of range");
+  if (src_kind == SB2_SRC_FIELD && npts > 0 && !d_values) return fail(sim, SB2_ERR_ARG, "membrane diffusion coefficient: values missing");
+  cudaSetDevice(sim->g.device);
+  Sb2MemSpecies& ms = sim->mem_species[mem_species];
+  if (ms.has_diff) return fail(sim, SB2_ERR_STATE, "membrane diffusion already set for this species");
+  const int set_n = sim->point_sets[ms.set].npts;
+  const int nterms = npts > 0 ? term_start[npts] : 0;
+  for (int p = 0; p < npts; ++p)
+    if (points[p] < 0 || points[p] >= set_n || term_start[p + 1] < term_start[p]) return fail(sim, SB2_ERR_ARG, "membrane diffusion: bad point list");
+  for (int t = 0; t < nterms; ++t)
+    if (adj[t] < 0 || adj[t] >= set_n) return fail(sim, SB2_ERR_ARG, "membrane diffusion: neighbour outside the point set");
+  ms.has_diff = true; ms.dkind = src_kind; ms.dsrc = src; ms.n_diff_pts = npts; ms.n_terms = nterms;
+  int rc;
+  if ((rc = upload_list(sim, &ms.d_diff_pts, points, (size_t)npts)) || (rc = upload_list(sim, &ms.d_term_start, term_start, (size_t)npts + 1)) ||
+      (rc = upload_list(sim, &ms.d_adj, adj, (size_t)nterms)) || (rc = upload_list(sim, &ms.d_s, s_ij, (size_t)nterms)) ||
+      (rc = upload_list(sim, &ms.d_d, d_ij, (size_t)nterms)) || (rc = upload_list(sim, &ms.d_area, area, (size_t)npts)))
+    return rc;
+  if (src_kind == SB2_SRC_FIELD && (rc = upload_list(sim, &ms.d_dvalues, d_values, (size_t)npts))) return rc;
+  return SB2_OK;
+}
+
+int sb2_set_mem_update_points(sb2_sim* sim, int mem_species, const int32_t* points, int npts) {
+  if (!sim || mem_species < 0 || mem_species >= (int)sim->mem_species.size()) return fail(sim, SB2_ERR_ARG, "unknown membrane species");
+  if (sim->finalized) return fail(sim, SB2_ERR_STATE, "simulator already finalized");
+  if (npts < 0 || (npts > 0 && !points)) return fail(sim, SB2_ERR_ARG, "null argument");
+  cudaSetDevice(sim->g.device);
+  Sb2MemSpecies& ms = sim->mem_species[mem_species];
+  const int set_n = sim->point_sets[ms.set].npts;
+  for (int p = 0; p < npts; ++p)
+    if (points[p] < 0 || points[p] >= set_n) return fail(sim, SB2_ERR_ARG, "membrane update list: point outside the point set");
+  if (ms.d_update_pts) { cudaFree(ms.d_update_pts); ms.d_update_pts = NULL; }
+  ms.n_update = npts;
+  return upload_list(sim, &ms.d_update_pts, points, (size_t)npts);
+}
+
+int sb2_set_mem_fill(sb2_sim* sim, int set, const int32_t* target, const int32_t* a, const int32_t* b, int n) {
+  if (!sim || set < 0 || set >= (int)sim->point_sets.size()) return fail(sim, SB2_ERR_ARG, "unknown point set");
+  if (sim->finalized) return fail(sim, SB2_ERR_STATE, "simulator already finalized");
+  if (n < 0 || (n > 0 && (!target || !a || !b))) return fail(sim, SB2_ERR_ARG, "null argument");
+  cudaSetDevice(sim->g.device);
+  Sb2PointSet& ps = sim->point_sets[set];
+  for (int i = 0; i < n; ++i)
+    if (target[i] < 0 || target[i] >= ps.npts || a[i] < 0 || a[i] >= ps.npts || b[i] < 0 || b[i] >= ps.npts)
+      return fail(sim, SB2_ERR_ARG, "pseudo-membrane fill: point outside the point set");
+  ps.n_fill = n;
+  int rc;
+  if ((rc = upload_list(sim, &ps.d_fill_target, target, (size_t)n)) || (rc = upload_list(sim, &ps.d_fill_a, a, (size_t)n)) ||
+      (rc = upload_list(sim, &ps.d_fill_b, b, (size_t)n)))
+    return rc;
+  return SB2_OK;
+}
+
+int sb2_add_assignment_rule(sb2_sim* sim, int target_kind, int target, int geo, const sb2_token* toks, int ntoks) {
+  if (!sim || (!toks && ntoks > 0) || ntoks < 0) return fail(sim, SB2_ERR_ARG, "null argument");
+  if (sim->finalized) return fail(sim, SB2_ERR_STATE, "simulator already finalized");
+  if (target_kind == 0 && (target < 0 || target >= (int)sim->d_fields.size())) return fail(sim, SB2_ERR_ARG, "assignment rule: unknown field");
+  if (target_kind == 1 && (target < 0 || target >= (int)sim->species.size())) return fail(sim, SB2_ERR_ARG, "assignment rule: unknown species");
+  if (target_kind != 0 && target_kind != 1) return fail(sim, SB2_ERR_ARG, "assignment rule: bad target kind");
+  if (geo >= (int)sim->d_flags.size()) return fail(sim, SB2_ERR_ARG, "assignment rule: unknown geometry");
+  for (int i = 0; i < ntoks; ++i) {
+    if (toks[i].kind == SB2_TOK_VAR && toks[i].slot >= sim->species.size()) return fail(sim, SB2_ERR_ARG, "assignment rule: token references unknown species");
+    if (toks[i].kind == SB2_TOK_FIELD && toks[i].slot >= sim->d_fields.size()) return fail(sim, SB2_ERR_ARG, "assignment rule: token references unknown field");
+    if (toks[i].kind == SB2_TOK_CONST && toks[i].slot >= SB2_MAX_CONSTS) return fail(sim, SB2_ERR_ARG, "assignment rule: constant slot out of range");
+    if (toks[i].kind == SB2_TOK_MEMVAR) return fail(sim, SB2_ERR_ARG, "assignment rule: membrane species operands are not supported");
+  }
+  cudaSetDevice(sim->g.device);
+  Sb2CellRule r;
+  std::string err;
+  int rc = sb2_build_cell_rule(toks, ntoks, target_kind, target, geo, sim->stream, r, err);
+  if (rc) return fail(sim, rc, err);
+  sim->cell_rules.push_back(r);
+  return SB2_OK;
+}
+
+int sb2_download_mem_species(sb2_sim* sim, int mem_species, double* out) {
+  if (!sim || !out || mem_species < 0 || mem_species >= (int)sim->mem_species.size()) return fail(sim, SB2_ERR_ARG, "bad membrane species");
+  cudaSetDevice(sim->g.device);
+  const Sb2MemSpecies& ms = sim->mem_species[mem_species];
+  const int n = sim->point_sets[ms.set].npts;
+  if (n > 0) CK(cudaMemcpyAsync(out, ms.u, sizeof(double) * n, cudaMemcpyDeviceToHost, sim->stream));
+  CK(cudaStreamSynchronize(sim->stream));
+  return SB2_OK;
+}
+
+int sb2_upload_mem_species(sb2_sim* sim, int mem_species, const double* in) {
+  if (!sim || !in || mem_species < 0 || mem_species >= (int)sim->mem_species.size()) return fail(sim, SB2_ERR_ARG, "bad membrane species");
+  cudaSetDevice(sim->g.device);
+  const Sb2MemSpecies& ms = sim->mem_species[mem_species];
+  const int n = sim->point_sets[ms.set].npts;
+  if (n > 0) CK(cudaMemcpyAsync(ms.u, in, sizeof(double) * n, cudaMemcpyHostToDevice, sim->stream));
+  CK(cudaStreamSynchronize(sim->stream));
+  return SB2_OK;
+}
+
+int sb2_download_mem_stage(sb2_sim* sim, int mem_species, int m, double* out) {
+  if (!sim || !out || mem_species < 0 || mem_species >= (int)sim->mem_species.size() || m < 0 || m > 3) return fail(sim, SB2_ERR_ARG, "bad membrane species / stage");
+  cudaSetDevice(sim->g.device);
+  const Sb2MemSpecies& ms = sim->mem_species[mem_species];
+  const int n = sim->point_sets[ms.set].npts;
+  if (n > 0) CK(cudaMemcpyAsync(out, ms.k[m], sizeof(double) * n, cudaMemcpyDeviceToHost, sim->stream));
+  CK(cudaStreamSynchronize(sim->stream));
   return SB2_OK;
 }
 
@@ -946,24 +1170,39 @@ int sb2_stage(sb2_sim* sim, int m, int phase) {
   const double dt = sim->cur_dt;
 
   if (phase == 0 || phase == 1) {
-    // membrane transport first: its flux is the carry-in of the stage accumulators
+    static const double rk[4] = {0.0, 0.5, 0.5, 1.0};
+    // membrane transport first: its flux is the carry-in of the stage accumulators of the volume species
     if (!sim->transports.empty()) {
       for (size_t s = 0; s < sim->species.size(); ++s) {
         if (sim->carry_k0 && m == 0) continue;  // k0 already holds the carried Neumann flux
         CK(cudaMemsetAsync(sim->species[s].k[m], 0, sizeof(double) * sim->nalloc, sim->stream));
       }
-      for (size_t i = 0; i < sim->transports.size(); ++i) {
-        std::vector<const double*> u(sim->species.size()), kp(sim->species.size());
-        std::vector<double*> ko(sim->species.size());
-        for (size_t s = 0; s < sim->species.size(); ++s) {
-          u[s] = sim->species[s].u[sim->species[s].cur];
-          kp[s] = m > 0 ? sim->species[s].k[m - 1] : NULL;
-          ko[s] = sim->species[s].k[m];
-        }
-        static const double rk[4] = {0.0, 0.5, 0.5, 1.0};
-        cudaError_t e = sb2_launch_transport(sim->transports[i], sim->g, u.data(), kp.data(), ko.data(), sim->consts, m,
-                                             rk[m] * dt, sim->stream, &sim->launches);
-        if (e != cudaSuccess) return cuda_fail(sim, e, "membrane transport kernels");
+    }
+    // transports and membrane reactions in the order of the reference's reaction list (what a membrane species receives
+    // adds up in that order), then surface diffusion (spatialsimulator.cpp:1369-1479)
+    if (!sim->mem_ops.empty() || !sim->mem_species.empty()) {
+      const Sb2MemView mv = mem_view(sim);
+      const double* mu[SB2_MAX_MEM_SPECIES]; const double* mkp[SB2_MAX_MEM_SPECIES]; double* mko[SB2_MAX_MEM_SPECIES];
+      for (int i = 0; i < SB2_MAX_MEM_SPECIES; ++i) { mu[i] = mv.u[i]; mkp[i] = m > 0 ? mv.k[i][m - 1] : NULL; mko[i] = mv.k[i][m]; }
+      std::vector<const double*> u(sim->species.size()), kp(sim->species.size());
+      std::vector<double*> ko(sim->species.size());
+      for (size_t s = 0; s < sim->species.size(); ++s) {
+        u[s] = sim->species[s].u[sim->species[s].cur];
+        kp[s] = m > 0 ? sim->species[s].k[m - 1] : NULL;
+        ko[s] = sim->species[s].k[m];
+      }
+      for (size_t i = 0; i < sim->mem_ops.size(); ++i) {
+        cudaError_t e;
+        if (sim->mem_ops[i].type == 0)
+          e = sb2_launch_transport(sim->transports[sim->mem_ops[i].index], sim->g, u.data(), kp.data(), ko.data(), mu, mkp, mko, sim->consts, m,
+                                   rk[m] * dt, sim->stream, &sim->launches);
+        else
+          e = sb2_launch_mem_reaction(sim->mem_reactions[sim->mem_ops[i].index], mv, sim->consts, m, rk[m] * dt, sim->stream, &sim->launches);
+        if (e != cudaSuccess) return cuda_fail(sim, e, "membrane transport / reaction kernels");
+      }
+      for (size_t i = 0; i < sim->mem_species.size(); ++i) {
+        cudaError_t e = sb2_launch_mem_diffusion(sim->mem_species[i], (int)i, mv, sim->consts, m, rk[m] * dt, sim->g.dim, sim->stream, &sim->launches);
+        if (e != cudaSuccess) return cuda_fail(sim, e, "membrane diffusion kernel");
       }
     }
   }
@@ -1060,6 +1299,34 @@ int sb2_end_step(sb2_sim* sim) {
                                        sim->stream, &sim->launches);
     if (e != cudaSuccess) return cuda_fail(sim, e, "boundary kernels");
   }
+  // species on membranes: RK4 update on the points of their geometry (updateSpecies, spatialsimulator.cpp:1526-1537)
+  if (!sim->mem_species.empty()) {
+    const Sb2MemView mv = mem_view(sim);
+    for (size_t i = 0; i < sim->mem_species.size(); ++i) {
+      cudaError_t e = sb2_launch_mem_update(sim->mem_species[i], (int)i, mv, dt, sim->stream, &sim->launches);
+      if (e != cudaSuccess) return cuda_fail(sim, e, "membrane species update kernel");
+    }
+  }
+  // assignment rules in dependency order (updateAssignmentRules, spatialsimulator.cpp:1566-1581), on the new values
+  for (size_t i = 0; i < sim->cell_rules.size(); ++i) {
+    const Sb2CellRule& r = sim->cell_rules[i];
+    Sb2CellRuleArgs a;
+    memset(&a, 0, sizeof(a));
+    a.nx = sim->g.nx; a.ny = sim->g.ny; a.nz = sim->g.nz; a.P = sim->P; a.PL = sim->PL; a.first = sim->first;
+    a.ntoks = r.ntoks; a.tok = r.d_tok;
+    a.out = r.target_kind == 1 ? sim->species[r.target].u[sim->species[r.target].cur] : sim->d_fields[r.target];
+    a.mask = r.geo >= 0 ? sim->d_flags[r.geo] : NULL;
+    for (size_t q = 0; q < S; ++q) a.species[q] = sim->species[q].u[sim->species[q].cur];
+    for (size_t f = 0; f < sim->d_fields.size(); ++f) a.fields[f] = sim->d_fields[f];
+    memcpy(a.consts, sim->consts, sizeof(a.consts));
+    cudaError_t e = sb2_launch_cell_rule(a, sim->stream, &sim->launches);
+    if (e != cudaSuccess) return cuda_fail(sim, e, "assignment rule kernel");
+  }
+  // pseudo-membrane points take the smaller of their two membrane neighbours (spatialsimulator.cpp:1614-1663)
+  for (size_t i = 0; i < sim->mem_species.size(); ++i) {
+    cudaError_t e = sb2_launch_mem_fill(sim->point_sets[sim->mem_species[i].set], sim->mem_species[i].u, sim->stream, &sim->launches);
+    if (e != cudaSuccess) return cuda_fail(sim, e, "pseudo-membrane fill kernel");
+  }
   sim->k0_carry_valid = sim->carry_k0;
   sim->in_step = false;
   return SB2_OK;
@@ -1149,7 +1416,7 @@ int sb2_step_host(sb2_sim* sim, double t_arg, double dt, int time_slot, const do
   if (sim->g.own_hi > sim->g.own_lo) return fail(sim, SB2_ERR_STATE, "sb2_step_host needs a handle that owns its whole grid");
   int rc = sb2_begin_step(sim, t_arg, dt, time_slot);
   if (rc) return rc;
-  if (!sim->fuse_combine || !sim->transports.empty() || sim->blists.n_dirichlet > 0) {
+  if (!sim->fuse_combine || !sim->transports.empty() || sim->blists.n_dirichlet > 0 || !sim->mem_species.empty() || !sim->cell_rules.empty()) {
     sim->in_step = false;
     return fail(sim, SB2_ERR_STATE, "sb2_step_host: the model needs the unfused schedule (advection, membrane transport, non-zero flux or Dirichlet)");
   }
@@ -1238,6 +1505,12 @@ int sb2_download_stage(sb2_sim* sim, int species, int m, double* out) {
   return download_padded<double>(sim, out, sim->species[species].k[m]);
 }
 
+int sb2_download_field(sb2_sim* sim, int field, double* out) {
+  if (!sim || !out || field < 0 || field >= (int)sim->d_fields.size()) return fail(sim, SB2_ERR_ARG, "bad field");
+  cudaSetDevice(sim->g.device);
+  return download_padded<double>(sim, out, sim->d_fields[field]);
+}
+
 int sb2_upload_field(sb2_sim* sim, int field, const double* in) {
   if (!sim || !in || field < 0 || field >= (int)sim->d_fields.size()) return fail(sim, SB2_ERR_ARG, "bad field");
   cudaSetDevice(sim->g.device);
@@ -1292,6 +1565,12 @@ int sb2_min_dt(sb2_sim* sim, double dt, double* out) {
     double r = dt;
     cudaError_t e = sb2_launch_min_dt(a, sim->d_scratch, sim->stream, &sim->launches, &r);
     if (e != cudaSuccess) return cuda_fail(sim, e, "min-dt reduction");
+    if (r < best) best = r;
+  }
+  for (size_t i = 0; i < sim->mem_species.size(); ++i) {  // checkMemDiffusionStab
+    double r = dt;
+    cudaError_t e = sb2_launch_mem_min_dt(sim->mem_species[i], sim->consts, dt, sim->d_scratch, sim->stream, &sim->launches, &r);
+    if (e != cudaSuccess) return cuda_fail(sim, e, "membrane min-dt reduction");
     if (r < best) best = r;
   }
   *out = best;

@@ -43,7 +43,7 @@ void parallelRanges(int64_t n, int64_t grain, F f) {
 Var::Var()
     : sp(NULL), com(NULL), para(NULL), hasValue(false), isUniform(false), isResolved(false), inVol(true),
       hasDelta(false), hasAssignmentRule(false), uniformValue(0.0), offGridInit(0.0), geo(NULL), hasDiff(false),
-      hasAdv(false), hasBC(false), hasRpn(false), constSlot(-1), fieldId(-1), speciesId(-1) {
+      hasAdv(false), hasBC(false), hasRpn(false), onMembrane(false), constSlot(-1), fieldId(-1), speciesId(-1), memSpeciesId(-1) {
   for (int i = 0; i < 3; ++i) { diffC[i] = NULL; advC[i] = NULL; }
   for (int i = 0; i < 6; ++i) { bc[i] = NULL; bcKind[i] = SB2_BC_NONE; }
 }
@@ -72,6 +72,55 @@ Geo* Model::geoByCompartment(const std::string& id) const {
 Geo* Model::geoByDomainType(const std::string& id) const {
   for (size_t i = 0; i < geos.size(); ++i) if (geos[i]->domainTypeId == id) return geos[i];
   return NULL;
+}
+
+int Geo::storageOf(int64_t idx) const {
+  std::vector<int64_t>::const_iterator it = std::lower_bound(storage.begin(), storage.end(), idx);
+  return (it != storage.end() && *it == idx) ? (int)(it - storage.begin()) : -1;
+}
+
+// What the reference's full doubled-grid array of a variable holds at one point when the model is set up: coordinates are
+// analytic, a parameter with an initial assignment / assignment rule was evaluated at EVERY point (isAllArea, calcPDE.cpp:28),
+// a volume species was flooded with its initial value and later assigned / zeroed at volume cells only, a membrane species
+// lives on the points of its membrane.
+double Model::valueAtDoubled(const Var* v, int X, int Y, int Z, int depth) const {
+  if (!v || !v->hasValue) return 0.0;
+  if (v->isUniform) return v->uniformValue;
+  if (v == xVar) return coordinateAt(v, X);
+  if (v == yVar) return coordinateAt(v, Y);
+  if (v == zVar) return coordinateAt(v, Z);
+  const int64_t idx = ((int64_t)Z * Yindex + Y) * Xindex + X;
+  if (v->onMembrane) {
+    const int k = v->geo ? v->geo->storageOf(idx) : -1;
+    return k >= 0 && (size_t)k < v->field.size() ? v->field[k] : 0.0;
+  }
+  if (!((X | Y | Z) & 1)) {
+    const int i = X / 2, j = Y / 2 - off[1], k = Z / 2 - off[2];
+    if (i >= 0 && i < nx && j >= 0 && j < ny && k >= 0 && k < nz) return v->field[((int64_t)k * ny + j) * nx + i];
+    return v->offGridInit;
+  }
+  if (!v->sp && v->hasRpn && depth < 8) {
+    double st[64] = {0}, out = v->offGridInit;
+    evalRpnAtPoint(v->rpn, X, Y, Z, st, &out, depth + 1);
+    return out;
+  }
+  return v->offGridInit;
+}
+
+bool Model::evalRpnAtPoint(const Rpn& rpn, int X, int Y, int Z, double* st, double* out, int depth) const {
+  int sp = 0;
+  for (size_t i = 0; i < rpn.size(); ++i) {
+    const Tok& t = rpn[i];
+    if (t.kind == Tok::VAR) { st[sp++] = valueAtDoubled(t.var, X, Y, Z, depth); if (sp > 60) sp = 60; continue; }
+    if (t.kind == Tok::CONSTVAR) { st[sp++] = t.var->uniformValue; if (sp > 60) sp = 60; continue; }
+    if (t.kind == Tok::LITERAL) { st[sp++] = t.literal; if (sp > 60) sp = 60; continue; }
+    if (sp > 0) --sp;
+    if (t.kind != Tok::OP) continue;
+    rpnApplyOp(t.astType, st, sp);
+    if (sp > 60) sp = 60;
+  }
+  if (sp > 0) { *out = st[--sp]; return true; }
+  return false;
 }
 
 namespace {
@@ -158,8 +207,9 @@ void Model::setSpecies() {
       if (s->isSetInitialAmount() || s->isSetInitialConcentration()) {
         const double init = s->isSetInitialAmount() ? s->getInitialAmount() : s->getInitialConcentration();
         v->hasValue = true;
-        v->field.assign(ncells(), init);  // the reference floods every doubled-grid point
-        v->offGridInit = init;
+        v->onMembrane = !v->inVol && v->com && memDimension != 0 && v->com->getSpatialDimensions() == memDimension;
+        if (!v->onMembrane) v->field.assign(ncells(), init);  // the reference floods every doubled-grid point
+        v->offGridInit = init;                                // (membrane species: sized by allocateMembraneFields)
         v->hasDelta = speciesIsVariable(s);
         v->isResolved = true;
       }
@@ -623,6 +673,27 @@ void Model::setMembraneGeometries() {
   }
 }
 
+// Storage of the species that live on a membrane: one value per membrane point, pseudo-membrane point and any other point the
+// membrane's domainIndex names (its 2-D frame quirk), in ascending doubled-grid index.
+void Model::allocateMembraneFields() {
+  for (size_t gi = 0; gi < geos.size(); ++gi) {
+    Geo* g = geos[gi];
+    if (g->isVol) continue;
+    std::set<int64_t> pts;
+    for (size_t k = 0; k < g->memPoints.size(); ++k) pts.insert(g->memPoints[k].index);
+    for (size_t k = 0; k < g->pseudoMemIndex.size(); ++k) pts.insert(g->pseudoMemIndex[k]);
+    for (size_t k = 0; k < g->memDomainIndex.size(); ++k) pts.insert(g->memDomainIndex[k]);
+    for (std::unordered_map<int64_t, uint8_t>::const_iterator it = g->memClass.begin(); it != g->memClass.end(); ++it) pts.insert(it->first);
+    g->storage.assign(pts.begin(), pts.end());
+  }
+  for (size_t i = 0; i < vars.size(); ++i) {
+    Var* v = vars[i];
+    if (!v->onMembrane || !v->sp) continue;
+    v->geo = geoByCompartment(v->sp->getCompartment());
+    v->field.assign(v->geo ? v->geo->storage.size() : 0, v->offGridInit);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // initial assignments / assignment rules in dependency order (spatialsimulator.cpp:1051-1153)
 // ---------------------------------------------------------------------------------------------
@@ -645,7 +716,13 @@ bool Model::resolveAssignments() {
     }
     if (!v->hasValue) {
       v->hasValue = true;
-      v->field.assign(nc, 0.0);
+      v->onMembrane = v->sp && !v->inVol && v->com && memDimension != 0 && v->com->getSpatialDimensions() == memDimension;
+      if (v->onMembrane) {
+        v->geo = geoByCompartment(v->sp->getCompartment());
+        v->field.assign(v->geo ? v->geo->storage.size() : 0, 0.0);
+      } else {
+        v->field.assign(nc, 0.0);
+      }
       v->offGridInit = 0.0;
       if (v->sp && speciesIsVariable(v->sp)) v->hasDelta = true;
     }
@@ -687,6 +764,17 @@ bool Model::resolveAssignments() {
         std::vector<uint8_t> mask(nc);
         for (int64_t c = 0; c < nc; ++c) mask[c] = v->geo->isDomain[c] == 1;
         evalRpnCompact(v->rpn, mask.data(), nc, v->field.data());
+      } else if (v->geo && !v->geo->isVol && v->onMembrane) {
+        // membrane species: the points its membrane's domainIndex names, in that order, with one stack for the whole sweep
+        double st[64] = {0};
+        const int64_t Xi = Xindex, Yi = Yindex;
+        for (size_t q = 0; q < v->geo->memDomainIndex.size(); ++q) {
+          const int64_t idx = v->geo->memDomainIndex[q];
+          const int k = v->geo->storageOf(idx);
+          if (k < 0) continue;
+          const int Z = (int)(idx / (Xi * Yi)), Y = (int)((idx - (int64_t)Z * Xi * Yi) / Xi), X = (int)(idx - (int64_t)Z * Xi * Yi - (int64_t)Y * Xi);
+          evalRpnAtPoint(v->rpn, X, Y, Z, st, &v->field[k]);
+        }
       }
       v->isResolved = true;
       if (v->hasAssignmentRule) orderedAssignmentRules.push_back(v);
@@ -877,6 +965,190 @@ void Model::setNormals() {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Voronoi neighbours of the membrane points: contour neighbours one step away in each plane the point's membrane crosses,
+// their distance d_ij measured in the tangent plane and (3-D) the facet length s_ij, then the symmetrising average
+// (setVoronoiInfo, setInfoFunction.cpp:1134-1546)
+// ---------------------------------------------------------------------------------------------
+void Model::setVoronoi() {
+  if (dimension < 2 || !xVar || !yVar || (dimension == 3 && !zVar)) return;
+  const int64_t Xi = Xindex, Yi = Yindex;
+  const int64_t total = ndoubled();
+  const int64_t stride[3] = {1, Xi, Xi * Yi};
+  struct P3 { double x, y, z; };
+  for (size_t gi = 0; gi < geos.size(); ++gi) {
+    Geo* g = geos[gi];
+    if (g->isVol || g->memPoints.empty()) continue;
+    std::map<int64_t, size_t> pointOf;
+    for (size_t k = 0; k < g->memPoints.size(); ++k) pointOf[g->memPoints[k].index] = k;
+    std::unordered_map<int64_t, std::vector<P3> > contour;  // planeAdjacent: projected neighbours, [XY0, XY1, YZ0, YZ1, XZ0, XZ1]
+    int planeH[3][2] = {{0, 0}, {0, 0}, {0, 0}}, planeV[3][2] = {{0, 0}, {0, 0}, {0, 0}};  // persist across points like the reference's locals
+    const size_t M = g->memDomainIndex.size();
+    auto crosses = [](const MemPoint& p, int pl) {
+      const bool bx = (p.bof & SB2_F_XP) && (p.bof & SB2_F_XM), by = (p.bof & SB2_F_YP) && (p.bof & SB2_F_YM),
+                 bz = (p.bof & SB2_F_ZP) && (p.bof & SB2_F_ZM);
+      return pl == 0 ? (bx || by) : pl == 1 ? (by || bz) : (bx || bz);
+    };
+    auto X_of = [&](int64_t idx) { return (int)(idx % Xi); };
+    auto Y_of = [&](int64_t idx) { return (int)((idx / Xi) % Yi); };
+    auto Z_of = [&](int64_t idx) { return (int)(idx / (Xi * Yi)); };
+    auto xAt = [&](int64_t idx) { return coordinateAt(xVar, X_of(idx)); };
+    auto yAt = [&](int64_t idx) { return coordinateAt(yVar, Y_of(idx)); };
+    auto zAt = [&](int64_t idx) { return zVar ? coordinateAt(zVar, Z_of(idx)) : 0.0; };
+    // planes: 0 = xy (hor X, ver Y), 1 = yz (hor Y, ver Z), 2 = xz (hor X, ver Z)
+    const int hAxis[3] = {0, 1, 0}, vAxis[3] = {1, 2, 2};
+    // --- neighbours and d_ij (:1160-1232)
+    for (size_t j = 0; j < M; ++j) {
+      const int64_t index = g->memDomainIndex[j];
+      std::map<int64_t, size_t>::const_iterator pit = pointOf.find(index);
+      if (pit == pointOf.end()) continue;  // an entry that is no membrane point has an all-false bType: no plane
+      const MemPoint& p = g->memPoints[pit->second];
+      const int co[3] = {p.X, p.Y, p.Z};
+      Geo::Voronoi& v = g->voronoi[index];
+      std::vector<P3>& ct = contour[index];
+      if (ct.empty()) ct.assign(6, P3{0.0, 0.0, 0.0});
+      for (int pl = 0; pl < (dimension == 3 ? 3 : 1); ++pl) {
+        if (!crosses(p, pl)) continue;
+        PlaneWalker w;
+        w.g = g; w.total = total; w.sh = stride[hAxis[pl]]; w.sv = stride[vAxis[pl]];
+        w.ends(index, co[hAxis[pl]], co[vAxis[pl]], 1, planeH[pl], planeV[pl]);
+        for (int l = 0; l < 2; ++l) {
+          int q[3] = {co[0], co[1], co[2]};
+          q[hAxis[pl]] = planeH[pl][l];
+          q[vAxis[pl]] = planeV[pl][l];
+          const int64_t aidx = (int64_t)q[2] * Xi * Yi + (int64_t)q[1] * Xi + q[0];
+          v.adj[2 * pl + l] = aidx;
+          double inner;
+          if (dimension == 2) inner = p.nx * (xAt(aidx) - xAt(index)) + p.ny * (yAt(aidx) - yAt(index));
+          else inner = p.nx * (xAt(aidx) - xAt(index)) + p.ny * (yAt(aidx) - yAt(index)) + p.nz * (zAt(aidx) - zAt(index));
+          P3& c = ct[2 * pl + l];
+          c.x = xAt(aidx) - p.nx * inner;
+          c.y = yAt(aidx) - p.ny * inner;
+          if (dimension == 2) {
+            v.di[2 * pl + l] = sqrt(pow(xAt(index) - c.x, 2) + pow(yAt(index) - c.y, 2));
+          } else {
+            c.z = zAt(aidx) - p.nz * inner;
+            v.di[2 * pl + l] = sqrt(pow(xAt(index) - c.x, 2) + pow(yAt(index) - c.y, 2) + pow(zAt(index) - c.z, 2));
+          }
+        }
+      }
+    }
+    // --- s_ij: the tangent plane is rotated into z = const and the perpendicular bisectors of neighbouring planes are
+    // intersected (3-D only, :1234-1430)
+    if (dimension == 3) {
+      for (size_t j = 0; j < M; ++j) {
+        const int64_t index = g->memDomainIndex[j];
+        std::map<int64_t, size_t>::const_iterator pit = pointOf.find(index);
+        if (pit == pointOf.end()) continue;
+        const MemPoint& p = g->memPoints[pit->second];
+        Geo::Voronoi& v = g->voronoi[index];
+        const std::vector<P3>& ct = contour[index];
+        const double phi = atan2(p.ny, p.nx), theta = acos(p.nz);
+        const double rix = cos(theta) * (xAt(index) * cos(phi) + yAt(index) * sin(phi)) - zAt(index) * sin(theta);
+        const double riy = -xAt(index) * sin(phi) + yAt(index) * cos(phi);
+        double rx[6], ry[6];
+        for (int q = 0; q < 6; ++q) {
+          rx[q] = cos(theta) * (ct[q].x * cos(phi) + ct[q].y * sin(phi)) - ct[q].z * sin(theta);
+          ry[q] = -ct[q].x * sin(phi) + ct[q].y * cos(phi);
+        }
+        // facet lengths of plane A against the two neighbours of plane B
+        auto facets = [&](int A, int B) {
+          for (int l = 0; l < 2; ++l) {
+            double Px[4], Py[4], cpx[2], cpy[2];
+            Px[0] = (rx[2 * A + l] + rix) / 2.0;
+            Py[0] = (ry[2 * A + l] + riy) / 2.0;
+            Px[2] = -(ry[2 * A + l] - riy) + Px[0];
+            Py[2] = (rx[2 * A + l] - rix) + Py[0];
+            for (int k = 0; k < 2; ++k) {
+              Px[1] = (rx[2 * B + k] + rix) / 2.0;
+              Py[1] = (ry[2 * B + k] + riy) / 2.0;
+              Px[3] = -(ry[2 * B + k] - riy) + Px[1];
+              Py[3] = (rx[2 * B + k] - rix) + Py[1];
+              const double a013 = ((Px[3] - Px[1]) * (Py[0] - Py[1]) - (Py[3] - Py[1]) * (Px[0] - Px[1])) / 2.0;
+              const double a123 = ((Px[3] - Px[1]) * (Py[1] - Py[2]) - (Py[3] - Py[1]) * (Px[1] - Px[2])) / 2.0;
+              cpx[k] = Px[0] + ((Px[2] - Px[0]) * a013) / (a013 + a123);
+              cpy[k] = Py[0] + ((Py[2] - Py[0]) * a013) / (a013 + a123);
+            }
+            v.si[2 * A + l] = sqrt(pow(cpx[0] - cpx[1], 2) + pow(cpy[0] - cpy[1], 2));
+          }
+        };
+        const bool pxy = crosses(p, 0), pyz = crosses(p, 1), pxz = crosses(p, 2);
+        if (pxy && pyz) { facets(0, 1); facets(1, 0); }
+        if (pxy && pxz) { facets(0, 2); facets(2, 0); }
+        if (pyz && pxz) { facets(1, 2); facets(2, 1); }
+      }
+    }
+    // --- d_ij and s_ij are averaged with the neighbour's view of the same edge (:1476-1540).  When the neighbour does not list
+    // this point (k runs to 2) the reference reuses the d_ji / s_ji of the previous edge and writes one slot past the
+    // neighbour's pair, which in voronoiInfo's layout is the first slot of the next plane; both are mirrored here for the
+    // xy and yz planes (the xz overflow leaves the struct).
+    double d_ji = 0.0, s_ji = 0.0;
+    for (size_t j = 0; j < M; ++j) {
+      const int64_t index = g->memDomainIndex[j];
+      std::map<int64_t, size_t>::const_iterator pit = pointOf.find(index);
+      if (pit == pointOf.end()) continue;
+      const MemPoint& p = g->memPoints[pit->second];
+      for (int pl = 0; pl < (dimension == 3 ? 3 : 1); ++pl) {
+        if (!crosses(p, pl)) continue;
+        for (int l = 0; l < 2; ++l) {
+          Geo::Voronoi& v = g->voronoi[index];
+          if (v.isAve[2 * pl + l]) continue;
+          const int64_t aidx = v.adj[2 * pl + l];
+          if (aidx < 0) continue;
+          const double d_ij = v.di[2 * pl + l], s_ij = v.si[2 * pl + l];
+          Geo::Voronoi& o = g->voronoi[aidx];
+          int k = 0;
+          for (; k < 2; ++k)
+            if (index == o.adj[2 * pl + k]) { d_ji = o.di[2 * pl + k]; s_ji = o.si[2 * pl + k]; break; }
+          Geo::Voronoi& v2 = g->voronoi[index];  // (operator[] above may have rehashed)
+          v2.di[2 * pl + l] = (d_ij + d_ji) / 2.0;
+          v2.si[2 * pl + l] = (s_ij + s_ji) / 2.0;
+          v2.isAve[2 * pl + l] = true;
+          const int slot = 2 * pl + k;
+          if (slot < 6) {
+            Geo::Voronoi& o2 = g->voronoi[aidx];
+            o2.di[slot] = v2.di[2 * pl + l];
+            o2.si[slot] = v2.si[2 * pl + l];
+            o2.isAve[slot] = true;
+          }
+        }
+      }
+    }
+  }
+}
+
+// Pseudo-membrane fill: which two membrane points a pseudo-membrane point takes the minimum of.  The same cascade of tests
+// appears in setBoundaryType (boundaryFunction.cpp:98-111, 173-203: every point classified 2) and in updateAssignmentRules
+// (spatialsimulator.cpp:1614-1663: the points of pseudoMemIndex, in list order).  Lists are in storage indices of the geometry.
+void pseudoFillPairs(const Model& m, const Geo* g, bool everyClassifiedPoint, std::vector<int32_t>& target, std::vector<int32_t>& a,
+                     std::vector<int32_t>& b) {
+  target.clear(); a.clear(); b.clear();
+  std::vector<int64_t> pts;
+  if (everyClassifiedPoint) {
+    for (std::unordered_map<int64_t, uint8_t>::const_iterator it = g->memClass.begin(); it != g->memClass.end(); ++it)
+      if (it->second == 2) pts.push_back(it->first);
+    std::sort(pts.begin(), pts.end());
+  } else {
+    pts = g->pseudoMemIndex;
+  }
+  const int64_t Xi = m.Xindex, Yi = m.Yindex, total = m.ndoubled();
+  for (size_t q = 0; q < pts.size(); ++q) {
+    const int64_t idx = pts[q];
+    // flat-index arithmetic as in the reference (no bounds tests); points outside the array read as "not a membrane point"
+    const int64_t n[6] = {idx + 1, idx - 1, idx + Xi, idx - Xi, idx + Xi * Yi, idx - Xi * Yi};  // Xp Xm Yp Ym Zp Zm
+    bool is1[6];
+    for (int k = 0; k < 6; ++k) is1[k] = n[k] >= 0 && n[k] < total && g->memIsDomain(n[k]) == 1;
+    if (m.dimension != 3) is1[4] = is1[5] = false;
+    static const int order[15][2] = {{0, 1}, {2, 3}, {4, 5}, {0, 2}, {0, 3}, {0, 4}, {0, 5}, {1, 2}, {1, 3}, {1, 4}, {1, 5}, {2, 4}, {2, 5}, {3, 4}, {3, 5}};
+    for (int c = 0; c < 15; ++c) {
+      if (!(is1[order[c][0]] && is1[order[c][1]])) continue;
+      const int t = g->storageOf(idx), sa = g->storageOf(n[order[c][0]]), sb = g->storageOf(n[order[c][1]]);
+      if (t >= 0 && sa >= 0 && sb >= 0) { target.push_back(t); a.push_back(sa); b.push_back(sb); }
+      break;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // boundary types of the volumes that host spatial species (setBoundaryType, boundaryFunction.cpp:13-217)
 // ---------------------------------------------------------------------------------------------
 void Model::setBoundaryTypes() {
@@ -890,8 +1162,12 @@ void Model::setBoundaryTypes() {
     v->geo = g;
     if (!g->hasMask) continue;
     if (!g->isVol) {
-      // membrane species: value outside the membrane is zeroed and pseudo-membrane points take the
-      // minimum of their neighbours; membrane fields live on sparse points (not staged on the device yet)
+      // membrane species (boundaryFunction.cpp:89-118, 170-210): values off the membrane are zero (they have no storage
+      // here), pseudo-membrane points take the smaller of two neighbouring membrane points
+      if (!v->onMembrane || !v->hasValue) continue;
+      std::vector<int32_t> t, a, b;
+      pseudoFillPairs(*this, g, true, t, a, b);
+      for (size_t q = 0; q < t.size(); ++q) v->field[t[q]] = std::min(v->field[a[q]], v->field[b[q]]);
       continue;
     }
     if (v->hasValue) {
@@ -1073,6 +1349,7 @@ bool Model::build(SBMLDocument* d, int xdim, int ydim, int zdim, int slabLo, int
   if (!setVolumeGeometries()) return false;
   lap("volume geometries");
   setMembraneGeometries();
+  allocateMembraneFields();
   lap("membrane geometries");
   if (!resolveAssignments()) return false;
   lap("assignments");
@@ -1087,7 +1364,10 @@ bool Model::build(SBMLDocument* d, int xdim, int ydim, int zdim, int slabLo, int
   for (size_t i = 0; i < rxns.size(); ++i) needNormals = needNormals || rxns[i]->isMemTransport;
   for (size_t i = 0; i < vars.size(); ++i)
     needNormals = needNormals || (vars[i]->sp && !vars[i]->isUniform && vars[i]->geo && !vars[i]->geo->isVol);
-  if (needNormals) setNormals();
+  if (needNormals) {
+    setNormals();
+    setVoronoi();
+  }
   return true;
 }
 

@@ -55,8 +55,11 @@ struct Var {
   Rpn rpn;        // initial assignment / assignment rule
   bool hasRpn;
   std::vector<Var*> dependence;
+  // A species whose compartment is a membrane: `field` holds one value per storage point of its geometry (Geo::storage)
+  // instead of one per volume cell.
+  bool onMembrane;
   // device binding
-  int constSlot, fieldId, speciesId;
+  int constSlot, fieldId, speciesId, memSpeciesId;
   Var();
 };
 
@@ -85,7 +88,21 @@ struct Geo {
   std::vector<int64_t> pseudoMemIndex;
   Rpn rpn;
   int deviceGeo;
-  Geo() : isVol(true), hasMask(false), nDomain(0), adjacent1(NULL), adjacent2(NULL), deviceGeo(-1) {}
+  // membranes that host species: the doubled-grid points such a species needs storage for (membrane points, pseudo-membrane
+  // points and whatever else domainIndex names), ascending; Var::field of a membrane species is aligned with it
+  std::vector<int64_t> storage;
+  int storageOf(int64_t idx) const;  // -1: no storage
+  // voronoiInfo (mystruct.h:116-129) of setVoronoiInfo (setInfoFunction.cpp:1134-1546), keyed by doubled-grid index; slots are
+  // [XY0, XY1, YZ0, YZ1, XZ0, XZ1]
+  struct Voronoi {
+    int64_t adj[6];
+    double si[6], di[6];
+    bool isAve[6];
+    Voronoi() { for (int i = 0; i < 6; ++i) { adj[i] = -1; si[i] = 1.0; di[i] = 0.0; isAve[i] = false; } }
+  };
+  std::unordered_map<int64_t, Voronoi> voronoi;
+  int devicePointSet;
+  Geo() : isVol(true), hasMask(false), nDomain(0), adjacent1(NULL), adjacent2(NULL), deviceGeo(-1), devicePointSet(-1) {}
   int memIsDomain(int64_t idx) const {
     std::unordered_map<int64_t, uint8_t>::const_iterator it = memClass.find(idx);
     return it == memClass.end() ? 0 : it->second;
@@ -134,6 +151,15 @@ struct Model {
   // (owned rows plus halo); slabLo == slabHi == 0 means the whole grid.
   bool build(SBMLDocument* d, int xdim, int ydim, int zdim, int slabLo = 0, int slabHi = 0);
   bool isSlab() const { return nx != gn[0] || ny != gn[1] || nz != gn[2]; }
+  // value of a coordinate variable at doubled-grid coordinate C of its axis (setInfoFunction.cpp:308): min + C*delta/2.0
+  double coordinateAt(const Var* v, int C) const {
+    const double delta = v == xVar ? deltaX : v == yVar ? deltaY : deltaZ;
+    return v->offGridInit + (double)C * delta / 2.0;
+  }
+  // what the reference's value[] array of `v` holds at doubled-grid point (X, Y, Z) at set-up time
+  double valueAtDoubled(const Var* v, int X, int Y, int Z, int depth = 0) const;
+  // reversePolishInitial at a single doubled-grid point; returns false when the stream leaves nothing on the stack
+  bool evalRpnAtPoint(const Rpn& rpn, int X, int Y, int Z, double* st, double* out, int depth = 0) const;
   // local cell on a local array edge that is not an edge of the whole grid (its neighbour lives in another slab)
   bool cutEdge(int i, int j, int k) const {
     return (j == 0 && off[1] > 0) || (j == ny - 1 && off[1] + ny < gn[1]) || (k == 0 && off[2] > 0) ||
@@ -148,10 +174,16 @@ struct Model {
   void setMembraneGeometries();
   bool resolveAssignments();
   void setNormals();
+  void setVoronoi();
+  void allocateMembraneFields();
   void setBoundaryTypes();
   void setReactions();
   void setRateRules();
 };
+
+// which two membrane points every pseudo-membrane point takes the minimum of (storage indices of g)
+void pseudoFillPairs(const Model& m, const Geo* g, bool everyClassifiedPoint, std::vector<int32_t>& target, std::vector<int32_t>& a,
+                     std::vector<int32_t>& b);
 
 // AST normalisation + post-order emission (astFunction.cpp:18-235)
 void rearrangeAst(ASTNode* ast);
@@ -162,6 +194,8 @@ void collectDependence(const ASTNode* ast, const Model& m, std::vector<Var*>& de
 // reference's reversePolishInitial (calcPDE.cpp:21-222) over compact cells.  `cells` == NULL
 // evaluates every cell; `mask` (optional) restricts to cells with a non-zero byte.
 void evalRpnCompact(const Rpn& rpn, const uint8_t* mask, int64_t ncells, double* out);
+// one operator token of the reference interpreter acting on the stack st[0..sp] after the pop (calcPDE.cpp:47-215)
+void rpnApplyOp(int astType, double* st, int& sp);
 
 }  // namespace sb2host
 

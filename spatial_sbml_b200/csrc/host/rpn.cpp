@@ -176,6 +176,51 @@ void collectDependence(const ASTNode* ast, const Model& m, std::vector<Var*>& de
   if (v) dep.push_back(v);
 }
 
+// one operator of the reference interpreter (calcPDE.cpp:47-215) acting on the stack after the pop
+void rpnApplyOp(int astType, double* st, int& sp) {
+  double& a = st[sp > 0 ? sp - 1 : 0];
+  const double b = st[sp];
+  switch (astType) {
+    case AST_PLUS: if (sp > 0) a += b; break;
+    case AST_MINUS: if (sp > 0) a -= b; break;
+    case AST_TIMES: if (sp > 0) a *= b; break;
+    case AST_DIVIDE: if (sp > 0) a /= b; break;
+    case AST_POWER:
+    case AST_FUNCTION_POWER: if (sp > 0) a = pow(a, b); break;
+    case AST_FUNCTION_LOG: if (sp > 0) a = log(b) / log(a); break;
+    case AST_LOGICAL_AND: if (sp > 0) a = ((int)a == 1 && (int)(b == 1)) ? 1.0 : 0.0; break;
+    case AST_LOGICAL_OR: if (sp > 0) a = ((int)a == 1 || (int)(b == 1)) ? 1.0 : 0.0; break;
+    case AST_LOGICAL_XOR:
+      if (sp > 0) a = (((int)a == 1 && (int)(b == 0)) || ((int)a == 0 && (int)(b == 1))) ? 1.0 : 0.0;
+      break;
+    case AST_RELATIONAL_EQ: if (sp > 0) a = (a == b) ? 1.0 : 0.0; break;
+    case AST_RELATIONAL_GEQ: if (sp > 0) a = (a >= b) ? 1.0 : 0.0; break;
+    case AST_RELATIONAL_GT: if (sp > 0) a = (a > b) ? 1.0 : 0.0; break;
+    case AST_RELATIONAL_LEQ: if (sp > 0) a = (a <= b) ? 1.0 : 0.0; break;
+    case AST_RELATIONAL_LT: if (sp > 0) a = (a < b) ? 1.0 : 0.0; break;
+    case AST_RELATIONAL_NEQ: if (sp > 0) a = (a != b) ? 1.0 : 0.0; break;
+    // unary functions rewrite the popped slot and push it back
+    case AST_FUNCTION_ABS: st[sp] = fabs(b); ++sp; break;
+    case AST_FUNCTION_ARCCOS: st[sp] = acos(b); ++sp; break;
+    case AST_FUNCTION_ARCCOSH: st[sp] = acosh(b); ++sp; break;
+    case AST_FUNCTION_ARCCSC: st[sp] = asin(1.0 / b); ++sp; break;
+    case AST_FUNCTION_ARCSIN: st[sp] = asin(b); ++sp; break;
+    case AST_FUNCTION_ARCTAN: st[sp] = atan(b); ++sp; break;
+    case AST_FUNCTION_COS: st[sp] = cos(b); ++sp; break;
+    case AST_FUNCTION_COSH: st[sp] = cosh(b); ++sp; break;
+    case AST_FUNCTION_CSC: st[sp] = 1.0 / sin(b); ++sp; break;
+    case AST_FUNCTION_EXP: st[sp] = exp(b); ++sp; break;
+    case AST_FUNCTION_LN: st[sp] = log(b); ++sp; break;
+    case AST_FUNCTION_ROOT: st[sp] = sqrt(b); ++sp; break;  // sqrt whatever the degree
+    case AST_FUNCTION_SIN: st[sp] = sin(b); ++sp; break;
+    case AST_FUNCTION_SINH: st[sp] = sinh(b); ++sp; break;
+    case AST_FUNCTION_TAN: st[sp] = tan(b); ++sp; break;
+    case AST_FUNCTION_TANH: st[sp] = tanh(b); ++sp; break;
+    case AST_LOGICAL_NOT: st[sp] = ((int)b == 0) ? 1.0 : 0.0; ++sp; break;
+    default: break;  // listed-but-empty operators only pop
+  }
+}
+
 namespace {
 void evalRange(const Rpn& rpn, const uint8_t* mask, int64_t c0, int64_t c1, double* out);
 
@@ -243,47 +288,7 @@ void evalRange(const Rpn& rpn, const uint8_t* mask, int64_t cbegin, int64_t cend
       if (t.kind == Tok::LITERAL) { st[sp++] = t.literal; continue; }
       if (sp > 0) --sp;
       if (t.kind != Tok::OP) continue;
-      double& a = st[sp > 0 ? sp - 1 : 0];
-      const double b = st[sp];
-      switch (t.astType) {
-        case AST_PLUS: if (sp > 0) a += b; break;
-        case AST_MINUS: if (sp > 0) a -= b; break;
-        case AST_TIMES: if (sp > 0) a *= b; break;
-        case AST_DIVIDE: if (sp > 0) a /= b; break;
-        case AST_POWER:
-        case AST_FUNCTION_POWER: if (sp > 0) a = pow(a, b); break;
-        case AST_FUNCTION_LOG: if (sp > 0) a = log(b) / log(a); break;
-        case AST_LOGICAL_AND: if (sp > 0) a = ((int)a == 1 && (int)(b == 1)) ? 1.0 : 0.0; break;
-        case AST_LOGICAL_OR: if (sp > 0) a = ((int)a == 1 || (int)(b == 1)) ? 1.0 : 0.0; break;
-        case AST_LOGICAL_XOR:
-          if (sp > 0) a = (((int)a == 1 && (int)(b == 0)) || ((int)a == 0 && (int)(b == 1))) ? 1.0 : 0.0;
-          break;
-        case AST_RELATIONAL_EQ: if (sp > 0) a = (a == b) ? 1.0 : 0.0; break;
-        case AST_RELATIONAL_GEQ: if (sp > 0) a = (a >= b) ? 1.0 : 0.0; break;
-        case AST_RELATIONAL_GT: if (sp > 0) a = (a > b) ? 1.0 : 0.0; break;
-        case AST_RELATIONAL_LEQ: if (sp > 0) a = (a <= b) ? 1.0 : 0.0; break;
-        case AST_RELATIONAL_LT: if (sp > 0) a = (a < b) ? 1.0 : 0.0; break;
-        case AST_RELATIONAL_NEQ: if (sp > 0) a = (a != b) ? 1.0 : 0.0; break;
-        // unary functions rewrite the popped slot and push it back
-        case AST_FUNCTION_ABS: st[sp] = fabs(b); ++sp; break;
-        case AST_FUNCTION_ARCCOS: st[sp] = acos(b); ++sp; break;
-        case AST_FUNCTION_ARCCOSH: st[sp] = acosh(b); ++sp; break;
-        case AST_FUNCTION_ARCCSC: st[sp] = asin(1.0 / b); ++sp; break;
-        case AST_FUNCTION_ARCSIN: st[sp] = asin(b); ++sp; break;
-        case AST_FUNCTION_ARCTAN: st[sp] = atan(b); ++sp; break;
-        case AST_FUNCTION_COS: st[sp] = cos(b); ++sp; break;
-        case AST_FUNCTION_COSH: st[sp] = cosh(b); ++sp; break;
-        case AST_FUNCTION_CSC: st[sp] = 1.0 / sin(b); ++sp; break;
-        case AST_FUNCTION_EXP: st[sp] = exp(b); ++sp; break;
-        case AST_FUNCTION_LN: st[sp] = log(b); ++sp; break;
-        case AST_FUNCTION_ROOT: st[sp] = sqrt(b); ++sp; break;  // sqrt whatever the degree
-        case AST_FUNCTION_SIN: st[sp] = sin(b); ++sp; break;
-        case AST_FUNCTION_SINH: st[sp] = sinh(b); ++sp; break;
-        case AST_FUNCTION_TAN: st[sp] = tan(b); ++sp; break;
-        case AST_FUNCTION_TANH: st[sp] = tanh(b); ++sp; break;
-        case AST_LOGICAL_NOT: st[sp] = ((int)b == 0) ? 1.0 : 0.0; ++sp; break;
-        default: break;  // listed-but-empty operators only pop
-      }
+      rpnApplyOp(t.astType, st, sp);
       if (sp > 60) sp = 60;
     }
     if (sp > 0) out[c] = st[--sp];

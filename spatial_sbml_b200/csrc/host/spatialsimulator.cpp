@@ -83,12 +83,16 @@ struct SimImpl {
   std::vector<Var*> staged;     // device species id → variable
   std::vector<Var*> fieldVars;  // device field id → variable
   std::vector<char> stale;      // per staged species: device state is newer than Var::field
+  std::vector<Var*> ruleTargets;  // variables an assignment rule rewrites on the device after every step
+  bool rulesStale;                // ... whose host copies are older than the device's
+  std::vector<Var*> memStaged;  // device membrane species id → variable
+  std::vector<char> memStale;
   std::map<std::string, VarMirror> varMirrors;
   std::map<std::string, std::vector<int> > geoMirrors, boundaryMirrors;
   std::map<std::string, std::vector<boundaryType> > btMirrors;
   int ownLo, ownHi, heldLo;  // slab rows (global) owned / first row held locally
   long domainCells;
-  SimImpl() : ownedDoc(NULL), dev(NULL), timeSlot(-1), ownLo(0), ownHi(0), heldLo(0), domainCells(0) {}
+  SimImpl() : ownedDoc(NULL), dev(NULL), rulesStale(false), timeSlot(-1), ownLo(0), ownHi(0), heldLo(0), domainCells(0) {}
   ~SimImpl() {
     if (dev) sb2_destroy(dev);
     delete ownedDoc;
@@ -117,6 +121,11 @@ struct SimImpl {
     return v->offGridInit + (double)C * delta / 2.0;
   }
   bool isCoordinate(const Var* v) const { return v && (v == m.xVar || v == m.yVar || v == m.zVar); }
+  void markStale() {
+    for (size_t s = 0; s < stale.size(); ++s) stale[s] = 1;
+    for (size_t s = 0; s < memStale.size(); ++s) memStale[s] = 1;
+    rulesStale = !ruleTargets.empty();
+  }
 };
 
 // =============================================================================================
@@ -231,10 +240,6 @@ bool SpatialSimulator::buildDevice() {
     lastError = "the device step supports 2-D and 3-D geometries (this model has " + std::to_string(m.dimension) + " coordinate components)";
     return false;
   }
-  if (!m.orderedAssignmentRules.empty()) {
-    lastError = "assignment rules re-evaluated every step are not supported on the device yet";
-    return false;
-  }
   sb2_grid g;
   memset(&g, 0, sizeof(g));
   g.nx = m.nx; g.ny = m.ny; g.nz = m.nz; g.dim = m.dimension;
@@ -263,10 +268,7 @@ bool SpatialSimulator::buildDevice() {
     Var* v = m.findVar(m.model->getSpecies(i)->getId());
     if (!v || v->sp != m.model->getSpecies(i) || v->isUniform || !v->hasValue) continue;
     if (!v->geo) continue;  // no geometry for its compartment: the reference never touches it
-    if (!v->geo->isVol) {
-      lastError = "species '" + v->id + "' lives in a membrane compartment; membrane species are not supported on the device yet";
-      return false;
-    }
+    if (!v->geo->isVol) continue;  // species on a membrane: staged below (addMembraneSpecies)
     if (!v->hasDelta) continue;  // constant spatial species: a read-only field
     if (!v->geo->hasMask) continue;
     const int dg = deviceGeoOf(v->geo);
@@ -294,6 +296,8 @@ bool SpatialSimulator::buildDevice() {
           }
         }
   }
+
+  if (!addMembraneSpecies()) return false;
 
   auto fieldIdOf = [&](Var* v) -> int {
     if (v->fieldId >= 0) return v->fieldId;
@@ -390,7 +394,11 @@ bool SpatialSimulator::buildDevice() {
       for (size_t k = 0; k < x->spRefs.size(); ++k)
         if (x->spRefs[k] && x->spRefs[k]->geo) { geo = x->spRefs[k]->geo; break; }
       if (!geo) continue;  // every participant is uniform: the reference changes nothing
-      if (!geo->isVol || !geo->hasMask) { lastError = "reaction '" + x->id + "' takes place on a membrane (unsupported)"; return false; }
+      if (!geo->isVol) {
+        if (!addMembraneReaction(x, geo, 0)) return false;
+        continue;
+      }
+      if (!geo->hasMask) { lastError = "reaction '" + x->id + "': its compartment has no geometry"; return false; }
       const int dg = deviceGeoOf(geo);
       if (dg < 0) { lastError = std::string("sb2_add_geometry: ") + sb2_last_error(impl->dev); return false; }
       if (!toDeviceTokens(x->rpn, toks)) return false;
@@ -409,8 +417,12 @@ bool SpatialSimulator::buildDevice() {
     Var* target = m.findVar(rule->getVariable());
     if (i >= m.rxns.size()) { lastError = "rate rule '" + rule->getVariable() + "': the reference indexes its reaction list out of range here"; return false; }
     if (!target || !target->geo) continue;
-    if (!target->geo->isVol || !target->geo->hasMask) { lastError = "rate rule on a membrane variable (unsupported)"; return false; }
     Rxn* x = m.rxns[i];
+    if (!target->geo->isVol) {
+      if (!addMembraneReaction(x, target->geo, 1)) return false;
+      continue;
+    }
+    if (!target->geo->hasMask) { lastError = "rate rule '" + rule->getVariable() + "': its compartment has no geometry"; return false; }
     const int dg = deviceGeoOf(target->geo);
     if (dg < 0) { lastError = std::string("sb2_add_geometry: ") + sb2_last_error(impl->dev); return false; }
     if (!toDeviceTokens(x->rpn, toks)) return false;
@@ -418,9 +430,174 @@ bool SpatialSimulator::buildDevice() {
     DEV(sb2_add_reaction(impl->dev, dg, 1, toks.data(), (int)toks.size(), refs.data(), (int)refs.size(), 1));
   }
 
+  // assignment rules are re-evaluated after every step, in dependency order (updateAssignmentRules, spatialsimulator.cpp:1566-1581)
+  for (size_t i = 0; i < m.orderedAssignmentRules.size(); ++i) {
+    Var* v = m.orderedAssignmentRules[i];
+    if (v->onMembrane || (v->geo && !v->geo->isVol && v->sp)) {
+      lastError = "assignment rule on the membrane species '" + v->id + "' is not supported on the device yet";
+      return false;
+    }
+    int kind, target, geo = -1;
+    if (v->sp) {
+      // a species: only the cells of its compartment are written (isAllArea == false)
+      if (!v->geo || !v->geo->hasMask) continue;  // the reference would dereference a NULL geometry here
+      geo = deviceGeoOf(v->geo);
+      if (geo < 0) { lastError = std::string("sb2_add_geometry: ") + sb2_last_error(impl->dev); return false; }
+    }
+    if (v->speciesId >= 0) { kind = 1; target = v->speciesId; }
+    else {
+      kind = 0; target = fieldIdOf(v);
+      if (target < 0) { lastError = std::string("sb2_add_field: ") + sb2_last_error(impl->dev); return false; }
+    }
+    if (!toDeviceTokens(v->rpn, toks)) return false;
+    DEV(sb2_add_assignment_rule(impl->dev, kind, target, geo, toks.data(), (int)toks.size()));
+    impl->ruleTargets.push_back(v);
+  }
+
   if (m.tVar->constSlot >= 0) impl->timeSlot = m.tVar->constSlot;
   if (!impl->consts.empty()) DEV(sb2_set_constants(impl->dev, impl->consts.data(), (int)impl->consts.size()));
   DEV(sb2_finalize(impl->dev));
+  return true;
+}
+
+namespace {
+void pointCoords(const sb2host::Model& m, int64_t idx, int& X, int& Y, int& Z) {
+  const int64_t Xi = m.Xindex, Yi = m.Yindex;
+  Z = (int)(idx / (Xi * Yi));
+  Y = (int)((idx - (int64_t)Z * Xi * Yi) / Xi);
+  X = (int)(idx - (int64_t)Z * Xi * Yi - (int64_t)Y * Xi);
+}
+}  // namespace
+
+// Species that live on a membrane: storage on a point set, update list, surface diffusion over the Voronoi neighbours
+// (calcMemDiffusion, calcPDE.cpp:1484-1581), pseudo-membrane fill (spatialsimulator.cpp:1614-1663)
+bool SpatialSimulator::addMembraneSpecies() {
+  sb2host::Model& m = impl->m;
+  for (unsigned int i = 0; i < m.model->getNumSpecies(); ++i) {
+    Var* v = m.findVar(m.model->getSpecies(i)->getId());
+    if (!v || v->sp != m.model->getSpecies(i) || v->isUniform || !v->hasValue || !v->geo || v->geo->isVol) continue;
+    if (!v->onMembrane || !v->hasDelta) continue;  // a constant membrane species is only ever read (per-point operand values)
+    if (m.isSlab()) { lastError = "species '" + v->id + "' lives on a membrane; membrane species are not supported on a sharded grid yet"; return false; }
+    Geo* g = v->geo;
+    if (g->storage.size() > (size_t)0x7fffffff) { lastError = "membrane '" + g->compartmentId + "' has too many points"; return false; }
+    if (g->devicePointSet < 0) {
+      g->devicePointSet = sb2_add_point_set(impl->dev, (int)g->storage.size());
+      if (g->devicePointSet < 0) { lastError = std::string("sb2_add_point_set: ") + sb2_last_error(impl->dev); return false; }
+      std::vector<int32_t> t, a, b;
+      sb2host::pseudoFillPairs(m, g, false, t, a, b);
+      DEV(sb2_set_mem_fill(impl->dev, g->devicePointSet, t.data(), a.data(), b.data(), (int)t.size()));
+    }
+    const int id = sb2_add_mem_species(impl->dev, g->devicePointSet, v->field.data());
+    if (id < 0) { lastError = std::string("sb2_add_mem_species: ") + sb2_last_error(impl->dev); return false; }
+    v->memSpeciesId = id;
+    impl->memStaged.push_back(v);
+    impl->memStale.push_back(0);
+    std::vector<int32_t> upd;
+    for (size_t q = 0; q < g->memDomainIndex.size(); ++q) {
+      const int k = g->storageOf(g->memDomainIndex[q]);
+      if (k >= 0) upd.push_back(k);
+    }
+    DEV(sb2_set_mem_update_points(impl->dev, id, upd.data(), (int)upd.size()));
+    if (!v->hasDiff || !v->diffC[0] || !v->diffC[0]->hasValue) continue;  // calcMemDiffusion reads diffCInfo[0] only
+    Var* dc = v->diffC[0];
+    std::map<int64_t, const MemPoint*> pointOf;
+    for (size_t k = 0; k < g->memPoints.size(); ++k) pointOf[g->memPoints[k].index] = &g->memPoints[k];
+    std::vector<int32_t> pts, start(1, 0), adj;
+    std::vector<double> sij, dij, area, dvals;
+    for (size_t q = 0; q < g->memDomainIndex.size(); ++q) {
+      const int64_t idx = g->memDomainIndex[q];
+      const int k = g->storageOf(idx);
+      if (k < 0) continue;
+      std::unordered_map<int64_t, Geo::Voronoi>::const_iterator vit = g->voronoi.find(idx);
+      Geo::Voronoi vor;
+      if (vit != g->voronoi.end()) vor = vit->second;
+      // area = sum_j (d_xy s_xy + d_yz s_yz + d_xz s_xz), halved in 2-D, quartered in 3-D (calcPDE.cpp:1520-1527)
+      double ar = 0.0;
+      for (int j = 0; j < 2; ++j) {
+        ar += vor.di[0 + j] * vor.si[0 + j];
+        ar += vor.di[2 + j] * vor.si[2 + j];
+        ar += vor.di[4 + j] * vor.si[4 + j];
+      }
+      if (m.dimension == 2) ar /= 2.0;
+      else if (m.dimension == 3) ar /= 4.0;
+      pts.push_back(k);
+      area.push_back(ar);
+      if (!dc->isUniform) {
+        int X, Y, Z;
+        pointCoords(m, idx, X, Y, Z);
+        dvals.push_back(m.valueAtDoubled(dc, X, Y, Z));
+      }
+      std::map<int64_t, const MemPoint*>::const_iterator pit = pointOf.find(idx);
+      if (pit != pointOf.end()) {
+        const uint8_t bof = pit->second->bof;
+        const bool bx = (bof & SB2_F_XP) && (bof & SB2_F_XM), by = (bof & SB2_F_YP) && (bof & SB2_F_YM), bz = (bof & SB2_F_ZP) && (bof & SB2_F_ZM);
+        const bool plane[3] = {bx || by, m.dimension == 3 && (by || bz), m.dimension == 3 && (bx || bz)};
+        for (int pl = 0; pl < 3; ++pl) {
+          if (!plane[pl]) continue;
+          for (int j = 0; j < 2; ++j) {
+            const int a = vor.adj[2 * pl + j] >= 0 ? g->storageOf(vor.adj[2 * pl + j]) : -1;
+            if (a < 0) continue;  // no neighbour found on this side (the reference would read outside its array)
+            adj.push_back(a); sij.push_back(vor.si[2 * pl + j]); dij.push_back(vor.di[2 * pl + j]);
+          }
+        }
+      }
+      start.push_back((int32_t)adj.size());
+    }
+    const int kind = dc->isUniform ? SB2_SRC_CONST : SB2_SRC_FIELD;
+    const int src = dc->isUniform ? impl->constSlotOf(dc) : 0;
+    DEV(sb2_set_mem_diffusion(impl->dev, id, kind, src, dvals.empty() ? NULL : dvals.data(), pts.data(), (int)pts.size(), start.data(),
+                              adj.data(), sij.data(), dij.data(), area.data()));
+  }
+  return true;
+}
+
+// A reaction between species of one membrane (kind 0) or a rate rule on a membrane variable (kind 1): the reference runs
+// reversePolishRK over every entry of the membrane's domainIndex (spatialsimulator.cpp:1381-1390, calcPDE.cpp:224-451)
+bool SpatialSimulator::addMembraneReaction(void* rx, void* geo, int kind) {
+  Rxn* x = static_cast<Rxn*>(rx);
+  Geo* g = static_cast<Geo*>(geo);
+  sb2host::Model& m = impl->m;
+  if (m.isSlab()) { lastError = "reaction '" + x->id + "' takes place on a membrane; not supported on a sharded grid yet"; return false; }
+  if (g->devicePointSet < 0) return true;  // no variable species lives on this membrane: nothing can change
+  std::vector<int32_t> pts;
+  std::vector<int64_t> idxs;
+  for (size_t q = 0; q < g->memDomainIndex.size(); ++q) {
+    const int k = g->storageOf(g->memDomainIndex[q]);
+    if (k >= 0) { pts.push_back(k); idxs.push_back(g->memDomainIndex[q]); }
+  }
+  std::vector<sb2_token> toks;
+  std::vector<double> values;
+  for (size_t i = 0; i < x->rpn.size(); ++i) {
+    const Tok& t = x->rpn[i];
+    sb2_token d;
+    d.kind = SB2_TOK_NOP; d.op = 0; d.slot = 0;
+    if (t.kind == Tok::OP) { d.kind = SB2_TOK_OP; d.op = (uint8_t)opOfAst(t.astType); }
+    else if (t.kind == Tok::LITERAL) { d.kind = SB2_TOK_CONST; d.slot = (uint16_t)impl->literalSlotOf(t.literal); }
+    else if (t.kind == Tok::CONSTVAR) { d.kind = SB2_TOK_CONST; d.slot = (uint16_t)impl->constSlotOf(t.var); }
+    else if (t.kind == Tok::VAR && t.var->memSpeciesId >= 0 && t.var->geo == g) { d.kind = SB2_TOK_MEMVAR; d.slot = (uint16_t)t.var->memSpeciesId; }
+    else if (t.kind == Tok::VAR) {
+      // anything else keeps, at a membrane point, the value it was set up with (volume species are only ever advanced at
+      // volume cells, their slopes at other points stay zero)
+      d.kind = SB2_TOK_FIELD;
+      for (size_t q = 0; q < idxs.size(); ++q) {
+        int X, Y, Z;
+        pointCoords(m, idxs[q], X, Y, Z);
+        values.push_back(m.valueAtDoubled(t.var, X, Y, Z));
+      }
+    }
+    toks.push_back(d);
+  }
+  std::vector<sb2_ref> refs;
+  for (size_t k = 0; k < x->spRefs.size(); ++k) {
+    sb2_ref r;
+    Var* v = x->spRefs[k];
+    r.species = (v && !v->isUniform && v->memSpeciesId >= 0 && v->geo == g) ? SB2_MEM_SPECIES + v->memSpeciesId : -1;
+    r.is_variable = x->isVariable[k] ? 1 : 0;
+    r.stoichiometry = x->stoichiometry[k];
+    refs.push_back(r);
+  }
+  DEV(sb2_add_mem_reaction(impl->dev, g->devicePointSet, kind, toks.data(), (int)toks.size(), refs.data(), (int)refs.size(),
+                           kind == 0 ? x->nReactants : 1, pts.data(), (int)pts.size(), values.empty() ? NULL : values.data()));
   return true;
 }
 
@@ -447,17 +624,26 @@ bool SpatialSimulator::addMemTransport(void* rx) {
   Geo* reactantGeo = geoOfSpecies(r->getReactant(0)->getSpecies());
   Geo* productGeo = geoOfSpecies(r->getProduct(0)->getSpecies());
   const bool haveRV = reactantGeo && reactantGeo->isVol, havePV = productGeo && productGeo->isVol;
-  if (haveRV != havePV) {
-    lastError = "reaction '" + x->id + "' binds a volume species to a membrane species (unsupported)";
-    return false;
-  }
-  Geo* mem = NULL;
+  std::vector<Geo*> mems;  // every membrane calcMemTransport is called on for this reaction, in call order
   for (size_t j = 0; j < m.geos.size(); ++j) {
     Geo* g = m.geos[j];
     if (g->isVol) continue;
-    if ((g->adjacent1 == reactantGeo && g->adjacent2 == productGeo) || (g->adjacent1 == productGeo && g->adjacent2 == reactantGeo)) { mem = g; break; }
+    if ((g->adjacent1 == reactantGeo && g->adjacent2 == productGeo) || (g->adjacent1 == productGeo && g->adjacent2 == reactantGeo)) { mems.push_back(g); break; }
   }
-  if (!mem) return true;  // no membrane between the two compartments: nothing happens
+  // binding: one side of the reaction lives on a membrane (spatialsimulator.cpp:1440-1450)
+  if (haveRV != havePV) {
+    if (!haveRV && reactantGeo) mems.push_back(reactantGeo);
+    if (!havePV && productGeo) mems.push_back(productGeo);
+  }
+  for (size_t q = 0; q < mems.size(); ++q)
+    if (!addMemTransportOn(x, mems[q])) return false;
+  return true;  // (no membrane between the two compartments: nothing happens)
+}
+
+bool SpatialSimulator::addMemTransportOn(void* rx, void* memGeo) {
+  Rxn* x = static_cast<Rxn*>(rx);
+  Geo* mem = static_cast<Geo*>(memGeo);
+  sb2host::Model& m = impl->m;
 
   const int Xi = m.Xindex, Yi = m.Yindex, Zi = m.Zindex;
   const int64_t N = m.ndoubled();
@@ -495,11 +681,21 @@ bool SpatialSimulator::addMemTransport(void* rx) {
     if (t.kind == Tok::OP) { d.kind = SB2_TOK_OP; d.op = (uint8_t)opOfAst(t.astType); }
     else if (t.kind == Tok::LITERAL) { d.kind = SB2_TOK_CONST; d.slot = (uint16_t)impl->literalSlotOf(t.literal); }
     else if (t.kind == Tok::CONSTVAR) { d.kind = SB2_TOK_CONST; d.slot = (uint16_t)impl->constSlotOf(t.var); }
+    else if (t.kind == Tok::VAR && t.var->hasDelta && t.var->memSpeciesId >= 0) {
+      // a symbol that lives on a membrane is read at the point itself (calcPDE.cpp:1214-1217); the reference decides
+      // "volume or membrane" by the species reference it matched last
+      for (size_t j = 0; j < x->spRefs.size(); ++j)
+        if (x->spRefs[j] == t.var) { symbol = x->spRefs[j]; break; }
+      d.kind = SB2_TOK_MEMVAR; d.slot = (uint16_t)t.var->memSpeciesId;
+      for (int p = 0; p < npts; ++p) {
+        operandCells.push_back(t.var->geo ? t.var->geo->storageOf(pts[p]->index) : -1);
+        operandCells.push_back(-1);
+      }
+    }
     else if (t.kind == Tok::VAR && t.var->hasDelta && t.var->speciesId >= 0) {
       for (size_t j = 0; j < x->spRefs.size(); ++j)
         if (x->spRefs[j] == t.var) { symbol = x->spRefs[j]; break; }
       if (!symbol || !symbol->geo) { lastError = "membrane transport '" + x->id + "': operand '" + t.var->id + "' has no geometry"; return false; }
-      if (!symbol->geo->isVol) { lastError = "membrane transport '" + x->id + "' reads a membrane species (unsupported)"; return false; }
       d.kind = SB2_TOK_VAR; d.slot = (uint16_t)t.var->speciesId;
       for (int p = 0; p < npts; ++p) {
         const MemPoint& mp = *pts[p];
@@ -527,9 +723,7 @@ bool SpatialSimulator::addMemTransport(void* rx) {
       d.kind = SB2_TOK_FIELD; d.slot = 0;
       for (int p = 0; p < npts; ++p) {
         const MemPoint& mp = *pts[p];
-        double val = t.var->offGridInit;
-        if (impl->isCoordinate(t.var)) val = impl->coordinateAt(t.var, t.var == m.xVar ? mp.X : t.var == m.yVar ? mp.Y : mp.Z);
-        operandValues.push_back(val);
+        operandValues.push_back(m.valueAtDoubled(t.var, mp.X, mp.Y, mp.Z));
       }
     }
     toks.push_back(d);
@@ -548,7 +742,8 @@ bool SpatialSimulator::addMemTransport(void* rx) {
     sb2_ref rr;
     Var* v = x->spRefs[k];
     const bool ok = v && !v->isUniform && v->speciesId >= 0 && v->geo && v->geo->isVol;
-    rr.species = ok ? v->speciesId : -1;
+    const bool onMem = v && !v->isUniform && v->memSpeciesId >= 0 && v->geo && !v->geo->isVol;
+    rr.species = ok ? v->speciesId : onMem ? SB2_MEM_SPECIES + v->memSpeciesId : -1;
     rr.is_variable = x->isVariable[k] ? 1 : 0;
     rr.stoichiometry = x->stoichiometry[k];
     refs.push_back(rr);
@@ -556,6 +751,12 @@ bool SpatialSimulator::addMemTransport(void* rx) {
       const MemPoint& mp = *pts[p];
       const int a = dpts[p].axis;
       const int dx = a == 0, dy = a == 1, dz = a == 2;
+      if (onMem) {
+        // binding: the species' own membrane holds this point (isDomain[index] == 1, calcPDE.cpp:1405)
+        targets.push_back(v->geo->memIsDomain(mp.index) == 1 ? v->geo->storageOf(mp.index) : -1);
+        targets.push_back(-1);
+        continue;
+      }
       targets.push_back(ok ? cellIn(v->geo, mp.X + dx, mp.Y + dy, mp.Z + dz) : -1);
       targets.push_back(ok ? cellIn(v->geo, mp.X - dx, mp.Y - dy, mp.Z - dz) : -1);
     }
@@ -577,6 +778,16 @@ void SpatialSimulator::syncBeforeStep() {
     if (!it->second.handedOut) continue;
     Var* v = m.findVar(it->first);
     if (!v || v->isUniform || m.isSlab()) continue;
+    if (v->onMembrane) {
+      if (v->memSpeciesId < 0 || impl->memStale[v->memSpeciesId] || !v->geo) continue;
+      bool changed = false;
+      for (size_t k = 0; k < v->geo->storage.size(); ++k) {
+        const double x = it->second.data[(size_t)v->geo->storage[k]];
+        if (memcmp(&x, &v->field[k], sizeof(double)) != 0) { v->field[k] = x; changed = true; }
+      }
+      if (changed) sb2_upload_mem_species(impl->dev, v->memSpeciesId, v->field.data());
+      continue;
+    }
     if (v->speciesId >= 0 && impl->stale[v->speciesId]) continue;  // mirror was not refreshed since the last step
     bool changed = false;
     const double* d = it->second.data.data();
@@ -615,7 +826,7 @@ double SpatialSimulator::oneStep(double initialTime, double step) {
     lastError = std::string("sb2_step: ") + sb2_last_error(impl->dev);
     throw std::runtime_error(lastError);
   }
-  for (size_t s = 0; s < impl->stale.size(); ++s) impl->stale[s] = 1;
+  impl->markStale();
   return initialTime + step;
 }
 
@@ -653,7 +864,7 @@ double SpatialSimulator::oneStepHost(double initialTime, double step, int n, con
     lastError = std::string("sb2_step_host: ") + sb2_last_error(impl->dev);
     throw std::runtime_error(lastError);
   }
-  for (size_t s = 0; s < S; ++s) impl->stale[s] = 1;
+  impl->markStale();
   return initialTime + step;
 }
 
@@ -670,12 +881,12 @@ void SpatialSimulator::runSteps(double firstStepIndex, double step, int nsteps) 
   }
   impl->m.simTime = (firstStepIndex + nsteps - 1) * step;
   impl->m.tVar->uniformValue = impl->m.simTime;
-  for (size_t s = 0; s < impl->stale.size(); ++s) impl->stale[s] = 1;
+  impl->markStale();
 }
 
 void SpatialSimulator::deviceStateChanged() {
   if (!impl) return;
-  for (size_t s = 0; s < impl->stale.size(); ++s) impl->stale[s] = 1;
+  impl->markStale();
 }
 
 // spatialsimulator.cpp:1667-1703 without the gnuplot pipe
@@ -780,6 +991,18 @@ long SpatialSimulator::getDeviceLaunchCount() const { return impl && impl->dev ?
 namespace {
 // bring Var::field up to date with the device
 bool refreshCompact(SimImpl* impl, Var* v) {
+  if (impl->rulesStale && impl->dev) {  // fields rewritten by assignment rules
+    for (size_t i = 0; i < impl->ruleTargets.size(); ++i) {
+      Var* r = impl->ruleTargets[i];
+      if (r->fieldId >= 0 && sb2_download_field(impl->dev, r->fieldId, r->field.data()) < 0) return false;
+    }
+    impl->rulesStale = false;
+  }
+  if (v->memSpeciesId >= 0 && impl->dev && impl->memStale[v->memSpeciesId]) {
+    if (sb2_download_mem_species(impl->dev, v->memSpeciesId, v->field.data()) < 0) return false;
+    impl->memStale[v->memSpeciesId] = 0;
+    return true;
+  }
   if (v->speciesId < 0 || !impl->dev || !impl->stale[v->speciesId]) return true;
   if (sb2_download_species(impl->dev, v->speciesId, v->field.data()) < 0) return false;
   impl->stale[v->speciesId] = 0;
@@ -795,6 +1018,11 @@ bool SpatialSimulator::getVariableCompact(const std::string& id, double* out, si
     for (size_t i = 0; i < n; ++i) out[i] = v->uniformValue;
     return true;
   }
+  if (v->onMembrane) {  // one value per storage point of its membrane (getMembranePoints)
+    if (n != v->field.size() || !refreshCompact(impl, v)) return false;
+    memcpy(out, v->field.data(), n * sizeof(double));
+    return true;
+  }
   if (n != (size_t)impl->m.ncells()) return false;
   // device state newer than the host copy: copy straight into the caller's buffer (which may be
   // pinned) instead of going through the host copy
@@ -806,7 +1034,17 @@ bool SpatialSimulator::getVariableCompact(const std::string& id, double* out, si
 bool SpatialSimulator::setVariableCompact(const std::string& id, const double* in, size_t n) {
   if (!impl || !in) return false;
   Var* v = impl->m.findVar(id);
-  if (!v || !v->hasValue || v->isUniform || n != (size_t)impl->m.ncells()) return false;
+  if (!v || !v->hasValue || v->isUniform) return false;
+  if (v->onMembrane) {
+    if (n != v->field.size()) return false;
+    memcpy(v->field.data(), in, n * sizeof(double));
+    if (impl->dev && v->memSpeciesId >= 0) {
+      impl->memStale[v->memSpeciesId] = 0;
+      return sb2_upload_mem_species(impl->dev, v->memSpeciesId, v->field.data()) >= 0;
+    }
+    return true;
+  }
+  if (n != (size_t)impl->m.ncells()) return false;
   if (impl->dev && v->speciesId >= 0) {
     // upload straight from the caller's buffer; the host copy is refreshed on demand
     if (sb2_upload_species(impl->dev, v->speciesId, in) < 0) return false;
@@ -827,11 +1065,19 @@ double* SpatialSimulator::getVariable(const std::string& id, int& length) {
   length = getVariableLength();
   if (v->isUniform) return &v->uniformValue;  // the reference hands out the single double as well
   if (m.isSlab()) { length = 0; lastError = "doubled-grid mirrors are not available on a sharded grid; use getVariableCompact"; return NULL; }
-  const bool wasStale = v->speciesId >= 0 && impl->stale[v->speciesId];
+  const bool wasStale = (v->speciesId >= 0 && impl->stale[v->speciesId]) || (v->memSpeciesId >= 0 && impl->memStale[v->memSpeciesId]);
   if (!refreshCompact(impl, v)) { length = 0; return NULL; }
   VarMirror& mir = impl->varMirrors[id];
   const bool fresh = mir.data.empty();
   const int Xi = m.Xindex, Yi = m.Yindex, Zi = m.Zindex;
+  if (v->onMembrane) {
+    // zero off the membrane (boundaryFunction.cpp:97, 169), the species' values at its membrane / pseudo-membrane points
+    if (fresh) mir.data.assign((size_t)m.ndoubled(), 0.0);
+    if ((fresh || wasStale || !mir.handedOut) && v->geo)
+      for (size_t k = 0; k < v->geo->storage.size() && k < v->field.size(); ++k) mir.data[(size_t)v->geo->storage[k]] = v->field[k];
+    mir.handedOut = true;
+    return mir.data.data();
+  }
   if (fresh) {
     mir.data.assign((size_t)m.ndoubled(), v->offGridInit);
     if (impl->isCoordinate(v)) {
@@ -1072,6 +1318,28 @@ std::string SpatialSimulator::getSetupText(const std::string& what) {
     Geo* g = m.geoByCompartment(what.substr(9));
     if (!g) return "";
     for (size_t k = 0; k < g->memDomainIndex.size(); ++k) os << g->memDomainIndex[k] << "\n";
+    return os.str();
+  }
+  if (what.compare(0, 8, "voronoi/") == 0) {
+    // per domainIndex entry: the six neighbours [XY0 YZ0 XZ0 XY1 YZ1 XZ1], then s_ij and d_ij in the same slot order
+    // (the layout oracle/ref_driver.cpp dumps vorI in)
+    Geo* g = m.geoByCompartment(what.substr(8));
+    if (!g) return "";
+    static const int slot[6] = {0, 2, 4, 1, 3, 5};
+    for (size_t k = 0; k < g->memDomainIndex.size(); ++k) {
+      std::unordered_map<int64_t, Geo::Voronoi>::const_iterator it = g->voronoi.find(g->memDomainIndex[k]);
+      Geo::Voronoi v;
+      if (it != g->voronoi.end()) v = it->second;
+      for (int q = 0; q < 6; ++q) os << v.adj[slot[q]] << " ";
+      for (int q = 0; q < 6; ++q) os << v.si[slot[q]] << " ";
+      for (int q = 0; q < 6; ++q) os << v.di[slot[q]] << (q == 5 ? "\n" : " ");
+    }
+    return os.str();
+  }
+  if (what.compare(0, 8, "storage/") == 0) {
+    Geo* g = m.geoByCompartment(what.substr(8));
+    if (!g) return "";
+    for (size_t k = 0; k < g->storage.size(); ++k) os << g->storage[k] << "\n";
     return os.str();
   }
   if (what.compare(0, 7, "pseudo/") == 0) {

@@ -121,6 +121,9 @@ class __attribute__((visibility("default"))) SpatialSimulator {
   void clear();
   bool buildDevice();
   bool addMemTransport(void* rxn);
+  bool addMemTransportOn(void* rxn, void* membraneGeo);
+  bool addMembraneSpecies();
+  bool addMembraneReaction(void* rxn, void* geo, int kind);
   void syncBeforeStep();
 
   int Xdiv, Ydiv, Zdiv;

@@ -97,7 +97,7 @@ def _geometry(axes, dims, lo, hi):
             '</spatial:geometry>' % (cc, _MATH, inside, _MATH, _cn(1)))
 
 
-def _document(model_id, axes, dims, species, params, assignments, reactions, lo=1, hi=None):
+def _document(model_id, axes, dims, species, params, assignments, reactions, lo=1, hi=None, rules=None):
     hi = hi or [n - 2 for n in dims]
     comps = ('<compartment id="inside" spatialDimensions="3" size="1" constant="true">'
              '<spatial:compartmentMapping spatial:id="m_in" spatial:domainType="dt_in" spatial:unitSize="1"/></compartment>'
@@ -111,11 +111,12 @@ def _document(model_id, axes, dims, species, params, assignments, reactions, lo=
     return ('<?xml version="1.0" encoding="UTF-8"?>\n'
             '<sbml xmlns="http://www.sbml.org/sbml/level3/version1/core" xmlns:spatial="%s" level="3" version="1" '
             'spatial:required="true"><model id="%s"><listOfCompartments>%s</listOfCompartments>'
-            '<listOfSpecies>%s</listOfSpecies><listOfParameters>%s%s</listOfParameters>%s'
-            '<listOfReactions>%s</listOfReactions>%s</model></sbml>\n'
+            '<listOfSpecies>%s</listOfSpecies><listOfParameters>%s%s</listOfParameters>%s%s'
+            '%s%s</model></sbml>\n'
             % (SPATIAL_NS, model_id, comps, sp, coords, "".join(params),
                ("<listOfInitialAssignments>%s</listOfInitialAssignments>" % ia) if ia else "",
-               "".join(reactions), _geometry(axes, dims, lo, hi)))
+               ("<listOfRules>%s</listOfRules>" % "".join(rules)) if rules else "",
+               ("<listOfReactions>%s</listOfReactions>" % "".join(reactions)) if reactions else "", _geometry(axes, dims, lo, hi)))
 
 
 def turing(nx, ny, nz=None, blob=True, bc_values=None, D=(4.0, 0.4)):
@@ -287,3 +288,81 @@ def membrane(nx, ny, nz=None, shape="disc", transport=True):
             '<listOfInitialAssignments>%s</listOfInitialAssignments>'
             '<listOfReactions>%s</listOfReactions>%s</model></sbml>\n'
             % (SPATIAL_NS, comps, species, coords, "".join(params), ia_xml, "".join(rx), _membrane_geometry(axes, dims, inside)))
+
+
+def membrane_box(nx, ny, nz=None):
+    """membrane() around a box-shaped cell: straight membrane segments and corners (the corner branches of the pseudo-membrane fill)."""
+    return membrane(nx, ny, nz, shape="box")
+
+
+_TIME = '<csymbol encoding="text" definitionURL="http://www.sbml.org/sbml/symbols/time"> t </csymbol>'
+
+
+def _assignment_rule(var, math):
+    return '<assignmentRule variable="%s"><math %s>%s</math></assignmentRule>' % (var, _MATH, math)
+
+
+def _rate_rule(var, math):
+    return '<rateRule variable="%s"><math %s>%s</math></rateRule>' % (var, _MATH, math)
+
+
+def _varparam(pid):
+    return '<parameter id="%s" constant="false"/>' % pid
+
+
+def rules(nx, ny, nz=None):
+    """Brusselator kinetics steered by ASSIGNMENT RULES that the reference re-evaluates after every step (updateAssignmentRules,
+    spatialsimulator.cpp:1566-1581): `act`, a field that depends on time and position (sin, exp, unary minus), `gain`, a field
+    that depends on the species (a division, abs, ln, root, power), `W`, a species defined by a rule, and `late`, a rule listed
+    before the rule it depends on (the dependency ordering of spatialsimulator.cpp:1108-1153).  dt 0.05."""
+    dims = [nx, ny] + ([nz] if nz else [])
+    axes = ["x", "y", "z"][:len(dims)]
+    params = _transport_params("X", 0.16, axes) + _transport_params("Y", 0.8, axes)
+    params += [_param("k", 0.1), _param("A", 2.5), _param("B", 5.24), _varparam("late"), _varparam("act"), _varparam("gain")]
+    species = [("X", None), ("Y", 2.0), ("W", None)]
+    assignments = [("X", _apply("plus", _cn(2.5), _apply("times", _cn(0.01), _ci("x"))))]
+    act = _apply("plus", _cn(1.0), _apply("times", _cn(0.4), _apply("sin", _apply("times", _cn(0.9), _TIME)),
+                                          _apply("exp", _apply("minus", _apply("times", _cn(0.02), _ci("y"))))))
+    gain = _apply("divide", _apply("plus", _cn(1.0), _apply("abs", _apply("minus", _ci("X"), _ci("Y")))),
+                  _apply("plus", _cn(1.5), _apply("ln", _apply("plus", _cn(1.0), _apply("root", _apply("power", _ci("Y"), _cn(2)))))))
+    rules_ = [_assignment_rule("late", _apply("times", _cn(0.5), _ci("act"), _ci("gain"))),
+              _assignment_rule("act", act), _assignment_rule("gain", gain),
+              _assignment_rule("W", _apply("times", _cn(0.5), _apply("plus", _ci("X"), _ci("Y"))))]
+    rx = [
+        _reaction("J0", [], [("X", 1)], _apply("times", _ci("k"), _ci("A"), _ci("act"))),
+        _reaction("J1", [("Y", 1)], [("X", 1)], _apply("times", _ci("k"), _ci("X"), _ci("X"), _ci("Y"))),
+        _reaction("J2", [("X", 1)], [("Y", 1)], _apply("times", _ci("k"), _ci("X"), _ci("B"), _ci("gain"))),
+        _reaction("J3", [("X", 1)], [], _apply("times", _ci("k"), _ci("X"), _apply("plus", _cn(0.8), _ci("late")))),
+    ]
+    return _document("synthetic_rules", axes, dims, species, params, assignments, rx, rules=rules_)
+
+
+def raterules(nx, ny, nz=None):
+    """Two diffusing species driven by RATE RULES only (no reactions, so that the reference's rInfoList[ruleIndex] is the rule
+    itself, spatialsimulator.cpp:1455-1461), with the rarely used operators in the laws: power, log to a base, xor / eq / neq,
+    piecewise, tanh, cos, a listed-but-empty operator that only pops (floor) and the `time` symbol.  dt 0.05."""
+    dims = [nx, ny] + ([nz] if nz else [])
+    axes = ["x", "y", "z"][:len(dims)]
+    params = _transport_params("P", 0.3, axes) + _transport_params("Q", 0.6, axes)
+    params += [_param("a", 0.7), _param("b", 0.2)]
+    species = [("P", None), ("Q", None)]
+    assignments = [("P", _apply("plus", _cn(1.0), _apply("times", _cn(0.02), _ci("x")))),
+                   ("Q", _apply("plus", _cn(0.5), _apply("times", _cn(0.01), _ci("y"))))]
+    # dP/dt = a*Q^1.5 - b*P*tanh(P) + 0.05*piecewise(1, xor(P > 1.2, Q > 0.6), 0) + 0.01*cos(t)
+    dP = _apply("plus",
+                _apply("minus", _apply("times", _ci("a"), _apply("power", _ci("Q"), _cn(1.5))),
+                       _apply("times", _ci("b"), _ci("P"), _apply("tanh", _ci("P")))),
+                _apply("times", _cn(0.05), _piecewise(_cn(1), _apply("xor", _apply("gt", _ci("P"), _cn(1.2)), _apply("gt", _ci("Q"), _cn(0.6))), _cn(0))),
+                _apply("times", _cn(0.01), _apply("cos", _TIME)))
+    # dQ/dt = 0.1*log_2(1 + P) - 0.3*Q*(Q != 0.5) + 0.02*(P == Q)
+    dQ = _apply("plus",
+                _apply("minus", _apply("times", _cn(0.1), "<apply><log/><logbase>%s</logbase>%s</apply>" % (_cn(2), _apply("plus", _cn(1.0), _ci("P")))),
+                       _apply("times", _cn(0.3), _ci("Q"), _apply("neq", _ci("Q"), _cn(0.5)))),
+                _apply("times", _cn(0.02), _apply("eq", _ci("P"), _ci("Q"))))
+    # dR/dt = (0.1 + 0.3) + 0.02*floor(P): floor is listed but empty in the reference's interpreter - it pops its operand and
+    # pushes nothing, the stream runs the stack empty and the rate is what was last stored at the bottom of the stack
+    dR = _apply("plus", _apply("plus", _cn(0.1), _cn(0.3)), _apply("times", _cn(0.02), _apply("floor", _ci("P"))))
+    rules_ = [_rate_rule("P", dP), _rate_rule("Q", dQ), _rate_rule("R", dR)]
+    species.append(("R", 1.0))
+    params += _transport_params("R", 0.2, axes)
+    return _document("synthetic_raterules", axes, dims, species, params, assignments, [], rules=rules_)

@@ -25,6 +25,19 @@ def model_path(name):
     return os.path.join(GOLDEN, "models", name + ".xml")
 
 
+def is_membrane_species(g, sp):
+    return ("memgeo/%s" % sp) in g.files
+
+
+def species_values(sim, g, sp):
+    """The values of a species laid out like the golden file stores them: compact volume cells, or - for a species that lives on
+    a membrane - its values at every classified point of that membrane (geo/<membrane>/points, doubled-grid indices)."""
+    if is_membrane_species(g, sp):
+        pts = g["geo/%s/points" % str(g["memgeo/%s" % sp])]
+        return np.asarray(sim.getVariable(sp))[pts]
+    return sim.getVariableCompact(sp)
+
+
 @pytest.fixture(scope="session")
 def lib():
     import spatial_sbml_b200 as sb

@@ -72,6 +72,16 @@ CASES = {
     "syn_cascade3_2d": ("synthetic:cascade3:150:40", (150, 40, 1), 0.05, [1, 10, 40], {}, []),
     # 3-D boundary pass: non-zero fluxes on all six sides, Dirichlet values on the z sides
     "syn_turing_3d_flux": ("synthetic:turing_flux3d:18:14:10", (18, 14, 10), 0.02, [1, 2, 10, 40], {}, []),
+    # species ON a membrane: surface diffusion over the Voronoi neighbours, binding / unbinding of a volume species, a reaction
+    # between membrane species, the pseudo-membrane fill, and a membrane transport beside them (no example has a membrane species)
+    # assignment rules re-evaluated after every step (time-, position- and species-dependent fields, a species defined by a rule)
+    "syn_rules_2d": ("synthetic:rules:30:26", (30, 26, 1), 0.05, [1, 2, 10, 100], {}, []),
+    "syn_rules_3d": ("synthetic:rules:14:12:10", (14, 12, 10), 0.05, [1, 10, 40], {}, []),
+    # rate rules only, with the rare operators: power, log to a base, xor, eq, neq, piecewise, tanh, cos, time, a pop-only operator
+    "syn_raterules_2d": ("synthetic:raterules:30:26", (30, 26, 1), 0.05, [1, 2, 10, 100], {}, []),
+    "syn_membrane_2d": ("synthetic:membrane:40:36", (40, 36, 1), 0.05, [1, 2, 10, 100], {}, []),
+    "syn_membrane_box_2d": ("synthetic:membrane_box:30:26", (30, 26, 1), 0.05, [1, 2, 10, 100], {}, []),
+    "syn_membrane_3d": ("synthetic:membrane:20:18:16", (20, 18, 16), 0.05, [1, 2, 10, 50], {}, []),
 }
 
 
@@ -158,6 +168,9 @@ def build_case(name):
             out["geo/%s/pseudoMemIndex" % g] = d[p + "pseudoMemIndex"].astype(np.int64)
             if p + "nuVec" in d:
                 out["geo/%s/nuVec" % g] = d[p + "nuVec"].reshape(-1, 3)
+            if p + "vorAdj" in d:  # per domainIndex entry: neighbours [XY0 YZ0 XZ0 XY1 YZ1 XZ1], s_ij, d_ij in the same slot order
+                out["geo/%s/vorAdj" % g] = d[p + "vorAdj"].reshape(-1, 6).astype(np.int64)
+                out["geo/%s/vorSiDi" % g] = d[p + "vorSiDi"].reshape(-1, 12)
         if p + "rpn" in d:
             out["geo/%s/rpn" % g] = np.array(d[p + "rpn"])
     i = 0
@@ -172,9 +185,20 @@ def build_case(name):
         if m and d[key].size > 1:
             species.append(m.group(1))
     out["species"] = np.array(species)
+    # a species that lives on a membrane is stored at every classified point of its membrane ("geo/<g>/points")
+    on_membrane = {}
+    for sp in species:
+        gname = d.get("var/%s/geo" % sp, "")
+        if gname and not int(d["geo/%s/isVol" % gname][0]):
+            on_membrane[sp] = np.flatnonzero(d["geo/%s/isDomain" % gname])
+            out["memgeo/%s" % sp] = np.array(gname)
     for s in [0] + steps:
         for sp in species:
             full = d["step/%d/%s" % (s, sp)]
+            if sp in on_membrane:
+                out["step/%d/%s" % (s, sp)] = full[on_membrane[sp]]
+                assert not np.delete(full, on_membrane[sp]).any(), "membrane species set off its membrane"
+                continue
             out["step/%d/%s" % (s, sp)] = even(full)
             if sp in advected:
                 v = full.reshape(Zi, Yi, Xi)

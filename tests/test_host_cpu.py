@@ -11,7 +11,7 @@ import re
 import numpy as np
 import pytest
 
-from conftest import REPO, golden_cases, load_golden, model_path
+from conftest import REPO, golden_cases, is_membrane_species, load_golden, model_path
 
 import spatial_sbml_b200 as sb
 
@@ -114,7 +114,7 @@ def test_membrane_classification_bit_exact(case):
     sim.close()
 
 
-@pytest.mark.parametrize("case", ["transport", "transport_rate"])
+@pytest.mark.parametrize("case", ["transport", "transport_rate", "syn_membrane_2d", "syn_membrane_box_2d", "syn_membrane_3d"])
 def test_membrane_normals_bit_exact(case):
     """nuVec at the membrane points of the models whose transport reactions read it
     (reference setInfoFunction.cpp:495-1546)."""
@@ -165,9 +165,36 @@ def test_initial_fields_bit_exact(case):
     for sp in [str(s) for s in g["species"]]:
         full = sim.getVariable(sp)
         assert full is not None, sp
+        if is_membrane_species(g, sp):
+            # a species on a membrane: its membrane and pseudo-membrane points (the latter filled with the smaller neighbour,
+            # boundaryFunction.cpp:98-111), zero everywhere else
+            pts = g["geo/%s/points" % str(g["memgeo/%s" % sp])]
+            assert np.array_equal(np.asarray(full)[pts], g["step/0/" + sp]), "initial values of %s on its membrane" % sp
+            assert not np.delete(np.asarray(full), pts).any()
+            continue
         assert np.array_equal(even(full, dims), g["step/0/" + sp]), "initial field of %s" % sp
         got = sim.getVariableCompact(sp)
         assert np.array_equal(got, g["step/0/" + sp])
+    sim.close()
+
+
+@pytest.mark.parametrize("case", [c for c in golden_cases() if "membrane" in c])
+def test_voronoi_neighbours_bit_exact(case):
+    """setVoronoiInfo (reference setInfoFunction.cpp:1134-1546): the contour neighbours of every membrane point, the facet
+    lengths s_ij (3-D: bisector intersections in the rotated tangent plane) and the distances d_ij after the symmetrising
+    average, against the reference's own vorI array."""
+    sim, g, dims = host_sim(case)
+    checked = 0
+    for name in [str(s) for s in g["geo_names"]]:
+        key = "geo/%s/vorAdj" % name
+        if key not in g.files or not len(g[key]):
+            continue
+        rows = np.array([[float(x) for x in l.split()] for l in sim.getSetupText("voronoi/" + name).strip().split("\n")])
+        assert np.array_equal(rows[:, :6].astype(np.int64), g[key]), "%s neighbours" % name
+        assert np.array_equal(rows[:, 6:12], g["geo/%s/vorSiDi" % name][:, :6]), "%s s_ij" % name
+        assert np.array_equal(rows[:, 12:18], g["geo/%s/vorSiDi" % name][:, 6:]), "%s d_ij" % name
+        checked += 1
+    assert checked >= 1
     sim.close()
 
 

@@ -29,7 +29,9 @@ RESTATED = {"turing_tiny": 1000, "turing_tiny_cl": 100, "turing_uniform": 100, "
             # cipCSLR restated on the doubled grid (cell + face values)
             "advection": 100,
             # calcMemTransport restated per membrane point (incl. the rpStack[1] rate quirk)
-            "transport": 100, "transport_rate": 100}
+            "transport": 100, "transport_rate": 100,
+            # rate rules only; power, log to a base, xor / eq / neq, tanh, cos, time and a pop-only operator in the laws
+            "syn_raterules_2d": 100}
 
 
 def build(case):
@@ -58,10 +60,20 @@ def test_restatement_matches_reference_bit_for_bit(case):
     assert done > 0
 
 
+# Goldens the numpy restatement does not cover: species ON a membrane (calcMemDiffusion, binding, pseudo-membrane fill) and
+# per-step assignment rules.  Those
+# paths are pinned to the reference directly: the device is compared with the reference's own fields (tests/test_parity_gpu.py)
+# and the host set-up (Voronoi neighbours, s_ij, d_ij, normals, initial values) with the reference's arrays (tests/test_host_cpu.py).
+NOT_RESTATED = {"syn_membrane_2d", "syn_membrane_box_2d", "syn_membrane_3d",
+                # assignment rules re-evaluated every step (updateAssignmentRules): pinned the same way
+                "syn_rules_2d", "syn_rules_3d"}
+
+
 def test_every_golden_case_is_restated():
-    """The restatement now covers every path the goldens exercise: no case may be missing from the table above."""
+    """The restatement covers every path the goldens exercise except the ones listed (with the reason) above."""
     from conftest import golden_cases
-    assert sorted(RESTATED) == sorted(golden_cases())
+    assert sorted(set(RESTATED) | NOT_RESTATED) == sorted(golden_cases())
+    assert not (set(RESTATED) & NOT_RESTATED)
 
 
 @pytest.mark.parametrize("case", ["turing_tiny", "syn_turing_3d"])
