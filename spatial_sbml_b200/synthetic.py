@@ -366,3 +366,120 @@ def raterules(nx, ny, nz=None):
     species.append(("R", 1.0))
     params += _transport_params("R", 0.2, axes)
     return _document("synthetic_raterules", axes, dims, species, params, assignments, [], rules=rules_)
+
+
+def sampled(nx, ny):
+    """The Brusselator in a cell whose shape comes from an IMAGE: a SampledFieldGeometry (reference spatialsimulator.cpp:483-604;
+    the image rows are stored top-down, so sample (x, y) of the grid is row numSamples2 - 1 - y) with two sampled volumes, an
+    L-shaped cell (value 1) in a bath (value 0), and the membrane between them.  dt 0.05."""
+    img = [[0] * nx for _ in range(ny)]
+    for y in range(ny):
+        for x in range(nx):
+            in_l = (3 <= x <= nx // 3 and 3 <= y <= ny - 4) or (3 <= x <= nx - 5 and 3 <= y <= ny // 3)
+            in_hole = (5 <= x <= 7 and 5 <= y <= 7)
+            img[ny - 1 - y][x] = 1 if (in_l and not in_hole) else 0
+    samples = " ".join(str(v) for row in img for v in row)
+    axes, dims = ["x", "y"], [nx, ny]
+    kinds = {"x": "cartesianX", "y": "cartesianY"}
+    cc = "".join('<spatial:coordinateComponent spatial:id="%s" spatial:type="%s">'
+                 '<spatial:boundaryMin spatial:id="%smin" spatial:value="0"/>'
+                 '<spatial:boundaryMax spatial:id="%smax" spatial:value="%d"/></spatial:coordinateComponent>'
+                 % (a, kinds[a], a.upper(), a.upper(), n - 1) for a, n in zip(axes, dims))
+    geometry = ('<spatial:geometry spatial:id="geometry" spatial:coordinateSystem="cartesian">'
+                '<spatial:listOfCoordinateComponents>%s</spatial:listOfCoordinateComponents>'
+                '<spatial:listOfDomainTypes><spatial:domainType spatial:id="dt_cell" spatial:spatialDimensions="3"/>'
+                '<spatial:domainType spatial:id="dt_out" spatial:spatialDimensions="3"/>'
+                '<spatial:domainType spatial:id="dt_mem" spatial:spatialDimensions="2"/></spatial:listOfDomainTypes>'
+                '<spatial:listOfDomains><spatial:domain spatial:id="dom_cell" spatial:domainType="dt_cell"/>'
+                '<spatial:domain spatial:id="dom_out" spatial:domainType="dt_out"/>'
+                '<spatial:domain spatial:id="dom_mem" spatial:domainType="dt_mem"/></spatial:listOfDomains>'
+                '<spatial:listOfAdjacentDomains>'
+                '<spatial:adjacentDomains spatial:id="ad0" spatial:domain1="dom_mem" spatial:domain2="dom_cell"/>'
+                '<spatial:adjacentDomains spatial:id="ad1" spatial:domain1="dom_mem" spatial:domain2="dom_out"/>'
+                '</spatial:listOfAdjacentDomains>'
+                '<spatial:listOfGeometryDefinitions><spatial:sampledFieldGeometry spatial:id="sfg" spatial:isActive="true" '
+                'spatial:sampledField="img"><spatial:listOfSampledVolumes>'
+                '<spatial:sampledVolume spatial:id="sv_cell" spatial:domainType="dt_cell" spatial:sampledValue="1"/>'
+                '<spatial:sampledVolume spatial:id="sv_out" spatial:domainType="dt_out" spatial:sampledValue="0"/>'
+                '</spatial:listOfSampledVolumes></spatial:sampledFieldGeometry></spatial:listOfGeometryDefinitions>'
+                '<spatial:listOfSampledFields><spatial:sampledField spatial:id="img" spatial:dataType="uint8" '
+                'spatial:numSamples1="%d" spatial:numSamples2="%d" spatial:numSamples3="1" spatial:interpolationType="nearestNeighbor" '
+                'spatial:compression="uncompressed" spatial:samplesLength="%d">%s</spatial:sampledField></spatial:listOfSampledFields>'
+                '</spatial:geometry>' % (cc, nx, ny, nx * ny, samples))
+    comps = ('<compartment id="cell" spatialDimensions="3" size="1" constant="true">'
+             '<spatial:compartmentMapping spatial:id="m_cell" spatial:domainType="dt_cell" spatial:unitSize="1"/></compartment>'
+             '<compartment id="bath" spatialDimensions="3" size="1" constant="true">'
+             '<spatial:compartmentMapping spatial:id="m_out" spatial:domainType="dt_out" spatial:unitSize="1"/></compartment>'
+             '<compartment id="mem" spatialDimensions="2" size="1" constant="true">'
+             '<spatial:compartmentMapping spatial:id="m_mem" spatial:domainType="dt_mem" spatial:unitSize="1"/></compartment>')
+    def sp(sid, comp, conc):
+        return ('<species id="%s" compartment="%s" hasOnlySubstanceUnits="false" boundaryCondition="false" constant="false" '
+                'spatial:isSpatial="true"%s/>' % (sid, comp, (' initialConcentration="%r"' % float(conc)) if conc is not None else ""))
+    species = sp("X", "cell", None) + sp("Y", "cell", 2.0) + sp("E", "bath", 0.1)
+    params = _transport_params("X", 0.16, axes) + _transport_params("Y", 0.8, axes) + _transport_params("E", 0.4, axes)
+    params += [_param("k", 0.1), _param("A", 2.5), _param("B", 5.24), _param("kl", 0.05)]
+    coords = "".join(_param(a, 0.0, '<spatial:spatialSymbolReference spatial:spatialRef="%s"/>' % a) for a in axes)
+    ia = '<initialAssignment symbol="X"><math %s>%s</math></initialAssignment>' % (
+        _MATH, _apply("plus", _cn(2.5), _apply("times", _cn(0.02), _ci("x"))))
+    rx = [_reaction("J0", [], [("X", 1)], _apply("times", _ci("k"), _ci("A"))),
+          _reaction("J1", [("Y", 1)], [("X", 1)], _apply("times", _ci("k"), _ci("X"), _ci("X"), _ci("Y"))),
+          _reaction("J2", [("X", 1)], [("Y", 1)], _apply("times", _ci("k"), _ci("X"), _ci("B"))),
+          _reaction("J3", [("X", 1)], [], _apply("times", _ci("k"), _ci("X"))),
+          _reaction("leak", [("Y", 1)], [("E", 1)], _apply("times", _ci("kl"), _ci("Y")))]
+    return ('<?xml version="1.0" encoding="UTF-8"?>\n'
+            '<sbml xmlns="http://www.sbml.org/sbml/level3/version1/core" xmlns:spatial="%s" level="3" version="1" '
+            'spatial:required="true"><model id="synthetic_sampled"><listOfCompartments>%s</listOfCompartments>'
+            '<listOfSpecies>%s</listOfSpecies><listOfParameters>%s%s</listOfParameters>'
+            '<listOfInitialAssignments>%s</listOfInitialAssignments>'
+            '<listOfReactions>%s</listOfReactions>%s</model></sbml>\n'
+            % (SPATIAL_NS, comps, species, coords, "".join(params), ia, "".join(rx), geometry))
+
+
+def fieldcoeff(nx, ny, nz=None):
+    """Diffusion coefficients that are FIELDS (a parameter with an initial assignment in x / y: the reference reads
+    diffCInfo->value[index] per cell, calcPDE.cpp:486-511) on a grid with non-unit spacing would take the general stencil path;
+    here the spacing is 1 and only the coefficients vary.  Brusselator kinetics.  dt 0.05."""
+    dims = [nx, ny] + ([nz] if nz else [])
+    axes = ["x", "y", "z"][:len(dims)]
+    kinds = {"x": "cartesianX", "y": "cartesianY", "z": "cartesianZ"}
+    params = []
+    ia = [("X", _apply("plus", _cn(2.5), _apply("times", _cn(0.03), _ci("x")))),
+          ("Y", _apply("plus", _cn(2.0), _apply("times", _cn(0.02), _ci("y"))))]
+    for s_, base in (("X", 0.16), ("Y", 0.5)):
+        for k_, a in enumerate(axes):
+            pid = "%s_diff_%s" % (s_, a)
+            params.append('<parameter id="%s" constant="true"><spatial:diffusionCoefficient spatial:variable="%s" '
+                          'spatial:type="isotropic" spatial:coordinateReference1="%s"/></parameter>' % (pid, s_, kinds[a]))
+            ia.append((pid, _apply("plus", _cn(base), _apply("times", _cn(0.004 * (k_ + 1)), _ci(axes[(k_ + 1) % len(axes)])))))
+        for a in axes:
+            for side in ("min", "max"):
+                b = "%s%s" % (a.upper(), side)
+                params.append(_param("%s_BC_%s" % (s_, b), 0.0, '<spatial:boundaryCondition spatial:variable="%s" spatial:type="Neumann" '
+                                                               'spatial:coordinateBoundary="%s"/>' % (s_, b)))
+    params += [_param("k", 0.1), _param("A", 2.5), _param("B", 5.24)]
+    rx = [_reaction("J0", [], [("X", 1)], _apply("times", _ci("k"), _ci("A"))),
+          _reaction("J1", [("Y", 1)], [("X", 1)], _apply("times", _ci("k"), _ci("X"), _ci("X"), _ci("Y"))),
+          _reaction("J2", [("X", 1)], [("Y", 1)], _apply("times", _ci("k"), _ci("X"), _ci("B"))),
+          _reaction("J3", [("X", 1)], [], _apply("times", _ci("k"), _ci("X")))]
+    return _document("synthetic_fieldcoeff", axes, dims, [("X", None), ("Y", None)], params, ia, rx)
+
+
+def chain6(nx, ny, nz=None):
+    """Six diffusing species in one compartment, a linear conversion chain S0 -> S1 -> ... -> S5 -> (degraded) with a feed into S0
+    and one nonlinear step: more staged species than the rd_stage kernel variants hold (4), so the first-generation stage kernel's
+    8-species instantiation runs.  dt 0.05."""
+    dims = [nx, ny] + ([nz] if nz else [])
+    axes = ["x", "y", "z"][:len(dims)]
+    names = ["S%d" % i for i in range(6)]
+    params = []
+    for i, n in enumerate(names):
+        params += _transport_params(n, 0.1 + 0.07 * i, axes)
+    params += [_param("kf", 0.2), _param("kc", 0.15), _param("kd", 0.05)]
+    species = [(n, None if i == 0 else 0.1 * (i + 1)) for i, n in enumerate(names)]
+    assignments = [("S0", _apply("plus", _cn(1.0), _apply("times", _cn(0.02), _ci("x")), _apply("times", _cn(0.01), _ci("y"))))]
+    rx = [_reaction("feed", [], [("S0", 1)], _ci("kf"))]
+    for i in range(5):
+        law = _apply("times", _ci("kc"), _ci(names[i])) if i != 2 else _apply("times", _ci("kc"), _ci(names[i]), _ci(names[i + 1]))
+        rx.append(_reaction("c%d" % i, [(names[i], 1)], [(names[i + 1], 1)], law))
+    rx.append(_reaction("deg", [("S5", 1)], [], _apply("times", _ci("kd"), _ci("S5"))))
+    return _document("synthetic_chain6", axes, dims, species, params, assignments, rx)

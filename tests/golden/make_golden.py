@@ -79,6 +79,13 @@ CASES = {
     "syn_rules_3d": ("synthetic:rules:14:12:10", (14, 12, 10), 0.05, [1, 10, 40], {}, []),
     # rate rules only, with the rare operators: power, log to a base, xor, eq, neq, piecewise, tanh, cos, time, a pop-only operator
     "syn_raterules_2d": ("synthetic:raterules:30:26", (30, 26, 1), 0.05, [1, 2, 10, 100], {}, []),
+    # geometry from an image (SampledFieldGeometry, y-flipped sample rows), a membrane transport across its membrane
+    "syn_sampled_2d": ("synthetic:sampled:34:28", (34, 28, 1), 0.05, [1, 2, 10, 100], {}, []),
+    # diffusion coefficients that are fields (the general stencil path of the stage kernel)
+    "syn_fieldcoeff_2d": ("synthetic:fieldcoeff:40:30", (40, 30, 1), 0.05, [1, 10, 100], {}, []),
+    "syn_fieldcoeff_3d": ("synthetic:fieldcoeff:16:12:10", (16, 12, 10), 0.05, [1, 10, 40], {}, []),
+    # six staged species: the first-generation stage kernel's 8-species instantiation
+    "syn_chain6_2d": ("synthetic:chain6:70:24", (70, 24, 1), 0.05, [1, 10, 100], {}, []),
     "syn_membrane_2d": ("synthetic:membrane:40:36", (40, 36, 1), 0.05, [1, 2, 10, 100], {}, []),
     "syn_membrane_box_2d": ("synthetic:membrane_box:30:26", (30, 26, 1), 0.05, [1, 2, 10, 100], {}, []),
     "syn_membrane_3d": ("synthetic:membrane:20:18:16", (20, 18, 16), 0.05, [1, 2, 10, 50], {}, []),

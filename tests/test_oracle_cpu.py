@@ -31,7 +31,9 @@ RESTATED = {"turing_tiny": 1000, "turing_tiny_cl": 100, "turing_uniform": 100, "
             # calcMemTransport restated per membrane point (incl. the rpStack[1] rate quirk)
             "transport": 100, "transport_rate": 100,
             # rate rules only; power, log to a base, xor / eq / neq, tanh, cos, time and a pop-only operator in the laws
-            "syn_raterules_2d": 100}
+            "syn_raterules_2d": 100,
+            # geometry from an image + a membrane transport; six species
+            "syn_sampled_2d": 100, "syn_chain6_2d": 100}
 
 
 def build(case):
@@ -66,7 +68,9 @@ def test_restatement_matches_reference_bit_for_bit(case):
 # and the host set-up (Voronoi neighbours, s_ij, d_ij, normals, initial values) with the reference's arrays (tests/test_host_cpu.py).
 NOT_RESTATED = {"syn_membrane_2d", "syn_membrane_box_2d", "syn_membrane_3d",
                 # assignment rules re-evaluated every step (updateAssignmentRules): pinned the same way
-                "syn_rules_2d", "syn_rules_3d"}
+                "syn_rules_2d", "syn_rules_3d",
+                # field-valued diffusion coefficients (the restatement takes uniform coefficients only)
+                "syn_fieldcoeff_2d", "syn_fieldcoeff_3d"}
 
 
 def test_every_golden_case_is_restated():
