@@ -255,6 +255,35 @@ SB2_API int sb2_begin_step(sb2_sim* sim, double t_arg, double dt, int time_slot)
 SB2_API int sb2_stage(sb2_sim* sim, int m, int phase);
 SB2_API int sb2_stage_on(sb2_sim* sim, int m, int phase, void* cuda_stream); /* the same on another stream (ordering: caller's events) */
 SB2_API int sb2_end_step(sb2_sim* sim);
+/* ---- sharded stepping, orchestrated by the library -------------------------------------------------------
+ * A handle that owns rows [own_lo, own_hi) of a larger grid steps with sb2_sharded_begin + a loop over sb2_sharded_next.  The
+ * library decides which rows run when and on which of its streams (edge rows first, on a high-priority stream, so that their
+ * transfer overlaps the interior kernel) and what has to travel: whenever sb2_sharded_next returns 1 the caller exchanges the
+ * rows described by *x with the neighbouring slabs — for every buffer, send the first `width` owned rows to the slab below
+ * and the last `width` owned rows to the slab above, receive the neighbours' rows into the `width` halo rows on either side —
+ * queued on x->stream (a cudaStream_t that already waits for the producing kernels), with NCCL send / recv, peer copies, or
+ * anything else that is stream-ordered, and calls sb2_sharded_next again.  0 = the step is complete.  Row r of a buffer is
+ * ptr + base + r * unit (doubles).  What travels per step: k_m after each of the first three stages (and u where a Dirichlet
+ * condition rewrites it), the new u after the last one; for models with advection u and the face values after every
+ * CIP-CSLR pass (two rows); the new u after the update when it is not fused into the last stage. */
+#define SB2_MAX_XBUF 40
+typedef struct {
+  int32_t n;                 /* buffers */
+  void* ptr[SB2_MAX_XBUF];   /* device arrays of doubles */
+  int32_t width;             /* rows (2-D) / planes (3-D) per side */
+  int64_t unit, base;        /* doubles per row / plane; offset of local row 0 */
+  int32_t own_lo, own_hi;    /* owned local rows */
+  int32_t has_lo, has_hi;    /* a neighbouring slab exists below / above */
+  void* stream;              /* cudaStream_t to queue the exchange on */
+  void* ready_event;         /* cudaEvent_t recorded when the rows to send are final (for callers that PULL from a neighbour) */
+  int32_t device;
+} sb2_exchange;
+SB2_API int sb2_sharded_begin(sb2_sim* sim, double t_arg, double dt, int time_slot);
+SB2_API int sb2_sharded_next(sb2_sim* sim, sb2_exchange* x);
+/* One step of n slabs held by ONE process (handles on the same or on different devices; sims[i] lies below sims[i+1]): the
+ * loop above with peer copies between the handles.  A C++ caller of SpatialSimulator gets its multi-GPU step from this. */
+SB2_API int sb2_group_step(sb2_sim* const* sims, int n, double t_arg, double dt, int time_slot);
+
 /* After sb2_begin_step: 1 when the RK combine of this step is fused into stage 3 (the new u is
  * written to view 5 by sb2_stage(3, ...)), 0 when sb2_end_step computes it in place. */
 SB2_API int sb2_combine_is_fused(const sb2_sim* sim);

@@ -34,6 +34,10 @@ SSB_API int ssb_is_initialized(ssb_sim* s);
 SSB_API void ssb_set_device(ssb_sim* s, int ordinal);             /* before init */
 SSB_API void ssb_set_host_only(ssb_sim* s, int host_only);        /* before init */
 SSB_API void ssb_set_slab(ssb_sim* s, int lo, int hi);            /* before init: owned rows of the slab axis */
+/* before init: several GPUs behind one simulator - one slab of the grid per entry (an ordinal may repeat), stepped by the
+ * library's sharded step with peer copies of the halo rows; results are bit-identical to one device */
+SSB_API void ssb_set_devices(ssb_sim* s, const int* ordinals, int n);
+SSB_API int ssb_get_num_slabs(ssb_sim* s);
 SSB_API void ssb_set_cuda_stream(ssb_sim* s, void* cuda_stream);
 
 SSB_API int ssb_init_from_file(ssb_sim* s, const char* file, int xdim, int ydim, int zdim);   /* :66 */

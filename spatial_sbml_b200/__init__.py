@@ -100,6 +100,9 @@ def _proto(lib):
         "sb2_stage_on": (ci, [vp, ci, ci, vp]),
         "sb2_end_step": (ci, [vp]),
         "sb2_combine_is_fused": (ci, [vp]),
+        "sb2_sharded_begin": (ci, [vp, cd, cd, ci]),
+        "sb2_sharded_next": (ci, [vp, vp]),
+        "sb2_group_step": (ci, [C.POINTER(vp), ci, cd, cd, ci]),
         "sb2_launch_count": (C.c_int64, [vp]),
         "sb2_program_text": (ci, [vp, C.c_char_p, ci]),
         "sb2_specialized": (ci, [vp]),
@@ -114,6 +117,8 @@ def _proto(lib):
         "ssb_set_device": (None, [vp, ci]),
         "ssb_set_host_only": (None, [vp, ci]),
         "ssb_set_slab": (None, [vp, ci, ci]),
+        "ssb_set_devices": (None, [vp, C.POINTER(ci), ci]),
+        "ssb_get_num_slabs": (ci, [vp]),
         "ssb_set_cuda_stream": (None, [vp, vp]),
         "ssb_init_from_file": (ci, [vp, cs, ci, ci, ci]),
         "ssb_init_from_string": (ci, [vp, cs, ci, ci, ci]),
@@ -201,10 +206,15 @@ class SpatialSimulator(object):
     """Python face of the SpatialSimulator class (same method names as the reference's
     SpatialSBML/spatialsimulator.h:49-294, snake_case aliases not provided on purpose)."""
 
-    def __init__(self, device=0, host_only=False, stream=None, slab=None):
+    def __init__(self, device=0, host_only=False, stream=None, slab=None, devices=None):
+        """devices: list of CUDA ordinals (one may repeat): the grid is cut into one slab per entry and stepped by all of them
+        (SpatialSimulator::setDevices); results are bit-identical to one device."""
         self._lib = load_library()
         self._h = self._lib.ssb_new()
         self._lib.ssb_set_device(self._h, int(device))
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            self._lib.ssb_set_devices(self._h, arr, len(devices))
         if host_only:
             self._lib.ssb_set_host_only(self._h, 1)
         if slab is not None:
@@ -368,6 +378,9 @@ class SpatialSimulator(object):
 
     def getNumStagedSpecies(self):
         return self._lib.ssb_get_num_staged_species(self._h)
+
+    def getNumSlabs(self):
+        return self._lib.ssb_get_num_slabs(self._h)
 
     def getTimeSlot(self):
         """Constants-table slot of the model's `time` symbol (what sb2_begin_step takes), -1 when unused."""

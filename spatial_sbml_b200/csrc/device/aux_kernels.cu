@@ -37,6 +37,7 @@ struct BcEntry {
   int64_t cell, valcell;
   int side;
   int seq;
+  int slabc;  // row (2-D) / plane (3-D) of the written cell along the slab axis
 };
 
 struct BcKernelArgs {
@@ -77,12 +78,17 @@ __global__ void __launch_bounds__(128) bc_kernel(const __grid_constant__ BcKerne
 
 }  // namespace
 
+// out[0]: every owned row; for a slab also out[1]: the edge_w owned rows next to each neighbouring slab, out[2]: the other
+// owned rows (the boundary pass of a sharded step is split like its stage kernels)
 int sb2_build_boundary_lists(const sb2_grid& g, int64_t P, int64_t PL, int64_t first,
                              const std::vector<std::vector<uint8_t> >& h_flags, const std::vector<Sb2BcSpecies>& bcs,
-                             const double* consts, cudaStream_t stream, Sb2BoundaryLists& out, std::string& err) {
+                             const double* consts, cudaStream_t stream, int edge_w, Sb2BoundaryLists* out3, std::string& err) {
   (void)consts;
-  memset(&out, 0, sizeof(out));
-  out.delta[0] = g.dx; out.delta[1] = g.dy; out.delta[2] = g.dz;
+  Sb2BoundaryLists& out = out3[0];
+  for (int part = 0; part < 3; ++part) {
+    memset(&out3[part], 0, sizeof(out3[part]));
+    out3[part].delta[0] = g.dx; out3[part].delta[1] = g.dy; out3[part].delta[2] = g.dz;
+  }
   std::vector<BcEntry> entries;
   const int nx = g.nx, ny = g.ny, nz = g.nz;
   auto pad = [&](int i, int j, int k) { return first + (int64_t)k * PL + (int64_t)j * P + i; };
@@ -92,7 +98,8 @@ int sb2_build_boundary_lists(const sb2_grid& g, int64_t P, int64_t PL, int64_t f
   const int own_lo = whole ? 0 : g.own_lo, own_hi = whole ? n_held : g.own_hi;
   const int gj0 = g.dim == 2 ? g.row0 : 0, gk0 = g.dim == 3 ? g.row0 : 0;
   for (size_t s = 0; s < bcs.size(); ++s) {
-    for (int k = 0; k < 6; ++k) { out.kind[s][k] = bcs[s].kind[k]; out.skind[s][k] = bcs[s].skind[k]; out.src[s][k] = bcs[s].src[k]; }
+    for (int part = 0; part < 3; ++part)
+      for (int k = 0; k < 6; ++k) { out3[part].kind[s][k] = bcs[s].kind[k]; out3[part].skind[s][k] = bcs[s].skind[k]; out3[part].src[s][k] = bcs[s].src[k]; }
     if (!bcs[s].has_bc) continue;
     const std::vector<uint8_t>& fl = h_flags[bcs[s].geo];
     auto dom = [&](int i, int j, int k) -> bool {
@@ -110,7 +117,7 @@ int sb2_build_boundary_lists(const sb2_grid& g, int64_t P, int64_t PL, int64_t f
         const int slabc = g.dim == 3 ? ak : aj;
         if (slabc < own_lo || slabc >= own_hi) return;
         BcEntry e;
-        e.species = (int)s; e.cell = pad(ai, aj, ak); e.valcell = pad(vi, vj, vk); e.side = side; e.seq = 0;
+        e.species = (int)s; e.cell = pad(ai, aj, ak); e.valcell = pad(vi, vj, vk); e.side = side; e.seq = 0; e.slabc = slabc;
         local.push_back(e);
       };
       for (int64_t row = row_begin; row < row_end; ++row) {
@@ -169,32 +176,41 @@ int sb2_build_boundary_lists(const sb2_grid& g, int64_t P, int64_t PL, int64_t f
     if (a.species != b.species) return a.species < b.species;
     return a.cell < b.cell;
   });
-  std::vector<int32_t> gstart, gspecies, eside;
-  std::vector<int64_t> ecell, evalcell;
-  for (size_t i = 0; i < entries.size(); ++i) {
-    if (i == 0 || entries[i].species != entries[i - 1].species || entries[i].cell != entries[i - 1].cell) {
-      gstart.push_back((int32_t)i);
-      gspecies.push_back(entries[i].species);
+  const bool lo_nb = !whole && own_lo > 0, hi_nb = !whole && own_hi < n_held;
+  for (int part = 0; part < (whole ? 1 : 3); ++part) {
+    Sb2BoundaryLists& o = out3[part];
+    std::vector<int32_t> gstart, gspecies, eside;
+    std::vector<int64_t> ecell, evalcell;
+    int last = -1;
+    for (size_t i = 0; i < entries.size(); ++i) {
+      const bool edge = (lo_nb && entries[i].slabc < own_lo + edge_w) || (hi_nb && entries[i].slabc >= own_hi - edge_w);
+      if ((part == 1 && !edge) || (part == 2 && edge)) continue;
+      if (last < 0 || entries[i].species != entries[last].species || entries[i].cell != entries[last].cell) {
+        gstart.push_back((int32_t)ecell.size());
+        gspecies.push_back(entries[i].species);
+      }
+      last = (int)i;
+      ecell.push_back(entries[i].cell);
+      evalcell.push_back(entries[i].valcell);
+      eside.push_back(entries[i].side);
+      const int kind = bcs[entries[i].species].kind[entries[i].side];
+      if (kind == SB2_BC_NEUMANN) o.n_neumann++;
+      if (kind == SB2_BC_DIRICHLET) o.n_dirichlet++;
     }
-    ecell.push_back(entries[i].cell);
-    evalcell.push_back(entries[i].valcell);
-    eside.push_back(entries[i].side);
-    const int kind = bcs[entries[i].species].kind[entries[i].side];
-    if (kind == SB2_BC_NEUMANN) out.n_neumann++;
-    if (kind == SB2_BC_DIRICHLET) out.n_dirichlet++;
+    gstart.push_back((int32_t)ecell.size());
+    o.n_groups = (int)gspecies.size();
+    o.n_entries = (int)ecell.size();
+    cudaError_t e;
+    if ((e = to_device(&o.d_group_start, gstart, stream)) != cudaSuccess ||
+        (e = to_device(&o.d_group_species, gspecies, stream)) != cudaSuccess ||
+        (e = to_device(&o.d_entry_cell, ecell, stream)) != cudaSuccess ||
+        (e = to_device(&o.d_entry_valcell, evalcell, stream)) != cudaSuccess ||
+        (e = to_device(&o.d_entry_side, eside, stream)) != cudaSuccess) {
+      err = std::string("boundary lists: ") + cudaGetErrorString(e);
+      return SB2_ERR_CUDA;
+    }
   }
-  gstart.push_back((int32_t)entries.size());
-  out.n_groups = (int)gspecies.size();
-  out.n_entries = (int)entries.size();
-  cudaError_t e;
-  if ((e = to_device(&out.d_group_start, gstart, stream)) != cudaSuccess ||
-      (e = to_device(&out.d_group_species, gspecies, stream)) != cudaSuccess ||
-      (e = to_device(&out.d_entry_cell, ecell, stream)) != cudaSuccess ||
-      (e = to_device(&out.d_entry_valcell, evalcell, stream)) != cudaSuccess ||
-      (e = to_device(&out.d_entry_side, eside, stream)) != cudaSuccess) {
-    err = std::string("boundary lists: ") + cudaGetErrorString(e);
-    return SB2_ERR_CUDA;
-  }
+  (void)out;
   return SB2_OK;
 }
 
@@ -204,8 +220,8 @@ void sb2_free_boundary_lists(Sb2BoundaryLists& l) {
   memset(&l, 0, sizeof(l));
 }
 
-bool sb2_neumann_active(const Sb2BoundaryLists& l, int nspecies, const double* consts) {
-  if (l.n_neumann == 0) return false;
+bool sb2_neumann_active(const Sb2BoundaryLists& l, int nspecies, const double* consts, bool whole_grid) {
+  if (whole_grid && l.n_neumann == 0) return false;
   for (int s = 0; s < nspecies; ++s)
     for (int k = 0; k < 6; ++k) {
       if (l.kind[s][k] != SB2_BC_NEUMANN) continue;
@@ -263,7 +279,7 @@ __device__ __forceinline__ bool cip_dom(const Sb2CipArgs& A, int64_t idx, int c,
 // flux loop of one direction pass (calcPDE.cpp:581-651 for X; Y and Z passes are identical up to the axis)
 __global__ void __launch_bounds__(256) cip_flux_kernel(const __grid_constant__ Sb2CipArgs A, int axis) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = blockIdx.y, k = blockIdx.z;
+  const int j = blockIdx.y + (A.dim == 2 ? A.row_begin : 0), k = blockIdx.z + (A.dim == 3 ? A.row_begin : 0);
   if (i >= A.nx) return;
   const int64_t idx = A.first + (int64_t)k * A.PL + (int64_t)j * A.P + i;
   const uint32_t f = A.flags[idx];
@@ -331,7 +347,7 @@ __global__ void __launch_bounds__(256) cip_flux_kernel(const __grid_constant__ S
 // update sweep (calcPDE.cpp:654-673): add the increments and advance the faces of the other axes
 __global__ void __launch_bounds__(256) cip_update_kernel(const __grid_constant__ Sb2CipArgs A, int axis) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = blockIdx.y, k = blockIdx.z;
+  const int j = blockIdx.y + (A.dim == 2 ? A.row_begin : 0), k = blockIdx.z + (A.dim == 3 ? A.row_begin : 0);
   if (i >= A.nx) return;
   const int64_t idx = A.first + (int64_t)k * A.PL + (int64_t)j * A.P + i;
   const double dc = A.tmp_cell[idx];
@@ -352,23 +368,23 @@ __global__ void __launch_bounds__(256) cip_update_kernel(const __grid_constant__
 
 }  // namespace
 
-cudaError_t sb2_launch_cip(const Sb2CipArgs& a, cudaStream_t stream, int* launches) {
-  dim3 block(256), grid((a.nx + 255) / 256, a.ny, a.nz);
-  for (int axis = 0; axis < a.dim; ++axis) {
-    // the reference runs the update sweep of a pass even without a velocity along it; with zero
-    // increments that sweep changes nothing, so the whole pass is skipped here
-    if (a.akind[axis] == SB2_SRC_NONE) continue;
-    cudaError_t e = cudaMemsetAsync(a.tmp_cell, 0, sizeof(double) * a.nalloc, stream);
-    if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(a.tmp_face, 0, sizeof(double) * a.nalloc, stream);
-    if (e != cudaSuccess) return e;
-    if (launches) *launches += 2;
-    cip_flux_kernel<<<grid, block, 0, stream>>>(a, axis);
-    cip_update_kernel<<<grid, block, 0, stream>>>(a, axis);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-  }
-  return cudaSuccess;
+cudaError_t sb2_launch_cip_pass(const Sb2CipArgs& a, int axis, cudaStream_t stream, int* launches) {
+  // the reference runs the update sweep of a pass even without a velocity along it; with zero
+  // increments that sweep changes nothing, so the caller skips such passes
+  if (a.akind[axis] == SB2_SRC_NONE) return cudaSuccess;
+  const int nflux = a.flux_row_end - a.row_begin, nupd = a.row_end - a.row_begin;
+  if (nupd <= 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(a.tmp_cell, 0, sizeof(double) * a.nalloc, stream);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(a.tmp_face, 0, sizeof(double) * a.nalloc, stream);
+  if (e != cudaSuccess) return e;
+  if (launches) *launches += 2;
+  dim3 block(256);
+  dim3 gflux((a.nx + 255) / 256, a.dim == 2 ? nflux : a.ny, a.dim == 3 ? nflux : 1);
+  dim3 gupd((a.nx + 255) / 256, a.dim == 2 ? nupd : a.ny, a.dim == 3 ? nupd : 1);
+  cip_flux_kernel<<<gflux, block, 0, stream>>>(a, axis);
+  cip_update_kernel<<<gupd, block, 0, stream>>>(a, axis);
+  return cudaGetLastError();
 }
 
 // =============================================================================================

@@ -28,12 +28,14 @@ struct Sb2BoundaryLists {
   double delta[3];
 };
 
+// out3[0]: every owned row; on a slab also out3[1]: the edge_w owned rows next to each neighbouring slab, out3[2]: the others
 int sb2_build_boundary_lists(const sb2_grid& g, int64_t P, int64_t PL, int64_t first,
                              const std::vector<std::vector<uint8_t> >& h_flags, const std::vector<Sb2BcSpecies>& bcs,
-                             const double* consts, cudaStream_t stream, Sb2BoundaryLists& out, std::string& err);
+                             const double* consts, cudaStream_t stream, int edge_w, Sb2BoundaryLists* out3, std::string& err);
 void sb2_free_boundary_lists(Sb2BoundaryLists& l);
-// true when some Neumann side currently carries a value that is not exactly zero
-bool sb2_neumann_active(const Sb2BoundaryLists& l, int nspecies, const double* consts);
+// true when some Neumann side currently carries a value that is not exactly zero.  whole_grid: a handle that holds the whole
+// grid may skip the pass when no cell receives a flux; a slab may not (the slabs of a grid must agree on the schedule).
+bool sb2_neumann_active(const Sb2BoundaryLists& l, int nspecies, const double* consts, bool whole_grid);
 cudaError_t sb2_apply_boundary(const Sb2BoundaryLists& l, double* const* k, double* const* u, const double* consts,
                                double* const* fields, bool do_neumann, cudaStream_t stream, int* launches);
 
@@ -51,8 +53,12 @@ struct Sb2CipArgs {
   const uint8_t* flags;
   double* tmp_cell;   // scratch: cell increments
   double* tmp_face;   // scratch: face increments of the pass direction
+  // rows (2-D) / planes (3-D) of the slab axis: the update sweep runs on [row_begin, row_end), the flux loop on
+  // [row_begin, flux_row_end) (one more row where a neighbouring slab's first row feeds a face of the last owned row)
+  int32_t row_begin, row_end, flux_row_end;
 };
-cudaError_t sb2_launch_cip(const Sb2CipArgs& a, cudaStream_t stream, int* launches);
+// one direction pass (flux loop + update sweep) along `axis`
+cudaError_t sb2_launch_cip_pass(const Sb2CipArgs& a, int axis, cudaStream_t stream, int* launches);
 
 // ---------------- membrane transport (calcMemTransport, calcPDE.cpp:1036-1482) ----------------
 struct Sb2MemTransport {

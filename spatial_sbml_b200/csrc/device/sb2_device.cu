@@ -56,7 +56,14 @@ struct sb2_sim {
   struct MemOp { int type, index; };  // type 0: transports[index], 1: mem_reactions[index]
   std::vector<MemOp> mem_ops;
   std::vector<Sb2CellRule> cell_rules;  // assignment rules re-evaluated after every step, in dependency order
-  Sb2BoundaryLists blists;
+  Sb2BoundaryLists blists[3];  // every owned row / the edge rows of a slab / its other rows
+  bool model_dirichlet;        // some species declares a Dirichlet side (whether or not this slab touches it)
+  int edge_w, end_w;           // slab: owned rows per side computed first and exchanged per stage / rows exchanged at the end of a step
+  // sharded stepping (sb2_sharded_begin / sb2_sharded_next)
+  cudaStream_t sh_edge, sh_comm;
+  cudaEvent_t ev_edge, ev_interior, ev_comm, ev_ready, ev_pulled;
+  int sh_phase, sh_passes;
+  bool sh_awaiting, sh_comm_valid, sh_first_stage;
   bool finalized, any_adv;
   bool fuse_combine;    // this step: RK combine fused into stage 4
   bool carry_k0;        // this step: a non-zero Neumann flux is carried in k0 (spatialsimulator.cpp:1540-1542)
@@ -647,6 +654,11 @@ int sb2_create(const sb2_grid* grid, sb2_sim** out) {
   sim->jit_job = NULL; sim->jit_mode = 0; sim->steps_seen = 0; sim->capturing = false;
   sim->trace = getenv("SB2_TRACE") != NULL;
   memset(&sim->base, 0, sizeof(sim->base));
+  memset(sim->blists, 0, sizeof(sim->blists));
+  sim->edge_w = 1; sim->end_w = 1;
+  sim->sh_edge = NULL; sim->sh_comm = NULL;
+  sim->ev_edge = sim->ev_interior = sim->ev_comm = sim->ev_ready = sim->ev_pulled = NULL;
+  sim->sh_phase = -1; sim->sh_passes = 0; sim->sh_awaiting = false; sim->sh_comm_valid = false; sim->sh_first_stage = true;
   *out = sim;
   return SB2_OK;
 }
@@ -664,7 +676,14 @@ void sb2_destroy(sb2_sim* sim) {
     for (int a = 0; a < 3; ++a) if (s.faces[a]) cudaFree(s.faces[a]);
   }
   for (size_t i = 0; i < sim->transports.size(); ++i) sb2_free_transport(sim->transports[i]);
-  sb2_free_boundary_lists(sim->blists);
+  for (int part = 0; part < 3; ++part) sb2_free_boundary_lists(sim->blists[part]);
+  if (sim->sh_edge) cudaStreamDestroy(sim->sh_edge);
+  if (sim->sh_comm) cudaStreamDestroy(sim->sh_comm);
+  if (sim->ev_edge) cudaEventDestroy(sim->ev_edge);
+  if (sim->ev_interior) cudaEventDestroy(sim->ev_interior);
+  if (sim->ev_comm) cudaEventDestroy(sim->ev_comm);
+  if (sim->ev_ready) cudaEventDestroy(sim->ev_ready);
+  if (sim->ev_pulled) cudaEventDestroy(sim->ev_pulled);
   for (size_t i = 0; i < sim->mem_reactions.size(); ++i) sb2_free_mem_reaction(sim->mem_reactions[i]);
   for (size_t i = 0; i < sim->cell_rules.size(); ++i) sb2_free_cell_rule(sim->cell_rules[i]);
   for (size_t i = 0; i < sim->point_sets.size(); ++i) {
@@ -1110,8 +1129,15 @@ int sb2_finalize(sb2_sim* sim) {
     bcs[s].geo = sp.geo; bcs[s].has_bc = sp.has_bc;
     for (int k = 0; k < 6; ++k) { bcs[s].kind[k] = sp.bckind[k]; bcs[s].skind[k] = sp.bcskind[k]; bcs[s].src[k] = sp.bcsrc[k]; }
   }
+  // slab: a model with membrane transport reads cells two rows away from a membrane point, one with advection needs two rows
+  // of u and of the face values around every owned row
+  sim->model_dirichlet = false;
+  for (size_t s = 0; s < sim->species.size(); ++s)
+    for (int k = 0; k < 6; ++k) if (sim->species[s].has_bc && sim->species[s].bckind[k] == SB2_BC_DIRICHLET) sim->model_dirichlet = true;
+  sim->edge_w = sim->transports.empty() ? 1 : 2;
+  sim->end_w = (sim->any_adv || !sim->transports.empty()) ? 2 : 1;
   int rc = sb2_build_boundary_lists(sim->g, sim->P, sim->PL, sim->first, sim->h_flags, bcs, sim->consts, sim->stream,
-                                    sim->blists, err);
+                                    sim->edge_w, sim->blists, err);
   if (rc) return fail(sim, rc, err);
 
   // advected species carry CIP face values (allocated by sb2_upload_faces or here, zero-filled)
@@ -1145,11 +1171,11 @@ int sb2_begin_step(sb2_sim* sim, double t_arg, double dt, int time_slot) {
   // A Neumann flux that is exactly zero adds +0.0 everywhere (all shipped models): the boundary
   // passes are skipped and the combine can be fused.  A non-zero flux takes the un-fused schedule,
   // which reproduces the reference's order of additions including the flux carried in k0.
-  sim->carry_k0 = sb2_neumann_active(sim->blists, (int)sim->species.size(), sim->consts);
+  sim->carry_k0 = sb2_neumann_active(sim->blists[0], (int)sim->species.size(), sim->consts, sim->g.own_hi <= sim->g.own_lo);
   sim->fuse_combine = !sim->any_adv && !sim->carry_k0;
-  if (sim->g.own_hi > sim->g.own_lo && (sim->carry_k0 || sim->blists.n_dirichlet > 0))
-    return fail(sim, SB2_ERR_STATE, "non-zero Neumann flux / Dirichlet conditions are not supported on a slab of a sharded grid yet "
-                                    "(their boundary pass is not split into edge and interior rows)");
+  // on a slab a Dirichlet value imposed after the update has to reach the neighbours' halo rows: the new u is exchanged
+  // after sb2_end_step instead of right after the last stage
+  if (sim->g.own_hi > sim->g.own_lo && sim->model_dirichlet) sim->fuse_combine = false;
   if (sim->carry_k0 && !sim->k0_carry_valid) {
     for (size_t s = 0; s < sim->species.size(); ++s)
       CK(cudaMemsetAsync(sim->species[s].k[0], 0, sizeof(double) * sim->nalloc, sim->stream));
@@ -1158,79 +1184,100 @@ int sb2_begin_step(sb2_sim* sim, double t_arg, double dt, int time_slot) {
   return SB2_OK;
 }
 
+namespace {
+// rows / planes of the slab axis: what is held, what is owned, and how many owned rows on either side face a neighbour
+struct SlabRows { int n_held, own_lo, own_hi, lo_edge, hi_edge; };
+SlabRows slab_rows(const sb2_sim* sim) {
+  SlabRows r;
+  r.n_held = sim->g.dim == 3 ? sim->g.nz : sim->g.ny;
+  const bool whole = sim->g.own_hi <= sim->g.own_lo;
+  r.own_lo = whole ? 0 : sim->g.own_lo;
+  r.own_hi = whole ? r.n_held : sim->g.own_hi;
+  // owned rows next to a neighbouring slab (their results are what the neighbours' halos need): edge_w on either side
+  r.lo_edge = r.own_lo > 0 ? sim->edge_w : 0;
+  r.hi_edge = r.own_hi < r.n_held ? sim->edge_w : 0;
+  if (r.lo_edge + r.hi_edge > r.own_hi - r.own_lo) {  // a thin slab is all edge
+    r.lo_edge = r.own_lo > 0 ? r.own_hi - r.own_lo : 0;
+    r.hi_edge = r.lo_edge ? 0 : r.own_hi - r.own_lo;
+  }
+  return r;
+}
+
+// membrane transport and the work on membrane species of one stage (everything is O(perimeter))
+int launch_membrane_ops(sb2_sim* sim, int m) {
+  static const double rk[4] = {0.0, 0.5, 0.5, 1.0};
+  const double dt = sim->cur_dt;
+  // membrane transport first: its flux is the carry-in of the stage accumulators of the volume species
+  if (!sim->transports.empty()) {
+    for (size_t s = 0; s < sim->species.size(); ++s) {
+      if (sim->carry_k0 && m == 0) continue;  // k0 already holds the carried Neumann flux
+      CK(cudaMemsetAsync(sim->species[s].k[m], 0, sizeof(double) * sim->nalloc, sim->stream));
+    }
+  }
+  // transports and membrane reactions in the order of the reference's reaction list (what a membrane species receives
+  // adds up in that order), then surface diffusion (spatialsimulator.cpp:1369-1479)
+  if (sim->mem_ops.empty() && sim->mem_species.empty()) return SB2_OK;
+  const Sb2MemView mv = mem_view(sim);
+  const double* mu[SB2_MAX_MEM_SPECIES]; const double* mkp[SB2_MAX_MEM_SPECIES]; double* mko[SB2_MAX_MEM_SPECIES];
+  for (int i = 0; i < SB2_MAX_MEM_SPECIES; ++i) { mu[i] = mv.u[i]; mkp[i] = m > 0 ? mv.k[i][m - 1] : NULL; mko[i] = mv.k[i][m]; }
+  std::vector<const double*> u(sim->species.size()), kp(sim->species.size());
+  std::vector<double*> ko(sim->species.size());
+  for (size_t s = 0; s < sim->species.size(); ++s) {
+    u[s] = sim->species[s].u[sim->species[s].cur];
+    kp[s] = m > 0 ? sim->species[s].k[m - 1] : NULL;
+    ko[s] = sim->species[s].k[m];
+  }
+  for (size_t i = 0; i < sim->mem_ops.size(); ++i) {
+    cudaError_t e;
+    if (sim->mem_ops[i].type == 0)
+      e = sb2_launch_transport(sim->transports[sim->mem_ops[i].index], sim->g, u.data(), kp.data(), ko.data(), mu, mkp, mko, sim->consts, m,
+                               rk[m] * dt, sim->stream, &sim->launches);
+    else
+      e = sb2_launch_mem_reaction(sim->mem_reactions[sim->mem_ops[i].index], mv, sim->consts, m, rk[m] * dt, sim->stream, &sim->launches);
+    if (e != cudaSuccess) return cuda_fail(sim, e, "membrane transport / reaction kernels");
+  }
+  for (size_t i = 0; i < sim->mem_species.size(); ++i) {
+    cudaError_t e = sb2_launch_mem_diffusion(sim->mem_species[i], (int)i, mv, sim->consts, m, rk[m] * dt, sim->g.dim, sim->stream, &sim->launches);
+    if (e != cudaSuccess) return cuda_fail(sim, e, "membrane diffusion kernel");
+  }
+  return SB2_OK;
+}
+
+// calcBoundary of stage m on the rows of one phase (0 all owned rows, 1 edge rows, 2 the others); it follows the diffusion of
+// the same stage and the same rows (spatialsimulator.cpp:1476-1478)
+int launch_boundary(sb2_sim* sim, int m, int phase) {
+  if (m == 3 && sim->fuse_combine) return SB2_OK;
+  std::vector<double*> ko(sim->species.size()), uc(sim->species.size());
+  for (size_t s = 0; s < sim->species.size(); ++s) { ko[s] = sim->species[s].k[m]; uc[s] = sim->species[s].u[sim->species[s].cur]; }
+  cudaError_t e = sb2_apply_boundary(sim->blists[phase], ko.data(), uc.data(), sim->consts, sim->d_fields.data(), sim->carry_k0,
+                                     sim->stream, &sim->launches);
+  if (e != cudaSuccess) return cuda_fail(sim, e, "boundary kernels");
+  return SB2_OK;
+}
+}  // namespace
+
 int sb2_stage(sb2_sim* sim, int m, int phase) {
   if (!sim || !sim->in_step) return fail(sim, SB2_ERR_STATE, "sb2_stage outside sb2_begin_step / sb2_end_step");
   if (m < 0 || m > 3) return fail(sim, SB2_ERR_ARG, "stage index out of range");
+  if (phase < 0 || phase > 2) return fail(sim, SB2_ERR_ARG, "phase out of range");
   cudaSetDevice(sim->g.device);
-  const int n_held = sim->g.dim == 3 ? sim->g.nz : sim->g.ny;
-  const bool whole = sim->g.own_hi <= sim->g.own_lo;
-  const int own_lo = whole ? 0 : sim->g.own_lo, own_hi = whole ? n_held : sim->g.own_hi;
-  // owned rows next to a neighbouring slab (their results are what the neighbours' halos need)
-  const int lo_edge = own_lo > 0 ? 1 : 0, hi_edge = own_hi < n_held ? 1 : 0;
+  const SlabRows r = slab_rows(sim);
   const double dt = sim->cur_dt;
-
-  if (phase == 0 || phase == 1) {
-    static const double rk[4] = {0.0, 0.5, 0.5, 1.0};
-    // membrane transport first: its flux is the carry-in of the stage accumulators of the volume species
-    if (!sim->transports.empty()) {
-      for (size_t s = 0; s < sim->species.size(); ++s) {
-        if (sim->carry_k0 && m == 0) continue;  // k0 already holds the carried Neumann flux
-        CK(cudaMemsetAsync(sim->species[s].k[m], 0, sizeof(double) * sim->nalloc, sim->stream));
-      }
-    }
-    // transports and membrane reactions in the order of the reference's reaction list (what a membrane species receives
-    // adds up in that order), then surface diffusion (spatialsimulator.cpp:1369-1479)
-    if (!sim->mem_ops.empty() || !sim->mem_species.empty()) {
-      const Sb2MemView mv = mem_view(sim);
-      const double* mu[SB2_MAX_MEM_SPECIES]; const double* mkp[SB2_MAX_MEM_SPECIES]; double* mko[SB2_MAX_MEM_SPECIES];
-      for (int i = 0; i < SB2_MAX_MEM_SPECIES; ++i) { mu[i] = mv.u[i]; mkp[i] = m > 0 ? mv.k[i][m - 1] : NULL; mko[i] = mv.k[i][m]; }
-      std::vector<const double*> u(sim->species.size()), kp(sim->species.size());
-      std::vector<double*> ko(sim->species.size());
-      for (size_t s = 0; s < sim->species.size(); ++s) {
-        u[s] = sim->species[s].u[sim->species[s].cur];
-        kp[s] = m > 0 ? sim->species[s].k[m - 1] : NULL;
-        ko[s] = sim->species[s].k[m];
-      }
-      for (size_t i = 0; i < sim->mem_ops.size(); ++i) {
-        cudaError_t e;
-        if (sim->mem_ops[i].type == 0)
-          e = sb2_launch_transport(sim->transports[sim->mem_ops[i].index], sim->g, u.data(), kp.data(), ko.data(), mu, mkp, mko, sim->consts, m,
-                                   rk[m] * dt, sim->stream, &sim->launches);
-        else
-          e = sb2_launch_mem_reaction(sim->mem_reactions[sim->mem_ops[i].index], mv, sim->consts, m, rk[m] * dt, sim->stream, &sim->launches);
-        if (e != cudaSuccess) return cuda_fail(sim, e, "membrane transport / reaction kernels");
-      }
-      for (size_t i = 0; i < sim->mem_species.size(); ++i) {
-        cudaError_t e = sb2_launch_mem_diffusion(sim->mem_species[i], (int)i, mv, sim->consts, m, rk[m] * dt, sim->g.dim, sim->stream, &sim->launches);
-        if (e != cudaSuccess) return cuda_fail(sim, e, "membrane diffusion kernel");
-      }
-    }
-  }
-
-  auto launch = [&](int rb, int re) -> int { return launch_stage_rows(sim, m, dt, rb, re); };
   int rc = SB2_OK;
-  if (phase == 0) rc = launch(own_lo, own_hi);
+  if (phase == 0 || phase == 1) {
+    if ((rc = launch_membrane_ops(sim, m))) return rc;
+  }
+  auto launch = [&](int rb, int re) -> int { return launch_stage_rows(sim, m, dt, rb, re); };
+  if (phase == 0) rc = launch(r.own_lo, r.own_hi);
   else if (phase == 1) {
-    if (lo_edge) rc = launch(own_lo, own_lo + 1);
-    if (!rc && hi_edge && (own_hi - 1 > own_lo || !lo_edge)) rc = launch(own_hi - 1, own_hi);
+    if (r.lo_edge) rc = launch(r.own_lo, r.own_lo + r.lo_edge);
+    if (!rc && r.hi_edge) rc = launch(r.own_hi - r.hi_edge, r.own_hi);
   } else {
-    const int b = own_lo + lo_edge, e = own_hi - hi_edge;
-    if (e > b) rc = launch(b, e);  // (a one-row slab with both neighbours is fully covered by phase 1)
+    const int b = r.own_lo + r.lo_edge, e = r.own_hi - r.hi_edge;
+    if (e > b) rc = launch(b, e);  // (a thin slab is fully covered by phase 1)
   }
   if (rc) return rc;
-
-  if (phase == 0 || phase == 2) {
-    // boundary conditions act after diffusion of the same stage (spatialsimulator.cpp:1476-1478)
-    const bool final = (m == 3 && sim->fuse_combine);
-    if (!final) {
-      std::vector<double*> ko(sim->species.size()), uc(sim->species.size());
-      for (size_t s = 0; s < sim->species.size(); ++s) { ko[s] = sim->species[s].k[m]; uc[s] = sim->species[s].u[sim->species[s].cur]; }
-      cudaError_t e = sb2_apply_boundary(sim->blists, ko.data(), uc.data(), sim->consts, sim->d_fields.data(), sim->carry_k0,
-                                         sim->stream, &sim->launches);
-      if (e != cudaSuccess) return cuda_fail(sim, e, "boundary kernels");
-    }
-  }
-  return SB2_OK;
+  return launch_boundary(sim, m, phase);
 }
 
 // sb2_stage on another stream (cudaStream_t as void*): lets the caller run the edge rows and the interior rows of a
@@ -1245,37 +1292,56 @@ int sb2_stage_on(sb2_sim* sim, int m, int phase, void* cuda_stream) {
   return rc;
 }
 
-int sb2_end_step(sb2_sim* sim) {
-  if (!sim || !sim->in_step) return fail(sim, SB2_ERR_STATE, "sb2_end_step without sb2_begin_step");
-  cudaSetDevice(sim->g.device);
+namespace {
+// the CIP-CSLR passes of one step, flattened: (species, axis) for every advected species and every axis it has a velocity on
+struct AdvPass { int species, axis; };
+std::vector<AdvPass> advection_passes(const sb2_sim* sim) {
+  std::vector<AdvPass> out;
+  for (size_t s = 0; s < sim->species.size(); ++s) {
+    if (!sim->species[s].has_adv) continue;
+    for (int a = 0; a < sim->g.dim; ++a)
+      if (sim->species[s].akind[a] != SB2_SRC_NONE) { AdvPass p = {(int)s, a}; out.push_back(p); }
+  }
+  return out;
+}
+
+// one direction pass of cipCSLR for one species (calcPDE.cpp:581-673) on the owned rows
+int launch_advection_pass(sb2_sim* sim, const AdvPass& p) {
+  Sb2Species& sp = sim->species[p.species];
+  const SlabRows r = slab_rows(sim);
+  Sb2CipArgs c;
+  memset(&c, 0, sizeof(c));
+  c.nx = sim->g.nx; c.ny = sim->g.ny; c.nz = sim->g.nz; c.dim = sim->g.dim;
+  c.P = sim->P; c.PL = sim->PL; c.first = sim->first; c.nalloc = sim->nalloc;
+  c.delta[0] = sim->g.dx; c.delta[1] = sim->g.dy; c.delta[2] = sim->g.dz;
+  c.dt = sim->cur_dt;
+  c.u = sp.u[sp.cur];
+  for (int a = 0; a < 3; ++a) {
+    c.faces[a] = sp.faces[a];
+    c.akind[a] = sp.akind[a];
+    c.aconst[a] = sp.akind[a] == SB2_SRC_CONST ? sim->consts[sp.asrc[a]] : 0.0;
+    c.afield[a] = sp.akind[a] == SB2_SRC_FIELD ? sim->d_fields[sp.asrc[a]] : NULL;
+  }
+  c.flags = sim->d_flags[sp.geo];
+  c.tmp_cell = sp.u[sp.cur ^ 1];  // the idle half of the double buffer is scratch here
+  c.tmp_face = sim->d_tmp_face;
+  c.row_begin = r.own_lo; c.row_end = r.own_hi;
+  // the update sweep moves the faces of the OTHER axes by the mean increment of the two cells they separate: the face between
+  // the last owned row and the neighbouring slab needs the increment of that slab's first row, which is computed here as well
+  c.flux_row_end = (p.axis != (sim->g.dim == 3 ? 2 : 1) && r.own_hi < r.n_held) ? r.own_hi + 1 : r.own_hi;
+  cudaError_t e = sb2_launch_cip_pass(c, p.axis, sim->stream, &sim->launches);
+  if (e != cudaSuccess) return cuda_fail(sim, e, "CIP-CSLR advection kernels");
+  return SB2_OK;
+}
+
+// what follows the stages and the advection: updateSpecies for every species (unless fused into the last stage), the
+// post-update boundary pass, membrane species, assignment rules, pseudo-membrane fill
+int finish_step(sb2_sim* sim) {
   const double dt = sim->cur_dt;
   const size_t S = sim->species.size();
   if (sim->fuse_combine) {
     for (size_t s = 0; s < S; ++s) sim->species[s].cur ^= 1;
   } else {
-    // advection between the last stage and the update (spatialsimulator.cpp:1484-1491)
-    for (size_t s = 0; s < S; ++s) {
-      Sb2Species& sp = sim->species[s];
-      if (!sp.has_adv) continue;
-      Sb2CipArgs c;
-      memset(&c, 0, sizeof(c));
-      c.nx = sim->g.nx; c.ny = sim->g.ny; c.nz = sim->g.nz; c.dim = sim->g.dim;
-      c.P = sim->P; c.PL = sim->PL; c.first = sim->first; c.nalloc = sim->nalloc;
-      c.delta[0] = sim->g.dx; c.delta[1] = sim->g.dy; c.delta[2] = sim->g.dz;
-      c.dt = dt;
-      c.u = sp.u[sp.cur];
-      for (int a = 0; a < 3; ++a) {
-        c.faces[a] = sp.faces[a];
-        c.akind[a] = sp.akind[a];
-        c.aconst[a] = sp.akind[a] == SB2_SRC_CONST ? sim->consts[sp.asrc[a]] : 0.0;
-        c.afield[a] = sp.akind[a] == SB2_SRC_FIELD ? sim->d_fields[sp.asrc[a]] : NULL;
-      }
-      c.flags = sim->d_flags[sp.geo];
-      c.tmp_cell = sp.u[sp.cur ^ 1];  // the idle half of the double buffer is scratch here
-      c.tmp_face = sim->d_tmp_face;
-      cudaError_t e = sb2_launch_cip(c, sim->stream, &sim->launches);
-      if (e != cudaSuccess) return cuda_fail(sim, e, "CIP-CSLR advection kernels");
-    }
     Sb2CombineArgs c;
     memset(&c, 0, sizeof(c));
     c.nx = sim->g.nx; c.ny = sim->g.ny; c.nz = sim->g.nz; c.dim = sim->g.dim; c.S = (int)S;
@@ -1290,12 +1356,12 @@ int sb2_end_step(sb2_sim* sim) {
   }
   // post-update calcBoundary(m = 0) (spatialsimulator.cpp:1540-1542): Dirichlet values are
   // re-imposed, Neumann flux is parked in the zeroed k0 and carried into the next step
-  if (sim->blists.n_dirichlet > 0 || sim->carry_k0) {
+  if (sim->blists[0].n_dirichlet > 0 || sim->carry_k0) {  // (no entries: nothing to write, on a slab as well)
     std::vector<double*> k0(S), uc(S);
     for (size_t s = 0; s < S; ++s) { k0[s] = sim->species[s].k[0]; uc[s] = sim->species[s].u[sim->species[s].cur]; }
     if (sim->carry_k0)
       for (size_t s = 0; s < S; ++s) CK(cudaMemsetAsync(k0[s], 0, sizeof(double) * sim->nalloc, sim->stream));
-    cudaError_t e = sb2_apply_boundary(sim->blists, k0.data(), uc.data(), sim->consts, sim->d_fields.data(), sim->carry_k0,
+    cudaError_t e = sb2_apply_boundary(sim->blists[0], k0.data(), uc.data(), sim->consts, sim->d_fields.data(), sim->carry_k0,
                                        sim->stream, &sim->launches);
     if (e != cudaSuccess) return cuda_fail(sim, e, "boundary kernels");
   }
@@ -1330,6 +1396,231 @@ int sb2_end_step(sb2_sim* sim) {
   sim->k0_carry_valid = sim->carry_k0;
   sim->in_step = false;
   return SB2_OK;
+}
+}  // namespace
+
+int sb2_end_step(sb2_sim* sim) {
+  if (!sim || !sim->in_step) return fail(sim, SB2_ERR_STATE, "sb2_end_step without sb2_begin_step");
+  cudaSetDevice(sim->g.device);
+  if (!sim->fuse_combine) {
+    // advection between the last stage and the update (spatialsimulator.cpp:1484-1491)
+    const std::vector<AdvPass> passes = advection_passes(sim);
+    if (!passes.empty() && sim->g.own_hi > sim->g.own_lo)
+      return fail(sim, SB2_ERR_STATE, "advection on a slab needs a halo exchange after every pass: step it with sb2_sharded_begin / sb2_sharded_next");
+    for (size_t i = 0; i < passes.size(); ++i) {
+      int rc = launch_advection_pass(sim, passes[i]);
+      if (rc) return rc;
+    }
+  }
+  return finish_step(sim);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sharded stepping, orchestrated here: which rows run on which stream, what is exchanged with the neighbouring slabs and when
+// (SURVEY.md §8e).  The caller only moves the rows sb2_sharded_next hands it, on the stream it names.
+// ---------------------------------------------------------------------------------------------
+namespace {
+int ensure_shard_streams(sb2_sim* sim) {
+  if (sim->sh_edge) return SB2_OK;
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);  // (lowest, highest): the edge rows go first
+  CK(cudaStreamCreateWithPriority(&sim->sh_edge, cudaStreamNonBlocking, hi));
+  CK(cudaStreamCreateWithFlags(&sim->sh_comm, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&sim->ev_edge, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&sim->ev_interior, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&sim->ev_comm, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&sim->ev_ready, cudaEventDisableTiming));
+  return SB2_OK;
+}
+
+void fill_exchange(sb2_sim* sim, sb2_exchange* x, const std::vector<double*>& bufs, int width) {
+  const SlabRows r = slab_rows(sim);
+  memset(x, 0, sizeof(*x));
+  x->n = (int)bufs.size();
+  for (size_t i = 0; i < bufs.size() && i < SB2_MAX_XBUF; ++i) x->ptr[i] = bufs[i];
+  x->width = width;
+  if (sim->g.dim == 3) { x->unit = sim->PL; x->base = sim->first - sim->P; }
+  else { x->unit = sim->P; x->base = sim->first; }
+  x->own_lo = r.own_lo; x->own_hi = r.own_hi;
+  x->has_lo = r.own_lo > 0 ? 1 : 0;
+  x->has_hi = r.own_hi < r.n_held ? 1 : 0;
+  x->stream = (void*)sim->sh_comm;
+  x->ready_event = (void*)sim->ev_ready;
+  x->device = sim->g.device;
+}
+}  // namespace
+
+int sb2_sharded_begin(sb2_sim* sim, double t_arg, double dt, int time_slot) {
+  if (!sim || !sim->finalized) return fail(sim, SB2_ERR_STATE, "simulator not finalized");
+  if (sim->in_step) return fail(sim, SB2_ERR_STATE, "sb2_sharded_begin inside a step");
+  cudaSetDevice(sim->g.device);
+  int rc = ensure_shard_streams(sim);
+  if (rc) return rc;
+  if ((rc = sb2_begin_step(sim, t_arg, dt, time_slot))) return rc;
+  sim->sh_phase = 0;
+  sim->sh_passes = (int)advection_passes(sim).size();
+  sim->sh_first_stage = true;
+  return SB2_OK;
+}
+
+// Runs the step up to its next halo exchange.  Returns 1 and fills *x when the caller has to exchange rows now (then call
+// again), 0 when the step is complete, negative on error.
+//   phases 0..7: stage m = phase / 2: even = edge rows (then exchange k_m, or the new u after a fused last stage), odd = the
+//                other owned rows;   8 .. 8+P-1: advection pass p (then exchange u and the faces of its species);
+//   8+P: update, boundary pass, membrane species, rules (then exchange u unless it travelled after the last stage)
+int sb2_sharded_next(sb2_sim* sim, sb2_exchange* x) {
+  if (!sim || !x) return SB2_ERR_ARG;
+  if (!sim->in_step && sim->sh_phase != 1000) return fail(sim, SB2_ERR_STATE, "sb2_sharded_next without sb2_sharded_begin");
+  cudaSetDevice(sim->g.device);
+  const size_t S = sim->species.size();
+  const cudaStream_t compute = sim->stream;
+  if (sim->sh_awaiting) {
+    // the exchange handed out by the previous call has been queued on the communication stream by now
+    CK(cudaEventRecord(sim->ev_comm, sim->sh_comm));
+    sim->sh_comm_valid = true;
+    sim->sh_awaiting = false;
+  }
+  int rc;
+  for (;;) {
+    const int ph = sim->sh_phase;
+    if (ph == 1000) {  // the exchange that ended the step is in flight: everything later waits for it
+      CK(cudaStreamWaitEvent(compute, sim->ev_comm, 0));
+      sim->sh_phase = -1;
+      return 0;
+    }
+    if (ph < 8 && (ph & 1) == 0) {
+      const int m = ph / 2;
+      // edge rows of stage m: they need the neighbours' rows of the previous exchange and this slab's rows of stage m-1
+      if (sim->sh_comm_valid) CK(cudaStreamWaitEvent(sim->sh_edge, sim->ev_comm, 0));
+      if (sim->sh_first_stage) {
+        CK(cudaEventRecord(sim->ev_interior, compute));  // whatever the compute stream still has queued (uploads, earlier steps)
+        sim->sh_first_stage = false;
+      }
+      CK(cudaStreamWaitEvent(sim->sh_edge, sim->ev_interior, 0));
+      if (m > 0) CK(cudaStreamWaitEvent(compute, sim->ev_edge, 0));  // the interior of stage m reads the edge rows of stage m-1
+      sim->multi_stream = true;
+      sim->stream = sim->sh_edge;
+      rc = sb2_stage(sim, m, 1);
+      sim->stream = compute;
+      if (rc) return rc;
+      CK(cudaEventRecord(sim->ev_edge, sim->sh_edge));
+      if (!sim->transports.empty() || !sim->mem_species.empty()) CK(cudaStreamWaitEvent(compute, sim->ev_edge, 0));  // the membrane work ran there
+      sim->sh_phase = ph + 1;
+      std::vector<double*> bufs;
+      const bool last = m == 3;
+      if (!last) for (size_t s = 0; s < S; ++s) bufs.push_back(sim->species[s].k[m]);
+      else if (sim->fuse_combine) for (size_t s = 0; s < S; ++s) bufs.push_back(sim->species[s].u[sim->species[s].cur ^ 1]);
+      // a Dirichlet value written by the boundary pass of this stage changes u itself (calcPDE.cpp:995)
+      if (sim->model_dirichlet) for (size_t s = 0; s < S; ++s) bufs.push_back(sim->species[s].u[sim->species[s].cur]);
+      if (bufs.empty()) continue;
+      CK(cudaEventRecord(sim->ev_ready, sim->sh_edge));
+      CK(cudaStreamWaitEvent(sim->sh_comm, sim->ev_ready, 0));
+      fill_exchange(sim, x, bufs, sim->edge_w);
+      sim->sh_awaiting = true;
+      return 1;
+    }
+    if (ph < 8) {
+      const int m = ph / 2;
+      if ((rc = sb2_stage(sim, m, 2))) return rc;
+      CK(cudaEventRecord(sim->ev_interior, compute));
+      sim->sh_phase = ph + 1;
+      continue;
+    }
+    if (ph == 8) {
+      // everything after the stages runs on the compute stream: it needs the edge rows and the halos of the last exchange
+      CK(cudaStreamWaitEvent(compute, sim->ev_edge, 0));
+      if (sim->sh_comm_valid) CK(cudaStreamWaitEvent(compute, sim->ev_comm, 0));
+    }
+    const int npass = sim->fuse_combine ? 0 : sim->sh_passes;
+    if (ph - 8 < npass) {
+      if (ph > 8 && sim->sh_comm_valid) CK(cudaStreamWaitEvent(compute, sim->ev_comm, 0));  // halos of the previous pass
+      const std::vector<AdvPass> passes = advection_passes(sim);
+      const AdvPass& p = passes[ph - 8];
+      if ((rc = launch_advection_pass(sim, p))) return rc;
+      sim->sh_phase = ph + 1;
+      std::vector<double*> bufs;
+      Sb2Species& sp = sim->species[p.species];
+      bufs.push_back(sp.u[sp.cur]);
+      for (int a = 0; a < sim->g.dim; ++a) if (sp.faces[a]) bufs.push_back(sp.faces[a]);
+      CK(cudaEventRecord(sim->ev_ready, compute));
+      CK(cudaStreamWaitEvent(sim->sh_comm, sim->ev_ready, 0));
+      fill_exchange(sim, x, bufs, 2);
+      sim->sh_awaiting = true;
+      return 1;
+    }
+    // last phase
+    if (npass > 0 && sim->sh_comm_valid) CK(cudaStreamWaitEvent(compute, sim->ev_comm, 0));
+    const bool fused = sim->fuse_combine;
+    if ((rc = finish_step(sim))) return rc;
+    if (fused) {  // the new u travelled after the last stage; later work must see it
+      if (sim->sh_comm_valid) CK(cudaStreamWaitEvent(compute, sim->ev_comm, 0));
+      sim->sh_phase = -1;
+      return 0;
+    }
+    std::vector<double*> bufs;
+    for (size_t s = 0; s < S; ++s) bufs.push_back(sim->species[s].u[sim->species[s].cur]);
+    CK(cudaEventRecord(sim->ev_ready, compute));
+    CK(cudaStreamWaitEvent(sim->sh_comm, sim->ev_ready, 0));
+    fill_exchange(sim, x, bufs, sim->end_w);
+    sim->sh_awaiting = true;
+    sim->sh_phase = 1000;
+    return 1;
+  }
+}
+
+// The same step for several slabs held by ONE process (one handle per slab, on the same or on different devices): the rows
+// move with peer copies on the handles' communication streams.  sims[i] owns the rows below sims[i+1]'s.
+int sb2_group_step(sb2_sim* const* sims, int n, double t_arg, double dt, int time_slot) {
+  if (!sims || n < 1) return SB2_ERR_ARG;
+  int rc;
+  for (int i = 0; i < n; ++i)
+    if ((rc = sb2_sharded_begin(sims[i], t_arg, dt, time_slot))) return rc;
+  std::vector<sb2_exchange> xs(n);
+  std::vector<cudaEvent_t> pulled(n, (cudaEvent_t)NULL);
+  for (;;) {
+    int more = 0, done = 0;
+    for (int i = 0; i < n; ++i) {
+      rc = sb2_sharded_next(sims[i], &xs[i]);
+      if (rc < 0) return rc;
+      if (rc == 1) ++more; else ++done;
+    }
+    if (more && done) return fail(sims[0], SB2_ERR_STATE, "sb2_group_step: the slabs disagree on the schedule of the step");
+    if (!more) return SB2_OK;
+    // every slab pulls the rows it needs from its neighbours, after the neighbour's producer event
+    for (int i = 0; i < n; ++i) {
+      sb2_sim* sim = sims[i];
+      const sb2_exchange& x = xs[i];
+      cudaSetDevice(sim->g.device);
+      cudaStream_t st = (cudaStream_t)x.stream;
+      for (int side = 0; side < 2; ++side) {
+        const int j = side == 0 ? i - 1 : i + 1;
+        if (j < 0 || j >= n || !(side == 0 ? x.has_lo : x.has_hi)) continue;
+        const sb2_exchange& y = xs[j];
+        if (y.n != x.n || y.width != x.width || y.unit != x.unit) return fail(sim, SB2_ERR_STATE, "sb2_group_step: neighbouring slabs disagree on an exchange");
+        CK(cudaStreamWaitEvent(st, (cudaEvent_t)y.ready_event, 0));
+        const size_t bytes = sizeof(double) * (size_t)x.unit * x.width;
+        for (int b = 0; b < x.n; ++b) {
+          // my halo rows below own_lo <- the neighbour's last owned rows; my halo rows from own_hi <- its first owned rows
+          double* dst = (double*)x.ptr[b] + x.base + (int64_t)(side == 0 ? x.own_lo - x.width : x.own_hi) * x.unit;
+          const double* src = (const double*)y.ptr[b] + y.base + (int64_t)(side == 0 ? y.own_hi - y.width : y.own_lo) * y.unit;
+          CK(cudaMemcpyPeerAsync(dst, x.device, src, y.device, bytes, st));
+        }
+      }
+    }
+    // a slab may not overwrite rows a neighbour is still pulling: its communication stream waits for the neighbours' pulls
+    for (int i = 0; i < n; ++i) {
+      sb2_sim* sim = sims[i];
+      cudaSetDevice(sim->g.device);
+      if (!sim->ev_pulled) CK(cudaEventCreateWithFlags(&sim->ev_pulled, cudaEventDisableTiming));
+      CK(cudaEventRecord(sim->ev_pulled, (cudaStream_t)xs[i].stream));
+    }
+    for (int i = 0; i < n; ++i) {
+      sb2_sim* sim = sims[i];
+      cudaSetDevice(sim->g.device);
+      if (i > 0) CK(cudaStreamWaitEvent((cudaStream_t)xs[i].stream, sims[i - 1]->ev_pulled, 0));
+      if (i + 1 < n) CK(cudaStreamWaitEvent((cudaStream_t)xs[i].stream, sims[i + 1]->ev_pulled, 0));
+    }
+  }
 }
 
 namespace {
@@ -1416,7 +1707,7 @@ int sb2_step_host(sb2_sim* sim, double t_arg, double dt, int time_slot, const do
   if (sim->g.own_hi > sim->g.own_lo) return fail(sim, SB2_ERR_STATE, "sb2_step_host needs a handle that owns its whole grid");
   int rc = sb2_begin_step(sim, t_arg, dt, time_slot);
   if (rc) return rc;
-  if (!sim->fuse_combine || !sim->transports.empty() || sim->blists.n_dirichlet > 0 || !sim->mem_species.empty() || !sim->cell_rules.empty()) {
+  if (!sim->fuse_combine || !sim->transports.empty() || sim->blists[0].n_dirichlet > 0 || !sim->mem_species.empty() || !sim->cell_rules.empty()) {
     sim->in_step = false;
     return fail(sim, SB2_ERR_STATE, "sb2_step_host: the model needs the unfused schedule (advection, membrane transport, non-zero flux or Dirichlet)");
   }

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <iostream>
 #include <map>
+#include <set>
 #include <sstream>
 #include <stdexcept>
 
@@ -83,6 +84,9 @@ struct SimImpl {
   std::vector<Var*> staged;     // device species id → variable
   std::vector<Var*> fieldVars;  // device field id → variable
   std::vector<char> stale;      // per staged species: device state is newer than Var::field
+  std::vector<SpatialSimulator*> slabs;  // group mode (setDevices): one simulator per slab; this object keeps the whole grid's host model
+  std::vector<std::pair<int, int> > slabRows;  // owned rows [lo, hi) of each slab
+  std::set<const Var*> groupFresh;       // group mode: variables whose host copy is as new as the slabs' device state
   std::vector<Var*> ruleTargets;  // variables an assignment rule rewrites on the device after every step
   bool rulesStale;                // ... whose host copies are older than the device's
   std::vector<Var*> memStaged;  // device membrane species id → variable
@@ -92,8 +96,9 @@ struct SimImpl {
   std::map<std::string, std::vector<boundaryType> > btMirrors;
   int ownLo, ownHi, heldLo;  // slab rows (global) owned / first row held locally
   long domainCells;
-  SimImpl() : ownedDoc(NULL), dev(NULL), rulesStale(false), timeSlot(-1), ownLo(0), ownHi(0), heldLo(0), domainCells(0) {}
+  SimImpl() : ownedDoc(NULL), dev(NULL), timeSlot(-1), rulesStale(false), ownLo(0), ownHi(0), heldLo(0), domainCells(0) {}
   ~SimImpl() {
+    for (size_t i = 0; i < slabs.size(); ++i) delete slabs[i];
     if (dev) sb2_destroy(dev);
     delete ownedDoc;
   }
@@ -201,13 +206,69 @@ void SpatialSimulator::initFromModel(SBMLDocument* doc, int xdim, int ydim, int 
   Xdiv = impl->m.gn[0];
   Ydiv = impl->m.gn[1];
   Zdiv = impl->m.gn[2];
+  if (!hostOnly && groupDevices.size() >= 2 && !impl->m.isSlab()) {
+    if (!buildSlabs(doc, xdim, ydim, zdim)) {
+      for (size_t i = 0; i < impl->slabs.size(); ++i) delete impl->slabs[i];
+      impl->slabs.clear();
+    }
+    return;
+  }
   if (!hostOnly && !buildDevice()) {
     // keep the host model for inspection, but there is no device → oneStep() will throw
     if (impl->dev) { sb2_destroy(impl->dev); impl->dev = NULL; }
   }
 }
 
-bool SpatialSimulator::isInitialized() const { return impl != NULL && (hostOnly || impl->dev != NULL); }
+// group mode: one simulator per slab, each on its device; this object keeps the host model of the whole grid
+bool SpatialSimulator::buildSlabs(SBMLDocument* doc, int xdim, int ydim, int zdim) {
+  sb2host::Model& m = impl->m;
+  const int n = m.dimension == 3 ? m.gn[2] : m.gn[1];
+  const int G = (int)groupDevices.size();
+  if (m.dimension != 2 && m.dimension != 3) { lastError = "slabs need a 2-D or 3-D grid"; return false; }
+  if (G > n) { lastError = "more devices than rows along the slab axis"; return false; }
+  for (int i = 0; i < G; ++i) {
+    const int lo = (int)((int64_t)i * n / G), hi = (int)((int64_t)(i + 1) * n / G);
+    SpatialSimulator* s = new SpatialSimulator();
+    impl->slabs.push_back(s);
+    impl->slabRows.push_back(std::make_pair(lo, hi));
+    s->setDevice(groupDevices[i]);
+    s->setSlab(lo, hi);
+    s->initFromModel(doc, xdim, ydim, zdim);
+    if (!s->isInitialized()) {
+      lastError = "slab " + std::to_string(i) + " (rows " + std::to_string(lo) + ".." + std::to_string(hi) + ", device " +
+                  std::to_string(groupDevices[i]) + "): " + s->getLastError();
+      return false;
+    }
+  }
+  impl->domainCells = 0;
+  for (int i = 0; i < G; ++i) impl->domainCells += impl->slabs[i]->getNumDomainCells();
+  return true;
+}
+
+// group mode: the owned rows of every slab, put together in a compact array of the whole grid
+bool SpatialSimulator::gatherCompact(const std::string& id, double* out) {
+  sb2host::Model& m = impl->m;
+  const int64_t rowCells = m.dimension == 3 ? (int64_t)m.nx * m.ny : (int64_t)m.nx;
+  std::vector<double> tmp;
+  for (size_t i = 0; i < impl->slabs.size(); ++i) {
+    SpatialSimulator* s = impl->slabs[i];
+    const int lo = impl->slabRows[i].first, hi = impl->slabRows[i].second;
+    const int heldLo = s->impl->heldLo;
+    const size_t nloc = (size_t)s->impl->m.ncells();
+    tmp.resize(nloc);
+    if (!s->getVariableCompact(id, tmp.data(), nloc)) return false;
+    memcpy(out + (int64_t)lo * rowCells, tmp.data() + (int64_t)(lo - heldLo) * rowCells, sizeof(double) * (size_t)((hi - lo) * rowCells));
+  }
+  return true;
+}
+
+bool SpatialSimulator::isInitialized() const { return impl != NULL && (hostOnly || impl->dev != NULL || !impl->slabs.empty()); }
+void SpatialSimulator::setDevices(const int* ordinals, int n) {
+  groupDevices.clear();
+  for (int i = 0; i < n && ordinals; ++i) groupDevices.push_back(ordinals[i]);
+  if (n == 1) deviceOrdinal = ordinals[0];
+}
+int SpatialSimulator::getNumSlabs() const { return impl ? (int)impl->slabs.size() : 0; }
 const std::string& SpatialSimulator::getLastError() const { return lastError; }
 void SpatialSimulator::setDevice(int ordinal) { deviceOrdinal = ordinal; }
 void SpatialSimulator::setHostOnly(bool h) { hostOnly = h; }
@@ -335,7 +396,6 @@ bool SpatialSimulator::buildDevice() {
         if (kind != SB2_SRC_NONE) DEV(sb2_set_boundary(impl->dev, v->speciesId, k, v->bcKind[k], kind, src));
       }
     if (v->hasAdv) {
-      if (m.isSlab()) { lastError = "advection is not supported on a sharded grid yet"; return false; }
       for (int a = 0; a < 3; ++a) {
         if (!v->advC[a]) continue;
         if (!sourceOf(v->advC[a], kind, src)) return false;
@@ -815,6 +875,24 @@ void SpatialSimulator::syncBeforeStep() {
 }
 
 double SpatialSimulator::oneStep(double initialTime, double step) {
+  if (impl && !impl->slabs.empty()) {
+    std::vector<sb2_sim*> handles;
+    for (size_t i = 0; i < impl->slabs.size(); ++i) {
+      impl->slabs[i]->syncBeforeStep();
+      handles.push_back(impl->slabs[i]->impl->dev);
+    }
+    impl->m.simTime = initialTime * step;
+    impl->m.tVar->uniformValue = impl->m.simTime;
+    const int rc = sb2_group_step(handles.data(), (int)handles.size(), initialTime, step, impl->slabs[0]->impl->timeSlot);
+    if (rc < 0) {
+      lastError = "sb2_group_step: ";
+      for (size_t i = 0; i < handles.size(); ++i) if (*sb2_last_error(handles[i])) { lastError += sb2_last_error(handles[i]); break; }
+      throw std::runtime_error(lastError);
+    }
+    for (size_t i = 0; i < impl->slabs.size(); ++i) impl->slabs[i]->deviceStateChanged();
+    impl->groupFresh.clear();
+    return initialTime + step;
+  }
   if (!impl || !impl->dev)
     throw std::runtime_error("SpatialSimulator::oneStep: no device simulator (" + (lastError.empty() ? std::string("not initialised") : lastError) +
                              "); there is no CPU fallback");
@@ -832,6 +910,14 @@ double SpatialSimulator::oneStep(double initialTime, double step) {
 
 double SpatialSimulator::oneStepHost(double initialTime, double step, int n, const char* const* ids, const double* const* in,
                                      double* const* out, int nslabs) {
+  if (impl && !impl->slabs.empty()) {
+    for (int i = 0; i < n; ++i)
+      if (in && in[i] && !setVariableCompact(ids[i], in[i], (size_t)impl->m.ncells())) throw std::runtime_error(std::string("oneStepHost: cannot set ") + ids[i]);
+    oneStep(initialTime, step);
+    for (int i = 0; i < n; ++i)
+      if (out && out[i] && !getVariableCompact(ids[i], out[i], (size_t)impl->m.ncells())) throw std::runtime_error(std::string("oneStepHost: cannot read ") + ids[i]);
+    return initialTime + step;
+  }
   if (!impl || !impl->dev)
     throw std::runtime_error("SpatialSimulator::oneStepHost: no device simulator (" + (lastError.empty() ? std::string("not initialised") : lastError) +
                              "); there is no CPU fallback");
@@ -869,6 +955,10 @@ double SpatialSimulator::oneStepHost(double initialTime, double step, int n, con
 }
 
 void SpatialSimulator::runSteps(double firstStepIndex, double step, int nsteps) {
+  if (impl && !impl->slabs.empty()) {
+    for (int i = 0; i < nsteps; ++i) oneStep(firstStepIndex + i, step);
+    return;
+  }
   if (!impl || !impl->dev)
     throw std::runtime_error("SpatialSimulator::runSteps: no device simulator (" + (lastError.empty() ? std::string("not initialised") : lastError) +
                              "); there is no CPU fallback");
@@ -886,6 +976,7 @@ void SpatialSimulator::runSteps(double firstStepIndex, double step, int nsteps) 
 
 void SpatialSimulator::deviceStateChanged() {
   if (!impl) return;
+  impl->groupFresh.clear();
   impl->markStale();
 }
 
@@ -903,6 +994,11 @@ void SpatialSimulator::run(double endTime, double step) {
 }
 
 double SpatialSimulator::getStableTimeStep(double dt) {
+  if (impl && !impl->slabs.empty()) {
+    double best = dt;  // the reduction of checkStability.cpp over the whole grid: the minimum over the slabs
+    for (size_t i = 0; i < impl->slabs.size(); ++i) best = std::min(best, impl->slabs[i]->getStableTimeStep(dt));
+    return best;
+  }
   if (!impl || !impl->dev) throw std::runtime_error("SpatialSimulator::getStableTimeStep: no device simulator; there is no CPU fallback");
   syncBeforeStep();
   double out = dt;
@@ -921,6 +1017,8 @@ void SpatialSimulator::setParameterUniformly(const std::string& id, double value
   sb2host::Model& m = impl->m;
   Var* v = m.findVar(id);
   if (!v || !v->hasValue) return;
+  for (size_t i = 0; i < impl->slabs.size(); ++i) impl->slabs[i]->setParameterUniformly(id, value);
+  impl->groupFresh.erase(v);
   if (v->isUniform) {
     v->uniformValue = value;  // reaches the device constants table in syncBeforeStep()
     return;
@@ -984,9 +1082,22 @@ int SpatialSimulator::getVariableLength() const {
 }
 int SpatialSimulator::getGeometryLength() const { return impl ? (int)impl->m.ndoubled() : 0; }
 long SpatialSimulator::getNumDomainCells() const { return impl ? impl->domainCells : 0; }
-int SpatialSimulator::getNumStagedSpecies() const { return impl ? (int)impl->staged.size() : 0; }
-int SpatialSimulator::getTimeSlot() const { return impl ? impl->timeSlot : -1; }
-long SpatialSimulator::getDeviceLaunchCount() const { return impl && impl->dev ? (long)sb2_launch_count(impl->dev) : 0; }
+int SpatialSimulator::getNumStagedSpecies() const {
+  if (impl && !impl->slabs.empty()) return impl->slabs[0]->getNumStagedSpecies();
+  return impl ? (int)impl->staged.size() : 0;
+}
+int SpatialSimulator::getTimeSlot() const {
+  if (impl && !impl->slabs.empty()) return impl->slabs[0]->getTimeSlot();
+  return impl ? impl->timeSlot : -1;
+}
+long SpatialSimulator::getDeviceLaunchCount() const {
+  if (impl && !impl->slabs.empty()) {
+    long n = 0;
+    for (size_t i = 0; i < impl->slabs.size(); ++i) n += impl->slabs[i]->getDeviceLaunchCount();
+    return n;
+  }
+  return impl && impl->dev ? (long)sb2_launch_count(impl->dev) : 0;
+}
 
 namespace {
 // bring Var::field up to date with the device
@@ -1018,6 +1129,11 @@ bool SpatialSimulator::getVariableCompact(const std::string& id, double* out, si
     for (size_t i = 0; i < n; ++i) out[i] = v->uniformValue;
     return true;
   }
+  if (!impl->slabs.empty()) {
+    if (v->onMembrane || n != (size_t)impl->m.ncells()) return false;
+    if (impl->groupFresh.count(v)) { memcpy(out, v->field.data(), n * sizeof(double)); return true; }
+    return gatherCompact(id, out);
+  }
   if (v->onMembrane) {  // one value per storage point of its membrane (getMembranePoints)
     if (n != v->field.size() || !refreshCompact(impl, v)) return false;
     memcpy(out, v->field.data(), n * sizeof(double));
@@ -1035,6 +1151,18 @@ bool SpatialSimulator::setVariableCompact(const std::string& id, const double* i
   if (!impl || !in) return false;
   Var* v = impl->m.findVar(id);
   if (!v || !v->hasValue || v->isUniform) return false;
+  if (!impl->slabs.empty()) {
+    // every slab takes the rows it holds (its own and the halo rows)
+    if (v->onMembrane || n != (size_t)impl->m.ncells()) return false;
+    const int64_t rowCells = impl->m.dimension == 3 ? (int64_t)impl->m.nx * impl->m.ny : (int64_t)impl->m.nx;
+    for (size_t i = 0; i < impl->slabs.size(); ++i) {
+      SpatialSimulator* sl = impl->slabs[i];
+      if (!sl->setVariableCompact(id, in + (int64_t)sl->impl->heldLo * rowCells, (size_t)sl->impl->m.ncells())) return false;
+    }
+    memcpy(v->field.data(), in, n * sizeof(double));
+    impl->groupFresh.insert(v);
+    return true;
+  }
   if (v->onMembrane) {
     if (n != v->field.size()) return false;
     memcpy(v->field.data(), in, n * sizeof(double));
@@ -1065,7 +1193,12 @@ double* SpatialSimulator::getVariable(const std::string& id, int& length) {
   length = getVariableLength();
   if (v->isUniform) return &v->uniformValue;  // the reference hands out the single double as well
   if (m.isSlab()) { length = 0; lastError = "doubled-grid mirrors are not available on a sharded grid; use getVariableCompact"; return NULL; }
-  const bool wasStale = (v->speciesId >= 0 && impl->stale[v->speciesId]) || (v->memSpeciesId >= 0 && impl->memStale[v->memSpeciesId]);
+  bool wasStale = (v->speciesId >= 0 && impl->stale[v->speciesId]) || (v->memSpeciesId >= 0 && impl->memStale[v->memSpeciesId]);
+  if (!impl->slabs.empty() && !v->onMembrane && !impl->isCoordinate(v) && !impl->groupFresh.count(v)) {
+    if (!gatherCompact(id, v->field.data())) { length = 0; return NULL; }
+    impl->groupFresh.insert(v);
+    wasStale = true;
+  }
   if (!refreshCompact(impl, v)) { length = 0; return NULL; }
   VarMirror& mir = impl->varMirrors[id];
   const bool fresh = mir.data.empty();
@@ -1226,6 +1359,10 @@ double SpatialSimulator::getVariableAt(const std::string& id, int x, int y, int 
   const int64_t c = (int64_t)(Y / 2) * m.nx + X / 2;
   if (!v->geo->isVol) return 0.0;
   if (v->geo->isDomain[c] == 0) return 0.0;
+  if (!impl->slabs.empty() && !impl->groupFresh.count(v)) {
+    if (!gatherCompact(id, v->field.data())) return 0.0;
+    impl->groupFresh.insert(v);
+  }
   if (!refreshCompact(impl, v)) return 0.0;
   return v->field[c];
 }
@@ -1233,11 +1370,25 @@ double SpatialSimulator::getVariableAt(const std::string& id, int x, int y, int 
 // =============================================================================================
 // inspection
 // =============================================================================================
-bool SpatialSimulator::specializeNow() { return impl && impl->dev && sb2_specialize_now(impl->dev) == 1; }
+bool SpatialSimulator::specializeNow() {
+  if (impl && !impl->slabs.empty()) {
+    bool all = true;
+    for (size_t i = 0; i < impl->slabs.size(); ++i) all = impl->slabs[i]->specializeNow() && all;
+    return all;
+  }
+  return impl && impl->dev && sb2_specialize_now(impl->dev) == 1;
+}
 
-bool SpatialSimulator::isSpecialized() { return impl && impl->dev && sb2_specialized(impl->dev) == 1; }
+bool SpatialSimulator::isSpecialized() {
+  if (impl && !impl->slabs.empty()) {
+    for (size_t i = 0; i < impl->slabs.size(); ++i) if (!impl->slabs[i]->isSpecialized()) return false;
+    return true;
+  }
+  return impl && impl->dev && sb2_specialized(impl->dev) == 1;
+}
 
 std::string SpatialSimulator::getSpecializeInfo() {
+  if (impl && !impl->slabs.empty()) return impl->slabs[0]->getSpecializeInfo();
   if (!impl || !impl->dev) return "";
   std::vector<char> buf(1 << 14);
   sb2_specialize_info(impl->dev, buf.data(), (int)buf.size());

@@ -100,6 +100,13 @@ class __attribute__((visibility("default"))) SpatialSimulator {
   void deviceStateChanged();
   void setCudaStream(void* stream);
   void setDevice(int ordinal);  // before init
+  // Several GPUs of one box behind this one object: before init, name the devices; the grid is then cut into
+  // one slab per entry along its slowest axis (y in 2-D, z in 3-D), every slab lives on its device (an ordinal may repeat),
+  // and oneStep() runs the sharded step of the library (sb2_group_step: edge rows first, halo rows by peer copies, interior
+  // rows meanwhile).  Results are bit-identical to a single device.  getVariableCompact / setVariableCompact / getVariable /
+  // getVariableAt / setParameter work on the whole grid as before.
+  void setDevices(const int* ordinals, int n);
+  int getNumSlabs() const;
   // Slab of a larger grid (multi-GPU): this simulator owns rows [lo, hi) of the slab
   // axis (y in 2-D, z in 3-D) of the model's grid.  Call before init; lo = hi = 0 means everything.
   void setSlab(int lo, int hi);
@@ -120,6 +127,8 @@ class __attribute__((visibility("default"))) SpatialSimulator {
   SpatialSimulator& operator=(const SpatialSimulator&);
   void clear();
   bool buildDevice();
+  bool buildSlabs(SBMLDocument* doc, int xdim, int ydim, int zdim);
+  bool gatherCompact(const std::string& id, double* out);
   bool addMemTransport(void* rxn);
   bool addMemTransportOn(void* rxn, void* membraneGeo);
   bool addMembraneSpecies();
@@ -134,6 +143,7 @@ class __attribute__((visibility("default"))) SpatialSimulator {
   void* externalStream;
   bool hostOnly;
   int slabLo, slabHi;
+  std::vector<int> groupDevices;
 };
 
 #endif  // SPATIAL_SIMULATOR_B200_H

@@ -1,12 +1,14 @@
 """Slab-sharded stepping across the GPUs of one box: one process per GPU,
-torch.distributed for the plumbing, NCCL send/recv of the slab edge rows / planes per RK stage.
+torch.distributed for the plumbing, NCCL send/recv of the slab edge rows / planes.
 
 The grid is cut along its slowest axis (y in 2-D, z in 3-D).  Every rank builds the model for its
-own rows plus two halo rows of each neighbour (masks only), computes only the rows it owns, and after
-each stage sends its first / last owned row of k_m (and of the new u after the last stage) to the
-neighbours.  The edge rows are computed first (phase 1) so that their transfer overlaps the
-interior kernel (phase 2).  There is no reduction inside the step, so the result is bit-identical to
-the single-GPU run.
+own rows plus two halo rows of each neighbour and computes only the rows it owns.  The step itself is
+orchestrated INSIDE the library (sb2_sharded_begin / sb2_sharded_next, include/spatial_b200.h): it
+runs the edge rows first on a high-priority stream, hands back the list of rows that have to travel
+(k_m after each stage, the new u after the last one, u and the face values after every advection
+pass, ...) together with the stream to queue the transfer on, and runs the interior rows while the
+transfer is in flight.  This module only moves the rows it is handed.  There is no reduction inside
+the step, so the result is bit-identical to the single-GPU run.
 
 The exchange itself (`exchange_rows`) works on any torch tensors, which is what the world-size-2
 gloo tests exercise on CPU.
@@ -16,7 +18,16 @@ import ctypes as C
 import torch
 import torch.distributed as dist
 
-from . import FieldView, SpatialSimulator, load_library
+from . import SpatialSimulator, load_library
+
+SB2_MAX_XBUF = 40
+
+
+class Exchange(C.Structure):
+    """sb2_exchange of include/spatial_b200.h"""
+    _fields_ = [("n", C.c_int32), ("ptr", C.c_void_p * SB2_MAX_XBUF), ("width", C.c_int32), ("unit", C.c_int64), ("base", C.c_int64),
+                ("own_lo", C.c_int32), ("own_hi", C.c_int32), ("has_lo", C.c_int32), ("has_hi", C.c_int32),
+                ("stream", C.c_void_p), ("ready_event", C.c_void_p), ("device", C.c_int32)]
 
 
 def partition(n, world):
@@ -24,20 +35,20 @@ def partition(n, world):
     return [((r * n) // world, ((r + 1) * n) // world) for r in range(world)]
 
 
-def exchange_rows(tensors, unit, base, own_lo, own_hi, rank, world, group=None):
-    """Fill the halo row below / above the owned rows of every flat tensor in `tensors` with the
+def exchange_rows(tensors, unit, base, own_lo, own_hi, rank, world, group=None, width=1):
+    """Fill the `width` halo rows below / above the owned rows of every flat tensor in `tensors` with the
     neighbours' edge rows.  Row r of a tensor is tensor[base + r*unit : base + (r+1)*unit].
     Returns the list of outstanding requests (wait on them before the halos are read)."""
     ops = []
-    def row(t, r):
-        return t[base + r * unit: base + (r + 1) * unit]
+    def rows(t, r):
+        return t[base + r * unit: base + (r + width) * unit]
     for t in tensors:
         if rank > 0:
-            ops.append(dist.P2POp(dist.isend, row(t, own_lo), rank - 1, group))
-            ops.append(dist.P2POp(dist.irecv, row(t, own_lo - 1), rank - 1, group))
+            ops.append(dist.P2POp(dist.isend, rows(t, own_lo), rank - 1, group))
+            ops.append(dist.P2POp(dist.irecv, rows(t, own_lo - width), rank - 1, group))
         if rank < world - 1:
-            ops.append(dist.P2POp(dist.isend, row(t, own_hi - 1), rank + 1, group))
-            ops.append(dist.P2POp(dist.irecv, row(t, own_hi), rank + 1, group))
+            ops.append(dist.P2POp(dist.isend, rows(t, own_hi - width), rank + 1, group))
+            ops.append(dist.P2POp(dist.irecv, rows(t, own_hi), rank + 1, group))
     if not ops:
         return []
     return dist.batch_isend_irecv(ops)
@@ -63,8 +74,6 @@ class ShardedSimulator(object):
         self.lo, self.hi = partition(n, self.world)[self.rank]
         self.lib = load_library()
         self.compute = torch.cuda.current_stream()
-        self.comm = torch.cuda.Stream()
-        self.edge = torch.cuda.Stream(priority=-1)  # the slab's edge rows run beside the interior kernel
         self.sim = SpatialSimulator(device=device, slab=(self.lo, self.hi) if self.world > 1 else None,
                                     stream=self.compute.cuda_stream)
         self.sim.initFromString(sbml, xdim, ydim, zdim)
@@ -76,87 +85,60 @@ class ShardedSimulator(object):
         self.held_lo = max(0, self.lo - 2) if self.world > 1 else 0
         self.own_lo = self.lo - self.held_lo
         self.own_hi = self.hi - self.held_lo
-        self.views = {}
-        if self.world > 1:
-            for s in range(self.S):
-                for which in (0, 1, 2, 3, 5):
-                    v = FieldView()
-                    if self.lib.sb2_species_view(self.h, s, which, C.byref(v)) != 0:
-                        raise RuntimeError(self.lib.sb2_last_error(self.h).decode())
-                    self.views[(s, which)] = torch.as_tensor(_DevArray(v.ptr, v.n_alloc), device="cuda")
-                    if dim == 3:
-                        self.unit, self.base = v.plane_pitch, v.first_cell - v.row_pitch
-                    else:
-                        self.unit, self.base = v.row_pitch, v.first_cell
-            # view 0 / 5 name "current" / "other" at creation time; track which buffer is current
-            self.cur = 0
         self.time_slot = self.sim.getTimeSlot()  # sim_time = stepIndex * dt reaches the kinetic laws through this constant
-        self.halo_ready = None
-
-    def _u(self, s, current):
-        which = 0 if (self.cur == 0) == current else 5
-        return self.views[(s, which)]
-
-    def _exchange(self, tensors, after_event):
-        with torch.cuda.stream(self.comm):
-            self.comm.wait_event(after_event)
-            reqs = exchange_rows(tensors, self.unit, self.base, self.own_lo, self.own_hi, self.rank, self.world, self.group)
-            for r in reqs:
-                r.wait()
-        done = torch.cuda.Event()
-        done.record(self.comm)
-        return done
+        self._x = Exchange()
+        self._streams = {}
+        self._views = {}
+        self.exchanges = 0
 
     def _ck(self, rc):
-        if rc != 0:
+        if rc < 0:
             raise RuntimeError(self.lib.sb2_last_error(self.h).decode())
+        return rc
+
+    def _rows(self, ptr, first_row, x):
+        """torch view of rows [first_row, first_row + width) of one buffer of an exchange"""
+        off = x.base + first_row * x.unit
+        key = (ptr, off, x.width * x.unit)
+        v = self._views.get(key)
+        if v is None:
+            v = torch.as_tensor(_DevArray(ptr + 8 * off, x.width * x.unit), device="cuda")
+            self._views[key] = v
+        return v
+
+    def _exchange(self, x):
+        """Move the rows the library asked for, ordered on the stream it named."""
+        st = self._streams.get(x.stream)
+        if st is None:
+            st = torch.cuda.ExternalStream(x.stream)
+            self._streams[x.stream] = st
+        ops = []
+        w = x.width
+        for b in range(x.n):
+            p = x.ptr[b]
+            if x.has_lo:
+                ops.append(dist.P2POp(dist.isend, self._rows(p, x.own_lo, x), self.rank - 1, self.group))
+                ops.append(dist.P2POp(dist.irecv, self._rows(p, x.own_lo - w, x), self.rank - 1, self.group))
+            if x.has_hi:
+                ops.append(dist.P2POp(dist.isend, self._rows(p, x.own_hi - w, x), self.rank + 1, self.group))
+                ops.append(dist.P2POp(dist.irecv, self._rows(p, x.own_hi, x), self.rank + 1, self.group))
+        if not ops:
+            return
+        with torch.cuda.stream(st):
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()  # stream-ordered: the library's stream now waits for the transfer
+        self.exchanges += 1
 
     def step(self, step_index, dt):
         """One RK4 step with the reference's run() convention oneStep(stepIndex, dt)."""
         if self.world == 1:
             self.sim.oneStep(step_index, dt)
             return
-        lib, h = self.lib, self.h
-        self._ck(lib.sb2_begin_step(h, float(step_index), float(dt), self.time_slot))
-        fused = lib.sb2_combine_is_fused(h) == 1
-        # Per stage: the two edge rows on their own stream (they need the neighbours' halo rows of the previous stage),
-        # the interior rows on the compute stream (they need only this rank's rows), the halo exchange of the new edge
-        # rows on the communication stream as soon as the edge kernel is done — all three overlap.
-        pending = self.halo_ready      # halos of u from the previous step (None at the first step)
-        prev_interior = None
-        prev_edge = None
-        for m in range(4):
-            if pending is not None:
-                self.edge.wait_event(pending)
-            if prev_interior is not None:
-                self.edge.wait_event(prev_interior)
-            else:
-                self.edge.wait_stream(self.compute)
-            if prev_edge is not None:
-                self.compute.wait_event(prev_edge)
-            self._ck(lib.sb2_stage_on(h, m, 1, C.c_void_p(self.edge.cuda_stream)))
-            ev = torch.cuda.Event()
-            ev.record(self.edge)
-            prev_edge = ev
-            if m < 3:
-                pending = self._exchange([self.views[(s, 1 + m)] for s in range(self.S)], ev)
-            elif fused:
-                pending = self._exchange([self._u(s, current=False) for s in range(self.S)], ev)
-            self._ck(lib.sb2_stage(h, m, 2))      # interior rows
-            prev_interior = torch.cuda.Event()
-            prev_interior.record(self.compute)
-        self.compute.wait_event(prev_edge)
-        self._ck(lib.sb2_end_step(h))
+        lib, h, x = self.lib, self.h, self._x
+        self._ck(lib.sb2_sharded_begin(h, float(step_index), float(dt), self.time_slot))
+        while self._ck(lib.sb2_sharded_next(h, C.byref(x))) == 1:
+            self._exchange(x)
         self.sim.deviceStateChanged()  # the host mirrors of the species are stale now
-        if fused:
-            self.cur ^= 1
-        else:
-            ev = torch.cuda.Event()
-            ev.record(self.compute)
-            pending = self._exchange([self._u(s, current=True) for s in range(self.S)], ev)
-        self.halo_ready = pending
-        if pending is not None:
-            self.compute.wait_event(pending)
 
     def run_steps(self, first_step_index, dt, nsteps):
         if self.world == 1:
@@ -164,6 +146,15 @@ class ShardedSimulator(object):
             return
         for i in range(nsteps):
             self.step(first_step_index + i, dt)
+
+    def stable_time_step(self, dt):
+        """getStableTimeStep over the whole grid: the smallest admissible step of any slab (one 8-byte MIN all-reduce)."""
+        v = self.sim.getStableTimeStep(dt)
+        if self.world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+        return float(t[0])
 
     def owned(self, species):
         """Compact values of the rows this rank owns (numpy)."""
