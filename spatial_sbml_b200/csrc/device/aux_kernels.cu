@@ -55,7 +55,7 @@ struct BcKernelArgs {
   double* k[SB2_MAX_SPECIES];
   double* u[SB2_MAX_SPECIES];
   const double* fields[SB2_MAX_FIELDS];
-  int do_neumann;
+  int do_neumann, do_dirichlet;
 };
 
 __global__ void __launch_bounds__(128) bc_kernel(const __grid_constant__ BcKernelArgs A) {
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(128) bc_kernel(const __grid_constant__ BcKerne
       // delta += -2.0 * (-bc) / deltaX   (calcPDE.cpp:994)
       if (A.do_neumann) A.k[s][c] = A.k[s][c] + (-2.0 * (-v)) / A.delta[side >> 1];
     } else if (kind == SB2_BC_DIRICHLET) {
-      A.u[s][c] = v;  // calcPDE.cpp:995
+      if (A.do_dirichlet) A.u[s][c] = v;  // calcPDE.cpp:995
     }
   }
 }
@@ -232,9 +232,9 @@ bool sb2_neumann_active(const Sb2BoundaryLists& l, int nspecies, const double* c
 }
 
 cudaError_t sb2_apply_boundary(const Sb2BoundaryLists& l, double* const* k, double* const* u, const double* consts,
-                               double* const* fields, bool do_neumann, cudaStream_t stream, int* launches) {
+                               double* const* fields, bool do_neumann, bool do_dirichlet, cudaStream_t stream, int* launches) {
   if (l.n_groups == 0) return cudaSuccess;
-  if (!do_neumann && l.n_dirichlet == 0) return cudaSuccess;
+  if (!(do_neumann && l.n_neumann > 0) && !(do_dirichlet && l.n_dirichlet > 0)) return cudaSuccess;
   BcKernelArgs a;
   memset(&a, 0, sizeof(a));
   a.n_groups = l.n_groups;
@@ -260,6 +260,7 @@ cudaError_t sb2_apply_boundary(const Sb2BoundaryLists& l, double* const* k, doub
     for (int j = 0; j < 6; ++j)
       if (l.kind[s][j] != SB2_BC_NONE && l.skind[s][j] == SB2_SRC_FIELD) a.fields[l.src[s][j]] = fields[l.src[s][j]];
   a.do_neumann = do_neumann ? 1 : 0;
+  a.do_dirichlet = do_dirichlet ? 1 : 0;
   if (launches) ++*launches;
   bc_kernel<<<(l.n_groups + 127) / 128, 128, 0, stream>>>(a);
   return cudaGetLastError();

@@ -37,7 +37,7 @@ void sb2_free_boundary_lists(Sb2BoundaryLists& l);
 // grid may skip the pass when no cell receives a flux; a slab may not (the slabs of a grid must agree on the schedule).
 bool sb2_neumann_active(const Sb2BoundaryLists& l, int nspecies, const double* consts, bool whole_grid);
 cudaError_t sb2_apply_boundary(const Sb2BoundaryLists& l, double* const* k, double* const* u, const double* consts,
-                               double* const* fields, bool do_neumann, cudaStream_t stream, int* launches);
+                               double* const* fields, bool do_neumann, bool do_dirichlet, cudaStream_t stream, int* launches);
 
 // ---------------- CIP-CSLR advection (cipCSLR, calcPDE.cpp:564-869) ----------------
 struct Sb2CipArgs {

@@ -1249,8 +1249,13 @@ int launch_boundary(sb2_sim* sim, int m, int phase) {
   if (m == 3 && sim->fuse_combine) return SB2_OK;
   std::vector<double*> ko(sim->species.size()), uc(sim->species.size());
   for (size_t s = 0; s < sim->species.size(); ++s) { ko[s] = sim->species[s].k[m]; uc[s] = sim->species[s].u[sim->species[s].cur]; }
+  // A Dirichlet value rewrites u itself (calcPDE.cpp:995), after every cell has read u for this stage.  The edge rows of a slab
+  // run beside its other rows, which read them as neighbours: their Dirichlet values are written with the second phase, once
+  // both kernels of the stage are done, and travel to the neighbouring slabs after that.
   cudaError_t e = sb2_apply_boundary(sim->blists[phase], ko.data(), uc.data(), sim->consts, sim->d_fields.data(), sim->carry_k0,
-                                     sim->stream, &sim->launches);
+                                     phase != 1, sim->stream, &sim->launches);
+  if (e == cudaSuccess && phase == 2)
+    e = sb2_apply_boundary(sim->blists[1], ko.data(), uc.data(), sim->consts, sim->d_fields.data(), false, true, sim->stream, &sim->launches);
   if (e != cudaSuccess) return cuda_fail(sim, e, "boundary kernels");
   return SB2_OK;
 }
@@ -1361,7 +1366,7 @@ int finish_step(sb2_sim* sim) {
     for (size_t s = 0; s < S; ++s) { k0[s] = sim->species[s].k[0]; uc[s] = sim->species[s].u[sim->species[s].cur]; }
     if (sim->carry_k0)
       for (size_t s = 0; s < S; ++s) CK(cudaMemsetAsync(k0[s], 0, sizeof(double) * sim->nalloc, sim->stream));
-    cudaError_t e = sb2_apply_boundary(sim->blists[0], k0.data(), uc.data(), sim->consts, sim->d_fields.data(), sim->carry_k0,
+    cudaError_t e = sb2_apply_boundary(sim->blists[0], k0.data(), uc.data(), sim->consts, sim->d_fields.data(), sim->carry_k0, true,
                                        sim->stream, &sim->launches);
     if (e != cudaSuccess) return cuda_fail(sim, e, "boundary kernels");
   }
@@ -1510,8 +1515,6 @@ int sb2_sharded_next(sb2_sim* sim, sb2_exchange* x) {
       const bool last = m == 3;
       if (!last) for (size_t s = 0; s < S; ++s) bufs.push_back(sim->species[s].k[m]);
       else if (sim->fuse_combine) for (size_t s = 0; s < S; ++s) bufs.push_back(sim->species[s].u[sim->species[s].cur ^ 1]);
-      // a Dirichlet value written by the boundary pass of this stage changes u itself (calcPDE.cpp:995)
-      if (sim->model_dirichlet) for (size_t s = 0; s < S; ++s) bufs.push_back(sim->species[s].u[sim->species[s].cur]);
       if (bufs.empty()) continue;
       CK(cudaEventRecord(sim->ev_ready, sim->sh_edge));
       CK(cudaStreamWaitEvent(sim->sh_comm, sim->ev_ready, 0));
@@ -1524,6 +1527,16 @@ int sb2_sharded_next(sb2_sim* sim, sb2_exchange* x) {
       if ((rc = sb2_stage(sim, m, 2))) return rc;
       CK(cudaEventRecord(sim->ev_interior, compute));
       sim->sh_phase = ph + 1;
+      if (sim->model_dirichlet && m < 3) {
+        // the boundary pass of this stage may have rewritten u on the edge rows (Dirichlet): the neighbours need it for stage m+1
+        std::vector<double*> bufs;
+        for (size_t s = 0; s < S; ++s) bufs.push_back(sim->species[s].u[sim->species[s].cur]);
+        CK(cudaEventRecord(sim->ev_ready, compute));
+        CK(cudaStreamWaitEvent(sim->sh_comm, sim->ev_ready, 0));
+        fill_exchange(sim, x, bufs, sim->edge_w);
+        sim->sh_awaiting = true;
+        return 1;
+      }
       continue;
     }
     if (ph == 8) {

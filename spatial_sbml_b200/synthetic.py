@@ -483,3 +483,10 @@ def chain6(nx, ny, nz=None):
         rx.append(_reaction("c%d" % i, [(names[i], 1)], [(names[i + 1], 1)], law))
     rx.append(_reaction("deg", [("S5", 1)], [], _apply("times", _ci("kd"), _ci("S5"))))
     return _document("synthetic_chain6", axes, dims, species, params, assignments, rx)
+
+
+def turing_dirichlet3d(nx, ny, nz):
+    """The 3-D Turing model with Dirichlet values on both z sides of species_2 and zero fluxes everywhere else: the fused
+    schedule (combine inside the last stage) together with the Dirichlet overwrite, incl. the reference's Z-side quirks.  dt 0.02."""
+    bc = {("species_2", "Zmax"): (0.12, "Dirichlet"), ("species_2", "Zmin"): (0.09, "Dirichlet")}
+    return turing(nx, ny, nz, bc_values=bc)

@@ -25,7 +25,7 @@ RESTATED = {"turing_tiny": 1000, "turing_tiny_cl": 100, "turing_uniform": 100, "
             "brusselator": 100, "brusselator_nonunit": 100, "brusselator_300": 1, "fish": 10, "fish_300": 1,
             "syn_turing_2d": 100, "syn_turing_3d": 50, "syn_brusselator_3d": 20, "syn_cascade3_3d": 40, "syn_cascade3_2d": 40,
             # calcBoundary restated too: non-zero Neumann flux (carried in k0 between steps) and a Dirichlet side
-            "turing_tiny_flux": 100, "fish_dirichlet": 10, "syn_turing_3d_flux": 40,
+            "turing_tiny_flux": 100, "fish_dirichlet": 10, "syn_turing_3d_flux": 40, "syn_turing_3d_dirichlet": 40,
             # cipCSLR restated on the doubled grid (cell + face values)
             "advection": 100,
             # calcMemTransport restated per membrane point (incl. the rpStack[1] rate quirk)

@@ -71,7 +71,8 @@ def test_slabs_with_live_boundary_conditions(nslabs):
     _run_pair(synthetic.turing_bc(dims[0], dims[1]), dims, 0.05, 12, ("species_1", "species_2"), [0] * nslabs)
 
 
-@pytest.mark.parametrize("case,nslabs", [("fish_dirichlet", 2), ("fish_dirichlet", 3), ("turing_tiny_flux", 2), ("syn_turing_3d_flux", 2)])
+@pytest.mark.parametrize("case,nslabs", [("fish_dirichlet", 2), ("fish_dirichlet", 3), ("turing_tiny_flux", 2), ("syn_turing_3d_flux", 2),
+                                         ("syn_turing_3d_flux", 3), ("syn_turing_3d_dirichlet", 2), ("syn_turing_3d_dirichlet", 3)])
 def test_slabs_golden_models_with_boundary_conditions(case, nslabs):
     g = load_golden(case)
     dims = tuple(int(v) for v in g["dims"])
