@@ -124,7 +124,7 @@ def test_group_accessors():
     b.close()
 
 
-@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("dim", ["2", "3", "bc", "adv"])
 def test_nccl_sharded_step_is_bit_identical(dim):
     import torch
     n = torch.cuda.device_count()
@@ -132,7 +132,7 @@ def test_nccl_sharded_step_is_bit_identical(dim):
         pytest.skip("the NCCL path needs at least two GPUs (the same slab logic runs on one GPU in the tests above)")
     world = 2
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
-           "--master-port", str(29500 + dim), os.path.join(REPO, "tools", "sharded_check.py"), str(dim), "12"]
+           "--master-port", str(29500 + ["2", "3", "bc", "adv"].index(dim)), os.path.join(REPO, "tools", "sharded_check.py"), dim, "12"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "BIT-IDENTICAL" in r.stdout

@@ -1,5 +1,5 @@
-"""Run under torchrun (one rank per GPU): the slab-sharded step must be BIT-IDENTICAL to the single-GPU step
-(no reduction inside the step).  usage: torchrun --nproc-per-node N tools/sharded_check.py [2|3] [steps]"""
+"""Run under torchrun (one rank per GPU): the slab-sharded step over NCCL must be BIT-IDENTICAL to the single-GPU step
+(no reduction inside the step).  usage: torchrun --nproc-per-node N tools/sharded_check.py [2|3|bc|adv] [steps]"""
 import os
 import sys
 
@@ -13,17 +13,25 @@ from spatial_sbml_b200 import synthetic
 from spatial_sbml_b200.sharded import ShardedSimulator
 import spatial_sbml_b200 as sb
 
-dim = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+what = sys.argv[1] if len(sys.argv) > 1 else "2"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 12
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-if dim == 2:
-    dims = (700, 96 * world + 5, 1)
+names = ("species_1", "species_2")
+if what == "2":
+    dim, dims = 2, (700, 96 * world + 5, 1)
     model, dt = synthetic.turing(dims[0], dims[1]), 0.07
-else:
-    dims = (200, 40, 6 * world + 3)
+elif what == "3":
+    dim, dims = 3, (200, 40, 6 * world + 3)
     model, dt = synthetic.turing(*dims), 0.02
+elif what == "bc":
+    dim, dims = 2, (128, 24 * world + 3, 1)
+    model, dt = synthetic.turing_bc(dims[0], dims[1]), 0.05
+else:  # the reference's advection example
+    dim, dims = 2, (101, 101, 1)
+    model, dt = open(os.path.join(REPO, "tests", "golden", "models", "advection.xml")).read(), 0.05
+    names = ("A_cytosol", "B_cytosol", "C_cytosol")
 shard = ShardedSimulator(model, dims[0], dims[1], dims[2], dim=dim, device=local)
 shard.run_steps(0, dt, steps)
 torch.cuda.synchronize()
@@ -31,7 +39,7 @@ ok = True
 ref = sb.SpatialSimulator(device=local)
 ref.initFromString(model, *dims)
 ref.runSteps(0, dt, steps)
-for name in ("species_1", "species_2"):
+for name in names:
     whole = ref.getVariableCompact(name)
     mine = shard.owned(name)
     want = whole[shard.lo:shard.hi] if dim == 3 else whole[:, shard.lo:shard.hi]
@@ -43,9 +51,12 @@ for name in ("species_1", "species_2"):
             rank, name, np.abs(mine - want).max(), len(bad), rows[:6], rows[-3:], mine.shape[0 if dim == 3 else 1],
             bad[:, 2].min(), bad[:, 2].max()), flush=True)
     ok = ok and same
+# the stability reduction over the slabs is one MIN all-reduce
+ok = ok and shard.stable_time_step(10.0) == ref.getStableTimeStep(10.0)
 t = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print("sharded_check dim %d world %d steps %d rows [%d,%d): %s" % (dim, world, steps, shard.lo, shard.hi, "BIT-IDENTICAL" if int(t[0]) else "MISMATCH"), flush=True)
+    print("sharded_check %s world %d steps %d rows [%d,%d) exchanges %d: %s" % (what, world, steps, shard.lo, shard.hi, shard.exchanges,
+                                                                               "BIT-IDENTICAL" if int(t[0]) else "MISMATCH"), flush=True)
 dist.destroy_process_group()
 sys.exit(0 if int(t[0]) else 1)
