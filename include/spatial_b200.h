@@ -151,6 +151,9 @@ SB2_API int sb2_add_reaction(sb2_sim* sim, int geo, int kind, const sb2_token* t
 SB2_API int sb2_set_diffusion(sb2_sim* sim, int species, int axis, int src_kind, int src);
 /* Advection velocity along axis (variableInfo::adCInfo; calcPDE.cpp:564-869). */
 SB2_API int sb2_set_advection(sb2_sim* sim, int species, int axis, int src_kind, int src);
+/* A field-valued velocity is also read BETWEEN the cells (the divergence correction of the face value, calcPDE.cpp:623-625,
+ * takes it at the odd doubled-grid points): field[cell] = the velocity at the face between cell and cell + e_axis. */
+SB2_API int sb2_set_advection_faces(sb2_sim* sim, int species, int axis, int field);
 /* Boundary condition of a species on one side (variableInfo::boundaryInfo; calcPDE.cpp:871-1034). */
 SB2_API int sb2_set_boundary(sb2_sim* sim, int species, int side, int bc_kind, int src_kind, int src);
 

@@ -70,6 +70,7 @@ def _proto(lib):
         "sb2_add_reaction": (ci, [vp, ci, ci, C.POINTER(Token), ci, C.POINTER(Ref), ci, ci]),
         "sb2_set_diffusion": (ci, [vp, ci, ci, ci, ci]),
         "sb2_set_advection": (ci, [vp, ci, ci, ci, ci]),
+        "sb2_set_advection_faces": (ci, [vp, ci, ci, ci]),
         "sb2_set_boundary": (ci, [vp, ci, ci, ci, ci, ci]),
         "sb2_add_mem_transport": (ci, [vp, C.POINTER(Token), ci, C.POINTER(Ref), ci, ci, C.POINTER(MemPoint), ci,
                                        C.POINTER(C.c_int32), dp, C.POINTER(C.c_int32)]),

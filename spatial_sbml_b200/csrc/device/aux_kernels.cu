@@ -304,7 +304,9 @@ __global__ void __launch_bounds__(256) cip_flux_kernel(const __grid_constant__ S
   const double vm1 = d_m1 ? face[idx - st] : v0;
   const double vm2 = d_m1 ? val[idx - st] : v0;
 
-  const double ux = A.aconst[axis];
+  // uniform velocity, or the mean of the cell's value and its (collapsed) plus neighbour's (calcPDE.cpp:612-613)
+  const bool ufield = A.akind[axis] == SB2_SRC_FIELD;
+  const double ux = ufield ? (A.afield[axis][idx] + A.afield[axis][d_p1 ? idx + st : idx]) / 2.0 : A.aconst[axis];
   const double Dx = -copysign(1.0, ux) * delta;
   const double xi = ux * dt;
   const bool bofp = f & (SB2_F_XP << (2 * axis));
@@ -323,7 +325,14 @@ __global__ void __launch_bounds__(256) cip_flux_kernel(const __grid_constant__ S
     }
     const double mxi = -xi;
     const double den = 1.0 + beta_i * mxi;
-    const double newface = (a_i + 2 * b_i * mxi + beta_i * b_i * (mxi * mxi)) / (den * den) - vp1;
+    double newface = (a_i + 2 * b_i * mxi + beta_i * b_i * (mxi * mxi)) / (den * den) - vp1;
+    if (ufield) {
+      // correction due to velocity divergence (calcPDE.cpp:623-625): the velocity at Xplus3 and Xminus1, i.e. at the face of the
+      // next cell and of the previous cell, each collapsed like the value indices
+      const double u3 = d_p2 ? A.afield_face[axis][idx + st] : (d_p1 ? A.afield[axis][idx + st] : A.afield[axis][idx]);
+      const double um1 = d_m1 ? A.afield_face[axis][idx - st] : A.afield[axis][idx];
+      newface = newface + ((dt / (2 * delta)) * (vp1 + newface)) * (u3 - um1);
+    }
     if (d_p1) A.tmp_face[idx] = newface;
     const double G = (-a_i * xi + b_i * (xi * xi)) / (-1.0 + beta_i * xi);
     if (ux >= 0) g_out = G; else g_in = -G;

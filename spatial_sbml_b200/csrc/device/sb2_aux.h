@@ -49,7 +49,8 @@ struct Sb2CipArgs {
   double* faces[3];   // face point values: faces[a][cell] = face between cell and cell + e_a
   int32_t akind[3];
   double aconst[3];
-  const double* afield[3];
+  const double* afield[3];       // field-valued velocity at the cells
+  const double* afield_face[3];  // ... and at the plus faces along the same axis (the odd doubled-grid points between two cells)
   const uint8_t* flags;
   double* tmp_cell;   // scratch: cell increments
   double* tmp_face;   // scratch: face increments of the pass direction

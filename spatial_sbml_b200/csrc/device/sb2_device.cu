@@ -23,6 +23,7 @@ struct Sb2Species {
   double* k[4];
   int dkind[3], dsrc[3];
   int akind[3], asrc[3];
+  int afacesrc[3];   // field holding a field-valued velocity at the plus faces along the same axis, -1: none
   int bckind[6], bcskind[6], bcsrc[6];
   bool has_diff, has_adv, has_bc;
   double* faces[3];  // CIP face values (advected species only)
@@ -818,6 +819,14 @@ int sb2_set_advection(sb2_sim* sim, int species, int axis, int src_kind, int src
   return SB2_OK;
 }
 
+int sb2_set_advection_faces(sb2_sim* sim, int species, int axis, int field) {
+  if (!sim || species < 0 || species >= (int)sim->species.size() || axis < 0 || axis > 2)
+    return fail(sim, SB2_ERR_ARG, "bad species / axis");
+  if (field < 0 || field >= (int)sim->d_fields.size()) return fail(sim, SB2_ERR_ARG, "unknown field");
+  sim->species[species].afacesrc[axis] = field + 1;  // stored + 1: the species record is zero-initialised
+  return SB2_OK;
+}
+
 int sb2_set_boundary(sb2_sim* sim, int species, int side, int bc_kind, int src_kind, int src) {
   if (!sim || species < 0 || species >= (int)sim->species.size() || side < 0 || side > 5)
     return fail(sim, SB2_ERR_ARG, "bad species / side");
@@ -1145,7 +1154,8 @@ int sb2_finalize(sb2_sim* sim) {
     Sb2Species& sp = sim->species[s];
     if (!sp.has_adv) continue;
     for (int a = 0; a < sim->g.dim; ++a) {
-      if (sp.akind[a] == SB2_SRC_FIELD) return fail(sim, SB2_ERR_LIMIT, "non-uniform advection velocities are not supported on the device yet");
+      if (sp.akind[a] == SB2_SRC_FIELD && (sp.asrc[a] < 0 || sp.asrc[a] >= (int)sim->d_fields.size() || sp.afacesrc[a] <= 0))
+        return fail(sim, SB2_ERR_ARG, "field-valued advection velocity: cell field and face field (sb2_set_advection_faces) are both needed");
       if (!sp.faces[a]) { rc = alloc_field(sim, &sp.faces[a]); if (rc) return rc; }
     }
   }
@@ -1326,6 +1336,7 @@ int launch_advection_pass(sb2_sim* sim, const AdvPass& p) {
     c.akind[a] = sp.akind[a];
     c.aconst[a] = sp.akind[a] == SB2_SRC_CONST ? sim->consts[sp.asrc[a]] : 0.0;
     c.afield[a] = sp.akind[a] == SB2_SRC_FIELD ? sim->d_fields[sp.asrc[a]] : NULL;
+    c.afield_face[a] = (sp.akind[a] == SB2_SRC_FIELD && sp.afacesrc[a] > 0) ? sim->d_fields[sp.afacesrc[a] - 1] : NULL;
   }
   c.flags = sim->d_flags[sp.geo];
   c.tmp_cell = sp.u[sp.cur ^ 1];  // the idle half of the double buffer is scratch here

@@ -400,6 +400,21 @@ bool SpatialSimulator::buildDevice() {
         if (!v->advC[a]) continue;
         if (!sourceOf(v->advC[a], kind, src)) return false;
         if (kind != SB2_SRC_NONE) DEV(sb2_set_advection(impl->dev, v->speciesId, a, kind, src));
+        if (kind == SB2_SRC_FIELD) {
+          // the velocity between the cells: its value at the odd doubled-grid point on the plus side of every cell
+          Var* c = v->advC[a];
+          std::vector<double> fv((size_t)m.ncells(), 0.0);
+          for (int kk = 0; kk < m.nz; ++kk)
+            for (int jj = 0; jj < m.ny; ++jj)
+              for (int ii = 0; ii < m.nx; ++ii) {
+                const int X = 2 * (ii + m.off[0]) + (a == 0), Y = 2 * (jj + m.off[1]) + (a == 1), Z = 2 * (kk + m.off[2]) + (a == 2);
+                if (X < m.Xindex && Y < m.Yindex && Z < m.Zindex) fv[((size_t)kk * m.ny + jj) * m.nx + ii] = m.valueAtDoubled(c, X, Y, Z);
+              }
+          const int ff = sb2_add_field(impl->dev, fv.data());
+          if (ff < 0) { lastError = std::string("sb2_add_field: ") + sb2_last_error(impl->dev); return false; }
+          impl->fieldVars.push_back(NULL);  // device field without a model variable of its own
+          DEV(sb2_set_advection_faces(impl->dev, v->speciesId, a, ff));
+        }
       }
       // CIP face point values = the odd doubled-grid points of the species array (calcPDE.cpp:588-603)
       std::vector<double> faces((size_t)m.ncells(), v->offGridInit);

@@ -490,3 +490,34 @@ def turing_dirichlet3d(nx, ny, nz):
     schedule (combine inside the last stage) together with the Dirichlet overwrite, incl. the reference's Z-side quirks.  dt 0.02."""
     bc = {("species_2", "Zmax"): (0.12, "Dirichlet"), ("species_2", "Zmin"): (0.09, "Dirichlet")}
     return turing(nx, ny, nz, bc_values=bc)
+
+
+def advection_field(nx, ny, uniform=False):
+    """CIP-CSLR advection (cipCSLR, calcPDE.cpp:564-869) of two species in a box with velocities that are FIELDS — a shear flow
+    u_x = 0.6 + 0.02 y, u_y = -0.4 + 0.015 x for P (positive and negative components) and a rotation-like field for Q — so
+    that the face-averaged velocity (:612-613) and the divergence correction of the face values (:623-625) are live; a little
+    diffusion and a decay reaction run beside it.  uniform=True: constant velocities (the large-grid advection benchmark).  dt 0.05."""
+    axes, dims = ["x", "y"], [nx, ny]
+    kinds = {"x": "cartesianX", "y": "cartesianY"}
+    params = _transport_params("P", 0.05, axes) + _transport_params("Q", 0.02, axes)
+    ia = [("P", _apply("plus", _cn(0.2), _apply("times", _cn(2.0), _apply("exp", _apply("minus", _apply("times", _cn(0.02), _apply(
+              "plus", _apply("power", _apply("minus", _ci("x"), _cn(0.35 * (nx - 1))), _cn(2)),
+              _apply("power", _apply("minus", _ci("y"), _cn(0.55 * (ny - 1))), _cn(2))))))))),
+          ("Q", _piecewise(_cn(3.0), _apply("and", _apply("gt", _ci("x"), _cn(0.5 * (nx - 1))), _apply("lt", _ci("x"), _cn(0.7 * (nx - 1))),
+                                            _apply("gt", _ci("y"), _cn(0.2 * (ny - 1))), _apply("lt", _ci("y"), _cn(0.45 * (ny - 1)))), _cn(0.5)))]
+    vel = {("P", "x"): (0.6, 0.02, "y"), ("P", "y"): (-0.4, 0.015, "x"), ("Q", "x"): (0.3, -0.02, "y"), ("Q", "y"): (-0.25, 0.02, "x")}
+    for (sp_, a), (c0, c1, dep) in sorted(vel.items()):
+        pid = "%s_adv_%s" % (sp_, a)
+        inner = '<spatial:advectionCoefficient spatial:variable="%s" spatial:coordinate="%s"/>' % (sp_, kinds[a])
+        if uniform:
+            params.append(_param(pid, c0, inner))
+        else:
+            params.append('<parameter id="%s" constant="true">%s</parameter>' % (pid, inner))
+            ia.append((pid, _apply("plus", _cn(c0), _apply("times", _cn(c1), _ci(dep)))))
+    params.append(_param("kd", 0.01))
+    rx = [_reaction("decay", [("P", 1)], [("Q", 1)], _apply("times", _ci("kd"), _ci("P")))]
+    return _document("synthetic_advection_field", axes, dims, [("P", None), ("Q", None)], params, ia, rx)
+
+
+def advection_uniform(nx, ny):
+    return advection_field(nx, ny, uniform=True)

@@ -75,6 +75,9 @@ CASES = {
     # species ON a membrane: surface diffusion over the Voronoi neighbours, binding / unbinding of a volume species, a reaction
     # between membrane species, the pseudo-membrane fill, and a membrane transport beside them (no example has a membrane species)
     "syn_turing_3d_dirichlet": ("synthetic:turing_dirichlet3d:18:14:10", (18, 14, 10), 0.02, [1, 2, 10, 40], {}, []),
+    # advection with velocities that are fields (face-averaged velocity, divergence correction) / the same flow with constants
+    "syn_advection_field_2d": ("synthetic:advection_field:44:36", (44, 36, 1), 0.05, [1, 2, 10, 100], {}, ["P", "Q"]),
+    "syn_advection_uniform_2d": ("synthetic:advection_uniform:44:36", (44, 36, 1), 0.05, [1, 10, 100], {}, ["P", "Q"]),
     # assignment rules re-evaluated after every step (time-, position- and species-dependent fields, a species defined by a rule)
     "syn_rules_2d": ("synthetic:rules:30:26", (30, 26, 1), 0.05, [1, 2, 10, 100], {}, []),
     "syn_rules_3d": ("synthetic:rules:14:12:10", (14, 12, 10), 0.05, [1, 10, 40], {}, []),

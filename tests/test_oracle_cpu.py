@@ -33,7 +33,8 @@ RESTATED = {"turing_tiny": 1000, "turing_tiny_cl": 100, "turing_uniform": 100, "
             # rate rules only; power, log to a base, xor / eq / neq, tanh, cos, time and a pop-only operator in the laws
             "syn_raterules_2d": 100,
             # geometry from an image + a membrane transport; six species
-            "syn_sampled_2d": 100, "syn_chain6_2d": 100}
+            "syn_sampled_2d": 100, "syn_chain6_2d": 100,
+            "syn_advection_uniform_2d": 100}
 
 
 def build(case):
@@ -70,7 +71,9 @@ NOT_RESTATED = {"syn_membrane_2d", "syn_membrane_box_2d", "syn_membrane_3d",
                 # assignment rules re-evaluated every step (updateAssignmentRules): pinned the same way
                 "syn_rules_2d", "syn_rules_3d",
                 # field-valued diffusion coefficients (the restatement takes uniform coefficients only)
-                "syn_fieldcoeff_2d", "syn_fieldcoeff_3d"}
+                "syn_fieldcoeff_2d", "syn_fieldcoeff_3d",
+                # field-valued advection velocities
+                "syn_advection_field_2d"}
 
 
 def test_every_golden_case_is_restated():
