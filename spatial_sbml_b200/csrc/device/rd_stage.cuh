@@ -892,10 +892,17 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
 
   const uint64_t keep = (MODE == MODE_FINAL) ? l2_policy_keep() : 0;
   // one lane: bulk copies of the raw rows (u and k_{m-1} of every species, halo columns included) of plane pz
-  auto issue_rows = [&](int pz) {
+  // (element offsets of this warp's rows in plane 0; the issue adds pz * PL: the address arithmetic of the bulk copies was a
+  // ninth of all instructions issued at 512^3 when every term was recomputed per copy)
+  // Running element offsets instead of products per use: grow / ghrow = this warp's own / halo row in the plane the next bulk copies
+  // fetch (planes are requested in order, one per iteration); the address arithmetic of the copies - 64-bit products of plane
+  // and row pitch for every array - was a ninth of all instructions issued at 512^3.
+  int64_t grow = A.first + (int64_t)(zb - 1) * A.PL + (int64_t)y * A.P + x0 - 2;
+  int64_t ghrow = A.first + (int64_t)(zb - 1) * A.PL + (int64_t)(halo_lo ? y0 - 1 : y0 + W) * A.P + x0 - 2;
+  auto issue_rows = [&]() {
     mbar_expect_tx(mybar, row_bytes * NARR * S * nrows);
-    const int64_t g = A.first + (int64_t)pz * A.PL + (int64_t)y * A.P + x0 - 2;
-    const int64_t gh = A.first + (int64_t)pz * A.PL + (int64_t)(halo_lo ? y0 - 1 : y0 + W) * A.P + x0 - 2;
+    const int64_t g = grow;
+    const int64_t gh = ghrow;
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
       if (s < S) {
@@ -913,9 +920,8 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
       }
     }
   };
-  auto issue_combine = [&](int pz) {
+  auto issue_combine = [&](int64_t g) {  // g: element offset of the strip row's first cell in the plane wanted
     mbar_expect_tx(mycbar, SW * sizeof(double) * 2 * S);
-    const int64_t g = A.first + (int64_t)pz * A.PL + (int64_t)y * A.P + x0;
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
       if (s < S) {
@@ -958,18 +964,71 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
   for (int p = 0; p < NP; ++p) active[p] = x0 + p * 64 + 2 * lane < A.nx;
 
   if (elect_one()) {
-    issue_rows(zb - 1);
-    if (MODE == MODE_FINAL && computes) issue_combine(zb);
+    issue_rows();
+    if (MODE == MODE_FINAL && computes) issue_combine(A.first + (int64_t)zb * A.PL + (int64_t)y * A.P + x0);
   }
+  grow += A.PL; ghrow += A.PL;
   uint32_t parity = 0, cparity = 0;
   // zc: the plane computed in this iteration; plane zc + 1 is staged first.  Planes zb-1 .. ze are staged (ring slot and
   // use count of plane pz follow from pz - (zb - 1)), planes zb .. ze-1 are computed.
-  int cls_cur = 2;  // class of this warp's strip row in plane zc, fetched one iteration ahead
+  // Class bytes and per-cell flag bytes come from global memory; both are requested a whole iteration before they are decoded,
+  // so that their latency is covered by the staging and the arithmetic of the plane in between (decoding them right after the
+  // load cost a fifth of all issue-stall samples at 512^3).
+  //   cls_cur / seg_cur: class of this warp's strip row in the plane computed in this iteration, and which 64-cell segments need
+  //   the per-cell predicates;  cb_next: the raw class bytes of the next plane;  fraw: raw flag bytes of the plane computed in
+  //   this iteration (requested in the previous one, when its class was decoded)
+  int cls_cur = 2;
   uint32_t seg_cur = 0xffffffffu;  // bit p: the 64-cell segment of cell pair p is not all-interior
-  for (int zc = zb - 2; zc < ze; ++zc) {
+  int cb_next[NP];
+  uchar2 fraw[NP][SB2_MAX_GEOS];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    cb_next[p] = 2;
+#pragma unroll
+    for (int g = 0; g < SB2_MAX_GEOS; ++g) fraw[p][g] = make_uchar2(0, 0);
+  }
+  auto load_class = [&](int plane) {  // one byte per 64 cells: 1 all interior, 2 all outside, 0 mixed
+    const uint8_t* cb = A.cls + ((uint32_t)plane * (uint32_t)A.ny + (uint32_t)y) * (uint32_t)A.nstrips + blockIdx.x * NP;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) cb_next[p] = ((int)blockIdx.x * NP + p < A.nstrips) ? (int)cb[p] : -1;
+  };
+  auto decode_class = [&]() {
+    if (A.carry) { cls_cur = 0; seg_cur = 0xffffffffu; return; }
+    int c = cb_next[0];
+    uint32_t m = c == 1 ? 0u : 1u;
+#pragma unroll
+    for (int p = 1; p < NP; ++p) {
+      const int cp = cb_next[p];
+      if (cp >= 0) {
+        if (cp != c) c = 0;
+        if (cp != 1) m |= 1u << p;
+      } else {
+        // past the grid: the pair is inactive and must take the predicated path, so an interior row becomes mixed
+        m |= 1u << p;
+        if (c == 1) c = 0;
+      }
+    }
+    cls_cur = c;
+    seg_cur = m;
+  };
+  auto load_flags = [&](int64_t i0, uint32_t segs) {  // raw flag bytes of the segments that need them; i0: the lane's first cell
+
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      if (!((segs >> p) & 1u) || !active[p]) continue;
+#pragma unroll
+      for (int g = 0; g < SB2_MAX_GEOS; ++g)
+        if (g < MODEL_G(A)) fraw[p][g] = *reinterpret_cast<const uchar2*>(A.flags[g] + i0 + p * 64);
+    }
+  };
+  if (computes && !A.carry) load_class(zb);
+  int64_t idx_run = A.first + (int64_t)(zb - 2) * A.PL + (int64_t)y * A.P + x0 + 2 * lane;  // this lane's first cell in plane zc
+  // ring slot and barrier phase of the plane staged in this iteration (qs, phs: iteration count modulo / over NSLOT) and of the
+  // plane computed in it (qc, phc: one iteration older; qm: two), kept as running values instead of divisions by NSLOT
+  int qs = 0, qc = 0, qm = 0;
+  uint32_t phs = 0, phc = 0;
+  for (int zc = zb - 2; zc < ze; ++zc, idx_run += A.PL, qm = qc, qc = qs, phc = phs, qs = (qs + 1 == NSLOT ? 0 : qs + 1), phs ^= (qs == 0 ? 1u : 0u)) {
     const int pz = zc + 1;
-    // class byte of the next plane and, for mixed rows, the per-cell flag bytes of this one: requested before the
-    // staging work so that their latency is covered by it
     const bool compute = computes && zc >= zb;
     const int cls = compute ? cls_cur : 2;
 #ifdef SB2_RD_ROWMASK  // experiments: per-cell predicates on every segment of a mixed strip row
@@ -977,30 +1036,8 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
 #else
     const uint32_t segmask = seg_cur;
 #endif
-    if (computes && pz >= zb && pz < ze) {
-      if (A.carry) { cls_cur = 0; seg_cur = 0xffffffffu; }
-      else {
-        // one byte per 64 cells: all segments interior -> 1, all outside -> 2, else mixed
-        const uint8_t* cb = A.cls + ((uint32_t)pz * (uint32_t)A.ny + (uint32_t)y) * (uint32_t)A.nstrips + blockIdx.x * NP;
-        int c = (int)cb[0];
-        uint32_t m = c == 1 ? 0u : 1u;
-#pragma unroll
-        for (int p = 1; p < NP; ++p) {
-          if ((int)blockIdx.x * NP + p < A.nstrips) {
-            const int cp = (int)cb[p];
-            if (cp != c) c = 0;
-            if (cp != 1) m |= 1u << p;
-          } else {
-            // past the grid: the pair is inactive and must take the predicated path, so an interior row becomes mixed
-            m |= 1u << p;
-            if (c == 1) c = 0;
-          }
-        }
-        cls_cur = c;
-        seg_cur = m;
-      }
-    }
-    const int64_t idx0 = A.first + (int64_t)zc * A.PL + (int64_t)y * A.P + x0 + 2 * lane;
+    const int64_t idx0 = idx_run;
+    // flag words of the plane computed now, from the bytes requested one iteration ago
     uint32_t fl[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) fl[c] = 0x01010101u;
@@ -1013,20 +1050,31 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
 #pragma unroll
           for (int g = 0; g < SB2_MAX_GEOS; ++g) {
             if (g < MODEL_G(A)) {
-              const uchar2 v = *reinterpret_cast<const uchar2*>(A.flags[g] + idx0 + p * 64);
-              fl[2 * p] |= (uint32_t)v.x << (8 * g);
-              fl[2 * p + 1] |= (uint32_t)v.y << (8 * g);
+              fl[2 * p] |= (uint32_t)fraw[p][g].x << (8 * g);
+              fl[2 * p + 1] |= (uint32_t)fraw[p][g].y << (8 * g);
             }
           }
         }
       }
     }
-    if (pz >= zb - 1) {
-      const uint32_t up = (uint32_t)(pz - (zb - 1));
-      const int q = (int)(up % NSLOT);
+    // the class of plane pz (computed in the next iteration) was requested an iteration ago: decode it, request the flag bytes
+    // that plane needs and the class bytes of the plane after it
+    if (computes && pz >= zb && pz < ze) {
+      decode_class();
+      if (cls_cur == 0) {
+#ifdef SB2_RD_ROWMASK
+        load_flags(idx_run + A.PL, 0xffffffffu);
+#else
+        load_flags(idx_run + A.PL, seg_cur);
+#endif
+      }
+      if (!A.carry && pz + 1 < ze) load_class(pz + 1);
+    }
+    {
+      const int q = qs;
       // (1) the slot still holds plane pz - NSLOT: the neighbours must have computed it
-      if (up >= NSLOT) {
-        const uint32_t ph = ((up - NSLOT) / NSLOT) & 1u;
+      if (pz - (zb - 1) >= NSLOT) {
+        const uint32_t ph = phs ^ 1u;
         bool ok = true;
         if (wait_lo) ok = mbar_wait(donebar0 + 8 * (q * W + warp - 1), ph, A.dbg == nullptr);
         if (done_hi) ok = mbar_wait(donebar0 + 8 * (q * W + warp + 1), ph, A.dbg == nullptr) && ok;
@@ -1045,14 +1093,14 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
       __syncwarp();
       if (lane == 0) mbar_arrive(rowbar0 + 8 * (q * W + warp));
       // the raw slots are free again: fetch the rows of the next plane
-      if (pz + 1 <= ze && elect_one()) issue_rows(pz + 1);
+      if (pz + 1 <= ze && elect_one()) issue_rows();
+      grow += A.PL; ghrow += A.PL;
     }
     if (zc < zb - 1) continue;
     // (3) rows j-1 and j+1 of plane zc; every warp that stages waits, whether it computes or not: the order in which
     // ring slots may be overwritten is carried from warp to warp by these waits
     {
-      const uint32_t u = (uint32_t)(zc - (zb - 1));
-      const uint32_t q = u % NSLOT, ph = (u / NSLOT) & 1u;
+      const uint32_t q = (uint32_t)qc, ph = phc;
       bool ok = true;
       if (wait_lo) ok = mbar_wait(rowbar0 + 8 * (q * W + warp - 1), ph, A.dbg == nullptr);
       if (wait_hi) ok = mbar_wait(rowbar0 + 8 * (q * W + warp + 1), ph, A.dbg == nullptr) && ok;
@@ -1060,7 +1108,7 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
         if (atomicAdd(&A.dbg[0], 1u) == 0) { A.dbg[1] = blockIdx.x; A.dbg[2] = blockIdx.y; A.dbg[3] = warp; A.dbg[4] = (uint32_t)zc; A.dbg[5] = 99; A.dbg[6] = (uint32_t)zb; A.dbg[7] = (uint32_t)ze; }
       }
     }
-    const int qc = (int)((uint32_t)(zc - (zb - 1)) % NSLOT), qp = qc + 1 == NSLOT ? 0 : qc + 1, qm = qc == 0 ? NSLOT - 1 : qc - 1;
+    const int qp = qs;  // plane zc + 1 was staged in this iteration
     if (!compute) {
       // plane zb-1 is never computed: its row-computed phase completes here, so that the use count of a slot is the
       // same for both kinds of barrier
@@ -1078,7 +1126,7 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(donebar0 + 8 * (qc * W + warp));  // (5) row (zc, j) will not be read by this warp's stencil again
-    if (MODE == MODE_FINAL && zc + 1 < ze && elect_one()) issue_combine(zc + 1);
+    if (MODE == MODE_FINAL && zc + 1 < ze && elect_one()) issue_combine(idx_run + A.PL - 2 * lane);
   }
 }
 
