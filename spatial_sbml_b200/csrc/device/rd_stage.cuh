@@ -157,6 +157,14 @@ struct BoolTag { static constexpr bool value = B; };
 // What never changes for a model - species and geometry counts, which species diffuse, which take the uniform-coefficient
 // stencil, the geometry a species lives in - is read from the kernel parameters by the interpreter build and is a literal
 // in a model-specialised build (rd_jit.cu defines the SB2_RD_* macros), where the tests on it fold away.
+// Debug words (SB2_DEBUG=1: waits that time out are recorded instead of trapping).  A model-specialised build never carries
+// them (the library runs the interpreter kernel when debugging), so its waits need no bookkeeping at all.
+#ifdef SB2_RD_PROGRAM
+#define RD_DBG(A) ((uint32_t*)nullptr)
+#else
+#define RD_DBG(A) (A).dbg
+#endif
+
 #ifdef SB2_RD_MODEL_BITS
 #define MODEL_S(A) SB2_RD_NS
 #define MODEL_G(A) SB2_RD_G
@@ -577,7 +585,7 @@ CASE(OP, 4, (4 < NS ? 0 : DEPTH)) CASE(OP, 5, (5 < NS ? 0 : DEPTH)) CASE(OP, 6, 
   }
 
   // ---------------- diffusion (calcPDE.cpp:484-559) + output ----------------
-  if (MODE == MODE_FINAL) mbar_wait(mycbar, cparity, A.dbg == nullptr);  // k0 / k1 of this row (requested one batch ago)
+  if (MODE == MODE_FINAL) mbar_wait(mycbar, cparity, RD_DBG(A) == nullptr);  // k0 / k1 of this row (requested one batch ago)
   rd_emit_row<NS, NP, MODE, D3>(A, S, cls, lane, active, fl, acc, idx0, mycs, cur0, up0, dn0, zp0, zm0, SSTRIDE, segmask);
   return true;
 }
@@ -693,8 +701,8 @@ __device__ __forceinline__ void rd_stage_body(const Sb2RdArgs& A, const double* 
 
     // (1) + (2): raw row → w ring
     if (wrow >= yb - 1 && wrow <= ye) {
-      if (!mbar_wait(mybar, parity, A.dbg == nullptr) && A.dbg && lane == 0) {
-        if (atomicAdd(&A.dbg[0], 1u) == 0) { A.dbg[1] = blockIdx.x; A.dbg[2] = blockIdx.y; A.dbg[3] = warp; A.dbg[4] = (uint32_t)wrow; A.dbg[5] = parity; A.dbg[6] = (uint32_t)yb; A.dbg[7] = (uint32_t)ye; }
+      if (!mbar_wait(mybar, parity, RD_DBG(A) == nullptr) && RD_DBG(A) && lane == 0) {
+        if (atomicAdd(&RD_DBG(A)[0], 1u) == 0) { RD_DBG(A)[1] = blockIdx.x; RD_DBG(A)[2] = blockIdx.y; RD_DBG(A)[3] = warp; RD_DBG(A)[4] = (uint32_t)wrow; RD_DBG(A)[5] = parity; RD_DBG(A)[6] = (uint32_t)yb; RD_DBG(A)[7] = (uint32_t)ye; }
       }
       parity ^= 1;
       const int wslot = slot_w;
@@ -739,7 +747,7 @@ __device__ __forceinline__ void rd_stage_body(const Sb2RdArgs& A, const double* 
     // still has to wait for them and to request the next row
     auto combine_done = [&](bool waited) {
       if (MODE != MODE_FINAL) return;
-      if (!waited) { mbar_wait(mycbar, cparity, A.dbg == nullptr); }
+      if (!waited) { mbar_wait(mycbar, cparity, RD_DBG(A) == nullptr); }
       cparity ^= 1;
       __syncwarp();
       if (srow + W < ye && elect_one()) issue_combine(srow + W);
@@ -776,10 +784,10 @@ __device__ __forceinline__ void rd_stage_body(const Sb2RdArgs& A, const double* 
       // ordering is carried from warp to warp by these waits.
       const uint32_t q = (uint32_t)(srow - (yb - 1));  // >= 1
       const uint32_t qc = q % RW, qd = (q - 1) % RW;
-      bool ok = mbar_wait(rowbar0 + 8 * qd, ((q - 1) / RW) & 1u, A.dbg == nullptr);
-      ok = mbar_wait(rowbar0 + 8 * qc, (q / RW) & 1u, A.dbg == nullptr) && ok;
-      if (!ok && A.dbg && lane == 0) {
-        if (atomicAdd(&A.dbg[0], 1u) == 0) { A.dbg[1] = blockIdx.x; A.dbg[2] = blockIdx.y; A.dbg[3] = warp; A.dbg[4] = (uint32_t)srow; A.dbg[5] = 99; A.dbg[6] = (uint32_t)yb; A.dbg[7] = (uint32_t)ye; }
+      bool ok = mbar_wait(rowbar0 + 8 * qd, ((q - 1) / RW) & 1u, RD_DBG(A) == nullptr);
+      ok = mbar_wait(rowbar0 + 8 * qc, (q / RW) & 1u, RD_DBG(A) == nullptr) && ok;
+      if (!ok && RD_DBG(A) && lane == 0) {
+        if (atomicAdd(&RD_DBG(A)[0], 1u) == 0) { RD_DBG(A)[1] = blockIdx.x; RD_DBG(A)[2] = blockIdx.y; RD_DBG(A)[3] = warp; RD_DBG(A)[4] = (uint32_t)srow; RD_DBG(A)[5] = 99; RD_DBG(A)[6] = (uint32_t)yb; RD_DBG(A)[7] = (uint32_t)ye; }
       }
     }
 
@@ -980,12 +988,12 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
   int cls_cur = 2;
   uint32_t seg_cur = 0xffffffffu;  // bit p: the 64-cell segment of cell pair p is not all-interior
   int cb_next[NP];
-  uchar2 fraw[NP][SB2_MAX_GEOS];
+  uint32_t fraw[NP][SB2_MAX_GEOS];  // the two flag bytes of a cell pair as loaded (16 bits), split only where they are used
 #pragma unroll
   for (int p = 0; p < NP; ++p) {
     cb_next[p] = 2;
 #pragma unroll
-    for (int g = 0; g < SB2_MAX_GEOS; ++g) fraw[p][g] = make_uchar2(0, 0);
+    for (int g = 0; g < SB2_MAX_GEOS; ++g) fraw[p][g] = 0u;
   }
   auto load_class = [&](int plane) {  // one byte per 64 cells: 1 all interior, 2 all outside, 0 mixed
     const uint8_t* cb = A.cls + ((uint32_t)plane * (uint32_t)A.ny + (uint32_t)y) * (uint32_t)A.nstrips + blockIdx.x * NP;
@@ -1018,7 +1026,7 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
       if (!((segs >> p) & 1u) || !active[p]) continue;
 #pragma unroll
       for (int g = 0; g < SB2_MAX_GEOS; ++g)
-        if (g < MODEL_G(A)) fraw[p][g] = *reinterpret_cast<const uchar2*>(A.flags[g] + i0 + p * 64);
+        if (g < MODEL_G(A)) fraw[p][g] = (uint32_t)*reinterpret_cast<const unsigned short*>(A.flags[g] + i0 + p * 64);
     }
   };
   if (computes && !A.carry) load_class(zb);
@@ -1050,8 +1058,8 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
 #pragma unroll
           for (int g = 0; g < SB2_MAX_GEOS; ++g) {
             if (g < MODEL_G(A)) {
-              fl[2 * p] |= (uint32_t)fraw[p][g].x << (8 * g);
-              fl[2 * p + 1] |= (uint32_t)fraw[p][g].y << (8 * g);
+              fl[2 * p] |= (fraw[p][g] & 0xffu) << (8 * g);
+              fl[2 * p + 1] |= (fraw[p][g] >> 8) << (8 * g);
             }
           }
         }
@@ -1076,14 +1084,14 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
       if (pz - (zb - 1) >= NSLOT) {
         const uint32_t ph = phs ^ 1u;
         bool ok = true;
-        if (wait_lo) ok = mbar_wait(donebar0 + 8 * (q * W + warp - 1), ph, A.dbg == nullptr);
-        if (done_hi) ok = mbar_wait(donebar0 + 8 * (q * W + warp + 1), ph, A.dbg == nullptr) && ok;
-        if (!ok && A.dbg && lane == 0) {
-          if (atomicAdd(&A.dbg[0], 1u) == 0) { A.dbg[1] = blockIdx.x; A.dbg[2] = blockIdx.y; A.dbg[3] = warp; A.dbg[4] = (uint32_t)pz; A.dbg[5] = 98; A.dbg[6] = (uint32_t)zb; A.dbg[7] = (uint32_t)ze; }
+        if (wait_lo) ok = mbar_wait(donebar0 + 8 * (q * W + warp - 1), ph, RD_DBG(A) == nullptr);
+        if (done_hi) ok = mbar_wait(donebar0 + 8 * (q * W + warp + 1), ph, RD_DBG(A) == nullptr) && ok;
+        if (!ok && RD_DBG(A) && lane == 0) {
+          if (atomicAdd(&RD_DBG(A)[0], 1u) == 0) { RD_DBG(A)[1] = blockIdx.x; RD_DBG(A)[2] = blockIdx.y; RD_DBG(A)[3] = warp; RD_DBG(A)[4] = (uint32_t)pz; RD_DBG(A)[5] = 98; RD_DBG(A)[6] = (uint32_t)zb; RD_DBG(A)[7] = (uint32_t)ze; }
         }
       }
-      if (!mbar_wait(mybar, parity, A.dbg == nullptr) && A.dbg && lane == 0) {
-        if (atomicAdd(&A.dbg[0], 1u) == 0) { A.dbg[1] = blockIdx.x; A.dbg[2] = blockIdx.y; A.dbg[3] = warp; A.dbg[4] = (uint32_t)pz; A.dbg[5] = parity; A.dbg[6] = (uint32_t)zb; A.dbg[7] = (uint32_t)ze; }
+      if (!mbar_wait(mybar, parity, RD_DBG(A) == nullptr) && RD_DBG(A) && lane == 0) {
+        if (atomicAdd(&RD_DBG(A)[0], 1u) == 0) { RD_DBG(A)[1] = blockIdx.x; RD_DBG(A)[2] = blockIdx.y; RD_DBG(A)[3] = warp; RD_DBG(A)[4] = (uint32_t)pz; RD_DBG(A)[5] = parity; RD_DBG(A)[6] = (uint32_t)zb; RD_DBG(A)[7] = (uint32_t)ze; }
       }
       parity ^= 1;
       double* tile = wring + (size_t)q * NR * SWP;
@@ -1102,10 +1110,10 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
     {
       const uint32_t q = (uint32_t)qc, ph = phc;
       bool ok = true;
-      if (wait_lo) ok = mbar_wait(rowbar0 + 8 * (q * W + warp - 1), ph, A.dbg == nullptr);
-      if (wait_hi) ok = mbar_wait(rowbar0 + 8 * (q * W + warp + 1), ph, A.dbg == nullptr) && ok;
-      if (!ok && A.dbg && lane == 0) {
-        if (atomicAdd(&A.dbg[0], 1u) == 0) { A.dbg[1] = blockIdx.x; A.dbg[2] = blockIdx.y; A.dbg[3] = warp; A.dbg[4] = (uint32_t)zc; A.dbg[5] = 99; A.dbg[6] = (uint32_t)zb; A.dbg[7] = (uint32_t)ze; }
+      if (wait_lo) ok = mbar_wait(rowbar0 + 8 * (q * W + warp - 1), ph, RD_DBG(A) == nullptr);
+      if (wait_hi) ok = mbar_wait(rowbar0 + 8 * (q * W + warp + 1), ph, RD_DBG(A) == nullptr) && ok;
+      if (!ok && RD_DBG(A) && lane == 0) {
+        if (atomicAdd(&RD_DBG(A)[0], 1u) == 0) { RD_DBG(A)[1] = blockIdx.x; RD_DBG(A)[2] = blockIdx.y; RD_DBG(A)[3] = warp; RD_DBG(A)[4] = (uint32_t)zc; RD_DBG(A)[5] = 99; RD_DBG(A)[6] = (uint32_t)zb; RD_DBG(A)[7] = (uint32_t)ze; }
       }
     }
     const int qp = qs;  // plane zc + 1 was staged in this iteration
@@ -1121,7 +1129,7 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
         A, kc, smem_raw + HDRZ, S, cls, lane, active, fl, idx0, cur, cur + SWP, cur - SWP, base + (size_t)qp * NR * SWP,
         base + (size_t)qm * NR * SWP, mycs, mycbar, cparity, segmask);
     if (MODE == MODE_FINAL) {
-      if (!waited) mbar_wait(mycbar, cparity, A.dbg == nullptr);
+      if (!waited) mbar_wait(mycbar, cparity, RD_DBG(A) == nullptr);
       cparity ^= 1;
     }
     __syncwarp();

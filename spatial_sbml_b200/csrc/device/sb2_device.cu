@@ -1113,7 +1113,8 @@ int sb2_finalize(sb2_sim* sim) {
     {
       const char* jenv = getenv("SB2_JIT");
       const bool require = jenv && !strcmp(jenv, "require");
-      if (jenv && !strcmp(jenv, "0")) { sim->jit_mode = 0; sim->jit_info = "interpreter kernel: SB2_JIT=0"; }
+      if (getenv("SB2_DEBUG")) { sim->jit_mode = 0; sim->jit_info = "interpreter kernel: SB2_DEBUG is set (the specialised build carries no debug words)"; }
+      else if (jenv && !strcmp(jenv, "0")) { sim->jit_mode = 0; sim->jit_info = "interpreter kernel: SB2_JIT=0"; }
       else if (jenv && !strcmp(jenv, "background")) sim->jit_mode = 2;
       else if (jenv) sim->jit_mode = 1;
       else sim->jit_mode = ncells(sim) >= (1 << 20) ? 1 : 2;
