@@ -344,6 +344,48 @@ def sharded_check(h, synthetic, ShardedSimulator, sb):
     return out
 
 
+def advection_workload(sb, synthetic, torch, peak, K, W, n=4096):
+    """CIP-CSLR advection at scale (+40 * d * S_adv bytes per cell-update): two species advected along x and y
+    (uniform velocities) with diffusion and a reaction beside it, n x n cells.  Reports the whole step and the direction pass on
+    its own, the pass against the HBM roofline with the survey's 40 bytes per cell, pass and species."""
+    import ctypes as C
+    t0 = time.time()
+    sim = sb.SpatialSimulator()
+    sim.initFromString(synthetic.advection_uniform(n, n), n, n, 1)
+    init_s = time.time() - t0
+    dt = 0.05
+    cells = sim.getNumDomainCells()
+    sim.runSteps(0, dt, W)
+    times = []
+    for r in range(3):
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        sim.runSteps(W + r * K, dt, K)
+        torch.cuda.synchronize()
+        times.append(1e3 * (time.perf_counter() - t1) / K)
+    ms_step = statistics.median(times)
+    lib = sb.load_library()
+    ms_pass, npass = C.c_double(0.0), C.c_int(0)
+    rc = lib.sb2_time_advection(C.c_void_p(sim.getDeviceHandle()), dt, 10, C.byref(ms_pass), C.byref(npass))
+    u = sim.getVariableCompact("P")
+    import numpy as np
+    finite = bool(np.isfinite(u).all())
+    sim.close()
+    S_adv, d = 2, 2
+    bytes_pass = 40.0 * cells  # per species and direction pass
+    ach = bytes_pass / (ms_pass.value * 1e-3) / 1e9 if ms_pass.value > 0 else None
+    bytes_step = cells * (104 * S_adv + 4 + 40 * d * S_adv)
+    return {"workload": "synthetic advection (2 species, uniform velocities on both axes, diffusion, one reaction) %dx%d cells, 1 GPU" % (n, n),
+            "grid": [n, n], "dt": dt, "cells": int(cells), "init_s": init_s, "ms_per_step": ms_step, "value": cells / (ms_step * 1e-3),
+            "unit": "cell-updates/s", "finite": finite, "passes_per_step": npass.value, "rc": rc,
+            "roofline_step": {"bound": "hbm", "achieved": bytes_step / (ms_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                              "frac": bytes_step / (ms_step * 1e-3) / 1e9 / peak,
+                              "algorithmic_bytes_per_cell_update": 104 * S_adv + 4 + 40 * d * S_adv},
+            "roofline": {"bound": "hbm", "kernel": "cip2d_x_kernel / cip2d_y_kernel (one fused direction pass of one species)",
+                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
+                         "algorithmic_bytes_per_launch": bytes_pass, "avg_launch_ms": ms_pass.value}}
+
+
 def example_models(sb, torch, steps=300):
     """The reference's own example models (BASELINE configs 1-4): µs per oneStep on the GPU (model-specialised kernel, what a long
     run settles to) next to the reference's serial CPU step timed in the same run, with the fraction of the HBM roofline."""
@@ -409,7 +451,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="only the headline workload (profiling runs)")
-    ap.add_argument("--secondary", default=os.environ.get("BENCH_SECONDARY", "dim3,strong2d,strong3d,brusselator,examples"))
+    ap.add_argument("--secondary", default=os.environ.get("BENCH_SECONDARY", "dim3,strong2d,strong3d,brusselator,advection,examples"))
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -585,6 +627,12 @@ def main():
             secondary["strong_3d_global_512cubed"] = {"same_as": "dim3_weak_512cubed_per_gpu (one GPU)", "value": d3.get("value"), "ms_per_step": d3.get("ms_per_step")}
     if "brusselator" in want and args.model != "brusselator":
         secondary["brusselator_8192sq_per_gpu"] = run_secondary("brusselator", "brusselator", 2, 8192, "weak", 0.1, peak)
+
+    if "advection" in want and world == 1 and rank == 0:
+        try:
+            secondary["advection_4096sq"] = advection_workload(sb, synthetic, torch, peak, K, W)
+        except Exception as e:  # noqa: BLE001
+            secondary["advection_4096sq"] = {"error": repr(e)}
 
     if rank != 0:
         if world > 1:

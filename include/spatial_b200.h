@@ -238,6 +238,10 @@ SB2_API int sb2_download_field(sb2_sim* sim, int field, double* out);  /* fields
 SB2_API int sb2_upload_faces(sb2_sim* sim, int species, int axis, const double* in);
 SB2_API int sb2_download_faces(sb2_sim* sim, int species, int axis, double* out);
 
+/* Measurement aid (bench.py): runs the CIP-CSLR direction passes of one step `reps` times and reports the mean duration of a
+ * pass (CUDA events on the handle's stream) and how many passes a step has.  The state is advected along. */
+SB2_API int sb2_time_advection(sb2_sim* sim, double dt, int reps, double* ms_per_pass, int* passes_per_step);
+
 /* checkStability.cpp:10-52 / 119-154: largest admissible dt (min-reduction over the domain). */
 SB2_API int sb2_min_dt(sb2_sim* sim, double dt, double* out);
 

@@ -95,6 +95,7 @@ def _proto(lib):
         "sb2_upload_faces": (ci, [vp, ci, ci, dp]),
         "sb2_download_faces": (ci, [vp, ci, ci, dp]),
         "sb2_min_dt": (ci, [vp, cd, dp]),
+        "sb2_time_advection": (ci, [vp, cd, ci, dp, C.POINTER(ci)]),
         "sb2_species_view": (ci, [vp, ci, ci, C.POINTER(FieldView)]),
         "sb2_begin_step": (ci, [vp, cd, cd, ci]),
         "sb2_stage": (ci, [vp, ci, ci]),

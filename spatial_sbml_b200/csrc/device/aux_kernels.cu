@@ -277,22 +277,15 @@ __device__ __forceinline__ bool cip_dom(const Sb2CipArgs& A, int64_t idx, int c,
   return A.flags[idx + off * st] & SB2_F_DOMAIN;
 }
 
-// flux loop of one direction pass (calcPDE.cpp:581-651 for X; Y and Z passes are identical up to the axis)
-__global__ void __launch_bounds__(256) cip_flux_kernel(const __grid_constant__ Sb2CipArgs A, int axis) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = blockIdx.y + (A.dim == 2 ? A.row_begin : 0), k = blockIdx.z + (A.dim == 3 ? A.row_begin : 0);
-  if (i >= A.nx) return;
-  const int64_t idx = A.first + (int64_t)k * A.PL + (int64_t)j * A.P + i;
-  const uint32_t f = A.flags[idx];
-  if (!(f & SB2_F_DOMAIN)) return;
-  const int c = axis == 0 ? i : axis == 1 ? j : k;
-  const int n = axis == 0 ? A.nx : axis == 1 ? A.ny : A.nz;
-  const int64_t st = axis == 0 ? 1 : axis == 1 ? A.P : A.PL;
+// One cell of the flux loop of a direction pass (calcPDE.cpp:581-651 for X; the Y and Z passes are identical up to the axis):
+// the increment of the cell average dc = (g_in - g_out) / delta and, when the cell has a plus face inside the domain, the
+// increment of that face's point value.
+__device__ __forceinline__ void cip_cell(const Sb2CipArgs& A, const int axis, const int64_t idx, const int c, const int n, const int64_t st,
+                                         const uint32_t f, double& dc, double& newface, bool& has_face) {
   const double* val = A.u;
   const double* face = A.faces[axis];
   const double delta = A.delta[axis];
   const double dt = A.dt;
-
   const bool d_p1 = cip_dom(A, idx, c, n, 1, st), d_p2 = cip_dom(A, idx, c, n, 2, st);
   const bool d_m1 = cip_dom(A, idx, c, n, -1, st), d_m2 = cip_dom(A, idx, c, n, -2, st);
   const double v0 = val[idx];
@@ -312,6 +305,8 @@ __global__ void __launch_bounds__(256) cip_flux_kernel(const __grid_constant__ S
   const bool bofp = f & (SB2_F_XP << (2 * axis));
   const bool bofm = f & (SB2_F_XM << (2 * axis));
   double g_in = 0.0, g_out = 0.0;
+  has_face = false;
+  newface = 0.0;
   if (!bofp) {
     double a_i, b_i, beta_i;
     if (ux >= 0) {
@@ -325,15 +320,15 @@ __global__ void __launch_bounds__(256) cip_flux_kernel(const __grid_constant__ S
     }
     const double mxi = -xi;
     const double den = 1.0 + beta_i * mxi;
-    double newface = (a_i + 2 * b_i * mxi + beta_i * b_i * (mxi * mxi)) / (den * den) - vp1;
+    double nf = (a_i + 2 * b_i * mxi + beta_i * b_i * (mxi * mxi)) / (den * den) - vp1;
     if (ufield) {
       // correction due to velocity divergence (calcPDE.cpp:623-625): the velocity at Xplus3 and Xminus1, i.e. at the face of the
       // next cell and of the previous cell, each collapsed like the value indices
       const double u3 = d_p2 ? A.afield_face[axis][idx + st] : (d_p1 ? A.afield[axis][idx + st] : A.afield[axis][idx]);
       const double um1 = d_m1 ? A.afield_face[axis][idx - st] : A.afield[axis][idx];
-      newface = newface + ((dt / (2 * delta)) * (vp1 + newface)) * (u3 - um1);
+      nf = nf + ((dt / (2 * delta)) * (vp1 + nf)) * (u3 - um1);
     }
-    if (d_p1) A.tmp_face[idx] = newface;
+    if (d_p1) { has_face = true; newface = nf; }
     const double G = (-a_i * xi + b_i * (xi * xi)) / (-1.0 + beta_i * xi);
     if (ux >= 0) g_out = G; else g_in = -G;
   }
@@ -351,7 +346,95 @@ __global__ void __launch_bounds__(256) cip_flux_kernel(const __grid_constant__ S
       g_out = -(-a_i2 * xi + b_i2 * (xi * xi)) / (-1.0 + beta_i2 * xi);
     }
   }
-  A.tmp_cell[idx] = (g_in - g_out) / delta;
+  dc = (g_in - g_out) / delta;
+}
+
+// flux loop of one direction pass, one cell per thread (3-D grids; 2-D grids run the fused pass below)
+__global__ void __launch_bounds__(256) cip_flux_kernel(const __grid_constant__ Sb2CipArgs A, int axis) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y + (A.dim == 2 ? A.row_begin : 0), k = blockIdx.z + (A.dim == 3 ? A.row_begin : 0);
+  if (i >= A.nx) return;
+  const int64_t idx = A.first + (int64_t)k * A.PL + (int64_t)j * A.P + i;
+  const uint32_t f = A.flags[idx];
+  if (!(f & SB2_F_DOMAIN)) return;
+  const int c = axis == 0 ? i : axis == 1 ? j : k;
+  const int n = axis == 0 ? A.nx : axis == 1 ? A.ny : A.nz;
+  const int64_t st = axis == 0 ? 1 : axis == 1 ? A.P : A.PL;
+  double dc, nf;
+  bool has_face;
+  cip_cell(A, axis, idx, c, n, st, f, dc, nf, has_face);
+  if (has_face) A.tmp_face[idx] = nf;
+  A.tmp_cell[idx] = dc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2-D: one kernel per direction pass.  A thread owns a column of a strip and marches over the rows of its block: flux loop,
+// update sweep and the advance of the other axis' faces in one go, out of place for u and for the faces of the pass axis
+// (the flux loop of a neighbouring cell must still see the old values; the caller swaps the buffers), in place for the
+// faces of the other axis (only their own cell touches them).  Per cell and pass: read u, the axis faces and a flag byte,
+// write u and the axis faces, read-modify-write the other faces — 49 bytes, against two full-array memsets, two kernels
+// and ~140 bytes before.  The increment of the cell across the other axis, which the face between them needs, comes from
+// the previous row of the march (X pass) or from the neighbouring thread through shared memory (Y pass).
+constexpr int kCipThreads = 128;
+constexpr int kCipRows = 32;
+
+__global__ void __launch_bounds__(kCipThreads) cip2d_x_kernel(const __grid_constant__ Sb2CipArgs A) {
+  const int i = blockIdx.x * kCipThreads + threadIdx.x;
+  if (i >= A.nx) return;
+  const int jb = A.row_begin + (int)blockIdx.y * kCipRows;
+  const int je = min(jb + kCipRows, A.row_end);
+  // one more row (flux only) where the face above the block's last row needs the increment of the row beyond
+  const int jl = je < A.flux_row_end ? je + 1 : je;
+  double dc_prev = 0.0;
+  uint32_t f_prev = 0;
+  for (int j = jb; j < jl; ++j) {
+    const int64_t idx = A.first + (int64_t)j * A.P + i;
+    const uint32_t f = A.flags[idx];
+    double dc = 0.0, nf = 0.0;
+    bool has_face = false;
+    if (f & SB2_F_DOMAIN) cip_cell(A, 0, idx, i, A.nx, 1, f, dc, nf, has_face);
+    if (j < je) {
+      // val += val_delta at every point of the row (calcPDE.cpp:657): cells and the faces of this axis
+      A.u_out[idx] = A.u[idx] + dc;
+      A.face_out[idx] = A.faces[0][idx] + (has_face ? nf : 0.0);
+    }
+    if (j > jb && (f_prev & SB2_F_DOMAIN) && !(f_prev & SB2_F_YP) && j < A.ny) {
+      // val(x, y+1/2) += (val_delta(x, y+1) + val_delta(x, y)) / 2 for the row below (calcPDE.cpp:659-663)
+      const int64_t ip = idx - A.P;
+      A.faces[1][ip] = A.faces[1][ip] + (dc + dc_prev) / 2.0;
+    }
+    dc_prev = dc;
+    f_prev = f;
+  }
+}
+
+__global__ void __launch_bounds__(kCipThreads) cip2d_y_kernel(const __grid_constant__ Sb2CipArgs A) {
+  // strips overlap by one column: the last thread of a block only supplies the increment its left neighbour needs
+  const int i = (int)blockIdx.x * (kCipThreads - 1) + threadIdx.x;
+  const int jb = A.row_begin + (int)blockIdx.y * kCipRows;
+  const int je = min(jb + kCipRows, A.row_end);
+  __shared__ double sdc[2][kCipThreads];
+  const bool inside = i < A.nx;
+  const bool owner = inside && threadIdx.x < kCipThreads - 1;
+  int buf = 0;
+  for (int j = jb; j < je; ++j, buf ^= 1) {
+    const int64_t idx = A.first + (int64_t)j * A.P + i;
+    uint32_t f = 0;
+    double dc = 0.0, nf = 0.0;
+    bool has_face = false;
+    if (inside) {
+      f = A.flags[idx];
+      if (f & SB2_F_DOMAIN) cip_cell(A, 1, idx, j, A.ny, A.P, f, dc, nf, has_face);
+    }
+    sdc[buf][threadIdx.x] = dc;
+    __syncthreads();
+    if (owner) {
+      A.u_out[idx] = A.u[idx] + dc;
+      A.face_out[idx] = A.faces[1][idx] + (has_face ? nf : 0.0);
+      if ((f & SB2_F_DOMAIN) && !(f & SB2_F_XP) && i + 1 < A.nx)
+        A.faces[0][idx] = A.faces[0][idx] + (sdc[buf][threadIdx.x + 1] + dc) / 2.0;  // calcPDE.cpp:747-751
+    }
+  }
 }
 
 // update sweep (calcPDE.cpp:654-673): add the increments and advance the faces of the other axes
@@ -384,6 +467,13 @@ cudaError_t sb2_launch_cip_pass(const Sb2CipArgs& a, int axis, cudaStream_t stre
   if (a.akind[axis] == SB2_SRC_NONE) return cudaSuccess;
   const int nflux = a.flux_row_end - a.row_begin, nupd = a.row_end - a.row_begin;
   if (nupd <= 0) return cudaSuccess;
+  if (a.dim == 2 && a.u_out && a.face_out) {
+    // fused pass: the caller swaps u / u_out and faces[axis] / face_out afterwards
+    if (launches) *launches += 1;
+    if (axis == 0) cip2d_x_kernel<<<dim3((a.nx + kCipThreads - 1) / kCipThreads, (nupd + kCipRows - 1) / kCipRows), kCipThreads, 0, stream>>>(a);
+    else cip2d_y_kernel<<<dim3((a.nx + kCipThreads - 2) / (kCipThreads - 1), (nupd + kCipRows - 1) / kCipRows), kCipThreads, 0, stream>>>(a);
+    return cudaGetLastError();
+  }
   cudaError_t e = cudaMemsetAsync(a.tmp_cell, 0, sizeof(double) * a.nalloc, stream);
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(a.tmp_face, 0, sizeof(double) * a.nalloc, stream);

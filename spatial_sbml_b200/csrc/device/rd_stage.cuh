@@ -258,8 +258,18 @@ __device__ __forceinline__ void rd_emit_row(const Sb2RdArgs& A, const int S, con
               cu[p] = *reinterpret_cast<const double2*>(sp.u + i);        // L2 hits: staged through L2 one batch ago
               ck2[p] = *reinterpret_cast<const double2*>(sp.kprev + i);
             }
+#ifdef SB2_RD_FINAL_LDG
+            // k0 / k1 are read once and never shared: plain loads (no shared-memory slot, which buys the last stage of a 3-D
+            // grid a second CTA per SM at four cells per thread)
+            ck0[p] = ck1[p] = make_double2(0.0, 0.0);
+            if (!MASKED || active[p]) {
+              ck0[p] = *reinterpret_cast<const double2*>(sp.k0 + i);
+              ck1[p] = *reinterpret_cast<const double2*>(sp.k1 + i);
+            }
+#else
             ck0[p] = *reinterpret_cast<const double2*>(mycs + (s * 2) * SW + p * 64 + 2 * lane);
             ck1[p] = *reinterpret_cast<const double2*>(mycs + (s * 2 + 1) * SW + p * 64 + 2 * lane);
+#endif
           }
         }
         // one pair of cells; PM: this pair's 64-cell segment needs the per-cell predicates (segmask, warp-uniform)
@@ -379,8 +389,13 @@ __device__ __forceinline__ void rd_emit_row(const Sb2RdArgs& A, const int S, con
             const double2 u = *reinterpret_cast<const double2*>(sp.u + idx);
             double2 o = u;
             if (in0 || in1) {
+#ifdef SB2_RD_FINAL_LDG
+              const double2 k0 = *reinterpret_cast<const double2*>(sp.k0 + idx);
+              const double2 k1 = *reinterpret_cast<const double2*>(sp.k1 + idx);
+#else
               const double2 k0 = *reinterpret_cast<const double2*>(mycs + (s * 2) * SW + p * 64 + 2 * lane);
               const double2 k1 = *reinterpret_cast<const double2*>(mycs + (s * 2 + 1) * SW + p * 64 + 2 * lane);
+#endif
               const double2 k2 = *reinterpret_cast<const double2*>(sp.kprev + idx);
               if (in0) o.x = dadd(u.x, div6(dmul(A.dt, dadd(dadd(dadd(k0.x, dmul(2.0, k1.x)), dmul(2.0, k2.x)), a0))));
               if (in1) o.y = dadd(u.y, div6(dmul(A.dt, dadd(dadd(dadd(k0.y, dmul(2.0, k1.y)), dmul(2.0, k2.y)), a1))));
@@ -585,7 +600,12 @@ CASE(OP, 4, (4 < NS ? 0 : DEPTH)) CASE(OP, 5, (5 < NS ? 0 : DEPTH)) CASE(OP, 6, 
   }
 
   // ---------------- diffusion (calcPDE.cpp:484-559) + output ----------------
-  if (MODE == MODE_FINAL) mbar_wait(mycbar, cparity, RD_DBG(A) == nullptr);  // k0 / k1 of this row (requested one batch ago)
+#ifdef SB2_RD_FINAL_LDG
+  constexpr bool kSlots = !D3;  // (the 2-D kernel keeps its k0 / k1 slots)
+#else
+  constexpr bool kSlots = true;
+#endif
+  if (MODE == MODE_FINAL && kSlots) mbar_wait(mycbar, cparity, RD_DBG(A) == nullptr);  // k0 / k1 of this row (requested one batch ago)
   rd_emit_row<NS, NP, MODE, D3>(A, S, cls, lane, active, fl, acc, idx0, mycs, cur0, up0, dn0, zp0, zm0, SSTRIDE, segmask);
   return true;
 }
@@ -971,9 +991,14 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
 #pragma unroll
   for (int p = 0; p < NP; ++p) active[p] = x0 + p * 64 + 2 * lane < A.nx;
 
+#ifdef SB2_RD_FINAL_LDG
+  constexpr bool kSlots = false;
+#else
+  constexpr bool kSlots = true;
+#endif
   if (elect_one()) {
     issue_rows();
-    if (MODE == MODE_FINAL && computes) issue_combine(A.first + (int64_t)zb * A.PL + (int64_t)y * A.P + x0);
+    if (MODE == MODE_FINAL && kSlots && computes) issue_combine(A.first + (int64_t)zb * A.PL + (int64_t)y * A.P + x0);
   }
   grow += A.PL; ghrow += A.PL;
   uint32_t parity = 0, cparity = 0;
@@ -1128,13 +1153,13 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
     const bool waited = rd_compute_row<NS, NP, MODE, DEPTH, true, SSTRIDE>(
         A, kc, smem_raw + HDRZ, S, cls, lane, active, fl, idx0, cur, cur + SWP, cur - SWP, base + (size_t)qp * NR * SWP,
         base + (size_t)qm * NR * SWP, mycs, mycbar, cparity, segmask);
-    if (MODE == MODE_FINAL) {
+    if (MODE == MODE_FINAL && kSlots) {
       if (!waited) mbar_wait(mycbar, cparity, RD_DBG(A) == nullptr);
       cparity ^= 1;
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(donebar0 + 8 * (qc * W + warp));  // (5) row (zc, j) will not be read by this warp's stencil again
-    if (MODE == MODE_FINAL && zc + 1 < ze && elect_one()) issue_combine(idx_run + A.PL - 2 * lane);
+    if (MODE == MODE_FINAL && kSlots && zc + 1 < ze && elect_one()) issue_combine(idx_run + A.PL - 2 * lane);
   }
 }
 

@@ -54,6 +54,10 @@ struct Sb2CipArgs {
   const uint8_t* flags;
   double* tmp_cell;   // scratch: cell increments
   double* tmp_face;   // scratch: face increments of the pass direction
+  // 2-D fused pass (NULL: the two-kernel pass): the new cell averages and the new faces of the pass axis are written here,
+  // the caller swaps them with u / faces[axis] afterwards
+  double* u_out;
+  double* face_out;
   // rows (2-D) / planes (3-D) of the slab axis: the update sweep runs on [row_begin, row_end), the flux loop on
   // [row_begin, flux_row_end) (one more row where a neighbouring slab's first row feeds a face of the last owned row)
   int32_t row_begin, row_end, flux_row_end;

@@ -27,6 +27,8 @@ struct Sb2Species {
   int bckind[6], bcskind[6], bcsrc[6];
   bool has_diff, has_adv, has_bc;
   double* faces[3];  // CIP face values (advected species only)
+  double* faces_alt[3];  // 2-D: the other half of their double buffer (a fused direction pass writes the new faces of its axis there)
+  int face_par;          // bit a: the halves of axis a have been swapped an odd number of times
 };
 
 struct Sb2Stmt {
@@ -92,10 +94,12 @@ struct sb2_sim {
   std::vector<cudaEvent_t> ev_up, ev_done;
   cudaEvent_t ev_start;
   // sb2_step: CUDA graph of two consecutive steps (one per buffer parity) for small, launch-latency-bound grids
-  cudaGraphExec_t gexec[2];
-  double g_dt[2];
-  uint64_t g_version[2];
-  int g_launches[2];
+#define SB2_GRAPH_SLOTS 8
+  cudaGraphExec_t gexec[SB2_GRAPH_SLOTS];
+  double g_dt[SB2_GRAPH_SLOTS];
+  uint64_t g_version[SB2_GRAPH_SLOTS];
+  int g_launches[SB2_GRAPH_SLOTS];
+  int64_t g_key[SB2_GRAPH_SLOTS];  // the buffer state (par_key) a slot's graph was captured in
   uint64_t version;  // bumped by everything that can change a kernel argument (constants, uploads that allocate)
   std::vector<Sb2RdTok> rdprog;  // lowered token records (constants patched per launch from rdslot)
   std::vector<int> rdslot;       // constants-table slot of each record's inline constant, -1 = none
@@ -123,6 +127,13 @@ int cuda_fail(sb2_sim* s, cudaError_t e, const char* what) {
 #define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail(sim, e__, #call); } while (0)
 
 int64_t ncells(const sb2_sim* s) { return (int64_t)s->g.nx * s->g.ny * s->g.nz; }
+
+// which halves of the double buffers are current (a captured step graph is valid for exactly one such state)
+uint64_t par_key(const sb2_sim* s) {
+  uint64_t k = 1;
+  for (size_t i = 0; i < s->species.size(); ++i) k = k * 16 + (uint64_t)(s->species[i].cur * 8 + s->species[i].face_par);
+  return k;
+}
 
 Sb2MemView mem_view(const sb2_sim* s) {
   Sb2MemView v;
@@ -490,7 +501,7 @@ void fill_stage_args(sb2_sim* sim, Sb2StageCore& a, int m, double dt, int row_be
 Sb2RdJitSpec jit_spec(const sb2_sim* sim) {
   Sb2RdJitSpec spec;
   spec.ns = sim->base.S; spec.np = sim->rd.np; spec.w = sim->rd.w; spec.depth = sim->base.depth; spec.d3 = sim->g.dim == 3;
-  spec.minb = 2; spec.np_final = 0; spec.minb_final = 0;
+  spec.minb = 2; spec.np_final = 0; spec.minb_final = 0; spec.final_ldg = 0;
   if (spec.d3 && spec.w == 8 && spec.np == 1) {
     // 3-D (the class map has 64-cell granularity, so the strip width is free per stage).  Last stage: 2 cells per
     // thread, 74-80 registers, three CTAs per SM (deep expression stacks keep the room of two).  Other stages, up to
@@ -498,6 +509,11 @@ Sb2RdJitSpec jit_spec(const sb2_sim* sim) {
     spec.np_final = 1; spec.minb_final = spec.depth <= 4 ? 3 : 2;
     if (spec.ns <= 2 && spec.depth <= 4 && !getenv("SB2_JIT_NP1")) { spec.np = 2; spec.minb = 2; }
     else spec.minb = spec.minb_final;
+    // experiments: the last stage with four cells per thread and k0 / k1 read by plain loads (two CTAs of 105 KB per SM)
+    if (const char* e = getenv("SB2_JIT_FINAL_LDG")) {
+      spec.final_ldg = 1;
+      if (atoi(e) >= 2 && spec.np == 2) { spec.np_final = 2; spec.minb_final = 2; }
+    }
   }
   if (const char* e = getenv("SB2_JIT_MINB")) spec.minb = atoi(e) > 0 ? atoi(e) : 2;  // experiments
   spec.fold = getenv("SB2_JIT_NOFOLD") ? 0 : 1;
@@ -651,7 +667,8 @@ int sb2_create(const sb2_grid* grid, sb2_sim** out) {
   sim->launches = 0; sim->in_step = false; sim->cur_dt = 0; sim->d_scratch = NULL;
   sim->rd_id = -1; sim->d_cls = NULL; sim->nstrips = 0; sim->d_dbg = NULL;
   sim->h2d = NULL; sim->d2h = NULL; sim->ev_start = NULL; sim->d_rdtok = NULL; sim->rd_buf = 0; sim->multi_stream = false;
-  sim->gexec[0] = sim->gexec[1] = NULL; sim->version = 1; sim->jit = NULL;
+  for (int p = 0; p < SB2_GRAPH_SLOTS; ++p) { sim->gexec[p] = NULL; sim->g_key[p] = -1; }
+  sim->version = 1; sim->jit = NULL;
   sim->jit_job = NULL; sim->jit_mode = 0; sim->steps_seen = 0; sim->capturing = false;
   sim->trace = getenv("SB2_TRACE") != NULL;
   memset(&sim->base, 0, sizeof(sim->base));
@@ -674,7 +691,7 @@ void sb2_destroy(sb2_sim* sim) {
     Sb2Species& s = sim->species[i];
     cudaFree(s.u[0]); cudaFree(s.u[1]);
     for (int m = 0; m < 4; ++m) cudaFree(s.k[m]);
-    for (int a = 0; a < 3; ++a) if (s.faces[a]) cudaFree(s.faces[a]);
+    for (int a = 0; a < 3; ++a) { if (s.faces[a]) cudaFree(s.faces[a]); if (s.faces_alt[a]) cudaFree(s.faces_alt[a]); }
   }
   for (size_t i = 0; i < sim->transports.size(); ++i) sb2_free_transport(sim->transports[i]);
   for (int part = 0; part < 3; ++part) sb2_free_boundary_lists(sim->blists[part]);
@@ -702,7 +719,7 @@ void sb2_destroy(sb2_sim* sim) {
   if (sim->d_rdtok) cudaFree(sim->d_rdtok);
   sb2_rd_jit_free(sim->jit);
   if (sim->jit_job) sb2_rd_jit_abandon(sim->jit_job);
-  for (int p = 0; p < 2; ++p) if (sim->gexec[p]) cudaGraphExecDestroy(sim->gexec[p]);
+  for (int p = 0; p < SB2_GRAPH_SLOTS; ++p) if (sim->gexec[p]) cudaGraphExecDestroy(sim->gexec[p]);
   if (sim->h2d) cudaStreamDestroy(sim->h2d);
   if (sim->d2h) cudaStreamDestroy(sim->d2h);
   if (sim->ev_start) cudaEventDestroy(sim->ev_start);
@@ -1158,6 +1175,7 @@ int sb2_finalize(sb2_sim* sim) {
       if (sp.akind[a] == SB2_SRC_FIELD && (sp.asrc[a] < 0 || sp.asrc[a] >= (int)sim->d_fields.size() || sp.afacesrc[a] <= 0))
         return fail(sim, SB2_ERR_ARG, "field-valued advection velocity: cell field and face field (sb2_set_advection_faces) are both needed");
       if (!sp.faces[a]) { rc = alloc_field(sim, &sp.faces[a]); if (rc) return rc; }
+      if (sim->g.dim == 2 && !sp.faces_alt[a] && !getenv("SB2_CIP_UNFUSED")) { rc = alloc_field(sim, &sp.faces_alt[a]); if (rc) return rc; }
     }
   }
   if (sim->any_adv) { rc = alloc_field(sim, &sim->d_tmp_face); if (rc) return rc; }
@@ -1346,8 +1364,17 @@ int launch_advection_pass(sb2_sim* sim, const AdvPass& p) {
   // the update sweep moves the faces of the OTHER axes by the mean increment of the two cells they separate: the face between
   // the last owned row and the neighbouring slab needs the increment of that slab's first row, which is computed here as well
   c.flux_row_end = (p.axis != (sim->g.dim == 3 ? 2 : 1) && r.own_hi < r.n_held) ? r.own_hi + 1 : r.own_hi;
+  const bool fused = sim->g.dim == 2 && sp.faces_alt[p.axis] != NULL;
+  if (fused) { c.u_out = sp.u[sp.cur ^ 1]; c.face_out = sp.faces_alt[p.axis]; }
   cudaError_t e = sb2_launch_cip_pass(c, p.axis, sim->stream, &sim->launches);
   if (e != cudaSuccess) return cuda_fail(sim, e, "CIP-CSLR advection kernels");
+  if (fused) {
+    // the pass wrote the new cell averages and the new faces of its axis out of place: they are the current ones now.  Rows this
+    // handle does not own (halo rows of a slab) are stale in the new halves until the exchange that follows every pass.
+    sp.cur ^= 1;
+    std::swap(sp.faces[p.axis], sp.faces_alt[p.axis]);
+    sp.face_par ^= 1 << p.axis;
+  }
   return SB2_OK;
 }
 
@@ -1669,13 +1696,21 @@ int sb2_step(sb2_sim* sim, double t_arg, double t_incr, double dt, int nsteps, i
   if (graphable) {
     for (; i < 2; ++i) if ((rc = one_plain_step(sim, t_arg + i * t_incr, dt, time_slot))) return rc;
     const int pairs = (nsteps - i) / 2;
-    const int par = sim->species.empty() ? 0 : sim->species[0].cur;
+    // which halves of the double buffers are current: u of every species and, for advected species, the faces
+    int par = 0;
+    for (size_t s = 0; s < sim->species.size(); ++s) par = (par * 5 + sim->species[s].cur * 8 + sim->species[s].face_par) & 0xffff;
+    par = (int)((unsigned)par % SB2_GRAPH_SLOTS);
+    if (sim->g_key[par] != (int64_t)par_key(sim)) {  // another buffer state hashed to this slot: rebuild
+      if (sim->gexec[par]) { cudaGraphExecDestroy(sim->gexec[par]); sim->gexec[par] = NULL; }
+      sim->g_key[par] = (int64_t)par_key(sim);
+    }
     bool fresh = false;
     if (!sim->gexec[par] || sim->g_dt[par] != dt || sim->g_version[par] != sim->version) {
       if (sim->gexec[par]) { cudaGraphExecDestroy(sim->gexec[par]); sim->gexec[par] = NULL; }
       // host-side state the two captured steps will advance
       std::vector<int> cur0(sim->species.size());
       for (size_t s = 0; s < sim->species.size(); ++s) cur0[s] = sim->species[s].cur;
+      const std::vector<Sb2Species> species0(sim->species);
       const bool carry_valid0 = sim->k0_carry_valid;
       const int launches0 = sim->launches;
       cudaGraph_t graph = NULL;
@@ -1693,6 +1728,7 @@ int sb2_step(sb2_sim* sim, double t_arg, double t_incr, double dt, int nsteps, i
         // not capturable after all: put the host state back and take the ordinary path
         cudaGetLastError();
         sim->gexec[par] = NULL;
+        sim->species = species0;
         for (size_t s = 0; s < sim->species.size(); ++s) sim->species[s].cur = cur0[s];
         sim->k0_carry_valid = carry_valid0;
         sim->launches = launches0;
@@ -1893,6 +1929,35 @@ int sb2_min_dt(sb2_sim* sim, double dt, double* out) {
   return SB2_OK;
 }
 
+// Measurement aid: `reps` times the CIP-CSLR direction passes of one step, timed with CUDA events on the handle's stream.
+int sb2_time_advection(sb2_sim* sim, double dt, int reps, double* ms_per_pass, int* passes_per_step) {
+  if (!sim || !sim->finalized || !ms_per_pass || reps < 1) return fail(sim, SB2_ERR_ARG, "bad argument");
+  if (sim->g.own_hi > sim->g.own_lo) return fail(sim, SB2_ERR_STATE, "sb2_time_advection needs a handle that owns its whole grid");
+  cudaSetDevice(sim->g.device);
+  sim->cur_dt = dt;
+  const std::vector<AdvPass> passes = advection_passes(sim);
+  if (passes_per_step) *passes_per_step = (int)passes.size();
+  *ms_per_pass = 0.0;
+  if (passes.empty()) return SB2_OK;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  int rc = SB2_OK;
+  for (size_t i = 0; i < passes.size() && !rc; ++i) rc = launch_advection_pass(sim, passes[i]);  // warm-up
+  CK(cudaEventRecord(e0, sim->stream));
+  for (int r = 0; r < reps && !rc; ++r)
+    for (size_t i = 0; i < passes.size() && !rc; ++i) rc = launch_advection_pass(sim, passes[i]);
+  CK(cudaEventRecord(e1, sim->stream));
+  CK(cudaEventSynchronize(e1));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (rc) return rc;
+  *ms_per_pass = (double)ms / ((double)reps * (double)passes.size());
+  ++sim->version;
+  return SB2_OK;
+}
+
 int sb2_species_view(sb2_sim* sim, int species, int which, sb2_field_view* out) {
   if (!sim || !out || species < 0 || species >= (int)sim->species.size() || which < 0 || which > 5)
     return fail(sim, SB2_ERR_ARG, "bad species / selector");
@@ -1931,7 +1996,7 @@ int sb2_specialize_dry_run(const uint32_t* code, const uint32_t* arg, int n, int
   for (int i = 0; i < n; ++i) { prog[i].code = code[i]; prog[i].arg = arg[i]; prog[i].c = 0.0; }
   Sb2RdJitSpec spec;
   spec.ns = ns; spec.np = np; spec.w = w; spec.depth = depth; spec.minb = minb; spec.d3 = d3;
-  spec.np_final = 0; spec.minb_final = 0;
+  spec.np_final = 0; spec.minb_final = 0; spec.final_ldg = 0;
   // a typical model: one geometry, every species diffuses with uniform coefficients
   spec.fold = 1; spec.G = 1; spec.hasdiff_mask = spec.fastpath_mask = (1u << ns) - 1u; spec.geo_bits = 0;
   std::vector<char> cubin;

@@ -119,11 +119,12 @@ int sb2_stage_pairs(int nx, int nspecies);
 // Grid and dynamic shared memory of an rd_stage launch (rd_stage.cuh describes the layouts): np cell pairs per thread,
 // w warps per CTA, mode 0 / 1 / 2 = first / middle / last stage, tokb = bytes of token records held in shared memory.
 // 2-D: a CTA owns a strip of 64*np cells and rows_per_block rows.  3-D: a strip, w rows and rows_per_block planes.
-static inline void sb2_rd_launch_shape(const Sb2RdArgs& a, int np, int w, int mode, bool d3, int tokb, dim3* grid, size_t* smem) {
+static inline void sb2_rd_launch_shape(const Sb2RdArgs& a, int np, int w, int mode, bool d3, int tokb, dim3* grid, size_t* smem,
+                                       bool final_ldg = false) {
   const int sw = 64 * np, swp = sw + 4, narr = mode == 0 ? 1 : 2;
   const size_t ring = d3 ? (size_t)a.S * 3 * (w + 2) * swp : (size_t)a.S * (2 * w + 2) * swp;
   const size_t raw = (size_t)(d3 ? w + 2 : w) * a.S * narr * swp;
-  const size_t cs = mode == 2 ? (size_t)w * a.S * 2 * sw : 0;
+  const size_t cs = (mode == 2 && !(d3 && final_ldg)) ? (size_t)w * a.S * 2 * sw : 0;
   const size_t hdr = d3 ? (size_t)(8 * w * 8 + 511) / 512 * 512 : 512;  // mbarriers
   *smem = hdr + tokb + sizeof(double) * (ring + raw + cs);
   grid->x = (a.nx + sw - 1) / sw;
@@ -149,6 +150,7 @@ cudaError_t sb2_rd_classify(const uint8_t* const* flags, int G, int nx, int ny, 
 struct Sb2RdJitSpec {
   int ns, np, w, depth, minb, d3;
   int np_final, minb_final;  // the last stage may use a narrower strip (3-D: it also holds the k0 / k1 rows); 0: like the others
+  int final_ldg;             // 3-D last stage: k0 / k1 are read with plain loads instead of bulk copies into shared-memory slots
   // model constants folded into the build when fold != 0: geometries, bit s of the masks = species s diffuses / takes the
   // uniform-coefficient stencil, 2 bits per species = its geometry
   int fold, G;
