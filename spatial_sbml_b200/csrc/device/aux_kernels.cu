@@ -349,6 +349,53 @@ __device__ __forceinline__ void cip_cell(const Sb2CipArgs& A, const int axis, co
   dc = (g_in - g_out) / delta;
 }
 
+// The plus-face half of cip_cell for a UNIFORM velocity: the flux through the face between the cell and its plus neighbour,
+// F = (-a xi + b xi^2) / (-1 + beta xi), and the increment of the face's point value.  With a uniform velocity the minus-face
+// flux of a cell is, operand for operand, the plus-face flux of its minus neighbour (g_in(i) = F(i-1) for u >= 0,
+// g_out(i) = -F(i-1) for u < 0, whenever the cell is not a minus-boundary cell), so each face is evaluated once.
+__device__ __forceinline__ void cip_plus_face(const Sb2CipArgs& A, const int axis, const int64_t idx, const int c, const int n, const int64_t st,
+                                              const uint32_t f, double& F, double& newface, bool& has_face) {
+  F = 0.0; newface = 0.0; has_face = false;
+  if (f & (SB2_F_XP << (2 * axis))) return;
+  const double* val = A.u;
+  const double* face = A.faces[axis];
+  const double delta = A.delta[axis];
+  const bool d_p1 = cip_dom(A, idx, c, n, 1, st), d_p2 = cip_dom(A, idx, c, n, 2, st);
+  const bool d_m1 = cip_dom(A, idx, c, n, -1, st);
+  const double v0 = val[idx];
+  const double vp1 = d_p1 ? face[idx] : v0;
+  const double ux = A.aconst[axis];
+  const double Dx = -copysign(1.0, ux) * delta;
+  const double xi = ux * A.dt;
+  double a_i, b_i, beta_i;
+  if (ux >= 0) {
+    const double vm1 = d_m1 ? face[idx - st] : v0;
+    a_i = vp1;
+    beta_i = ((fabs(vp1 - v0) + DBL_EPSILON) / (fabs(v0 - vm1) + DBL_EPSILON) - 1.0) / Dx;
+    b_i = ((1.0 + beta_i * Dx) * v0 - vp1) / Dx;
+  } else {
+    const double vp3 = d_p2 ? face[idx + st] : (d_p1 ? val[idx + st] : v0);
+    const double vp2 = d_p1 ? val[idx + st] : v0;
+    a_i = vp1;
+    beta_i = ((fabs(vp1 - vp2) + DBL_EPSILON) / (fabs(vp2 - vp3) + DBL_EPSILON) - 1.0) / Dx;
+    b_i = ((1.0 + beta_i * Dx) * vp2 - vp1) / Dx;
+  }
+  const double mxi = -xi;
+  const double den = 1.0 + beta_i * mxi;
+  const double nf = (a_i + 2 * b_i * mxi + beta_i * b_i * (mxi * mxi)) / (den * den) - vp1;
+  if (d_p1) { has_face = true; newface = nf; }
+  F = (-a_i * xi + b_i * (xi * xi)) / (-1.0 + beta_i * xi);
+}
+// increment of the cell average from the fluxes through its two faces (Fm: the plus-face flux of the minus neighbour)
+__device__ __forceinline__ double cip_dc(const Sb2CipArgs& A, const int axis, const uint32_t f, const double Fp, const double Fm) {
+  const double ux = A.aconst[axis];
+  const bool bofp = f & (SB2_F_XP << (2 * axis)), bofm = f & (SB2_F_XM << (2 * axis));
+  double g_in = 0.0, g_out = 0.0;
+  if (ux >= 0) { if (!bofp) g_out = Fp; if (!bofm) g_in = Fm; }
+  else { if (!bofp) g_in = -Fp; if (!bofm) g_out = -Fm; }
+  return (g_in - g_out) / A.delta[axis];
+}
+
 // flux loop of one direction pass, one cell per thread (3-D grids; 2-D grids run the fused pass below)
 __global__ void __launch_bounds__(256) cip_flux_kernel(const __grid_constant__ Sb2CipArgs A, int axis) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -379,20 +426,34 @@ constexpr int kCipThreads = 128;
 constexpr int kCipRows = 32;
 
 __global__ void __launch_bounds__(kCipThreads) cip2d_x_kernel(const __grid_constant__ Sb2CipArgs A) {
-  const int i = blockIdx.x * kCipThreads + threadIdx.x;
-  if (i >= A.nx) return;
+  // strips overlap by one column on the left: thread 0 only supplies the face flux its right neighbour needs
+  const int i = (int)blockIdx.x * (kCipThreads - 1) + (int)threadIdx.x - 1;
   const int jb = A.row_begin + (int)blockIdx.y * kCipRows;
   const int je = min(jb + kCipRows, A.row_end);
   // one more row (flux only) where the face above the block's last row needs the increment of the row beyond
   const int jl = je < A.flux_row_end ? je + 1 : je;
+  const bool inside = i >= 0 && i < A.nx;
+  const bool owner = inside && threadIdx.x > 0;
+  const bool shared_flux = A.akind[0] == SB2_SRC_CONST;  // uniform velocity: every face flux is evaluated once
+  __shared__ double sF[2][kCipThreads];
   double dc_prev = 0.0;
   uint32_t f_prev = 0;
-  for (int j = jb; j < jl; ++j) {
+  int buf = 0;
+  for (int j = jb; j < jl; ++j, buf ^= 1) {
     const int64_t idx = A.first + (int64_t)j * A.P + i;
-    const uint32_t f = A.flags[idx];
-    double dc = 0.0, nf = 0.0;
+    uint32_t f = 0;
+    double dc = 0.0, nf = 0.0, Fp = 0.0;
     bool has_face = false;
-    if (f & SB2_F_DOMAIN) cip_cell(A, 0, idx, i, A.nx, 1, f, dc, nf, has_face);
+    if (inside) f = A.flags[idx];
+    if (shared_flux) {
+      if (f & SB2_F_DOMAIN) cip_plus_face(A, 0, idx, i, A.nx, 1, f, Fp, nf, has_face);
+      sF[buf][threadIdx.x] = Fp;
+      __syncthreads();
+      if (owner && (f & SB2_F_DOMAIN)) dc = cip_dc(A, 0, f, Fp, sF[buf][threadIdx.x - 1]);
+    } else if (owner && (f & SB2_F_DOMAIN)) {
+      cip_cell(A, 0, idx, i, A.nx, 1, f, dc, nf, has_face);
+    }
+    if (!owner) continue;
     if (j < je) {
       // val += val_delta at every point of the row (calcPDE.cpp:657): cells and the faces of this axis
       A.u_out[idx] = A.u[idx] + dc;
@@ -416,6 +477,15 @@ __global__ void __launch_bounds__(kCipThreads) cip2d_y_kernel(const __grid_const
   __shared__ double sdc[2][kCipThreads];
   const bool inside = i < A.nx;
   const bool owner = inside && threadIdx.x < kCipThreads - 1;
+  const bool shared_flux = A.akind[1] == SB2_SRC_CONST;
+  // uniform velocity: the flux through the face below a cell is the plus-face flux of the row below, carried along the march
+  double F_prev = 0.0;
+  if (shared_flux && inside && jb > 0) {
+    const int64_t idx = A.first + (int64_t)(jb - 1) * A.P + i;
+    const uint32_t f = A.flags[idx];
+    double nf; bool hf;
+    if (f & SB2_F_DOMAIN) cip_plus_face(A, 1, idx, jb - 1, A.ny, A.P, f, F_prev, nf, hf);
+  }
   int buf = 0;
   for (int j = jb; j < je; ++j, buf ^= 1) {
     const int64_t idx = A.first + (int64_t)j * A.P + i;
@@ -424,7 +494,13 @@ __global__ void __launch_bounds__(kCipThreads) cip2d_y_kernel(const __grid_const
     bool has_face = false;
     if (inside) {
       f = A.flags[idx];
-      if (f & SB2_F_DOMAIN) cip_cell(A, 1, idx, j, A.ny, A.P, f, dc, nf, has_face);
+      if (shared_flux) {
+        double Fp = 0.0;
+        if (f & SB2_F_DOMAIN) { cip_plus_face(A, 1, idx, j, A.ny, A.P, f, Fp, nf, has_face); dc = cip_dc(A, 1, f, Fp, F_prev); }
+        F_prev = Fp;
+      } else if (f & SB2_F_DOMAIN) {
+        cip_cell(A, 1, idx, j, A.ny, A.P, f, dc, nf, has_face);
+      }
     }
     sdc[buf][threadIdx.x] = dc;
     __syncthreads();
@@ -470,7 +546,7 @@ cudaError_t sb2_launch_cip_pass(const Sb2CipArgs& a, int axis, cudaStream_t stre
   if (a.dim == 2 && a.u_out && a.face_out) {
     // fused pass: the caller swaps u / u_out and faces[axis] / face_out afterwards
     if (launches) *launches += 1;
-    if (axis == 0) cip2d_x_kernel<<<dim3((a.nx + kCipThreads - 1) / kCipThreads, (nupd + kCipRows - 1) / kCipRows), kCipThreads, 0, stream>>>(a);
+    if (axis == 0) cip2d_x_kernel<<<dim3((a.nx + kCipThreads - 2) / (kCipThreads - 1), (nupd + kCipRows - 1) / kCipRows), kCipThreads, 0, stream>>>(a);
     else cip2d_y_kernel<<<dim3((a.nx + kCipThreads - 2) / (kCipThreads - 1), (nupd + kCipRows - 1) / kCipRows), kCipThreads, 0, stream>>>(a);
     return cudaGetLastError();
   }
