@@ -227,6 +227,14 @@ SB2_API int sb2_step(sb2_sim* sim, double t_arg, double t_incr, double dt, int n
  * that exchange the whole state with the host every step.  Only for models on the fused schedule (no advection,
  * membrane transport, Dirichlet or non-zero flux conditions): SB2_ERR_STATE otherwise, and the caller falls back. */
 SB2_API int sb2_step_host(sb2_sim* sim, double t_arg, double dt, int time_slot, const double* const* in, double* const* out, int nslabs);
+/* The same in two halves, which is how a SLAB of a sharded grid (holding four halo rows on either side; host arrays cover the rows
+ * the handle holds) steps from host memory: _begin queues the uploads, the rows of the two edge sub-slabs first, and - when it
+ * returns 1 - hands out ONE exchange of the four edge rows of u with the neighbouring slabs (sb2_exchange below; queue it on
+ * x->stream); _finish recomputes the apron rows that reach into the halo, so no exchange per stage is needed, runs the stages
+ * and the downloads and waits for them.  Upload, compute and download of every rank overlap as on a single GPU. */
+struct sb2_exchange_s;
+SB2_API int sb2_step_host_begin(sb2_sim* sim, double t_arg, double dt, int time_slot, const double* const* in, int nslabs, struct sb2_exchange_s* x);
+SB2_API int sb2_step_host_finish(sb2_sim* sim, double* const* out);
 
 SB2_API int sb2_download_species(sb2_sim* sim, int species, double* out);      /* compact nx*ny*nz */
 SB2_API int sb2_upload_species(sb2_sim* sim, int species, const double* in);
@@ -274,7 +282,7 @@ SB2_API int sb2_end_step(sb2_sim* sim);
  * condition rewrites it), the new u after the last one; for models with advection u and the face values after every
  * CIP-CSLR pass (two rows); the new u after the update when it is not fused into the last stage. */
 #define SB2_MAX_XBUF 40
-typedef struct {
+typedef struct sb2_exchange_s {
   int32_t n;                 /* buffers */
   void* ptr[SB2_MAX_XBUF];   /* device arrays of doubles */
   int32_t width;             /* rows (2-D) / planes (3-D) per side */
@@ -290,6 +298,11 @@ SB2_API int sb2_sharded_next(sb2_sim* sim, sb2_exchange* x);
 /* One step of n slabs held by ONE process (handles on the same or on different devices; sims[i] lies below sims[i+1]): the
  * loop above with peer copies between the handles.  A C++ caller of SpatialSimulator gets its multi-GPU step from this. */
 SB2_API int sb2_group_step(sb2_sim* const* sims, int n, double t_arg, double dt, int time_slot);
+/* sb2_step_host for the slabs of such a group: in[i] / out[i] are slab i's arrays of per-species host pointers, each to the
+ * first row slab i HOLDS.  One peer copy of four edge rows of u per neighbour and step; every slab's upload / stages / download
+ * pipeline then runs beside the others'.  SB2_ERR_STATE (nothing computed) when the model needs the unfused schedule. */
+SB2_API int sb2_group_step_host(sb2_sim* const* sims, int n, double t_arg, double dt, int time_slot, const double* const* const* in,
+                                double* const* const* out, int nslabs);
 
 /* After sb2_begin_step: 1 when the RK combine of this step is fused into stage 3 (the new u is
  * written to view 5 by sb2_stage(3, ...)), 0 when sb2_end_step computes it in place. */

@@ -38,6 +38,7 @@ SSB_API void ssb_set_slab(ssb_sim* s, int lo, int hi);            /* before init
  * library's sharded step with peer copies of the halo rows; results are bit-identical to one device */
 SSB_API void ssb_set_devices(ssb_sim* s, const int* ordinals, int n);
 SSB_API int ssb_get_num_slabs(ssb_sim* s);
+SSB_API void ssb_get_slab_rows(ssb_sim* s, int* held_lo, int* own_lo, int* own_hi);  /* rows of the whole grid; zeros when not a slab */
 SSB_API void ssb_set_cuda_stream(ssb_sim* s, void* cuda_stream);
 
 SSB_API int ssb_init_from_file(ssb_sim* s, const char* file, int xdim, int ydim, int zdim);   /* :66 */

@@ -87,6 +87,9 @@ def _proto(lib):
         "sb2_finalize": (ci, [vp]),
         "sb2_step": (ci, [vp, cd, cd, cd, ci, ci]),
         "sb2_step_host": (ci, [vp, cd, cd, ci, C.POINTER(dp), C.POINTER(dp), ci]),
+        "sb2_step_host_begin": (ci, [vp, cd, cd, ci, C.POINTER(dp), ci, vp]),
+        "sb2_step_host_finish": (ci, [vp, C.POINTER(dp)]),
+        "sb2_group_step_host": (ci, [C.POINTER(vp), ci, cd, cd, ci, C.POINTER(C.POINTER(dp)), C.POINTER(C.POINTER(dp)), ci]),
         "sb2_download_species": (ci, [vp, ci, dp]),
         "sb2_upload_species": (ci, [vp, ci, dp]),
         "sb2_download_stage": (ci, [vp, ci, ci, dp]),
@@ -121,6 +124,7 @@ def _proto(lib):
         "ssb_set_slab": (None, [vp, ci, ci]),
         "ssb_set_devices": (None, [vp, C.POINTER(ci), ci]),
         "ssb_get_num_slabs": (ci, [vp]),
+        "ssb_get_slab_rows": (None, [vp, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci)]),
         "ssb_set_cuda_stream": (None, [vp, vp]),
         "ssb_init_from_file": (ci, [vp, cs, ci, ci, ci]),
         "ssb_init_from_string": (ci, [vp, cs, ci, ci, ci]),
@@ -380,6 +384,12 @@ class SpatialSimulator(object):
 
     def getNumStagedSpecies(self):
         return self._lib.ssb_get_num_staged_species(self._h)
+
+    def getSlabRows(self):
+        """(first row held, first owned row, one past the last owned row) in rows of the whole grid; zeros unless a slab"""
+        a, b, c = C.c_int(0), C.c_int(0), C.c_int(0)
+        self._lib.ssb_get_slab_rows(self._h, C.byref(a), C.byref(b), C.byref(c))
+        return a.value, b.value, c.value
 
     def getNumSlabs(self):
         return self._lib.ssb_get_num_slabs(self._h)

@@ -66,6 +66,9 @@ struct sb2_sim {
   cudaStream_t sh_edge, sh_comm;
   cudaEvent_t ev_edge, ev_interior, ev_comm, ev_ready, ev_pulled;
   int sh_phase, sh_passes;
+  int host_nslabs;       // sb2_step_host_begin / _finish: sub-slabs of the step in flight
+  bool host_exchange;    // ... and whether the caller was handed an exchange of the edge rows
+  bool halo_stale;       // slab: the halo rows of u were not refreshed after the last step (sb2_step_host_finish)
   bool sh_awaiting, sh_comm_valid, sh_first_stage;
   bool finalized, any_adv;
   bool fuse_combine;    // this step: RK combine fused into stage 4
@@ -676,6 +679,7 @@ int sb2_create(const sb2_grid* grid, sb2_sim** out) {
   sim->edge_w = 1; sim->end_w = 1;
   sim->sh_edge = NULL; sim->sh_comm = NULL;
   sim->ev_edge = sim->ev_interior = sim->ev_comm = sim->ev_ready = sim->ev_pulled = NULL;
+  sim->host_nslabs = 0; sim->host_exchange = false; sim->halo_stale = false;
   sim->sh_phase = -1; sim->sh_passes = 0; sim->sh_awaiting = false; sim->sh_comm_valid = false; sim->sh_first_stage = true;
   *out = sim;
   return SB2_OK;
@@ -1525,6 +1529,17 @@ int sb2_sharded_next(sb2_sim* sim, sb2_exchange* x) {
     sim->sh_awaiting = false;
   }
   int rc;
+  if (sim->halo_stale && sim->sh_phase == 0) {
+    // the last step came through sb2_step_host_finish, which leaves the halo rows of the new u unexchanged: refresh them first
+    std::vector<double*> bufs;
+    for (size_t s = 0; s < S; ++s) bufs.push_back(sim->species[s].u[sim->species[s].cur]);
+    CK(cudaEventRecord(sim->ev_ready, compute));
+    CK(cudaStreamWaitEvent(sim->sh_comm, sim->ev_ready, 0));
+    fill_exchange(sim, x, bufs, sim->edge_w > sim->end_w ? sim->edge_w : sim->end_w);
+    sim->halo_stale = false;
+    sim->sh_awaiting = true;
+    return 1;
+  }
   for (;;) {
     const int ph = sim->sh_phase;
     if (ph == 1000) {  // the exchange that ended the step is in flight: everything later waits for it
@@ -1620,6 +1635,47 @@ int sb2_sharded_next(sb2_sim* sim, sb2_exchange* x) {
   }
 }
 
+namespace {
+// Every slab of a group pulls the rows of one exchange from its neighbours (peer copies on the handles' communication streams,
+// after the neighbour's producer event).  sims[i] owns the rows below sims[i+1]'s.
+int group_pull(sb2_sim* const* sims, const std::vector<sb2_exchange>& xs, int n) {
+  for (int i = 0; i < n; ++i) {
+    sb2_sim* sim = sims[i];
+    const sb2_exchange& x = xs[i];
+    cudaSetDevice(sim->g.device);
+    cudaStream_t st = (cudaStream_t)x.stream;
+    for (int side = 0; side < 2; ++side) {
+      const int j = side == 0 ? i - 1 : i + 1;
+      if (j < 0 || j >= n || !(side == 0 ? x.has_lo : x.has_hi)) continue;
+      const sb2_exchange& y = xs[j];
+      if (y.n != x.n || y.width != x.width || y.unit != x.unit) return fail(sim, SB2_ERR_STATE, "neighbouring slabs disagree on an exchange");
+      CK(cudaStreamWaitEvent(st, (cudaEvent_t)y.ready_event, 0));
+      const size_t bytes = sizeof(double) * (size_t)x.unit * x.width;
+      for (int b = 0; b < x.n; ++b) {
+        // my halo rows below own_lo <- the neighbour's last owned rows; my halo rows from own_hi <- its first owned rows
+        double* dst = (double*)x.ptr[b] + x.base + (int64_t)(side == 0 ? x.own_lo - x.width : x.own_hi) * x.unit;
+        const double* src = (const double*)y.ptr[b] + y.base + (int64_t)(side == 0 ? y.own_hi - y.width : y.own_lo) * y.unit;
+        CK(cudaMemcpyPeerAsync(dst, x.device, src, y.device, bytes, st));
+      }
+    }
+  }
+  // a slab may not overwrite rows a neighbour is still pulling: its communication stream waits for the neighbours' pulls
+  for (int i = 0; i < n; ++i) {
+    sb2_sim* sim = sims[i];
+    cudaSetDevice(sim->g.device);
+    if (!sim->ev_pulled) CK(cudaEventCreateWithFlags(&sim->ev_pulled, cudaEventDisableTiming));
+    CK(cudaEventRecord(sim->ev_pulled, (cudaStream_t)xs[i].stream));
+  }
+  for (int i = 0; i < n; ++i) {
+    sb2_sim* sim = sims[i];
+    cudaSetDevice(sim->g.device);
+    if (i > 0) CK(cudaStreamWaitEvent((cudaStream_t)xs[i].stream, sims[i - 1]->ev_pulled, 0));
+    if (i + 1 < n) CK(cudaStreamWaitEvent((cudaStream_t)xs[i].stream, sims[i + 1]->ev_pulled, 0));
+  }
+  return SB2_OK;
+}
+}  // namespace
+
 // The same step for several slabs held by ONE process (one handle per slab, on the same or on different devices): the rows
 // move with peer copies on the handles' communication streams.  sims[i] owns the rows below sims[i+1]'s.
 int sb2_group_step(sb2_sim* const* sims, int n, double t_arg, double dt, int time_slot) {
@@ -1628,7 +1684,6 @@ int sb2_group_step(sb2_sim* const* sims, int n, double t_arg, double dt, int tim
   for (int i = 0; i < n; ++i)
     if ((rc = sb2_sharded_begin(sims[i], t_arg, dt, time_slot))) return rc;
   std::vector<sb2_exchange> xs(n);
-  std::vector<cudaEvent_t> pulled(n, (cudaEvent_t)NULL);
   for (;;) {
     int more = 0, done = 0;
     for (int i = 0; i < n; ++i) {
@@ -1638,40 +1693,7 @@ int sb2_group_step(sb2_sim* const* sims, int n, double t_arg, double dt, int tim
     }
     if (more && done) return fail(sims[0], SB2_ERR_STATE, "sb2_group_step: the slabs disagree on the schedule of the step");
     if (!more) return SB2_OK;
-    // every slab pulls the rows it needs from its neighbours, after the neighbour's producer event
-    for (int i = 0; i < n; ++i) {
-      sb2_sim* sim = sims[i];
-      const sb2_exchange& x = xs[i];
-      cudaSetDevice(sim->g.device);
-      cudaStream_t st = (cudaStream_t)x.stream;
-      for (int side = 0; side < 2; ++side) {
-        const int j = side == 0 ? i - 1 : i + 1;
-        if (j < 0 || j >= n || !(side == 0 ? x.has_lo : x.has_hi)) continue;
-        const sb2_exchange& y = xs[j];
-        if (y.n != x.n || y.width != x.width || y.unit != x.unit) return fail(sim, SB2_ERR_STATE, "sb2_group_step: neighbouring slabs disagree on an exchange");
-        CK(cudaStreamWaitEvent(st, (cudaEvent_t)y.ready_event, 0));
-        const size_t bytes = sizeof(double) * (size_t)x.unit * x.width;
-        for (int b = 0; b < x.n; ++b) {
-          // my halo rows below own_lo <- the neighbour's last owned rows; my halo rows from own_hi <- its first owned rows
-          double* dst = (double*)x.ptr[b] + x.base + (int64_t)(side == 0 ? x.own_lo - x.width : x.own_hi) * x.unit;
-          const double* src = (const double*)y.ptr[b] + y.base + (int64_t)(side == 0 ? y.own_hi - y.width : y.own_lo) * y.unit;
-          CK(cudaMemcpyPeerAsync(dst, x.device, src, y.device, bytes, st));
-        }
-      }
-    }
-    // a slab may not overwrite rows a neighbour is still pulling: its communication stream waits for the neighbours' pulls
-    for (int i = 0; i < n; ++i) {
-      sb2_sim* sim = sims[i];
-      cudaSetDevice(sim->g.device);
-      if (!sim->ev_pulled) CK(cudaEventCreateWithFlags(&sim->ev_pulled, cudaEventDisableTiming));
-      CK(cudaEventRecord(sim->ev_pulled, (cudaStream_t)xs[i].stream));
-    }
-    for (int i = 0; i < n; ++i) {
-      sb2_sim* sim = sims[i];
-      cudaSetDevice(sim->g.device);
-      if (i > 0) CK(cudaStreamWaitEvent((cudaStream_t)xs[i].stream, sims[i - 1]->ev_pulled, 0));
-      if (i + 1 < n) CK(cudaStreamWaitEvent((cudaStream_t)xs[i].stream, sims[i + 1]->ev_pulled, 0));
-    }
+    if ((rc = group_pull(sims, xs, n))) return rc;
   }
 }
 
@@ -1754,24 +1776,34 @@ int sb2_step(sb2_sim* sim, double t_arg, double t_incr, double dt, int nsteps, i
   return SB2_OK;
 }
 
-// One step with HOST inputs and outputs, pipelined over slabs of the slowest axis: while slab j is computed (all four
+// One step with HOST inputs and outputs, pipelined over sub-slabs of the slowest axis: while sub-slab j is computed (all four
 // stages, on a row range that shrinks by one row per stage so that every stage finds its neighbours' values computed:
-// rows [r0-3+m, r1+3-m) in stage m), slab j+1 is uploaded and slab j-1 is downloaded, each on its own stream.  The
-// redundant apron rows cost 12 row-stages per slab.  The result is the same step, bit for bit.
-int sb2_step_host(sb2_sim* sim, double t_arg, double dt, int time_slot, const double* const* in, double* const* out, int nslabs) {
+// rows [r0-3+m, r1+3-m) in stage m), sub-slab j+1 is uploaded and sub-slab j-1 is downloaded, each on its own stream.  The
+// redundant apron rows cost 12 row-stages per sub-slab.  The result is the same step, bit for bit.
+//
+// A handle that is itself a slab of a sharded grid (and holds four halo rows on either side) steps the same way: the rows of
+// its two edge sub-slabs are uploaded first, the four edge rows of u travel to the neighbouring slabs ONCE (the exchange
+// sb2_step_host_begin hands out), and the apron rows that reach into the halo are recomputed from them - no exchange per
+// stage, so upload, compute and download of a rank overlap exactly as on a single GPU.
+int sb2_step_host_begin(sb2_sim* sim, double t_arg, double dt, int time_slot, const double* const* in, int nslabs, sb2_exchange* x) {
   if (!sim || !sim->finalized) return fail(sim, SB2_ERR_STATE, "simulator not finalized");
-  if (!in || !out) return fail(sim, SB2_ERR_ARG, "null argument");
+  if (!in) return fail(sim, SB2_ERR_ARG, "null argument");
   cudaSetDevice(sim->g.device);
   const int S = (int)sim->species.size();
   const bool d3 = sim->g.dim == 3;
-  const int n = d3 ? sim->g.nz : sim->g.ny;  // rows (2-D) / planes (3-D) of the slab axis
-  if (sim->g.own_hi > sim->g.own_lo) return fail(sim, SB2_ERR_STATE, "sb2_step_host needs a handle that owns its whole grid");
+  const SlabRows r = slab_rows(sim);
+  const bool slab = sim->g.own_hi > sim->g.own_lo;
+  const bool has_lo = r.own_lo > 0, has_hi = r.own_hi < r.n_held;
+  if (slab && ((has_lo && r.own_lo < 4) || (has_hi && r.n_held - r.own_hi < 4)))
+    return fail(sim, SB2_ERR_STATE, "sb2_step_host on a slab needs four halo rows on either side");
   int rc = sb2_begin_step(sim, t_arg, dt, time_slot);
   if (rc) return rc;
-  if (!sim->fuse_combine || !sim->transports.empty() || sim->blists[0].n_dirichlet > 0 || !sim->mem_species.empty() || !sim->cell_rules.empty()) {
+  if (!sim->fuse_combine || !sim->transports.empty() || sim->blists[0].n_dirichlet > 0 || sim->model_dirichlet || !sim->mem_species.empty() ||
+      !sim->cell_rules.empty()) {
     sim->in_step = false;
     return fail(sim, SB2_ERR_STATE, "sb2_step_host: the model needs the unfused schedule (advection, membrane transport, non-zero flux or Dirichlet)");
   }
+  const int n = r.own_hi - r.own_lo;
   if (nslabs < 1) nslabs = 16;
   if (nslabs > n / 8) nslabs = n / 8 > 0 ? n / 8 : 1;
   if (!sim->h2d) {
@@ -1785,21 +1817,16 @@ int sb2_step_host(sb2_sim* sim, double t_arg, double dt, int time_slot, const do
     CK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
     sim->ev_up.push_back(a); sim->ev_done.push_back(b);
   }
+  sim->host_nslabs = nslabs;
   const sb2_grid& g = sim->g;
   const int64_t plane_cells = (int64_t)g.nx * g.ny;
-  auto copy_rows = [&](double* dev, double* host, int r0, int r1, bool up, cudaStream_t st) -> cudaError_t {
-    // rows [r0, r1) of the slab axis between a compact host array and the padded device array
-    if (!d3) {
-      double* d = dev + sim->first + (int64_t)r0 * sim->P;
-      double* h = host + (int64_t)r0 * g.nx;
-      return up ? cudaMemcpy2DAsync(d, sizeof(double) * sim->P, h, sizeof(double) * g.nx, sizeof(double) * g.nx, r1 - r0, cudaMemcpyHostToDevice, st)
-                : cudaMemcpy2DAsync(h, sizeof(double) * g.nx, d, sizeof(double) * sim->P, sizeof(double) * g.nx, r1 - r0, cudaMemcpyDeviceToHost, st);
-    }
+  auto upload_rows = [&](double* dev, const double* host, int r0, int r1) -> cudaError_t {
+    // rows [r0, r1) of the slab axis from a compact host array (the rows this handle holds) into the padded device array
+    if (!d3) return cudaMemcpy2DAsync(dev + sim->first + (int64_t)r0 * sim->P, sizeof(double) * sim->P, host + (int64_t)r0 * g.nx,
+                                      sizeof(double) * g.nx, sizeof(double) * g.nx, r1 - r0, cudaMemcpyHostToDevice, sim->h2d);
     for (int z = r0; z < r1; ++z) {
-      double* d = dev + sim->first + (int64_t)z * sim->PL;
-      double* h = host + (int64_t)z * plane_cells;
-      cudaError_t e = up ? cudaMemcpy2DAsync(d, sizeof(double) * sim->P, h, sizeof(double) * g.nx, sizeof(double) * g.nx, g.ny, cudaMemcpyHostToDevice, st)
-                         : cudaMemcpy2DAsync(h, sizeof(double) * g.nx, d, sizeof(double) * sim->P, sizeof(double) * g.nx, g.ny, cudaMemcpyDeviceToHost, st);
+      cudaError_t e = cudaMemcpy2DAsync(dev + sim->first + (int64_t)z * sim->PL, sizeof(double) * sim->P, host + (int64_t)z * plane_cells,
+                                        sizeof(double) * g.nx, sizeof(double) * g.nx, g.ny, cudaMemcpyHostToDevice, sim->h2d);
       if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
@@ -1808,32 +1835,132 @@ int sb2_step_host(sb2_sim* sim, double t_arg, double dt, int time_slot, const do
   CK(cudaEventRecord(sim->ev_start, sim->stream));
   CK(cudaStreamWaitEvent(sim->h2d, sim->ev_start, 0));
   CK(cudaStreamWaitEvent(sim->d2h, sim->ev_start, 0));
-  auto lo_of = [&](int j) { return (int)((int64_t)j * n / nslabs); };
-  for (int j = 0; j < nslabs; ++j) {  // all uploads are queued up front, in slab order
+  auto lo_of = [&](int j) { return r.own_lo + (int)((int64_t)j * n / nslabs); };
+  // uploads are queued up front; on a slab the two edge sub-slabs go first (their edge rows travel to the neighbours)
+  std::vector<int> order;
+  if (slab) { order.push_back(0); if (nslabs > 1) order.push_back(nslabs - 1); for (int j = 1; j + 1 < nslabs; ++j) order.push_back(j); }
+  else for (int j = 0; j < nslabs; ++j) order.push_back(j);
+  for (size_t q = 0; q < order.size(); ++q) {
+    const int j = order[q];
     for (int s = 0; s < S; ++s)
-      if (in[s]) CK(copy_rows(sim->species[s].u[sim->species[s].cur], const_cast<double*>(in[s]), lo_of(j), lo_of(j + 1), true, sim->h2d));
+      if (in[s]) CK(upload_rows(sim->species[s].u[sim->species[s].cur], in[s], lo_of(j), lo_of(j + 1)));
     CK(cudaEventRecord(sim->ev_up[j], sim->h2d));
   }
+  sim->host_exchange = false;
+  if (slab && (has_lo || has_hi) && !x) {
+    sim->in_step = false;
+    return fail(sim, SB2_ERR_ARG, "sb2_step_host_begin on a slab with neighbours needs an exchange to fill");
+  }
+  if (slab && (has_lo || has_hi)) {
+    if ((rc = ensure_shard_streams(sim))) return rc;
+    CK(cudaStreamWaitEvent(sim->sh_comm, sim->ev_up[0], 0));
+    CK(cudaStreamWaitEvent(sim->sh_comm, sim->ev_up[nslabs - 1], 0));
+    CK(cudaEventRecord(sim->ev_ready, sim->sh_comm));
+    std::vector<double*> bufs;
+    for (int s = 0; s < S; ++s) bufs.push_back(sim->species[s].u[sim->species[s].cur]);
+    fill_exchange(sim, x, bufs, 4);
+    sim->host_exchange = true;
+    return 1;
+  }
+  return 0;
+}
+
+namespace {
+// second half of a host step: everything is queued, nothing waited for
+int step_host_queue(sb2_sim* sim, double* const* out) {
+  if (!sim || !sim->in_step) return fail(sim, SB2_ERR_STATE, "sb2_step_host_finish without sb2_step_host_begin");
+  if (!out) return fail(sim, SB2_ERR_ARG, "null argument");
+  cudaSetDevice(sim->g.device);
+  const int S = (int)sim->species.size();
+  const bool d3 = sim->g.dim == 3;
+  const SlabRows r = slab_rows(sim);
+  const int n = r.own_hi - r.own_lo, nslabs = sim->host_nslabs;
+  const double dt = sim->cur_dt;
+  const sb2_grid& g = sim->g;
+  const int64_t plane_cells = (int64_t)g.nx * g.ny;
+  auto download_rows = [&](const double* dev, double* host, int r0, int r1) -> cudaError_t {
+    if (!d3) return cudaMemcpy2DAsync(host + (int64_t)r0 * g.nx, sizeof(double) * g.nx, dev + sim->first + (int64_t)r0 * sim->P,
+                                      sizeof(double) * sim->P, sizeof(double) * g.nx, r1 - r0, cudaMemcpyDeviceToHost, sim->d2h);
+    for (int z = r0; z < r1; ++z) {
+      cudaError_t e = cudaMemcpy2DAsync(host + (int64_t)z * plane_cells, sizeof(double) * g.nx, dev + sim->first + (int64_t)z * sim->PL,
+                                        sizeof(double) * sim->P, sizeof(double) * g.nx, g.ny, cudaMemcpyDeviceToHost, sim->d2h);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  };
+  if (sim->host_exchange) {
+    // the caller queued the exchange of the edge rows on the communication stream: everything computed waits for it
+    CK(cudaEventRecord(sim->ev_comm, sim->sh_comm));
+    CK(cudaStreamWaitEvent(sim->stream, sim->ev_comm, 0));
+  }
+  auto lo_of = [&](int j) { return r.own_lo + (int)((int64_t)j * n / nslabs); };
+  int rc;
   for (int j = 0; j < nslabs; ++j) {
     const int r0 = lo_of(j), r1 = lo_of(j + 1);
-    CK(cudaStreamWaitEvent(sim->stream, sim->ev_up[j + 1 < nslabs ? j + 1 : j], 0));  // the apron rows lie in the next slab
+    CK(cudaStreamWaitEvent(sim->stream, sim->ev_up[j], 0));
+    CK(cudaStreamWaitEvent(sim->stream, sim->ev_up[j + 1 < nslabs ? j + 1 : j], 0));  // the apron rows lie in the next sub-slab
     for (int m = 0; m < 4; ++m) {
       int b = r0 - (3 - m), e = r1 + (3 - m);
       if (b < 0) b = 0;
-      if (e > n) e = n;
+      if (e > r.n_held) e = r.n_held;
       if ((rc = launch_stage_rows(sim, m, dt, b, e))) return rc;
     }
     CK(cudaEventRecord(sim->ev_done[j], sim->stream));
     CK(cudaStreamWaitEvent(sim->d2h, sim->ev_done[j], 0));
     for (int s = 0; s < S; ++s)
-      if (out[s]) CK(copy_rows(sim->species[s].u[sim->species[s].cur ^ 1], out[s], r0, r1, false, sim->d2h));
+      if (out[s]) CK(download_rows(sim->species[s].u[sim->species[s].cur ^ 1], out[s], r0, r1));
   }
   for (int s = 0; s < S; ++s) sim->species[s].cur ^= 1;
   sim->k0_carry_valid = false;
   sim->in_step = false;
+  // a slab's halo rows of the new u are not valid (they were never exchanged): a later sharded step must not rely on them
+  sim->sh_comm_valid = false;
+  sim->halo_stale = sim->g.own_hi > sim->g.own_lo;
+  return SB2_OK;
+}
+int step_host_wait(sb2_sim* sim) {
+  cudaSetDevice(sim->g.device);
   CK(cudaStreamSynchronize(sim->d2h));
   CK(cudaStreamSynchronize(sim->stream));
   return SB2_OK;
+}
+}  // namespace
+
+int sb2_step_host_finish(sb2_sim* sim, double* const* out) {
+  int rc = step_host_queue(sim, out);
+  if (rc) return rc;
+  return step_host_wait(sim);
+}
+
+// The same for the slabs of a group held by one process: in[i] / out[i] are slab i's arrays of per-species host pointers (each
+// to the first row that slab HOLDS); the edge rows move with peer copies, then every slab's pipeline runs beside the others'.
+int sb2_group_step_host(sb2_sim* const* sims, int n, double t_arg, double dt, int time_slot, const double* const* const* in,
+                        double* const* const* out, int nslabs) {
+  if (!sims || n < 1 || !in || !out) return SB2_ERR_ARG;
+  std::vector<sb2_exchange> xs(n);
+  int rc, handed = 0;
+  for (int i = 0; i < n; ++i) {
+    rc = sb2_step_host_begin(sims[i], t_arg, dt, time_slot, in[i], nslabs, &xs[i]);
+    if (rc < 0) {
+      // nothing of the step has been computed: the slabs that had begun leave it again (their uploads are harmless)
+      for (int j = 0; j < i; ++j) sims[j]->in_step = false;
+      return rc;
+    }
+    handed += rc;
+  }
+  if (handed != (n > 1 ? n : 0)) return fail(sims[0], SB2_ERR_STATE, "sb2_group_step_host: the slabs disagree on the exchange");
+  if (n > 1 && (rc = group_pull(sims, xs, n))) return rc;
+  for (int i = 0; i < n; ++i) if ((rc = step_host_queue(sims[i], out[i]))) return rc;
+  for (int i = 0; i < n; ++i) if ((rc = step_host_wait(sims[i]))) return rc;
+  return SB2_OK;
+}
+
+int sb2_step_host(sb2_sim* sim, double t_arg, double dt, int time_slot, const double* const* in, double* const* out, int nslabs) {
+  if (!sim || !in || !out) return fail(sim, SB2_ERR_ARG, "null argument");
+  if (sim->g.own_hi > sim->g.own_lo) return fail(sim, SB2_ERR_STATE, "sb2_step_host needs a handle that owns its whole grid (a slab steps with sb2_step_host_begin / _finish)");
+  int rc = sb2_step_host_begin(sim, t_arg, dt, time_slot, in, nslabs, NULL);
+  if (rc < 0) return rc;
+  return sb2_step_host_finish(sim, out);
 }
 
 int sb2_download_species(sb2_sim* sim, int species, double* out) {
@@ -1847,6 +1974,7 @@ int sb2_upload_species(sb2_sim* sim, int species, const double* in) {
   cudaSetDevice(sim->g.device);
   int rc = upload_interior<double>(sim, sim->species[species].u[sim->species[species].cur], in);
   if (rc) return rc;
+  sim->halo_stale = false;  // (the caller uploads every held row, halo rows included)
   CK(cudaStreamSynchronize(sim->stream));
   return SB2_OK;
 }

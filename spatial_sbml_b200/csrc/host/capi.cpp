@@ -37,6 +37,13 @@ void ssb_set_host_only(ssb_sim* s, int h) { if (s) s->sim.setHostOnly(h != 0); }
 void ssb_set_slab(ssb_sim* s, int lo, int hi) { if (s) s->sim.setSlab(lo, hi); }
 void ssb_set_devices(ssb_sim* s, const int* ordinals, int n) { if (s) s->sim.setDevices(ordinals, n); }
 int ssb_get_num_slabs(ssb_sim* s) { return s ? s->sim.getNumSlabs() : 0; }
+void ssb_get_slab_rows(ssb_sim* s, int* held_lo, int* own_lo, int* own_hi) {
+  int a = 0, b = 0, c = 0;
+  if (s) s->sim.getSlabRows(a, b, c);
+  if (held_lo) *held_lo = a;
+  if (own_lo) *own_lo = b;
+  if (own_hi) *own_hi = c;
+}
 void ssb_set_cuda_stream(ssb_sim* s, void* st) { if (s) s->sim.setCudaStream(st); }
 
 int ssb_init_from_file(ssb_sim* s, const char* file, int x, int y, int z) {

@@ -51,7 +51,7 @@ Var::Var()
 Model::Model()
     : doc(NULL), model(NULL), nx(1), ny(1), nz(1), Xindex(1), Yindex(1), Zindex(1), dimension(0), volDimension(0),
       memDimension(0), deltaX(0), deltaY(0), deltaZ(0), Xsize(0), Ysize(0), Zsize(0), simTime(0), xVar(NULL),
-      yVar(NULL), zVar(NULL), tVar(NULL) {}
+      yVar(NULL), zVar(NULL), tVar(NULL), slab(false) {}
 
 Model::~Model() {
   for (size_t i = 0; i < vars.size(); ++i) delete vars[i];
@@ -1317,7 +1317,8 @@ bool Model::build(SBMLDocument* d, int xdim, int ydim, int zdim, int slabLo, int
   gn[0] = nx; gn[1] = ny; gn[2] = nz;
   off[0] = off[1] = off[2] = 0;
   Xindex = 2 * nx - 1; Yindex = 2 * ny - 1; Zindex = 2 * nz - 1;  // doubled grid of the WHOLE grid
-  if (slabHi > slabLo) {
+  slab = slabHi > slabLo;
+  if (slab) {
     const int axis = dimension == 3 ? 2 : 1;
     if (dimension < 2 || slabLo < 0 || slabHi > gn[axis]) { error = "slab range outside the grid"; return false; }
     off[axis] = slabLo;

@@ -150,7 +150,8 @@ struct Model {
   // slabLo/slabHi: rows (2-D: y, 3-D: z) [slabLo, slabHi) of the whole grid are held locally
   // (owned rows plus halo); slabLo == slabHi == 0 means the whole grid.
   bool build(SBMLDocument* d, int xdim, int ydim, int zdim, int slabLo = 0, int slabHi = 0);
-  bool isSlab() const { return nx != gn[0] || ny != gn[1] || nz != gn[2]; }
+  bool slab;  // built for a slab of a sharded grid (the rows held may still be the whole grid when the slabs are thin)
+  bool isSlab() const { return slab; }
   // value of a coordinate variable at doubled-grid coordinate C of its axis (setInfoFunction.cpp:308): min + C*delta/2.0
   double coordinateAt(const Var* v, int C) const {
     const double delta = v == xVar ? deltaX : v == yVar ? deltaY : deltaZ;

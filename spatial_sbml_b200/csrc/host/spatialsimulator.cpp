@@ -25,7 +25,9 @@ using sb2host::Var;
 
 namespace {
 
-const int kSlabHalo = 2;  // rows / planes of neighbouring slabs whose masks are known locally
+// rows / planes of the neighbouring slabs held locally: two are exchanged by models with advection / membrane transport, four
+// let a slab step from host memory with a single exchange of edge rows (sb2_step_host_begin)
+const int kSlabHalo = 4;
 
 struct VarMirror {
   std::vector<double> data;  // doubled grid
@@ -269,6 +271,9 @@ void SpatialSimulator::setDevices(const int* ordinals, int n) {
   if (n == 1) deviceOrdinal = ordinals[0];
 }
 int SpatialSimulator::getNumSlabs() const { return impl ? (int)impl->slabs.size() : 0; }
+void SpatialSimulator::getSlabRows(int& heldLo, int& ownLo, int& ownHi) const {
+  heldLo = impl ? impl->heldLo : 0; ownLo = impl ? impl->ownLo : 0; ownHi = impl ? impl->ownHi : 0;
+}
 const std::string& SpatialSimulator::getLastError() const { return lastError; }
 void SpatialSimulator::setDevice(int ordinal) { deviceOrdinal = ordinal; }
 void SpatialSimulator::setHostOnly(bool h) { hostOnly = h; }
@@ -926,11 +931,52 @@ double SpatialSimulator::oneStep(double initialTime, double step) {
 double SpatialSimulator::oneStepHost(double initialTime, double step, int n, const char* const* ids, const double* const* in,
                                      double* const* out, int nslabs) {
   if (impl && !impl->slabs.empty()) {
-    for (int i = 0; i < n; ++i)
-      if (in && in[i] && !setVariableCompact(ids[i], in[i], (size_t)impl->m.ncells())) throw std::runtime_error(std::string("oneStepHost: cannot set ") + ids[i]);
-    oneStep(initialTime, step);
-    for (int i = 0; i < n; ++i)
-      if (out && out[i] && !getVariableCompact(ids[i], out[i], (size_t)impl->m.ncells())) throw std::runtime_error(std::string("oneStepHost: cannot read ") + ids[i]);
+    // group: every slab pipelines its own rows (sb2_group_step_host); models on the unfused schedule take the plain sequence
+    const size_t G = impl->slabs.size();
+    const int64_t rowCells = impl->m.dimension == 3 ? (int64_t)impl->m.nx * impl->m.ny : (int64_t)impl->m.nx;
+    const size_t S = (size_t)impl->slabs[0]->getNumStagedSpecies();
+    std::vector<std::vector<const double*> > din(G, std::vector<const double*>(S, (const double*)NULL));
+    std::vector<std::vector<double*> > dout(G, std::vector<double*>(S, (double*)NULL));
+    bool staged_only = in != NULL && out != NULL;
+    for (int i = 0; i < n && staged_only; ++i) {
+      const Var* v = impl->slabs[0]->impl->m.findVar(ids[i]);
+      if (!v || v->speciesId < 0) { staged_only = false; break; }
+      for (size_t g = 0; g < G; ++g) {
+        const int64_t off = (int64_t)impl->slabs[g]->impl->heldLo * rowCells;
+        din[g][v->speciesId] = in[i] ? in[i] + off : NULL;
+        dout[g][v->speciesId] = out[i] ? out[i] + off : NULL;
+      }
+    }
+    int rc = SB2_ERR_STATE;
+    if (staged_only) {
+      std::vector<sb2_sim*> handles;
+      std::vector<const double* const*> pin;
+      std::vector<double* const*> pout;
+      for (size_t g = 0; g < G; ++g) {
+        impl->slabs[g]->syncBeforeStep();
+        impl->slabs[g]->impl->m.simTime = initialTime * step;
+        impl->slabs[g]->impl->m.tVar->uniformValue = initialTime * step;
+        handles.push_back(impl->slabs[g]->impl->dev);
+        pin.push_back(din[g].data());
+        pout.push_back(dout[g].data());
+      }
+      rc = sb2_group_step_host(handles.data(), (int)G, initialTime, step, impl->slabs[0]->impl->timeSlot, pin.data(), pout.data(), nslabs);
+      if (rc < 0 && rc != SB2_ERR_STATE) {
+        lastError = std::string("sb2_group_step_host: ") + sb2_last_error(handles[0]);
+        throw std::runtime_error(lastError);
+      }
+    }
+    if (rc == SB2_ERR_STATE) {
+      for (int i = 0; i < n; ++i)
+        if (in && in[i] && !setVariableCompact(ids[i], in[i], (size_t)impl->m.ncells())) throw std::runtime_error(std::string("oneStepHost: cannot set ") + ids[i]);
+      oneStep(initialTime, step);
+      for (int i = 0; i < n; ++i)
+        if (out && out[i] && !getVariableCompact(ids[i], out[i], (size_t)impl->m.ncells())) throw std::runtime_error(std::string("oneStepHost: cannot read ") + ids[i]);
+      return initialTime + step;
+    }
+    impl->m.simTime = initialTime * step;
+    impl->groupFresh.clear();
+    for (size_t g = 0; g < G; ++g) impl->slabs[g]->deviceStateChanged();
     return initialTime + step;
   }
   if (!impl || !impl->dev)

@@ -107,6 +107,8 @@ class __attribute__((visibility("default"))) SpatialSimulator {
   // getVariableAt / setParameter work on the whole grid as before.
   void setDevices(const int* ordinals, int n);
   int getNumSlabs() const;
+  // slab (setSlab): first row held locally and the owned rows [ownLo, ownHi), all in rows of the whole grid; zeros otherwise
+  void getSlabRows(int& heldLo, int& ownLo, int& ownHi) const;
   // Slab of a larger grid (multi-GPU): this simulator owns rows [lo, hi) of the slab
   // axis (y in 2-D, z in 3-D) of the model's grid.  Call before init; lo = hi = 0 means everything.
   void setSlab(int lo, int hi);

@@ -81,8 +81,8 @@ class ShardedSimulator(object):
         self.S = self.sim.getNumStagedSpecies()
         nz, ny, nx = self.sim.localShape()
         self.held = nz if dim == 3 else ny
-        # halo rows held below the owned range (2 unless the slab touches the grid edge)
-        self.held_lo = max(0, self.lo - 2) if self.world > 1 else 0
+        # first row held: the owned range plus the halo rows of the neighbouring slab below it
+        self.held_lo = self.sim.getSlabRows()[0] if self.world > 1 else 0
         self.own_lo = self.lo - self.held_lo
         self.own_hi = self.hi - self.held_lo
         self.time_slot = self.sim.getTimeSlot()  # sim_time = stepIndex * dt reaches the kinetic laws through this constant
@@ -140,6 +140,25 @@ class ShardedSimulator(object):
             self._exchange(x)
         self.sim.deviceStateChanged()  # the host mirrors of the species are stale now
 
+    def step_host(self, step_index, dt, names, inputs, outputs, nslabs=0):
+        """One step whose species values come from / go to HOST arrays (one per name, shaped like sim.localShape(), ideally pinned):
+        upload, compute and download of this rank's slab are pipelined over sub-slabs; the edge rows of u travel to the neighbouring
+        ranks once per step and the apron rows are recomputed (sb2_step_host_begin / _finish)."""
+        if self.world == 1:
+            self.sim.oneStepHost(step_index, dt, dict(zip(names, inputs)), dict(zip(names, outputs)), nslabs)
+            return
+        dp = C.POINTER(C.c_double)
+        n = len(names)
+        # species ids on the device follow the model's species order; names are given in that order by the caller
+        cin = (dp * self.S)(*[inputs[i].ctypes.data_as(dp) if i < n else dp() for i in range(self.S)])
+        cout = (dp * self.S)(*[outputs[i].ctypes.data_as(dp) if i < n else dp() for i in range(self.S)])
+        x = self._x
+        rc = self._ck(self.lib.sb2_step_host_begin(self.h, float(step_index), float(dt), self.time_slot, cin, int(nslabs), C.byref(x)))
+        if rc == 1:
+            self._exchange(x)
+        self._ck(self.lib.sb2_step_host_finish(self.h, cout))
+        self.sim.deviceStateChanged()
+
     def run_steps(self, first_step_index, dt, nsteps):
         if self.world == 1:
             self.sim.runSteps(first_step_index, dt, nsteps)
@@ -162,6 +181,12 @@ class ShardedSimulator(object):
         if self.world == 1:
             return a
         return a[self.own_lo:self.own_hi] if self.dim == 3 else a[:, self.own_lo:self.own_hi]
+
+    def owned_of(self, local_array):
+        """The owned rows of an array shaped like sim.localShape()"""
+        if self.world == 1:
+            return local_array
+        return local_array[self.own_lo:self.own_hi] if self.dim == 3 else local_array[:, self.own_lo:self.own_hi]
 
     def num_domain_cells(self):
         return self.sim.getNumDomainCells()

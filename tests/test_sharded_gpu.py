@@ -62,6 +62,13 @@ def test_slabs_on_one_device_turing_3d(nslabs, jit, monkeypatch):
     _run_pair(synthetic.turing(*dims), dims, 0.02, 8, ("species_1", "species_2"), [0] * nslabs, jit, monkeypatch)
 
 
+def test_thin_slabs_whose_halo_rows_cover_the_whole_grid():
+    """Slabs of three rows hold, with their four halo rows either side, the whole grid: they are slabs all the same."""
+    from spatial_sbml_b200 import synthetic
+    dims = (96, 10, 1)
+    _run_pair(synthetic.turing_bc(dims[0], dims[1]), dims, 0.05, 8, ("species_1", "species_2"), [0, 0, 0])
+
+
 @pytest.mark.parametrize("nslabs", [2, 3])
 def test_slabs_with_live_boundary_conditions(nslabs):
     """Non-zero Neumann fluxes (carried in k0 between steps) and a Dirichlet side: the boundary pass is split into edge rows and
@@ -124,7 +131,62 @@ def test_group_accessors():
     b.close()
 
 
-@pytest.mark.parametrize("dim", ["2", "3", "bc", "adv"])
+@pytest.mark.parametrize("nslabs", [2, 3])
+@pytest.mark.parametrize("d3", [False, True])
+@pytest.mark.parametrize("jit", [None, "1"])
+def test_group_host_step_is_the_same_step(nslabs, d3, jit, monkeypatch):
+    """oneStepHost on a grid held by several slabs (sb2_group_step_host: every slab pipelines upload / stages / download over its
+    own rows, ONE exchange of four edge rows of u per step, apron rows recomputed) gives the fields of oneStep on one device, also
+    when plain steps (which must first refresh the halo rows a host step leaves unexchanged) are mixed in."""
+    import spatial_sbml_b200 as sb
+    from spatial_sbml_b200 import synthetic
+    if jit:
+        monkeypatch.setenv("SB2_JIT", jit)
+    dims = (140, 24, 17 * nslabs + 3) if d3 else (300, 41 * nslabs + 5, 1)
+    dt = 0.02 if d3 else 0.07
+    model = synthetic.turing(*dims) if d3 else synthetic.turing(dims[0], dims[1])
+    species = ("species_1", "species_2")
+    one = sb.SpatialSimulator()
+    one.initFromString(model, *dims)
+    many = sb.SpatialSimulator(devices=[0] * nslabs)
+    many.initFromString(model, *dims)
+    cur = {sp: many.getVariableCompact(sp).copy() for sp in species}
+    for t in range(7):
+        one.oneStep(t, dt)
+        if t == 3:
+            many.oneStep(t, dt)
+            cur = {sp: many.getVariableCompact(sp).copy() for sp in species}
+        else:
+            nxt = {sp: np.empty_like(cur[sp]) for sp in species}
+            many.oneStepHost(t, dt, cur, nxt, 2)
+            cur = nxt
+        for sp in species:
+            want = one.getVariableCompact(sp)
+            assert np.array_equal(cur[sp], want), (t, sp, int((cur[sp] != want).sum()))
+    for sp in species:
+        assert np.array_equal(many.getVariableCompact(sp), cur[sp])
+    assert many.getDeviceLaunchCount() > 0
+    one.close()
+    many.close()
+
+
+def test_group_host_step_falls_back_for_unfused_models():
+    import spatial_sbml_b200 as sb
+    g = load_golden("advection")
+    dims = tuple(int(v) for v in g["dims"])
+    species = [str(s) for s in g["species"]]
+    many = sb.SpatialSimulator(devices=[0, 0])
+    many.initFromFile(model_path("advection"), *dims)
+    cur = {sp: many.getVariableCompact(sp).copy() for sp in species}
+    out = {sp: np.empty_like(cur[sp]) for sp in species}
+    many.oneStepHost(0, float(g["dt"]), cur, out)
+    for sp in species:
+        ref = g["step/1/" + sp]
+        assert np.abs(out[sp] - ref).max() <= 1e-10 * np.abs(ref).max(), sp
+    many.close()
+
+
+@pytest.mark.parametrize("dim", ["2", "3", "bc", "adv", "host2", "host3"])
 def test_nccl_sharded_step_is_bit_identical(dim):
     import torch
     n = torch.cuda.device_count()
@@ -132,7 +194,7 @@ def test_nccl_sharded_step_is_bit_identical(dim):
         pytest.skip("the NCCL path needs at least two GPUs (the same slab logic runs on one GPU in the tests above)")
     world = 2
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
-           "--master-port", str(29500 + ["2", "3", "bc", "adv"].index(dim)), os.path.join(REPO, "tools", "sharded_check.py"), dim, "12"]
+           "--master-port", str(29500 + ["2", "3", "bc", "adv", "host2", "host3"].index(dim)), os.path.join(REPO, "tools", "sharded_check.py"), dim, "12"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "BIT-IDENTICAL" in r.stdout
