@@ -513,6 +513,231 @@ __global__ void __launch_bounds__(kCipThreads) cip2d_y_kernel(const __grid_const
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// 2-D, UNIFORM velocity along the pass axis (the common case: an advectionCoefficient that is a plain parameter): the same
+// fused pass with warps that share nothing.  A warp owns a strip of a row block and marches over its rows; a lane holds TWO
+// adjacent cells (16-byte loads and stores); what a cell needs from its neighbours across x comes through warp shuffles
+// (the strips overlap by the one or two lanes that only supply values), what it needs along y is carried in registers along
+// the march; the rows of the NEXT iteration are requested before the current one is computed, so the long fp64 dependency
+// chain of a face (three divisions in sequence) runs under the loads.  No shared memory, no block barrier.  Divisions by
+// +-delta are multiplications by the reciprocal when delta is a power of two (exact, hence bit-identical).
+// The arithmetic is cip_plus_face / cip_dc operand for operand.
+struct CipRow {
+  double2 v, fa, fo;  // cell averages, faces of the pass axis, faces of the other axis
+  uint32_t fl;        // flag bytes of the two cells (byte 0: first cell); zero for cells outside the grid
+};
+
+__device__ __forceinline__ CipRow cip_load_row(const Sb2CipArgs& A, const int axis, const int j, const int xa, const bool in_a, const bool in_b) {
+  CipRow r;
+  r.v = make_double2(0.0, 0.0); r.fa = r.v; r.fo = r.v; r.fl = 0;
+  if (j < 0 || j >= A.ny || !(in_a || in_b)) return r;
+  const int64_t idx = A.first + (int64_t)j * A.P + xa;
+  // (a pair is 16-byte aligned: first and P are multiples of 4, xa is even; its second cell may lie in the row padding)
+  r.v = *reinterpret_cast<const double2*>(A.u + idx);
+  r.fa = *reinterpret_cast<const double2*>(A.faces[axis] + idx);
+  r.fo = *reinterpret_cast<const double2*>(A.faces[axis ^ 1] + idx);
+  const uint32_t f2 = *reinterpret_cast<const uint16_t*>(A.flags + idx);
+  r.fl = (in_a ? (f2 & 0xffu) : 0u) | (in_b ? (f2 & 0xff00u) : 0u);
+  return r;
+}
+
+template <bool P2>
+__device__ __forceinline__ double cip_div_delta(const double x, const double d, const double rd) { return P2 ? x * rd : x / d; }
+
+// F and the face increment of one cell (cip_plus_face with its operands in registers).  f: the cell's flag byte; d_*: whether
+// the neighbours along the axis are cells of the domain; POS: ux >= 0 (uses v0, vp1 = face of the cell, fm1 = face of the
+// minus neighbour), else (v0, vp1, vn = value of the plus neighbour, fn = its face)
+template <int AXIS, bool POS, bool P2>
+__device__ __forceinline__ void cip_face_regs(const uint32_t f, const bool d_p1, const bool d_p2, const bool d_m1, const double v0,
+                                              const double face0, const double fm1, const double vn, const double fn, const double xi,
+                                              const double Dx, const double rDx, double& F, double& nf, bool& has_face) {
+  F = 0.0; nf = 0.0; has_face = false;
+  if (!(f & SB2_F_DOMAIN) || (f & (SB2_F_XP << (2 * AXIS)))) return;
+  const double vp1 = d_p1 ? face0 : v0;
+  double a_i, b_i, beta_i;
+  if (POS) {
+    const double vm1 = d_m1 ? fm1 : v0;
+    a_i = vp1;
+    beta_i = cip_div_delta<P2>((fabs(vp1 - v0) + DBL_EPSILON) / (fabs(v0 - vm1) + DBL_EPSILON) - 1.0, Dx, rDx);
+    b_i = cip_div_delta<P2>((1.0 + beta_i * Dx) * v0 - vp1, Dx, rDx);
+  } else {
+    const double vp3 = d_p2 ? fn : (d_p1 ? vn : v0);
+    const double vp2 = d_p1 ? vn : v0;
+    a_i = vp1;
+    beta_i = cip_div_delta<P2>((fabs(vp1 - vp2) + DBL_EPSILON) / (fabs(vp2 - vp3) + DBL_EPSILON) - 1.0, Dx, rDx);
+    b_i = cip_div_delta<P2>((1.0 + beta_i * Dx) * vp2 - vp1, Dx, rDx);
+  }
+  const double mxi = -xi;
+  const double den = 1.0 + beta_i * mxi;
+  const double n = (a_i + 2 * b_i * mxi + beta_i * b_i * (mxi * mxi)) / (den * den) - vp1;
+  if (d_p1) { has_face = true; nf = n; }
+  F = (-a_i * xi + b_i * (xi * xi)) / (-1.0 + beta_i * xi);
+}
+
+template <int AXIS, bool POS, bool P2>
+__device__ __forceinline__ double cip_dc_regs(const uint32_t f, const double Fp, const double Fm, const double delta, const double rdelta) {
+  if (!(f & SB2_F_DOMAIN)) return 0.0;
+  const bool bofp = f & (SB2_F_XP << (2 * AXIS)), bofm = f & (SB2_F_XM << (2 * AXIS));
+  double g_in = 0.0, g_out = 0.0;
+  if (POS) { if (!bofp) g_out = Fp; if (!bofm) g_in = Fm; }
+  else { if (!bofp) g_in = -Fp; if (!bofm) g_out = -Fm; }
+  return cip_div_delta<P2>(g_in - g_out, delta, rdelta);
+}
+
+__device__ __forceinline__ double shfl_up_d(double x) { return __shfl_up_sync(0xffffffffu, x, 1); }
+__device__ __forceinline__ double shfl_down_d(double x) { return __shfl_down_sync(0xffffffffu, x, 1); }
+
+constexpr int kCipUWarps = 4;
+
+// X pass: lanes 1..30 own their pair, lanes 0 and 31 only supply neighbour values: 60 owned cells per warp and row
+template <bool POS, bool P2>
+__global__ void __launch_bounds__(kCipUWarps * 32) cip2d_ux_kernel(const __grid_constant__ Sb2CipArgs A, const int rows_per_block) {
+  const int lane = threadIdx.x & 31;
+  const int strip = (int)blockIdx.x * kCipUWarps + (threadIdx.x >> 5);
+  const int xa = strip * 60 - 2 + 2 * lane;
+  if (strip * 60 >= A.nx) return;
+  const bool in_a = xa >= 0 && xa < A.nx, in_b = xa + 1 >= 0 && xa + 1 < A.nx;
+  const bool owner = lane >= 1 && lane <= 30 && in_a;
+  const int jb = A.row_begin + (int)blockIdx.y * rows_per_block;
+  const int je = min(jb + rows_per_block, A.row_end);
+  const int jl = je < A.flux_row_end ? je + 1 : je;  // one more row (flux only): the face above the block's last row needs its increment
+  const double ux = A.aconst[0], delta = A.delta[0];
+  const double Dx = -copysign(1.0, ux) * delta, rDx = 1.0 / Dx, rdelta = 1.0 / delta, xi = ux * A.dt;
+  double2 dc_prev = make_double2(0.0, 0.0), fo_prev = dc_prev;
+  uint32_t fl_prev = 0;
+  CipRow cur = cip_load_row(A, 0, jb, xa, in_a, in_b);
+  for (int j = jb; j < jl; ++j) {
+    const CipRow nxt = cip_load_row(A, 0, j + 1 < jl ? j + 1 : -1, xa, in_a, in_b);
+    const uint32_t fa_ = cur.fl & 0xffu, fb_ = cur.fl >> 8;
+    const uint32_t fl_l = __shfl_up_sync(0xffffffffu, cur.fl, 1), fl_r = __shfl_down_sync(0xffffffffu, cur.fl, 1);
+    // neighbours across x: cell a has (lane-1).b on its left, b on its right, (lane+1).a two to the right
+    const bool dom_b = fb_ & SB2_F_DOMAIN, dom_a = fa_ & SB2_F_DOMAIN;
+    const bool dom_lb = (fl_l >> 8) & SB2_F_DOMAIN, dom_ra = fl_r & SB2_F_DOMAIN, dom_rb = (fl_r >> 8) & SB2_F_DOMAIN;
+    double Fa, Fb, nfa, nfb;
+    bool hfa, hfb;
+    if (POS) {
+      const double fa_l = shfl_up_d(cur.fa.y);
+      cip_face_regs<0, true, P2>(fa_, dom_b, false, dom_lb, cur.v.x, cur.fa.x, fa_l, 0.0, 0.0, xi, Dx, rDx, Fa, nfa, hfa);
+      cip_face_regs<0, true, P2>(fb_, dom_ra, false, dom_a, cur.v.y, cur.fa.y, cur.fa.x, 0.0, 0.0, xi, Dx, rDx, Fb, nfb, hfb);
+    } else {
+      const double v_r = shfl_down_d(cur.v.x), fa_r = shfl_down_d(cur.fa.x);
+      cip_face_regs<0, false, P2>(fa_, dom_b, dom_ra, false, cur.v.x, cur.fa.x, 0.0, cur.v.y, cur.fa.y, xi, Dx, rDx, Fa, nfa, hfa);
+      cip_face_regs<0, false, P2>(fb_, dom_ra, dom_rb, false, cur.v.y, cur.fa.y, 0.0, v_r, fa_r, xi, Dx, rDx, Fb, nfb, hfb);
+    }
+    const double Fl = shfl_up_d(Fb);  // the plus-face flux of the cell left of a
+    double2 dc;
+    dc.x = cip_dc_regs<0, POS, P2>(fa_, Fa, Fl, delta, rdelta);
+    dc.y = cip_dc_regs<0, POS, P2>(fb_, Fb, Fa, delta, rdelta);
+    if (owner) {
+      const int64_t idx = A.first + (int64_t)j * A.P + xa;
+      if (j < je) {
+        // val += val_delta at every point of the row (calcPDE.cpp:657): cells and the faces of this axis
+        const double2 un = make_double2(cur.v.x + dc.x, cur.v.y + dc.y);
+        const double2 fn = make_double2(cur.fa.x + (hfa ? nfa : 0.0), cur.fa.y + (hfb ? nfb : 0.0));
+        if (in_b) {
+          *reinterpret_cast<double2*>(A.u_out + idx) = un;
+          *reinterpret_cast<double2*>(A.face_out + idx) = fn;
+        } else {
+          A.u_out[idx] = un.x;
+          A.face_out[idx] = fn.x;
+        }
+      }
+      if (j > jb && j < A.ny) {
+        // val(x, y+1/2) += (val_delta(x, y+1) + val_delta(x, y)) / 2 for the row below (calcPDE.cpp:659-663)
+        const uint32_t pa = fl_prev & 0xffu, pb = fl_prev >> 8;
+        const bool ua = (pa & SB2_F_DOMAIN) && !(pa & SB2_F_YP), ub = (pb & SB2_F_DOMAIN) && !(pb & SB2_F_YP);
+        if (ua || ub) {
+          double2 fo = fo_prev;
+          if (ua) fo.x = fo.x + (dc.x + dc_prev.x) / 2.0;
+          if (ub) fo.y = fo.y + (dc.y + dc_prev.y) / 2.0;
+          double* dst = A.faces[1] + (idx - A.P);
+          if (ub) *reinterpret_cast<double2*>(dst) = fo; else dst[0] = fo.x;
+        }
+      }
+    }
+    dc_prev = dc; fo_prev = cur.fo; fl_prev = cur.fl;
+    cur = nxt;
+  }
+}
+
+// Y pass: the march runs along the pass axis, so the minus-face flux of a row is the plus-face flux of the previous one
+// (carried); across x only the increment of the right neighbour is needed (other-axis faces): lane 31 only supplies it,
+// 62 owned cells per warp and row
+template <bool POS, bool P2>
+__global__ void __launch_bounds__(kCipUWarps * 32) cip2d_uy_kernel(const __grid_constant__ Sb2CipArgs A, const int rows_per_block) {
+  const int lane = threadIdx.x & 31;
+  const int strip = (int)blockIdx.x * kCipUWarps + (threadIdx.x >> 5);
+  const int xa = strip * 62 + 2 * lane;
+  if (strip * 62 >= A.nx) return;
+  const bool in_a = xa < A.nx, in_b = xa + 1 < A.nx;
+  const bool owner = lane <= 30 && in_a;
+  const int jb = A.row_begin + (int)blockIdx.y * rows_per_block;
+  const int je = min(jb + rows_per_block, A.row_end);
+  const double ux = A.aconst[1], delta = A.delta[1];
+  const double Dx = -copysign(1.0, ux) * delta, rDx = 1.0 / Dx, rdelta = 1.0 / delta, xi = ux * A.dt;
+  // the march starts one row early (flux only) to have the flux through the lower face of the block's first row
+  const int js = jb > 0 ? jb - 1 : jb;
+  CipRow prev = cip_load_row(A, 1, js - 1, xa, in_a, in_b);
+  CipRow cur = cip_load_row(A, 1, js, xa, in_a, in_b);
+  CipRow nxt = cip_load_row(A, 1, js + 1, xa, in_a, in_b);
+  double2 F_prev = make_double2(0.0, 0.0);
+  for (int j = js; j < je; ++j) {
+    // two rows ahead: ux < 0 needs the flags of row j + 2, and the loads get a longer start
+    const CipRow nn = cip_load_row(A, 1, j + 2, xa, in_a, in_b);
+    const uint32_t fa_ = cur.fl & 0xffu, fb_ = cur.fl >> 8;
+    double2 F, nf;
+    bool hfa, hfb;
+    cip_face_regs<1, POS, P2>(fa_, nxt.fl & SB2_F_DOMAIN, nn.fl & SB2_F_DOMAIN, prev.fl & SB2_F_DOMAIN, cur.v.x, cur.fa.x, prev.fa.x, nxt.v.x,
+                              nxt.fa.x, xi, Dx, rDx, F.x, nf.x, hfa);
+    cip_face_regs<1, POS, P2>(fb_, (nxt.fl >> 8) & SB2_F_DOMAIN, (nn.fl >> 8) & SB2_F_DOMAIN, (prev.fl >> 8) & SB2_F_DOMAIN, cur.v.y, cur.fa.y,
+                              prev.fa.y, nxt.v.y, nxt.fa.y, xi, Dx, rDx, F.y, nf.y, hfb);
+    if (j >= jb) {
+      double2 dc;
+      dc.x = cip_dc_regs<1, POS, P2>(fa_, F.x, F_prev.x, delta, rdelta);
+      dc.y = cip_dc_regs<1, POS, P2>(fb_, F.y, F_prev.y, delta, rdelta);
+      const double dc_r = shfl_down_d(dc.x);  // the increment of the cell right of b
+      if (owner) {
+        const int64_t idx = A.first + (int64_t)j * A.P + xa;
+        const double2 un = make_double2(cur.v.x + dc.x, cur.v.y + dc.y);
+        const double2 fn = make_double2(cur.fa.x + (hfa ? nf.x : 0.0), cur.fa.y + (hfb ? nf.y : 0.0));
+        if (in_b) {
+          *reinterpret_cast<double2*>(A.u_out + idx) = un;
+          *reinterpret_cast<double2*>(A.face_out + idx) = fn;
+        } else {
+          A.u_out[idx] = un.x;
+          A.face_out[idx] = fn.x;
+        }
+        // val(x+1/2, y) += (val_delta(x+1, y) + val_delta(x, y)) / 2 (calcPDE.cpp:747-751)
+        const bool ua = (fa_ & SB2_F_DOMAIN) && !(fa_ & SB2_F_XP) && xa + 1 < A.nx;
+        const bool ub = (fb_ & SB2_F_DOMAIN) && !(fb_ & SB2_F_XP) && xa + 2 < A.nx;
+        if (ua || ub) {
+          double2 fo = cur.fo;
+          if (ua) fo.x = fo.x + (dc.y + dc.x) / 2.0;
+          if (ub) fo.y = fo.y + (dc_r + dc.y) / 2.0;
+          double* dst = A.faces[0] + idx;
+          if (ub) *reinterpret_cast<double2*>(dst) = fo; else dst[0] = fo.x;
+        }
+      }
+    }
+    F_prev = F;
+    prev = cur; cur = nxt; nxt = nn;
+  }
+}
+
+template <bool POS, bool P2>
+cudaError_t cip2d_uniform_launch(const Sb2CipArgs& a, int axis, cudaStream_t stream) {
+  const int nupd = a.row_end - a.row_begin;
+  const int per = axis == 0 ? 60 : 62;
+  const int nstrips = (a.nx + per - 1) / per;
+  // rows per block: long marches amortise the prologue rows, short ones fill the machine
+  int rpb = 64;
+  while (rpb > 8 && (int64_t)nstrips * ((nupd + rpb - 1) / rpb) < 148 * 16 * 3) rpb /= 2;
+  const dim3 grid((nstrips + kCipUWarps - 1) / kCipUWarps, (nupd + rpb - 1) / rpb);
+  if (axis == 0) cip2d_ux_kernel<POS, P2><<<grid, kCipUWarps * 32, 0, stream>>>(a, rpb);
+  else cip2d_uy_kernel<POS, P2><<<grid, kCipUWarps * 32, 0, stream>>>(a, rpb);
+  return cudaGetLastError();
+}
+
 // update sweep (calcPDE.cpp:654-673): add the increments and advance the faces of the other axes
 __global__ void __launch_bounds__(256) cip_update_kernel(const __grid_constant__ Sb2CipArgs A, int axis) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -546,6 +771,14 @@ cudaError_t sb2_launch_cip_pass(const Sb2CipArgs& a, int axis, cudaStream_t stre
   if (a.dim == 2 && a.u_out && a.face_out) {
     // fused pass: the caller swaps u / u_out and faces[axis] / face_out afterwards
     if (launches) *launches += 1;
+    static const bool old_pass = getenv("SB2_CIP_OLD") != NULL;  // experiments: the block-cooperative pass for uniform velocities too
+    if (a.akind[axis] == SB2_SRC_CONST && !old_pass) {
+      int e2 = 0;
+      const bool p2 = frexp(a.delta[axis], &e2) == 0.5;  // a power of two: x / delta == x * (1 / delta) bit for bit
+      const bool pos = a.aconst[axis] >= 0;
+      return pos ? (p2 ? cip2d_uniform_launch<true, true>(a, axis, stream) : cip2d_uniform_launch<true, false>(a, axis, stream))
+                 : (p2 ? cip2d_uniform_launch<false, true>(a, axis, stream) : cip2d_uniform_launch<false, false>(a, axis, stream));
+    }
     if (axis == 0) cip2d_x_kernel<<<dim3((a.nx + kCipThreads - 2) / (kCipThreads - 1), (nupd + kCipRows - 1) / kCipRows), kCipThreads, 0, stream>>>(a);
     else cip2d_y_kernel<<<dim3((a.nx + kCipThreads - 2) / (kCipThreads - 1), (nupd + kCipRows - 1) / kCipRows), kCipThreads, 0, stream>>>(a);
     return cudaGetLastError();
