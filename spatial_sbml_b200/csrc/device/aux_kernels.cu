@@ -730,8 +730,10 @@ cudaError_t cip2d_uniform_launch(const Sb2CipArgs& a, int axis, cudaStream_t str
   const int per = axis == 0 ? 60 : 62;
   const int nstrips = (a.nx + per - 1) / per;
   // rows per block: long marches amortise the prologue rows, short ones fill the machine
+  // (small grids are bound by the latency of a march, not by throughput: down to two rows per warp, four along the pass axis
+  // where every march pays a flux-only row)
   int rpb = 64;
-  while (rpb > 8 && (int64_t)nstrips * ((nupd + rpb - 1) / rpb) < 148 * 16 * 3) rpb /= 2;
+  while (rpb > (axis == 0 ? 2 : 4) && (int64_t)nstrips * ((nupd + rpb - 1) / rpb) < 148 * 48) rpb /= 2;
   const dim3 grid((nstrips + kCipUWarps - 1) / kCipUWarps, (nupd + rpb - 1) / rpb);
   if (axis == 0) cip2d_ux_kernel<POS, P2><<<grid, kCipUWarps * 32, 0, stream>>>(a, rpb);
   else cip2d_uy_kernel<POS, P2><<<grid, kCipUWarps * 32, 0, stream>>>(a, rpb);

@@ -75,6 +75,14 @@ __device__ __forceinline__ void mbar_fence_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+// Programmatic dependent launch: consecutive stage kernels of a step are launched with programmatic stream serialisation
+// (sb2_rd_launch_config), so a kernel's CTAs are scheduled and set up their barriers while the previous kernel drains;
+// pdl_wait() returns when the previous kernel has completed and its writes are visible (a no-op without the attribute).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("fence.proxy.async;" ::: "memory");  // the bulk copies below read what the previous kernel wrote with plain stores
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -638,6 +646,7 @@ __device__ __forceinline__ void rd_stage_body(const Sb2RdArgs& A, const double* 
   // the slab axis is y, a tile is a range of the slab's rows (3-D grids: rd_stage3_body below)
   const int yb = A.row_begin + (int)blockIdx.y * A.rows_per_block;
   const int ye = min(yb + A.rows_per_block, A.row_end);
+  pdl_launch_dependents();
   if (yb >= ye) return;
   const int64_t plane0 = A.first;
 
@@ -657,6 +666,7 @@ __device__ __forceinline__ void rd_stage_body(const Sb2RdArgs& A, const double* 
       for (int q = 0; q < RW; ++q) mbar_init(rowbar0 + 8 * q, 1);
     mbar_fence_init();
   }
+  pdl_wait();
 #ifndef SB2_RD_PROGRAM
   // the token records move from their device buffer to shared memory once (first read after the first barrier)
   for (int i = threadIdx.x; i < A.nrd + 2; i += W * 32) {
@@ -882,6 +892,7 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
   const int y = y0 + warp;
   const int zb = A.row_begin + (int)blockIdx.z * A.rows_per_block;
   const int ze = min(zb + A.rows_per_block, A.row_end);
+  pdl_launch_dependents();
   if (zb >= ze) return;
 
   const uint32_t mybar = smem_addr(&bars[warp]);
@@ -895,6 +906,7 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
       for (int q = 0; q < 2 * NSLOT * W; ++q) mbar_init(rowbar0 + 8 * q, 1);
     mbar_fence_init();
   }
+  pdl_wait();
 #ifndef SB2_RD_PROGRAM
   for (int i = threadIdx.x; i < A.nrd + 2; i += W * 32) {
     const Sb2RdTok t = A.rdtok[i];
@@ -1195,8 +1207,10 @@ cudaError_t launch_variant(const Sb2RdArgs& a, cudaStream_t stream) {
     configured = smem;
   }
   if (grid.y == 0 || grid.z == 0) return cudaSuccess;
-  rd_stage_kernel<NS, NP, W, MODE, DEPTH, MINB, D3><<<grid, W * 32, smem, stream>>>(a);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  sb2_rd_launch_config(&cfg, attr, grid, W * 32, smem, stream);
+  return cudaLaunchKernelEx(&cfg, rd_stage_kernel<NS, NP, W, MODE, DEPTH, MINB, D3>, a);
 }
 
 template <int NS, int NP, int W, int DEPTH, int MINB, bool D3>

@@ -137,6 +137,20 @@ static inline void sb2_rd_launch_shape(const Sb2RdArgs& a, int np, int w, int mo
   }
 }
 
+// Launch configuration of a stage kernel: programmatic stream serialisation lets the CTAs of a stage kernel be scheduled
+// while the previous kernel of the stream drains (the kernels call griddepcontrol.wait before they read anything a
+// predecessor wrote); SB2_NO_PDL=1 turns it off.
+static inline void sb2_rd_launch_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, dim3 grid, int threads, size_t smem,
+                                        cudaStream_t stream) {
+  static const bool pdl = getenv("SB2_NO_PDL") == NULL;
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->gridDim = grid; cfg->blockDim = dim3(threads); cfg->dynamicSmemBytes = smem; cfg->stream = stream;
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg->attrs = attr;
+  cfg->numAttrs = pdl ? 1 : 0;
+}
+
 // rd_stage kernel family (rd_stage.cuh, instantiated in rd_stage_ns*.cu)
 struct Sb2RdVariant { int id, ns, np, w, depth; };
 // picks the variant for a 2-D model (returns id or -1 when only the first-generation kernel applies)
