@@ -32,6 +32,7 @@ extern "C" {
 #define SB2_ERR_CUDA (-2)
 #define SB2_ERR_STATE (-3)
 #define SB2_ERR_LIMIT (-4) /* model exceeds a documented device limit (species / depth / tokens) */
+#define SB2_ERR_UNFUSED (-5) /* sb2_step_host: the model needs the unfused schedule; nothing was computed, step with sb2_step instead */
 
 #define SB2_MAX_SPECIES 8   /* staged (RK) volume species per simulator */
 #define SB2_MAX_GEOS 4      /* volume geometries that host staged species */
@@ -225,7 +226,7 @@ SB2_API int sb2_step(sb2_sim* sim, double t_arg, double t_incr, double dt, int n
  * (<= 0: 16) and upload, the four stages and download of successive slabs overlap on three streams.  Replaces the
  * sequence "write through getVariable pointers, oneStep, read them back" (spatialsimulator.h:88, :209) for callers
  * that exchange the whole state with the host every step.  Only for models on the fused schedule (no advection,
- * membrane transport, Dirichlet or non-zero flux conditions): SB2_ERR_STATE otherwise, and the caller falls back. */
+ * membrane transport, Dirichlet or non-zero flux conditions): SB2_ERR_UNFUSED otherwise (nothing computed), and the caller falls back. */
 SB2_API int sb2_step_host(sb2_sim* sim, double t_arg, double dt, int time_slot, const double* const* in, double* const* out, int nslabs);
 /* The same in two halves, which is how a SLAB of a sharded grid (holding four halo rows on either side; host arrays cover the rows
  * the handle holds) steps from host memory: _begin queues the uploads, the rows of the two edge sub-slabs first, and - when it
@@ -300,7 +301,7 @@ SB2_API int sb2_sharded_next(sb2_sim* sim, sb2_exchange* x);
 SB2_API int sb2_group_step(sb2_sim* const* sims, int n, double t_arg, double dt, int time_slot);
 /* sb2_step_host for the slabs of such a group: in[i] / out[i] are slab i's arrays of per-species host pointers, each to the
  * first row slab i HOLDS.  One peer copy of four edge rows of u per neighbour and step; every slab's upload / stages / download
- * pipeline then runs beside the others'.  SB2_ERR_STATE (nothing computed) when the model needs the unfused schedule. */
+ * pipeline then runs beside the others'.  SB2_ERR_UNFUSED (nothing computed) when the model needs the unfused schedule. */
 SB2_API int sb2_group_step_host(sb2_sim* const* sims, int n, double t_arg, double dt, int time_slot, const double* const* const* in,
                                 double* const* const* out, int nslabs);
 

@@ -65,6 +65,9 @@ SSB_API double ssb_get_variable_at(ssb_sim* s, const char* id, int x, int y, int
 SSB_API void ssb_flip_volume_order(ssb_sim* s);                                               /* :187 */
 
 SSB_API double* ssb_get_variable(ssb_sim* s, const char* id, int* length);                    /* :209 */
+/* the array behind ssb_get_variable is kept current after every step (and written values are picked up before the next one),
+ * as the reference's pointer into its state is; ssb_release_variable ends that for `id` (the pointer stays valid) */
+SSB_API void ssb_release_variable(ssb_sim* s, const char* id);
 SSB_API int* ssb_get_geometry(ssb_sim* s, const char* compartment, int* length);              /* :220 */
 SSB_API uint8_t* ssb_get_boundary_type(ssb_sim* s, const char* compartment, int* length);     /* :231, 6 bools per point */
 SSB_API int* ssb_get_boundary(ssb_sim* s, const char* compartment, int* length);              /* :242 */

@@ -143,6 +143,7 @@ def _proto(lib):
         "ssb_get_variable_at": (cd, [vp, cs, ci, ci, ci]),
         "ssb_flip_volume_order": (None, [vp]),
         "ssb_get_variable": (dp, [vp, cs, C.POINTER(ci)]),
+        "ssb_release_variable": (None, [vp, cs]),
         "ssb_get_geometry": (C.POINTER(ci), [vp, cs, C.POINTER(ci)]),
         "ssb_get_boundary_type": (C.POINTER(C.c_uint8), [vp, cs, C.POINTER(ci)]),
         "ssb_get_boundary": (C.POINTER(ci), [vp, cs, C.POINTER(ci)]),
@@ -329,6 +330,19 @@ class SpatialSimulator(object):
             return None
         total = self.getGeometryLength() if n > 0 and n + 1 == self.getGeometryLength() else n
         return np.ctypeslib.as_array(p, shape=(total,))
+
+    def getSpeciesCompartment(self, id):
+        """compartment id of a variable (what getModel()->getSpecies(id)->getCompartment() gives a caller of the reference), or None"""
+        for line in self.getSetupText("summary").split("\n"):
+            t = line.split()
+            if len(t) > 2 and t[0] == "var" and t[1] == id and "geo" in t:
+                c = t[t.index("geo") + 1]
+                return None if c == "-" else c
+        return None
+
+    def releaseVariable(self, id):
+        """Stop keeping the array behind getVariable(id) current after every step (a download per step otherwise)."""
+        self._lib.ssb_release_variable(self._h, id.encode())
 
     def getGeometry(self, compartment):
         p, n = self._borrow(self._lib.ssb_get_geometry, compartment, np.int32)

@@ -1801,7 +1801,7 @@ int sb2_step_host_begin(sb2_sim* sim, double t_arg, double dt, int time_slot, co
   if (!sim->fuse_combine || !sim->transports.empty() || sim->blists[0].n_dirichlet > 0 || sim->model_dirichlet || !sim->mem_species.empty() ||
       !sim->cell_rules.empty()) {
     sim->in_step = false;
-    return fail(sim, SB2_ERR_STATE, "sb2_step_host: the model needs the unfused schedule (advection, membrane transport, non-zero flux or Dirichlet)");
+    return fail(sim, SB2_ERR_UNFUSED, "sb2_step_host: the model needs the unfused schedule (advection, membrane transport, non-zero flux or Dirichlet)");
   }
   const int n = r.own_hi - r.own_lo;
   if (nslabs < 1) nslabs = 16;

@@ -87,6 +87,7 @@ int ssb_get_zdim(ssb_sim* s) { return s ? s->sim.getZDim() : 0; }
 double ssb_get_variable_at(ssb_sim* s, const char* id, int x, int y, int z) { return s && id ? s->sim.getVariableAt(id, x, y, z) : 0.0; }
 void ssb_flip_volume_order(ssb_sim* s) { if (s) s->sim.flipVolumeOrder(); }
 
+void ssb_release_variable(ssb_sim* s, const char* id) { if (s && id) s->sim.releaseVariable(id); }
 double* ssb_get_variable(ssb_sim* s, const char* id, int* length) {
   int n = 0;
   double* p = s && id ? s->sim.getVariable(id, n) : NULL;

@@ -853,6 +853,30 @@ bool SpatialSimulator::addMemTransportOn(void* rx, void* memGeo) {
 // =============================================================================================
 void SpatialSimulator::syncBeforeStep() {
   sb2host::Model& m = impl->m;
+  if (!impl->slabs.empty()) {
+    // group: values written through a getVariable() pointer go to the slabs that hold the rows (the mirror is current: handed-out
+    // mirrors are refreshed after every step); then every slab settles its own constants
+    for (std::map<std::string, VarMirror>::iterator it = impl->varMirrors.begin(); it != impl->varMirrors.end(); ++it) {
+      if (!it->second.handedOut) continue;
+      Var* v = m.findVar(it->first);
+      if (!v || v->isUniform || v->onMembrane || impl->isCoordinate(v) || !impl->groupFresh.count(v)) continue;
+      bool changed = false;
+      const double* d = it->second.data.data();
+      for (int k = 0; k < m.nz; ++k)
+        for (int j = 0; j < m.ny; ++j) {
+          const double* row = d + (int64_t)(2 * k) * m.Yindex * m.Xindex + (int64_t)(2 * j) * m.Xindex;
+          double* f = v->field.data() + ((int64_t)k * m.ny + j) * m.nx;
+          for (int i = 0; i < m.nx; ++i)
+            if (memcmp(&row[2 * i], &f[i], sizeof(double)) != 0) { f[i] = row[2 * i]; changed = true; }
+        }
+      if (changed) {
+        const std::vector<double> copy(v->field);
+        setVariableCompact(it->first, copy.data(), copy.size());
+      }
+    }
+    for (size_t i = 0; i < impl->slabs.size(); ++i) impl->slabs[i]->syncBeforeStep();
+    return;
+  }
   // values written through a pointer handed out by getVariable()
   for (std::map<std::string, VarMirror>::iterator it = impl->varMirrors.begin(); it != impl->varMirrors.end(); ++it) {
     if (!it->second.handedOut) continue;
@@ -897,10 +921,8 @@ void SpatialSimulator::syncBeforeStep() {
 double SpatialSimulator::oneStep(double initialTime, double step) {
   if (impl && !impl->slabs.empty()) {
     std::vector<sb2_sim*> handles;
-    for (size_t i = 0; i < impl->slabs.size(); ++i) {
-      impl->slabs[i]->syncBeforeStep();
-      handles.push_back(impl->slabs[i]->impl->dev);
-    }
+    syncBeforeStep();
+    for (size_t i = 0; i < impl->slabs.size(); ++i) handles.push_back(impl->slabs[i]->impl->dev);
     impl->m.simTime = initialTime * step;
     impl->m.tVar->uniformValue = impl->m.simTime;
     const int rc = sb2_group_step(handles.data(), (int)handles.size(), initialTime, step, impl->slabs[0]->impl->timeSlot);
@@ -911,6 +933,7 @@ double SpatialSimulator::oneStep(double initialTime, double step) {
     }
     for (size_t i = 0; i < impl->slabs.size(); ++i) impl->slabs[i]->deviceStateChanged();
     impl->groupFresh.clear();
+    refreshHandedOut();
     return initialTime + step;
   }
   if (!impl || !impl->dev)
@@ -925,6 +948,7 @@ double SpatialSimulator::oneStep(double initialTime, double step) {
     throw std::runtime_error(lastError);
   }
   impl->markStale();
+  refreshHandedOut();
   return initialTime + step;
 }
 
@@ -947,13 +971,13 @@ double SpatialSimulator::oneStepHost(double initialTime, double step, int n, con
         dout[g][v->speciesId] = out[i] ? out[i] + off : NULL;
       }
     }
-    int rc = SB2_ERR_STATE;
+    int rc = SB2_ERR_UNFUSED;
     if (staged_only) {
       std::vector<sb2_sim*> handles;
       std::vector<const double* const*> pin;
       std::vector<double* const*> pout;
+      syncBeforeStep();
       for (size_t g = 0; g < G; ++g) {
-        impl->slabs[g]->syncBeforeStep();
         impl->slabs[g]->impl->m.simTime = initialTime * step;
         impl->slabs[g]->impl->m.tVar->uniformValue = initialTime * step;
         handles.push_back(impl->slabs[g]->impl->dev);
@@ -961,12 +985,12 @@ double SpatialSimulator::oneStepHost(double initialTime, double step, int n, con
         pout.push_back(dout[g].data());
       }
       rc = sb2_group_step_host(handles.data(), (int)G, initialTime, step, impl->slabs[0]->impl->timeSlot, pin.data(), pout.data(), nslabs);
-      if (rc < 0 && rc != SB2_ERR_STATE) {
+      if (rc < 0 && rc != SB2_ERR_UNFUSED) {
         lastError = std::string("sb2_group_step_host: ") + sb2_last_error(handles[0]);
         throw std::runtime_error(lastError);
       }
     }
-    if (rc == SB2_ERR_STATE) {
+    if (rc == SB2_ERR_UNFUSED) {
       for (int i = 0; i < n; ++i)
         if (in && in[i] && !setVariableCompact(ids[i], in[i], (size_t)impl->m.ncells())) throw std::runtime_error(std::string("oneStepHost: cannot set ") + ids[i]);
       oneStep(initialTime, step);
@@ -977,6 +1001,7 @@ double SpatialSimulator::oneStepHost(double initialTime, double step, int n, con
     impl->m.simTime = initialTime * step;
     impl->groupFresh.clear();
     for (size_t g = 0; g < G; ++g) impl->slabs[g]->deviceStateChanged();
+    refreshHandedOut();
     return initialTime + step;
   }
   if (!impl || !impl->dev)
@@ -997,8 +1022,8 @@ double SpatialSimulator::oneStepHost(double initialTime, double step, int n, con
     din[v->speciesId] = in ? in[i] : NULL;
     dout[v->speciesId] = out ? out[i] : NULL;
   }
-  int rc = staged_only ? sb2_step_host(impl->dev, initialTime, step, impl->timeSlot, din.data(), dout.data(), nslabs) : SB2_ERR_STATE;
-  if (rc == SB2_ERR_STATE) {
+  int rc = staged_only ? sb2_step_host(impl->dev, initialTime, step, impl->timeSlot, din.data(), dout.data(), nslabs) : SB2_ERR_UNFUSED;
+  if (rc == SB2_ERR_UNFUSED) {
     // unfused schedule (or a variable that is not a staged species): the plain sequence
     for (int i = 0; i < n; ++i)
       if (in && in[i] && !setVariableCompact(ids[i], in[i], (size_t)impl->m.ncells())) throw std::runtime_error(std::string("oneStepHost: cannot set ") + ids[i]);
@@ -1012,6 +1037,7 @@ double SpatialSimulator::oneStepHost(double initialTime, double step, int n, con
     throw std::runtime_error(lastError);
   }
   impl->markStale();
+  refreshHandedOut();
   return initialTime + step;
 }
 
@@ -1033,6 +1059,26 @@ void SpatialSimulator::runSteps(double firstStepIndex, double step, int nsteps) 
   impl->m.simTime = (firstStepIndex + nsteps - 1) * step;
   impl->m.tVar->uniformValue = impl->m.simTime;
   impl->markStale();
+  refreshHandedOut();
+}
+
+// The reference's getVariable() pointer aliases the live state (SpatialUI reads concentrations and applies doses through it,
+// simulationthread.cpp:136-185).  Here it points to a host mirror: after every step the mirrors that were handed out are
+// filled again from the device, so reads through the pointer see the new values and writes (compared with the host copy
+// before the next step, syncBeforeStep) reach the device.  releaseVariable() ends that for callers that are done with a pointer.
+void SpatialSimulator::refreshHandedOut() {
+  if (!impl || impl->m.isSlab()) return;
+  std::vector<std::string> ids;
+  for (std::map<std::string, VarMirror>::iterator it = impl->varMirrors.begin(); it != impl->varMirrors.end(); ++it)
+    if (it->second.handedOut) ids.push_back(it->first);
+  int len = 0;
+  for (size_t i = 0; i < ids.size(); ++i) getVariable(ids[i], len);
+}
+
+void SpatialSimulator::releaseVariable(const std::string& id) {
+  if (!impl) return;
+  std::map<std::string, VarMirror>::iterator it = impl->varMirrors.find(id);
+  if (it != impl->varMirrors.end()) it->second.handedOut = false;
 }
 
 void SpatialSimulator::deviceStateChanged() {

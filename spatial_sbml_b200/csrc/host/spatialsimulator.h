@@ -65,6 +65,10 @@ class __attribute__((visibility("default"))) SpatialSimulator {
   // destroyed.  A variable pointer stays "live": values written through it are uploaded before the
   // next step, and the mirror is refreshed by the next accessor call after a step.
   double* getVariable(const std::string& id, int& length);            // :209
+  // The pointer stays live like the reference's (which aliases the simulator's state): after every step the array is filled
+  // again from the device, values written through it reach the device before the next step.  That costs a download per step
+  // and handed-out variable; releaseVariable() ends it (the pointer stays valid, it is just no longer kept current).
+  void releaseVariable(const std::string& id);
   int* getGeometry(const std::string& id, int& length);               // :220
   boundaryType* getBoundaryType(const std::string& id, int& length);  // :231
   int* getBoundary(const std::string& id, int& length);               // :242
@@ -136,6 +140,7 @@ class __attribute__((visibility("default"))) SpatialSimulator {
   bool addMembraneSpecies();
   bool addMembraneReaction(void* rxn, void* geo, int kind);
   void syncBeforeStep();
+  void refreshHandedOut();
 
   int Xdiv, Ydiv, Zdiv;
   SimImpl* impl;

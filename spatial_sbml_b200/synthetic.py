@@ -240,7 +240,7 @@ def _membrane_geometry(axes, dims, inside_math):
             '</spatial:geometry>' % (cc, _MATH, inside_math, _MATH, _cn(1)))
 
 
-def membrane(nx, ny, nz=None, shape="disc", transport=True):
+def membrane(nx, ny, nz=None, shape="disc", transport=True, mixed=False, surface=True):
     """A cell (disc / ball, or a box with shape="box") in a bath with species ON the membrane between them: what the reference
     calls membrane diffusion (calcMemDiffusion over the Voronoi neighbours of setVoronoiInfo), binding of a volume species to
     a membrane species (the binding branches of calcMemTransport), a reaction between membrane species (reversePolishRK over
@@ -248,6 +248,10 @@ def membrane(nx, ny, nz=None, shape="disc", transport=True):
     membrane transport between the two volumes beside them.  No example file of the reference has a membrane species.
       A (cell, diffuses) --bind: kon*A--> M (membrane, surface diffusion, non-uniform start) --conv: kc*M--> N (membrane)
       M --unbind: koff*M--> A;   A (cell) --leak: kl*A--> E (bath), a transport across the membrane.
+    mixed=True: ordinary volume reactions on the transported species as well, listed BEFORE the transports (-> A: g, A ->: kd*A)
+    and after them (E ->: ke*E), so that the order in which the reference accumulates the terms of a species (rInfoList order,
+    spatialsimulator.cpp:1374-1451) matters to the last bit.  surface=False: no species on the membrane (M, N and their reactions
+    are left out), only the transport across it.
     dt 0.05."""
     dims = [nx, ny] + ([nz] if nz else [])
     axes = ["x", "y", "z"][:len(dims)]
@@ -267,20 +271,27 @@ def membrane(nx, ny, nz=None, shape="disc", transport=True):
     def sp(sid, comp, conc):
         return ('<species id="%s" compartment="%s" hasOnlySubstanceUnits="false" boundaryCondition="false" constant="false" '
                 'spatial:isSpatial="true"%s/>' % (sid, comp, (' initialConcentration="%r"' % float(conc)) if conc is not None else ""))
-    species = sp("A", "cell", None) + sp("E", "bath", 0.25) + sp("M", "mem", None) + sp("N", "mem", 0.0)
+    species = sp("A", "cell", None) + sp("E", "bath", 0.25) + (sp("M", "mem", None) + sp("N", "mem", 0.0) if surface else "")
     params = _transport_params("A", 0.8, axes) + _transport_params("E", 0.5, axes)
-    params.append(_param("M_diff", 0.35, '<spatial:diffusionCoefficient spatial:variable="M" spatial:type="isotropic"/>'))
-    params.append(_param("N_diff", 0.2, '<spatial:diffusionCoefficient spatial:variable="N" spatial:type="isotropic"/>'))
+    if surface:
+        params.append(_param("M_diff", 0.35, '<spatial:diffusionCoefficient spatial:variable="M" spatial:type="isotropic"/>'))
+        params.append(_param("N_diff", 0.2, '<spatial:diffusionCoefficient spatial:variable="N" spatial:type="isotropic"/>'))
     params += [_param("kon", 0.3), _param("koff", 0.05), _param("kc", 0.11), _param("kl", 0.07)]
     coords = "".join(_param(a, 0.0, '<spatial:spatialSymbolReference spatial:spatialRef="%s"/>' % a) for a in axes)
     ia = [("A", _apply("plus", _cn(1.0), _apply("times", _cn(0.02), _ci("x")))),
           ("M", _apply("plus", _cn(0.5), _apply("times", _cn(0.03), _ci("y")), _apply("times", _cn(0.01), _ci("x"))))]
+    if not surface:
+        ia = ia[:1]
     ia_xml = "".join('<initialAssignment symbol="%s"><math %s>%s</math></initialAssignment>' % (s, _MATH, m) for s, m in ia)
-    rx = [_reaction("bind", [("A", 1)], [("M", 1)], _apply("times", _ci("kon"), _ci("A"))),
+    rx = [] if not surface else [_reaction("bind", [("A", 1)], [("M", 1)], _apply("times", _ci("kon"), _ci("A"))),
           _reaction("conv", [("M", 1)], [("N", 1)], _apply("times", _ci("kc"), _ci("M"))),
           _reaction("unbind", [("M", 1)], [("A", 1)], _apply("times", _ci("koff"), _ci("M")))]
     if transport:
         rx.append(_reaction("leak", [("A", 1)], [("E", 1)], _apply("times", _ci("kl"), _ci("A"))))
+    if mixed:
+        params += [_param("g", 0.013), _param("kd", 0.021), _param("ke", 0.017)]
+        rx = ([_reaction("growA", [], [("A", 1)], _ci("g")), _reaction("decayA", [("A", 1)], [], _apply("times", _ci("kd"), _ci("A")))]
+              + rx + [_reaction("decayE", [("E", 1)], [], _apply("times", _ci("ke"), _ci("E")))])
     return ('<?xml version="1.0" encoding="UTF-8"?>\n'
             '<sbml xmlns="http://www.sbml.org/sbml/level3/version1/core" xmlns:spatial="%s" level="3" version="1" '
             'spatial:required="true"><model id="synthetic_membrane"><listOfCompartments>%s</listOfCompartments>'
@@ -288,6 +299,17 @@ def membrane(nx, ny, nz=None, shape="disc", transport=True):
             '<listOfInitialAssignments>%s</listOfInitialAssignments>'
             '<listOfReactions>%s</listOfReactions>%s</model></sbml>\n'
             % (SPATIAL_NS, comps, species, coords, "".join(params), ia_xml, "".join(rx), _membrane_geometry(axes, dims, inside)))
+
+
+def membrane_mixed(nx, ny, nz=None):
+    """membrane() with ordinary reactions on the transported species before and after the transports in the reaction list"""
+    return membrane(nx, ny, nz, mixed=True)
+
+
+def transport_mixed(nx, ny, nz=None):
+    """A transport across a membrane without membrane species, with ordinary reactions on the transported species listed before
+    (A) and after (E) the transport"""
+    return membrane(nx, ny, nz, mixed=True, surface=False)
 
 
 def membrane_box(nx, ny, nz=None):

@@ -91,6 +91,8 @@ CASES = {
     # six staged species: the first-generation stage kernel's 8-species instantiation
     "syn_chain6_2d": ("synthetic:chain6:70:24", (70, 24, 1), 0.05, [1, 10, 100], {}, []),
     "syn_membrane_2d": ("synthetic:membrane:40:36", (40, 36, 1), 0.05, [1, 2, 10, 100], {}, []),
+    "syn_membrane_mixed_2d": ("synthetic:membrane_mixed:40:36", (40, 36, 1), 0.05, [1, 2, 10, 100], {}, []),
+    "syn_transport_mixed_2d": ("synthetic:transport_mixed:40:36", (40, 36, 1), 0.05, [1, 2, 10, 100], {}, []),
     "syn_membrane_box_2d": ("synthetic:membrane_box:30:26", (30, 26, 1), 0.05, [1, 2, 10, 100], {}, []),
     "syn_membrane_3d": ("synthetic:membrane:20:18:16", (20, 18, 16), 0.05, [1, 2, 10, 50], {}, []),
 }

@@ -355,3 +355,96 @@ def test_threaded_host_setup_gives_the_same_model(monkeypatch):
         assert np.array_equal(out["1"][key], out["7"][key]), key
     assert out["1"]["summary"] == out["7"]["summary"]
     assert out["1"]["geo"].sum() == (dims[0] - 2) * (dims[1] - 2)
+
+
+def test_dmp_round_trip_and_clamping(tmp_path):
+    """DataHelper (datahelper.hh): "maxX maxY" + maxX lines of maxY numbers in default iostream formatting, data[x][y],
+    operator() floors and clamps"""
+    from spatial_sbml_b200.dmp import DataHelper
+    h = DataHelper(rows=3, cols=2)
+    h.data[:] = [[0.5, 1234567.0], [1e-7, -2.25], [3.0, 0.1 + 0.2]]
+    f = str(tmp_path / "a.dmp")
+    h.write(f)
+    assert open(f).read() == "3 2\n0.5 1.23457e+06 \n1e-07 -2.25 \n3 0.3 \n"
+    g = DataHelper(f)
+    assert g.is_valid() and g.data.shape == (3, 2)
+    assert g(1.9, 1.2) == -2.25 and g(-4, 7) == 1234570.0 and g(99, 0) == 3.0
+    assert not DataHelper(str(tmp_path / "missing.dmp")).is_valid()
+
+
+def test_dmp_import_export_follow_the_ui(tmp_path):
+    """exportConcentration collects getVariableAt(x, y); importConcentration doses every cell of the species' compartment and
+    leaves the others alone (spatialmainwidget.cpp:205-257, simulationthread.cpp:160-185)."""
+    from spatial_sbml_b200.dmp import DataHelper
+    sim, g, dims = host_sim("turing_tiny")
+    nx, ny = dims[0], dims[1]
+    h = DataHelper.from_simulator(sim, "species_1")
+    assert h.data.shape == (nx, ny)
+    for x, y in ((0, 0), (5, 7), (nx - 1, 3), (10, ny - 2)):
+        assert h(x, y) == sim.getVariableAt("species_1", x, y, 0)
+    f = str(tmp_path / "s.dmp")
+    h.data[:] = np.arange(nx * ny, dtype=np.float64).reshape(nx, ny) / 8.0  # exactly representable with six digits
+    h.write(f)
+    before = sim.getVariableCompact("species_1").copy()
+    assert sim.getSpeciesCompartment("species_1") is not None
+    assert DataHelper(f).apply(sim, "species_1")
+    after = sim.getVariableCompact("species_1")
+    geo = np.asarray(sim.getGeometry(sim.getSpeciesCompartment("species_1"))).reshape(2 * ny - 1, 2 * nx - 1)[::2, ::2] != 0
+    assert geo.any() and not geo.all()
+    assert np.array_equal(after[0][geo], (h.data.T)[geo])
+    assert np.array_equal(after[0][~geo], before[0][~geo])
+    sim.close()
+
+
+@pytest.mark.parametrize("case", ["syn_membrane_2d", "syn_membrane_3d"])
+def test_membrane_csv_of_the_cli_lists_every_doubled_grid_point(case, tmp_path):
+    """outputTimeCource's membrane file (outputFunction.cpp:65-98, :133-152, :175-198): one row per point of the doubled grid with
+    `mFlag, value` per membrane species, a blank line after each row of points (3-D: not after the last row of a plane)."""
+    from spatial_sbml_b200 import cli
+    sim, g, dims = host_sim(case)
+    nx, ny, nz = dims
+    X, Y, Z = 2 * nx - 1, 2 * ny - 1, 2 * nz - 1
+    mem = cli.membrane_species(sim)
+    assert mem and all(is_membrane_species(g, sid) for sid, _ in mem)
+    vol = [n for n in cli.spatial_species(sim) if n not in set(s for s, _ in mem)]
+    assert vol and not any(is_membrane_species(g, n) for n in vol)
+    f = str(tmp_path / "m.csv")
+    cli.write_membrane_csv(f, sim, mem, case, 1.0, 0.1, 0.0)
+    lines = open(f).read().split("\n")
+    assert lines[0] == "# results of %s.xml simulation" % case
+    assert lines[2].startswith("# about mFlag")
+    assert lines[5] == "# x, y%s" % (", z" if nz > 1 else "") + "".join(", mFlag, " + sid for sid, _ in mem)
+    body = lines[6:]
+    rows = [l for l in body if l]
+    assert len(rows) == X * Y * Z
+    blanks = len([l for l in body[:-1] if not l])
+    assert blanks == (Y if nz == 1 else Z * (Y - 1))
+    t = np.array([[float(v) for v in r.split(", ")] for r in rows])
+    c0 = 3 if nz > 1 else 2
+    sid, comp = mem[0]
+    flags = t[:, c0].astype(int)
+    assert set(np.unique(flags)) == {0, 1, 2}
+    assert np.array_equal(flags, np.asarray(sim.getGeometry(comp))[:X * Y * Z])
+    pts = g["geo/%s/points" % str(g["memgeo/%s" % sid])]
+    assert np.array_equal(t[pts, c0 + 1], g["step/0/" + sid])
+    assert not t[flags == 0, c0 + 1].any()
+    sim.close()
+
+
+def test_the_references_own_cli_compiles_against_our_header():
+    """Source compatibility of the drop-in class: SpatialCL/main.cpp of the reference, unmodified and in place, compiled against
+    csrc/host/spatialsimulator.h and linked with libspatialb200.so (oracle/Makefile, target spatialcl_b200).  Without a GPU the
+    program must fail loudly - there is no CPU path to fall back to."""
+    import subprocess
+    exe = os.path.join(REPO, "oracle", "_ref", "spatialcl_b200")
+    if os.path.isdir("/root/reference/SpatialCL"):
+        subprocess.run(["make", "-s", "-C", os.path.join(REPO, "oracle"), exe], check=True)
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/spatialcl_b200 is built where /root/reference is mounted")
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("run on the GPU by tests/test_parity_gpu.py")
+    r = subprocess.run([exe, model_path("turing_tiny")], capture_output=True, text=True)
+    assert r.returncode != 0
+    assert "spatial required: yes" in r.stdout
+    assert "no CPU fallback" in r.stderr

@@ -30,6 +30,8 @@ RESTATED = {"turing_tiny": 1000, "turing_tiny_cl": 100, "turing_uniform": 100, "
             "advection": 100,
             # calcMemTransport restated per membrane point (incl. the rpStack[1] rate quirk)
             "transport": 100, "transport_rate": 100,
+            # ... with ordinary reactions on the transported species before and after the transport in the reaction list
+            "syn_transport_mixed_2d": 100,
             # rate rules only; power, log to a base, xor / eq / neq, tanh, cos, time and a pop-only operator in the laws
             "syn_raterules_2d": 100,
             # geometry from an image + a membrane transport; six species
@@ -67,7 +69,7 @@ def test_restatement_matches_reference_bit_for_bit(case):
 # per-step assignment rules.  Those
 # paths are pinned to the reference directly: the device is compared with the reference's own fields (tests/test_parity_gpu.py)
 # and the host set-up (Voronoi neighbours, s_ij, d_ij, normals, initial values) with the reference's arrays (tests/test_host_cpu.py).
-NOT_RESTATED = {"syn_membrane_2d", "syn_membrane_box_2d", "syn_membrane_3d",
+NOT_RESTATED = {"syn_membrane_2d", "syn_membrane_box_2d", "syn_membrane_3d", "syn_membrane_mixed_2d",
                 # assignment rules re-evaluated every step (updateAssignmentRules): pinned the same way
                 "syn_rules_2d", "syn_rules_3d",
                 # field-valued diffusion coefficients (the restatement takes uniform coefficients only)

@@ -6,10 +6,12 @@ to 1000 steps on the non-pattern-forming models.  Pattern-forming models (blob-i
 fish) amplify rounding differences exponentially, so they are held to 1e-10 on a short horizon and to
 a looser bound later; the bound is written next to each case.
 """
+import os
+
 import numpy as np
 import pytest
 
-from conftest import golden_cases, load_golden, model_path, species_values
+from conftest import REPO, golden_cases, load_golden, model_path, species_values
 
 pytestmark = pytest.mark.gpu
 
@@ -237,6 +239,52 @@ def test_host_pipelined_step_is_the_same_step(case, nslabs, jit, monkeypatch):
         assert np.array_equal(b.getVariableCompact(sp), cur[sp])
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("devices", [None, [0, 0]])
+def test_get_variable_pointer_is_live_like_the_reference(devices):
+    """The SpatialUI pattern (simulationthread.cpp:136-185): keep the getVariable() array, read concentrations from it after
+    every step and apply a dose by writing into it - without calling getVariable() again."""
+    import spatial_sbml_b200 as sb
+    g = load_golden("turing_blob")
+    nx, ny, nz = [int(v) for v in g["dims"]]
+    dt = float(g["dt"])
+    a = sb.SpatialSimulator(devices=devices)
+    a.initFromFile(model_path("turing_blob"), nx, ny, nz)
+    b = sb.SpatialSimulator()
+    b.initFromFile(model_path("turing_blob"), nx, ny, nz)
+    live = a.getVariable("species_1")
+    idx = a.getIndexForPosition(40, 37)
+    for t in range(6):
+        if t == 3:  # the dose: through the pointer on one side, through the accessor on the other
+            live[idx] = 7.5
+            c = b.getVariableCompact("species_1")
+            c[0, 37, 40] = 7.5
+            b.setVariableCompact("species_1", c)
+        a.oneStep(t, dt)
+        b.oneStep(t, dt)
+        want = b.getVariableCompact("species_1")
+        assert np.array_equal(live.reshape(2 * ny - 1, 2 * nx - 1)[::2, ::2], want[0]), t
+    a.releaseVariable("species_1")
+    a.oneStep(6, dt)
+    b.oneStep(6, dt)
+    assert not np.array_equal(live.reshape(2 * ny - 1, 2 * nx - 1)[::2, ::2], b.getVariableCompact("species_1")[0])
+    assert np.array_equal(a.getVariableCompact("species_1"), b.getVariableCompact("species_1"))
+    a.close()
+    b.close()
+
+
+def test_the_references_own_cli_runs_on_the_library():
+    """SpatialCL/main.cpp of the reference (unmodified, compiled against our spatialsimulator.h, oracle/Makefile): a 101 x 101 grid,
+    run(1001, 0.01) = 100 101 steps."""
+    import subprocess
+    exe = os.path.join(REPO, "oracle", "_ref", "spatialcl_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/spatialcl_b200 is built where /root/reference is mounted")
+    r = subprocess.run([exe, model_path("turing_tiny_cl")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "spatial required: yes" in r.stdout and "100% finished" in r.stdout
+    assert "time:" in r.stderr
 
 
 def test_host_step_falls_back_for_unfused_models():
