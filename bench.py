@@ -393,7 +393,7 @@ def advection_workload(sb, synthetic, torch, peak, K, W, n=4096):
             "roofline_step": {"bound": "hbm", "achieved": bytes_step / (ms_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                               "frac": bytes_step / (ms_step * 1e-3) / 1e9 / peak,
                               "algorithmic_bytes_per_cell_update": 104 * S_adv + 4 + 40 * d * S_adv},
-            "roofline": {"bound": "hbm", "kernel": "cip2d_x_kernel / cip2d_y_kernel (one fused direction pass of one species)",
+            "roofline": {"bound": "hbm", "kernel": "cip2d_ux_kernel / cip2d_uy_kernel (one fused, warp-independent direction pass of one species with a uniform velocity)",
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
                          "algorithmic_bytes_per_launch": bytes_pass, "avg_launch_ms": ms_pass.value}}
 

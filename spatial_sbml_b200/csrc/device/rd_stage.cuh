@@ -1024,26 +1024,28 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
   //   this iteration (requested in the previous one, when its class was decoded)
   int cls_cur = 2;
   uint32_t seg_cur = 0xffffffffu;  // bit p: the 64-cell segment of cell pair p is not all-interior
-  int cb_next[NP];
+  uint32_t cb_next[NP];  // as loaded: nothing may consume them before decode_class(), an iteration later
+  bool cb_valid[NP];     // the 64-cell segment of pair p exists (the last strip of a row may be narrower)
   uint32_t fraw[NP][SB2_MAX_GEOS];  // the two flag bytes of a cell pair as loaded (16 bits), split only where they are used
 #pragma unroll
   for (int p = 0; p < NP; ++p) {
-    cb_next[p] = 2;
+    cb_next[p] = 2u;
+    cb_valid[p] = (int)blockIdx.x * NP + p < A.nstrips;
 #pragma unroll
     for (int g = 0; g < SB2_MAX_GEOS; ++g) fraw[p][g] = 0u;
   }
   auto load_class = [&](int plane) {  // one byte per 64 cells: 1 all interior, 2 all outside, 0 mixed
     const uint8_t* cb = A.cls + ((uint32_t)plane * (uint32_t)A.ny + (uint32_t)y) * (uint32_t)A.nstrips + blockIdx.x * NP;
 #pragma unroll
-    for (int p = 0; p < NP; ++p) cb_next[p] = ((int)blockIdx.x * NP + p < A.nstrips) ? (int)cb[p] : -1;
+    for (int p = 0; p < NP; ++p) cb_next[p] = cb[cb_valid[p] ? p : 0];  // (the select is on the address: the byte itself stays untouched)
   };
   auto decode_class = [&]() {
     if (A.carry) { cls_cur = 0; seg_cur = 0xffffffffu; return; }
-    int c = cb_next[0];
+    int c = cb_valid[0] ? (int)cb_next[0] : -1;
     uint32_t m = c == 1 ? 0u : 1u;
 #pragma unroll
     for (int p = 1; p < NP; ++p) {
-      const int cp = cb_next[p];
+      const int cp = cb_valid[p] ? (int)cb_next[p] : -1;
       if (cp >= 0) {
         if (cp != c) c = 0;
         if (cp != 1) m |= 1u << p;
