@@ -938,7 +938,7 @@ int sb2_build_transport(const sb2_grid& g, int64_t P, int64_t PL, int64_t first,
       const bool mem = toks[i].kind == SB2_TOK_MEMVAR;
       if (!mem && toks[i].slot >= nspecies) { err = "membrane transport: token references unknown species"; return SB2_ERR_ARG; }
       if (mem && toks[i].slot >= SB2_MAX_MEM_SPECIES) { err = "membrane transport: token references unknown membrane species"; return SB2_ERR_ARG; }
-      if (!operand_cells) { err = "membrane transport: operand cells missing"; return SB2_ERR_ARG; }
+      if (!operand_cells && npts > 0) { err = "membrane transport: operand cells missing"; return SB2_ERR_ARG; }
       out.tok_operand.push_back(rows++);
       for (int p = 0; p < npts; ++p) {
         const int32_t c0 = operand_cells[((int64_t)nvar * npts + p) * 2 + 0], c1 = operand_cells[((int64_t)nvar * npts + p) * 2 + 1];
@@ -948,7 +948,7 @@ int sb2_build_transport(const sb2_grid& g, int64_t P, int64_t PL, int64_t first,
       }
       ++nvar;
     } else if (toks[i].kind == SB2_TOK_FIELD) {
-      if (!operand_values) { err = "membrane transport: field operand values missing"; return SB2_ERR_ARG; }
+      if (!operand_values && npts > 0) { err = "membrane transport: field operand values missing"; return SB2_ERR_ARG; }
       out.tok_operand.push_back(rows++);
       for (int p = 0; p < npts; ++p) {
         near_c.push_back(-1); far_c.push_back(-1);

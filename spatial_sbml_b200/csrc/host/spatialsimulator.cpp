@@ -98,8 +98,20 @@ struct SimImpl {
   std::map<std::string, std::vector<boundaryType> > btMirrors;
   int ownLo, ownHi, heldLo;  // slab rows (global) owned / first row held locally
   long domainCells;
-  SimImpl() : ownedDoc(NULL), dev(NULL), timeSlot(-1), rulesStale(false), ownLo(0), ownHi(0), heldLo(0), domainCells(0) {}
+  // slab with membrane transport: host model of the WHOLE grid (membrane points, their normals and the frame tests of the
+  // reference refer to the whole doubled grid); built on first use, never stepped
+  sb2host::Model* whole;
+  SimImpl() : ownedDoc(NULL), dev(NULL), timeSlot(-1), rulesStale(false), ownLo(0), ownHi(0), heldLo(0), domainCells(0), whole(NULL) {}
+  sb2host::Model* wholeModel(std::string& err) {
+    if (!m.isSlab()) return &m;
+    if (!whole) {
+      whole = new sb2host::Model;
+      if (!whole->build(m.doc, m.gn[0], m.gn[1], m.gn[2], 0, 0)) { err = whole->error; delete whole; whole = NULL; }
+    }
+    return whole;
+  }
   ~SimImpl() {
+    delete whole;
     for (size_t i = 0; i < slabs.size(); ++i) delete slabs[i];
     if (dev) sb2_destroy(dev);
     delete ownedDoc;
@@ -485,7 +497,6 @@ bool SpatialSimulator::buildDevice() {
       toDeviceRefs(x, refs);
       DEV(sb2_add_reaction(impl->dev, dg, 0, toks.data(), (int)toks.size(), refs.data(), (int)refs.size(), x->nReactants));
     } else {
-      if (m.isSlab()) { lastError = "membrane transport is not supported on a sharded grid yet"; return false; }
       if (!addMemTransport(x)) return false;
     }
   }
@@ -724,9 +735,27 @@ bool SpatialSimulator::addMemTransportOn(void* rx, void* memGeo) {
   Rxn* x = static_cast<Rxn*>(rx);
   Geo* mem = static_cast<Geo*>(memGeo);
   sb2host::Model& m = impl->m;
+  // On a slab the membrane comes from the host model of the whole grid (gm): its points, their normals and the volume masks
+  // around them are looked up in whole-grid coordinates, the cells the device is handed are local ones.  A slab evaluates the
+  // points next to the rows it owns and accumulates into owned cells only (the neighbouring slab does the same for its rows;
+  // the two halo rows the operands may reach into are exchanged per stage, sb2_device.cu edge_w).
+  const bool slab = m.isSlab();
+  sb2host::Model* gmp = impl->wholeModel(lastError);
+  if (!gmp) return false;
+  sb2host::Model& gm = *gmp;
+  if (slab) {
+    mem = gm.geoByCompartment(mem->compartmentId);
+    if (!mem) { lastError = "membrane transport '" + x->id + "': the membrane is missing from the whole-grid model"; return false; }
+    for (size_t k = 0; k < x->spRefs.size(); ++k)
+      if (x->spRefs[k] && x->spRefs[k]->onMembrane) { lastError = "reaction '" + x->id + "' binds to a membrane species; not supported on a sharded grid yet"; return false; }
+  }
+  const int slabAxis = m.dimension == 3 ? 2 : 1;
+  const int rowOff = slab ? m.off[slabAxis] : 0;                      // first held row, in rows of the whole grid
+  const int ownLoL = slab ? impl->ownLo - impl->heldLo : 0;           // owned rows, local
+  const int ownHiL = slab ? impl->ownHi - impl->heldLo : (m.dimension == 3 ? m.nz : m.ny);
 
-  const int Xi = m.Xindex, Yi = m.Yindex, Zi = m.Zindex;
-  const int64_t N = m.ndoubled();
+  const int Xi = gm.Xindex, Yi = gm.Yindex, Zi = gm.Zindex;
+  const int64_t N = gm.ndoubled();
   // participating points: listed in domainIndex, off the frame, isDomain == 1
   std::vector<const MemPoint*> pts;
   std::map<int64_t, const MemPoint*> pointOf;
@@ -738,16 +767,36 @@ bool SpatialSimulator::addMemTransportOn(void* rx, void* memGeo) {
     if (m.dimension == 2 && (X == 0 || Y == 0 || X == Xi - 1 || Y == Yi - 1)) continue;
     std::map<int64_t, const MemPoint*>::const_iterator it = pointOf.find(idx);
     if (it == pointOf.end()) continue;  // isDomain[index] != 1
+    if (slab) {
+      // the cells a point feeds lie at +-1 along its axis: doubled rows 2 * (ownLo + heldLo) - 1 ... 2 * (ownHi + heldLo - 1) + 1
+      const int R = slabAxis == 2 ? Z : Y;
+      if (R < 2 * (ownLoL + rowOff) - 1 || R > 2 * (ownHiL + rowOff - 1) + 1) continue;
+    }
     pts.push_back(it->second);
   }
   const int npts = (int)pts.size();
-  // compact cell of a doubled-grid point, -1 unless it is a volume cell of `geo`
+  // compact LOCAL cell of a doubled-grid point of the whole grid, -1 unless it is a volume cell of `geo` that is held locally
   auto cellIn = [&](Geo* geo, int X, int Y, int Z) -> int32_t {
     if (!geo || !geo->isVol || !geo->hasMask) return -1;
     if (X < 0 || Y < 0 || Z < 0 || X >= Xi || Y >= Yi || Z >= Zi) return -1;
     if ((X | Y | Z) & 1) return -1;
-    const int64_t c = ((int64_t)(Z / 2) * m.ny + Y / 2) * m.nx + X / 2;
-    return geo->isDomain[c] == 1 ? (int32_t)c : -1;
+    if (!slab) {
+      const int64_t c = ((int64_t)(Z / 2) * m.ny + Y / 2) * m.nx + X / 2;
+      return geo->isDomain[c] == 1 ? (int32_t)c : -1;
+    }
+    Geo* wg = gm.geoByCompartment(geo->compartmentId);
+    if (!wg || !wg->hasMask) return -1;
+    const int64_t cw = ((int64_t)(Z / 2) * gm.ny + Y / 2) * gm.nx + X / 2;
+    if (wg->isDomain[cw] != 1) return -1;
+    const int lj = Y / 2 - (slabAxis == 1 ? rowOff : 0), lk = Z / 2 - (slabAxis == 2 ? rowOff : 0);
+    if (lj < 0 || lj >= m.ny || lk < 0 || lk >= m.nz) return -1;
+    return (int32_t)(((int64_t)lk * m.ny + lj) * m.nx + X / 2);
+  };
+  // a target cell must be OWNED by this slab (halo cells receive their increments from the slab that owns them)
+  auto ownedCell = [&](int32_t c) -> int32_t {
+    if (!slab || c < 0) return c;
+    const int row = slabAxis == 2 ? (int)(c / ((int64_t)m.nx * m.ny)) : (int)((c / m.nx) % m.ny);
+    return (row >= ownLoL && row < ownHiL) ? c : -1;
   };
 
   std::vector<sb2_token> toks;
@@ -803,7 +852,7 @@ bool SpatialSimulator::addMemTransportOn(void* rx, void* memGeo) {
       d.kind = SB2_TOK_FIELD; d.slot = 0;
       for (int p = 0; p < npts; ++p) {
         const MemPoint& mp = *pts[p];
-        operandValues.push_back(m.valueAtDoubled(t.var, mp.X, mp.Y, mp.Z));
+        operandValues.push_back(gm.valueAtDoubled(slab ? gm.findVar(t.var->id) : t.var, mp.X, mp.Y, mp.Z));
       }
     }
     toks.push_back(d);
@@ -837,8 +886,8 @@ bool SpatialSimulator::addMemTransportOn(void* rx, void* memGeo) {
         targets.push_back(-1);
         continue;
       }
-      targets.push_back(ok ? cellIn(v->geo, mp.X + dx, mp.Y + dy, mp.Z + dz) : -1);
-      targets.push_back(ok ? cellIn(v->geo, mp.X - dx, mp.Y - dy, mp.Z - dz) : -1);
+      targets.push_back(ok ? ownedCell(cellIn(v->geo, mp.X + dx, mp.Y + dy, mp.Z + dz)) : -1);
+      targets.push_back(ok ? ownedCell(cellIn(v->geo, mp.X - dx, mp.Y - dy, mp.Z - dz)) : -1);
     }
   }
   int rc = sb2_add_mem_transport(impl->dev, toks.data(), (int)toks.size(), refs.data(), (int)refs.size(), x->nReactants,

@@ -103,6 +103,21 @@ def test_slabs_with_advection(nslabs):
         assert np.abs(got - ref).max() <= 1e-10 * max(np.abs(ref).max(), 1e-300), sp
 
 
+@pytest.mark.parametrize("case", ["transport", "transport_rate", "syn_transport_mixed_2d", "syn_sampled_2d"])
+@pytest.mark.parametrize("nslabs", [2, 3, 5])
+def test_slabs_with_membrane_transport(case, nslabs):
+    """calcMemTransport on slabs: every slab evaluates the membrane points next to its rows (taken from a host model of the whole
+    grid: the reference's frame tests and normals refer to the whole doubled grid), reads operands up to two rows into its halo
+    (k rows travel two deep per stage) and accumulates into the cells it owns."""
+    g = load_golden(case)
+    dims = tuple(int(v) for v in g["dims"])
+    species = [str(s) for s in g["species"]]
+    out = _run_pair(model_path(case), dims, float(g["dt"]), 10, species, [0] * nslabs, from_file=True)
+    for sp, got in zip(species, out):
+        ref = g["step/10/" + sp]
+        assert np.abs(got - ref).max() <= 1e-10 * max(np.abs(ref).max(), 1e-300), sp
+
+
 def test_group_accessors():
     """setVariableCompact / getVariableCompact / getVariable / getVariableAt / setParameter / getStableTimeStep on a grid held
     by several slabs behave like on one device."""
@@ -186,7 +201,7 @@ def test_group_host_step_falls_back_for_unfused_models():
     many.close()
 
 
-@pytest.mark.parametrize("dim", ["2", "3", "bc", "adv", "host2", "host3"])
+@pytest.mark.parametrize("dim", ["2", "3", "bc", "adv", "mt", "host2", "host3"])
 def test_nccl_sharded_step_is_bit_identical(dim):
     import torch
     n = torch.cuda.device_count()
@@ -194,7 +209,7 @@ def test_nccl_sharded_step_is_bit_identical(dim):
         pytest.skip("the NCCL path needs at least two GPUs (the same slab logic runs on one GPU in the tests above)")
     world = 2
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
-           "--master-port", str(29500 + ["2", "3", "bc", "adv", "host2", "host3"].index(dim)), os.path.join(REPO, "tools", "sharded_check.py"), dim, "12"]
+           "--master-port", str(29500 + ["2", "3", "bc", "adv", "mt", "host2", "host3"].index(dim)), os.path.join(REPO, "tools", "sharded_check.py"), dim, "12"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "BIT-IDENTICAL" in r.stdout

@@ -1,5 +1,5 @@
 """Run under torchrun (one rank per GPU): the slab-sharded step over NCCL must be BIT-IDENTICAL to the single-GPU step
-(no reduction inside the step).  usage: torchrun --nproc-per-node N tools/sharded_check.py [2|3|bc|adv|host2|host3] [steps]
+(no reduction inside the step).  usage: torchrun --nproc-per-node N tools/sharded_check.py [2|3|bc|adv|mt|host2|host3] [steps]
 host2 / host3: the steps go through ShardedSimulator.step_host (host arrays in and out every step, one exchange of edge rows per step),
 with a plain sharded step in between (which first refreshes the halo rows the host step left unexchanged)."""
 import os
@@ -33,6 +33,10 @@ elif what == "3":
 elif what == "bc":
     dim, dims = 2, (128, 24 * world + 3, 1)
     model, dt = synthetic.turing_bc(dims[0], dims[1]), 0.05
+elif what == "mt":  # membrane transport with reactions around it
+    dim, dims = 2, (40, 36, 1)
+    model, dt = open(os.path.join(REPO, "tests", "golden", "models", "syn_transport_mixed_2d.xml")).read(), 0.05
+    names = ("A", "E")
 else:  # the reference's advection example
     dim, dims = 2, (101, 101, 1)
     model, dt = open(os.path.join(REPO, "tests", "golden", "models", "advection.xml")).read(), 0.05
