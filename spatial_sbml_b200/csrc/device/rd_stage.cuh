@@ -1206,6 +1206,8 @@ cudaError_t launch_variant(const Sb2RdArgs& a, cudaStream_t stream) {
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(rd_stage_kernel<NS, NP, W, MODE, DEPTH, MINB, D3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    // one shared-memory carve-out for all stage kernels: no SM reconfiguration between consecutive launches (see rd_jit.cu)
+    cudaFuncSetAttribute(rd_stage_kernel<NS, NP, W, MODE, DEPTH, MINB, D3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = smem;
   }
   if (grid.y == 0 || grid.z == 0) return cudaSuccess;
