@@ -514,20 +514,25 @@ def turing_dirichlet3d(nx, ny, nz):
     return turing(nx, ny, nz, bc_values=bc)
 
 
-def advection_field(nx, ny, uniform=False):
+def advection_field(nx, ny, uniform=False, nz=None):
     """CIP-CSLR advection (cipCSLR, calcPDE.cpp:564-869) of two species in a box with velocities that are FIELDS — a shear flow
     u_x = 0.6 + 0.02 y, u_y = -0.4 + 0.015 x for P (positive and negative components) and a rotation-like field for Q — so
     that the face-averaged velocity (:612-613) and the divergence correction of the face values (:623-625) are live; a little
-    diffusion and a decay reaction run beside it.  uniform=True: constant velocities (the large-grid advection benchmark).  dt 0.05."""
-    axes, dims = ["x", "y"], [nx, ny]
-    kinds = {"x": "cartesianX", "y": "cartesianY"}
+    diffusion and a decay reaction run beside it.  uniform=True: constant velocities (the large-grid advection benchmark).
+    nz: the same in 3-D (a z component of either sign, the Z pass of the dimension split).  dt 0.05."""
+    dims = [nx, ny] + ([nz] if nz else [])
+    axes = ["x", "y", "z"][:len(dims)]
+    kinds = {"x": "cartesianX", "y": "cartesianY", "z": "cartesianZ"}
     params = _transport_params("P", 0.05, axes) + _transport_params("Q", 0.02, axes)
-    ia = [("P", _apply("plus", _cn(0.2), _apply("times", _cn(2.0), _apply("exp", _apply("minus", _apply("times", _cn(0.02), _apply(
-              "plus", _apply("power", _apply("minus", _ci("x"), _cn(0.35 * (nx - 1))), _cn(2)),
-              _apply("power", _apply("minus", _ci("y"), _cn(0.55 * (ny - 1))), _cn(2))))))))),
-          ("Q", _piecewise(_cn(3.0), _apply("and", _apply("gt", _ci("x"), _cn(0.5 * (nx - 1))), _apply("lt", _ci("x"), _cn(0.7 * (nx - 1))),
-                                            _apply("gt", _ci("y"), _cn(0.2 * (ny - 1))), _apply("lt", _ci("y"), _cn(0.45 * (ny - 1)))), _cn(0.5)))]
+    blob = [_apply("power", _apply("minus", _ci(a), _cn(f * (n - 1))), _cn(2)) for a, n, f in zip(axes, dims, (0.35, 0.55, 0.45))]
+    box = []
+    for a, n, (lo, hi) in zip(axes, dims, ((0.5, 0.7), (0.2, 0.45), (0.3, 0.8))):
+        box += [_apply("gt", _ci(a), _cn(lo * (n - 1))), _apply("lt", _ci(a), _cn(hi * (n - 1)))]
+    ia = [("P", _apply("plus", _cn(0.2), _apply("times", _cn(2.0), _apply("exp", _apply("minus", _apply("times", _cn(0.02), _apply("plus", *blob))))))),
+          ("Q", _piecewise(_cn(3.0), _apply("and", *box), _cn(0.5)))]
     vel = {("P", "x"): (0.6, 0.02, "y"), ("P", "y"): (-0.4, 0.015, "x"), ("Q", "x"): (0.3, -0.02, "y"), ("Q", "y"): (-0.25, 0.02, "x")}
+    if nz:
+        vel.update({("P", "z"): (-0.5, 0.01, "x"), ("Q", "z"): (0.35, -0.015, "y")})
     for (sp_, a), (c0, c1, dep) in sorted(vel.items()):
         pid = "%s_adv_%s" % (sp_, a)
         inner = '<spatial:advectionCoefficient spatial:variable="%s" spatial:coordinate="%s"/>' % (sp_, kinds[a])
@@ -543,3 +548,11 @@ def advection_field(nx, ny, uniform=False):
 
 def advection_uniform(nx, ny):
     return advection_field(nx, ny, uniform=True)
+
+
+def advection_uniform3d(nx, ny, nz):
+    return advection_field(nx, ny, uniform=True, nz=nz)
+
+
+def advection_field3d(nx, ny, nz):
+    return advection_field(nx, ny, uniform=False, nz=nz)

@@ -77,6 +77,8 @@ CASES = {
     "syn_turing_3d_dirichlet": ("synthetic:turing_dirichlet3d:18:14:10", (18, 14, 10), 0.02, [1, 2, 10, 40], {}, []),
     # advection with velocities that are fields (face-averaged velocity, divergence correction) / the same flow with constants
     "syn_advection_field_2d": ("synthetic:advection_field:44:36", (44, 36, 1), 0.05, [1, 2, 10, 100], {}, ["P", "Q"]),
+    "syn_advection_uniform_3d": ("synthetic:advection_uniform3d:18:14:12", (18, 14, 12), 0.05, [1, 2, 10, 40], {}, ["P", "Q"]),
+    "syn_advection_field_3d": ("synthetic:advection_field3d:18:14:12", (18, 14, 12), 0.05, [1, 2, 10, 40], {}, ["P", "Q"]),
     "syn_advection_uniform_2d": ("synthetic:advection_uniform:44:36", (44, 36, 1), 0.05, [1, 10, 100], {}, ["P", "Q"]),
     # assignment rules re-evaluated after every step (time-, position- and species-dependent fields, a species defined by a rule)
     "syn_rules_2d": ("synthetic:rules:30:26", (30, 26, 1), 0.05, [1, 2, 10, 100], {}, []),
@@ -217,6 +219,8 @@ def build_case(name):
                 v = full.reshape(Zi, Yi, Xi)
                 out["step/%d/%s/faceX" % (s, sp)] = np.ascontiguousarray(v[::2, ::2, 1::2])
                 out["step/%d/%s/faceY" % (s, sp)] = np.ascontiguousarray(v[::2, 1::2, ::2])
+                if Zi > 1:
+                    out["step/%d/%s/faceZ" % (s, sp)] = np.ascontiguousarray(v[1::2, ::2, ::2])
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
     os.remove(sbd)
     print("%-22s dims %s species %s -> %.0f kB" % (name, dims, species, os.path.getsize(os.path.join(HERE, name + ".npz")) / 1e3))

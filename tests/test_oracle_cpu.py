@@ -36,7 +36,7 @@ RESTATED = {"turing_tiny": 1000, "turing_tiny_cl": 100, "turing_uniform": 100, "
             "syn_raterules_2d": 100,
             # geometry from an image + a membrane transport; six species
             "syn_sampled_2d": 100, "syn_chain6_2d": 100,
-            "syn_advection_uniform_2d": 100}
+            "syn_advection_uniform_2d": 100, "syn_advection_uniform_3d": 40}
 
 
 def build(case):
@@ -75,7 +75,7 @@ NOT_RESTATED = {"syn_membrane_2d", "syn_membrane_box_2d", "syn_membrane_3d", "sy
                 # field-valued diffusion coefficients (the restatement takes uniform coefficients only)
                 "syn_fieldcoeff_2d", "syn_fieldcoeff_3d",
                 # field-valued advection velocities
-                "syn_advection_field_2d"}
+                "syn_advection_field_2d", "syn_advection_field_3d"}
 
 
 def test_every_golden_case_is_restated():

@@ -90,6 +90,20 @@ def test_slabs_golden_models_with_boundary_conditions(case, nslabs):
         assert np.abs(got - ref).max() <= 1e-10 * max(np.abs(ref).max(), 1e-300), sp
 
 
+@pytest.mark.parametrize("case", ["syn_advection_uniform_3d", "syn_advection_field_3d", "syn_advection_field_2d"])
+@pytest.mark.parametrize("nslabs", [2, 3])
+def test_slabs_with_advection_more_models(case, nslabs):
+    """z-slabs of a 3-D grid (three direction passes per species, two halo planes of u and of the three face arrays) and
+    field-valued velocities on slabs"""
+    g = load_golden(case)
+    dims = tuple(int(v) for v in g["dims"])
+    species = [str(s) for s in g["species"]]
+    out = _run_pair(model_path(case), dims, float(g["dt"]), 10, species, [0] * nslabs, from_file=True)
+    for sp, got in zip(species, out):
+        ref = g["step/10/" + sp]
+        assert np.abs(got - ref).max() <= 1e-10 * max(np.abs(ref).max(), 1e-300), sp
+
+
 @pytest.mark.parametrize("nslabs", [2, 3, 4])
 def test_slabs_with_advection(nslabs):
     """CIP-CSLR advection on slabs: two halo rows of u and of the face values, exchanged after every direction pass; the golden
