@@ -294,6 +294,11 @@ typedef struct sb2_exchange_s {
   void* ready_event;         /* cudaEvent_t recorded when the rows to send are final (for callers that PULL from a neighbour) */
   int32_t device;
 } sb2_exchange;
+/* Apron schedule (before the first sharded step; every slab of a grid alike): models on the fused schedule exchange the four
+ * edge rows of u ONCE per step and recompute the apron rows that reach into the halo, instead of exchanging after every stage:
+ * one exchange and six launches per step instead of four and twelve.  Needs four halo rows on the sides with a neighbour and
+ * at least eight owned rows per slab; other models keep the per-stage exchanges.  Bit-identical results either way. */
+SB2_API int sb2_sharded_set_apron(sb2_sim* sim, int on);
 SB2_API int sb2_sharded_begin(sb2_sim* sim, double t_arg, double dt, int time_slot);
 SB2_API int sb2_sharded_next(sb2_sim* sim, sb2_exchange* x);
 /* One step of n slabs held by ONE process (handles on the same or on different devices; sims[i] lies below sims[i+1]): the

@@ -89,6 +89,7 @@ def _proto(lib):
         "sb2_step_host": (ci, [vp, cd, cd, ci, C.POINTER(dp), C.POINTER(dp), ci]),
         "sb2_step_host_begin": (ci, [vp, cd, cd, ci, C.POINTER(dp), ci, vp]),
         "sb2_step_host_finish": (ci, [vp, C.POINTER(dp)]),
+        "sb2_sharded_set_apron": (ci, [vp, ci]),
         "sb2_group_step_host": (ci, [C.POINTER(vp), ci, cd, cd, ci, C.POINTER(C.POINTER(dp)), C.POINTER(C.POINTER(dp)), ci]),
         "sb2_download_species": (ci, [vp, ci, dp]),
         "sb2_upload_species": (ci, [vp, ci, dp]),

@@ -69,6 +69,7 @@ struct sb2_sim {
   int host_nslabs;       // sb2_step_host_begin / _finish: sub-slabs of the step in flight
   bool host_exchange;    // ... and whether the caller was handed an exchange of the edge rows
   bool halo_stale;       // slab: the halo rows of u were not refreshed after the last step (sb2_step_host_finish)
+  bool sh_apron;         // slab: sharded steps exchange four rows of u once and recompute the apron rows (sb2_sharded_set_apron)
   bool sh_awaiting, sh_comm_valid, sh_first_stage;
   bool finalized, any_adv;
   bool fuse_combine;    // this step: RK combine fused into stage 4
@@ -679,7 +680,7 @@ int sb2_create(const sb2_grid* grid, sb2_sim** out) {
   sim->edge_w = 1; sim->end_w = 1;
   sim->sh_edge = NULL; sim->sh_comm = NULL;
   sim->ev_edge = sim->ev_interior = sim->ev_comm = sim->ev_ready = sim->ev_pulled = NULL;
-  sim->host_nslabs = 0; sim->host_exchange = false; sim->halo_stale = false;
+  sim->host_nslabs = 0; sim->host_exchange = false; sim->halo_stale = false; sim->sh_apron = false;
   sim->sh_phase = -1; sim->sh_passes = 0; sim->sh_awaiting = false; sim->sh_comm_valid = false; sim->sh_first_stage = true;
   *out = sim;
   return SB2_OK;
@@ -1498,6 +1499,25 @@ void fill_exchange(sb2_sim* sim, sb2_exchange* x, const std::vector<double*>& bu
 }
 }  // namespace
 
+// The schedule on which a step is four stage kernels and nothing else (the RK combine fused into the last one): no advection,
+// membrane transport, membrane species, Dirichlet or non-zero flux conditions, per-step rules.  Known after sb2_begin_step.
+static bool step_is_fused_only(const sb2_sim* sim) {
+  return sim->fuse_combine && sim->transports.empty() && sim->blists[0].n_dirichlet == 0 && !sim->model_dirichlet && sim->mem_species.empty() &&
+         sim->cell_rules.empty();
+}
+
+// Sharded steps of a slab on the fused schedule can trade the exchange per stage for redundant work: the four edge rows of u
+// travel ONCE per step (behind the part of stage 1 that needs no halo), stage m then runs on rows [own_lo - 3 + m, own_hi + 3 - m)
+// - the apron rows reach into the four halo rows and are recomputed on both sides.  One exchange and six launches per step
+// instead of four exchanges and twelve launches, which is what strong scaling (short slabs) and callers with an expensive
+// exchange need; the result is the same step bit for bit.  Every slab of a grid must be set alike (the caller knows all of them:
+// sharded.py, SpatialSimulator::setDevices); models off the fused schedule keep the per-stage exchanges whatever is set here.
+int sb2_sharded_set_apron(sb2_sim* sim, int on) {
+  if (!sim) return SB2_ERR_ARG;
+  sim->sh_apron = on != 0;
+  return SB2_OK;
+}
+
 int sb2_sharded_begin(sb2_sim* sim, double t_arg, double dt, int time_slot) {
   if (!sim || !sim->finalized) return fail(sim, SB2_ERR_STATE, "simulator not finalized");
   if (sim->in_step) return fail(sim, SB2_ERR_STATE, "sb2_sharded_begin inside a step");
@@ -1529,6 +1549,41 @@ int sb2_sharded_next(sb2_sim* sim, sb2_exchange* x) {
     sim->sh_awaiting = false;
   }
   int rc;
+  if (sim->sh_apron && step_is_fused_only(sim) && sim->sh_phase >= 0 && sim->sh_phase <= 1) {
+    const SlabRows r = slab_rows(sim);
+    const bool has_lo = r.own_lo > 0, has_hi = r.own_hi < r.n_held;
+    if ((has_lo && r.own_lo < 4) || (has_hi && r.n_held - r.own_hi < 4) || r.own_hi - r.own_lo < 8)
+      return fail(sim, SB2_ERR_STATE, "the apron schedule needs four halo rows on either side and at least eight owned rows");
+    if (sim->sh_phase == 0) {
+      // the four edge rows of the current u go to the neighbours (halo rows a host step or an upload left stale are covered too)
+      std::vector<double*> bufs;
+      for (size_t s = 0; s < S; ++s) bufs.push_back(sim->species[s].u[sim->species[s].cur]);
+      CK(cudaEventRecord(sim->ev_ready, compute));
+      CK(cudaStreamWaitEvent(sim->sh_comm, sim->ev_ready, 0));
+      fill_exchange(sim, x, bufs, 4);
+      sim->halo_stale = false;
+      sim->sh_awaiting = true;
+      sim->sh_phase = 1;
+      if (has_lo || has_hi) return 1;
+      sim->sh_awaiting = false;  // a slab without neighbours: nothing travels
+    }
+    const double dt = sim->cur_dt;
+    // stage 1: the rows that read no halo row run beside the exchange, the rows around the edges once it has landed
+    const int bi = has_lo ? r.own_lo + 1 : r.own_lo, ei = has_hi ? r.own_hi - 1 : r.own_hi;
+    if ((rc = launch_stage_rows(sim, 0, dt, bi, ei))) return rc;
+    if (sim->sh_comm_valid) CK(cudaStreamWaitEvent(compute, sim->ev_comm, 0));
+    if (has_lo && (rc = launch_stage_rows(sim, 0, dt, r.own_lo - 3, bi))) return rc;
+    if (has_hi && (rc = launch_stage_rows(sim, 0, dt, ei, r.own_hi + 3))) return rc;
+    for (int m = 1; m < 4; ++m)
+      if ((rc = launch_stage_rows(sim, m, dt, has_lo ? r.own_lo - (3 - m) : r.own_lo, has_hi ? r.own_hi + (3 - m) : r.own_hi))) return rc;
+    for (size_t s = 0; s < S; ++s) sim->species[s].cur ^= 1;
+    sim->k0_carry_valid = false;
+    sim->in_step = false;
+    sim->sh_comm_valid = false;  // (the halo rows of the new u are exchanged by the next step, whichever kind it is)
+    sim->halo_stale = true;
+    sim->sh_phase = -1;
+    return 0;
+  }
   if (sim->halo_stale && sim->sh_phase == 0) {
     // the last step came through sb2_step_host_finish, which leaves the halo rows of the new u unexchanged: refresh them first
     std::vector<double*> bufs;

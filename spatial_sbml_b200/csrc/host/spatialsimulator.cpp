@@ -256,6 +256,12 @@ bool SpatialSimulator::buildSlabs(SBMLDocument* doc, int xdim, int ydim, int zdi
   }
   impl->domainCells = 0;
   for (int i = 0; i < G; ++i) impl->domainCells += impl->slabs[i]->getNumDomainCells();
+  // slabs of eight rows or more: one exchange of four rows of u per step, apron rows recomputed (sb2_sharded_set_apron; models off
+  // the fused schedule keep the exchange per stage)
+  int minRows = n;
+  for (int i = 0; i < G; ++i) minRows = std::min(minRows, impl->slabRows[i].second - impl->slabRows[i].first);
+  if (minRows >= 8 && !getenv("SB2_NO_APRON"))
+    for (int i = 0; i < G; ++i) sb2_sharded_set_apron(impl->slabs[i]->impl->dev, 1);
   return true;
 }
 

@@ -14,6 +14,7 @@ The exchange itself (`exchange_rows`) works on any torch tensors, which is what 
 gloo tests exercise on CPU.
 """
 import ctypes as C
+import os
 
 import torch
 import torch.distributed as dist
@@ -86,6 +87,12 @@ class ShardedSimulator(object):
         self.own_lo = self.lo - self.held_lo
         self.own_hi = self.hi - self.held_lo
         self.time_slot = self.sim.getTimeSlot()  # sim_time = stepIndex * dt reaches the kinetic laws through this constant
+        # every rank knows every slab's size (they differ by at most one row): with eight rows or more per slab the library
+        # exchanges four rows of u once per step and recomputes the apron rows, instead of exchanging after every stage
+        # (models off the fused schedule keep the per-stage exchanges); SB2_NO_APRON=1 keeps them for every model
+        self.apron = self.world > 1 and n // self.world >= 8 and not os.environ.get("SB2_NO_APRON")
+        if self.apron:
+            self.lib.sb2_sharded_set_apron(self.h, 1)
         self._x = Exchange()
         self._streams = {}
         self._views = {}
