@@ -506,6 +506,9 @@ Sb2RdJitSpec jit_spec(const sb2_sim* sim) {
   Sb2RdJitSpec spec;
   spec.ns = sim->base.S; spec.np = sim->rd.np; spec.w = sim->rd.w; spec.depth = sim->base.depth; spec.d3 = sim->g.dim == 3;
   spec.minb = 2; spec.np_final = 0; spec.minb_final = 0; spec.final_ldg = 0;
+  // large 2-D grids: the first stage (no k rows) at three CTAs per SM; small grids are bound by latency and lose a microsecond
+  // per step to the tighter register budget
+  spec.minb_first = (!spec.d3 && spec.ns <= 2 && spec.w == 8 && ncells(sim) >= (1 << 20)) ? 3 : 0;
   if (spec.d3 && spec.w == 8 && spec.np == 1) {
     // 3-D (the class map has 64-cell granularity, so the strip width is free per stage).  Last stage: 2 cells per
     // thread, 74-80 registers, three CTAs per SM (deep expression stacks keep the room of two).  Other stages, up to
@@ -2179,7 +2182,7 @@ int sb2_specialize_dry_run(const uint32_t* code, const uint32_t* arg, int n, int
   for (int i = 0; i < n; ++i) { prog[i].code = code[i]; prog[i].arg = arg[i]; prog[i].c = 0.0; }
   Sb2RdJitSpec spec;
   spec.ns = ns; spec.np = np; spec.w = w; spec.depth = depth; spec.minb = minb; spec.d3 = d3;
-  spec.np_final = 0; spec.minb_final = 0; spec.final_ldg = 0;
+  spec.np_final = 0; spec.minb_final = 0; spec.final_ldg = 0; spec.minb_first = 0;
   // a typical model: one geometry, every species diffuses with uniform coefficients
   spec.fold = 1; spec.G = 1; spec.hasdiff_mask = spec.fastpath_mask = (1u << ns) - 1u; spec.geo_bits = 0;
   std::vector<char> cubin;

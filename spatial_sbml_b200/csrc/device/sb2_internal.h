@@ -163,6 +163,7 @@ cudaError_t sb2_rd_classify(const uint8_t* const* flags, int G, int nx, int ny, 
 // model-specialised rd_stage kernels built at run time (rd_jit.cu)
 struct Sb2RdJitSpec {
   int ns, np, w, depth, minb, d3;
+  int minb_first;            // CTAs per SM the first-stage kernel is built for (0: like the others)
   int np_final, minb_final;  // the last stage may use a narrower strip (3-D: it also holds the k0 / k1 rows); 0: like the others
   int final_ldg;             // 3-D last stage: k0 / k1 are read with plain loads instead of bulk copies into shared-memory slots
   // model constants folded into the build when fold != 0: geometries, bit s of the masks = species s diffuses / takes the

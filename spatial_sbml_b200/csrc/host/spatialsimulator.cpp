@@ -260,7 +260,8 @@ bool SpatialSimulator::buildSlabs(SBMLDocument* doc, int xdim, int ydim, int zdi
   // the fused schedule keep the exchange per stage)
   int minRows = n;
   for (int i = 0; i < G; ++i) minRows = std::min(minRows, impl->slabRows[i].second - impl->slabRows[i].first);
-  if (minRows >= 8 && !getenv("SB2_NO_APRON"))
+  // (2-D grids only: in 3-D the apron is twelve whole planes per slab and step, measured slower than the exchanges it saves)
+  if (minRows >= 8 && !getenv("SB2_NO_APRON") && (impl->m.dimension == 2 || getenv("SB2_APRON")))
     for (int i = 0; i < G; ++i) sb2_sharded_set_apron(impl->slabs[i]->impl->dev, 1);
   return true;
 }

@@ -90,7 +90,8 @@ class ShardedSimulator(object):
         # every rank knows every slab's size (they differ by at most one row): with eight rows or more per slab the library
         # exchanges four rows of u once per step and recomputes the apron rows, instead of exchanging after every stage
         # (models off the fused schedule keep the per-stage exchanges); SB2_NO_APRON=1 keeps them for every model
-        self.apron = self.world > 1 and n // self.world >= 8 and not os.environ.get("SB2_NO_APRON")
+        # (2-D grids: in 3-D the apron is twelve whole planes per slab and step, measured slower than the exchanges it saves)
+        self.apron = self.world > 1 and n // self.world >= 8 and not os.environ.get("SB2_NO_APRON") and (dim == 2 or bool(os.environ.get("SB2_APRON")))
         if self.apron:
             self.lib.sb2_sharded_set_apron(self.h, 1)
         self._x = Exchange()

@@ -47,11 +47,12 @@ def _run_pair(model, dims, dt, steps, species, devices, jit=None, monkeypatch=No
 
 @pytest.mark.parametrize("nslabs", [2, 3])
 @pytest.mark.parametrize("d3", [False, True])
-def test_slabs_with_an_exchange_per_stage(nslabs, d3, monkeypatch):
+def test_slabs_on_the_other_sharded_schedule(nslabs, d3, monkeypatch):
     """Slabs of eight rows or more exchange once per step and recompute the apron rows (sb2_sharded_set_apron; the tests below);
     SB2_NO_APRON keeps the schedule with an exchange after every stage, which thin slabs and unfused models always take."""
     from spatial_sbml_b200 import synthetic
-    monkeypatch.setenv("SB2_NO_APRON", "1")
+    # 2-D grids take the apron schedule by default, 3-D grids the exchange per stage: run the other one here
+    monkeypatch.setenv("SB2_APRON" if d3 else "SB2_NO_APRON", "1")
     dims = (140, 24, 9 * nslabs + 2) if d3 else (300, 50 * nslabs + 7, 1)
     model = synthetic.turing(*dims) if d3 else synthetic.turing(dims[0], dims[1])
     _run_pair(model, dims, 0.02 if d3 else 0.07, 8, ("species_1", "species_2"), [0] * nslabs)
