@@ -41,15 +41,21 @@ __global__ void __launch_bounds__(256) classify_kernel(const uint8_t* f0, const 
 }
 }  // namespace
 
-int sb2_rd_pick_variant(int dim, int nx, int nspecies, int depth, Sb2RdVariant* out) {
+int sb2_rd_pick_variant(int dim, int nx, int nspecies, int depth, Sb2RdVariant* out, int64_t ncells) {
   if ((dim != 2 && dim != 3) || nspecies < 1 || nspecies > 4) return -1;
   int id;
   if (dim == 3) {
     // the z-marching kernel keeps three plane tiles of W + 2 rows in shared memory: 8 warps and 2 cells per thread leave
     // room for three CTAs per SM with two species
     id = nspecies <= 2 ? 2 : 6;
-  } else if (nspecies <= 2) id = (depth <= 4 && nx >= 192) ? 1 : 2;  // (measured at 8192^2: variant 1 beats 0 and 5)
-  else id = (depth <= 4 && nx >= 192) ? 3 : 4;
+  } else {
+    // four cells per thread on wide grids (measured at 8192^2: variant 1 beats 0 and 5).  Grids of up to 2^18 cells are bound by
+    // the latency of a warp's instruction stream, not by throughput: two cells per thread there (301^2 Brusselator: 16.4 ->
+    // 14.4 us per step)
+    const bool wide = depth <= 4 && nx >= 192 && (ncells <= 0 || ncells > ((int64_t)1 << 18));
+    if (nspecies <= 2) id = wide ? 1 : 2;
+    else id = wide ? 3 : 4;
+  }
   const char* force = getenv("SB2_RD_VARIANT");  // experiments: force a variant that fits the model
   if (force && atoi(force) >= 0 && atoi(force) < kNumVariants && kVariants[atoi(force)].ns >= nspecies) id = atoi(force);
   if (depth > kVariants[id].depth) return -1;

@@ -1102,7 +1102,7 @@ int sb2_finalize(sb2_sim* sim) {
   // 2-D models with up to four staged species run the rd_stage kernel; SB2_STAGE_KERNEL=gen1 forces the
   // first-generation kernel (kept for 3-D grids and more species, and as a cross-check in the tests)
   const char* force = getenv("SB2_STAGE_KERNEL");
-  sim->rd_id = (force && !strcmp(force, "gen1")) ? -1 : sb2_rd_pick_variant(sim->g.dim, sim->g.nx, b.S, b.depth, &sim->rd);
+  sim->rd_id = (force && !strcmp(force, "gen1")) ? -1 : sb2_rd_pick_variant(sim->g.dim, sim->g.nx, b.S, b.depth, &sim->rd, ncells(sim));
   if (sim->rd_id >= 0) {
     if (const char* ge = getenv("SB2_RD_GEOM")) {  // experiments with the specialised kernel only: "np,w" (no prebuilt kernel has this shape)
       int np = 0, w = 0;

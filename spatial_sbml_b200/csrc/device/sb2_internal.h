@@ -154,7 +154,7 @@ static inline void sb2_rd_launch_config(cudaLaunchConfig_t* cfg, cudaLaunchAttri
 // rd_stage kernel family (rd_stage.cuh, instantiated in rd_stage_ns*.cu)
 struct Sb2RdVariant { int id, ns, np, w, depth; };
 // picks the variant for a 2-D model (returns id or -1 when only the first-generation kernel applies)
-int sb2_rd_pick_variant(int dim, int nx, int nspecies, int depth, Sb2RdVariant* out);
+int sb2_rd_pick_variant(int dim, int nx, int nspecies, int depth, Sb2RdVariant* out, int64_t ncells = 0);
 cudaError_t sb2_rd_launch(const Sb2RdArgs& a, cudaStream_t stream);
 // class map: cls[(z * ny + y) * nstrips + strip] for strips of sw cells, every held row of every held plane
 cudaError_t sb2_rd_classify(const uint8_t* const* flags, int G, int nx, int ny, int nz, int64_t P, int64_t PL, int64_t first,
