@@ -819,12 +819,12 @@ struct MtEvalArgs {
   double consts[SB2_MAX_CONSTS];
 };
 
-// interpreter of calcMemTransport (calcPDE.cpp:1084-1393), one membrane point per thread
-__global__ void __launch_bounds__(128) mt_eval_kernel(const __grid_constant__ MtEvalArgs A) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= A.npts) return;
+// interpreter of calcMemTransport (calcPDE.cpp:1084-1393): the rate at membrane point p
+__device__ __noinline__ double mt_rate(const MtEvalArgs& A, const int p) {
   double st[50];
-  for (int i = 0; i < 50; ++i) st[i] = 0.0;
+  // (the stack never grows beyond the number of tokens: only that part has to read as zero)
+  const int ninit = A.ntoks + 2 < 50 ? A.ntoks + 2 : 50;
+  for (int i = 0; i < ninit; ++i) st[i] = 0.0;
   int sp = 0;
   for (int i = 0; i < A.ntoks; ++i) {
     const uint32_t t = A.tok[i];
@@ -875,7 +875,7 @@ __global__ void __launch_bounds__(128) mt_eval_kernel(const __grid_constant__ Mt
   // "if (st_index > 1) st_index--;" then the rate is rpStack[st_index] (calcPDE.cpp:1392-1393): with the
   // normal final depth 1 this reads slot 1 — the right operand of the last binary operator
   if (sp > 1) --sp;
-  A.rate[p] = st[sp];
+  return st[sp];
 }
 
 struct MtApplyArgs {
@@ -887,20 +887,22 @@ struct MtApplyArgs {
   const double* entry_coef;
   const double* entry_delta;
   const int32_t* entry_sign;
-  const double* rate;
+  const uint8_t* group_first;  // NULL: every group accumulates on top of what its cell holds
   double* kout[SB2_MAX_SPECIES + SB2_MAX_MEM_SPECIES];  // volume species, then membrane species
 };
 
 // gather formulation of the scatter at calcPDE.cpp:1394-1479: one thread per (species, cell) sums its
 // contributions in the reference's order
-__global__ void __launch_bounds__(128) mt_apply_kernel(const __grid_constant__ MtApplyArgs A) {
+// The rate of every membrane point a cell is fed by is evaluated by that cell's thread (a point feeds two to four cells; the
+// evaluation is a handful of operations), so one launch does what took a rate kernel and a gather kernel.
+__global__ void __launch_bounds__(128) mt_fused_kernel(const __grid_constant__ MtEvalArgs E, const __grid_constant__ MtApplyArgs A) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= A.n_groups) return;
   double* kp = A.kout[A.group_species[g]] + A.group_cell[g];
-  double acc = *kp;
+  double acc = (A.group_first && A.group_first[g]) ? 0.0 : *kp;
   for (int e = A.group_start[g]; e < A.group_start[g + 1]; ++e) {
     // fabs(n) * stoich * rate / delta
-    const double term = A.entry_coef[e] * A.rate[A.entry_pt[e]] / A.entry_delta[e];
+    const double term = A.entry_coef[e] * mt_rate(E, A.entry_pt[e]) / A.entry_delta[e];
     acc = A.entry_sign[e] < 0 ? acc - term : acc + term;
   }
   *kp = acc;
@@ -1002,6 +1004,7 @@ int sb2_build_transport(const sb2_grid& g, int64_t P, int64_t PL, int64_t first,
   }
   gstart.push_back((int32_t)entries.size());
   out.n_groups = (int)gspecies.size(); out.n_entries = (int)entries.size();
+  out.h_group_species = gspecies; out.h_group_cell = gcell; out.d_group_first = NULL;
   cudaError_t e;
   std::vector<double> rate0(std::max(npts, 1), 0.0);
   if ((e = to_device(&out.d_near, near_c, stream)) != cudaSuccess || (e = to_device(&out.d_far, far_c, stream)) != cudaSuccess ||
@@ -1030,16 +1033,15 @@ void sb2_free_transport(Sb2MemTransport& t) {
   cudaFree(t.d_near); cudaFree(t.d_far); cudaFree(t.d_fieldval); cudaFree(t.d_rate);
   cudaFree(t.d_group_start); cudaFree(t.d_group_species); cudaFree(t.d_group_cell);
   cudaFree(t.d_entry_pt); cudaFree(t.d_entry_coef); cudaFree(t.d_entry_delta); cudaFree(t.d_entry_sign);
-  cudaFree(t.d_tok); cudaFree(t.d_operand);
+  cudaFree(t.d_tok); cudaFree(t.d_operand); cudaFree(t.d_group_first);
 }
 
 cudaError_t sb2_launch_transport(const Sb2MemTransport& t, const sb2_grid& g, const double* const* u,
                                  const double* const* kprev, double* const* kout, const double* const* mu,
                                  const double* const* mkprev, double* const* mkout, const double* consts, int m,
-                                 double cdt, cudaStream_t stream, int* launches) {
+                                 double cdt, bool first_resets, cudaStream_t stream, int* launches) {
   (void)g;
-  if (t.npts == 0) return cudaSuccess;
-  cudaError_t e;
+  if (t.npts == 0 || t.n_groups == 0) return cudaSuccess;
   MtEvalArgs a;
   a.npts = t.npts; a.ntoks = t.ntoks; a.m = m; a.cdt = cdt;
   a.tok = t.d_tok; a.tok_operand = t.d_operand;
@@ -1051,21 +1053,21 @@ cudaError_t sb2_launch_transport(const Sb2MemTransport& t, const sb2_grid& g, co
     if ((t.tok[i] & 0xff) == SB2_TOK_MEMVAR && mu) { const int s = t.tok[i] >> 16; a.mu[s] = mu[s]; a.mkprev[s] = mkprev[s]; }
   }
   memcpy(a.consts, consts, sizeof(a.consts));
-  if (launches) ++*launches;
-  mt_eval_kernel<<<(t.npts + 127) / 128, 128, 0, stream>>>(a);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  if (t.n_groups == 0) return cudaSuccess;
   MtApplyArgs b;
   b.n_groups = t.n_groups;
   b.group_start = t.d_group_start; b.group_species = t.d_group_species; b.group_cell = t.d_group_cell;
   b.entry_pt = t.d_entry_pt; b.entry_coef = t.d_entry_coef; b.entry_delta = t.d_entry_delta; b.entry_sign = t.d_entry_sign;
-  b.rate = t.d_rate;
+  b.group_first = first_resets ? t.d_group_first : NULL;
   for (int s = 0; s < SB2_MAX_SPECIES; ++s) b.kout[s] = s < t.nspecies ? kout[s] : NULL;
   for (int s = 0; s < SB2_MAX_MEM_SPECIES; ++s) b.kout[SB2_MAX_SPECIES + s] = mkout ? mkout[s] : NULL;
   if (launches) ++*launches;
-  mt_apply_kernel<<<(t.n_groups + 127) / 128, 128, 0, stream>>>(b);
+  mt_fused_kernel<<<(t.n_groups + 127) / 128, 128, 0, stream>>>(a, b);
   return cudaGetLastError();
+}
+
+cudaError_t sb2_transport_set_first(Sb2MemTransport& t, const std::vector<uint8_t>& first, cudaStream_t stream) {
+  if (t.d_group_first) { cudaFree(t.d_group_first); t.d_group_first = NULL; }
+  return to_device(&t.d_group_first, first, stream);
 }
 
 // =============================================================================================

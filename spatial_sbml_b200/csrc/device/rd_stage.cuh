@@ -448,7 +448,7 @@ __device__ __forceinline__ bool rd_compute_row(const Sb2RdArgs& A, const double*
     uint32_t anyf = 0;
 #pragma unroll
     for (int c = 0; c < NC; ++c) anyf |= fl[c];
-    if (!__any_sync(0xffffffffu, (anyf & 0x01010101u) != 0) && !A.carry) {
+    if (!__any_sync(0xffffffffu, (anyf & 0x01010101u) != 0) && A.carry != 1) {
       // this warp's cells are all outside (a class-0 strip row is mixed only as a whole)
 #pragma unroll
       for (int s = 0; s < NS; ++s) {
@@ -472,8 +472,8 @@ __device__ __forceinline__ bool rd_compute_row(const Sb2RdArgs& A, const double*
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
       acc[s][2 * p] = 0.0; acc[s][2 * p + 1] = 0.0;
-      if (A.carry && s < S && active[p]) {
-        const double2 c = *reinterpret_cast<const double2*>(A.sp[s].kout + idx0 + p * 64);
+      if (A.carry && (A.carry == 1 || cls == 0) && s < S && active[p]) {
+        const double2 c = *reinterpret_cast<const double2*>(A.sp[s].kcarry + idx0 + p * 64);
         acc[s][2 * p] = c.x; acc[s][2 * p + 1] = c.y;
       }
     }
@@ -727,7 +727,7 @@ __device__ __forceinline__ void rd_stage_body(const Sb2RdArgs& A, const double* 
     const int srow = Y + warp;  // row this warp computes in the current batch
     const bool compute = (Y >= yb) && (srow < ye);
     int cls = 2;
-    if (compute) cls = A.carry ? 0 : (int)A.cls[(uint32_t)srow * (uint32_t)A.nstrips + blockIdx.x];
+    if (compute) cls = A.carry == 1 ? 0 : (int)A.cls[(uint32_t)srow * (uint32_t)A.nstrips + blockIdx.x];
 
     // (1) + (2): raw row → w ring
     if (wrow >= yb - 1 && wrow <= ye) {
@@ -1040,7 +1040,7 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
     for (int p = 0; p < NP; ++p) cb_next[p] = cb[cb_valid[p] ? p : 0];  // (the select is on the address: the byte itself stays untouched)
   };
   auto decode_class = [&]() {
-    if (A.carry) { cls_cur = 0; seg_cur = 0xffffffffu; return; }
+    if (A.carry == 1) { cls_cur = 0; seg_cur = 0xffffffffu; return; }
     int c = cb_valid[0] ? (int)cb_next[0] : -1;
     uint32_t m = c == 1 ? 0u : 1u;
 #pragma unroll
@@ -1068,7 +1068,7 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
         if (g < MODEL_G(A)) fraw[p][g] = (uint32_t)*reinterpret_cast<const unsigned short*>(A.flags[g] + i0 + p * 64);
     }
   };
-  if (computes && !A.carry) load_class(zb);
+  if (computes && A.carry != 1) load_class(zb);
   int64_t idx_run = A.first + (int64_t)(zb - 2) * A.PL + (int64_t)y * A.P + x0 + 2 * lane;  // this lane's first cell in plane zc
   // ring slot and barrier phase of the plane staged in this iteration (qs, phs: iteration count modulo / over NSLOT) and of the
   // plane computed in it (qc, phc: one iteration older; qm: two), kept as running values instead of divisions by NSLOT
@@ -1115,7 +1115,7 @@ __device__ __forceinline__ void rd_stage3_body(const Sb2RdArgs& A, const double*
         load_flags(idx_run + A.PL, seg_cur);
 #endif
       }
-      if (!A.carry && pz + 1 < ze) load_class(pz + 1);
+      if (A.carry != 1 && pz + 1 < ze) load_class(pz + 1);
     }
     {
       const int q = qs;

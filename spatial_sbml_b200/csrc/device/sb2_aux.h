@@ -85,6 +85,11 @@ struct Sb2MemTransport {
   double* d_entry_coef;     // [n_entries] fabs(n)*stoich with the sign of reactant(-)/product(+) folded in separately
   double* d_entry_delta;    // [n_entries] deltaX/Y/Z of the point's axis
   int32_t* d_entry_sign;    // [n_entries] -1 reactant, +1 product
+  // host copies of the group keys and, per group, whether no transport declared earlier feeds the same (species, cell): such a
+  // group starts from zero instead of from what the buffer holds (sb2_finalize fills it in; see launch_membrane_ops)
+  std::vector<int32_t> h_group_species;
+  std::vector<int64_t> h_group_cell;
+  uint8_t* d_group_first;   // [n_groups] or NULL
 };
 int sb2_build_transport(const sb2_grid& g, int64_t P, int64_t PL, int64_t first, int nspecies, const sb2_token* toks,
                         int ntoks, const sb2_ref* refs, int nrefs, int n_reactants, const sb2_mem_point* pts, int npts,
@@ -92,10 +97,13 @@ int sb2_build_transport(const sb2_grid& g, int64_t P, int64_t PL, int64_t first,
                         cudaStream_t stream, Sb2MemTransport& out, std::string& err);
 void sb2_free_transport(Sb2MemTransport& t);
 // mu / mkprev / mkout: the membrane species (binding reactions), indexed by membrane species id; may be NULL
+// first_resets: groups of volume species flagged in d_group_first start from zero (kout is then the persistent transport
+// buffer of the species, which needs no clearing between stages)
 cudaError_t sb2_launch_transport(const Sb2MemTransport& t, const sb2_grid& g, const double* const* u,
                                  const double* const* kprev, double* const* kout, const double* const* mu,
                                  const double* const* mkprev, double* const* mkout, const double* consts, int m,
-                                 double cdt, cudaStream_t stream, int* launches);
+                                 double cdt, bool first_resets, cudaStream_t stream, int* launches);
+cudaError_t sb2_transport_set_first(Sb2MemTransport& t, const std::vector<uint8_t>& first, cudaStream_t stream);
 
 // ---------------- stability (checkStability.cpp:10-52, 119-154) ----------------
 struct Sb2MinDtArgs {

@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <chrono>
+#include <set>
 #include <sstream>
 
 namespace {
@@ -29,6 +30,10 @@ struct Sb2Species {
   double* faces[3];  // CIP face values (advected species only)
   double* faces_alt[3];  // 2-D: the other half of their double buffer (a fused direction pass writes the new faces of its axis there)
   int face_par;          // bit a: the halves of axis a have been swapped an odd number of times
+  // models with membrane transport: what the transports add to this species in a stage.  Zero everywhere except at the cells next
+  // to a membrane, which the transport kernels rewrite in every stage - so it never needs clearing, and the stage kernel starts
+  // its accumulators from it (Sb2SpeciesArgs::kcarry) instead of from a k_m that had to be zero-filled first
+  double* tcarry;
 };
 
 struct Sb2Stmt {
@@ -441,6 +446,10 @@ const char* kOpcNames[OPC_COUNT] = {"END", "PUSHC", "PUSHV", "PUSHF", "ADD", "SU
   "LEQ", "LT", "AND", "OR", "ADDC", "SUBC", "MULC", "DIVC", "RSUBC", "RDIVC", "GEQC", "GTC", "LEQC", "LTC", "ADDV", "SUBV", "MULV",
   "DIVV", "UNARY", "BINR", "MOV0", "MOVUP", "MASK", "ACCSUB", "ACCADD", "ACCSUB1", "ACCADD1", "ACCSUBC1", "ACCADDC1", "ACCSUBM", "ACCADDM"};
 
+// Membrane transport of stage m goes to the species' transport buffers (no zero-filling of k_m) unless k_0 carries a Neumann flux
+// from the previous step, which the transports then add to in place
+bool transport_in_buffer(const sb2_sim* sim, int m) { return !sim->transports.empty() && !(sim->carry_k0 && m == 0); }
+
 void fill_stage_args(sb2_sim* sim, Sb2StageCore& a, int m, double dt, int row_begin, int row_end) {
   static const double rk[4] = {0.0, 0.5, 0.5, 1.0};
   a = sim->base;
@@ -448,7 +457,9 @@ void fill_stage_args(sb2_sim* sim, Sb2StageCore& a, int m, double dt, int row_be
   a.dt = dt;
   a.cdt = rk[m] * dt;
   a.final = (m == 3 && sim->fuse_combine) ? 1 : 0;
-  a.carry = (sim->carry_k0 && m == 0) || !sim->transports.empty() ? 1 : 0;
+  // (cells next to a membrane are boundary cells of their geometry: the transport buffer is zero in every strip row that is all
+  // interior or all outside, so those rows need not read it)
+  a.carry = (sim->carry_k0 && m == 0) ? 1 : transport_in_buffer(sim, m) ? 2 : 0;
   a.row_begin = row_begin;
   a.row_end = row_end;
   const int S = (int)sim->species.size();
@@ -460,6 +471,7 @@ void fill_stage_args(sb2_sim* sim, Sb2StageCore& a, int m, double dt, int row_be
     o.u_out = sp.u[sp.cur ^ 1];
     o.kprev = m > 0 ? sp.k[m - 1] : sp.k[0];
     o.kout = sp.k[m];
+    o.kcarry = transport_in_buffer(sim, m) ? sp.tcarry : sp.k[m];
     o.k0 = sp.k[0];
     o.k1 = sp.k[1];
   }
@@ -700,6 +712,7 @@ void sb2_destroy(sb2_sim* sim) {
     cudaFree(s.u[0]); cudaFree(s.u[1]);
     for (int m = 0; m < 4; ++m) cudaFree(s.k[m]);
     for (int a = 0; a < 3; ++a) { if (s.faces[a]) cudaFree(s.faces[a]); if (s.faces_alt[a]) cudaFree(s.faces_alt[a]); }
+    if (s.tcarry) cudaFree(s.tcarry);
   }
   for (size_t i = 0; i < sim->transports.size(); ++i) sb2_free_transport(sim->transports[i]);
   for (int part = 0; part < 3; ++part) sb2_free_boundary_lists(sim->blists[part]);
@@ -1171,6 +1184,23 @@ int sb2_finalize(sb2_sim* sim) {
     for (int k = 0; k < 6; ++k) if (sim->species[s].has_bc && sim->species[s].bckind[k] == SB2_BC_DIRICHLET) sim->model_dirichlet = true;
   sim->edge_w = sim->transports.empty() ? 1 : 2;
   sim->end_w = (sim->any_adv || !sim->transports.empty()) ? 2 : 1;
+  if (!sim->transports.empty()) {
+    // transport buffers of the volume species, and per transport which of its (species, cell) groups no earlier transport feeds
+    for (size_t s = 0; s < sim->species.size(); ++s)
+      if (!sim->species[s].tcarry) { int rc0 = alloc_field(sim, &sim->species[s].tcarry); if (rc0) return rc0; }
+    std::set<std::pair<int, int64_t> > seen;
+    for (size_t i = 0; i < sim->mem_ops.size(); ++i) {
+      if (sim->mem_ops[i].type != 0) continue;
+      Sb2MemTransport& t = sim->transports[sim->mem_ops[i].index];
+      std::vector<uint8_t> first(t.h_group_species.size(), 0);
+      for (size_t g = 0; g < first.size(); ++g) {
+        if (t.h_group_species[g] >= SB2_MAX_SPECIES) continue;  // membrane species accumulate in their own k arrays
+        first[g] = seen.insert(std::make_pair((int)t.h_group_species[g], t.h_group_cell[g])).second ? 1 : 0;
+      }
+      cudaError_t e = sb2_transport_set_first(t, first, sim->stream);
+      if (e != cudaSuccess) return cuda_fail(sim, e, "membrane transport lists");
+    }
+  }
   int rc = sb2_build_boundary_lists(sim->g, sim->P, sim->PL, sim->first, sim->h_flags, bcs, sim->consts, sim->stream,
                                     sim->edge_w, sim->blists, err);
   if (rc) return fail(sim, rc, err);
@@ -1245,12 +1275,7 @@ int launch_membrane_ops(sb2_sim* sim, int m) {
   static const double rk[4] = {0.0, 0.5, 0.5, 1.0};
   const double dt = sim->cur_dt;
   // membrane transport first: its flux is the carry-in of the stage accumulators of the volume species
-  if (!sim->transports.empty()) {
-    for (size_t s = 0; s < sim->species.size(); ++s) {
-      if (sim->carry_k0 && m == 0) continue;  // k0 already holds the carried Neumann flux
-      CK(cudaMemsetAsync(sim->species[s].k[m], 0, sizeof(double) * sim->nalloc, sim->stream));
-    }
-  }
+  const bool in_buffer = transport_in_buffer(sim, m);  // else: k0 already holds the carried Neumann flux, the transports add to it
   // transports and membrane reactions in the order of the reference's reaction list (what a membrane species receives
   // adds up in that order), then surface diffusion (spatialsimulator.cpp:1369-1479)
   if (sim->mem_ops.empty() && sim->mem_species.empty()) return SB2_OK;
@@ -1262,13 +1287,13 @@ int launch_membrane_ops(sb2_sim* sim, int m) {
   for (size_t s = 0; s < sim->species.size(); ++s) {
     u[s] = sim->species[s].u[sim->species[s].cur];
     kp[s] = m > 0 ? sim->species[s].k[m - 1] : NULL;
-    ko[s] = sim->species[s].k[m];
+    ko[s] = in_buffer ? sim->species[s].tcarry : sim->species[s].k[m];
   }
   for (size_t i = 0; i < sim->mem_ops.size(); ++i) {
     cudaError_t e;
     if (sim->mem_ops[i].type == 0)
       e = sb2_launch_transport(sim->transports[sim->mem_ops[i].index], sim->g, u.data(), kp.data(), ko.data(), mu, mkp, mko, sim->consts, m,
-                               rk[m] * dt, sim->stream, &sim->launches);
+                               rk[m] * dt, in_buffer, sim->stream, &sim->launches);
     else
       e = sb2_launch_mem_reaction(sim->mem_reactions[sim->mem_ops[i].index], mv, sim->consts, m, rk[m] * dt, sim->stream, &sim->launches);
     if (e != cudaSuccess) return cuda_fail(sim, e, "membrane transport / reaction kernels");
@@ -1775,7 +1800,11 @@ int sb2_step(sb2_sim* sim, double t_arg, double t_incr, double dt, int nsteps, i
                          ncells(sim) <= (1 << 18) && nsteps >= 12;
   if (graphable) {
     for (; i < 2; ++i) if ((rc = one_plain_step(sim, t_arg + i * t_incr, dt, time_slot))) return rc;
-    const int pairs = (nsteps - i) / 2;
+    // steps per graph: an even number (the u double buffer is back in the captured state after two steps); longer graphs spread
+    // the cost of a graph launch over more steps
+    static const int gsteps_env = getenv("SB2_GRAPH_STEPS") ? atoi(getenv("SB2_GRAPH_STEPS")) : 8;
+    const int gsteps = gsteps_env >= 2 ? (gsteps_env & ~1) : 2;
+    const int pairs = (nsteps - i) / gsteps;
     // which halves of the double buffers are current: u of every species and, for advected species, the faces
     int par = 0;
     for (size_t s = 0; s < sim->species.size(); ++s) par = (par * 5 + sim->species[s].cur * 8 + sim->species[s].face_par) & 0xffff;
@@ -1798,7 +1827,7 @@ int sb2_step(sb2_sim* sim, double t_arg, double t_incr, double dt, int nsteps, i
       rc = SB2_OK;
       if (e == cudaSuccess) {
         sim->capturing = true;
-        for (int k = 0; k < 2 && !rc; ++k) rc = one_plain_step(sim, t_arg + (i + k) * t_incr, dt, time_slot);
+        for (int k = 0; k < gsteps && !rc; ++k) rc = one_plain_step(sim, t_arg + (i + k) * t_incr, dt, time_slot);
         sim->capturing = false;
         e = cudaStreamEndCapture(sim->stream, &graph);
       }
@@ -1821,12 +1850,12 @@ int sb2_step(sb2_sim* sim, double t_arg, double t_incr, double dt, int nsteps, i
     if (sim->gexec[par] && pairs > 0) {
       for (int r = 0; r < pairs; ++r) CK(cudaGraphLaunch(sim->gexec[par], sim->stream));
       sim->launches += sim->g_launches[par] * (pairs - (fresh ? 1 : 0));
-      sim->steps_seen += 2 * (pairs - (fresh ? 1 : 0));
-      i += 2 * pairs;
+      sim->steps_seen += gsteps * (pairs - (fresh ? 1 : 0));
+      i += gsteps * pairs;
     } else if (fresh) {
       // captured but nothing to replay (cannot happen with nsteps >= 12): execute the captured pair once
       CK(cudaGraphLaunch(sim->gexec[par], sim->stream));
-      i += 2;
+      i += gsteps;
     }
   }
   for (; i < nsteps; ++i)

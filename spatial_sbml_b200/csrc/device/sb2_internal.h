@@ -61,6 +61,7 @@ struct Sb2SpeciesArgs {
   double* u_out;        // fused combine target (other half of the double buffer)
   const double* kprev;  // k_{m-1}
   double* kout;         // k_m
+  const double* kcarry; // carry != 0: what the accumulators start from (kout itself, or the membrane-transport buffer of the species)
   const double* k0;     // fused combine inputs
   const double* k1;
   int32_t geo;
@@ -82,7 +83,8 @@ struct Sb2StageCore {
   int32_t m;       // RK stage 0..3
   int32_t S, G;
   int32_t final;   // fused RK combine: write u_out instead of k3
-  int32_t carry;   // accumulate on top of what kout already holds
+  int32_t carry;   // 1: the accumulators start from kcarry (= kout: a carried flux); 2: from kcarry (the transport buffer), which is
+                   // zero outside mixed strip rows - those keep their fast paths
   int32_t ntok;
   int32_t depth;   // deepest expression-stack slot the program touches + 1
   double cdt;      // rk[m]*dt

@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(NT, (NS * NP <= 2) ? 5 : (NS * NP <= 4) ? 3 : 
         for (int p = 0; p < NP; ++p) {
           acc[s][2 * p] = 0.0; acc[s][2 * p + 1] = 0.0;
           if (A.carry && s < S && active[p]) {
-            const double2 c = *reinterpret_cast<const double2*>(A.sp[s].kout + idx0 + p * 2 * NT);
+            const double2 c = *reinterpret_cast<const double2*>(A.sp[s].kcarry + idx0 + p * 2 * NT);
             acc[s][2 * p] = c.x; acc[s][2 * p + 1] = c.y;
           }
         }
@@ -441,7 +441,8 @@ __global__ void __launch_bounds__(NT, (NS * NP <= 2) ? 5 : (NS * NP <= 4) ? 3 : 
             if (!active[p]) continue;
             const int64_t idx = idx0 + p * 2 * NT;
             if (MODE != MODE_FINAL) {
-              if (!A.carry) *reinterpret_cast<double2*>(A.sp[s].kout + idx) = make_double2(0.0, 0.0);
+              *reinterpret_cast<double2*>(A.sp[s].kout + idx) =
+                  A.carry ? *reinterpret_cast<const double2*>(A.sp[s].kcarry + idx) : make_double2(0.0, 0.0);
             } else {
               *reinterpret_cast<double2*>(A.sp[s].u_out + idx) = *reinterpret_cast<const double2*>(A.sp[s].u + idx);
             }
