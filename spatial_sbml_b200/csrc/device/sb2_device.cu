@@ -1909,6 +1909,9 @@ int sb2_step_host_begin(sb2_sim* sim, double t_arg, double dt, int time_slot, co
   const int64_t plane_cells = (int64_t)g.nx * g.ny;
   auto upload_rows = [&](double* dev, const double* host, int r0, int r1) -> cudaError_t {
     // rows [r0, r1) of the slab axis from a compact host array (the rows this handle holds) into the padded device array
+    // (rows without padding are one contiguous block on both sides: a plain copy)
+    if (!d3 && sim->P == g.nx) return cudaMemcpyAsync(dev + sim->first + (int64_t)r0 * sim->P, host + (int64_t)r0 * g.nx,
+                                                      sizeof(double) * (size_t)g.nx * (r1 - r0), cudaMemcpyHostToDevice, sim->h2d);
     if (!d3) return cudaMemcpy2DAsync(dev + sim->first + (int64_t)r0 * sim->P, sizeof(double) * sim->P, host + (int64_t)r0 * g.nx,
                                       sizeof(double) * g.nx, sizeof(double) * g.nx, r1 - r0, cudaMemcpyHostToDevice, sim->h2d);
     for (int z = r0; z < r1; ++z) {
@@ -1966,6 +1969,8 @@ int step_host_queue(sb2_sim* sim, double* const* out) {
   const sb2_grid& g = sim->g;
   const int64_t plane_cells = (int64_t)g.nx * g.ny;
   auto download_rows = [&](const double* dev, double* host, int r0, int r1) -> cudaError_t {
+    if (!d3 && sim->P == g.nx) return cudaMemcpyAsync(host + (int64_t)r0 * g.nx, dev + sim->first + (int64_t)r0 * sim->P,
+                                                      sizeof(double) * (size_t)g.nx * (r1 - r0), cudaMemcpyDeviceToHost, sim->d2h);
     if (!d3) return cudaMemcpy2DAsync(host + (int64_t)r0 * g.nx, sizeof(double) * g.nx, dev + sim->first + (int64_t)r0 * sim->P,
                                       sizeof(double) * sim->P, sizeof(double) * g.nx, r1 - r0, cudaMemcpyDeviceToHost, sim->d2h);
     for (int z = r0; z < r1; ++z) {
