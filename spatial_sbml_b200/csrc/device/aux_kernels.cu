@@ -732,8 +732,9 @@ cudaError_t cip2d_uniform_launch(const Sb2CipArgs& a, int axis, cudaStream_t str
   // rows per block: long marches amortise the prologue rows, short ones fill the machine
   // (small grids are bound by the latency of a march, not by throughput: down to two rows per warp, four along the pass axis
   // where every march pays a flux-only row)
-  int rpb = 64;
+  int rpb = 32;  // (measured at 4096^2 / 8192^2: 8, 16, 32, 64, 128 rows -> 0.178, 0.177, 0.175, 0.211, 0.200 / -, 0.661, 0.649, 0.661, 0.669 ms per pass)
   while (rpb > (axis == 0 ? 2 : 4) && (int64_t)nstrips * ((nupd + rpb - 1) / rpb) < 148 * 48) rpb /= 2;
+  if (const char* e = getenv("SB2_CIP_RPB")) rpb = atoi(e) > 0 ? atoi(e) : rpb;  // experiments
   const dim3 grid((nstrips + kCipUWarps - 1) / kCipUWarps, (nupd + rpb - 1) / rpb);
   if (axis == 0) cip2d_ux_kernel<POS, P2><<<grid, kCipUWarps * 32, 0, stream>>>(a, rpb);
   else cip2d_uy_kernel<POS, P2><<<grid, kCipUWarps * 32, 0, stream>>>(a, rpb);
