@@ -33,6 +33,39 @@ def _free_port():
     return p
 
 
+def _worker_wide(rank, world, port, n_rows, unit, width, out):
+    """The exchange of `width` edge rows (4: what the apron schedule and the host step of a slab send once per step)"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = partition(n_rows, world)[rank]
+        held_lo, held_hi = max(0, lo - width), min(n_rows, hi + width)
+        own_lo, own_hi = lo - held_lo, hi - held_lo
+        base = unit + 4
+        t = torch.full((base + (held_hi - held_lo + 2) * unit,), -1.0, dtype=torch.float64)
+        for r in range(own_lo, own_hi):
+            t[base + r * unit: base + (r + 1) * unit] = torch.arange(unit, dtype=torch.float64) + 1000.0 * (held_lo + r)
+        for req in exchange_rows([t], unit, base, own_lo, own_hi, rank, world, width=width):
+            req.wait()
+        ok = True
+        for r in range(held_hi - held_lo):
+            g = held_lo + r
+            want = torch.arange(unit, dtype=torch.float64) + 1000.0 * g
+            ok = ok and bool(torch.equal(t[base + r * unit: base + (r + 1) * unit], want))  # owned rows and all halo rows
+        out[rank] = 1 if ok else 0
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,width", [(2, 4), (3, 4), (3, 2)])
+def test_wide_halo_exchange_over_gloo(world, width):
+    port = _free_port()
+    out = mp.get_context("spawn").Array("i", [0] * world)
+    mp.spawn(_worker_wide, args=(world, port, 41, 24, width, out), nprocs=world, join=True)
+    assert list(out) == [1] * world
+
+
 def _worker(rank, world, port, n_rows, unit, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
