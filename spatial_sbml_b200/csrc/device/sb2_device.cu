@@ -75,6 +75,10 @@ struct sb2_sim {
   bool host_exchange;    // ... and whether the caller was handed an exchange of the edge rows
   bool halo_stale;       // slab: the halo rows of u were not refreshed after the last step (sb2_step_host_finish)
   bool sh_apron;         // slab: sharded steps exchange four rows of u once and recompute the apron rows (sb2_sharded_set_apron)
+  // small grids: the CIP-CSLR passes of different species run side by side on streams of their own (created on first use)
+  std::vector<cudaStream_t> adv_streams;
+  std::vector<cudaEvent_t> adv_join;
+  cudaEvent_t adv_fork;
   bool sh_awaiting, sh_comm_valid, sh_first_stage;
   bool finalized, any_adv;
   bool fuse_combine;    // this step: RK combine fused into stage 4
@@ -696,6 +700,7 @@ int sb2_create(const sb2_grid* grid, sb2_sim** out) {
   sim->sh_edge = NULL; sim->sh_comm = NULL;
   sim->ev_edge = sim->ev_interior = sim->ev_comm = sim->ev_ready = sim->ev_pulled = NULL;
   sim->host_nslabs = 0; sim->host_exchange = false; sim->halo_stale = false; sim->sh_apron = false;
+  sim->adv_fork = NULL;
   sim->sh_phase = -1; sim->sh_passes = 0; sim->sh_awaiting = false; sim->sh_comm_valid = false; sim->sh_first_stage = true;
   *out = sim;
   return SB2_OK;
@@ -716,6 +721,9 @@ void sb2_destroy(sb2_sim* sim) {
   }
   for (size_t i = 0; i < sim->transports.size(); ++i) sb2_free_transport(sim->transports[i]);
   for (int part = 0; part < 3; ++part) sb2_free_boundary_lists(sim->blists[part]);
+  for (size_t i = 0; i < sim->adv_streams.size(); ++i) cudaStreamDestroy(sim->adv_streams[i]);
+  for (size_t i = 0; i < sim->adv_join.size(); ++i) cudaEventDestroy(sim->adv_join[i]);
+  if (sim->adv_fork) cudaEventDestroy(sim->adv_fork);
   if (sim->sh_edge) cudaStreamDestroy(sim->sh_edge);
   if (sim->sh_comm) cudaStreamDestroy(sim->sh_comm);
   if (sim->ev_edge) cudaEventDestroy(sim->ev_edge);
@@ -1484,9 +1492,43 @@ int sb2_end_step(sb2_sim* sim) {
     const std::vector<AdvPass> passes = advection_passes(sim);
     if (!passes.empty() && sim->g.own_hi > sim->g.own_lo)
       return fail(sim, SB2_ERR_STATE, "advection on a slab needs a halo exchange after every pass: step it with sb2_sharded_begin / sb2_sharded_next");
+    // The passes of one species follow each other (X, then Y, then Z); different species share nothing.  Grids small enough to be
+    // bound by the latency of a launch run them side by side: species 2, 3, ... on streams of their own, forked from and joined to
+    // the step's stream (inside a captured step graph these become parallel branches).
+    static const bool serial_adv = getenv("SB2_ADV_SERIAL") != NULL;
+    int nadv = 0;
+    for (size_t s = 0; s < sim->species.size(); ++s) nadv += sim->species[s].has_adv ? 1 : 0;
+    // (only the fused 2-D passes: the two-kernel pass of 3-D grids shares one scratch array between the species)
+    bool all_fused = sim->g.dim == 2;
+    for (size_t i = 0; i < passes.size(); ++i) all_fused = all_fused && sim->species[passes[i].species].faces_alt[passes[i].axis] != NULL;
+    const bool side_by_side = !serial_adv && nadv > 1 && all_fused && ncells(sim) <= (1 << 18);
+    if (side_by_side) {
+      if (!sim->adv_fork) CK(cudaEventCreateWithFlags(&sim->adv_fork, cudaEventDisableTiming));
+      while ((int)sim->adv_streams.size() < nadv - 1) {
+        cudaStream_t st; cudaEvent_t ev;
+        CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        sim->adv_streams.push_back(st); sim->adv_join.push_back(ev);
+      }
+      CK(cudaEventRecord(sim->adv_fork, sim->stream));
+    }
+    const cudaStream_t main_stream = sim->stream;
+    int branch = -1, last_species = -1;
     for (size_t i = 0; i < passes.size(); ++i) {
+      if (side_by_side && passes[i].species != last_species) {
+        if (branch >= 1) CK(cudaEventRecord(sim->adv_join[branch - 1], sim->stream));  // the previous species' branch is complete
+        ++branch;
+        last_species = passes[i].species;
+        sim->stream = branch == 0 ? main_stream : sim->adv_streams[branch - 1];
+        if (branch >= 1) CK(cudaStreamWaitEvent(sim->stream, sim->adv_fork, 0));
+      }
       int rc = launch_advection_pass(sim, passes[i]);
-      if (rc) return rc;
+      if (rc) { sim->stream = main_stream; return rc; }
+    }
+    if (side_by_side) {
+      if (branch >= 1) CK(cudaEventRecord(sim->adv_join[branch - 1], sim->stream));
+      sim->stream = main_stream;
+      for (int b = 1; b <= branch; ++b) CK(cudaStreamWaitEvent(main_stream, sim->adv_join[b - 1], 0));
     }
   }
   return finish_step(sim);
