@@ -503,6 +503,22 @@ void fill_stage_args(sb2_sim* sim, Sb2StageCore& a, int m, double dt, int row_be
     static const int rpb_batches = getenv("SB2_RD_BATCHES") ? atoi(getenv("SB2_RD_BATCHES")) : 12;
     int rpb = rpb_batches * W;
     while (rpb > W && (int64_t)sim->nstrips * ((rows + rpb - 1) / rpb) < 148 * 6) rpb -= W;
+    // Grids of a few waves of CTAs (a slab of a strongly scaled grid: 8192 x 1024 cells are 2.4 waves of 12-batch tiles) lose
+    // up to a third to the last, partly filled wave.  Where another tile height within 4 .. 12 batches makes waves x (rows of a
+    // tile + its prologue batch) more than 3 % smaller, take it; large grids (many waves) keep 12 batches.
+    static const bool wavefit = getenv("SB2_RD_NO_WAVEFIT") == NULL;
+    if (wavefit && (int64_t)sim->nstrips * rows >= (int64_t)148 * 2 * W * 4) {
+      const int per_sm = (m == 0 && sim->jit && ncells(sim) >= (1 << 20) && sim->rd.w == 8 && sim->base.S <= 2) ? 3 : 2;
+      const int64_t slots = 148 * per_sm;
+      auto cost = [&](int r) {
+        const int64_t tiles = (int64_t)sim->nstrips * ((rows + r - 1) / r);
+        return ((tiles + slots - 1) / slots) * (int64_t)(r + W);
+      };
+      int best = rpb;
+      for (int b = rpb_batches; b >= 4; --b)
+        if (cost(b * W) * 100 < cost(best) * 97) best = b * W;
+      rpb = best;
+    }
     a.rows_per_block = rpb;
     return;
   }
