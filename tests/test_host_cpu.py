@@ -448,3 +448,19 @@ def test_the_references_own_cli_compiles_against_our_header():
     assert r.returncode != 0
     assert "spatial required: yes" in r.stdout
     assert "no CPU fallback" in r.stderr
+
+
+def test_the_bridge_of_the_integration_guide_builds():
+    """INTEGRATION.md §A, compiled: oracle/ref_bridge.cpp links the reference's own unmodified objects (its host set-up) with
+    libspatialb200.so and drives the sb2_* C ABI from the reference's structs.  Without a GPU it must stop at sb2_create."""
+    import subprocess
+    exe = os.path.join(REPO, "oracle", "_ref", "ref_bridge")
+    if os.path.isdir("/root/reference/SpatialSBML"):
+        subprocess.run(["make", "-s", "-C", os.path.join(REPO, "oracle"), exe], check=True)
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_bridge is built where /root/reference is mounted")
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("run on the GPU by tests/test_parity_gpu.py")
+    r = subprocess.run([exe, model_path("turing_tiny"), "22", "22", "1", "0.07", "2"], capture_output=True, text=True)
+    assert r.returncode == 2 and "no CPU fallback" in r.stderr

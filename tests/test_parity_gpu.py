@@ -287,6 +287,26 @@ def test_the_references_own_cli_runs_on_the_library():
     assert "time:" in r.stderr
 
 
+@pytest.mark.parametrize("case", ["turing_tiny", "brusselator", "fish", "fish_dirichlet", "turing_tiny_flux", "syn_turing_3d_flux",
+                                  "syn_raterules_2d", "syn_fieldcoeff_3d", "syn_chain6_2d"])
+def test_reference_host_setup_on_the_device_abi(case):
+    """INTEGRATION.md §A for real (oracle/ref_bridge.cpp): the reference's OWN host code sets the model up, its structs are
+    flattened onto the sb2_* C ABI, the GPU steps - and the fields equal those of the reference's own CPU step after every step."""
+    import json
+    import subprocess
+    exe = os.path.join(REPO, "oracle", "_ref", "ref_bridge")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_bridge is built where /root/reference is mounted")
+    g = load_golden(case)
+    nx, ny, nz = [int(v) for v in g["dims"]]
+    r = subprocess.run([exe, model_path(case), str(nx), str(ny), str(nz), repr(float(g["dt"])), "10"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-500:] + r.stderr[-500:]
+    res = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert res["rel_linf_vs_reference_cpu"] <= 1e-10 and res["launches"] >= 40
+    if case != "syn_raterules_2d":  # (transcendental laws: 1e-10)
+        assert res["bit_identical"]
+
+
 def test_host_step_falls_back_for_unfused_models():
     import spatial_sbml_b200 as sb
     g = load_golden("advection")
