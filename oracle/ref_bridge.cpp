@@ -10,9 +10,10 @@
 //   ref_bridge <model.xml> <xdim> <ydim> <zdim> <dt> <steps>
 //
 // Covered: species in volumes, reactions and rate rules, uniform and field-valued diffusion coefficients, Neumann / Dirichlet
-// boundary conditions.  Refused (exit 3): membrane transport, species on membranes, advection, assignment rules — the
+// boundary conditions, CIP-CSLR advection with uniform and field-valued velocities, membrane transport between two volumes.
+// Refused (exit 3): species on membranes (and binding to them), assignment rules — the
 // library has them (see csrc/host/spatialsimulator.cpp for the same flattening written against our own host model), the
-// bridge keeps to what the reference's example models of BASELINE configs 1-3 need.
+// bridge keeps to what the reference's own example models (BASELINE configs 1-4) need.
 #define private public  // (test-only access to varInfoList / geoInfoList / rInfoList, as in ref_driver.cpp)
 #include "spatialsimulator.h"
 #undef private
@@ -96,6 +97,17 @@ struct Bridge {
         for (int i = 0; i < nx; ++i) out[((size_t)k * ny + j) * nx + i] = full[even(i, j, k)];
     return out;
   }
+  // the value at the odd doubled-grid point on the plus side of every cell along axis a (zero past the last cell)
+  std::vector<double> oddPoints(const double* full, int a) const {
+    std::vector<double> out((size_t)nx * ny * nz, 0.0);
+    for (int k = 0; k < nz; ++k)
+      for (int j = 0; j < ny; ++j)
+        for (int i = 0; i < nx; ++i) {
+          const int X = 2 * i + (a == 0), Y = 2 * j + (a == 1), Z = 2 * k + (a == 2);
+          if (X < ref.Xindex && Y < ref.Yindex && Z < ref.Zindex) out[((size_t)k * ny + j) * nx + i] = full[((int64_t)Z * ref.Yindex + Y) * ref.Xindex + X];
+        }
+    return out;
+  }
   variableInfo* ownerOfValue(const double* p) const {
     for (size_t i = 0; i < ref.varInfoList.size(); ++i)
       if (ref.varInfoList[i]->value == p) return ref.varInfoList[i];
@@ -125,14 +137,141 @@ struct Bridge {
     return src >= 0;
   }
 
+  variableInfo* infoById(const std::string& id) const {
+    for (size_t i = 0; i < ref.varInfoList.size(); ++i)
+      if (id == ref.varInfoList[i]->id) return ref.varInfoList[i];
+    return NULL;
+  }
+  // the geometry of a species, or of another species of its compartment (spatialsimulator.cpp:1394-1426)
+  GeometryInfo* geoOfSpecies(const std::string& sid) const {
+    variableInfo* v = infoById(sid);
+    if (v && v->geoi) return v->geoi;
+    const Species* s = ref.model->getSpecies(sid);
+    if (!s) return NULL;
+    for (unsigned int i = 0; i < ref.model->getNumSpecies(); ++i) {
+      const Species* cur = ref.model->getSpecies(i);
+      if (cur->getId() != sid && cur->getCompartment() == s->getCompartment()) {
+        variableInfo* cv = infoById(cur->getId());
+        if (cv && cv->geoi) return cv->geoi;
+      }
+    }
+    return NULL;
+  }
+  // compact cell of a doubled-grid point, -1 unless it is a volume cell of `geo`
+  int32_t cellIn(GeometryInfo* geo, int X, int Y, int Z) const {
+    if (!geo || !geo->isVol || !geo->isDomain) return -1;
+    if (X < 0 || Y < 0 || Z < 0 || X >= ref.Xindex || Y >= ref.Yindex || Z >= ref.Zindex) return -1;
+    if ((X | Y | Z) & 1) return -1;
+    return geo->isDomain[((int64_t)Z * ref.Yindex + Y) * ref.Xindex + X] == 1 ? (int32_t)(((int64_t)(Z / 2) * ny + Y / 2) * nx + X / 2) : -1;
+  }
+  // membrane transport between two volumes (calcMemTransport, calcPDE.cpp:1036-1482): the membrane's points from the reference's
+  // domainIndex / isDomain / bType / nuVec, the operand and target cells from the species' isDomain masks
+  int addTransport(reactionInfo* ri) {
+    Reaction* r = ri->reaction;
+    if (r->getNumReactants() == 0 || r->getNumProducts() == 0) return 0;
+    GeometryInfo* rg = geoOfSpecies(r->getReactant(0)->getSpecies());
+    GeometryInfo* pg = geoOfSpecies(r->getProduct(0)->getSpecies());
+    if (!rg || !pg || !rg->isVol || !pg->isVol) { fprintf(stderr, "ref_bridge: binding to a membrane species is outside the bridge's scope\n"); return 3; }
+    GeometryInfo* mem = NULL;
+    for (size_t j = 0; j < ref.geoInfoList.size() && !mem; ++j) {
+      GeometryInfo* g = ref.geoInfoList[j];
+      if (!g->isVol && ((g->adjacentGeo1 == rg && g->adjacentGeo2 == pg) || (g->adjacentGeo1 == pg && g->adjacentGeo2 == rg))) mem = g;
+    }
+    if (!mem) return 0;  // no membrane between the two compartments: nothing happens
+    const int Xi = ref.Xindex, Yi = ref.Yindex, Zi = ref.Zindex;
+    const int64_t N = (int64_t)Xi * Yi * Zi;
+    struct Pt { int X, Y, Z; int64_t index; };
+    std::vector<Pt> pts;
+    for (size_t k = 0; k < mem->domainIndex.size(); ++k) {
+      const int64_t idx = mem->domainIndex[k];
+      if (idx < 0 || idx >= N) continue;
+      Pt p;
+      p.index = idx; p.Z = (int)(idx / ((int64_t)Xi * Yi)); p.Y = (int)((idx - (int64_t)p.Z * Xi * Yi) / Xi); p.X = (int)(idx - (int64_t)p.Z * Xi * Yi - (int64_t)p.Y * Xi);
+      if (ref.dimension == 3 && (p.X == 0 || p.Y == 0 || p.Z == 0 || p.X == Xi - 1 || p.Y == Yi - 1 || p.Z == Zi - 1)) continue;
+      if (ref.dimension == 2 && (p.X == 0 || p.Y == 0 || p.X == Xi - 1 || p.Y == Yi - 1)) continue;
+      if (mem->isDomain[idx] != 1) continue;
+      pts.push_back(p);
+    }
+    const int npts = (int)pts.size();
+    reversePolishInfo* rp = ri->rpInfo;
+    std::vector<sb2_token> toks;
+    std::vector<int32_t> operandCells;
+    std::vector<double> operandValues;
+    variableInfo* symbol = NULL;  // persists across tokens like the reference's symbolInfo
+    for (int i = 0; i < rp->listNum; ++i) {
+      sb2_token d;
+      d.kind = SB2_TOK_NOP; d.op = 0; d.slot = 0;
+      if (rp->varList && rp->varList[i]) {
+        variableInfo* v = ownerOfValue(rp->varList[i]);
+        if (v && rp->deltaList && rp->deltaList[i] && speciesId.count(v)) {
+          for (size_t j = 0; j < ri->spRefList.size(); ++j)
+            if (ri->spRefList[j] == v) { symbol = ri->spRefList[j]; break; }
+          if (!symbol || !symbol->geoi) { fprintf(stderr, "ref_bridge: transport operand without geometry\n"); return 2; }
+          d.kind = SB2_TOK_VAR; d.slot = (uint16_t)speciesId[v];
+          for (int p = 0; p < npts; ++p) {
+            int32_t nearC = -1, farC = -1;
+            const int dX[3] = {1, 0, 0}, dY[3] = {0, 1, 0}, dZ[3] = {0, 0, 1};
+            for (int a = 0; a < (int)ref.dimension; ++a) {  // later axes overwrite earlier ones (calcPDE.cpp:1107-1213)
+              int32_t c = cellIn(symbol->geoi, pts[p].X + dX[a], pts[p].Y + dY[a], pts[p].Z + dZ[a]);
+              int sgn = 1;
+              if (c < 0) { c = cellIn(symbol->geoi, pts[p].X - dX[a], pts[p].Y - dY[a], pts[p].Z - dZ[a]); sgn = -1; }
+              if (c < 0) continue;
+              nearC = c;
+              const int64_t flat3 = pts[p].index + sgn * 3 * (a == 0 ? 1 : a == 1 ? (int64_t)Xi : (int64_t)Xi * Yi);
+              farC = -1;
+              if (flat3 < N && flat3 >= 0) {
+                const int Z3 = (int)(flat3 / ((int64_t)Xi * Yi)), Y3 = (int)((flat3 - (int64_t)Z3 * Xi * Yi) / Xi), X3 = (int)(flat3 - (int64_t)Z3 * Xi * Yi - (int64_t)Y3 * Xi);
+                farC = cellIn(symbol->geoi, X3, Y3, Z3);
+              }
+            }
+            operandCells.push_back(nearC);
+            operandCells.push_back(farC);
+          }
+        } else if (v) {  // no delta array: the raw value at the membrane point itself (calcPDE.cpp:1218-1221)
+          d.kind = SB2_TOK_FIELD; d.slot = 0;
+          for (int p = 0; p < npts; ++p) operandValues.push_back(v->value[pts[p].index]);
+        }
+      } else if (rp->constList && rp->constList[i]) {
+        d.kind = SB2_TOK_CONST; d.slot = (uint16_t)slotOf(rp->constList[i]);
+        if (rp->constList[i] == &ref.sim_time) timeSlot = d.slot;
+      } else if (rp->opfuncList && rp->opfuncList[i] != 0) {
+        d.kind = SB2_TOK_OP; d.op = (uint8_t)opOfAst(rp->opfuncList[i]);
+      }
+      toks.push_back(d);
+    }
+    std::vector<sb2_mem_point> dpts((size_t)npts);
+    for (int p = 0; p < npts; ++p) {
+      const boundaryType& b = mem->bType[pts[p].index];
+      const int axis = (b.isBofXp || b.isBofXm) ? 0 : (b.isBofYp || b.isBofYm) ? 1 : 2;
+      const normalUnitVector& n = ref.nuVec[pts[p].index];
+      dpts[p].axis = axis;
+      dpts[p].abs_normal = fabs(axis == 0 ? n.nx : axis == 1 ? n.ny : n.nz);
+    }
+    std::vector<sb2_ref> refs;
+    std::vector<int32_t> targets;
+    for (size_t k = 0; k < ri->spRefList.size(); ++k) {
+      variableInfo* v = ri->spRefList[k];
+      const bool ok = v && !v->isUniform && speciesId.count(v) && v->geoi && v->geoi->isVol;
+      sb2_ref rr;
+      rr.species = ok ? speciesId[v] : -1;
+      rr.is_variable = ri->isVariable[k] ? 1 : 0;
+      rr.stoichiometry = ri->srStoichiometry[k];
+      refs.push_back(rr);
+      for (int p = 0; p < npts; ++p) {
+        const int a = dpts[p].axis, dx = a == 0, dy = a == 1, dz = a == 2;
+        targets.push_back(ok ? cellIn(v->geoi, pts[p].X + dx, pts[p].Y + dy, pts[p].Z + dz) : -1);
+        targets.push_back(ok ? cellIn(v->geoi, pts[p].X - dx, pts[p].Y - dy, pts[p].Z - dz) : -1);
+      }
+    }
+    DEV(sb2_add_mem_transport(dev, toks.data(), (int)toks.size(), refs.data(), (int)refs.size(), (int)r->getNumReactants(), dpts.data(), npts,
+                              operandCells.empty() ? NULL : operandCells.data(), operandValues.empty() ? NULL : operandValues.data(),
+                              targets.empty() ? NULL : targets.data()));
+    return 0;
+  }
+
   int build(int device) {
     nx = ref.Xdiv; ny = ref.Ydiv; nz = ref.Zdiv;
     if (ref.dimension < 2) { fprintf(stderr, "ref_bridge: 2-D and 3-D models only\n"); return 3; }
-    for (size_t i = 0; i < ref.rInfoList.size(); ++i)
-      if (ref.rInfoList[i]->reaction && ref.rInfoList[i]->isMemTransport) {  // (the flag is only set for reactions)
-        fprintf(stderr, "ref_bridge: membrane transport is outside the bridge's scope\n");
-        return 3;
-      }
     if (!ref.orderedARule.empty()) { fprintf(stderr, "ref_bridge: assignment rules are outside the bridge's scope\n"); return 3; }
     sb2_grid g;
     memset(&g, 0, sizeof(g));
@@ -167,7 +306,6 @@ struct Bridge {
       variableInfo* v = ref.varInfoList[i];
       if (!v->sp || v->isUniform || !v->delta) continue;
       if (!v->inVol) { fprintf(stderr, "ref_bridge: species on membranes are outside the bridge's scope\n"); return 3; }
-      if (v->adCInfo) for (int a = 0; a < 3; ++a) if (v->adCInfo[a]) { fprintf(stderr, "ref_bridge: advection is outside the bridge's scope\n"); return 3; }
       if (!v->geoi || !geoId.count(v->geoi)) { fprintf(stderr, "ref_bridge: species %s has no volume geometry\n", v->id); return 2; }
       const std::vector<double> c = compact(v->value);
       const int id = sb2_add_species(dev, geoId[v->geoi], c.data());
@@ -178,6 +316,11 @@ struct Bridge {
     for (size_t r = 0; r < ref.rInfoList.size(); ++r) {
       reactionInfo* ri = ref.rInfoList[r];
       reversePolishInfo* rp = ri->rpInfo;
+      if (ri->reaction && ri->isMemTransport) {  // (the flag is only set for reactions)
+        const int rc2 = addTransport(ri);
+        if (rc2) return rc2;
+        continue;
+      }
       std::vector<sb2_token> toks((size_t)rp->listNum);
       for (int i = 0; i < rp->listNum; ++i) {
         sb2_token t;
@@ -219,6 +362,27 @@ struct Bridge {
         if (!source(v->diffCInfo[a], kind, src)) return 2;
         DEV(sb2_set_diffusion(dev, it->second, a, kind, src));
       }
+      // advection velocities (variableInfo::adCInfo) and the CIP face point values, which the reference keeps at the odd points of
+      // the species' own array (calcPDE.cpp:588-603)
+      bool advected = false;
+      for (int a = 0; a < (int)ref.dimension; ++a) {
+        if (!v->adCInfo || !v->adCInfo[a]) continue;
+        advected = true;
+        int kind, src;
+        if (!source(v->adCInfo[a], kind, src)) return 2;
+        DEV(sb2_set_advection(dev, it->second, a, kind, src));
+        if (kind == SB2_SRC_FIELD) {  // ... and the velocity between the cells (divergence correction, calcPDE.cpp:623-625)
+          const std::vector<double> fv = oddPoints(v->adCInfo[a]->value, a);
+          const int ff = sb2_add_field(dev, fv.data());
+          if (ff < 0) return 2;
+          DEV(sb2_set_advection_faces(dev, it->second, a, ff));
+        }
+      }
+      if (advected)
+        for (int a = 0; a < (int)ref.dimension; ++a) {
+          const std::vector<double> faces = oddPoints(v->value, a);
+          DEV(sb2_upload_faces(dev, it->second, a, faces.data()));
+        }
       for (int side = 0; side < 2 * (int)ref.dimension; ++side) {
         if (!v->boundaryInfo || !v->boundaryInfo[side]) continue;
         variableInfo* b = v->boundaryInfo[side];
