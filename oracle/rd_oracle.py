@@ -7,12 +7,13 @@ What is restated, in the reference's own evaluation order (all file:line relativ
   * the RK4 stage loop of performStep            spatialsimulator.cpp:1350-1492
   * reversePolishRK, the per-cell RPN evaluator   calcPDE.cpp:224-451  (stack discipline, operator semantics,
                                                   reactant -= / product += accumulation)
-  * calcDiffusion                                 calcPDE.cpp:453-562
+  * calcDiffusion (uniform and field-valued coefficients)   calcPDE.cpp:453-562
   * updateSpecies (RK4 combine, k := 0)           spatialsimulator.cpp:1518-1544
   * calcBoundary (Neumann flux, Dirichlet value)  calcPDE.cpp:871-1034, incl. the flux carried in k0 between steps
-  * cipCSLR (CIP-CSLR advection, uniform velocity)  calcPDE.cpp:564-869
+  * cipCSLR (CIP-CSLR advection; uniform and field-valued velocities: face-averaged velocity, divergence correction)  calcPDE.cpp:564-869
   * calcMemTransport (volume species on either side of a membrane, incl. the rpStack[1] rate quirk)  calcPDE.cpp:1036-1482
-Membrane species, field-valued velocities / boundary values raise NotImplementedError.
+  * updateAssignmentRules (ordered rules on parameters and species, re-evaluated after every step)  spatialsimulator.cpp:1566-1581
+Species ON membranes and field-valued boundary values raise NotImplementedError.
 
 Pinned: tests/test_oracle_cpu.py checks this restatement BIT FOR BIT against the fields the unmodified reference
 produced (tests/golden/*.npz) for the Turing, Brusselator, fish and synthetic 2-D / 3-D models.
@@ -173,7 +174,7 @@ class Membrane(object):
 class RDOracle(object):
     """State + oneStep of the restated path."""
 
-    def __init__(self, species, reactions, consts, delta, dimension, rate_rules=()):
+    def __init__(self, species, reactions, consts, delta, dimension, rate_rules=(), fields=None, rules=()):
         self.sp = {s.name: s for s in species}
         self.order = [s.name for s in species]
         self.rx = reactions
@@ -181,6 +182,10 @@ class RDOracle(object):
         # rInfoList[that index] for a rate rule (spatialsimulator.cpp:1455-1461), which is the rule itself only in a model
         # without reactions
         self.rate_rules = list(rate_rules)
+        # variables that are arrays but not integrated (coordinates, parameters and species set by assignments): name -> compact
+        # array; ordered assignment rules (orderedARule): (target, domain mask or None for "every point", tokens)
+        self.fields = dict(fields or {})
+        self.rules = list(rules)
         self.consts = dict(consts)
         self.delta = delta
         self.dimension = dimension
@@ -201,6 +206,8 @@ class RDOracle(object):
                 def operand(name, has_delta):
                     if name in w:
                         return w[name] if has_delta else self.sp[name].u
+                    if name in self.fields:
+                        return self.fields[name]  # no delta array: the raw value (calcPDE.cpp:249-251)
                     raise NotImplementedError("field operand %s" % name)
 
                 for r in self.rx:  # document order, spatialsimulator.cpp:1374-1390
@@ -242,6 +249,23 @@ class RDOracle(object):
                 # calcBoundary(m = 0) after the k's were zeroed: a non-zero flux is parked in k0 and carried into
                 # the next step, whose stage 0 adds it a second time (spatialsimulator.cpp:1540-1542)
                 self._boundary(s, 0)
+            # updateAssignmentRules (spatialsimulator.cpp:1566-1581): the ordered rules re-evaluated on the new state, a species'
+            # rule on the cells of its compartment, a parameter's on every point (reversePolishInitial, calcPDE.cpp:21-222)
+            for target, domain, toks in self.rules:
+                def now(name, has_delta):
+                    if name in self.sp:
+                        return self.sp[name].u
+                    if name in self.fields:
+                        return self.fields[name]
+                    raise NotImplementedError("rule operand %s" % name)
+                value = eval_stream(toks, now, self.consts, self.shape)
+                if target in self.sp:  # a species keeps its arrays (its k's stay zero without reactions); the rule overwrites u
+                    self.sp[target].u[domain] = value[domain]
+                elif domain is None:
+                    self.fields[target] = value.copy()
+                else:
+                    self.fields[target] = self.fields[target].copy()
+                    self.fields[target][domain] = value[domain]
         return t + dt
 
     def _mem_transport(self, r, m, dt):
@@ -352,7 +376,7 @@ class RDOracle(object):
     def _cip(self, s, dt):
         """cipCSLR, calcPDE.cpp:564-869: CIP-CSLR rational-function advection on the doubled grid, one dimension-split
         pass per axis; every pass reads the state before it (val) and writes val_delta, which is then added to the whole
-        grid together with the cross-axis face update (val_delta[cell + 2] + val_delta[cell]) / 2.  Uniform velocities."""
+        grid together with the cross-axis face update (val_delta[cell + 2] + val_delta[cell]) / 2.  Uniform and field-valued velocities."""
         import math
         full = s.full
         nzd, nyd, nxd = full.shape
@@ -384,39 +408,42 @@ class RDOracle(object):
                 m3 = np.where(d4m, m3, np.where(d2m, m2, idx))
                 p1, p2 = np.where(d2p, p1, idx), np.where(d2p, p2, idx)  # :604-611
                 m1, m2 = np.where(d2m, m1, idx), np.where(d2m, m2, idx)
-                D = -math.copysign(1.0, u) * dl
-                xi = u * dt
-                pw_mxi, pw_xi = (-xi) * (-xi), xi * xi
                 v0, vp1, vp2, vp3 = val[idx], val[p1], val[p2], val[p3]
                 vm1, vm2, vm3 = val[m1], val[m2], val[m3]
+                # :612-613 a uniform velocity, or the mean of the cell's and its (collapsed) plus neighbour's
+                field = not np.isscalar(u)
+                ux = (u[idx] + u[p2]) / 2.0 if field else np.full(idx.shape, float(u))
+                D = -np.copysign(1.0, ux) * dl
+                xi = ux * dt
+                pw_mxi, pw_xi = (-xi) * (-xi), xi * xi
+                pos = ux >= 0
                 g_in, g_out = np.zeros(idx.shape), np.zeros(idx.shape)
                 free_p = ((bt >> (1 + 2 * a)) & 1) == 0  # !isBof{X,Y,Z}p
                 free_m = ((bt >> (2 + 2 * a)) & 1) == 0
-                if u >= 0:  # :614-626 flux out through the plus face
-                    beta = ((np.abs(vp1 - v0) + eps) / (np.abs(v0 - vm1) + eps) - 1.0) / D
-                    b = ((1.0 + beta * D) * v0 - vp1) / D
-                else:       # :627-638 flux in through the plus face
-                    beta = ((np.abs(vp1 - vp2) + eps) / (np.abs(vp2 - vp3) + eps) - 1.0) / D
-                    b = ((1.0 + beta * D) * vp2 - vp1) / D
-                den = 1.0 + beta * (-xi)
-                face = (vp1 + 2 * b * (-xi) + beta * b * pw_mxi) / (den * den) - vp1
-                flux = (-vp1 * xi + b * pw_xi) / (-1.0 + beta * xi)
+                with np.errstate(all="ignore"):  # (both branches are evaluated everywhere, one is selected)
+                    # :614-638 the plus face: flux out for ux >= 0, flux in for ux < 0
+                    beta_p = ((np.abs(vp1 - v0) + eps) / (np.abs(v0 - vm1) + eps) - 1.0) / D
+                    b_p = ((1.0 + beta_p * D) * v0 - vp1) / D
+                    beta_n = ((np.abs(vp1 - vp2) + eps) / (np.abs(vp2 - vp3) + eps) - 1.0) / D
+                    b_n = ((1.0 + beta_n * D) * vp2 - vp1) / D
+                    beta, b = np.where(pos, beta_p, beta_n), np.where(pos, b_p, b_n)
+                    den = 1.0 + beta * (-xi)
+                    face = (vp1 + 2 * b * (-xi) + beta * b * pw_mxi) / (den * den) - vp1
+                    if field:  # :623-625 correction due to velocity divergence
+                        face = face + ((dt / (2 * dl)) * (vp1 + face)) * (u[p3] - u[m1])
+                    flux = (-vp1 * xi + b * pw_xi) / (-1.0 + beta * xi)
+                    # :639-648 the minus face: flux in for ux >= 0, flux out for ux < 0
+                    beta2_p = ((np.abs(vm1 - vm2) + eps) / (np.abs(vm2 - vm3) + eps) - 1.0) / D
+                    b2_p = ((1.0 + beta2_p * D) * vm2 - vm1) / D
+                    beta2_n = ((np.abs(vm1 - v0) + eps) / (np.abs(v0 - vp1) + eps) - 1.0) / D
+                    b2_n = ((1.0 + beta2_n * D) * v0 - vm1) / D
+                    beta2, b2 = np.where(pos, beta2_p, beta2_n), np.where(pos, b2_p, b2_n)
+                    flux2 = (-vm1 * xi + b2 * pw_xi) / (-1.0 + beta2 * xi)
                 vd[p1[free_p]] = face[free_p]
-                if u >= 0:
-                    g_out[free_p] = flux[free_p]
-                else:
-                    g_in[free_p] = -flux[free_p]
-                if u >= 0:  # :639-643 flux in through the minus face
-                    beta2 = ((np.abs(vm1 - vm2) + eps) / (np.abs(vm2 - vm3) + eps) - 1.0) / D
-                    b2 = ((1.0 + beta2 * D) * vm2 - vm1) / D
-                else:       # :644-648 flux out through the minus face
-                    beta2 = ((np.abs(vm1 - v0) + eps) / (np.abs(v0 - vp1) + eps) - 1.0) / D
-                    b2 = ((1.0 + beta2 * D) * v0 - vm1) / D
-                flux2 = (-vm1 * xi + b2 * pw_xi) / (-1.0 + beta2 * xi)
-                if u >= 0:
-                    g_in[free_m] = flux2[free_m]
-                else:
-                    g_out[free_m] = -flux2[free_m]
+                g_out[free_p & pos] = flux[free_p & pos]
+                g_in[free_p & ~pos] = -flux[free_p & ~pos]
+                g_in[free_m & pos] = flux2[free_m & pos]
+                g_out[free_m & ~pos] = -flux2[free_m & ~pos]
                 vd[idx] = (g_in - g_out) / dl  # :650 (after the face value: a collapsed face index is the cell itself)
             # :653-673: faces of the other axes move with the mean of the two cells they separate, then val += val_delta
             for b_ax in range(self.dimension):
@@ -575,7 +602,15 @@ def from_simulator(sim, xml_text, dims):
         btypes[comp] = even(sum((bt[:, k].astype(np.uint8) << (k + 1)) for k in range(6)).astype(np.uint8))
     species = []
     for name, comp in var_geo.items():
-        D = [uniform.get(pid) if pid is not None else None for pid in diff.get(name, [None, None, None])]
+        # uniform coefficient: its value; field-valued: the coefficient at the cell itself (calcPDE.cpp:487, dcIndex = index)
+        D = []
+        for pid in diff.get(name, [None, None, None]):
+            if pid is None:
+                D.append(None)
+            elif pid in uniform:
+                D.append(uniform[pid])
+            else:
+                D.append(even(np.asarray(sim.getVariable(pid))))
         bc = None
         if name in bcs:
             bc = {}
@@ -588,9 +623,14 @@ def from_simulator(sim, xml_text, dims):
         if name in advs:
             adv = []
             for pid in advs[name]:
-                if pid is not None and pid not in uniform:
-                    raise NotImplementedError("field-valued advection velocity %s" % pid)
-                adv.append(uniform[pid] if pid is not None else None)
+                # uniform velocity: its value; field-valued: the parameter on every point of the doubled grid (the face-averaged
+                # velocity and the divergence correction read it between the cells too)
+                if pid is None:
+                    adv.append(None)
+                elif pid in uniform:
+                    adv.append(uniform[pid])
+                else:
+                    adv.append(np.array(sim.getVariable(pid))[:(2 * nx - 1) * (2 * ny - 1) * (2 * nz - 1)])
             bt = sim.getBoundaryType(comp)
             extra = {"full": np.asarray(sim.getVariable(name)).reshape(2 * nz - 1, 2 * ny - 1, 2 * nx - 1),
                      "dom_d": sim.getGeometry(comp), "btype_d": sum((bt[:, k].astype(np.uint8) << (k + 1)) for k in range(6))}
@@ -654,9 +694,33 @@ def from_simulator(sim, xml_text, dims):
             raise NotImplementedError("rate rule %s: the reference indexes its reaction list out of range" % target)
         if target in var_geo:
             rate_rules.append((index, masks[var_geo[target]]))
-    if any(r.tag == CORE + "assignmentRule" for r in rules_el):
-        raise NotImplementedError("assignment rules re-evaluated every step are not restated here")
-    return RDOracle(species, reactions, uniform, delta, dimension, rate_rules)
+    # arrays that are not integrated: every non-uniform variable without a delta array (coordinates, parameters and species set by
+    # initial assignments / assignment rules), at the volume cells
+    fields = {}
+    comp_of = {}
+    for line in summary:
+        p = line.split()
+        if p[0] == "var" and p[3] == "0" and p[5] == "1" and p[7] == "0":
+            arr = sim.getVariable(p[1])
+            if arr is not None:
+                fields[p[1]] = even(np.array(arr)[:(2 * nx - 1) * (2 * ny - 1) * (2 * nz - 1)])
+                comp_of[p[1]] = p[9]
+    rules = []
+    i = 0
+    while True:
+        text = sim.getSetupText("arule/%d" % i)
+        if not text:
+            break
+        target, kind, stream = text.split("\n", 2)
+        domain = None
+        if kind == "species":  # only the cells of the species' compartment (isAllArea false)
+            comp = var_geo.get(target, comp_of.get(target))
+            if comp in (None, "-"):
+                raise NotImplementedError("assignment rule on species %s without a geometry" % target)
+            domain = even(sim.getGeometry(comp)) == 1
+        rules.append((target, domain, parse_stream(stream)))
+        i += 1
+    return RDOracle(species, reactions, uniform, delta, dimension, rate_rules, fields, rules)
 
 
 def _count_reactants(xml_text, index):

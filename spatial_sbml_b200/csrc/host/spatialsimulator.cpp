@@ -1381,6 +1381,13 @@ double* SpatialSimulator::getVariable(const std::string& id, int& length) {
         for (int Y = 0; Y < Yi; ++Y)
           for (int X = 0; X < Xi; ++X)
             mir.data[((int64_t)Z * Yi + Y) * Xi + X] = impl->coordinateAt(v, v == m.xVar ? X : v == m.yVar ? Y : Z);
+    } else if (!v->sp && v->hasRpn) {
+      // a parameter set by an initial assignment / assignment rule is evaluated on EVERY point of the doubled grid by the
+      // reference (isAllArea, spatialsimulator.cpp:1126-1139): the points that are not volume cells are filled here
+      for (int Z = 0; Z < Zi; ++Z)
+        for (int Y = 0; Y < Yi; ++Y)
+          for (int X = 0; X < Xi; ++X)
+            if ((X | Y | Z) & 1) mir.data[((int64_t)Z * Yi + Y) * Xi + X] = m.valueAtDoubled(v, X, Y, Z);
     }
   }
   if (fresh || wasStale || !mir.handedOut) {
@@ -1609,6 +1616,13 @@ std::string SpatialSimulator::getSetupText(const std::string& what) {
     const size_t i = (size_t)atoi(what.c_str() + 4);
     if (i < m.rxns.size()) return rpnText(m.rxns[i]->rpn);
     return "";
+  }
+  if (what.compare(0, 6, "arule/") == 0) {
+    // ordered assignment rules (orderedARule of the reference): the target's id, "species" / "parameter", then its stream
+    const size_t i = (size_t)atoi(what.c_str() + 6);
+    if (i >= m.orderedAssignmentRules.size()) return "";
+    const Var* v = m.orderedAssignmentRules[i];
+    return v->id + "\n" + (v->sp ? "species" : "parameter") + "\n" + rpnText(v->rpn);
   }
   if (what.compare(0, 5, "refs/") == 0) {
     const size_t i = (size_t)atoi(what.c_str() + 5);

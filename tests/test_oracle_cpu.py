@@ -36,7 +36,11 @@ RESTATED = {"turing_tiny": 1000, "turing_tiny_cl": 100, "turing_uniform": 100, "
             "syn_raterules_2d": 100,
             # geometry from an image + a membrane transport; six species
             "syn_sampled_2d": 100, "syn_chain6_2d": 100,
-            "syn_advection_uniform_2d": 100, "syn_advection_uniform_3d": 40}
+            "syn_advection_uniform_2d": 100, "syn_advection_uniform_3d": 40,
+            # field-valued advection velocities (face-averaged velocity, divergence correction) and diffusion coefficients
+            "syn_advection_field_2d": 100, "syn_advection_field_3d": 40, "syn_fieldcoeff_2d": 100, "syn_fieldcoeff_3d": 40,
+            # assignment rules re-evaluated every step (updateAssignmentRules) on parameters and on a species, field operands in laws
+            "syn_rules_2d": 100, "syn_rules_3d": 40}
 
 
 def build(case):
@@ -65,17 +69,10 @@ def test_restatement_matches_reference_bit_for_bit(case):
     assert done > 0
 
 
-# Goldens the numpy restatement does not cover: species ON a membrane (calcMemDiffusion, binding, pseudo-membrane fill) and
-# per-step assignment rules.  Those
+# Goldens the numpy restatement does not cover: species ON a membrane (calcMemDiffusion, binding, pseudo-membrane fill).  Those
 # paths are pinned to the reference directly: the device is compared with the reference's own fields (tests/test_parity_gpu.py)
 # and the host set-up (Voronoi neighbours, s_ij, d_ij, normals, initial values) with the reference's arrays (tests/test_host_cpu.py).
-NOT_RESTATED = {"syn_membrane_2d", "syn_membrane_box_2d", "syn_membrane_3d", "syn_membrane_mixed_2d",
-                # assignment rules re-evaluated every step (updateAssignmentRules): pinned the same way
-                "syn_rules_2d", "syn_rules_3d",
-                # field-valued diffusion coefficients (the restatement takes uniform coefficients only)
-                "syn_fieldcoeff_2d", "syn_fieldcoeff_3d",
-                # field-valued advection velocities
-                "syn_advection_field_2d", "syn_advection_field_3d"}
+NOT_RESTATED = {"syn_membrane_2d", "syn_membrane_box_2d", "syn_membrane_3d", "syn_membrane_mixed_2d"}
 
 
 def test_every_golden_case_is_restated():
@@ -101,3 +98,31 @@ def test_reference_build_reproduces_the_golden(case, tmp_path):
         for sp in [str(v) for v in g["species"]]:
             full = d["step/%d/%s" % (s, sp)].reshape(2 * nz - 1, 2 * ny - 1, 2 * nx - 1)
             assert np.array_equal(full[::2, ::2, ::2], g["step/%d/%s" % (s, sp)]), "%s step %d %s" % (case, s, sp)
+
+
+@pytest.mark.parametrize("case", ["turing_tiny", "syn_advection_field_2d", "syn_advection_field_3d", "syn_fieldcoeff_2d", "fish"])
+def test_every_variable_array_equals_the_references(case, tmp_path):
+    """getVariable() of EVERY non-uniform variable - species, coordinates, parameters set by initial assignments (which the
+    reference evaluates on every point of the doubled grid, spatialsimulator.cpp:1126-1139) - against the reference's own value[]
+    arrays, dumped by the reference build for this test."""
+    drv = os.path.join(REPO, "oracle", "_ref", "ref_driver")
+    if not os.path.exists(drv):
+        pytest.skip("oracle/_ref/ref_driver is not built (needs /root/reference; __graft_entry__.build() makes it)")
+    g = load_golden(case)
+    nx, ny, nz = [int(v) for v in g["dims"]]
+    out = str(tmp_path / "dump.sbd")
+    subprocess.run([drv, "dump", model_path(case), str(nx), str(ny), str(nz), repr(float(g["dt"])), out], check=True, stdout=subprocess.DEVNULL)
+    d = read_sbd(out)
+    sim = sb.SpatialSimulator(host_only=True)
+    sim.initFromFile(model_path(case), nx, ny, nz)
+    checked = 0
+    for name in d["varNames"].split():
+        key = "var/%s/value" % name
+        if key not in d or d[key].size <= 1:
+            continue
+        ours = sim.getVariable(name)
+        assert ours is not None, name
+        assert np.array_equal(np.asarray(ours)[:d[key].size], d[key]), name
+        checked += 1
+    assert checked >= 4
+    sim.close()
