@@ -11,15 +11,20 @@ What is restated, in the reference's own evaluation order (all file:line relativ
   * updateSpecies (RK4 combine, k := 0)           spatialsimulator.cpp:1518-1544
   * calcBoundary (Neumann flux, Dirichlet value)  calcPDE.cpp:871-1034, incl. the flux carried in k0 between steps
   * cipCSLR (CIP-CSLR advection; uniform and field-valued velocities: face-averaged velocity, divergence correction)  calcPDE.cpp:564-869
-  * calcMemTransport (volume species on either side of a membrane, incl. the rpStack[1] rate quirk)  calcPDE.cpp:1036-1482
+  * calcMemTransport (volume species on either side of a membrane, species bound to / released from the membrane itself,
+    incl. the rpStack[1] rate quirk)              calcPDE.cpp:1036-1482, call sites spatialsimulator.cpp:1392-1450
+  * calcMemDiffusion (species ON a membrane: finite volumes over the Voronoi neighbours)  calcPDE.cpp:1484-1581
+  * reactions between species on a membrane (reversePolishRK over the membrane's points) and their update
   * updateAssignmentRules (ordered rules on parameters and species, re-evaluated after every step)  spatialsimulator.cpp:1566-1581
-Species ON membranes and field-valued boundary values raise NotImplementedError.
+  * the pseudo-membrane fill that ends updateAssignmentRules  spatialsimulator.cpp:1609-1663
+Field-valued boundary values, and membrane species as operands of volume reactions or rules, raise NotImplementedError.
 
 Pinned: tests/test_oracle_cpu.py checks this restatement BIT FOR BIT against the fields the unmodified reference
-produced (tests/golden/*.npz) for the Turing, Brusselator, fish and synthetic 2-D / 3-D models.
+produced (tests/golden/*.npz): every golden case (38), every stored step.
 
-Every array is COMPACT (nz, ny, nx): volume cells only; compact cell (i,j,k) is the reference's doubled-grid point
-(2i,2j,2k) (spatialsimulator.cpp:354-358), so the reference's index +-2 is +-1 here.
+Every array of a volume species is COMPACT (nz, ny, nx): volume cells only; compact cell (i,j,k) is the reference's
+doubled-grid point (2i,2j,2k) (spatialsimulator.cpp:354-358), so the reference's index +-2 is +-1 here.  Advected species and
+species on membranes keep the reference's whole doubled grid.
 """
 import xml.etree.ElementTree as ET
 
@@ -153,30 +158,55 @@ class Species(object):
         self.bc = bc
 
 
+class MemSpecies(object):
+    """A species ON a membrane: like the reference it lives on the whole doubled grid (flat arrays); only the membrane's
+    domainIndex points are integrated, the pseudo-membrane points are filled from their neighbours after every step."""
+
+    def __init__(self, name, val, membrane, D, comp=None):
+        self.name, self.comp = name, comp
+        self.val = np.array(val, dtype=np.float64).reshape(-1)
+        self.k = [np.zeros_like(self.val) for _ in range(4)]
+        self.membrane = membrane   # Membrane (with the Voronoi data)
+        self.D = D                 # diffCInfo[0]: float, array on the doubled grid, or None
+
+
 class Reaction(object):
-    def __init__(self, toks, refs, n_reactants, domain, is_reaction=True, membrane=None):
+    def __init__(self, toks, refs, n_reactants, domain, is_reaction=True, membrane=None, on_membrane=None):
         self.toks, self.refs, self.n_reactants, self.domain, self.is_reaction = toks, refs, n_reactants, domain, is_reaction
-        self.membrane = membrane  # Membrane of a membrane-transport reaction (calcMemTransport), else None
+        # membrane transport: the Membranes calcMemTransport is called with, in call order; else None
+        self.membrane = membrane
+        # an ordinary reaction whose first species reference lives on a membrane: that Membrane (reversePolishRK over its points)
+        self.on_membrane = on_membrane
 
 
 class Membrane(object):
     """What calcMemTransport reads of a membrane compartment, all on the reference's doubled grid (flat indices)."""
 
-    def __init__(self, points, is_domain, btype, normals, vol_domains, shape_d):
+    def __init__(self, points, is_domain, btype, normals, vol_domains, shape_d, pseudo=(), vor=None):
         self.points = points            # domainIndex of the membrane, in the reference's order
         self.is_domain = is_domain      # isDomain of the membrane (1 membrane point, 2 pseudo membrane)
         self.btype = btype              # per point: bits 1..6 = isBofXp, Xm, Yp, Ym, Zp, Zm
         self.normals = normals          # flat index -> (nx, ny, nz)
-        self.vol_domains = vol_domains  # species name -> isDomain of its volume compartment (flat, doubled grid)
+        self.vol_domains = vol_domains  # species name -> isDomain of its compartment (flat, doubled grid), membrane species too
         self.shape_d = shape_d          # (Zindex, Yindex, Xindex)
+        self.pseudo = list(pseudo)      # pseudoMemIndex
+        # voronoiInfo of the points, rows in the order of `points`: (adjacent index, s_ij, d_ij), each [n, 6] with the columns
+        # XY[0], YZ[0], XZ[0], XY[1], YZ[1], XZ[1]
+        self.vor = vor
+        self.points_a = np.array(points, dtype=np.int64)
+        self.pseudo_pairs = None        # (pseudo point, neighbour a, neighbour b), built on first use
 
 
 class RDOracle(object):
     """State + oneStep of the restated path."""
 
-    def __init__(self, species, reactions, consts, delta, dimension, rate_rules=(), fields=None, rules=()):
+    def __init__(self, species, reactions, consts, delta, dimension, rate_rules=(), fields=None, rules=(), mem_species=()):
         self.sp = {s.name: s for s in species}
         self.order = [s.name for s in species]
+        # species on membranes, in the model's species order (they share no array with the volume species, so the two lists can
+        # be walked one after the other where the reference walks listOfSpecies once)
+        self.msp = {s.name: s for s in mem_species}
+        self.morder = [s.name for s in mem_species]
         self.rx = reactions
         # (index of the rule in the model's rule list, domain mask of its variable's compartment): the reference evaluates
         # rInfoList[that index] for a rate rule (spatialsimulator.cpp:1455-1461), which is the rule itself only in a model
@@ -214,7 +244,11 @@ class RDOracle(object):
                     if r is None or not r.is_reaction:
                         continue  # entries without a Reaction (rate rules) are skipped here (:1376-1377)
                     if r.membrane is not None:
-                        self._mem_transport(r, m, dt)
+                        for mem in r.membrane:  # one calcMemTransport per membrane, spatialsimulator.cpp:1428-1450
+                            self._mem_transport(r, mem, m, dt)
+                        continue
+                    if r.on_membrane is not None:
+                        self._mem_reaction(r, m, dt)
                         continue
                     rate = eval_stream(r.toks, operand, self.consts, self.shape)
                     for k, (name, stoich, is_var) in enumerate(r.refs):
@@ -237,6 +271,8 @@ class RDOracle(object):
                     s = self.sp[n]
                     self._diffusion(s, w[n], m)
                     self._boundary(s, m)
+                for n in self.morder:
+                    self._mem_diffusion(self.msp[n], m, dt)
             for n in self.order:  # advection after the RK stages, before the update (spatialsimulator.cpp:1482-1491)
                 if self.sp[n].full is not None:
                     self._cip(self.sp[n], dt)
@@ -249,6 +285,12 @@ class RDOracle(object):
                 # calcBoundary(m = 0) after the k's were zeroed: a non-zero flux is parked in k0 and carried into
                 # the next step, whose stage 0 adds it a second time (spatialsimulator.cpp:1540-1542)
                 self._boundary(s, 0)
+            for n in self.morder:  # updateSpecies over the membrane's domainIndex (no boundary conditions on a membrane)
+                s = self.msp[n]
+                pts = s.membrane.points_a
+                s.val[pts] += (dt * (s.k[0] + 2.0 * s.k[1] + 2.0 * s.k[2] + s.k[3]) / 6.0)[pts]
+                for m in range(4):
+                    s.k[m][pts] = 0.0
             # updateAssignmentRules (spatialsimulator.cpp:1566-1581): the ordered rules re-evaluated on the new state, a species'
             # rule on the cells of its compartment, a parameter's on every point (reversePolishInitial, calcPDE.cpp:21-222)
             for target, domain, toks in self.rules:
@@ -266,9 +308,116 @@ class RDOracle(object):
                 else:
                     self.fields[target] = self.fields[target].copy()
                     self.fields[target][domain] = value[domain]
+            for n in self.morder:  # pseudo-membrane points, at the end of updateAssignmentRules (spatialsimulator.cpp:1609-1663)
+                self._pseudo_fill(self.msp[n])
         return t + dt
 
-    def _mem_transport(self, r, m, dt):
+    def _mem_reaction(self, r, m, dt):
+        """reversePolishRK (calcPDE.cpp:224-451) over the domainIndex of a membrane: every operand is read AT the membrane point
+        (val + rk[m]*dt*delta[m-1] when it has a delta array), every variable species reference gains / loses stoich * rate there."""
+        rk = (0.0, 0.5, 0.5, 1.0)
+        pts = r.on_membrane.points_a
+
+        def operand(name, has_delta):
+            if name not in self.msp:
+                raise NotImplementedError("operand %s of a reaction on a membrane is not a membrane species" % name)
+            s = self.msp[name]
+            if m == 0 or not has_delta:
+                return s.val[pts]
+            return s.val[pts] + (rk[m] * dt) * s.k[m - 1][pts]
+
+        rate = eval_stream(r.toks, operand, self.consts, pts.shape)
+        for k, (name, stoich, is_var) in enumerate(r.refs):
+            if not is_var:
+                continue
+            if name not in self.msp:
+                raise NotImplementedError("volume species %s in a reaction on a membrane" % name)
+            km = self.msp[name].k[m]
+            if k < r.n_reactants:
+                km[pts] -= stoich * rate
+            else:
+                km[pts] += stoich * rate
+
+    def _mem_diffusion(self, s, m, dt):
+        """calcMemDiffusion, calcPDE.cpp:1484-1581: finite volumes over the Voronoi neighbours of each membrane point.  Per point
+        area = sum(d_ij * s_ij) / 2 (2-D) or / 4 (3-D) over the six neighbour slots; per plane that the point's boundary type
+        selects, both neighbours j add D * (v_j - v_i) * s_ij / d_ij / area — associated as ((D * dv * s) / d) / area in the
+        first stage (:1533) and as (D * ((dv * s) / d)) / area in the later ones (:1555-1557)."""
+        if s.D is None:
+            return
+        rk = (0.0, 0.5, 0.5, 1.0)
+        mem = s.membrane
+        pts = mem.points_a
+        adj, si, di = mem.vor
+        area = np.zeros(len(pts))
+        for c in range(6):  # j = 0: XY, YZ, XZ; j = 1: XY, YZ, XZ (:1521-1525)
+            area = area + di[:, c] * si[:, c]
+        area = area / (2.0 if self.dimension == 2 else 4.0)
+        D = s.D if np.isscalar(s.D) else np.asarray(s.D).reshape(-1)[pts]  # dcIndex = index for a field-valued coefficient
+        bt = mem.btype[pts]
+        xp, xm, yp, ym, zp, zm = [(bt >> b) & 1 == 1 for b in range(1, 7)]
+        planes = [(0, (xp & xm) | (yp & ym))]
+        if self.dimension == 3:
+            planes += [(1, (yp & ym) | (zp & zm)), (2, (xp & xm) | (zp & zm))]
+
+        def stage(idx):
+            if m == 0:
+                return s.val[idx]
+            return s.val[idx] + (rk[m] * dt) * s.k[m - 1][idx]
+
+        here = stage(pts)
+        km = s.k[m]
+        for col, use in planes:
+            if not use.any():
+                continue
+            for j in range(2):
+                c = col + 3 * j
+                a = adj[use, c]
+                if (a < 0).any():
+                    raise NotImplementedError("membrane point without a Voronoi neighbour in a plane its boundary type selects")
+                dv = stage(a) - here[use]
+                Du = D if np.isscalar(D) else D[use]
+                if m == 0:
+                    km[pts[use]] += ((Du * dv * si[use, c]) / di[use, c]) / area[use]
+                else:
+                    km[pts[use]] += Du * ((dv * si[use, c]) / di[use, c]) / area[use]
+
+    def _pseudo_fill(self, s):
+        """spatialsimulator.cpp:1609-1663: a pseudo-membrane point takes the smaller value of the first pair of its axis
+        neighbours that are both membrane points (isDomain == 1), pairs tried in the reference's order."""
+        mem = s.membrane
+        if mem.pseudo_pairs is None:
+            nzd, nyd, nxd = mem.shape_d
+            n = nxd * nyd * nzd
+            d3 = self.dimension == 3
+            first, second, targets = [], [], []
+            for index in mem.pseudo:
+                z, rem = divmod(index, nxd * nyd)
+                y, x = divmod(rem, nxd)
+
+                def on(dx, dy, dz):
+                    xx, yy, zz = x + dx, y + dy, z + dz
+                    if not (0 <= xx < nxd and 0 <= yy < nyd and 0 <= zz < nzd):
+                        return -1
+                    f = zz * nyd * nxd + yy * nxd + xx
+                    return f if mem.is_domain[f] == 1 else -1
+                Xp, Xm, Yp, Ym = on(1, 0, 0), on(-1, 0, 0), on(0, 1, 0), on(0, -1, 0)
+                Zp, Zm = (on(0, 0, 1), on(0, 0, -1)) if d3 else (-1, -1)
+                order = [(Xp, Xm), (Yp, Ym), (Zp, Zm), (Xp, Yp), (Xp, Ym), (Xp, Zp), (Xp, Zm), (Xm, Yp), (Xm, Ym), (Xm, Zp), (Xm, Zm),
+                         (Yp, Zp), (Yp, Zm), (Ym, Zp), (Ym, Zm)]
+                for a, b in order:
+                    if a >= 0 and b >= 0:
+                        targets.append(index)
+                        first.append(a)
+                        second.append(b)
+                        break
+            del n
+            mem.pseudo_pairs = (np.array(targets, dtype=np.int64), np.array(first, dtype=np.int64), np.array(second, dtype=np.int64))
+        t, a, b = mem.pseudo_pairs
+        if len(t):
+            s.val[t] = np.minimum(s.val[a], s.val[b])
+
+    def _mem_transport(self, r, mem, m, dt):
         """calcMemTransport, calcPDE.cpp:1036-1482, for volume species on either side of a membrane.  Per membrane point
         (not on the frame, isDomain == 1): the rate law is evaluated with every volume operand taken from the adjacent cell
         of whichever side lies in that species' domain, extrapolated 1.5*v(+-1) - 0.5*v(+-3) when the next cell is in the
@@ -278,7 +427,6 @@ class RDOracle(object):
         `if (st_index > 1) st_index--` (:1392-1393) makes the rate rpStack[1] for a well-formed law (the stale right operand
         of the last binary operator), not the result in rpStack[0]."""
         import math
-        mem = r.membrane
         nzd, nyd, nxd = mem.shape_d
         n_pts = nxd * nyd * nzd
         rk = (0.0, 0.5, 0.5, 1.0)
@@ -307,6 +455,11 @@ class RDOracle(object):
             for t in r.toks:
                 if t[0] == "V":
                     name, has_delta = t[1], t[2]
+                    if name in self.msp and has_delta:  # a symbol on the membrane: its value at the point (:1214-1218)
+                        ms = self.msp[name]
+                        stack[st] = float(ms.val[index]) if m == 0 else float(ms.val[index]) + rk[m] * dt * float(ms.k[m - 1][index])
+                        st += 1
+                        continue
                     if name not in self.sp or not has_delta:
                         raise NotImplementedError("membrane-transport operand %s" % name)
                     sp = self.sp[name]
@@ -361,17 +514,25 @@ class RDOracle(object):
                 continue
             n_a = abs(mem.normals[index][a])
             for j, (name, stoich, is_var) in enumerate(r.refs):
-                if not is_var or name not in self.sp:
+                if not is_var or (name not in self.sp and name not in self.msp):
+                    continue
+                dom = mem.vol_domains[name]
+                sign = -1.0 if j < r.n_reactants else 1.0
+                amount = n_a * stoich * rate / self.delta[a]
+                if name in self.msp:
+                    km = self.msp[name].k[m]
+                    for nb in (index + strides[a], index - strides[a]):
+                        if dom[nb] == 1:
+                            km[nb] += sign * amount
+                    if dom[index] == 1:  # binding: the species lives on the point itself (:1406-1408)
+                        km[index] += sign * (n_a * stoich * rate / (self.delta[a] / 2.0))
                     continue
                 sp = self.sp[name]
-                dom = mem.vol_domains[name]
-                amount = n_a * stoich * rate / self.delta[a]
+                if dom[index] == 1:
+                    raise NotImplementedError("volume species whose domain holds a membrane point")
                 for nb in (index + strides[a], index - strides[a]):  # plus side first, then minus side
                     if dom[nb] == 1:
-                        if j < r.n_reactants:
-                            sp.k[m][cell(nb)] -= amount
-                        else:
-                            sp.k[m][cell(nb)] += amount
+                        sp.k[m][cell(nb)] += sign * amount
 
     def _cip(self, s, dt):
         """cipCSLR, calcPDE.cpp:564-869: CIP-CSLR rational-function advection on the doubled grid, one dimension-split
@@ -595,6 +756,54 @@ def from_simulator(sim, xml_text, dims):
             mem_adjacent[p[1]] = (p[p.index("adjacent") + 1], p[p.index("adjacent") + 2])
     if features:
         raise NotImplementedError("not restated here: " + ", ".join(sorted(features)))
+    shape_d = (2 * nz - 1, 2 * ny - 1, 2 * nx - 1)
+    n_d = shape_d[0] * shape_d[1] * shape_d[2]
+    # species on membranes are kept apart from the volume species
+    mem_geo = {n: c for n, c in var_geo.items() if c in mem_adjacent}
+    var_geo = {n: c for n, c in var_geo.items() if c not in mem_adjacent}
+    if not var_geo:
+        raise NotImplementedError("a model without volume species")
+    flat_domain = {}
+
+    def domain_of(comp):  # isDomain of a compartment on the doubled grid (a copy: the simulator hands out borrowed pointers)
+        if comp not in flat_domain:
+            flat_domain[comp] = np.array(sim.getGeometry(comp)).reshape(-1)[:n_d]
+        return flat_domain[comp]
+
+    membranes = {}
+
+    def membrane_of(comp):
+        """everything calcMemTransport / calcMemDiffusion read of membrane compartment `comp`"""
+        if comp in membranes:
+            return membranes[comp]
+        bt = sim.getBoundaryType(comp)
+        normals = {}
+        for line in sim.getSetupText("normals/" + comp).splitlines():
+            q = line.split()
+            normals[int(q[0])] = (float(q[1]), float(q[2]), float(q[3]))
+        points = [int(v) for v in sim.getSetupText("memindex/" + comp).split()]
+        pseudo = [int(v) for v in sim.getSetupText("pseudo/" + comp).split()]
+        rows = [line.split() for line in sim.getSetupText("voronoi/" + comp).splitlines()]
+        vor = None
+        if rows:
+            if len(rows) != len(points):
+                raise NotImplementedError("voronoi rows do not match the membrane's points")
+            vor = (np.array([[int(v) for v in q[0:6]] for q in rows], dtype=np.int64),
+                   np.array([[float(v) for v in q[6:12]] for q in rows]), np.array([[float(v) for v in q[12:18]] for q in rows]))
+        doms = {n: domain_of(c) for n, c in list(var_geo.items()) + list(mem_geo.items())}
+        membranes[comp] = Membrane(points, domain_of(comp), sum((bt[:, k].astype(np.uint8) << (k + 1)) for k in range(6)).astype(np.uint8),
+                                   normals, doms, shape_d, pseudo, vor)
+        return membranes[comp]
+
+    mem_species = []
+    for name, comp in mem_geo.items():
+        pid = diff.get(name, [None, None, None])[0]  # calcMemDiffusion reads diffCInfo[0] only
+        D = None if pid is None else uniform[pid] if pid in uniform else np.array(sim.getVariable(pid))[:n_d]
+        if name in bcs or name in advs:
+            raise NotImplementedError("boundary condition / advection on membrane species %s" % name)
+        mem_species.append(MemSpecies(name, np.array(sim.getVariable(name))[:n_d], membrane_of(comp), D, comp))
+        if D is not None and mem_species[-1].membrane.vor is None:
+            raise NotImplementedError("membrane %s has no Voronoi data" % comp)
     masks, btypes = {}, {}
     for comp in set(var_geo.values()):
         masks[comp] = even(sim.getGeometry(comp)) == 1
@@ -652,32 +861,40 @@ def from_simulator(sim, xml_text, dims):
             i += 1
             continue
         dom = None
+        on_mem = None
         for name, _, _ in refs:  # geometry of the first species reference that has one (spatialsimulator.cpp:1381-1390)
             if name in var_geo:
                 dom = masks[var_geo[name]]
                 break
+            if name in mem_geo:
+                on_mem = membrane_of(mem_geo[name])
+                break
         if i in transport_rxn:
-            # the membrane between the compartments of the first reactant and the first product (spatialsimulator.cpp:1394-1438)
+            # calcMemTransport over the membrane between the compartments of the first reactant and the first product when both
+            # are volumes (spatialsimulator.cpp:1428-1438); when exactly one of them is a volume, over the membrane the other one
+            # lives on (binding / unbinding, :1440-1450)
             names = [name for name, _, _ in refs]
-            if n_reactants < 1 or len(names) <= n_reactants or names[0] not in var_geo or names[n_reactants] not in var_geo:
-                raise NotImplementedError("membrane transport between species without a volume geometry")
-            pair = {var_geo[names[0]], var_geo[names[n_reactants]]}
-            comp = [c for c, adj in mem_adjacent.items() if set(adj) == pair]
-            if not comp:
-                raise NotImplementedError("no membrane between %s" % sorted(pair))
-            comp = comp[0]
-            bt = sim.getBoundaryType(comp)
-            normals = {}
-            for line in sim.getSetupText("normals/" + comp).splitlines():
-                q = line.split()
-                normals[int(q[0])] = (float(q[1]), float(q[2]), float(q[3]))
-            points = [int(v) for v in sim.getSetupText("memindex/" + comp).split()]
-            # (copies: the simulator hands out borrowed pointers into its own arrays)
-            vol_domains = {n: np.array(sim.getGeometry(var_geo[n])).reshape(-1) for n in names if n in var_geo}
-            mem = Membrane(points, np.array(sim.getGeometry(comp)).reshape(-1),
-                           sum((bt[:, k].astype(np.uint8) << (k + 1)) for k in range(6)).astype(np.uint8), normals, vol_domains,
-                           (2 * nz - 1, 2 * ny - 1, 2 * nx - 1))
-            reactions.append(Reaction(parse_stream(text), refs, n_reactants, None, membrane=mem))
+            geo_of = dict(var_geo)
+            geo_of.update(mem_geo)
+            if n_reactants < 1 or len(names) <= n_reactants or names[0] not in geo_of or names[n_reactants] not in geo_of:
+                raise NotImplementedError("membrane transport between species without a geometry")
+            rg, pg = geo_of[names[0]], geo_of[names[n_reactants]]
+            calls = []
+            for c, adj in mem_adjacent.items():  # geoInfoList order
+                if adj == (rg, pg) or adj == (pg, rg):
+                    calls.append(membrane_of(c))
+                    break
+            r_vol, p_vol = rg not in mem_adjacent, pg not in mem_adjacent
+            if r_vol != p_vol:
+                if not r_vol:
+                    calls.append(membrane_of(rg))
+                if not p_vol:
+                    calls.append(membrane_of(pg))
+            if not calls and r_vol and p_vol:
+                raise NotImplementedError("no membrane between %s" % sorted((rg, pg)))
+            reactions.append(Reaction(parse_stream(text), refs, n_reactants, None, membrane=calls))
+        elif on_mem is not None:
+            reactions.append(Reaction(parse_stream(text), refs, n_reactants, None, on_membrane=on_mem))
         elif dom is not None:
             reactions.append(Reaction(parse_stream(text), refs, n_reactants, dom))
         else:
@@ -720,7 +937,7 @@ def from_simulator(sim, xml_text, dims):
             domain = even(sim.getGeometry(comp)) == 1
         rules.append((target, domain, parse_stream(stream)))
         i += 1
-    return RDOracle(species, reactions, uniform, delta, dimension, rate_rules, fields, rules)
+    return RDOracle(species, reactions, uniform, delta, dimension, rate_rules, fields, rules, mem_species)
 
 
 def _count_reactants(xml_text, index):

@@ -175,6 +175,47 @@ def test_large_grid_against_the_restated_oracle():
     sim.close()
 
 
+@pytest.mark.parametrize("dims,kind", [((97, 83, 1), "membrane"), ((61, 70, 1), "membrane_box"), ((90, 77, 1), "membrane_mixed"),
+                                       ((34, 30, 27), "membrane")])
+def test_membrane_species_against_the_restated_oracle(dims, kind):
+    """Species ON a membrane at sizes the golden files do not cover: surface diffusion over the Voronoi neighbours, binding /
+    unbinding, a reaction on the membrane and the pseudo-membrane fill, against the numpy restatement (itself bit for bit on the
+    reference's four membrane goldens).  Volume cells and membrane points alike; 1e-10 as for the goldens (the device adds a
+    cell's transport terms before its reaction terms)."""
+    import os
+    import sys
+    import spatial_sbml_b200 as sb
+    from spatial_sbml_b200 import synthetic
+    from conftest import REPO
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import rd_oracle
+    model = getattr(synthetic, kind)(dims[0], dims[1], dims[2] if dims[2] > 1 else None)
+    host = sb.SpatialSimulator(host_only=True)
+    host.initFromString(model, *dims)
+    orc = rd_oracle.from_simulator(host, model, dims)
+    host.close()
+    assert orc.morder == ["M", "N"]
+    sim = sb.SpatialSimulator()
+    sim.initFromString(model, *dims)
+    n_d = (2 * dims[0] - 1) * (2 * dims[1] - 1) * (2 * dims[2] - 1)
+    steps = 12
+    for t in range(steps):
+        orc.one_step(t, 0.05)
+    sim.runSteps(0, 0.05, steps)
+    for sp in orc.order:
+        assert rel_linf(sim.getVariableCompact(sp), orc.sp[sp].u) <= 1e-10, (dims, kind, sp)
+    for sp in orc.morder:
+        mem = orc.msp[sp].membrane
+        at = np.sort(np.concatenate([mem.points_a, np.array(mem.pseudo, dtype=np.int64)]))
+        got = np.array(sim.getVariable(sp))[:n_d][at]
+        sim.releaseVariable(sp)
+        want = orc.msp[sp].val[at]
+        assert np.abs(want).max() > 0 and np.isfinite(got).all()
+        assert rel_linf(got, want) <= 1e-10, (dims, kind, sp)
+    assert sim.getDeviceLaunchCount() > 0
+    sim.close()
+
+
 def test_uniform_state_is_preserved_at_full_size():
     """Size-independent property at a BASELINE-scale grid (4096 x 4096): a spatially uniform Brusselator state stays
     uniform bit for bit (every stencil term is exactly zero, every cell sees the same reaction arithmetic), whatever
