@@ -10,17 +10,24 @@
 //   ref_bridge <model.xml> <xdim> <ydim> <zdim> <dt> <steps>
 //
 // Covered: species in volumes, reactions and rate rules, uniform and field-valued diffusion coefficients, Neumann / Dirichlet
-// boundary conditions, CIP-CSLR advection with uniform and field-valued velocities, membrane transport between two volumes.
-// Refused (exit 3): species on membranes (and binding to them), assignment rules — the
-// library has them (see csrc/host/spatialsimulator.cpp for the same flattening written against our own host model), the
-// bridge keeps to what the reference's own example models (BASELINE configs 1-4) need.
+// boundary conditions, CIP-CSLR advection with uniform and field-valued velocities, membrane transport between two volumes,
+// species ON membranes (point sets from domainIndex / pseudoMemIndex, surface diffusion from the reference's voronoiInfo table,
+// reactions on the membrane, binding / unbinding, the pseudo-membrane fill), assignment rules re-evaluated every step.
+// Refused (exit 3): 1-D models; assignment rules on membrane species.
 #define private public  // (test-only access to varInfoList / geoInfoList / rInfoList, as in ref_driver.cpp)
 #include "spatialsimulator.h"
 #undef private
+#include "searchFunction.h"
 
 #include <sbml/SBMLTypes.h>
 #include <sbml/packages/spatial/common/SpatialExtensionTypes.h>
 
+#include <execinfo.h>
+#include <malloc.h>
+#include <signal.h>
+#include <unistd.h>
+
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -87,7 +94,18 @@ struct Bridge {
   std::map<const double*, int> constSlot;  // address of a uniform double the streams alias -> slot (astFunction.cpp:76-81)
   std::vector<const double*> constAddr;
   int timeSlot;
+  // a membrane that hosts species: its storage points (membrane + pseudo-membrane points, ascending doubled-grid index)
+  struct PointSet { int id; std::vector<int64_t> storage; std::map<int64_t, int> at; };
+  std::map<GeometryInfo*, PointSet> pointSets;
+  std::map<variableInfo*, int> memSpeciesId;
   explicit Bridge(SpatialSimulator& r) : ref(r), dev(NULL), timeSlot(-1) {}
+
+  int storageOf(GeometryInfo* g, int64_t idx) const {
+    std::map<GeometryInfo*, PointSet>::const_iterator it = pointSets.find(g);
+    if (it == pointSets.end()) return -1;
+    std::map<int64_t, int>::const_iterator q = it->second.at.find(idx);
+    return q == it->second.at.end() ? -1 : q->second;
+  }
 
   int64_t even(int i, int j, int k) const { return ((int64_t)(2 * k) * ref.Yindex + 2 * j) * ref.Xindex + 2 * i; }
   std::vector<double> compact(const double* full) const {
@@ -171,13 +189,26 @@ struct Bridge {
     if (r->getNumReactants() == 0 || r->getNumProducts() == 0) return 0;
     GeometryInfo* rg = geoOfSpecies(r->getReactant(0)->getSpecies());
     GeometryInfo* pg = geoOfSpecies(r->getProduct(0)->getSpecies());
-    if (!rg || !pg || !rg->isVol || !pg->isVol) { fprintf(stderr, "ref_bridge: binding to a membrane species is outside the bridge's scope\n"); return 3; }
-    GeometryInfo* mem = NULL;
-    for (size_t j = 0; j < ref.geoInfoList.size() && !mem; ++j) {
+    // every membrane the reference calls calcMemTransport on for this reaction, in call order (spatialsimulator.cpp:1428-1450):
+    // the membrane between the two compartments, then — binding / unbinding — the membrane one side lives on
+    std::vector<GeometryInfo*> mems;
+    for (size_t j = 0; j < ref.geoInfoList.size(); ++j) {
       GeometryInfo* g = ref.geoInfoList[j];
-      if (!g->isVol && ((g->adjacentGeo1 == rg && g->adjacentGeo2 == pg) || (g->adjacentGeo1 == pg && g->adjacentGeo2 == rg))) mem = g;
+      if (!g->isVol && ((g->adjacentGeo1 == rg && g->adjacentGeo2 == pg) || (g->adjacentGeo1 == pg && g->adjacentGeo2 == rg))) { mems.push_back(g); break; }
     }
-    if (!mem) return 0;  // no membrane between the two compartments: nothing happens
+    const bool haveRV = rg && rg->isVol, havePV = pg && pg->isVol;
+    if (haveRV != havePV) {
+      if (!haveRV && rg) mems.push_back(rg);
+      if (!havePV && pg) mems.push_back(pg);
+    }
+    for (size_t q = 0; q < mems.size(); ++q) {
+      const int rc = addTransportOn(ri, mems[q]);
+      if (rc) return rc;
+    }
+    return 0;  // (no membrane between the two compartments: nothing happens)
+  }
+  int addTransportOn(reactionInfo* ri, GeometryInfo* mem) {
+    Reaction* r = ri->reaction;
     const int Xi = ref.Xindex, Yi = ref.Yindex, Zi = ref.Zindex;
     const int64_t N = (int64_t)Xi * Yi * Zi;
     struct Pt { int X, Y, Z; int64_t index; };
@@ -203,7 +234,16 @@ struct Bridge {
       d.kind = SB2_TOK_NOP; d.op = 0; d.slot = 0;
       if (rp->varList && rp->varList[i]) {
         variableInfo* v = ownerOfValue(rp->varList[i]);
-        if (v && rp->deltaList && rp->deltaList[i] && speciesId.count(v)) {
+        if (v && rp->deltaList && rp->deltaList[i] && memSpeciesId.count(v)) {
+          // a symbol that lives on a membrane is read at the point itself (calcPDE.cpp:1214-1217)
+          for (size_t j = 0; j < ri->spRefList.size(); ++j)
+            if (ri->spRefList[j] == v) { symbol = ri->spRefList[j]; break; }
+          d.kind = SB2_TOK_MEMVAR; d.slot = (uint16_t)memSpeciesId[v];
+          for (int p = 0; p < npts; ++p) {
+            operandCells.push_back(storageOf(v->geoi, pts[p].index));
+            operandCells.push_back(-1);
+          }
+        } else if (v && rp->deltaList && rp->deltaList[i] && speciesId.count(v)) {
           for (size_t j = 0; j < ri->spRefList.size(); ++j)
             if (ri->spRefList[j] == v) { symbol = ri->spRefList[j]; break; }
           if (!symbol || !symbol->geoi) { fprintf(stderr, "ref_bridge: transport operand without geometry\n"); return 2; }
@@ -252,13 +292,19 @@ struct Bridge {
     for (size_t k = 0; k < ri->spRefList.size(); ++k) {
       variableInfo* v = ri->spRefList[k];
       const bool ok = v && !v->isUniform && speciesId.count(v) && v->geoi && v->geoi->isVol;
+      const bool onMem = v && !v->isUniform && memSpeciesId.count(v) && v->geoi && !v->geoi->isVol;
       sb2_ref rr;
-      rr.species = ok ? speciesId[v] : -1;
+      rr.species = ok ? speciesId[v] : onMem ? SB2_MEM_SPECIES + memSpeciesId[v] : -1;
       rr.is_variable = ri->isVariable[k] ? 1 : 0;
       rr.stoichiometry = ri->srStoichiometry[k];
       refs.push_back(rr);
       for (int p = 0; p < npts; ++p) {
         const int a = dpts[p].axis, dx = a == 0, dy = a == 1, dz = a == 2;
+        if (onMem) {  // binding: the species' own membrane holds this point (isDomain[index] == 1, calcPDE.cpp:1405-1407)
+          targets.push_back(v->geoi->isDomain[pts[p].index] == 1 ? storageOf(v->geoi, pts[p].index) : -1);
+          targets.push_back(-1);
+          continue;
+        }
         targets.push_back(ok ? cellIn(v->geoi, pts[p].X + dx, pts[p].Y + dy, pts[p].Z + dz) : -1);
         targets.push_back(ok ? cellIn(v->geoi, pts[p].X - dx, pts[p].Y - dy, pts[p].Z - dz) : -1);
       }
@@ -269,10 +315,193 @@ struct Bridge {
     return 0;
   }
 
+  // Point set of a membrane that hosts species, with the pseudo-membrane fill pairs (spatialsimulator.cpp:1609-1663)
+  int ensurePointSet(GeometryInfo* g) {
+    if (pointSets.count(g)) return 0;
+    PointSet ps;
+    for (size_t k = 0; k < g->domainIndex.size(); ++k) ps.storage.push_back(g->domainIndex[k]);
+    for (size_t k = 0; k < g->pseudoMemIndex.size(); ++k) ps.storage.push_back(g->pseudoMemIndex[k]);
+    std::sort(ps.storage.begin(), ps.storage.end());
+    ps.storage.erase(std::unique(ps.storage.begin(), ps.storage.end()), ps.storage.end());
+    for (size_t k = 0; k < ps.storage.size(); ++k) ps.at[ps.storage[k]] = (int)k;
+    ps.id = sb2_add_point_set(dev, (int)ps.storage.size());
+    if (ps.id < 0) { fprintf(stderr, "ref_bridge: sb2_add_point_set: %s\n", sb2_last_error(dev)); return 2; }
+    pointSets[g] = ps;
+    const int64_t Xi = ref.Xindex, Yi = ref.Yindex, total = Xi * Yi * ref.Zindex;
+    std::vector<int32_t> t, a, b;
+    for (size_t q = 0; q < g->pseudoMemIndex.size(); ++q) {
+      const int64_t idx = g->pseudoMemIndex[q];
+      const int64_t n[6] = {idx + 1, idx - 1, idx + Xi, idx - Xi, idx + Xi * Yi, idx - Xi * Yi};  // Xp Xm Yp Ym Zp Zm
+      bool is1[6];
+      for (int k = 0; k < 6; ++k) is1[k] = n[k] >= 0 && n[k] < total && g->isDomain[n[k]] == 1;
+      if (ref.dimension != 3) is1[4] = is1[5] = false;
+      static const int order[15][2] = {{0, 1}, {2, 3}, {4, 5}, {0, 2}, {0, 3}, {0, 4}, {0, 5}, {1, 2}, {1, 3}, {1, 4}, {1, 5}, {2, 4}, {2, 5}, {3, 4}, {3, 5}};
+      for (int c = 0; c < 15; ++c) {
+        if (!(is1[order[c][0]] && is1[order[c][1]])) continue;
+        const int st = storageOf(g, idx), sa = storageOf(g, n[order[c][0]]), sb = storageOf(g, n[order[c][1]]);
+        if (st >= 0 && sa >= 0 && sb >= 0) { t.push_back(st); a.push_back(sa); b.push_back(sb); }
+        break;
+      }
+    }
+    DEV(sb2_set_mem_fill(dev, ps.id, t.data(), a.data(), b.data(), (int)t.size()));
+    return 0;
+  }
+  // A species on a membrane: values at the storage points, the points updateSpecies advances, calcMemDiffusion's terms from the
+  // reference's voronoiInfo table (calcPDE.cpp:1484-1581)
+  int addMemSpecies(variableInfo* v) {
+    GeometryInfo* g = v->geoi;
+    int rc = ensurePointSet(g);
+    if (rc) return rc;
+    const PointSet& ps = pointSets[g];
+    std::vector<double> init(ps.storage.size() ? ps.storage.size() : 1);
+    for (size_t k = 0; k < ps.storage.size(); ++k) init[k] = v->value[ps.storage[k]];
+    const int id = sb2_add_mem_species(dev, ps.id, init.data());
+    if (id < 0) { fprintf(stderr, "ref_bridge: sb2_add_mem_species: %s\n", sb2_last_error(dev)); return 2; }
+    memSpeciesId[v] = id;
+    std::vector<int32_t> upd;
+    for (size_t q = 0; q < g->domainIndex.size(); ++q) upd.push_back(storageOf(g, g->domainIndex[q]));
+    DEV(sb2_set_mem_update_points(dev, id, upd.data(), (int)upd.size()));
+    if (!v->diffCInfo || !v->diffCInfo[0] || !ref.vorI) return 0;  // calcMemDiffusion reads diffCInfo[0] only
+    variableInfo* dc = v->diffCInfo[0];
+    std::vector<int32_t> start(1, 0), adj;
+    std::vector<double> sij, dij, area, dvals;
+    for (size_t q = 0; q < g->domainIndex.size(); ++q) {
+      const int64_t idx = g->domainIndex[q];
+      const voronoiInfo& vor = ref.vorI[idx];
+      double ar = 0.0;
+      for (int j = 0; j < 2; ++j) {
+        ar += vor.diXY[j] * vor.siXY[j];
+        ar += vor.diYZ[j] * vor.siYZ[j];
+        ar += vor.diXZ[j] * vor.siXZ[j];
+      }
+      if (ref.dimension == 2) ar /= 2.0;
+      else if (ref.dimension == 3) ar /= 4.0;
+      area.push_back(ar);
+      if (!dc->isUniform) dvals.push_back(dc->value[idx]);
+      const boundaryType& bt = g->bType[idx];
+      const bool bx = bt.isBofXp && bt.isBofXm, by = bt.isBofYp && bt.isBofYm, bz = bt.isBofZp && bt.isBofZm;
+      const bool plane[3] = {bx || by, ref.dimension == 3 && (by || bz), ref.dimension == 3 && (bx || bz)};
+      const int* adjOf[3] = {vor.adjacentIndexXY, vor.adjacentIndexYZ, vor.adjacentIndexXZ};
+      const double* sOf[3] = {vor.siXY, vor.siYZ, vor.siXZ};
+      const double* dOf[3] = {vor.diXY, vor.diYZ, vor.diXZ};
+      for (int pl = 0; pl < 3; ++pl) {
+        if (!plane[pl]) continue;
+        for (int j = 0; j < 2; ++j) {
+          const int a = adjOf[pl][j] >= 0 ? storageOf(g, adjOf[pl][j]) : -1;
+          if (a < 0) continue;  // no neighbour found on this side (the reference would read outside its array)
+          adj.push_back(a); sij.push_back(sOf[pl][j]); dij.push_back(dOf[pl][j]);
+        }
+      }
+      start.push_back((int32_t)adj.size());
+    }
+    const int kind = dc->isUniform ? SB2_SRC_CONST : SB2_SRC_FIELD;
+    const int src = dc->isUniform ? slotOf(dc->value) : 0;
+    DEV(sb2_set_mem_diffusion(dev, id, kind, src, dvals.empty() ? NULL : dvals.data(), upd.data(), (int)upd.size(), start.data(), adj.data(),
+                              sij.data(), dij.data(), area.data()));
+    return 0;
+  }
+  // A reaction (kind 0) or rate rule (kind 1) evaluated over a membrane's domainIndex (reversePolishRK, calcPDE.cpp:224-451)
+  int addMemReaction(reactionInfo* ri, GeometryInfo* g, int kind) {
+    if (!pointSets.count(g)) return 0;  // no variable species lives on this membrane: nothing can change
+    reversePolishInfo* rp = ri->rpInfo;
+    std::vector<int32_t> pts;
+    for (size_t q = 0; q < g->domainIndex.size(); ++q) pts.push_back(storageOf(g, g->domainIndex[q]));
+    std::vector<sb2_token> toks;
+    std::vector<double> values;
+    for (int i = 0; i < rp->listNum; ++i) {
+      sb2_token d;
+      d.kind = SB2_TOK_NOP; d.op = 0; d.slot = 0;
+      if (rp->varList && rp->varList[i]) {
+        variableInfo* v = ownerOfValue(rp->varList[i]);
+        if (v && rp->deltaList && rp->deltaList[i] && memSpeciesId.count(v) && v->geoi == g) { d.kind = SB2_TOK_MEMVAR; d.slot = (uint16_t)memSpeciesId[v]; }
+        else if (v) {  // anything else keeps, at a membrane point, the value it was set up with
+          d.kind = SB2_TOK_FIELD;
+          for (size_t q = 0; q < g->domainIndex.size(); ++q) values.push_back(v->value[g->domainIndex[q]]);
+        }
+      } else if (rp->constList && rp->constList[i]) {
+        d.kind = SB2_TOK_CONST; d.slot = (uint16_t)slotOf(rp->constList[i]);
+        if (rp->constList[i] == &ref.sim_time) timeSlot = d.slot;
+      } else if (rp->opfuncList && rp->opfuncList[i] != 0) {
+        d.kind = SB2_TOK_OP; d.op = (uint8_t)opOfAst(rp->opfuncList[i]);
+      }
+      toks.push_back(d);
+    }
+    std::vector<sb2_ref> refs;
+    for (size_t k = 0; k < ri->spRefList.size(); ++k) {
+      variableInfo* v = ri->spRefList[k];
+      sb2_ref rr;
+      rr.species = (v && !v->isUniform && memSpeciesId.count(v) && v->geoi == g) ? SB2_MEM_SPECIES + memSpeciesId[v] : -1;
+      rr.is_variable = ri->isVariable[k] ? 1 : 0;
+      rr.stoichiometry = ri->srStoichiometry[k];
+      refs.push_back(rr);
+    }
+    DEV(sb2_add_mem_reaction(dev, pointSets[g].id, kind, toks.data(), (int)toks.size(), refs.data(), (int)refs.size(),
+                             kind == 0 ? (int)ri->reaction->getNumReactants() : 1, pts.data(), (int)pts.size(), values.empty() ? NULL : values.data()));
+    return 0;
+  }
+  // Assignment rules, re-evaluated after every step in the reference's order (updateAssignmentRules, spatialsimulator.cpp:1566-1581):
+  // a rule on a species writes the cells of its compartment's volume, a rule on a parameter every cell
+  int addAssignmentRules() {
+    for (size_t i = 0; i < ref.orderedARule.size(); ++i) {
+      variableInfo* info = ref.orderedARule[i];
+      reversePolishInfo* rp = info->rpInfo;
+      if (!rp) continue;
+      int geo = -1;
+      if (info->sp) {
+        GeometryInfo* g = searchAvolInfoByCompartment(ref.geoInfoList, info->sp->getCompartment().c_str());
+        if (!g || !g->isVol) { fprintf(stderr, "ref_bridge: assignment rule on a membrane species is outside the bridge's scope\n"); return 3; }
+        if (!geoId.count(g)) {
+          const int rc = addGeometry(g);
+          if (rc) return rc;
+        }
+        geo = geoId[g];
+      }
+      std::vector<sb2_token> toks((size_t)rp->listNum);
+      for (int k = 0; k < rp->listNum; ++k) {
+        sb2_token t;
+        t.kind = SB2_TOK_NOP; t.op = 0; t.slot = 0;
+        if (rp->varList && rp->varList[k]) {
+          variableInfo* v = ownerOfValue(rp->varList[k]);
+          if (v && memSpeciesId.count(v)) { fprintf(stderr, "ref_bridge: membrane species in an assignment rule\n"); return 3; }
+          if (v && speciesId.count(v)) { t.kind = SB2_TOK_VAR; t.slot = (uint16_t)speciesId[v]; }
+          else if (v) { const int f = fieldOf(v); if (f < 0) return 2; t.kind = SB2_TOK_FIELD; t.slot = (uint16_t)f; }
+        } else if (rp->constList && rp->constList[k]) {
+          t.kind = SB2_TOK_CONST; t.slot = (uint16_t)slotOf(rp->constList[k]);
+          if (rp->constList[k] == &ref.sim_time) timeSlot = t.slot;
+        } else if (rp->opfuncList && rp->opfuncList[k] != 0) {
+          t.kind = SB2_TOK_OP; t.op = (uint8_t)opOfAst(rp->opfuncList[k]);
+        }
+        toks[k] = t;
+      }
+      int kind, target;
+      if (speciesId.count(info)) { kind = 1; target = speciesId[info]; }
+      else { kind = 0; target = fieldOf(info); if (target < 0) return 2; ruleFields.push_back(info); }
+      DEV(sb2_add_assignment_rule(dev, kind, target, geo, toks.data(), (int)toks.size()));
+    }
+    return 0;
+  }
+  std::vector<variableInfo*> ruleFields;  // variables without a time derivative that a rule rewrites every step (compared too)
+
+  int addGeometry(GeometryInfo* geo) {
+    std::vector<uint8_t> f((size_t)nx * ny * nz);
+    for (int k = 0; k < nz; ++k)
+      for (int j = 0; j < ny; ++j)
+        for (int i = 0; i < nx; ++i) {
+          const int64_t e = even(i, j, k);
+          const boundaryType& b = geo->bType[e];
+          f[((size_t)k * ny + j) * nx + i] = (uint8_t)((geo->isDomain[e] == 1 ? SB2_F_DOMAIN : 0) | (b.isBofXp ? SB2_F_XP : 0) | (b.isBofXm ? SB2_F_XM : 0) |
+                                                      (b.isBofYp ? SB2_F_YP : 0) | (b.isBofYm ? SB2_F_YM : 0) | (b.isBofZp ? SB2_F_ZP : 0) |
+                                                      (b.isBofZm ? SB2_F_ZM : 0));
+        }
+    const int id = sb2_add_geometry(dev, f.data());
+    if (id < 0) { fprintf(stderr, "ref_bridge: sb2_add_geometry: %s\n", sb2_last_error(dev)); return 2; }
+    geoId[geo] = id;
+    return 0;
+  }
+
   int build(int device) {
     nx = ref.Xdiv; ny = ref.Ydiv; nz = ref.Zdiv;
     if (ref.dimension < 2) { fprintf(stderr, "ref_bridge: 2-D and 3-D models only\n"); return 3; }
-    if (!ref.orderedARule.empty()) { fprintf(stderr, "ref_bridge: assignment rules are outside the bridge's scope\n"); return 3; }
     sb2_grid g;
     memset(&g, 0, sizeof(g));
     g.nx = nx; g.ny = ny; g.nz = nz; g.dim = (int)ref.dimension;
@@ -287,25 +516,18 @@ struct Bridge {
       for (size_t i = 0; i < ref.varInfoList.size(); ++i)
         hosts = hosts || (ref.varInfoList[i]->geoi == geo && ref.varInfoList[i]->sp && !ref.varInfoList[i]->isUniform && ref.varInfoList[i]->delta);
       if (!hosts) continue;
-      std::vector<uint8_t> f((size_t)nx * ny * nz);
-      for (int k = 0; k < nz; ++k)
-        for (int j = 0; j < ny; ++j)
-          for (int i = 0; i < nx; ++i) {
-            const int64_t e = even(i, j, k);
-            const boundaryType& b = geo->bType[e];
-            f[((size_t)k * ny + j) * nx + i] = (uint8_t)((geo->isDomain[e] == 1 ? SB2_F_DOMAIN : 0) | (b.isBofXp ? SB2_F_XP : 0) | (b.isBofXm ? SB2_F_XM : 0) |
-                                                        (b.isBofYp ? SB2_F_YP : 0) | (b.isBofYm ? SB2_F_YM : 0) | (b.isBofZp ? SB2_F_ZP : 0) |
-                                                        (b.isBofZm ? SB2_F_ZM : 0));
-          }
-      const int id = sb2_add_geometry(dev, f.data());
-      if (id < 0) { fprintf(stderr, "ref_bridge: sb2_add_geometry: %s\n", sb2_last_error(dev)); return 2; }
-      geoId[geo] = id;
+      const int rcg = addGeometry(geo);
+      if (rcg) return rcg;
     }
     // species with a time derivative: value[] + delta[4N] (setInfoFunction.cpp:121-126)
     for (size_t i = 0; i < ref.varInfoList.size(); ++i) {
       variableInfo* v = ref.varInfoList[i];
       if (!v->sp || v->isUniform || !v->delta) continue;
-      if (!v->inVol) { fprintf(stderr, "ref_bridge: species on membranes are outside the bridge's scope\n"); return 3; }
+      if (v->geoi && !v->geoi->isVol) {  // a species on a membrane
+        const int rcm = addMemSpecies(v);
+        if (rcm) return rcm;
+        continue;
+      }
       if (!v->geoi || !geoId.count(v->geoi)) { fprintf(stderr, "ref_bridge: species %s has no volume geometry\n", v->id); return 2; }
       const std::vector<double> c = compact(v->value);
       const int id = sb2_add_species(dev, geoId[v->geoi], c.data());
@@ -348,8 +570,13 @@ struct Bridge {
         refs.push_back(rr);
         if (!geo && v && v->geoi) geo = v->geoi;  // "first non-null geometry", spatialsimulator.cpp:1381-1390
       }
-      if (!geo || !geoId.count(geo)) continue;  // every participant uniform: the reference changes nothing
       const bool isRule = ri->reaction == NULL;
+      if (geo && !geo->isVol) {  // a reaction between species of one membrane
+        const int rcm = addMemReaction(ri, geo, isRule ? 1 : 0);
+        if (rcm) return rcm;
+        continue;
+      }
+      if (!geo || !geoId.count(geo)) continue;  // every participant uniform: the reference changes nothing
       const int nReact = isRule ? 0 : (int)ri->reaction->getNumReactants();
       DEV(sb2_add_reaction(dev, geoId[geo], isRule ? 1 : 0, toks.data(), (int)toks.size(), refs.data(), (int)refs.size(), nReact));
     }
@@ -393,6 +620,8 @@ struct Bridge {
         DEV(sb2_set_boundary(dev, it->second, side, bk, kind, src));
       }
     }
+    const int rcr = addAssignmentRules();
+    if (rcr) return rcr;
     std::vector<double> table(constAddr.size() ? constAddr.size() : 1, 0.0);
     for (size_t i = 0; i < constAddr.size(); ++i) table[i] = *constAddr[i];
     DEV(sb2_set_constants(dev, table.data(), (int)table.size()));
@@ -409,7 +638,23 @@ struct Bridge {
   }
 };
 
+static void onCrash(int sig) {  // REF_BRIDGE_VERBOSE: where a crash happened, then the default action
+  void* frames[48];
+  const int n = backtrace(frames, 48);
+  const char msg[] = "ref_bridge: fatal signal, backtrace:\n";
+  if (write(2, msg, sizeof(msg) - 1) < 0) {}
+  backtrace_symbols_fd(frames, n, 2);
+  signal(sig, SIG_DFL);
+  raise(sig);
+}
+
 int main(int argc, char** argv) {
+  if (getenv("REF_BRIDGE_VERBOSE")) { signal(SIGSEGV, onCrash); signal(SIGABRT, onCrash); }
+  // The reference's set-up reads isDomain[] of a membrane's neighbours without bounds tests (one row / plane past either end of the
+  // array at points on the frame, spatialsimulator.cpp:719-1038).  With large arrays in mappings of their own those reads can fault;
+  // kept on the ordinary heap they land in neighbouring allocations, as they do in the reference's own executables.
+  mallopt(M_MMAP_THRESHOLD, 1 << 30);
+  mallopt(M_TOP_PAD, 64 << 20);
   if (argc < 7) { fprintf(stderr, "usage: ref_bridge <model.xml> <xdim> <ydim> <zdim> <dt> <steps>\n"); return 64; }
   const int xd = atoi(argv[2]), yd = atoi(argv[3]), zd = atoi(argv[4]);
   const double dt = atof(argv[5]);
@@ -420,14 +665,21 @@ int main(int argc, char** argv) {
   host.initFromFile(argv[1], xd, yd, zd);
   cpu.initFromFile(argv[1], xd, yd, zd);
   Bridge b(host);
+  const bool verbose = getenv("REF_BRIDGE_VERBOSE") != NULL;  // per step and variable: the error, to stderr
+  if (verbose) fprintf(stderr, "reference set-up done (twice)\n");
   int rc = b.build(0);
   if (rc) return rc;
+  if (verbose) fprintf(stderr, "device model built\n");
   double worst = 0.0;
   bool identical = true;
+  std::string worstVar = "-";
+  int firstBad = -1;
   std::vector<double> got((size_t)b.nx * b.ny * b.nz);
   for (int t = 0; t < steps; ++t) {
     cpu.oneStep(t, dt);
+    if (verbose) fprintf(stderr, "step %d: reference stepped\n", t);
     if ((rc = b.step(t, dt))) return rc;
+    if (verbose) fprintf(stderr, "step %d: device stepped\n", t);
     for (std::map<variableInfo*, int>::iterator it = b.speciesId.begin(); it != b.speciesId.end(); ++it) {
       if (sb2_download_species(b.dev, it->second, got.data()) < 0) { fprintf(stderr, "ref_bridge: download failed\n"); return 2; }
       int len = 0;
@@ -441,12 +693,54 @@ int main(int argc, char** argv) {
             if (fabs(g - w) > err) err = fabs(g - w);
             if (memcmp(&w, &g, sizeof(double)) != 0 && !(w == 0.0 && g == 0.0)) identical = false;
           }
-      if (err / scale > worst) worst = err / scale;
+      if (err / scale > worst) { worst = err / scale; worstVar = it->first->id; }
+      if (err / scale > 1e-10 && firstBad < 0) firstBad = t;
+      if (verbose) fprintf(stderr, "step %d %s rel %.3e\n", t, it->first->id, err / scale);
+    }
+    // species on membranes: every storage point (membrane and pseudo-membrane points)
+    for (std::map<variableInfo*, int>::iterator it = b.memSpeciesId.begin(); it != b.memSpeciesId.end(); ++it) {
+      const Bridge::PointSet& ps = b.pointSets[it->first->geoi];
+      std::vector<double> mg(ps.storage.size() ? ps.storage.size() : 1);
+      if (sb2_download_mem_species(b.dev, it->second, mg.data()) < 0) { fprintf(stderr, "ref_bridge: download failed\n"); return 2; }
+      int len = 0;
+      const double* want = cpu.getVariable(it->first->id, len);
+      double scale = 1e-300, err = 0.0;
+      for (size_t k = 0; k < ps.storage.size(); ++k) {
+        const double w = want[ps.storage[k]], g = mg[k];
+        if (fabs(w) > scale) scale = fabs(w);
+        if (fabs(g - w) > err) err = fabs(g - w);
+        if (memcmp(&w, &g, sizeof(double)) != 0 && !(w == 0.0 && g == 0.0)) identical = false;
+      }
+      if (err / scale > worst) { worst = err / scale; worstVar = it->first->id; }
+      if (err / scale > 1e-10 && firstBad < 0) firstBad = t;
+      if (verbose) fprintf(stderr, "step %d %s rel %.3e\n", t, it->first->id, err / scale);
+    }
+    // variables an assignment rule rewrites every step, at the volume cells
+    for (size_t r = 0; r < b.ruleFields.size(); ++r) {
+      variableInfo* v = b.ruleFields[r];
+      if (sb2_download_field(b.dev, b.fieldId[v], got.data()) < 0) { fprintf(stderr, "ref_bridge: download failed\n"); return 2; }
+      int len = 0;
+      const double* want = cpu.getVariable(v->id, len);
+      if (!want) continue;
+      GeometryInfo* g = v->sp ? searchAvolInfoByCompartment(host.geoInfoList, v->sp->getCompartment().c_str()) : NULL;
+      double scale = 1e-300, err = 0.0;
+      for (int k = 0; k < b.nz; ++k)
+        for (int j = 0; j < b.ny; ++j)
+          for (int i = 0; i < b.nx; ++i) {
+            if (g && g->isDomain[b.even(i, j, k)] != 1) continue;
+            const double w = want[b.even(i, j, k)], gg = got[((size_t)k * b.ny + j) * b.nx + i];
+            if (fabs(w) > scale) scale = fabs(w);
+            if (fabs(gg - w) > err) err = fabs(gg - w);
+            if (memcmp(&w, &gg, sizeof(double)) != 0 && !(w == 0.0 && gg == 0.0)) identical = false;
+          }
+      if (err / scale > worst) { worst = err / scale; worstVar = v->id; }
+      if (err / scale > 1e-10 && firstBad < 0) firstBad = t;
+      if (verbose) fprintf(stderr, "step %d %s rel %.3e\n", t, v->id, err / scale);
     }
   }
   printf("{\"bridge\": \"reference host set-up -> sb2_* C ABI -> GPU step\", \"model\": \"%s\", \"dims\": [%d, %d, %d], \"steps\": %d, "
-         "\"species\": %d, \"constants\": %d, \"launches\": %lld, \"rel_linf_vs_reference_cpu\": %.3e, \"bit_identical\": %s}\n",
-         argv[1], b.nx, b.ny, b.nz, steps, (int)b.speciesId.size(), (int)b.constAddr.size(), (long long)sb2_launch_count(b.dev), worst,
+         "\"species\": %d, \"membrane_species\": %d, \"rule_fields\": %d, \"constants\": %d, \"launches\": %lld, \"rel_linf_vs_reference_cpu\": %.3e, \"worst_variable\": \"%s\", \"first_step_over_1e-10\": %d, \"bit_identical\": %s}\n",
+         argv[1], b.nx, b.ny, b.nz, steps, (int)b.speciesId.size(), (int)b.memSpeciesId.size(), (int)b.ruleFields.size(), (int)b.constAddr.size(), (long long)sb2_launch_count(b.dev), worst, worstVar.c_str(), firstBad,
          identical ? "true" : "false");
   sb2_destroy(b.dev);
   return worst <= 1e-10 ? 0 : 1;

@@ -330,7 +330,10 @@ def test_the_references_own_cli_runs_on_the_library():
 
 @pytest.mark.parametrize("case", ["turing_tiny", "brusselator", "fish", "fish_dirichlet", "turing_tiny_flux", "syn_turing_3d_flux",
                                   "syn_raterules_2d", "syn_fieldcoeff_3d", "syn_chain6_2d", "advection", "syn_advection_field_2d",
-                                  "syn_advection_uniform_3d", "transport", "transport_rate", "syn_transport_mixed_2d", "syn_sampled_2d"])
+                                  "syn_advection_uniform_3d", "transport", "transport_rate", "syn_transport_mixed_2d", "syn_sampled_2d",
+                                  # species on membranes (point sets, Voronoi terms, binding, pseudo-membrane fill), assignment rules
+                                  "syn_membrane_2d", "syn_membrane_box_2d", "syn_membrane_3d", "syn_membrane_mixed_2d", "syn_rules_2d",
+                                  "syn_rules_3d"])
 def test_reference_host_setup_on_the_device_abi(case):
     """INTEGRATION.md §A for real (oracle/ref_bridge.cpp): the reference's OWN host code sets the model up, its structs are
     flattened onto the sb2_* C ABI, the GPU steps - and the fields equal those of the reference's own CPU step after every step."""
@@ -347,8 +350,12 @@ def test_reference_host_setup_on_the_device_abi(case):
     assert res["rel_linf_vs_reference_cpu"] <= 1e-10 and res["launches"] >= 40
     # bit for bit, except laws with transcendental operators and a species with an ordinary reaction listed BEFORE its transport
     # (the library accumulates transports first): 1e-10
-    if case not in ("syn_raterules_2d", "syn_transport_mixed_2d", "syn_sampled_2d"):
+    if case not in ("syn_raterules_2d", "syn_transport_mixed_2d", "syn_sampled_2d", "syn_membrane_mixed_2d", "syn_rules_2d", "syn_rules_3d"):
         assert res["bit_identical"]
+    if case.startswith("syn_membrane"):
+        assert res["membrane_species"] == 2
+    if case.startswith("syn_rules"):
+        assert res["rule_fields"] >= 1
 
 
 def test_host_step_falls_back_for_unfused_models():
