@@ -661,7 +661,10 @@ int main(int argc, char** argv) {
   const int steps = atoi(argv[6]);
   // two identical simulators of the reference: `host` is set up by the reference and stepped on the GPU through the bridge,
   // `cpu` is the reference stepping itself
-  SpatialSimulator host, cpu;
+  // (static: zero-initialised before their constructors run.  The reference's constructor leaves sim_time unset and initFromFile
+  // evaluates the assignment rules with it - `time` in a rule reads whatever the object's storage held; on the stack that differed
+  // between the two objects and with the process environment)
+  static SpatialSimulator host, cpu;
   host.initFromFile(argv[1], xd, yd, zd);
   cpu.initFromFile(argv[1], xd, yd, zd);
   Bridge b(host);

@@ -86,7 +86,7 @@ static int doDump(int argc, char** argv) {
   if (!g_out) { perror("open out"); return 1; }
   fwrite("SBD1", 1, 4, g_out);
 
-  SpatialSimulator sim;
+  static SpatialSimulator sim;  // zero-initialised storage: the reference's constructor leaves sim_time unset, and rules read it at set-up
   sim.initFromFile(file, xd, yd, zd);
   int N = sim.numOfVolIndexes;
 
@@ -183,7 +183,7 @@ static int doTime(int argc, char** argv) {
   double dt = atof(argv[6]);
   int warm = atoi(argv[7]), steps = atoi(argv[8]);
   auto t0 = std::chrono::steady_clock::now();
-  SpatialSimulator sim;
+  static SpatialSimulator sim;  // zero-initialised storage: the reference's constructor leaves sim_time unset, and rules read it at set-up
   sim.initFromFile(file, xd, yd, zd);
   auto t1 = std::chrono::steady_clock::now();
   int t = 0;
@@ -216,7 +216,7 @@ double checkAdvectionStab(variableInfo* sInfo, double deltaX, double deltaY, dou
 double checkMemDiffusionStab(variableInfo* sInfo, voronoiInfo* vorI, int Xindex, int Yindex, double dt, double dimension);
 static int doStab(int argc, char** argv) {
   if (argc < 7) return 2;
-  SpatialSimulator sim;
+  static SpatialSimulator sim;  // zero-initialised storage: the reference's constructor leaves sim_time unset, and rules read it at set-up
   sim.initFromFile(argv[2], atoi(argv[3]), atoi(argv[4]), atoi(argv[5]));
   printf("{");
   for (int a = 6; a < argc; ++a) {

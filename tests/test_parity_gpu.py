@@ -332,12 +332,8 @@ def test_the_references_own_cli_runs_on_the_library():
                                   "syn_raterules_2d", "syn_fieldcoeff_3d", "syn_chain6_2d", "advection", "syn_advection_field_2d",
                                   "syn_advection_uniform_3d", "transport", "transport_rate", "syn_transport_mixed_2d", "syn_sampled_2d",
                                   # species on membranes (point sets, Voronoi terms, binding, pseudo-membrane fill), assignment rules
-                                  "syn_membrane_2d", "syn_membrane_box_2d", "syn_membrane_3d", "syn_membrane_mixed_2d", "syn_rules_3d",
-                                  # OPEN: run on its own (tools/bridge_repeat.sh, tools/bridge_probe.py: 20 of 20 runs) this case is
-                                  # within 2.5e-16 of the reference's CPU step at every step, but inside two multi-test pytest runs
-                                  # it came out 6.9e-4 off; the cause was not found before the GPU budget of the round ran out (the
-                                  # library's own host path passes the same model's golden in every full run).  Not strict.
-                                  pytest.param("syn_rules_2d", marks=pytest.mark.xfail(strict=False, reason="differs in multi-test runs; cause open"))])
+                                  "syn_membrane_2d", "syn_membrane_box_2d", "syn_membrane_3d", "syn_membrane_mixed_2d", "syn_rules_2d",
+                                  "syn_rules_3d"])
 def test_reference_host_setup_on_the_device_abi(case):
     """INTEGRATION.md §A for real (oracle/ref_bridge.cpp): the reference's OWN host code sets the model up, its structs are
     flattened onto the sb2_* C ABI, the GPU steps - and the fields equal those of the reference's own CPU step after every step."""
